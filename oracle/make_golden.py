@@ -1,0 +1,234 @@
+"""TEST INFRASTRUCTURE ONLY - generates tests/golden/*.npz by running the REFERENCE's own
+functions (loaded from /root/reference by oracle/ref_extract.py) on seeded synthetic inputs.
+
+Run once in the build container:  python -m oracle.make_golden
+The fixtures are committed; the GPU box never needs the reference tree.
+Input recipe follows SURVEY.md section 8c ("Golden vectors"): unit quats, |vel|<=3,
+dof in +-1 rad, progress in [0,167], contact forces N(0,30).
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from . import ref_extract
+from .oracle_np import (AMP_STEP_DIM, AMP_STEPS, CONTACT_BODIES, CONTROL_DT, DOF_SUBSET, EPISODE_LEN, HEAD,
+                        KEY_BODIES, NB, ND, NUM_TRAJ_SAMPLES, NUM_VERTS, TRAJ_SAMPLE_DT, center_height_points,
+                        square_height_points, traj_dt)
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def synth_state(N, seed, map_shape=(1080, 1080), rough=True):
+    """Seeded random-but-valid env state; also used (same code) by the GPU parity tests."""
+    rng = np.random.default_rng(seed)
+    f = np.float32
+    root_xy = rng.uniform(50.0, 58.0, (N, 2))
+    body_pos = rng.normal(0, 0.4, (N, NB, 3))
+    body_pos[:, 0] = 0
+    body_pos[..., 2] += 0.9
+    body_pos[..., :2] += root_xy[:, None]
+    q = rng.normal(0, 1, (N, NB, 4)); q /= np.linalg.norm(q, axis=-1, keepdims=True)
+    # roots mostly upright with random heading so that the heading frame is well conditioned
+    yaw = rng.uniform(-np.pi, np.pi, N)
+    tilt = rng.normal(0, 0.15, (N, 3))
+    qr = np.stack([tilt[:, 0], tilt[:, 1], np.sin(yaw / 2) + 0 * tilt[:, 2], np.cos(yaw / 2)], -1)
+    qr /= np.linalg.norm(qr, axis=-1, keepdims=True)
+    q[:, 0] = qr
+    body_vel = rng.uniform(-3, 3, (N, NB, 3))
+    body_ang = rng.uniform(-3, 3, (N, NB, 3))
+    rb = np.concatenate([body_pos, q, body_vel, body_ang], -1).astype(f)
+    dof_pos = rng.uniform(-1, 1, (N, ND))
+    dof_pos[: max(1, N // 8), :6] = 0.0          # exercise the |angle|<1e-5 default-axis branch
+    dof_vel = rng.uniform(-3, 3, (N, ND))
+    dof_state = np.stack([dof_pos, dof_vel], -1).astype(f)
+    contact = rng.normal(0, 30, (N, NB, 3)).astype(f)
+    dof_force = rng.normal(0, 50, (N, ND)).astype(f)
+    progress = rng.integers(0, EPISODE_LEN, N).astype(np.int64)
+    progress[:4] = [0, 1, 166, 167][: min(4, N)]
+    betas = np.concatenate([rng.integers(0, 3, (N, 1)), rng.normal(0, 1, (N, 16))], -1).astype(f)
+    # JTA-shaped polyline: smooth walk starting near the root
+    speed = rng.uniform(0, 3, (N, 1)); head = rng.uniform(-np.pi, np.pi, (N, 1))
+    turn = rng.uniform(-0.5, 0.5, (N, 1))
+    t = np.arange(NUM_VERTS)[None] * traj_dt()
+    ang = head + turn * t
+    vx, vy = speed * np.cos(ang), speed * np.sin(ang)
+    verts = np.zeros((N, NUM_VERTS, 3))
+    verts[..., 0] = root_xy[:, :1] + np.cumsum(vx, 1) * traj_dt() + rng.normal(0, 0.3, (N, 1))
+    verts[..., 1] = root_xy[:, 1:] + np.cumsum(vy, 1) * traj_dt() + rng.normal(0, 0.3, (N, 1))
+    verts = verts.astype(f)
+    if rough:
+        # blocky random steps (4x4 cells) - low entropy so the committed fixture stays small
+        blk = rng.integers(-40, 40, ((map_shape[0] + 3) // 4, (map_shape[1] + 3) // 4))
+        hs = np.kron(blk, np.ones((4, 4), np.int64))[:map_shape[0], :map_shape[1]].astype(np.int16)
+    else:
+        hs = np.zeros(map_shape, np.int16)
+    amp_buf = rng.normal(0, 1, (N, AMP_STEPS, AMP_STEP_DIM)).astype(f)
+    return dict(rb=rb, dof_state=dof_state, contact=contact, dof_force=dof_force, progress=progress,
+                betas=betas, verts=verts, height_samples=hs, amp_buf=amp_buf)
+
+
+def reference_post_step(st):
+    """Drives the reference functions exactly as the task code does (call sites cited inline)."""
+    R = ref_extract.load()
+    torch = R.torch
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    N = st["rb"].shape[0]
+    rb = T(st["rb"])
+    bp, br, bv, bw = rb[..., 0:3], rb[..., 3:7], rb[..., 7:10], rb[..., 10:13]
+    ds = T(st["dof_state"]); dpos, dvel = ds[..., 0].contiguous(), ds[..., 1].contiguous()
+    betas = T(st["betas"]); limb = torch.zeros(N, 10)
+    progress = T(st["progress"])
+    # --- self obs: humanoid_pedestrain_terrain.py:240-268 (root_height_obs False)
+    so = R.jit.compute_humanoid_observations_smpl_max(bp.clone(), br, bv, bw, betas, limb, True, False, True, True, False)
+    # --- flip self obs: humanoid.py:1066-1108
+    fp, fr, fv, fw = bp.clone(), br.clone(), bv.clone(), bw.clone()
+    l2r = R.left_to_right_index
+    fp[..., 1] *= -1; fp = fp[..., l2r, :]
+    fr[..., 0] *= -1; fr[..., 2] *= -1; fr = fr[..., l2r, :]
+    fv[..., 1] *= -1; fv = fv[..., l2r, :]
+    fw[..., 0] *= -1; fw[..., 2] *= -1; fw = fw[..., l2r, :]
+    fso = R.jit.compute_humanoid_observations_smpl_max(fp, fr, fv, fw, betas, limb, True, False, True, True, False)
+    # --- traj generator holder (traj_generator.py:24-36, 256-272)
+    tg = R.meth.TrajHolder()
+    tg._verts = T(st["verts"]); tg._verts_flat = tg._verts.view(-1, 3)
+    tg._dt = (EPISODE_LEN * CONTROL_DT) / (NUM_VERTS - 1)
+    tg.get_num_verts = lambda: tg._verts.shape[1]
+    tg.get_num_segs = lambda: tg._verts.shape[1] - 1
+    tg.get_traj_duration = lambda: tg.get_num_verts() * tg._dt
+    env_ids = torch.arange(N, dtype=torch.long)
+    # --- _fetch_traj_samples: humanoid_traj.py:208-224
+    t0 = progress * CONTROL_DT
+    ts = torch.arange(NUM_TRAJ_SAMPLES, dtype=torch.float) * TRAJ_SAMPLE_DT
+    tt = t0.unsqueeze(-1) + ts
+    ids = torch.broadcast_to(env_ids.unsqueeze(-1), tt.shape)
+    samples = tg.calc_pos(ids.flatten(), tt.flatten()).reshape(N, NUM_TRAJ_SAMPLES, 3)
+    root_states = torch.cat([bp[:, 0], br[:, 0], bv[:, 0], bw[:, 0]], -1)
+    loc = R.jit.compute_location_observations(root_states, samples, True)
+    # --- heights: humanoid_pedestrain_terrain.py:761-815, 732-759, 1212-1288
+    ter = R.meth.TerrainHolder()
+    ter.heightsamples = T(st["height_samples"]); ter.horizontal_scale = 0.1; ter.vertical_scale = 0.005
+    grid = T(square_height_points())[None].repeat(N, 1, 1)
+    grid9 = T(center_height_points())[None].repeat(N, 1, 1)
+    head = torch.cat([bp[:, HEAD], br[:, HEAD]], 1)
+    hq = R.ptu.calc_heading_quat(head[:, 3:7])
+    pts = R.itu.quat_apply(hq.repeat(1, grid.shape[1]).reshape(-1, 4), grid) + head[:, :3].unsqueeze(1)
+    meas = ter.sample_height_points(pts.clone()).view(N, -1)
+    base_quat = root_states[:, 3:7]
+    pts9 = R.jit.quat_apply_yaw(base_quat.repeat(1, 9), grid9) + root_states[:, :3].unsqueeze(1)
+    ch = ter.sample_height_points(pts9.clone()).view(N, -1).mean(dim=-1, keepdim=True)
+    heights = torch.clip(ch - meas, -3, 3.) * 5
+    tobs = torch.cat([loc, heights], dim=1)
+    # --- flip task obs: humanoid_pedestrain_terrain.py:455-491
+    nt = tobs.clone()
+    tr = nt[:, :30].view(N, 15, 2); tr[..., 1] *= -1
+    hsamp = nt[..., 30:30 + 1024].view(N, 32, 32).flip(2)
+    ftobs = torch.cat([tr.view(N, -1), hsamp.reshape(N, -1)], dim=1)
+    # --- reward: humanoid_pedestrain_terrain.py:907-930
+    tar = tg.calc_pos(env_ids, progress * CONTROL_DT)
+    loc_r = 1 * R.jit.compute_location_reward(bp[:, 0], tar)
+    power = torch.abs(torch.multiply(T(st["dof_force"]), dvel)).sum(dim=-1)
+    pow_r = -0.0005 * power
+    rew = loc_r + pow_r
+    rew_raw = torch.cat([loc_r[:, None], pow_r[:, None]], dim=-1)
+    # --- reset: humanoid_pedestrain_terrain.py:883-905
+    reset, term = R.jit.compute_humanoid_reset(
+        torch.zeros(N, dtype=torch.long), progress, T(st["contact"]), torch.tensor(CONTACT_BODIES),
+        ch, bp, tar, float(EPISODE_LEN), 4.0, True, torch.zeros(NB), False)
+    # --- AMP obs: humanoid_amp.py:585-657
+    key = bp[:, KEY_BODIES, :]
+    cur = R.jit.build_amp_observations_smpl(bp[:, 0], br[:, 0], bv[:, 0], bw[:, 0], dpos, dvel, key, betas, limb,
+                                            torch.from_numpy(DOF_SUBSET), True, False, True, True, False, True)
+    amp = T(st["amp_buf"]).clone()
+    amp[:, 1:] = amp[:, 0:AMP_STEPS - 1].clone()
+    amp[:, 0] = cur
+    out = dict(obs=torch.cat([so, tobs], -1), flip_obs=torch.cat([fso, ftobs], -1), rew=rew, reward_raw=rew_raw,
+               reset=reset, terminate=term, amp_obs=amp.view(N, -1), tar_pos=tar, traj_samples=samples)
+    return {k: v.numpy() for k, v in out.items()}
+
+
+def synth_locoval(B, seed):
+    rng = np.random.default_rng(seed)
+    f = np.float32
+    speed = rng.uniform(0, 3, (B, 1)); head = rng.uniform(-np.pi, np.pi, (B, 1)); turn = rng.uniform(-0.5, 0.5, (B, 1))
+    t = np.arange(13)[None] * 0.4
+    traj = np.zeros((B, 13, 2))
+    traj[..., 0] = np.cumsum(speed * np.cos(head + turn * t) * 0.4, 1)
+    traj[..., 1] = np.cumsum(speed * np.sin(head + turn * t) * 0.4, 1)
+    traj -= traj[:, :1]
+    traj[0, 1, 0] = 0.0                      # exercises the |x|<1e-10 epsilon branch
+    pose = rng.normal(0, 0.3, (B, 24, 3))
+    vel = (traj[:, 1] - traj[:, 0]) * 2.5
+    return traj.astype(f), pose.astype(f), vel.astype(f)
+
+
+def reference_locoval(traj, pose, vel, seed=0):
+    R = ref_extract.load()
+    torch = R.torch
+    torch.manual_seed(seed)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = R.ValuePoseNet(use_pose=True, use_vel=True)
+    with torch.no_grad():   # non-zero biases so the test is not blind to them
+        for m in net._network:
+            if hasattr(m, "bias"):
+                m.bias.uniform_(-0.1, 0.1)
+    W = {k: v.detach().numpy().copy() for k, v in net.state_dict().items()}
+    t = torch.from_numpy(traj.copy()).requires_grad_(True)
+    p = torch.from_numpy(pose.copy())
+    v = torch.from_numpy(vel.copy())
+    value, loss = net.calc_embodied_motion_loss(t, p, v)
+    loss.backward()
+    return W, dict(value=value.detach().numpy(), loss=loss.detach().numpy(), grad_traj=t.grad.numpy(),
+                   pose_after=p.detach().numpy())
+
+
+def reference_gae(T_, N, seed):
+    R = ref_extract.load()
+    torch = R.torch
+    rng = np.random.default_rng(seed)
+    f = np.float32
+    dones = (rng.uniform(0, 1, (T_, N)) < 0.05).astype(f)
+    values = rng.normal(0, 1, (T_, N, 1)).astype(f)
+    nvalues = rng.normal(0, 1, (T_, N, 1)).astype(f)
+    rewards = rng.uniform(0, 1, (T_, N, 1)).astype(f)
+    ag = R.meth.AgentHolder(); ag.horizon_length = T_; ag.gamma = 0.99; ag.tau = 0.95
+    adv = ag.discount_values(*[torch.from_numpy(a) for a in (dones, values, rewards, nvalues)])
+    return dict(dones=dones, values=values, rewards=rewards, next_values=nvalues, adv=adv.numpy())
+
+
+def reference_rms(x, mean, var):
+    R = ref_extract.load()
+    torch = R.torch
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = R.RunningMeanStd(x.shape[-1])
+    m.running_mean[:] = torch.from_numpy(mean); m.running_var[:] = torch.from_numpy(var)
+    m.eval()
+    return m(torch.from_numpy(x)).numpy()
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    for name, N, seed, rough in (("post_step_rough", 8, 0, True), ("post_step_flat", 6, 1, False)):
+        st = synth_state(N, seed, map_shape=(700, 700), rough=rough)
+        out = reference_post_step(st)
+        np.savez_compressed(os.path.join(OUT, f"{name}.npz"), seed=seed, N=N, rough=rough,
+                            **{f"in_{k}": v for k, v in st.items()}, **{f"out_{k}": v for k, v in out.items()})
+        print(name, {k: v.shape for k, v in out.items()})
+    traj, pose, vel = synth_locoval(64, 2)
+    W, out = reference_locoval(traj, pose, vel)
+    np.savez_compressed(os.path.join(OUT, "locoval.npz"), traj=traj, pose=pose, vel=vel,
+                        **{f"w_{k}": v for k, v in W.items()}, **{f"out_{k}": v for k, v in out.items()})
+    g = reference_gae(32, 16, 3)
+    np.savez_compressed(os.path.join(OUT, "gae.npz"), **g)
+    rng = np.random.default_rng(4)
+    x = rng.normal(0, 3, (16, 1422)).astype(np.float32)
+    mean = rng.normal(0, 1, 1422); var = rng.uniform(0.0, 4, 1422)
+    np.savez_compressed(os.path.join(OUT, "rms.npz"), x=x, mean=mean, var=var, y=reference_rms(x, mean, var))
+    print("golden fixtures written to", OUT)
+
+
+if __name__ == "__main__":
+    main()
