@@ -1,0 +1,118 @@
+"""ctypes binding of libemloco_b200.so (include/emloco.h).  No fallback: if the CUDA library is
+missing or does not load, importing the product path raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libemloco_b200.so")
+NB, ND = 24, 69
+
+SYMBOLS = [
+    "emloco_create", "emloco_destroy", "emloco_default_cfg", "emloco_tensor", "emloco_set_height_field",
+    "emloco_set_pd_targets", "emloco_simulate", "emloco_reset_indexed", "emloco_post_step", "emloco_step",
+    "emloco_step_host", "emloco_locoval_forward", "emloco_locoval_backward", "emloco_locoval_forward_host",
+    "emloco_plausibl_mlp_forward", "emloco_gae", "emloco_linear", "emloco_sync", "emloco_last_error", "emloco_version",
+]
+
+
+class EmlocoError(RuntimeError):
+    pass
+
+
+class Cfg(C.Structure):
+    _fields_ = [("num_envs", C.c_int32), ("device", C.c_int32), ("sim_dt", C.c_float), ("substeps", C.c_int32),
+                ("control_freq_inv", C.c_int32), ("gravity_z", C.c_float), ("contact_stiffness", C.c_float),
+                ("contact_damping", C.c_float), ("friction_damping", C.c_float), ("friction_mu", C.c_float),
+                ("contact_offset", C.c_float), ("max_ang_vel", C.c_float), ("angular_damping", C.c_float),
+                ("episode_length", C.c_int32), ("power_coefficient", C.c_float), ("location_coefficient", C.c_float),
+                ("fail_dist", C.c_float), ("traj_sample_dt", C.c_float), ("reserved", C.c_int32 * 8)]
+
+
+class Model(C.Structure):
+    _fields_ = [("parent", C.c_int32 * NB), ("offset", C.c_float * 3 * NB), ("mass", C.c_float * NB),
+                ("com", C.c_float * 3 * NB), ("inertia", C.c_float * 6 * NB), ("kp", C.c_float * ND),
+                ("kd", C.c_float * ND), ("armature", C.c_float * ND), ("geom_type", C.c_int32 * NB),
+                ("geom_a", C.c_float * 3 * NB), ("geom_b", C.c_float * 3 * NB), ("geom_r", C.c_float * NB),
+                ("pd_offset", C.c_float * ND), ("pd_scale", C.c_float * ND)]
+
+
+T_IDS = {n: i for i, n in enumerate([
+    "root_state", "dof_state", "rb_state", "contact", "dof_force", "pd_target", "obs", "flip_obs", "rew", "rew_raw",
+    "reset", "terminate", "progress", "amp_obs", "traj_verts", "betas", "height", "joint_quat", "actions"])}
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EmlocoError(f"{LIB_PATH} is missing - run `python -m emloco_b200.build` (or __graft_entry__.build()); "
+                          "there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+    lib.emloco_last_error.restype = C.c_char_p
+    lib.emloco_version.restype = C.c_char_p
+    lib.emloco_default_cfg.argtypes = [C.POINTER(Cfg)]
+    lib.emloco_default_cfg.restype = None
+    lib.emloco_create.argtypes = [C.POINTER(Cfg), C.POINTER(Model), C.POINTER(vp)]
+    lib.emloco_destroy.argtypes = [vp]
+    lib.emloco_tensor.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]
+    lib.emloco_set_height_field.argtypes = [vp, vp, i32, i32]
+    lib.emloco_set_pd_targets.argtypes = [vp, vp, vp]
+    lib.emloco_simulate.argtypes = [vp, vp]
+    lib.emloco_reset_indexed.argtypes = [vp, vp, i32, vp]
+    lib.emloco_post_step.argtypes = [vp, i32, vp]
+    lib.emloco_step.argtypes = [vp, vp, vp]
+    lib.emloco_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.emloco_locoval_forward.argtypes = [vp, i32, i32, vp, vp, vp, vp, i64, i32, vp]
+    lib.emloco_locoval_backward.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, i64, i32, vp]
+    lib.emloco_locoval_forward_host.argtypes = [vp, i32, i32, vp, vp, vp, vp, i64, i32, i32]
+    lib.emloco_plausibl_mlp_forward.argtypes = [vp, vp, vp, i64, vp]
+    lib.emloco_gae.argtypes = [vp, vp, vp, vp, vp, vp, i32, i64, f32, f32, vp]
+    lib.emloco_linear.argtypes = [vp, i64, vp, vp, vp, i64, i64, i32, i32, vp, vp, f32, i32, i32, vp]
+    lib.emloco_sync.argtypes = [vp]
+    for name in SYMBOLS:
+        fn = getattr(lib, name)
+        if name not in ("emloco_last_error", "emloco_version", "emloco_default_cfg"):
+            fn.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().emloco_last_error().decode()
+        raise EmlocoError(f"{what} failed ({rc}): {msg}")
+
+
+def default_cfg(**over) -> Cfg:
+    c = Cfg()
+    load().emloco_default_cfg(C.byref(c))
+    for k, v in over.items():
+        if not hasattr(c, k):
+            raise EmlocoError(f"unknown cfg field {k}")
+        setattr(c, k, v)
+    return c
+
+
+def make_model(arrs) -> Model:
+    m = Model()
+
+    def fill(dst, src, dt):
+        a = np.ascontiguousarray(np.asarray(src, dtype=dt))
+        assert a.nbytes == C.sizeof(dst), (a.shape, C.sizeof(dst))
+        C.memmove(dst, a.ctypes.data, a.nbytes)
+    fill(m.parent, arrs["parent"], np.int32); fill(m.offset, arrs["offset"], np.float32)
+    fill(m.mass, arrs["mass"], np.float32); fill(m.com, arrs["com"], np.float32)
+    fill(m.inertia, arrs["inertia6"], np.float32); fill(m.kp, arrs["kp"], np.float32)
+    fill(m.kd, arrs["kd"], np.float32); fill(m.armature, arrs["armature"], np.float32)
+    fill(m.geom_type, arrs["geom_type"], np.int32); fill(m.geom_a, arrs["geom_a"], np.float32)
+    fill(m.geom_b, arrs["geom_b"], np.float32); fill(m.geom_r, arrs["geom_r"], np.float32)
+    fill(m.pd_offset, arrs["pd_offset"], np.float32); fill(m.pd_scale, arrs["pd_scale"], np.float32)
+    return m

@@ -1,0 +1,311 @@
+// C ABI of libemloco_b200.so (see include/emloco.h for the reference interface each entry replaces).
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include "sim.h"
+
+cudaError_t eml_locoval_forward(const float*, int, int, float*, const float*, const float*, float*, long long, int, cudaStream_t);
+cudaError_t eml_locoval_backward(const float*, int, int, const float*, const float*, const float*, const float*, float*, long long, int, cudaStream_t);
+cudaError_t eml_plausibl_forward(const float*, const float*, float*, long long, cudaStream_t);
+cudaError_t eml_gae(const float*, const float*, const float*, const float*, float*, float*, int, long long, float, float, cudaStream_t);
+cudaError_t eml_linear_fma(const float*, long long, const float*, const float*, float*, long long, long long, int, int,
+                           const float*, const float*, float, int, cudaStream_t);
+cudaError_t eml_linear_tc(const float*, long long, const float*, const float*, float*, long long, long long, int, int,
+                          const float*, const float*, float, int, cudaStream_t);
+
+static thread_local std::string g_err;
+static int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+    char buf[512];
+    if (e != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    else snprintf(buf, sizeof buf, "%s", what);
+    g_err = buf;
+    return code;
+}
+#define CK(call, what) do { cudaError_t _e = (call); if (_e != cudaSuccess) return fail(EMLOCO_ECUDA, what, _e); } while (0)
+
+extern "C" {
+
+const char* emloco_last_error(void) { return g_err.c_str(); }
+const char* emloco_version(void) { return "emloco_b200 0.1 (sm_100a)"; }
+
+void emloco_default_cfg(emloco_cfg* c) {
+    memset(c, 0, sizeof *c);
+    c->num_envs = 4096; c->device = 0;
+    c->sim_dt = 1.0f / 60.0f; c->substeps = 2; c->control_freq_inv = 2;      // config.py:24, pacer.yaml:94,42
+    c->gravity_z = -9.81f;                                                  // base_task.py:225-231
+    c->contact_stiffness = 5.0e4f; c->contact_damping = 1.0e3f; c->friction_damping = 2.0e3f;
+    c->friction_mu = 1.0f;                                                  // pacer.yaml:71-72
+    c->contact_offset = 0.02f; c->max_ang_vel = 100.0f; c->angular_damping = 0.01f;
+    c->episode_length = 168; c->power_coefficient = 0.0005f; c->location_coefficient = 1.0f;
+    c->fail_dist = 4.0f; c->traj_sample_dt = 0.4f;
+}
+
+int emloco_create(const emloco_cfg* cfg, const emloco_model* model, emloco_sim** out) {
+    if (!cfg || !model || !out) return fail(EMLOCO_EINVAL, "emloco_create: null argument");
+    if (cfg->num_envs <= 0) return fail(EMLOCO_EINVAL, "emloco_create: num_envs must be positive");
+    if (cfg->substeps <= 0 || cfg->control_freq_inv <= 0 || cfg->sim_dt <= 0) return fail(EMLOCO_EINVAL, "emloco_create: bad time stepping");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev), "cudaGetDeviceCount");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(EMLOCO_EINVAL, "emloco_create: no such CUDA device");
+    CK(cudaSetDevice(cfg->device), "cudaSetDevice");
+
+    EmlModelDev md;
+    memset(&md, 0, sizeof md);
+    int nchild[EML_NB] = {0};
+    for (int i = 0; i < EML_NB; ++i) for (int s = 0; s < 3; ++s) md.child[i][s] = -1;
+    md.max_level = 0;
+    for (int i = 0; i < EML_NB; ++i) {
+        int p = model->parent[i];
+        if (i == 0 ? p != -1 : (p < 0 || p >= i)) return fail(EMLOCO_EINVAL, "emloco_create: bodies must be in DFS order with parent < child");
+        md.parent[i] = p;
+        md.level[i] = i == 0 ? 0 : md.level[p] + 1;
+        if (md.level[i] > md.max_level) md.max_level = md.level[i];
+        if (i > 0) {
+            if (nchild[p] >= 3) return fail(EMLOCO_EINVAL, "emloco_create: more than 3 children per body");
+            md.child[p][nchild[p]++] = i;
+            int d = 3 * (i - 1);
+            md.kp[i] = model->kp[d]; md.kd[i] = model->kd[d]; md.arm[i] = model->armature[d];
+            for (int k = 1; k < 3; ++k)
+                if (model->kp[d + k] != model->kp[d] || model->kd[d + k] != model->kd[d] || model->armature[d + k] != model->armature[d])
+                    return fail(EMLOCO_EINVAL, "emloco_create: x/y/z gains of a joint must be equal (spherical-joint formulation)");
+        }
+        md.mass[i] = model->mass[i];
+        md.geom_type[i] = model->geom_type[i]; md.geom_r[i] = model->geom_r[i];
+        for (int k = 0; k < 3; ++k) {
+            md.offset[i][k] = model->offset[i][k]; md.com[i][k] = model->com[i][k];
+            md.geom_a[i][k] = model->geom_a[i][k]; md.geom_b[i][k] = model->geom_b[i][k];
+        }
+        for (int k = 0; k < 6; ++k) md.inertia[i][k] = model->inertia[i][k];
+    }
+    // the level-synchronous child->parent reduction assumes multi-child bodies sit at levels 0 and 3 only
+    for (int i = 0; i < EML_NB; ++i)
+        if (nchild[i] > 1 && md.level[i] != 0 && md.level[i] != 3)
+            return fail(EMLOCO_EINVAL, "emloco_create: unsupported tree shape (branching body not at level 0 or 3)");
+    for (int d = 0; d < EML_ND; ++d) { md.pd_offset[d] = model->pd_offset[d]; md.pd_scale[d] = model->pd_scale[d]; }
+    CK(eml_upload_model(&md), "upload model");
+
+    emloco_sim* s = (emloco_sim*)calloc(1, sizeof(emloco_sim));
+    if (!s) return fail(EMLOCO_ENOMEM, "emloco_create: out of host memory");
+    s->cfg = *cfg; s->N = cfg->num_envs; s->device = cfg->device;
+    const size_t N = (size_t)s->N;
+#define ALLOC(ptr, count, type) do { CK(cudaMalloc((void**)&(ptr), (count) * sizeof(type)), "cudaMalloc " #ptr); \
+                                     CK(cudaMemset((ptr), 0, (count) * sizeof(type)), "cudaMemset " #ptr); } while (0)
+    ALLOC(s->root_state, N * 13, float); ALLOC(s->dof_state, N * EML_ND * 2, float); ALLOC(s->rb_state, N * EML_NB * 13, float);
+    ALLOC(s->contact, N * EML_NB * 3, float); ALLOC(s->dof_force, N * EML_ND, float); ALLOC(s->pd_target, N * EML_ND, float);
+    ALLOC(s->joint_quat, N * EML_NJ * 4, float); ALLOC(s->actions, N * EML_ND, float);
+    ALLOC(s->obs, N * EML_OBS, float); ALLOC(s->flip_obs, N * EML_OBS, float); ALLOC(s->rew, N, float); ALLOC(s->rew_raw, N * 2, float);
+    ALLOC(s->reset, N, int64_t); ALLOC(s->terminate, N, int64_t); ALLOC(s->progress, N, int64_t);
+    ALLOC(s->amp_obs, N * EML_AMP_OBS, float); ALLOC(s->verts, N * EML_NUM_VERTS * 3, float); ALLOC(s->betas, N * 17, float);
+    // default terrain: flat 1080 x 1080 (8 m map + 50 m border at 0.1 m, humanoid_pedestrain_terrain.py:1142-1165)
+    s->hf_rows = 1080; s->hf_cols = 1080;
+    ALLOC(s->height, (size_t)s->hf_rows * s->hf_cols, int16_t);
+#undef ALLOC
+    s->h_pin_bytes = N * (EML_ND + EML_OBS + EML_AMP_OBS + 1) * sizeof(float) + N * sizeof(int64_t);
+    CK(cudaMallocHost((void**)&s->h_pin, s->h_pin_bytes), "cudaMallocHost");
+    // identity pose: unit quaternions
+    {
+        float* h = (float*)malloc(N * 13 * sizeof(float));
+        memset(h, 0, N * 13 * sizeof(float));
+        for (size_t e = 0; e < N; ++e) h[e * 13 + 6] = 1.f;
+        CK(cudaMemcpy(s->root_state, h, N * 13 * sizeof(float), cudaMemcpyHostToDevice), "init root");
+        free(h);
+    }
+    CK(eml_launch_fk(s, nullptr, 0, 0), "initial forward kinematics");
+    CK(cudaDeviceSynchronize(), "emloco_create sync");
+    *out = s;
+    return EMLOCO_OK;
+}
+
+int emloco_destroy(emloco_sim* s) {
+    if (!s) return EMLOCO_OK;
+    cudaSetDevice(s->device);
+    void* ptrs[] = {s->root_state, s->dof_state, s->rb_state, s->contact, s->dof_force, s->pd_target, s->joint_quat, s->actions,
+                    s->obs, s->flip_obs, s->rew, s->rew_raw, s->reset, s->terminate, s->progress, s->amp_obs, s->verts, s->betas,
+                    s->height};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (s->h_pin) cudaFreeHost(s->h_pin);
+    free(s);
+    return EMLOCO_OK;
+}
+
+int emloco_tensor(emloco_sim* s, int which, void** d_ptr, int64_t* shape, int32_t* ndim, int32_t* dtype) {
+    if (!s || !d_ptr || !shape || !ndim || !dtype) return fail(EMLOCO_EINVAL, "emloco_tensor: null argument");
+    const int64_t N = s->N;
+    *dtype = EMLOCO_DTYPE_F32;
+    shape[0] = shape[1] = shape[2] = shape[3] = 1;
+    switch (which) {
+    case EMLOCO_T_ROOT_STATE: *d_ptr = s->root_state; *ndim = 2; shape[0] = N; shape[1] = 13; break;
+    case EMLOCO_T_DOF_STATE: *d_ptr = s->dof_state; *ndim = 2; shape[0] = N * EML_ND; shape[1] = 2; break;
+    case EMLOCO_T_RB_STATE: *d_ptr = s->rb_state; *ndim = 2; shape[0] = N * EML_NB; shape[1] = 13; break;
+    case EMLOCO_T_CONTACT: *d_ptr = s->contact; *ndim = 2; shape[0] = N * EML_NB; shape[1] = 3; break;
+    case EMLOCO_T_DOF_FORCE: *d_ptr = s->dof_force; *ndim = 1; shape[0] = N * EML_ND; break;
+    case EMLOCO_T_PD_TARGET: *d_ptr = s->pd_target; *ndim = 2; shape[0] = N; shape[1] = EML_ND; break;
+    case EMLOCO_T_OBS: *d_ptr = s->obs; *ndim = 2; shape[0] = N; shape[1] = EML_OBS; break;
+    case EMLOCO_T_FLIP_OBS: *d_ptr = s->flip_obs; *ndim = 2; shape[0] = N; shape[1] = EML_OBS; break;
+    case EMLOCO_T_REW: *d_ptr = s->rew; *ndim = 1; shape[0] = N; break;
+    case EMLOCO_T_REW_RAW: *d_ptr = s->rew_raw; *ndim = 2; shape[0] = N; shape[1] = 2; break;
+    case EMLOCO_T_RESET: *d_ptr = s->reset; *ndim = 1; shape[0] = N; *dtype = EMLOCO_DTYPE_I64; break;
+    case EMLOCO_T_TERMINATE: *d_ptr = s->terminate; *ndim = 1; shape[0] = N; *dtype = EMLOCO_DTYPE_I64; break;
+    case EMLOCO_T_PROGRESS: *d_ptr = s->progress; *ndim = 1; shape[0] = N; *dtype = EMLOCO_DTYPE_I64; break;
+    case EMLOCO_T_AMP_OBS: *d_ptr = s->amp_obs; *ndim = 3; shape[0] = N; shape[1] = EML_AMP_STEPS; shape[2] = EML_AMP_STEP; break;
+    case EMLOCO_T_TRAJ_VERTS: *d_ptr = s->verts; *ndim = 3; shape[0] = N; shape[1] = EML_NUM_VERTS; shape[2] = 3; break;
+    case EMLOCO_T_BETAS: *d_ptr = s->betas; *ndim = 2; shape[0] = N; shape[1] = 17; break;
+    case EMLOCO_T_HEIGHT: *d_ptr = s->height; *ndim = 2; shape[0] = s->hf_rows; shape[1] = s->hf_cols; *dtype = EMLOCO_DTYPE_I16; break;
+    case EMLOCO_T_JOINT_QUAT: *d_ptr = s->joint_quat; *ndim = 3; shape[0] = N; shape[1] = EML_NJ; shape[2] = 4; break;
+    case EMLOCO_T_ACTIONS: *d_ptr = s->actions; *ndim = 2; shape[0] = N; shape[1] = EML_ND; break;
+    default: return fail(EMLOCO_EINVAL, "emloco_tensor: unknown tensor id");
+    }
+    return EMLOCO_OK;
+}
+
+int emloco_set_height_field(emloco_sim* s, const int16_t* h, int32_t rows, int32_t cols) {
+    if (!s || !h || rows < 2 || cols < 2) return fail(EMLOCO_EINVAL, "emloco_set_height_field: bad argument");
+    CK(cudaSetDevice(s->device), "cudaSetDevice");
+    CK(cudaDeviceSynchronize(), "sync before terrain swap");
+    if ((size_t)rows * cols != (size_t)s->hf_rows * s->hf_cols) {
+        int16_t* n = nullptr;
+        CK(cudaMalloc((void**)&n, (size_t)rows * cols * sizeof(int16_t)), "cudaMalloc height");
+        cudaFree(s->height);
+        s->height = n;
+    }
+    s->hf_rows = rows; s->hf_cols = cols;
+    CK(cudaMemcpy(s->height, h, (size_t)rows * cols * sizeof(int16_t), cudaMemcpyHostToDevice), "copy height field");
+    return EMLOCO_OK;
+}
+
+int emloco_set_pd_targets(emloco_sim* s, const float* d_targets, void* stream) {
+    if (!s || !d_targets) return fail(EMLOCO_EINVAL, "emloco_set_pd_targets: null argument");
+    if (d_targets != s->pd_target)
+        CK(cudaMemcpyAsync(s->pd_target, d_targets, (size_t)s->N * EML_ND * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream), "copy pd targets");
+    return EMLOCO_OK;
+}
+
+int emloco_simulate(emloco_sim* s, void* stream) {
+    if (!s) return fail(EMLOCO_EINVAL, "emloco_simulate: null sim");
+    CK(eml_launch_physics(s, nullptr, s->cfg.substeps, 0, (cudaStream_t)stream), "physics kernel");
+    return EMLOCO_OK;
+}
+
+int emloco_reset_indexed(emloco_sim* s, const int32_t* d_env_ids, int32_t n, void* stream) {
+    if (!s) return fail(EMLOCO_EINVAL, "emloco_reset_indexed: null sim");
+    if (d_env_ids && n < 0) return fail(EMLOCO_EINVAL, "emloco_reset_indexed: negative count");
+    if (d_env_ids && n == 0) return EMLOCO_OK;
+    CK(eml_launch_fk(s, d_env_ids, n, (cudaStream_t)stream), "fk kernel");
+    return EMLOCO_OK;
+}
+
+int emloco_post_step(emloco_sim* s, int32_t advance_progress, void* stream) {
+    if (!s) return fail(EMLOCO_EINVAL, "emloco_post_step: null sim");
+    CK(eml_launch_post_step(s, advance_progress ? 1 : 0, (cudaStream_t)stream), "post-step kernel");
+    return EMLOCO_OK;
+}
+
+int emloco_step(emloco_sim* s, const float* d_actions, void* stream) {
+    if (!s || !d_actions) return fail(EMLOCO_EINVAL, "emloco_step: null argument");
+    CK(eml_launch_physics(s, d_actions, s->cfg.substeps * s->cfg.control_freq_inv, 1, (cudaStream_t)stream), "physics kernel");
+    CK(eml_launch_post_step(s, 1, (cudaStream_t)stream), "post-step kernel");
+    return EMLOCO_OK;
+}
+
+int emloco_step_host(emloco_sim* s, const float* h_actions, float* h_obs, float* h_rew, int64_t* h_reset, float* h_amp_obs) {
+    if (!s || !h_actions) return fail(EMLOCO_EINVAL, "emloco_step_host: null argument");
+    CK(cudaSetDevice(s->device), "cudaSetDevice");
+    const size_t N = (size_t)s->N;
+    float* p_act = s->h_pin;
+    float* p_obs = p_act + N * EML_ND;
+    float* p_rew = p_obs + N * EML_OBS;
+    float* p_amp = p_rew + N;
+    int64_t* p_reset = (int64_t*)(p_amp + N * EML_AMP_OBS);
+    memcpy(p_act, h_actions, N * EML_ND * sizeof(float));
+    cudaStream_t st = 0;
+    float* d_act = s->actions;   // staging: the physics kernel reads P.actions and re-writes the same values
+    CK(cudaMemcpyAsync(d_act, p_act, N * EML_ND * sizeof(float), cudaMemcpyHostToDevice, st), "H2D actions");
+    int rc = emloco_step(s, d_act, st);
+    if (rc) return rc;
+    if (h_obs) CK(cudaMemcpyAsync(p_obs, s->obs, N * EML_OBS * sizeof(float), cudaMemcpyDeviceToHost, st), "D2H obs");
+    if (h_rew) CK(cudaMemcpyAsync(p_rew, s->rew, N * sizeof(float), cudaMemcpyDeviceToHost, st), "D2H rew");
+    if (h_reset) CK(cudaMemcpyAsync(p_reset, s->reset, N * sizeof(int64_t), cudaMemcpyDeviceToHost, st), "D2H reset");
+    if (h_amp_obs) CK(cudaMemcpyAsync(p_amp, s->amp_obs, N * EML_AMP_OBS * sizeof(float), cudaMemcpyDeviceToHost, st), "D2H amp");
+    CK(cudaStreamSynchronize(st), "step_host sync");
+    if (h_obs) memcpy(h_obs, p_obs, N * EML_OBS * sizeof(float));
+    if (h_rew) memcpy(h_rew, p_rew, N * sizeof(float));
+    if (h_reset) memcpy(h_reset, p_reset, N * sizeof(int64_t));
+    if (h_amp_obs) memcpy(h_amp_obs, p_amp, N * EML_AMP_OBS * sizeof(float));
+    return EMLOCO_OK;
+}
+
+int emloco_locoval_forward(const float* d_traj, int32_t traj_stride, int32_t T, float* d_pose, const float* d_vel,
+                           const float* d_weights, float* d_value, int64_t batch, int32_t flags, void* stream) {
+    if (!d_traj || !d_weights || !d_value) return fail(EMLOCO_EINVAL, "emloco_locoval_forward: null argument");
+    if ((flags & 1) && !d_pose) return fail(EMLOCO_EINVAL, "emloco_locoval_forward: init_pose should be included");   // value_pose_net.py:114,136
+    if ((flags & 2) && !d_vel) return fail(EMLOCO_EINVAL, "emloco_locoval_forward: init_vel should be included");
+    if (traj_stride < 2 || (T != 13 && T != 5) || batch < 0) return fail(EMLOCO_EINVAL, "emloco_locoval_forward: bad shape");
+    CK(eml_locoval_forward(d_traj, traj_stride, T, d_pose, d_vel, d_weights, d_value, batch, flags, (cudaStream_t)stream), "locoval forward");
+    return EMLOCO_OK;
+}
+
+int emloco_locoval_backward(const float* d_traj, int32_t traj_stride, int32_t T, const float* d_pose, const float* d_vel,
+                            const float* d_weights, const float* d_grad_value, float* d_grad_traj, int64_t batch, int32_t flags,
+                            void* stream) {
+    if (!d_traj || !d_weights || !d_grad_value || !d_grad_traj) return fail(EMLOCO_EINVAL, "emloco_locoval_backward: null argument");
+    if ((flags & 1) && !d_pose) return fail(EMLOCO_EINVAL, "emloco_locoval_backward: init_pose should be included");
+    if ((flags & 2) && !d_vel) return fail(EMLOCO_EINVAL, "emloco_locoval_backward: init_vel should be included");
+    if (traj_stride < 2 || (T != 13 && T != 5) || batch < 0) return fail(EMLOCO_EINVAL, "emloco_locoval_backward: bad shape");
+    CK(eml_locoval_backward(d_traj, traj_stride, T, d_pose, d_vel, d_weights, d_grad_value, d_grad_traj, batch, flags, (cudaStream_t)stream), "locoval backward");
+    return EMLOCO_OK;
+}
+
+static int locoval_nweights(int T, int flags) {
+    int in = 2 * T + ((flags & 1) ? 72 : 0) + ((flags & 2) ? 2 : 0);
+    int h1 = in / 2 - 1, h2 = h1 / 2;
+    return in * h1 + h1 + h1 * h2 + h2 + h2 + 1;
+}
+
+int emloco_locoval_forward_host(const float* h_traj, int32_t traj_stride, int32_t T, const float* h_pose, const float* h_vel,
+                                const float* h_weights, float* h_value, int64_t B, int32_t flags, int32_t device) {
+    if (!h_traj || !h_weights || !h_value) return fail(EMLOCO_EINVAL, "emloco_locoval_forward_host: null argument");
+    if (B <= 0) return B == 0 ? EMLOCO_OK : fail(EMLOCO_EINVAL, "emloco_locoval_forward_host: negative batch");
+    CK(cudaSetDevice(device), "cudaSetDevice");
+    float *dt = nullptr, *dp = nullptr, *dv = nullptr, *dw = nullptr, *dval = nullptr;
+    size_t nt = (size_t)B * T * traj_stride, nw = locoval_nweights(T, flags);
+    CK(cudaMalloc((void**)&dt, nt * 4), "malloc traj"); CK(cudaMalloc((void**)&dw, nw * 4), "malloc w"); CK(cudaMalloc((void**)&dval, (size_t)B * 4), "malloc value");
+    CK(cudaMemcpyAsync(dt, h_traj, nt * 4, cudaMemcpyHostToDevice, 0), "H2D traj");
+    CK(cudaMemcpyAsync(dw, h_weights, nw * 4, cudaMemcpyHostToDevice, 0), "H2D w");
+    if (flags & 1) { CK(cudaMalloc((void**)&dp, (size_t)B * 72 * 4), "malloc pose"); CK(cudaMemcpyAsync(dp, h_pose, (size_t)B * 72 * 4, cudaMemcpyHostToDevice, 0), "H2D pose"); }
+    if (flags & 2) { CK(cudaMalloc((void**)&dv, (size_t)B * 2 * 4), "malloc vel"); CK(cudaMemcpyAsync(dv, h_vel, (size_t)B * 2 * 4, cudaMemcpyHostToDevice, 0), "H2D vel"); }
+    int rc = emloco_locoval_forward(dt, traj_stride, T, dp, dv, dw, dval, B, flags & ~32, 0);
+    if (!rc) { cudaError_t e = cudaMemcpy(h_value, dval, (size_t)B * 4, cudaMemcpyDeviceToHost); if (e != cudaSuccess) rc = fail(EMLOCO_ECUDA, "D2H value", e); }
+    cudaFree(dt); cudaFree(dw); cudaFree(dval); if (dp) cudaFree(dp); if (dv) cudaFree(dv);
+    return rc;
+}
+
+int emloco_plausibl_mlp_forward(const float* d_x, const float* d_weights, float* d_value, int64_t batch, void* stream) {
+    if (!d_x || !d_weights || !d_value || batch < 0) return fail(EMLOCO_EINVAL, "emloco_plausibl_mlp_forward: bad argument");
+    CK(eml_plausibl_forward(d_x, d_weights, d_value, batch, (cudaStream_t)stream), "plausibl mlp");
+    return EMLOCO_OK;
+}
+
+int emloco_gae(const float* d_dones, const float* d_values, const float* d_rewards, const float* d_next_values, float* d_adv,
+               float* d_ret, int32_t T, int64_t N, float gamma, float tau, void* stream) {
+    if (!d_dones || !d_values || !d_rewards || !d_next_values || !d_adv || T < 0 || N < 0) return fail(EMLOCO_EINVAL, "emloco_gae: bad argument");
+    CK(eml_gae(d_dones, d_values, d_rewards, d_next_values, d_adv, d_ret, T, N, gamma, tau, (cudaStream_t)stream), "gae kernel");
+    return EMLOCO_OK;
+}
+
+int emloco_linear(const float* d_x, int64_t ldx, const float* d_w, const float* d_b, float* d_y, int64_t ldy, int64_t M, int32_t N,
+                  int32_t K, const float* d_mean, const float* d_var, float eps, int32_t relu, int32_t use_tc, void* stream) {
+    if (!d_x || !d_w || !d_y || M < 0 || N <= 0 || K <= 0 || ldx < K || ldy < N) return fail(EMLOCO_EINVAL, "emloco_linear: bad argument");
+    if ((d_mean == nullptr) != (d_var == nullptr)) return fail(EMLOCO_EINVAL, "emloco_linear: mean and var must come together");
+    if (use_tc) CK(eml_linear_tc(d_x, ldx, d_w, d_b, d_y, ldy, M, N, K, d_mean, d_var, eps, relu, (cudaStream_t)stream), "linear (tensor core)");
+    else CK(eml_linear_fma(d_x, ldx, d_w, d_b, d_y, ldy, M, N, K, d_mean, d_var, eps, relu, (cudaStream_t)stream), "linear (fma)");
+    return EMLOCO_OK;
+}
+
+int emloco_sync(emloco_sim* s) {
+    if (s) CK(cudaSetDevice(s->device), "cudaSetDevice");
+    CK(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+    return EMLOCO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,265 @@
+// LocoVal: ValuePoseNet forward / input-gradient backward
+// (reference pacer/pacer/learning/value_pose_net.py:10-159) as one fused kernel each:
+// heading normalisation (:73-103) -> hide toes/spine (:141-144) -> Linear-ReLU-Linear-ReLU-Linear-sigmoid.
+// Also the plausibl value MLP (plausibl/test_value_mlp.py:24-113).
+//
+// One thread per sample; the 6 174 weights live in shared memory, transposed to [in][out] so every
+// weight read is a warp-wide broadcast LDS.128 and the hidden activations stay in registers.
+// The reference instead builds a [B,2,2] rotation matrix on the CPU and copies it H2D per call (:85-90).
+#include "sim.h"
+
+#define LV_THREADS 128
+
+template <int T, bool POSE, bool VEL>
+struct LvDims {
+    static constexpr int IN = 2 * T + (POSE ? 72 : 0) + (VEL ? 2 : 0);
+    static constexpr int H1 = IN / 2 - 1;       // value_pose_net.py:52
+    static constexpr int H2 = H1 / 2;           // :53
+    static constexpr int H1P = (H1 + 3) & ~3;   // padded to float4
+    static constexpr int H2P = (H2 + 3) & ~3;
+    static constexpr int NW = IN * H1 + H1 + H1 * H2 + H2 + H2 + 1;
+    static constexpr int SMEM = (IN * H1P + H1P + H1 * H2P + H2P + H2P + 4) * 4;
+};
+
+template <int T, bool POSE, bool VEL>
+__device__ __forceinline__ void lv_stage_weights(const float* __restrict__ w, float* s_w1t, float* s_b1, float* s_w2t,
+                                                 float* s_b2, float* s_w3, float* s_b3) {
+    using D = LvDims<T, POSE, VEL>;
+    const float* w1 = w; const float* b1 = w1 + D::IN * D::H1;
+    const float* w2 = b1 + D::H1; const float* b2 = w2 + D::H1 * D::H2;
+    const float* w3 = b2 + D::H2; const float* b3 = w3 + D::H2;
+    for (int i = threadIdx.x; i < D::IN * D::H1P; i += blockDim.x) {
+        int k = i / D::H1P, j = i % D::H1P;
+        s_w1t[i] = j < D::H1 ? w1[j * D::IN + k] : 0.f;
+    }
+    for (int i = threadIdx.x; i < D::H1 * D::H2P; i += blockDim.x) {
+        int j = i / D::H2P, o = i % D::H2P;
+        s_w2t[i] = o < D::H2 ? w2[o * D::H1 + j] : 0.f;
+    }
+    for (int i = threadIdx.x; i < D::H1P; i += blockDim.x) s_b1[i] = i < D::H1 ? b1[i] : 0.f;
+    for (int i = threadIdx.x; i < D::H2P; i += blockDim.x) { s_b2[i] = i < D::H2 ? b2[i] : 0.f; s_w3[i] = i < D::H2 ? w3[i] : 0.f; }
+    if (threadIdx.x == 0) s_b3[0] = b3[0];
+}
+
+// rotation angle of _rotate_normalization (:76-84)
+__device__ __forceinline__ void lv_angle(float x1, float y1, bool normalize, float& c, float& s, float& xe, bool& near0) {
+    near0 = fabsf(x1) < 1e-10f;
+    xe = near0 ? 1e-10f : x1;
+    if (normalize) { float a = atan2f(y1, xe); sincosf(a, &s, &c); } else { c = 1.f; s = 0.f; }
+}
+
+template <int T, bool POSE, bool VEL, bool BWD>
+__global__ void __launch_bounds__(LV_THREADS) locoval_kernel(const float* __restrict__ traj, int stride, float* pose_rw,
+                                                             const float* __restrict__ vel, const float* __restrict__ weights,
+                                                             float* __restrict__ value, const float* __restrict__ gvalue,
+                                                             float* __restrict__ gtraj, long long B, int flags) {
+    using D = LvDims<T, POSE, VEL>;
+    extern __shared__ __align__(16) float smem[];
+    float* s_w1t = smem;
+    float* s_b1 = s_w1t + D::IN * D::H1P;
+    float* s_w2t = s_b1 + D::H1P;
+    float* s_b2 = s_w2t + D::H1 * D::H2P;
+    float* s_w3 = s_b2 + D::H2P;
+    float* s_b3 = s_w3 + D::H2P;
+    lv_stage_weights<T, POSE, VEL>(weights, s_w1t, s_b1, s_w2t, s_b2, s_w3, s_b3);
+    __syncthreads();
+    const bool hide_toe = flags & 4, hide_spine = flags & 8, normalize = flags & 16, writeback = flags & 32;
+
+    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+        const float* tr = traj + b * T * stride;
+        float c, s, xe; bool near0;
+        const float x1 = tr[stride], y1 = tr[stride + 1];
+        lv_angle(x1, y1, normalize, c, s, xe, near0);
+
+        float h1[D::H1P];
+#pragma unroll
+        for (int j = 0; j < D::H1P; ++j) h1[j] = s_b1[j];
+        auto acc1 = [&](int k, float x) {
+            const float4* wr = reinterpret_cast<const float4*>(s_w1t + k * D::H1P);
+#pragma unroll
+            for (int j4 = 0; j4 < D::H1P / 4; ++j4) {
+                float4 w = wr[j4];
+                h1[4 * j4] += w.x * x; h1[4 * j4 + 1] += w.y * x; h1[4 * j4 + 2] += w.z * x; h1[4 * j4 + 3] += w.w * x;
+            }
+        };
+        // ---- layer 1, inputs generated on the fly: row-vector times [[c,-s],[s,c]] (:85-100) ----
+#pragma unroll 1
+        for (int n = 0; n < T; ++n) {
+            float x = tr[n * stride], y = tr[n * stride + 1];
+            acc1(2 * n, x * c + y * s);
+            acc1(2 * n + 1, y * c - x * s);
+        }
+        if (POSE) {
+            float* pp = pose_rw + b * 72;
+#pragma unroll 1
+            for (int j = 0; j < 24; ++j) {
+                float x = pp[3 * j], y = pp[3 * j + 1], z = pp[3 * j + 2];
+                float xr = x * c + y * s, yr = y * c - x * s;
+                if ((hide_toe && (j == 4 || j == 8)) || (hide_spine && j >= 9 && j <= 11)) { xr = 0.f; yr = 0.f; z = 0.f; }
+                if (!BWD && writeback) { pp[3 * j] = xr; pp[3 * j + 1] = yr; pp[3 * j + 2] = z; }
+                acc1(2 * T + 3 * j, xr); acc1(2 * T + 3 * j + 1, yr); acc1(2 * T + 3 * j + 2, z);
+            }
+        }
+        if (VEL) {
+            float x = vel[b * 2], y = vel[b * 2 + 1];
+            acc1(D::IN - 2, x * c + y * s);
+            acc1(D::IN - 1, y * c - x * s);
+        }
+        // ---- layer 2 / 3 ----
+        float h2[D::H2P];
+#pragma unroll
+        for (int o = 0; o < D::H2P; ++o) h2[o] = s_b2[o];
+#pragma unroll
+        for (int j = 0; j < D::H1; ++j) {
+            float a = fmaxf(h1[j], 0.f);
+            h1[j] = a;
+            const float4* wr = reinterpret_cast<const float4*>(s_w2t + j * D::H2P);
+#pragma unroll
+            for (int o4 = 0; o4 < D::H2P / 4; ++o4) {
+                float4 w = wr[o4];
+                h2[4 * o4] += w.x * a; h2[4 * o4 + 1] += w.y * a; h2[4 * o4 + 2] += w.z * a; h2[4 * o4 + 3] += w.w * a;
+            }
+        }
+        float z = s_b3[0];
+#pragma unroll
+        for (int o = 0; o < D::H2; ++o) { h2[o] = fmaxf(h2[o], 0.f); z += s_w3[o] * h2[o]; }
+        const float v = 1.0f / (1.0f + expf(-z));
+        if (!BWD) { value[b] = v; continue; }
+
+        // ---- backward: d value / d traj (autograd of calc_embodied_motion_loss, :151-159) ----
+        const float dz = gvalue[b] * v * (1.0f - v);
+#pragma unroll
+        for (int o = 0; o < D::H2P; ++o) h2[o] = (o < D::H2 && h2[o] > 0.f) ? s_w3[o] * dz : 0.f;   // dh2
+#pragma unroll
+        for (int j = 0; j < D::H1; ++j) {                                                            // dh1 in place
+            const float4* wr = reinterpret_cast<const float4*>(s_w2t + j * D::H2P);
+            float d = 0.f;
+#pragma unroll
+            for (int o4 = 0; o4 < D::H2P / 4; ++o4) {
+                float4 w = wr[o4];
+                d += w.x * h2[4 * o4] + w.y * h2[4 * o4 + 1] + w.z * h2[4 * o4 + 2] + w.w * h2[4 * o4 + 3];
+            }
+            h1[j] = h1[j] > 0.f ? d : 0.f;
+        }
+#pragma unroll
+        for (int j = D::H1; j < D::H1P; ++j) h1[j] = 0.f;
+        auto dx = [&](int k) {
+            const float4* wr = reinterpret_cast<const float4*>(s_w1t + k * D::H1P);
+            float d = 0.f;
+#pragma unroll
+            for (int j4 = 0; j4 < D::H1P / 4; ++j4) {
+                float4 w = wr[j4];
+                d += w.x * h1[4 * j4] + w.y * h1[4 * j4 + 1] + w.z * h1[4 * j4 + 2] + w.w * h1[4 * j4 + 3];
+            }
+            return d;
+        };
+        // d/dtheta of (x',y') = (x c + y s, y c - x s) is (y', -x')
+        float dtheta = 0.f;
+        float* gt = gtraj + b * T * stride;
+#pragma unroll 1
+        for (int n = 0; n < T; ++n) {
+            float x = tr[n * stride], y = tr[n * stride + 1];
+            float xr = x * c + y * s, yr = y * c - x * s;
+            float gx = dx(2 * n), gy = dx(2 * n + 1);
+            dtheta += gx * yr - gy * xr;
+            gt[n * stride] = gx * c - gy * s;
+            gt[n * stride + 1] = gx * s + gy * c;
+            for (int u = 2; u < stride; ++u) gt[n * stride + u] = 0.f;
+        }
+        if (POSE) {
+            const float* pp = pose_rw + b * 72;
+#pragma unroll 1
+            for (int j = 0; j < 24; ++j) {
+                if ((hide_toe && (j == 4 || j == 8)) || (hide_spine && j >= 9 && j <= 11)) continue;
+                float x = pp[3 * j], y = pp[3 * j + 1];
+                float xr = x * c + y * s, yr = y * c - x * s;
+                dtheta += dx(2 * T + 3 * j) * yr - dx(2 * T + 3 * j + 1) * xr;
+            }
+        }
+        if (VEL) {
+            float x = vel[b * 2], y = vel[b * 2 + 1];
+            float xr = x * c + y * s, yr = y * c - x * s;
+            dtheta += dx(D::IN - 2) * yr - dx(D::IN - 1) * xr;
+        }
+        if (normalize) {   // theta = atan2(y1, xe); xe = x1 unless |x1| < 1e-10 (:79-84)
+            float r2 = xe * xe + y1 * y1;
+            gt[stride + 1] += dtheta * xe / r2;
+            if (!near0) gt[stride] += -dtheta * y1 / r2;
+        }
+    }
+}
+
+template <int T, bool POSE, bool VEL, bool BWD>
+static cudaError_t lv_launch(const float* traj, int stride, float* pose, const float* vel, const float* w, float* value,
+                             const float* gv, float* gt, long long B, int flags, cudaStream_t st) {
+    using D = LvDims<T, POSE, VEL>;
+    auto k = locoval_kernel<T, POSE, VEL, BWD>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, D::SMEM);
+    if (e != cudaSuccess) return e;
+    if (B <= 0) return cudaSuccess;
+    long long blocks = (B + LV_THREADS - 1) / LV_THREADS;
+    // persistent-ish grid: weights are staged once per CTA, so cap at a few CTAs per SM (148 SMs)
+    long long cap = 148LL * 8;
+    int grid = (int)(blocks < cap ? blocks : cap);
+    k<<<grid, LV_THREADS, D::SMEM, st>>>(traj, stride, pose, vel, w, value, gv, gt, B, flags);
+    return cudaGetLastError();
+}
+
+template <bool BWD>
+static cudaError_t lv_dispatch(const float* traj, int stride, int T, float* pose, const float* vel, const float* w,
+                               float* value, const float* gv, float* gt, long long B, int flags, cudaStream_t st) {
+    bool P = flags & 1, V = flags & 2;
+#define LV_CASE(TT, PP, VV) if (T == TT && P == PP && V == VV) return lv_launch<TT, PP, VV, BWD>(traj, stride, pose, vel, w, value, gv, gt, B, flags, st)
+    LV_CASE(13, true, true); LV_CASE(13, true, false); LV_CASE(13, false, true); LV_CASE(13, false, false);
+    LV_CASE(5, true, true); LV_CASE(5, true, false); LV_CASE(5, false, true); LV_CASE(5, false, false);
+#undef LV_CASE
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t eml_locoval_forward(const float* traj, int stride, int T, float* pose, const float* vel, const float* w,
+                                float* value, long long B, int flags, cudaStream_t st) {
+    return lv_dispatch<false>(traj, stride, T, pose, vel, w, value, nullptr, nullptr, B, flags, st);
+}
+cudaError_t eml_locoval_backward(const float* traj, int stride, int T, const float* pose, const float* vel, const float* w,
+                                 const float* gv, float* gt, long long B, int flags, cudaStream_t st) {
+    return lv_dispatch<true>(traj, stride, T, const_cast<float*>(pose), vel, w, nullptr, gv, gt, B, flags, st);
+}
+
+// ---- plausibl/test_value_mlp.py:24-113: Linear(24,12)-ReLU-Linear(12,6)-ReLU-Linear(6,1) ----
+__global__ void plausibl_mlp_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ out, long long B) {
+    __shared__ float sw[24 * 12 + 12 + 12 * 6 + 6 + 6 + 1];
+    for (int i = threadIdx.x; i < 24 * 12 + 12 + 12 * 6 + 6 + 6 + 1; i += blockDim.x) sw[i] = w[i];
+    __syncthreads();
+    const float* w1 = sw; const float* b1 = w1 + 288; const float* w2 = b1 + 12; const float* b2 = w2 + 72;
+    const float* w3 = b2 + 6; const float* b3 = w3 + 6;
+    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+        float in[24];
+#pragma unroll
+        for (int k = 0; k < 24; ++k) in[k] = x[b * 24 + k];
+        float h1[12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {
+            float a = b1[j];
+#pragma unroll
+            for (int k = 0; k < 24; ++k) a += w1[j * 24 + k] * in[k];
+            h1[j] = fmaxf(a, 0.f);
+        }
+        float z = b3[0];
+#pragma unroll
+        for (int o = 0; o < 6; ++o) {
+            float a = b2[o];
+#pragma unroll
+            for (int j = 0; j < 12; ++j) a += w2[o * 12 + j] * h1[j];
+            z += w3[o] * fmaxf(a, 0.f);
+        }
+        out[b] = z;
+    }
+}
+
+cudaError_t eml_plausibl_forward(const float* x, const float* w, float* out, long long B, cudaStream_t st) {
+    if (B <= 0) return cudaSuccess;
+    long long blocks = (B + 127) / 128;
+    int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
+    plausibl_mlp_kernel<<<grid, 128, 0, st>>>(x, w, out, B);
+    return cudaGetLastError();
+}

@@ -1,0 +1,292 @@
+// Fused post-physics kernel: everything BaseTask.step does after gym.simulate/fetch_results
+// (reference pacer/pacer/env/tasks/base_task.py:258-265 -> humanoid_amp.py:139-157 ->
+// humanoid.py:1211-1232), i.e. SURVEY 8a rows a4-a9 in ONE launch:
+//   progress += 1                                              humanoid.py:1213
+//   self obs   compute_humanoid_observations_smpl_max          humanoid.py:1626-1687
+//   task obs   _fetch_traj_samples / calc_pos / location obs   humanoid_traj.py:208-224, traj_generator.py:278-296,
+//              head-rooted 32x32 height scan, centre heights    humanoid_pedestrain_terrain.py:394-452,732-815,1212-1288
+//   flip obs   mirrored self obs + flipped task obs            humanoid.py:1066-1108, ..terrain.py:455-491
+//   reward     exp(-2 d^2) - 0.0005 sum|tau qd|                 ..terrain.py:907-930,1581-1592
+//   reset      fallen / too-far / episode end (int64)           ..terrain.py:883-905,1468-1530
+//   AMP obs    history shift + new 206-float step               humanoid_amp.py:585-657,917-971
+//
+// HBM-bound: ~37 KB of traffic per env (27 KB of it the AMP history + obs writes), a few hundred
+// flops per output.  One 128-thread CTA per env; inputs are staged in shared memory with vector
+// loads, the 1422-float observation row is assembled in shared memory and streamed out (normal and
+// mirrored) with coalesced 8-byte stores; the AMP ring is shifted through registers.
+#include "sim.h"
+
+#define PS_THREADS 128
+
+__constant__ float c_grid32[32];     // np.linspace(-2, 2, 32)   (init_square_height_points, ..terrain.py:650-668)
+__constant__ float c_cgx[3];         // np.linspace(-0.1, 0.1, 3) (init_center_height_points, ..terrain.py:631-647)
+__constant__ float c_cgy[3];         // np.linspace(-0.2, 0.2, 3)
+__constant__ int c_l2r[EML_NB] = {0, 5, 6, 7, 8, 1, 2, 3, 4, 9, 10, 11, 12, 13, 19, 20, 21, 22, 23, 14, 15, 16, 17, 18};
+__constant__ int c_amp_joint[19] = {0, 1, 2, 4, 5, 6, 8, 9, 10, 11, 12, 13, 14, 15, 16, 18, 19, 20, 21};
+__constant__ int c_key_body[4] = {7, 3, 22, 17};   // R_Ankle, L_Ankle, R_Wrist, L_Wrist (pacer.yaml:50)
+
+struct PostParams {
+    const float* rb; const float* dof; const float* contact; const float* dof_force;
+    const float* verts; const float* betas; const int16_t* height; int hf_rows, hf_cols;
+    int64_t* progress; float* obs; float* flip_obs; float* rew; float* rew_raw;
+    int64_t* reset; int64_t* terminate; float* amp;
+    int N; int advance; float dt; float traj_dur; float sample_dt; int max_len;
+    float power_coef, loc_coef, fail_dist2;
+};
+
+// Terrain.world_points_to_map + sample (..terrain.py:1212-1218,1282-1288); fp32 division and
+// truncation exactly as torch does on the host path.
+__device__ __forceinline__ float sample_height(const int16_t* __restrict__ hf, int rows, int cols, float x, float y) {
+    long long px = (long long)__fdiv_rn(x, 0.1f);
+    long long py = (long long)__fdiv_rn(y, 0.1f);
+    px = px < 0 ? 0 : (px > rows - 2 ? rows - 2 : px);
+    py = py < 0 ? 0 : (py > cols - 2 ? cols - 2 : py);
+    int h1 = __ldg(hf + px * cols + py);
+    int h2 = __ldg(hf + (px + 1) * cols + py + 1);
+    return (float)(h1 < h2 ? h1 : h2) * 0.005f;
+}
+
+// quat_apply(q=(0,0,qz,qw), (bx,by,0)) + pos, contraction-free so the grid index matches torch's (torch_utils.py:49-56)
+__device__ __forceinline__ void yaw_apply(float qz, float qw, float bx, float by, float px, float py, float& ox, float& oy) {
+    float tx = __fmul_rn(-__fmul_rn(qz, by), 2.0f);
+    float ty = __fmul_rn(__fmul_rn(qz, bx), 2.0f);
+    float cx = -__fmul_rn(qz, ty);
+    float cy = __fmul_rn(qz, tx);
+    float rx = __fadd_rn(__fadd_rn(bx, __fmul_rn(qw, tx)), cx);
+    float ry = __fadd_rn(__fadd_rn(by, __fmul_rn(qw, ty)), cy);
+    ox = __fadd_rn(rx, px);
+    oy = __fadd_rn(ry, py);
+}
+
+// TrajGenerator.calc_pos (traj_generator.py:278-296)
+__device__ __forceinline__ f3 calc_pos(const float* __restrict__ verts, float t, float traj_dur) {
+    float phase = fminf(fmaxf(__fdiv_rn(t, traj_dur), 0.0f), 1.0f);
+    float seg = phase * (float)(EML_NUM_VERTS - 1);
+    float f0 = floorf(seg), f1 = ceilf(seg);
+    int i0 = (int)f0, i1 = (int)f1;
+    float l = seg - f0;
+    const float* a = verts + i0 * 3;
+    const float* b = verts + i1 * 3;
+    float w = 1.0f - l;
+    return mk3(w * a[0] + l * b[0], w * a[1] + l * b[1], w * a[2] + l * b[2]);
+}
+
+__global__ void __launch_bounds__(PS_THREADS) post_step_kernel(PostParams P) {
+    __shared__ __align__(16) float s_rb[EML_NB * 13];
+    __shared__ __align__(16) float s_dof[EML_ND * 2];
+    __shared__ __align__(16) float s_obs[EML_OBS + 2];
+    __shared__ __align__(16) float s_amp[EML_AMP_STEP];
+    __shared__ float s_misc[16];   // 0-3 hinv, 4-5 head yaw (z,w), 6-7 root yaw (z,w), 8 centre height, 9 time
+
+    const int env = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    if (env >= P.N) return;
+
+    // ---- stage state ----
+    {
+        const float4* g = reinterpret_cast<const float4*>(P.rb + (size_t)env * EML_NB * 13);
+        if (tid < 78) reinterpret_cast<float4*>(s_rb)[tid] = __ldg(g + tid);
+        const float2* d = reinterpret_cast<const float2*>(P.dof + (size_t)env * EML_ND * 2);
+        if (tid < EML_ND) reinterpret_cast<float2*>(s_dof)[tid] = __ldg(d + tid);
+    }
+    // AMP history: hist[k+1] = old[k] (humanoid_amp.py:585-594); read now, store after the last barrier
+    float2 hist[12];
+    {
+        const float2* a = reinterpret_cast<const float2*>(P.amp + (size_t)env * EML_AMP_OBS);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            int i = tid + PS_THREADS * k;
+            if (i < 14 * 103) hist[k] = a[i];
+        }
+    }
+    long long prog = P.progress[env] + P.advance;
+    __syncthreads();
+
+    const f3 root_pos = mk3(s_rb[0], s_rb[1], s_rb[2]);
+    if (tid == 0) {
+        f4 rr = mk4(s_rb[3], s_rb[4], s_rb[5], s_rb[6]);
+        f4 hinv = quat_from_angle_z(-calc_heading(rr));
+        s_misc[0] = hinv.x; s_misc[1] = hinv.y; s_misc[2] = hinv.z; s_misc[3] = hinv.w;
+        if (P.advance) P.progress[env] = prog;
+        s_misc[9] = (float)prog * P.dt;
+    } else if (tid == 32) {
+        const float* h = s_rb + EML_HEAD * 13;
+        f4 hq = quat_from_angle_z(calc_heading(mk4(h[3], h[4], h[5], h[6])));
+        s_misc[4] = hq.z; s_misc[5] = hq.w;
+    } else if (tid == 64) {
+        // quat_apply_yaw: zero x,y then normalise (..terrain.py:1533-1538)
+        float qz = s_rb[5], qw = s_rb[6];
+        float n = fmaxf(sqrtf(qz * qz + qw * qw), 1e-9f);
+        s_misc[6] = qz / n; s_misc[7] = qw / n;
+    }
+    __syncthreads();
+    const f4 hinv = mk4(s_misc[0], s_misc[1], s_misc[2], s_misc[3]);
+    const float time0 = s_misc[9];
+    const float* verts = P.verts + (size_t)env * EML_NUM_VERTS * 3;
+
+    if (warp == 0) {
+        // ---- self observation, one lane per body (humanoid.py:1626-1687) ----
+        if (lane < EML_NB) {
+            const float* b = s_rb + lane * 13;
+            f3 lp = quat_rotate(hinv, mk3(b[0], b[1], b[2]) - root_pos);
+            if (lane > 0) { float* o = s_obs + (lane - 1) * 3; o[0] = lp.x; o[1] = lp.y; o[2] = lp.z; }
+            f4 lr = quat_mul(hinv, mk4(b[3], b[4], b[5], b[6]));
+            quat_to_tan_norm(lr, s_obs + 69 + lane * 6);
+            f3 lv = quat_rotate(hinv, mk3(b[7], b[8], b[9]));
+            f3 lw = quat_rotate(hinv, mk3(b[10], b[11], b[12]));
+            float* ov = s_obs + 213 + lane * 3; ov[0] = lv.x; ov[1] = lv.y; ov[2] = lv.z;
+            float* ow = s_obs + 285 + lane * 3; ow[0] = lw.x; ow[1] = lw.y; ow[2] = lw.z;
+            if (lane == 0) {   // AMP root block reuses the same quantities (humanoid_amp.py:924-938)
+                for (int k = 0; k < 6; ++k) s_amp[k] = s_obs[69 + k];
+                s_amp[6] = lv.x; s_amp[7] = lv.y; s_amp[8] = lv.z;
+                s_amp[9] = lw.x; s_amp[10] = lw.y; s_amp[11] = lw.z;
+            }
+        }
+    } else if (warp == 1) {
+        // ---- trajectory samples, target, reward-location, centre height ----
+        if (lane < EML_TRAJ_SAMPLES) {
+            float t = time0 + (float)lane * P.sample_dt;
+            f3 s = calc_pos(verts, t, P.traj_dur);
+            f3 l = quat_rotate(hinv, s - root_pos);
+            s_obs[EML_SELF_OBS + 2 * lane] = l.x;
+            s_obs[EML_SELF_OBS + 2 * lane + 1] = l.y;
+        }
+        float ch = 0.f;
+        if (lane >= 16 && lane < 25) {
+            int i = lane - 16;
+            float x, y;
+            yaw_apply(s_misc[6], s_misc[7], c_cgx[i / 3], c_cgy[i % 3], root_pos.x, root_pos.y, x, y);
+            ch = sample_height(P.height, P.hf_rows, P.hf_cols, x, y);
+        }
+        ch = warp_sum(ch);
+        if (lane == 0) s_misc[8] = ch / 9.0f;
+    } else if (warp == 2) {
+        // ---- AMP step: joints (exp-map -> quat -> tan/norm), dof vel subset, key bodies ----
+        if (lane < 19) {
+            int j = c_amp_joint[lane];
+            f3 e = mk3(s_dof[(3 * j) * 2], s_dof[(3 * j + 1) * 2], s_dof[(3 * j + 2) * 2]);
+            quat_to_tan_norm(exp_map_to_quat(e), s_amp + 12 + lane * 6);
+            s_amp[126 + lane * 3 + 0] = s_dof[(3 * j) * 2 + 1];
+            s_amp[126 + lane * 3 + 1] = s_dof[(3 * j + 1) * 2 + 1];
+            s_amp[126 + lane * 3 + 2] = s_dof[(3 * j + 2) * 2 + 1];
+        } else if (lane < 23) {
+            int k = lane - 19;
+            const float* b = s_rb + c_key_body[k] * 13;
+            f3 l = quat_rotate(hinv, mk3(b[0], b[1], b[2]) - root_pos);
+            s_amp[183 + k * 3] = l.x; s_amp[184 + k * 3] = l.y; s_amp[185 + k * 3] = l.z;
+        }
+    } else {
+        // ---- reward, reset, shape parameters ----
+        float pw = 0.f;
+        const float* df = P.dof_force + (size_t)env * EML_ND;
+        for (int i = lane; i < EML_ND; i += 32) pw += fabsf(__ldg(df + i) * s_dof[2 * i + 1]);
+        pw = warp_sum(pw);
+        f3 cs = mk3(0.f, 0.f, 0.f);
+        if (lane < EML_NB && lane != 3 && lane != 4 && lane != 7 && lane != 8) {   // contactBodies masked (pacer.yaml:51)
+            const float* c = P.contact + ((size_t)env * EML_NB + lane) * 3;
+            cs = mk3(__ldg(c), __ldg(c + 1), __ldg(c + 2));
+        }
+        cs.x = warp_sum(cs.x); cs.y = warp_sum(cs.y); cs.z = warp_sum(cs.z);
+        if (lane < 11) {
+            float b = __ldg(P.betas + (size_t)env * 17 + lane);
+            s_obs[357 + lane] = b;
+            s_amp[195 + lane] = b;
+        }
+        if (lane == 31) {
+            f3 tar = calc_pos(verts, time0, P.traj_dur);
+            float dx = tar.x - root_pos.x, dy = tar.y - root_pos.y;
+            float err = dx * dx + dy * dy;
+            float loc = P.loc_coef * expf(-2.0f * err);
+            float pr = -P.power_coef * pw;
+            P.rew[env] = loc + pr;
+            P.rew_raw[2 * env] = loc; P.rew_raw[2 * env + 1] = pr;
+            bool fallen = sqrtf(cs.x * cs.x + cs.y * cs.y + cs.z * cs.z) > 50.0f && prog > 1;
+            bool fail = err > P.fail_dist2;
+            long long term = (fallen || fail) ? 1 : 0;
+            P.terminate[env] = term;
+            P.reset[env] = (prog >= P.max_len - 1) ? 1 : term;
+        }
+    }
+    __syncthreads();
+
+    // ---- head-rooted 32x32 height scan (..terrain.py:761-815), 8 points per thread ----
+    {
+        const float* h = s_rb + EML_HEAD * 13;
+        const float hx = h[0], hy = h[1], qz = s_misc[4], qw = s_misc[5], centre = s_misc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            int i = tid + PS_THREADS * k;
+            float x, y;
+            yaw_apply(qz, qw, c_grid32[i >> 5], c_grid32[i & 31], hx, hy, x, y);
+            float m = sample_height(P.height, P.hf_rows, P.hf_cols, x, y);
+            s_obs[EML_SELF_OBS + 30 + i] = fminf(fmaxf(centre - m, -3.0f), 3.0f) * 5.0f;
+        }
+    }
+    __syncthreads();
+
+    // ---- stream out: obs, mirrored obs, AMP ring ----
+    {
+        float2* o = reinterpret_cast<float2*>(P.obs + (size_t)env * EML_OBS);
+        float2* f = reinterpret_cast<float2*>(P.flip_obs + (size_t)env * EML_OBS);
+        for (int i2 = tid; i2 < EML_OBS / 2; i2 += PS_THREADS) {
+            o[i2] = reinterpret_cast<const float2*>(s_obs)[i2];
+            float v[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                int i = 2 * i2 + u;
+                float r;
+                if (i < 69) { int b = i / 3 + 1, c = i % 3; r = s_obs[(c_l2r[b] - 1) * 3 + c]; if (c == 1) r = -r; }
+                else if (i < 213) { int j = i - 69, b = j / 6, c = j % 6; r = s_obs[69 + c_l2r[b] * 6 + c]; if (c % 3 == 1) r = -r; }
+                else if (i < 285) { int j = i - 213, b = j / 3, c = j % 3; r = s_obs[213 + c_l2r[b] * 3 + c]; if (c == 1) r = -r; }
+                else if (i < 357) { int j = i - 285, b = j / 3, c = j % 3; r = s_obs[285 + c_l2r[b] * 3 + c]; if (c != 1) r = -r; }
+                else if (i < 368) { r = s_obs[i]; }
+                else if (i < 398) { r = s_obs[i]; if ((i - 368) & 1) r = -r; }
+                else { int j = i - 398; r = s_obs[398 + (j & ~31) + (31 - (j & 31))]; }
+                v[u] = r;
+            }
+            f[i2] = make_float2(v[0], v[1]);
+        }
+        float2* a = reinterpret_cast<float2*>(P.amp + (size_t)env * EML_AMP_OBS);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            int i = tid + PS_THREADS * k;
+            if (i < 14 * 103) a[103 + i] = hist[k];
+        }
+        if (tid < 103) a[tid] = reinterpret_cast<const float2*>(s_amp)[tid];
+    }
+}
+
+static bool g_tables_ready = false;
+
+cudaError_t eml_launch_post_step(emloco_sim* s, int advance_progress, cudaStream_t st) {
+    if (!g_tables_ready) {
+        float g32[32], cx[3], cy[3];
+        for (int i = 0; i < 32; ++i) g32[i] = (float)(-2.0 + (4.0 / 31.0) * i);   // np.linspace step form: start + i*step
+        g32[31] = 2.0f;
+        double sx = 0.2 / 2.0, sy = 0.4 / 2.0;
+        for (int i = 0; i < 3; ++i) { cx[i] = (float)(-0.1 + sx * i); cy[i] = (float)(-0.2 + sy * i); }
+        cx[2] = 0.1f; cy[2] = 0.2f;
+        cudaError_t e;
+        if ((e = cudaMemcpyToSymbol(c_grid32, g32, sizeof(g32))) != cudaSuccess) return e;
+        if ((e = cudaMemcpyToSymbol(c_cgx, cx, sizeof(cx))) != cudaSuccess) return e;
+        if ((e = cudaMemcpyToSymbol(c_cgy, cy, sizeof(cy))) != cudaSuccess) return e;
+        g_tables_ready = true;
+    }
+    PostParams P;
+    P.rb = s->rb_state; P.dof = s->dof_state; P.contact = s->contact; P.dof_force = s->dof_force;
+    P.verts = s->verts; P.betas = s->betas; P.height = s->height; P.hf_rows = s->hf_rows; P.hf_cols = s->hf_cols;
+    P.progress = s->progress; P.obs = s->obs; P.flip_obs = s->flip_obs; P.rew = s->rew; P.rew_raw = s->rew_raw;
+    P.reset = s->reset; P.terminate = s->terminate; P.amp = s->amp_obs;
+    P.N = s->N; P.advance = advance_progress;
+    double dt = (double)s->cfg.control_freq_inv * (double)s->cfg.sim_dt;          // humanoid.py:89
+    P.dt = (float)dt;
+    double tdt = ((double)s->cfg.episode_length * dt) / (EML_NUM_VERTS - 1);      // traj_generator.py:24
+    P.traj_dur = (float)(EML_NUM_VERTS * tdt);                                    // traj_generator.py:269-272
+    P.sample_dt = s->cfg.traj_sample_dt;
+    P.max_len = s->cfg.episode_length;
+    P.power_coef = s->cfg.power_coefficient; P.loc_coef = s->cfg.location_coefficient;
+    P.fail_dist2 = s->cfg.fail_dist * s->cfg.fail_dist;
+    post_step_kernel<<<s->N, PS_THREADS, 0, st>>>(P);
+    return cudaGetLastError();
+}

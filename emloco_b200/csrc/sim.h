@@ -1,0 +1,66 @@
+// Internal (not part of the C ABI): simulation object and kernel launchers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/emloco.h"
+#include "common.cuh"
+
+// Per-asset constants, uploaded once to __constant__ memory (shared by all envs: the default
+// run has no shape variation because the SMPL model files are not redistributable).
+struct EmlModelDev {
+    int   parent[EML_NB];
+    int   level[EML_NB];
+    int   child[EML_NB][3];       // up to 3 children per body, -1 padded
+    float offset[EML_NB][3];      // joint anchor in the parent frame
+    float mass[EML_NB];
+    float com[EML_NB][3];         // body frame
+    float inertia[EML_NB][6];     // about COM, body frame: xx xy xz yy yz zz
+    float kp[EML_NB];             // per joint (index = body), already scaled by mass/77*kp_scale
+    float kd[EML_NB];
+    float arm[EML_NB];
+    int   geom_type[EML_NB];
+    float geom_a[EML_NB][3];
+    float geom_b[EML_NB][3];
+    float geom_r[EML_NB];
+    float pd_offset[EML_ND];
+    float pd_scale[EML_ND];
+    int   max_level;
+};
+
+struct emloco_sim {
+    emloco_cfg cfg;
+    int N;
+    int device;
+    // --- state owned by the sim; addresses are stable for its lifetime (gymtorch.wrap_tensor aliases) ---
+    float*   root_state;    // [N,13]   pos3 quat4 lin3 ang3
+    float*   dof_state;     // [N*69,2] (exp-map pos, vel) interleaved
+    float*   rb_state;      // [N*24,13]
+    float*   contact;       // [N*24,3]
+    float*   dof_force;     // [N*69]
+    float*   pd_target;     // [N,69]
+    float*   joint_quat;    // [N,23,4] internal authoritative joint rotation
+    float*   actions;       // [N,69]  (copy of the last actions, humanoid.py:1186)
+    // --- task buffers (base_task.py:96-112) ---
+    float*   obs;           // [N,1422]
+    float*   flip_obs;      // [N,1422]
+    float*   rew;           // [N]
+    float*   rew_raw;       // [N,2]
+    int64_t* reset;         // [N]
+    int64_t* terminate;     // [N]
+    int64_t* progress;      // [N]
+    float*   amp_obs;       // [N,15,206]
+    float*   verts;         // [N,101,3] trajectory polylines (TrajGenerator._verts)
+    float*   betas;         // [N,17]
+    int16_t* height;        // [rows,cols]
+    int      hf_rows, hf_cols;
+    // pinned host staging for the *_host entry points
+    float*   h_pin;
+    size_t   h_pin_bytes;
+    cudaStream_t copy_stream;
+};
+
+// kernel launchers (defined in the .cu files)
+cudaError_t eml_upload_model(const EmlModelDev* m);
+cudaError_t eml_launch_post_step(emloco_sim* s, int advance_progress, cudaStream_t st);
+cudaError_t eml_launch_physics(emloco_sim* s, const float* d_actions, int n_substeps, int fuse_post, cudaStream_t st);
+cudaError_t eml_launch_fk(emloco_sim* s, const int32_t* d_env_ids, int n, cudaStream_t st);

@@ -1,0 +1,184 @@
+"""LocoVal drop-in: same surface as the reference ``ValuePoseNet``
+(pacer/pacer/learning/value_pose_net.py:10-159): constructor flags, ``forward``,
+``calc_embodied_motion_loss``, state-dict keys ``_network.fc{1,2,3}.{weight,bias}``, ``.eval()/.to()``.
+Callers: social-transmotion/train_jta.py:198-204,288-308, evaluate_jta.py:298-302,574-584,
+pacer/pacer/learning/amp_value_players.py:128-137,365-373, amp_continuous_value.py:123-145.
+
+The forward pass and the gradient w.r.t. the predicted trajectory run in the fused CUDA kernels of
+csrc/locoval.cu through the C ABI.  Like the reference, ``forward`` rotates and zeroes the caller's
+``init_pose`` IN PLACE (value_pose_net.py:97,141-144); pass ``mutate_pose=False`` to opt out.
+When the LocoVal weights themselves require grad (the fine-tuning step of
+amp_continuous_value.py:123-145, one small batch per rollout step) the weight gradients come from
+PyTorch autograd, as the survey scopes it ("backward stays PyTorch autograd").
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+F_POSE, F_VEL, F_HIDE_TOE, F_HIDE_SPINE, F_NORMALIZE, F_WRITEBACK = 1, 2, 4, 8, 16, 32
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class _LocoValFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, traj, pose, vel, wpack, flags, T):
+        B = traj.shape[0]
+        stride = traj.shape[-1]
+        value = torch.empty(B, 1, device=traj.device, dtype=torch.float32)
+        need_grad = traj.requires_grad
+        pose_saved = None
+        if pose is not None and need_grad:
+            pose_saved = pose.detach().clone() if (flags & F_WRITEBACK) else pose.detach()
+        _lib.check(_lib.load().emloco_locoval_forward(_p(traj), stride, T, _p(pose), _p(vel), _p(wpack), _p(value), B,
+                                                      flags, _stream()), "emloco_locoval_forward")
+        ctx.save_for_backward(traj, pose_saved, vel, wpack)
+        ctx.flags, ctx.T = flags, T
+        if pose is not None and (flags & F_WRITEBACK):
+            ctx.mark_dirty(pose)
+        return value
+
+    @staticmethod
+    def backward(ctx, gvalue):
+        traj, pose, vel, wpack = ctx.saved_tensors
+        g = gvalue.contiguous().float()
+        gtraj = torch.empty_like(traj)
+        _lib.check(_lib.load().emloco_locoval_backward(_p(traj), traj.shape[-1], ctx.T, _p(pose), _p(vel), _p(wpack), _p(g),
+                                                       _p(gtraj), traj.shape[0], ctx.flags & ~F_WRITEBACK, _stream()),
+                   "emloco_locoval_backward")
+        return gtraj, None, None, None, None, None
+
+
+class ValuePoseNet(nn.Module):
+    def __init__(self, use_pose, use_vel, hide_toe=True, hide_spine=True, normalize=True, vru=False, mutate_pose=True,
+                 **kwargs):
+        super().__init__(**kwargs)
+        self.use_pose, self.use_vel = bool(use_pose), bool(use_vel)
+        self.hide_toe, self.hide_spine, self.normalize, self.use_vru = hide_toe, hide_spine, normalize, vru
+        self.mutate_pose = mutate_pose
+        self.traj_size = 13 * 2 if not vru else 5 * 2                     # value_pose_net.py:37
+        self.pose_size, self.vel_size = 24 * 3, 2
+        n_in = self.traj_size + (self.pose_size if use_pose else 0) + (self.vel_size if use_vel else 0)
+        fc1_out = int(n_in / 2) - 1                                       # :52
+        fc2_out = int(fc1_out / 2)                                        # :53
+        self._network = nn.Sequential()
+        self._network.add_module("fc1", nn.Linear(n_in, fc1_out))
+        self._network.add_module("relu1", nn.ReLU())
+        self._network.add_module("fc2", nn.Linear(fc1_out, fc2_out))
+        self._network.add_module("relu2", nn.ReLU())
+        self._network.add_module("fc3", nn.Linear(fc2_out, 1))
+        self._network.add_module("sigmoid", nn.Sigmoid())
+        for m in self._network:                                           # :62-66
+            if isinstance(m, nn.Linear):
+                nn.init.xavier_uniform_(m.weight)
+                nn.init.constant_(m.bias, 0)
+        self.criterion = nn.MSELoss()
+        self._pack = None
+        self._pack_key = None
+
+    # ---- weights packed in state-dict order for the kernel (cached until a parameter changes) ----
+    def _weights(self):
+        ps = [self._network.fc1.weight, self._network.fc1.bias, self._network.fc2.weight, self._network.fc2.bias,
+              self._network.fc3.weight, self._network.fc3.bias]
+        key = tuple((p.data_ptr(), p._version, p.device) for p in ps)
+        if key != self._pack_key:
+            self._pack = torch.cat([p.detach().reshape(-1).float() for p in ps]).contiguous()
+            self._pack_key = key
+        return self._pack
+
+    def _flags(self):
+        return ((F_POSE if self.use_pose else 0) | (F_VEL if self.use_vel else 0) | (F_HIDE_TOE if self.hide_toe else 0)
+                | (F_HIDE_SPINE if self.hide_spine else 0) | (F_NORMALIZE if self.normalize else 0)
+                | (F_WRITEBACK if self.mutate_pose else 0))
+
+    def _weights_need_grad(self):
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self._network.parameters()) and self.training
+
+    def forward(self, waypoint_traj, init_pose=None, init_vel=None):
+        if self.use_pose:
+            assert init_pose is not None, "init_pose should be included"   # :114
+        if self.use_vel:
+            assert init_vel is not None, "init_vel should be included"     # :126
+        if not waypoint_traj.is_cuda:
+            raise _lib.EmlocoError("ValuePoseNet (emloco_b200) runs on CUDA tensors only; there is no CPU fallback")
+        if self._weights_need_grad():
+            return self._forward_autograd(waypoint_traj, init_pose, init_vel)
+        T = self.traj_size // 2
+        traj = waypoint_traj
+        if traj.dtype != torch.float32 or not traj.is_contiguous():
+            traj = traj.float().contiguous()
+        assert traj.dim() == 3 and traj.shape[1] == T and traj.shape[2] >= 2, "waypoint_traj must be [B, T, >=2]"
+        pose = vel = None
+        if self.use_pose:
+            pose = init_pose
+            if pose.dtype != torch.float32 or not pose.is_contiguous():
+                if self.mutate_pose:
+                    raise _lib.EmlocoError("init_pose must be contiguous float32 to be rotated in place like the reference does")
+                pose = pose.float().contiguous()
+            assert pose.shape[-2:] == (24, 3) and pose.shape[0] == traj.shape[0]
+        if self.use_vel:
+            vel = init_vel[:, :2].float().contiguous()
+        return _LocoValFn.apply(traj, pose, vel, self._weights(), self._flags(), T)
+
+    def _forward_autograd(self, traj, pose, vel):
+        """Weight-gradient path (LocoVal fine-tuning only): plain torch ops, same math as the kernel."""
+        xy = traj[..., :2]
+        if self.normalize:
+            x, y = xy[:, 1, 0], xy[:, 1, 1]
+            near = x.abs() < 1e-10
+            x = x * (~near) + near * 1e-10
+            ang = torch.atan2(y, x)
+            c, s = torch.cos(ang), torch.sin(ang)
+            R = torch.stack([torch.stack([c, -s], -1), torch.stack([s, c], -1)], -2)
+            xy = torch.bmm(xy, R)
+            if pose is not None:
+                pose[..., :2] = torch.bmm(pose[:, :, :2].clone(), R)
+            if vel is not None:
+                vel = torch.bmm(vel[:, :2].clone().unsqueeze(1), R)[:, 0]
+        feats = [xy.reshape(-1, self.traj_size)]
+        if self.use_pose:
+            if self.hide_toe:
+                pose[:, [4, 8]] = 0
+            if self.hide_spine:
+                pose[:, [9, 10, 11]] = 0
+            feats.append(pose.reshape(-1, self.pose_size))
+        if self.use_vel:
+            feats.append(vel.reshape(-1, self.vel_size))
+        return self._network(torch.cat(feats, dim=-1))
+
+    def calc_embodied_motion_loss(self, pred_traj, init_pose=None, init_vel=None):
+        pred_value = self.forward(pred_traj, init_pose, init_vel)
+        loss = self.criterion(pred_value, torch.ones_like(pred_value))     # :157
+        return pred_value, loss
+
+
+def score_host(traj, pose, vel, state_dict, device=0, use_pose=True, use_vel=True, hide_toe=True, hide_spine=True,
+               normalize=True):
+    """Batched LocoVal scoring straight from host (numpy) buffers through the C ABI - replaces the
+    batch-of-1 triple loop of social-transmotion/evaluate_jta.py:214-357."""
+    import numpy as np
+    traj = np.ascontiguousarray(traj, np.float32)
+    B, T, stride = traj.shape
+    keys = ["_network.fc1.weight", "_network.fc1.bias", "_network.fc2.weight", "_network.fc2.bias",
+            "_network.fc3.weight", "_network.fc3.bias"]
+    w = np.concatenate([np.asarray(state_dict[k], np.float32).reshape(-1) for k in keys])
+    flags = ((F_POSE if use_pose else 0) | (F_VEL if use_vel else 0) | (F_HIDE_TOE if hide_toe else 0)
+             | (F_HIDE_SPINE if hide_spine else 0) | (F_NORMALIZE if normalize else 0))
+    out = np.empty(B, np.float32)
+    pp = np.ascontiguousarray(pose, np.float32) if use_pose else None
+    vv = np.ascontiguousarray(vel, np.float32) if use_vel else None
+    vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    _lib.check(_lib.load().emloco_locoval_forward_host(vp(traj), stride, T, vp(pp), vp(vv), vp(w), vp(out), B, flags, device),
+               "emloco_locoval_forward_host")
+    return out

@@ -1,0 +1,181 @@
+/* emloco_b200 - C ABI of the B200-native EmLoco hot path (libemloco_b200.so).
+ *
+ * Plain C, plain pointers and sizes; no torch types.  Every entry point names the reference
+ * interface it replaces (paths relative to ImIntheMiddle/EmLoco).  All `d_` pointers are CUDA
+ * device pointers on the sim's device, all `h_` pointers are host pointers.  Calls are
+ * stream-ordered on the `cudaStream_t` passed as `void* stream` (NULL = default stream) and never
+ * synchronise unless the name says so (`*_host`, `emloco_sync`).  A sim handle is not re-entrant.
+ *
+ * Return convention: 0 = ok, negative = error (EMLOCO_E*); text via emloco_last_error().
+ * (Isaac Gym itself returns None / prints and the caller quit()s: pacer/pacer/env/tasks/base_task.py:239-241.)
+ */
+#ifndef EMLOCO_H
+#define EMLOCO_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMLOCO_OK        0
+#define EMLOCO_EINVAL   -1
+#define EMLOCO_ECUDA    -2
+#define EMLOCO_ENOMEM   -3
+
+#define EMLOCO_NB 24
+#define EMLOCO_ND 69
+
+/* Simulation parameters: gymapi.SimParams as filled by parse_sim_params
+ * (pacer/pacer/utils/config.py:141-174) from pacer/pacer/data/cfg/pacer.yaml:93-104. */
+typedef struct emloco_cfg {
+    int32_t num_envs;
+    int32_t device;               /* CUDA ordinal (compute_device_id of gym.create_sim) */
+    float   sim_dt;               /* 1/60 */
+    int32_t substeps;             /* 2: PhysX substeps per gym.simulate */
+    int32_t control_freq_inv;     /* 2: gym.simulate calls per env step (base_task.py:792-797) */
+    float   gravity_z;            /* -9.81 */
+    float   contact_stiffness;    /* N/m per contact point (implicit spring) */
+    float   contact_damping;      /* N s/m per contact point, normal */
+    float   friction_damping;     /* N s/m per contact point, tangential (sticking regime) */
+    float   friction_mu;          /* 1.0 (pacer.yaml:71-72) */
+    float   contact_offset;       /* 0.02 */
+    float   max_ang_vel;          /* 100 (humanoid.py:685-688) */
+    float   angular_damping;      /* 0.01 */
+    int32_t episode_length;       /* 168 (pacer.yaml:12) */
+    float   power_coefficient;    /* 0.0005 */
+    float   location_coefficient; /* 1 */
+    float   fail_dist;            /* 4.0 (humanoid_traj.py:31) */
+    float   traj_sample_dt;       /* 0.4 */
+    int32_t reserved[8];
+} emloco_cfg;
+
+/* Articulation + collision model: what gym.load_asset/create_actor build from
+ * mjcf/smpl_humanoid.xml (pacer/pacer/env/tasks/humanoid.py:643-835), flattened. */
+typedef struct emloco_model {
+    int32_t parent[EMLOCO_NB];
+    float   offset[EMLOCO_NB][3];
+    float   mass[EMLOCO_NB];
+    float   com[EMLOCO_NB][3];
+    float   inertia[EMLOCO_NB][6];   /* xx xy xz yy yz zz about COM, body frame */
+    float   kp[EMLOCO_ND];           /* DOF stiffness after the mass/77*kp_scale scaling, humanoid.py:905-910 */
+    float   kd[EMLOCO_ND];
+    float   armature[EMLOCO_ND];
+    int32_t geom_type[EMLOCO_NB];    /* 0 sphere, 1 capsule, 2 box */
+    float   geom_a[EMLOCO_NB][3];
+    float   geom_b[EMLOCO_NB][3];
+    float   geom_r[EMLOCO_NB];
+    float   pd_offset[EMLOCO_ND];    /* _build_pd_action_offset_scale, humanoid.py:950-1025 */
+    float   pd_scale[EMLOCO_ND];
+} emloco_model;
+
+typedef struct emloco_sim emloco_sim;
+
+/* Tensor ids for emloco_tensor(): the gym.acquire_*_tensor family (humanoid.py:137-150) plus the
+ * task buffers of base_task.py:96-112 that the fused post-step kernel writes. */
+enum {
+    EMLOCO_T_ROOT_STATE = 0,   /* f32 [N,13]     acquire_actor_root_state_tensor */
+    EMLOCO_T_DOF_STATE,        /* f32 [N*69,2]   acquire_dof_state_tensor */
+    EMLOCO_T_RB_STATE,         /* f32 [N*24,13]  acquire_rigid_body_state_tensor */
+    EMLOCO_T_CONTACT,          /* f32 [N*24,3]   acquire_net_contact_force_tensor */
+    EMLOCO_T_DOF_FORCE,        /* f32 [N*69]     acquire_dof_force_tensor */
+    EMLOCO_T_PD_TARGET,        /* f32 [N,69]     set_dof_position_target_tensor storage */
+    EMLOCO_T_OBS,              /* f32 [N,1422]   obs_buf */
+    EMLOCO_T_FLIP_OBS,         /* f32 [N,1422]   _flip_obs_buf (humanoid.py:1052-1057) */
+    EMLOCO_T_REW,              /* f32 [N]        rew_buf */
+    EMLOCO_T_REW_RAW,          /* f32 [N,2]      reward_raw */
+    EMLOCO_T_RESET,            /* i64 [N]        reset_buf */
+    EMLOCO_T_TERMINATE,        /* i64 [N]        _terminate_buf */
+    EMLOCO_T_PROGRESS,         /* i64 [N]        progress_buf */
+    EMLOCO_T_AMP_OBS,          /* f32 [N,15,206] _amp_obs_buf (humanoid_amp.py:92-98) */
+    EMLOCO_T_TRAJ_VERTS,       /* f32 [N,101,3]  TrajGenerator._verts (traj_generator.py:35-36) */
+    EMLOCO_T_BETAS,            /* f32 [N,17]     humanoid_betas */
+    EMLOCO_T_HEIGHT,           /* i16 [rows,cols] Terrain.heightsamples */
+    EMLOCO_T_JOINT_QUAT,       /* f32 [N,23,4]   internal joint rotations (xyzw) */
+    EMLOCO_T_ACTIONS,          /* f32 [N,69]     self.actions */
+    EMLOCO_T_COUNT
+};
+enum { EMLOCO_DTYPE_F32 = 0, EMLOCO_DTYPE_I64 = 1, EMLOCO_DTYPE_I16 = 2 };
+
+/* gym.create_sim + load_asset + create_env/create_actor x N + prepare_sim
+ * (base_task.py:238, humanoid.py:643-946, base_task.py:128). */
+int emloco_create(const emloco_cfg* cfg, const emloco_model* model, emloco_sim** out);
+int emloco_destroy(emloco_sim* sim);
+void emloco_default_cfg(emloco_cfg* cfg);
+
+/* gym.acquire_*_tensor -> gymapi.Tensor{data_address, shape, dtype} (isaacgym/python/isaacgym/gymtorch.py:61-106).
+ * shape must hold 4 entries. */
+int emloco_tensor(emloco_sim* sim, int which, void** d_ptr, int64_t* shape, int32_t* ndim, int32_t* dtype);
+
+/* Terrain height field: Terrain.heightsamples (humanoid_pedestrain_terrain.py:1166-1171), int16, first dim x. */
+int emloco_set_height_field(emloco_sim* sim, const int16_t* h_samples, int32_t rows, int32_t cols);
+
+/* gym.set_dof_position_target_tensor (humanoid.py:1202): copies [N,69] targets into the sim. */
+int emloco_set_pd_targets(emloco_sim* sim, const float* d_targets, void* stream);
+
+/* gym.simulate + fetch_results (base_task.py:795,258): `substeps` articulated-body sub-steps of
+ * sim_dt/substeps using the stored PD targets; refreshes every state tensor. */
+int emloco_simulate(emloco_sim* sim, void* stream);
+
+/* gym.set_actor_root_state_tensor_indexed + set_dof_state_tensor_indexed (humanoid.py:470-475):
+ * re-reads root_state / dof_state for the listed envs (the caller has written them through the
+ * aliases), rebuilds joint rotations and rigid-body state by forward kinematics, zeroes contact
+ * and DOF force.  d_env_ids == NULL means all envs. */
+int emloco_reset_indexed(emloco_sim* sim, const int32_t* d_env_ids, int32_t n, void* stream);
+
+/* post_physics_step (humanoid_amp.py:139-157 -> humanoid.py:1211-1232 -> humanoid_amp_task.py:62-86):
+ * progress += advance_progress; obs, flip obs, reward, reset/terminate, AMP obs ring.  One fused kernel. */
+int emloco_post_step(emloco_sim* sim, int32_t advance_progress, void* stream);
+
+/* BaseTask.step (base_task.py:245-265): pre_physics_step (actions -> PD targets, humanoid.py:1184-1209),
+ * control_freq_inv x simulate, post_physics_step.  d_actions [N,69]. */
+int emloco_step(emloco_sim* sim, const float* d_actions, void* stream);
+
+/* Same through HOST buffers (the vec-env call a CPU-side user makes, run.py:148-160): copies
+ * actions in, steps, copies obs/rew/reset out, synchronises.  Any output pointer may be NULL. */
+int emloco_step_host(emloco_sim* sim, const float* h_actions, float* h_obs, float* h_rew,
+                     int64_t* h_reset, float* h_amp_obs);
+
+/* ---- LocoVal: ValuePoseNet (pacer/pacer/learning/value_pose_net.py:10-159) ----
+ * weights: fc1.weight[H1,IN] fc1.bias[H1] fc2.weight[H2,H1] fc2.bias[H2] fc3.weight[1,H2] fc3.bias[1]
+ * packed in that order (state-dict order of `_network.fc{1,2,3}.{weight,bias}`).
+ * flags: bit0 use_pose, bit1 use_vel, bit2 hide_toe, bit3 hide_spine, bit4 normalize,
+ *        bit5 write the rotated/zeroed pose back into d_pose (the reference's in-place side effect, :97,:141-144).
+ * traj [B,T,traj_stride] (only x,y read; T = 13 or 5), pose [B,24,3], vel [B,2], value [B]. */
+int emloco_locoval_forward(const float* d_traj, int32_t traj_stride, int32_t num_waypoints, float* d_pose,
+                           const float* d_vel, const float* d_weights, float* d_value, int64_t batch,
+                           int32_t flags, void* stream);
+/* d value / d traj for the EmLoco loss (calc_embodied_motion_loss :151-159; gradient flows through LocoVal
+ * into the predictor, social-transmotion/train_jta.py:288-308).  grad_value [B] -> grad_traj [B,T,traj_stride].
+ * The pose/vel passed must be the ORIGINAL (un-rotated) inputs of the forward call. */
+int emloco_locoval_backward(const float* d_traj, int32_t traj_stride, int32_t num_waypoints, const float* d_pose,
+                            const float* d_vel, const float* d_weights, const float* d_grad_value,
+                            float* d_grad_traj, int64_t batch, int32_t flags, void* stream);
+/* Host-buffer scoring (the batch-of-1 filter loop of social-transmotion/evaluate_jta.py:298-302, batched). */
+int emloco_locoval_forward_host(const float* h_traj, int32_t traj_stride, int32_t num_waypoints, const float* h_pose,
+                                const float* h_vel, const float* h_weights, float* h_value, int64_t batch,
+                                int32_t flags, int32_t device);
+/* plausibl/test_value_mlp.py:24-113 MLP.forward: 24 -> 12 -> 6 -> 1, no sigmoid.  x [B,24], packed weights as above. */
+int emloco_plausibl_mlp_forward(const float* d_x, const float* d_weights, float* d_value, int64_t batch, void* stream);
+
+/* ---- GAE: discount_values (pacer/pacer/learning/common_agent.py:573-587) ----
+ * all [T,N] row-major f32; adv and ret ("mb_returns = mb_advs + mb_values", amp_continuous_value.py:163) written. */
+int emloco_gae(const float* d_dones, const float* d_values, const float* d_rewards, const float* d_next_values,
+               float* d_adv, float* d_ret, int32_t T, int64_t N, float gamma, float tau, void* stream);
+
+/* ---- dense layers of the actor / critic / discriminator (network builders) ----
+ * y[M,N] = act( norm(x)[M,K] @ W[N,K]^T + b ), optional input normalisation
+ * clamp((x-mean)/sqrt(var+eps),+-5) (utils/running_mean_std.py:60-84) folded into the operand load.
+ * x row stride ldx, y row stride ldy (lets callers concatenate without a copy).  relu: 0/1.
+ * mean/var may be NULL.  fp32 in/out; products in TF32 on the tensor cores when `use_tensor_cores`, else fp32 FMA. */
+int emloco_linear(const float* d_x, int64_t ldx, const float* d_w, const float* d_b, float* d_y, int64_t ldy,
+                  int64_t M, int32_t N, int32_t K, const float* d_mean, const float* d_var, float eps,
+                  int32_t relu, int32_t use_tensor_cores, void* stream);
+
+int emloco_sync(emloco_sim* sim);
+const char* emloco_last_error(void);
+const char* emloco_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMLOCO_H */

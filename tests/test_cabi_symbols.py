@@ -1,0 +1,69 @@
+"""CPU: the C-ABI library loads and exports every symbol include/emloco.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "emloco.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(emloco_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_declares_expected_entry_points():
+    names = _declared()
+    for must in ("emloco_create", "emloco_step", "emloco_post_step", "emloco_simulate", "emloco_reset_indexed",
+                 "emloco_locoval_forward", "emloco_locoval_backward", "emloco_gae", "emloco_linear", "emloco_tensor"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    from emloco_b200 import _lib, build
+    build.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in _declared():
+        assert hasattr(lib, name), f"{name} declared in emloco.h but not exported"
+    assert sorted(_lib.SYMBOLS) == _declared()
+
+
+def test_struct_layouts_match_header_sizes():
+    from emloco_b200 import _lib
+    # emloco_cfg: 18 4-byte fields + 8 reserved ints; emloco_model: arrays as declared
+    assert ctypes.sizeof(_lib.Cfg) == (18 + 8) * 4
+    nb, nd = 24, 69
+    assert ctypes.sizeof(_lib.Model) == 4 * (nb + 3 * nb + nb + 3 * nb + 6 * nb + 3 * nd + nb + 3 * nb + 3 * nb + nb + 2 * nd)
+
+
+def test_product_fails_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from emloco_b200 import _lib
+    from emloco_b200.sim import EmlocoSim
+    with pytest.raises(_lib.EmlocoError):
+        EmlocoSim(4)
+    from emloco_b200.value_pose_net import ValuePoseNet
+    net = ValuePoseNet(True, True)
+    with pytest.raises(_lib.EmlocoError):
+        net(torch.zeros(2, 13, 2), torch.zeros(2, 24, 3), torch.zeros(2, 2))
+
+
+def test_state_dict_keys_match_reference_contract():
+    from emloco_b200.value_pose_net import ValuePoseNet
+    net = ValuePoseNet(True, True)
+    assert list(net.state_dict().keys()) == [f"_network.fc{i}.{p}" for i in (1, 2, 3) for p in ("weight", "bias")]
+    assert net._network.fc1.weight.shape == (49, 100) and net._network.fc2.weight.shape == (24, 49)
+    assert sum(p.numel() for p in net.parameters()) == 6174
+
+
+def test_mjcf_model_table():
+    from emloco_b200.model import build_model_arrays
+    a = build_model_arrays()
+    assert len(a["names"]) == 24 and a["kp"].shape == (69,)
+    assert a["names"][13] == "Head" and a["names"][7] == "R_Ankle"
+    assert abs(a["pd_scale"][4] - 5) < 1e-6 and abs(a["pd_scale"][16] - 5) < 1e-6
+    assert 60 < a["total_mass"] < 90

@@ -1,0 +1,211 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the committed golden fixtures (produced
+by the REFERENCE's own functions) and against the oracle on seeded inputs.
+Tolerances: north_star says 1e-3 relative on floats, bit-exact on reset masks / indices."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-3, 2e-5
+
+
+def _sim(N, **kw):
+    from emloco_b200.sim import EmlocoSim
+    return EmlocoSim(N, **kw)
+
+
+def _load_state(sim, st):
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    N = st["rb"].shape[0]
+    sim.rb_state.copy_(T(st["rb"]).reshape(N * 24, 13))
+    sim.dof_state.copy_(T(st["dof_state"]).reshape(N * 69, 2))
+    sim.contact.copy_(T(st["contact"]).reshape(N * 24, 3))
+    sim.dof_force.copy_(T(st["dof_force"]).reshape(-1))
+    sim.progress.copy_(T(st["progress"]))
+    sim.betas.copy_(T(st["betas"]))
+    sim.traj_verts.copy_(T(st["verts"]))
+    sim.amp_obs.copy_(T(st["amp_buf"]))
+    sim.set_height_field(st["height_samples"])
+
+
+def _run_post(st):
+    N = st["rb"].shape[0]
+    sim = _sim(N)
+    _load_state(sim, st)
+    sim.post_step(advance_progress=False)
+    torch.cuda.synchronize()
+    out = dict(obs=sim.obs, flip_obs=sim.flip_obs, rew=sim.rew, reward_raw=sim.rew_raw, reset=sim.reset,
+               terminate=sim.terminate, amp_obs=sim.amp_obs.reshape(N, -1))
+    out = {k: v.cpu().numpy().copy() for k, v in out.items()}
+    sim.close()
+    return out
+
+
+def _height_mismatch_ok(got, want, max_frac=2e-3):
+    """Height samples are a discontinuous lookup: an ulp difference in sin/cos can move a grid point across a
+    cell edge.  Allow a tiny fraction of mismatching samples, everything else to tolerance."""
+    bad = ~np.isclose(got, want, rtol=RTOL, atol=ATOL)
+    return bad.mean() <= max_frac
+
+
+@pytest.mark.parametrize("name", ["post_step_rough.npz", "post_step_flat.npz"])
+def test_post_step_matches_reference_golden(name):
+    g = np.load(os.path.join(GOLDEN, name))
+    st = {k[3:]: g[k] for k in g.files if k.startswith("in_")}
+    out = _run_post(st)
+    for k in ("rew", "reward_raw", "amp_obs"):
+        np.testing.assert_allclose(out[k], g["out_" + k], rtol=RTOL, atol=ATOL, err_msg=k)
+    for k in ("obs", "flip_obs"):
+        np.testing.assert_allclose(out[k][:, :398], g["out_" + k][:, :398], rtol=RTOL, atol=ATOL, err_msg=k)
+        assert _height_mismatch_ok(out[k][:, 398:], g["out_" + k][:, 398:]), k + " heights"
+    for k in ("reset", "terminate"):
+        assert out[k].dtype == np.int64
+        np.testing.assert_array_equal(out[k], g["out_" + k])
+
+
+@pytest.mark.parametrize("N,rough", [(1, True), (257, True), (4096, False)])
+def test_post_step_matches_oracle(N, rough):
+    from oracle import oracle_np as O
+    from oracle.make_golden import synth_state
+    st = synth_state(N, seed=100 + N, map_shape=(700, 700), rough=rough)
+    out = _run_post(st)
+    n = min(N, 512)     # the numpy oracle is the slow side; full-size properties are checked below
+    sub = {k: (v[:n] if k != "height_samples" else v) for k, v in st.items()}
+    ref = O.post_physics_step(sub["rb"], sub["dof_state"], sub["contact"], sub["dof_force"], sub["progress"],
+                              sub["verts"], sub["betas"], sub["height_samples"], sub["amp_buf"])
+    for k in ("rew", "reward_raw", "amp_obs"):
+        np.testing.assert_allclose(out[k][:n], ref[k], rtol=RTOL, atol=ATOL, err_msg=k)
+    for k in ("obs", "flip_obs"):
+        np.testing.assert_allclose(out[k][:n, :398], ref[k][:, :398], rtol=RTOL, atol=ATOL, err_msg=k)
+        assert _height_mismatch_ok(out[k][:n, 398:], ref[k][:, 398:]), k
+    np.testing.assert_array_equal(out["reset"][:n], ref["reset"])
+    np.testing.assert_array_equal(out["terminate"][:n], ref["terminate"])
+    # size-independent properties at full size
+    obs, flip = out["obs"], out["flip_obs"]
+    np.testing.assert_array_equal(flip[:, 357:368], obs[:, 357:368])                       # shape params untouched
+    np.testing.assert_array_equal(flip[:, 368:398:2], obs[:, 368:398:2])                   # traj x kept
+    np.testing.assert_array_equal(flip[:, 369:398:2], -obs[:, 369:398:2])                  # traj y negated
+    hm = obs[:, 398:].reshape(N, 32, 32)
+    np.testing.assert_array_equal(flip[:, 398:].reshape(N, 32, 32), hm[:, :, ::-1])        # heightmap flipped
+    amp = out["amp_obs"].reshape(N, 15, 206)
+    np.testing.assert_array_equal(amp[:, 1:], st["amp_buf"][:, :-1])                       # ring shifted by one
+    assert set(np.unique(out["reset"])) <= {0, 1}
+    assert np.all(out["reset"] >= out["terminate"])
+
+
+def test_locoval_matches_reference_golden():
+    from emloco_b200.value_pose_net import ValuePoseNet
+    g = np.load(os.path.join(GOLDEN, "locoval.npz"))
+    net = ValuePoseNet(True, True).cuda().eval()
+    net.load_state_dict({k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("w_")})
+    traj = torch.from_numpy(g["traj"]).cuda().requires_grad_(True)
+    pose = torch.from_numpy(g["pose"]).cuda()
+    vel = torch.from_numpy(g["vel"]).cuda()
+    value, loss = net.calc_embodied_motion_loss(traj, pose, vel)
+    loss.backward()
+    np.testing.assert_allclose(value.detach().cpu().numpy(), g["out_value"], rtol=RTOL, atol=1e-6)
+    np.testing.assert_allclose(loss.item(), g["out_loss"], rtol=RTOL)
+    np.testing.assert_allclose(traj.grad.cpu().numpy(), g["out_grad_traj"], rtol=2e-3, atol=1e-7)
+    # the reference rotates / zeroes the caller's pose in place; so do we
+    np.testing.assert_allclose(pose.cpu().numpy(), g["out_pose_after"], rtol=RTOL, atol=1e-6)
+
+
+@pytest.mark.parametrize("use_pose,use_vel,vru", [(True, True, False), (False, False, False), (False, True, False),
+                                                  (True, False, False), (True, True, True)])
+def test_locoval_variants_match_oracle(use_pose, use_vel, vru):
+    from emloco_b200.value_pose_net import ValuePoseNet
+    from oracle import oracle_np as O
+    torch.manual_seed(0)
+    T = 5 if vru else 13
+    B = 1000
+    net = ValuePoseNet(use_pose, use_vel, vru=vru, mutate_pose=False).cuda().eval()
+    with torch.no_grad():
+        for m in net._network:
+            if hasattr(m, "bias"):
+                m.bias.uniform_(-0.2, 0.2)
+    traj = torch.randn(B, T, 3).cuda(); traj[:, 0] = 0
+    pose = torch.randn(B, 24, 3).cuda() * 0.3
+    vel = torch.randn(B, 2).cuda()
+    v = net(traj, pose if use_pose else None, vel if use_vel else None).cpu().numpy()
+    # oracle (full variant only has a dedicated function; build the others from its pieces)
+    W = {k: (getattr(net._network, k).weight.detach().cpu().numpy(), getattr(net._network, k).bias.detach().cpu().numpy())
+         for k in ("fc1", "fc2", "fc3")}
+    tr, pr, vr, _ = O.locoval_normalize(traj.cpu().numpy()[..., :2], pose.cpu().numpy(), vel.cpu().numpy())
+    pr[:, [4, 8]] = 0; pr[:, [9, 10, 11]] = 0
+    feats = [tr.reshape(B, -1)] + ([pr.reshape(B, 72)] if use_pose else []) + ([vr] if use_vel else [])
+    x = np.concatenate(feats, -1).astype(np.float32)
+    h = np.maximum(x @ W["fc1"][0].T + W["fc1"][1], 0); h = np.maximum(h @ W["fc2"][0].T + W["fc2"][1], 0)
+    ref = 1 / (1 + np.exp(-(h @ W["fc3"][0].T + W["fc3"][1])))
+    np.testing.assert_allclose(v, ref, rtol=RTOL, atol=1e-6)
+
+
+def test_locoval_edge_cases_and_full_size():
+    from emloco_b200.value_pose_net import ValuePoseNet, score_host
+    net = ValuePoseNet(True, True).cuda().eval()
+    # empty batch
+    out = net(torch.zeros(0, 13, 2).cuda(), torch.zeros(0, 24, 3).cuda(), torch.zeros(0, 2).cuda())
+    assert out.shape == (0, 1)
+    # batch of one (the evaluate_jta.py filter loop shape), first step exactly along +y (x == 0 -> epsilon branch)
+    t1 = torch.zeros(1, 13, 2).cuda(); t1[0, :, 1] = torch.arange(13).float() * 0.4
+    v1 = net(t1, torch.zeros(1, 24, 3).cuda(), torch.zeros(1, 2).cuda())
+    assert torch.isfinite(v1).all() and 0 < v1.item() < 1
+    # 1M batch: heading invariance (rotating traj+pose+vel together leaves the score unchanged) - a
+    # size-independent property of the normalisation
+    B = 1 << 20
+    g = torch.Generator(device="cuda").manual_seed(1)
+    traj = torch.randn(B, 13, 2, device="cuda", generator=g).cumsum(1) * 0.3; traj -= traj[:, :1].clone()
+    pose = torch.randn(B, 24, 3, device="cuda", generator=g) * 0.3
+    vel = (traj[:, 1] - traj[:, 0]) * 2.5
+    net2 = ValuePoseNet(True, True, mutate_pose=False).cuda().eval()
+    a = net2(traj, pose, vel)
+    th = torch.rand(B, device="cuda", generator=g) * 6.28
+    c, s = th.cos(), th.sin()
+    rot = lambda p: torch.stack([p[..., 0] * c[:, None] - p[..., 1] * s[:, None], p[..., 0] * s[:, None] + p[..., 1] * c[:, None]], -1)
+    pose_r = pose.clone(); pose_r[..., :2] = rot(pose[..., :2])
+    b = net2(rot(traj).contiguous(), pose_r, rot(vel[:, None])[:, 0].contiguous())
+    assert (a - b).abs().max().item() < 2e-4
+    # host-buffer entry point agrees with the device one
+    n = 5000
+    sd = {k: v.detach().cpu().numpy() for k, v in net2.state_dict().items()}
+    h = score_host(traj[:n].cpu().numpy(), pose[:n].cpu().numpy(), vel[:n].cpu().numpy(), sd)
+    np.testing.assert_allclose(h, a[:n, 0].cpu().numpy(), rtol=1e-6, atol=1e-7)
+
+
+def test_gae_matches_reference_golden_and_oracle():
+    from emloco_b200.sim import gae
+    from oracle import oracle_np as O
+    g = np.load(os.path.join(GOLDEN, "gae.npz"))
+    T = lambda a: torch.from_numpy(a).cuda()
+    adv, ret = gae(T(g["dones"]), T(g["values"]), T(g["rewards"]), T(g["next_values"]))
+    np.testing.assert_allclose(adv.cpu().numpy(), g["adv"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(ret.cpu().numpy(), g["adv"] + g["values"], rtol=1e-5, atol=1e-6)
+    rng = np.random.default_rng(0)
+    Th, N = 32, 4096
+    d = (rng.uniform(size=(Th, N)) < 0.03).astype(np.float32)
+    v, nv, r = (rng.normal(size=(Th, N, 1)).astype(np.float32) for _ in range(3))
+    adv, _ = gae(T(d), T(v), T(r), T(nv))
+    np.testing.assert_allclose(adv.cpu().numpy(), O.discount_values(d, v, r, nv), rtol=1e-5, atol=1e-5)
+    # ragged: a single env, horizon 1
+    a1, _ = gae(T(d[:1, :1]), T(v[:1, :1]), T(r[:1, :1]), T(nv[:1, :1]))
+    np.testing.assert_allclose(a1.cpu().numpy(), r[:1, :1] + 0.99 * nv[:1, :1] - v[:1, :1], rtol=1e-6)
+
+
+def test_linear_fma_matches_oracle():
+    from emloco_b200.sim import linear
+    from oracle import oracle_np as O
+    rng = np.random.default_rng(1)
+    M, K, N = 300, 1054, 512
+    x = rng.normal(0, 2, (M, 1422)).astype(np.float32)
+    w = (rng.normal(0, 1, (N, K)) / np.sqrt(K)).astype(np.float32)
+    b = rng.normal(0, 0.1, N).astype(np.float32)
+    mean = rng.normal(0, 1, 1422); var = rng.uniform(0.1, 4, 1422)
+    xt = torch.from_numpy(x).cuda()
+    y = linear(xt[:, 368:], torch.from_numpy(w).cuda(), torch.from_numpy(b).cuda(), relu=True,
+               mean=torch.from_numpy(mean[368:]).cuda(), var=torch.from_numpy(var[368:]).cuda())
+    ref = np.maximum(O.rms_normalize(x, mean, var)[:, 368:] @ w.T + b, 0)
+    np.testing.assert_allclose(y.cpu().numpy(), ref, rtol=1e-4, atol=1e-4)

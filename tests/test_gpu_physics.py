@@ -1,0 +1,133 @@
+"""GPU: physics kernel vs its fp64 CPU restatement (oracle/physics_oracle.c) on identical inputs, plus
+physical invariants.  PARITY AGAINST PhysX IS UNPINNED (the reference ships neither binaries nor tests for
+the physics step) - these tests pin the kernel to the builder's own algorithm."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup():
+    from emloco_b200.model import build_model_arrays, rest_root_height
+    from oracle import physics_oracle as PO
+    A = build_model_arrays()
+    M = PO.make_model(A["parent"], A["offset"], A["mass"], A["com"], A["inertia6"], A["kp_joint"], A["kd_joint"],
+                      A["arm_joint"], A["geom_type"], A["geom_a"], A["geom_b"], A["geom_r"])
+    return A, M, PO, rest_root_height(A)
+
+
+def _random_state(N, seed, z_lo, z_hi, vel=1.0, pose=0.4):
+    rng = np.random.default_rng(seed)
+    root = np.zeros((N, 13))
+    root[:, 0:2] = rng.uniform(52, 56, (N, 2))
+    root[:, 2] = rng.uniform(z_lo, z_hi, N)
+    yaw = rng.uniform(-np.pi, np.pi, N)
+    tilt = rng.normal(0, 0.05, (N, 2))
+    q = np.stack([tilt[:, 0], tilt[:, 1], np.sin(yaw / 2), np.cos(yaw / 2)], -1)
+    root[:, 3:7] = q / np.linalg.norm(q, axis=-1, keepdims=True)
+    root[:, 7:13] = rng.normal(0, vel, (N, 6))
+    dof_pos = rng.uniform(-pose, pose, (N, 69))
+    dof_vel = rng.normal(0, vel, (N, 69))
+    actions = rng.uniform(-0.3, 0.3, (N, 69))
+    return root, dof_pos, dof_vel, actions
+
+
+def _gpu_step(N, root, dof_pos, dof_vel, actions, steps=1):
+    from emloco_b200.sim import EmlocoSim
+    sim = EmlocoSim(N)
+    sim.root_state.copy_(torch.from_numpy(root).float().cuda())
+    ds = np.stack([dof_pos, dof_vel], -1).reshape(N * 69, 2)
+    sim.dof_state.copy_(torch.from_numpy(ds).float().cuda())
+    sim.reset_indexed(None)
+    act = torch.from_numpy(actions).float().cuda().contiguous()
+    for _ in range(steps):
+        sim.step(act)
+    torch.cuda.synchronize()
+    out = dict(root=sim.root_state, rb=sim.rb_state.reshape(N, 24, 13), dof=sim.dof_state.reshape(N, 69, 2),
+               contact=sim.contact.reshape(N, 24, 3), dof_force=sim.dof_force.reshape(N, 69), pd=sim.pd_target)
+    out = {k: v.cpu().numpy().astype(np.float64) for k, v in out.items()}
+    sim.close()
+    return out
+
+
+def _oracle_step(A, M, PO, root, dof_pos, dof_vel, actions, steps=1):
+    from oracle import oracle_np as O
+    N = root.shape[0]
+    cfg = PO.make_cfg(1.0 / 120.0)
+    r = root.astype(np.float32).astype(np.float64).copy()
+    jq = PO.expmap_to_quat(dof_pos.astype(np.float32).astype(np.float64)).reshape(N, 23, 4).copy()
+    jw = dof_vel.astype(np.float32).astype(np.float64).copy()
+    tgt = O.action_to_pd_targets(actions.astype(np.float32), A["pd_offset"], A["pd_scale"]).astype(np.float64)
+    for _ in range(steps):
+        rb, dp, ct, df = PO.step(M, cfg, 4, r, jq, jw, tgt)
+    return dict(root=r, rb=rb, dof=np.stack([dp, jw], -1), contact=ct, dof_force=df, pd=tgt)
+
+
+@pytest.mark.parametrize("case,z_lo,z_hi", [("airborne", 2.0, 3.0), ("contact", 0.80, 0.93)])
+def test_single_env_step_matches_fp64_oracle(case, z_lo, z_hi):
+    A, M, PO, h0 = _setup()
+    N = 256
+    root, dof_pos, dof_vel, actions = _random_state(N, 7 if case == "airborne" else 8, z_lo, z_hi)
+    g = _gpu_step(N, root, dof_pos, dof_vel, actions)
+    o = _oracle_step(A, M, PO, root, dof_pos, dof_vel, actions)
+    np.testing.assert_allclose(g["pd"], o["pd"], rtol=1e-6, atol=1e-6)
+    # 1e-3 relative (north_star) with an absolute floor scaled to each quantity's magnitude
+    np.testing.assert_allclose(g["root"], o["root"], rtol=1e-3, atol=2e-3)
+    np.testing.assert_allclose(g["rb"], o["rb"], rtol=1e-3, atol=5e-3)
+    np.testing.assert_allclose(g["dof"], o["dof"], rtol=1e-3, atol=5e-3)
+    np.testing.assert_allclose(g["dof_force"], o["dof_force"], rtol=2e-3, atol=0.5)
+    np.testing.assert_allclose(g["contact"], o["contact"], rtol=5e-3, atol=2.0)
+    if case == "contact":
+        assert (np.abs(o["contact"]).sum(axis=(1, 2)) > 0).mean() > 0.5, "test must exercise contacts"
+
+
+def test_free_fall_and_rest_pose_invariants():
+    A, M, PO, h0 = _setup()
+    N = 64
+    root = np.zeros((N, 13)); root[:, 6] = 1; root[:, 0:2] = 54.0
+    # free fall from 5 m, zero action: semi-implicit Euler gives z = z0 - g/2 * t * (t + dt)
+    root[:, 2] = 5.0
+    z = np.zeros((N, 69))
+    g = _gpu_step(N, root, z, z, z, steps=10)
+    t, dt = 10 * 4 / 120.0, 1 / 120.0
+    np.testing.assert_allclose(g["root"][:, 2], 5.0 - 0.5 * 9.81 * t * (t + dt), rtol=1e-4)
+    np.testing.assert_allclose(g["root"][:, 9], -9.81 * t, rtol=1e-4)
+    assert np.abs(g["dof"][..., 0]).max() < 1e-3            # joints stay at the PD target
+    assert np.abs(g["contact"]).max() == 0
+    # standing on flat ground for 1 s: stays upright, ground carries the weight
+    root[:, 2] = h0 + 0.005
+    g = _gpu_step(N, root, z, z, z, steps=30)
+    assert np.all(g["root"][:, 2] > h0 - 0.05)
+    np.testing.assert_allclose(g["contact"][:, :, 2].sum(1), A["total_mass"] * 9.81, rtol=0.05)
+    assert np.all(np.isfinite(g["rb"]))
+
+
+def test_rollout_stays_finite_with_random_actions():
+    A, M, PO, h0 = _setup()
+    N = 512
+    root, dof_pos, dof_vel, actions = _random_state(N, 3, h0, h0 + 0.1, vel=0.5, pose=0.2)
+    actions = np.random.default_rng(0).uniform(-1, 1, (N, 69))
+    g = _gpu_step(N, root, dof_pos, dof_vel, actions, steps=60)
+    assert np.all(np.isfinite(g["rb"])) and np.all(np.isfinite(g["dof"]))
+    assert np.abs(g["rb"][..., 0:3] - g["rb"][:, :1, 0:3]).max() < 2.5   # bodies stay attached
+    assert np.abs(g["dof"][..., 1]).max() <= 100.0 * np.sqrt(3) + 1e-3  # max_ang_vel clamp
+
+
+def test_reset_indexed_only_touches_listed_envs():
+    from emloco_b200.sim import EmlocoSim
+    N = 16
+    sim = EmlocoSim(N)
+    sim.root_state[:, 2] = 1.0
+    sim.reset_indexed(None)
+    torch.cuda.synchronize()
+    before = sim.rb_state.clone()
+    sim.root_state[:, 0] = 3.0
+    sim.dof_state.view(N, 69, 2)[:, 3, 0] = 0.5
+    sim.reset_indexed(torch.tensor([2, 5]))
+    torch.cuda.synchronize()
+    after = sim.rb_state.view(N, 24, 13)
+    changed = (after != before.view(N, 24, 13)).flatten(1).any(1).cpu().numpy()
+    assert changed.tolist() == [i in (2, 5) for i in range(N)]
+    assert abs(after[2, 0, 0].item() - 3.0) < 1e-6
+    sim.close()
