@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""Benchmark of the EmLoco rollout hot path (BASELINE.json: env-steps/s at 4096 humanoid envs per B200).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--envs 4096] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one control step of `AMPValueAgent.play_steps` (pacer/pacer/learning/amp_continuous_value.py:44-118) for all
+envs of every rank: device-side reset of done envs, actor/critic/task-value forward + action sampling, physics (4 sub-steps)
++ fused post-step, critic on the next obs, discriminator -> AMP reward, bookkeeping, LocoVal scoring; and once every 32
+steps the post-horizon discriminator pass over the stored [32,N,3090] AMP observations + reward combine + GAE (:150-163).
+Workload = BASELINE.json configs[1] (4096 envs on one B200; the other configs are parity-test sizes).  Envs are rank-local
+(weak scaling, no data-path collective).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# algorithmic bytes / flops per unit (restated in DESIGN.md "Measurement")
+BYTES_PHYSICS = 3296          # per env-step: actions + reduced state in, reduced + rigid-body + contact + dof force out
+BYTES_POST = 28264            # per env-step: state/contact/force/verts in, obs + flip obs + AMP ring shift + rewards out
+# MACs per env actually executed per step: policy 7.493 M (task MLP evaluated once, not twice as the reference does),
+# next-obs critic 4.047 M, discriminator 3.689 M (the post-horizon discriminator pass is outside the step segments)
+FLOP_NETS_STEP = 2 * (7.493154e6 + 4.046848e6 + 3.688960e6)
+BYTES_LOCOVAL = 404           # per score
+HORIZON = 32
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# =====================================================================================================
+# CPU arm: the oracle port on the host cores (the Isaac Gym CPU pipeline itself cannot run here)
+# =====================================================================================================
+def cpu_rollout_rate(envs, steps, warmup, seed=0, budget_s=None):
+    """env-steps/s of oracle/cpu_rollout.py on `envs` envs; stops early when `budget_s` is exceeded."""
+    import numpy as np
+    import torch
+    from emloco_b200.model import build_model_arrays, rest_root_height
+    from emloco_b200.policy import AMPSeptValueNetwork
+    from emloco_b200.synthetic import synthetic_env_state
+    from oracle.cpu_rollout import CpuRollout, weights_from_state_dict
+    A = build_model_arrays()
+    torch.manual_seed(seed)
+    P, D = weights_from_state_dict(AMPSeptValueNetwork().state_dict())
+    R = CpuRollout(A, synthetic_env_state(envs, seed, rest_root_height(A)), P, D)
+    rng = np.random.default_rng(seed)
+    for _ in range(warmup):
+        R.step(rng.standard_normal((envs, 69)).astype(np.float32))
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        R.step(rng.standard_normal((envs, 69)).astype(np.float32))
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return envs * done / dt, done, dt
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    envs = min(args.envs, 256)          # bounded sample of the 4096-env workload: ~0.3-1 s of host work per step
+    rate, done, dt = cpu_rollout_rate(envs, args.steps, min(args.warmup, 2), budget_s=150.0)
+    sample = f"{envs} of {args.envs} envs per step, {done} steps in {dt:.1f} s (oracle port: fp64 C physics + numpy nets/post-step)"
+    print(json.dumps({
+        "impl": "reference", "metric": "env_steps_per_sec", "value": rate, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": done, "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * dt / max(done, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.envs} SMPL-humanoid envs per GPU, PACER AMP rollout step + LocoVal scoring (configs[1])",
+                   "horizon": HORIZON},
+        "cpu_baseline": {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+
+
+# =====================================================================================================
+# GPU arm
+# =====================================================================================================
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from emloco_b200 import _lib
+    from emloco_b200.rollout import Rollout
+    from emloco_b200.synthetic import synthetic_locoval_batch
+    from emloco_b200.value_pose_net import ValuePoseNet
+
+    N, K, W = args.envs, args.steps, args.warmup
+    R = Rollout(N, device=local_rank, seed=args.seed + rank, tensor_cores=args.tensor_cores, recompute_disc=not args.dedup_disc)
+    pk = peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    step_i = [0]
+
+    def one_step():
+        n = step_i[0] % HORIZON
+        R.step(n)
+        if n == HORIZON - 1:
+            R.finish()
+        step_i[0] += 1
+
+    for _ in range(W):
+        one_step()
+    step_i[0] = 0
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    R.enable_segment_timing(True)
+    l0 = _lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        one_step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count - l0
+    seg, _ = R.segment_ms()
+    R.enable_segment_timing(False)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * N * K / (ms * 1e-3)
+
+    # ---- end to end: the vec-env / agent boundary with HOST buffers (rl_device = cpu): every step copies the step's
+    # inputs (obs for the nets, policy noise) from pinned host memory and reads the results back (next obs, rewards,
+    # dones, actions, neglogp, values) ----
+    pin = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt).pin_memory()
+    h_obs, h_noise = pin(N, 1422), pin(N, 69).normal_()
+    h_out = dict(obs=pin(N, 1422), rew=pin(N), reset=pin(N, dt=torch.int64), actions=pin(N, 69), neglogp=pin(N), values=pin(N, 1))
+    h_obs.copy_(R.sim.obs)
+    d_obs_in = torch.empty(N, 1422, device="cuda")
+    Ke = max(HORIZON, min(K, 2 * HORIZON))
+
+    def e2e_step(i):
+        n = i % HORIZON
+        d_obs_in.copy_(h_obs, non_blocking=True)
+        R.noise.copy_(h_noise, non_blocking=True)
+        R.sim.obs.copy_(d_obs_in)                       # the policy reads the obs the host handed over
+        R.step(n, noise=R.noise)
+        if n == HORIZON - 1:
+            R.finish()
+        h_out["obs"].copy_(R.sim.obs, non_blocking=True); h_out["rew"].copy_(R.sim.rew, non_blocking=True)
+        h_out["reset"].copy_(R.sim.reset, non_blocking=True); h_out["actions"].copy_(R.mb["actions"][n], non_blocking=True)
+        h_out["neglogp"].copy_(R.mb["neglogpacs"][n], non_blocking=True); h_out["values"].copy_(R.mb["values"][n], non_blocking=True)
+        torch.cuda.current_stream().synchronize()       # the host consumes the results before issuing the next step
+        h_obs.copy_(h_out["obs"])
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    e0.record()
+    for i in range(Ke):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * N * Ke / (float(t.item()) * 1e-3)
+    h2d = h_obs.numel() * 4 + h_noise.numel() * 4
+    d2h = sum(v.numel() * v.element_size() for v in h_out.values())
+
+    out = None
+    if rank == 0:
+        # ---- LocoVal scores/s: 1M synthetic 12-step futures (configs[3]), device-resident ----
+        B = args.locoval_batch
+        traj, pose, vel = (torch.from_numpy(a).cuda() for a in synthetic_locoval_batch(B, seed=args.seed))
+        net = ValuePoseNet(True, True, mutate_pose=False).cuda().eval()
+        for _ in range(3):
+            net(traj, pose, vel)
+        torch.cuda.synchronize()
+        reps = 20
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        lv_ms = 0.0
+        for _ in range(reps):
+            flush.zero_()                               # L2 flush between timed launches (inputs are 404 MB, > L2 anyway)
+            e0.record(); net(traj, pose, vel); e1.record()
+            torch.cuda.synchronize()
+            lv_ms += e0.elapsed_time(e1)
+        lv_ms /= reps
+        lv_rate = B / (lv_ms * 1e-3)
+
+        # ---- rooflines from the live segment timings ----
+        nets_ms = seg["policy"] + seg["critic"] + seg["disc"]
+        kern = {
+            "physics": {"bound": "hbm", "ms": seg["physics"], "achieved": N * BYTES_PHYSICS / (seg["physics"] * 1e-3) / 1e9,
+                        "peak": pk["hbm"], "unit": "GB/s"},
+            "post_step": {"bound": "hbm", "ms": seg["post_step"], "achieved": N * BYTES_POST / (seg["post_step"] * 1e-3) / 1e9,
+                          "peak": pk["hbm"], "unit": "GB/s", "note": "segment includes the 50 MB AMP-obs experience-row copy"},
+            "nets": {"bound": "tensor", "ms": nets_ms, "achieved": N * FLOP_NETS_STEP / (nets_ms * 1e-3) / 1e12, "peak": pk["tf_sustained"], "unit": "TFLOP/s"},
+            "locoval": {"bound": "hbm", "ms": lv_ms, "achieved": B * BYTES_LOCOVAL / (lv_ms * 1e-3) / 1e9, "peak": pk["hbm"],
+                        "unit": "GB/s"},
+        }
+        for k in kern.values():
+            k["frac"] = k["achieved"] / k["peak"]
+        dom = max(("physics", "post_step", "nets"), key=lambda k: kern[k]["ms"])
+        roof = dict(kern[dom]); roof.update(kernel=dom, traffic=None, peak_source=pk["src"])
+
+        # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ----
+        cores = os.cpu_count() or 1
+        cpu = None
+        if not args.no_cpu_baseline:
+            rate, done, dt = cpu_rollout_rate(64, 40, 1, seed=args.seed, budget_s=20.0)
+            cpu = {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                   "sample": f"64 envs x {done} steps in {dt:.1f} s (configs[0] size; fp64 C physics oracle with OpenMP + numpy nets/post-step)"}
+
+        out = {
+            "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if not args.tensor_cores else "f32 (tf32/bf16x3 tensor-core products)", "data": "synthetic",
+            "config": {"workload": f"{N} SMPL-humanoid envs per GPU, PACER AMP rollout step + LocoVal scoring (configs[1])",
+                       "horizon": HORIZON, "l2": "per-step working set (obs 23 MB + AMP obs 2x51 MB + experience rows + 45 MB weights) exceeds the 126 MB L2; experience rows rotate over 32 slots",
+                       "post_horizon_disc_pass": "recomputed" if not args.dedup_disc else "reused per-step logits",
+                       "tensor_cores": bool(args.tensor_cores)},
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
+            "roofline": roof, "kernels": kern, "segments_ms": seg,
+            "locoval": {"metric": "locoval_scores_per_sec", "value": lv_rate, "unit": "scores/s", "batch": B, "ms": lv_ms},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(out), flush=True)
+    R.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=32)
+    ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--tensor-cores", dest="tensor_cores", action="store_true", default=False)
+    ap.add_argument("--dedup-disc", action="store_true", default=False)
+    ap.add_argument("--locoval-batch", type=int, default=1 << 20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -15,7 +15,8 @@ SYMBOLS = [
     "emloco_create", "emloco_destroy", "emloco_default_cfg", "emloco_tensor", "emloco_set_height_field",
     "emloco_set_pd_targets", "emloco_simulate", "emloco_reset_indexed", "emloco_post_step", "emloco_step",
     "emloco_step_host", "emloco_locoval_forward", "emloco_locoval_backward", "emloco_locoval_forward_host",
-    "emloco_plausibl_mlp_forward", "emloco_gae", "emloco_linear", "emloco_sync", "emloco_last_error", "emloco_version",
+    "emloco_plausibl_mlp_forward", "emloco_gae", "emloco_reset_done", "emloco_sample_actions",
+    "emloco_disc_reward", "emloco_rollout_record", "emloco_normalize", "emloco_physics_step", "emloco_linear", "emloco_sync", "emloco_last_error", "emloco_version",
 ]
 
 
@@ -30,6 +31,12 @@ class Cfg(C.Structure):
                 ("contact_offset", C.c_float), ("max_ang_vel", C.c_float), ("angular_damping", C.c_float),
                 ("episode_length", C.c_int32), ("power_coefficient", C.c_float), ("location_coefficient", C.c_float),
                 ("fail_dist", C.c_float), ("traj_sample_dt", C.c_float), ("reserved", C.c_int32 * 8)]
+
+
+class RolloutCfg(C.Structure):
+    _fields_ = [("inversion_penalty_scale", C.c_float), ("reward_scale", C.c_float), ("value_mean", C.c_float),
+                ("value_std", C.c_float), ("disc_reward_scale", C.c_float), ("gamma", C.c_float),
+                ("step_to_pred", C.c_int32), ("unnorm_value", C.c_int32)]
 
 
 class Model(C.Structure):
@@ -69,6 +76,7 @@ def load():
     lib.emloco_reset_indexed.argtypes = [vp, vp, i32, vp]
     lib.emloco_post_step.argtypes = [vp, i32, vp]
     lib.emloco_step.argtypes = [vp, vp, vp]
+    lib.emloco_physics_step.argtypes = [vp, vp, vp]
     lib.emloco_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.emloco_locoval_forward.argtypes = [vp, i32, i32, vp, vp, vp, vp, i64, i32, vp]
     lib.emloco_locoval_backward.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, i64, i32, vp]
@@ -76,6 +84,11 @@ def load():
     lib.emloco_plausibl_mlp_forward.argtypes = [vp, vp, vp, i64, vp]
     lib.emloco_gae.argtypes = [vp, vp, vp, vp, vp, vp, i32, i64, f32, f32, vp]
     lib.emloco_linear.argtypes = [vp, i64, vp, vp, vp, i64, i64, i32, i32, vp, vp, f32, i32, i32, vp]
+    lib.emloco_reset_done.argtypes = [vp, vp, vp, vp]
+    lib.emloco_sample_actions.argtypes = [vp, i64, vp, vp, vp, vp, i64, i32, vp]
+    lib.emloco_disc_reward.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, vp]
+    lib.emloco_rollout_record.argtypes = [C.POINTER(RolloutCfg), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
+    lib.emloco_normalize.argtypes = [vp, i64, vp, i64, i64, i32, vp, vp, f32, vp]
     lib.emloco_sync.argtypes = [vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
@@ -85,7 +98,18 @@ def load():
     return lib
 
 
+# kernels launched per successful ABI call (the bench's `gpu_launches` claim is counted here, not estimated)
+LAUNCHES = {"emloco_step": 2, "emloco_physics_step": 1, "emloco_post_step": 1, "emloco_simulate": 1, "emloco_reset_done": 2,
+            "emloco_reset_indexed": 1, "emloco_linear": 1, "emloco_normalize": 1, "emloco_sample_actions": 1,
+            "emloco_disc_reward": 1, "emloco_rollout_record": 1, "emloco_gae": 1, "emloco_locoval_forward": 1,
+            "emloco_locoval_backward": 1, "emloco_plausibl_mlp_forward": 1, "emloco_step_host": 2,
+            "emloco_locoval_forward_host": 1}
+launch_count = 0
+
+
 def check(rc, what=""):
+    global launch_count
+    launch_count += LAUNCHES.get(what, 0)
     if rc != 0:
         msg = load().emloco_last_error().decode()
         raise EmlocoError(f"{what} failed ({rc}): {msg}")

@@ -208,6 +208,12 @@ int emloco_step(emloco_sim* s, const float* d_actions, void* stream) {
     return EMLOCO_OK;
 }
 
+int emloco_physics_step(emloco_sim* s, const float* d_actions, void* stream) {
+    if (!s || !d_actions) return fail(EMLOCO_EINVAL, "emloco_physics_step: null argument");
+    CK(eml_launch_physics(s, d_actions, s->cfg.substeps * s->cfg.control_freq_inv, 1, (cudaStream_t)stream), "physics kernel");
+    return EMLOCO_OK;
+}
+
 int emloco_step_host(emloco_sim* s, const float* h_actions, float* h_obs, float* h_rew, int64_t* h_reset, float* h_amp_obs) {
     if (!s || !h_actions) return fail(EMLOCO_EINVAL, "emloco_step_host: null argument");
     CK(cudaSetDevice(s->device), "cudaSetDevice");
@@ -299,6 +305,55 @@ int emloco_linear(const float* d_x, int64_t ldx, const float* d_w, const float* 
     if ((d_mean == nullptr) != (d_var == nullptr)) return fail(EMLOCO_EINVAL, "emloco_linear: mean and var must come together");
     if (use_tc) CK(eml_linear_tc(d_x, ldx, d_w, d_b, d_y, ldy, M, N, K, d_mean, d_var, eps, relu, (cudaStream_t)stream), "linear (tensor core)");
     else CK(eml_linear_fma(d_x, ldx, d_w, d_b, d_y, ldy, M, N, K, d_mean, d_var, eps, relu, (cudaStream_t)stream), "linear (fma)");
+    return EMLOCO_OK;
+}
+
+int emloco_reset_done(emloco_sim* s, const float* d_init_root, const float* d_init_dof, void* stream) {
+    if (!s || !d_init_root || !d_init_dof) return fail(EMLOCO_EINVAL, "emloco_reset_done: null argument");
+    CK(eml_reset_done(s, d_init_root, d_init_dof, (cudaStream_t)stream), "reset-done kernels");
+    return EMLOCO_OK;
+}
+
+int emloco_sample_actions(const float* d_mu, int64_t ldmu, const float* d_logstd, const float* d_noise, float* d_actions,
+                          float* d_neglogp, int64_t N, int32_t A, void* stream) {
+    if (!d_mu || !d_logstd || !d_noise || !d_actions || N < 0 || A <= 0 || ldmu < A) return fail(EMLOCO_EINVAL, "emloco_sample_actions: bad argument");
+    CK(eml_sample_actions(d_mu, ldmu, d_logstd, d_noise, d_actions, d_neglogp, N, A, (cudaStream_t)stream), "sample actions");
+    return EMLOCO_OK;
+}
+
+int emloco_disc_reward(const float* d_logit, const float* d_task_rew, float* d_disc, float* d_combined, int64_t M, float scale,
+                       float w_task, float w_disc, void* stream) {
+    if ((!d_logit && !d_disc) || M < 0 || (d_combined && !d_task_rew)) return fail(EMLOCO_EINVAL, "emloco_disc_reward: bad argument");
+    CK(eml_disc_reward(d_logit, d_task_rew, d_disc, d_combined, M, scale, w_task, w_disc, (cudaStream_t)stream), "disc reward");
+    return EMLOCO_OK;
+}
+
+int emloco_rollout_record(const emloco_rollout_cfg* c, const float* d_rew, const int64_t* d_reset, const int64_t* d_terminate,
+                          const float* d_value_raw, const float* d_next_value_raw, const float* d_disc_logit,
+                          const uint8_t* d_inverted, float* d_mb_values, float* d_mb_rewards,
+                          float* d_mb_dones, float* d_mb_next_values, float* d_mb_amp_rewards, float* d_state, int64_t N,
+                          void* stream) {
+    if (!c || !d_rew || !d_reset || !d_terminate || !d_next_value_raw || !d_disc_logit || !d_mb_rewards || !d_mb_dones ||
+        !d_mb_next_values || !d_state || N < 0 || (d_value_raw && !d_mb_values))
+        return fail(EMLOCO_EINVAL, "emloco_rollout_record: bad argument");
+    RecordParams P;
+    P.rew = d_rew; P.reset = d_reset; P.terminate = d_terminate; P.value_raw = d_value_raw; P.mb_values = d_mb_values;
+    P.next_value_raw = d_next_value_raw; P.disc_logit = d_disc_logit;
+    P.inverted = d_inverted; P.mb_rewards = d_mb_rewards; P.mb_dones = d_mb_dones; P.mb_next_values = d_mb_next_values;
+    P.mb_amp_rewards = d_mb_amp_rewards;
+    P.current_rewards = d_state; P.current_lengths = d_state + N; P.current_combined = d_state + 2 * N;
+    P.discount_coefs = d_state + 3 * N; P.game_combined = d_state + 4 * N; P.terminated_flags = d_state + 5 * N;
+    P.N = N; P.inv_penalty = c->inversion_penalty_scale; P.reward_scale = c->reward_scale; P.v_mean = c->value_mean;
+    P.v_std = c->value_std; P.disc_scale = c->disc_reward_scale; P.gamma = c->gamma; P.step_to_pred = (float)c->step_to_pred;
+    P.unnorm_value = c->unnorm_value;
+    CK(eml_rollout_record(P, (cudaStream_t)stream), "rollout record");
+    return EMLOCO_OK;
+}
+
+int emloco_normalize(const float* d_x, int64_t ldx, float* d_y, int64_t ldy, int64_t M, int32_t K, const float* d_mean,
+                     const float* d_var, float eps, void* stream) {
+    if (!d_x || !d_y || !d_mean || !d_var || M < 0 || K <= 0 || ldx < K || ldy < K) return fail(EMLOCO_EINVAL, "emloco_normalize: bad argument");
+    CK(eml_normalize(d_x, ldx, d_y, ldy, M, K, d_mean, d_var, eps, (cudaStream_t)stream), "normalize");
     return EMLOCO_OK;
 }
 

@@ -92,6 +92,9 @@ struct PhysParams {
     float* root; float* dof; float* jq; float* rb; float* contact; float* dof_force;
     const int16_t* height; int hf_rows, hf_cols;
     const int32_t* env_ids;             // FK-only mode: optional env list
+    const int64_t* reset_mask;          // FK-only mode: only envs whose flag is set (device-side reset of done envs)
+    const float* init_root;             // FK-only mode: take the state from these buffers instead of root/dof
+    const float* init_dof;
     int N; int n_sub; float dt;
     float gz, kn, cn, ct, mu, max_w;
     int fk_only;
@@ -111,6 +114,7 @@ __global__ void __launch_bounds__(PH_WARPS * 32) physics_kernel(PhysParams P) {
     const int slot = blockIdx.x * PH_WARPS + warp;
     if (slot >= P.N) return;                       // warp-uniform
     const int env = P.env_ids ? P.env_ids[slot] : slot;
+    if (P.reset_mask && P.reset_mask[env] == 0) return;   // warp-uniform
     const bool body = lane < EML_NB;
     const int b = body ? lane : 0;
     const EmlModelDev& Mo = *P.model;
@@ -130,14 +134,14 @@ __global__ void __launch_bounds__(PH_WARPS * 32) physics_kernel(PhysParams P) {
     // ---- load reduced state ----
     f3 p0 = mk3(0, 0, 0), v0 = p0, w0 = p0; f4 q0 = mk4(0, 0, 0, 1);
     {
-        const float* r = P.root + (size_t)env * 13;      // every lane reads the root (broadcast load)
+        const float* r = (P.init_root ? P.init_root : P.root) + (size_t)env * 13;   // every lane reads the root (broadcast load)
         p0 = mk3(r[0], r[1], r[2]); q0 = mk4(r[3], r[4], r[5], r[6]);
         v0 = mk3(r[7], r[8], r[9]); w0 = mk3(r[10], r[11], r[12]);
     }
     f4 jq = mk4(0, 0, 0, 1); f3 jw = mk3(0, 0, 0), target = mk3(0, 0, 0);
     if (joint) {
         const int d = 3 * (b - 1);
-        const float2* ds = reinterpret_cast<const float2*>(P.dof + ((size_t)env * EML_ND + d) * 2);
+        const float2* ds = reinterpret_cast<const float2*>((P.init_dof ? P.init_dof : P.dof) + ((size_t)env * EML_ND + d) * 2);
         float2 d0 = ds[0], d1 = ds[1], d2 = ds[2];
         jw = mk3(d0.y, d1.y, d2.y);
         if (P.fk_only) {
@@ -428,7 +432,7 @@ static void fill_params(emloco_sim* s, PhysParams& P) {
     P.root = s->root_state; P.dof = s->dof_state; P.jq = s->joint_quat; P.rb = s->rb_state;
     P.contact = s->contact; P.dof_force = s->dof_force;
     P.height = s->height; P.hf_rows = s->hf_rows; P.hf_cols = s->hf_cols;
-    P.env_ids = nullptr; P.N = s->N; P.n_sub = 0; P.dt = s->cfg.sim_dt / (float)s->cfg.substeps;
+    P.env_ids = nullptr; P.reset_mask = nullptr; P.init_root = nullptr; P.init_dof = nullptr; P.N = s->N; P.n_sub = 0; P.dt = s->cfg.sim_dt / (float)s->cfg.substeps;
     P.gz = s->cfg.gravity_z; P.kn = s->cfg.contact_stiffness; P.cn = s->cfg.contact_damping;
     P.ct = s->cfg.friction_damping; P.mu = s->cfg.friction_mu; P.max_w = s->cfg.max_ang_vel;
     P.fk_only = 0;
@@ -449,4 +453,16 @@ cudaError_t eml_launch_fk(emloco_sim* s, const int32_t* d_env_ids, int n, cudaSt
     int blocks = (P.N + PH_WARPS - 1) / PH_WARPS;
     physics_kernel<<<blocks, PH_WARPS * 32, 0, st>>>(P);
     return cudaGetLastError();
+}
+
+// Device-side reset of the envs whose reset flag is set (env_reset(done_indices) of play_steps,
+// amp_continuous_value.py:45 -> humanoid.py:455-481 with a fixed synthetic initial state): no host round trip.
+cudaError_t eml_reset_done(emloco_sim* s, const float* d_init_root, const float* d_init_dof, cudaStream_t st) {
+    PhysParams P; fill_params(s, P);
+    P.fk_only = 1; P.reset_mask = s->reset; P.init_root = d_init_root; P.init_dof = d_init_dof;
+    int blocks = (P.N + PH_WARPS - 1) / PH_WARPS;
+    physics_kernel<<<blocks, PH_WARPS * 32, 0, st>>>(P);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return eml_launch_post_reset(s, st);
 }

@@ -30,7 +30,7 @@ struct PostParams {
     const float* verts; const float* betas; const int16_t* height; int hf_rows, hf_cols;
     int64_t* progress; float* obs; float* flip_obs; float* rew; float* rew_raw;
     int64_t* reset; int64_t* terminate; float* amp;
-    int N; int advance; float dt; float traj_dur; float sample_dt; int max_len;
+    int N; int advance; int reset_mode; float dt; float traj_dur; float sample_dt; int max_len;
     float power_coef, loc_coef, fail_dist2;
 };
 
@@ -82,6 +82,10 @@ __global__ void __launch_bounds__(PS_THREADS) post_step_kernel(PostParams P) {
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     if (env >= P.N) return;
+    // reset mode (humanoid.py:455-465 + humanoid_amp.py:284-293,499-502): only envs flagged in reset_buf; progress := 0,
+    // observations recomputed, AMP history filled with the current step, reward untouched, flags cleared
+    const bool rmode = P.reset_mode != 0;
+    if (rmode && P.reset[env] == 0) return;
 
     // ---- stage state ----
     {
@@ -100,7 +104,7 @@ __global__ void __launch_bounds__(PS_THREADS) post_step_kernel(PostParams P) {
             if (i < 14 * 103) hist[k] = a[i];
         }
     }
-    long long prog = P.progress[env] + P.advance;
+    long long prog = rmode ? 0 : P.progress[env] + P.advance;
     __syncthreads();
 
     const f3 root_pos = mk3(s_rb[0], s_rb[1], s_rb[2]);
@@ -108,7 +112,7 @@ __global__ void __launch_bounds__(PS_THREADS) post_step_kernel(PostParams P) {
         f4 rr = mk4(s_rb[3], s_rb[4], s_rb[5], s_rb[6]);
         f4 hinv = quat_from_angle_z(-calc_heading(rr));
         s_misc[0] = hinv.x; s_misc[1] = hinv.y; s_misc[2] = hinv.z; s_misc[3] = hinv.w;
-        if (P.advance) P.progress[env] = prog;
+        if (P.advance || rmode) P.progress[env] = prog;
         s_misc[9] = (float)prog * P.dt;
     } else if (tid == 32) {
         const float* h = s_rb + EML_HEAD * 13;
@@ -193,7 +197,7 @@ __global__ void __launch_bounds__(PS_THREADS) post_step_kernel(PostParams P) {
             s_obs[357 + lane] = b;
             s_amp[195 + lane] = b;
         }
-        if (lane == 31) {
+        if (lane == 31 && !rmode) {
             f3 tar = calc_pos(verts, time0, P.traj_dur);
             float dx = tar.x - root_pos.x, dy = tar.y - root_pos.y;
             float err = dx * dx + dy * dy;
@@ -248,6 +252,11 @@ __global__ void __launch_bounds__(PS_THREADS) post_step_kernel(PostParams P) {
             f[i2] = make_float2(v[0], v[1]);
         }
         float2* a = reinterpret_cast<float2*>(P.amp + (size_t)env * EML_AMP_OBS);
+        if (rmode) {
+            for (int i = tid; i < 15 * 103; i += PS_THREADS) a[i] = reinterpret_cast<const float2*>(s_amp)[i % 103];
+            if (tid == 0) { P.reset[env] = 0; P.terminate[env] = 0; }
+            return;
+        }
 #pragma unroll
         for (int k = 0; k < 12; ++k) {
             int i = tid + PS_THREADS * k;
@@ -259,7 +268,11 @@ __global__ void __launch_bounds__(PS_THREADS) post_step_kernel(PostParams P) {
 
 static bool g_tables_ready = false;
 
-cudaError_t eml_launch_post_step(emloco_sim* s, int advance_progress, cudaStream_t st) {
+static cudaError_t launch_post(emloco_sim* s, int advance_progress, int reset_mode, cudaStream_t st);
+cudaError_t eml_launch_post_step(emloco_sim* s, int advance_progress, cudaStream_t st) { return launch_post(s, advance_progress, 0, st); }
+cudaError_t eml_launch_post_reset(emloco_sim* s, cudaStream_t st) { return launch_post(s, 0, 1, st); }
+
+static cudaError_t launch_post(emloco_sim* s, int advance_progress, int reset_mode, cudaStream_t st) {
     if (!g_tables_ready) {
         float g32[32], cx[3], cy[3];
         for (int i = 0; i < 32; ++i) g32[i] = (float)(-2.0 + (4.0 / 31.0) * i);   // np.linspace step form: start + i*step
@@ -278,7 +291,7 @@ cudaError_t eml_launch_post_step(emloco_sim* s, int advance_progress, cudaStream
     P.verts = s->verts; P.betas = s->betas; P.height = s->height; P.hf_rows = s->hf_rows; P.hf_cols = s->hf_cols;
     P.progress = s->progress; P.obs = s->obs; P.flip_obs = s->flip_obs; P.rew = s->rew; P.rew_raw = s->rew_raw;
     P.reset = s->reset; P.terminate = s->terminate; P.amp = s->amp_obs;
-    P.N = s->N; P.advance = advance_progress;
+    P.N = s->N; P.advance = advance_progress; P.reset_mode = reset_mode;
     double dt = (double)s->cfg.control_freq_inv * (double)s->cfg.sim_dt;          // humanoid.py:89
     P.dt = (float)dt;
     double tdt = ((double)s->cfg.episode_length * dt) / (EML_NUM_VERTS - 1);      // traj_generator.py:24

@@ -59,8 +59,36 @@ struct emloco_sim {
     cudaStream_t copy_stream;
 };
 
+struct RecordParams {
+    // inputs of this step
+    const float* rew;            // [N] env reward (rew_buf)
+    const int64_t* reset;        // [N] dones
+    const int64_t* terminate;    // [N]
+    const float* value_raw;      // [N] critic on the pre-step obs (get_action_values), normalised units, or NULL
+    const float* next_value_raw; // [N] critic on next obs, normalised units
+    const float* disc_logit;     // [N]
+    const uint8_t* inverted;     // [N] or NULL (task.inverted)
+    // experience-buffer rows of step n (each [N])
+    float* mb_values; float* mb_rewards; float* mb_dones; float* mb_next_values; float* mb_amp_rewards;
+    // persistent per-env state
+    float* current_rewards; float* current_lengths; float* current_combined; float* discount_coefs; float* game_combined;
+    float* terminated_flags;
+    long long N;
+    float inv_penalty, reward_scale, v_mean, v_std, disc_scale, gamma, step_to_pred;
+    int unnorm_value;
+};
+
 // kernel launchers (defined in the .cu files)
 cudaError_t eml_upload_model(const EmlModelDev* m);
 cudaError_t eml_launch_post_step(emloco_sim* s, int advance_progress, cudaStream_t st);
 cudaError_t eml_launch_physics(emloco_sim* s, const float* d_actions, int n_substeps, int fuse_post, cudaStream_t st);
 cudaError_t eml_launch_fk(emloco_sim* s, const int32_t* d_env_ids, int n, cudaStream_t st);
+cudaError_t eml_reset_done(emloco_sim* s, const float* d_init_root, const float* d_init_dof, cudaStream_t st);
+cudaError_t eml_launch_post_reset(emloco_sim* s, cudaStream_t st);
+cudaError_t eml_sample_actions(const float* mu, long long ldmu, const float* logstd, const float* noise, float* actions,
+                               float* neglogp, long long N, int A, cudaStream_t st);
+cudaError_t eml_disc_reward(const float* logit, const float* task_rew, float* disc, float* combined, long long M, float scale,
+                            float w_task, float w_disc, cudaStream_t st);
+cudaError_t eml_rollout_record(const RecordParams& P, cudaStream_t st);
+cudaError_t eml_normalize(const float* x, long long ldx, float* y, long long ldy, long long M, int K, const float* mean,
+                          const float* var, float eps, cudaStream_t st);

@@ -70,3 +70,12 @@ def rest_root_height(arrs):
             z = x[i, 2] + arrs["geom_a"][i][2] - arrs["geom_b"][i][2]
         low = min(low, z)
     return -low
+
+
+def rest_joint_positions(arrs):
+    """Joint (body-origin) positions of the rest pose relative to the pelvis: [24,3]."""
+    NBn = len(arrs["parent"])
+    x = np.zeros((NBn, 3), np.float32)
+    for i in range(1, NBn):
+        x[i] = x[arrs["parent"][i]] + arrs["offset"][i]
+    return x

@@ -1,0 +1,216 @@
+"""Host-side mirror of the reference's rollout networks, evaluated by the kernels of libemloco_b200.so.
+
+Reference: ``AMPSeptValueBuilder.Network`` (pacer/pacer/learning/amp_network_sept_value_builder.py:19-90 ->
+amp_network_sept_builder.py:22-127 -> amp_network_builder.py:16-121) wrapped by ``ModelAMPContinuousSeptValue``
+(amp_sept_value_models.py:22-30) with the input normaliser of utils/running_mean_std.py:60-98, as configured by
+data/cfg/train/rlg/amp_humanoid_smpl_sept_task.yaml:12-70.  Parameter names follow the reference's
+``a2c_network.*`` state-dict keys so an rl_games checkpoint's ``model`` dict loads with ``load_state_dict``.
+
+PyTorch holds the parameters and the workspace; every multiply-add, normalisation, activation and the Gaussian
+head runs in this repo's CUDA kernels through the C ABI (``emloco_linear``, ``emloco_normalize``,
+``emloco_sample_actions``).  There is no torch fallback: without the library or a CUDA device the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .sim import _ptr, _stream, linear
+
+SELF_OBS, TASK_OBS, TRAJ_OBS, OBS, AMP_OBS, ACTIONS = 368, 1054, 30, 1422, 3090, 69
+
+
+def _mlp(in_size, units):
+    layers, k = [], in_size
+    for u in units:
+        layers += [nn.Linear(k, u), nn.ReLU()]
+        k = u
+    return nn.Sequential(*layers)
+
+
+class RunningMeanStd(nn.Module):
+    """State holder with the reference's buffer names (running_mean/running_var/count, float64)."""
+
+    def __init__(self, size, epsilon=1e-5):
+        super().__init__()
+        self.epsilon = epsilon
+        self.register_buffer("running_mean", torch.zeros(size, dtype=torch.float64))
+        self.register_buffer("running_var", torch.ones(size, dtype=torch.float64))
+        self.register_buffer("count", torch.ones((), dtype=torch.float64))
+        self._f32 = None
+
+    def f32(self):
+        """(mean, var) as float32 - `current_var.float()` of running_mean_std.py:78-84 - cached until the stats change."""
+        key = (self.running_mean._version, self.running_var._version, self.running_mean.device)
+        if self._f32 is None or self._f32[0] != key:
+            self._f32 = (key, self.running_mean.float().contiguous(), self.running_var.float().contiguous())
+        return self._f32[1], self._f32[2]
+
+
+class AMPSeptValueNetwork(nn.Module):
+    """The `a2c_network` of the reference with the default cfg: shared task MLP 1054->512->256, actor and critic
+    624->2048->1024 (+mu 69 / value 1), task-value 30->15->6->1, discriminator 3090->1024->512->1, fixed logstd -2.9."""
+
+    def __init__(self, mlp_units=(2048, 1024), task_units=(512, 256), value_units=(15, 6), disc_units=(1024, 512),
+                 sigma_init=-2.9):
+        super().__init__()
+        ain = SELF_OBS + task_units[-1]
+        self.actor_mlp = _mlp(ain, mlp_units)
+        self.critic_mlp = _mlp(ain, mlp_units)
+        self.mu = nn.Linear(mlp_units[-1], ACTIONS)
+        self.sigma = nn.Parameter(torch.full((ACTIONS,), float(sigma_init)), requires_grad=False)
+        self.value = nn.Linear(mlp_units[-1], 1)
+        self._task_mlp = _mlp(TASK_OBS, task_units)
+        self._task_value_mlp = _mlp(TRAJ_OBS, value_units)
+        self._value_logits = nn.Linear(value_units[-1], 1)
+        self._disc_mlp = _mlp(AMP_OBS, disc_units)
+        self._disc_logits = nn.Linear(disc_units[-1], 1)
+        for m in list(self._disc_mlp) + list(self._task_value_mlp):
+            if isinstance(m, nn.Linear):
+                nn.init.zeros_(m.bias)                                     # amp_network_builder.py:107-111
+        nn.init.uniform_(self._disc_logits.weight, -1.0, 1.0)              # :113-114
+        nn.init.zeros_(self._disc_logits.bias)
+        nn.init.uniform_(self._value_logits.weight, -1.0, 1.0)             # amp_network_sept_value_builder.py:86-87
+        nn.init.zeros_(self._value_logits.bias)
+
+
+class RolloutNets:
+    """Evaluates the networks for a fixed row count with preallocated workspaces (CUDA-graph friendly)."""
+
+    def __init__(self, net: AMPSeptValueNetwork, obs_norm: RunningMeanStd, amp_norm: RunningMeanStd, rows: int,
+                 tensor_cores: bool = False):
+        self.net, self.obs_norm, self.amp_norm, self.M, self.tc = net, obs_norm, amp_norm, int(rows), bool(tensor_cores)
+        dev = net.mu.weight.device
+        if dev.type != "cuda":
+            raise _lib.EmlocoError("RolloutNets needs its parameters on a CUDA device; there is no CPU fallback")
+        f = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+        M = self.M
+        a1, a2 = net.actor_mlp[0].out_features, net.actor_mlp[2].out_features
+        t1, t2 = net._task_mlp[0].out_features, net._task_mlp[2].out_features
+        d1, d2 = net._disc_mlp[0].out_features, net._disc_mlp[2].out_features
+        v1, v2 = net._task_value_mlp[0].out_features, net._task_value_mlp[2].out_features
+        self.t1, self.ain = f(M, t1), f(M, SELF_OBS + t2)
+        self.ac1 = f(M, 2 * a1)                 # actor and critic first layers stacked: one GEMM over the shared input
+        self.a2, self.c2 = f(M, a2), f(M, a2)
+        self.mu, self.value, self.next_value, self.task_value = f(M, ACTIONS), f(M, 1), f(M, 1), f(M, 1)
+        self.v1, self.v2 = f(M, v1), f(M, v2)
+        self.d1, self.d2, self.logit = f(M, d1), f(M, d2), f(M, 1)
+        self.actions, self.neglogp = f(M, ACTIONS), f(M)
+        self._stacked = None
+
+    def _w_ac1(self):
+        n = self.net
+        ps = (n.actor_mlp[0].weight, n.actor_mlp[0].bias, n.critic_mlp[0].weight, n.critic_mlp[0].bias)
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if self._stacked is None or self._stacked[0] != key:
+            self._stacked = (key, torch.cat([ps[0].detach(), ps[2].detach()]).contiguous(),
+                             torch.cat([ps[1].detach(), ps[3].detach()]).contiguous())
+        return self._stacked[1], self._stacked[2]
+
+    def _lin(self, x, layer, relu, out, mean=None, var=None):
+        return linear(x, layer.weight.detach(), layer.bias.detach(), relu=relu, mean=mean, var=var, out=out,
+                      eps=self.obs_norm.epsilon, tensor_cores=self.tc)
+
+    def _trunk(self, obs):
+        """normalise -> task MLP -> [norm(self obs) | task_out] (amp_network_sept_builder.py:69-76,82-96)."""
+        n = self.net
+        mean, var = self.obs_norm.f32()
+        normalize(obs[:, :SELF_OBS], mean[:SELF_OBS], var[:SELF_OBS], self.obs_norm.epsilon, out=self.ain[:, :SELF_OBS])
+        self._lin(obs[:, SELF_OBS:], n._task_mlp[0], True, self.t1, mean[SELF_OBS:], var[SELF_OBS:])
+        self._lin(self.t1, n._task_mlp[2], True, self.ain[:, SELF_OBS:])
+        return mean, var
+
+    def action_values(self, obs, noise, mu_out=None, task_value_out=None, actions_out=None, neglogp_out=None):
+        """get_action_values (rl_games A2CBase; called at amp_continuous_value.py:53): mu, sigma(logstd), value (still in
+        normalised units), task value, sampled action, neglogp.  obs [M,1422], noise [M,69] (standard normal).
+        The *_out tensors let the heads write directly into the caller's experience rows."""
+        n = self.net
+        mu_out = self.mu if mu_out is None else mu_out
+        task_value_out = self.task_value if task_value_out is None else task_value_out
+        actions_out = self.actions if actions_out is None else actions_out
+        neglogp_out = self.neglogp if neglogp_out is None else neglogp_out
+        mean, var = self._trunk(obs)
+        w, b = self._w_ac1()
+        linear(self.ain, w, b, relu=True, out=self.ac1, tensor_cores=self.tc)
+        h = n.actor_mlp[0].out_features
+        self._lin(self.ac1[:, :h], n.actor_mlp[2], True, self.a2)
+        self._lin(self.ac1[:, h:], n.critic_mlp[2], True, self.c2)
+        self._lin(self.a2, n.mu, False, mu_out)
+        self._lin(self.c2, n.value, False, self.value)
+        # eval_task_value (amp_network_sept_value_builder.py:31-46): the 30 normalised trajectory features
+        self._lin(obs[:, SELF_OBS:SELF_OBS + TRAJ_OBS], n._task_value_mlp[0], True, self.v1,
+                  mean[SELF_OBS:SELF_OBS + TRAJ_OBS], var[SELF_OBS:SELF_OBS + TRAJ_OBS])
+        self._lin(self.v1, n._task_value_mlp[2], True, self.v2)
+        self._lin(self.v2, n._value_logits, False, task_value_out)
+        sample_actions(mu_out, n.sigma, noise, actions_out, neglogp_out)
+        return dict(mus=mu_out, sigmas=n.sigma, values=self.value, task_values=task_value_out, actions=actions_out,
+                    neglogpacs=neglogp_out)
+
+    def critic(self, obs):
+        """_eval_critic (common_agent.py:647-655) before value un-normalisation: [M,1]."""
+        n = self.net
+        self._trunk(obs)
+        h = n.critic_mlp[0].out_features
+        self._lin(self.ain, n.critic_mlp[0], True, self.ac1[:, h:])
+        self._lin(self.ac1[:, h:], n.critic_mlp[2], True, self.c2)
+        self._lin(self.c2, n.value, False, self.next_value)
+        return self.next_value
+
+    def disc_logits(self, amp_obs, out=None):
+        """_eval_disc (amp_continuous.py:666-668): normalise -> 3090->1024->512->1.  amp_obs [M',3090], M' <= M."""
+        n = self.net
+        m = amp_obs.shape[0]
+        mean, var = self.amp_norm.f32()
+        out = self.logit[:m] if out is None else out
+        linear(amp_obs, n._disc_mlp[0].weight.detach(), n._disc_mlp[0].bias.detach(), relu=True, mean=mean, var=var,
+               eps=self.amp_norm.epsilon, out=self.d1[:m], tensor_cores=self.tc)
+        self._lin(self.d1[:m], n._disc_mlp[2], True, self.d2[:m])
+        self._lin(self.d2[:m], n._disc_logits, False, out)
+        return out
+
+
+# ---- thin wrappers over the stateless C entry points -------------------------------------------------------
+def normalize(x, mean, var, eps=1e-5, out=None):
+    """RunningMeanStd.forward, eval branch (utils/running_mean_std.py:82-84): clamp((x-mean)/sqrt(var+eps), +-5)."""
+    assert x.dim() == 2 and x.stride(1) == 1 and x.dtype == torch.float32 and x.is_cuda
+    M, K = x.shape
+    if out is None:
+        out = torch.empty(M, K, device=x.device, dtype=torch.float32)
+    assert out.shape == (M, K) and out.stride(1) == 1
+    _lib.check(_lib.load().emloco_normalize(_ptr(x), x.stride(0), _ptr(out), out.stride(0), M, K, _ptr(mean), _ptr(var), eps,
+                                            _stream()), "emloco_normalize")
+    return out
+
+
+def sample_actions(mu, logstd, noise, actions=None, neglogp=None):
+    M, A = mu.shape
+    assert mu.stride(1) == 1 and noise.is_contiguous() and noise.shape == (M, A)
+    if actions is None:
+        actions = torch.empty(M, A, device=mu.device, dtype=torch.float32)
+    if neglogp is None:
+        neglogp = torch.empty(M, device=mu.device, dtype=torch.float32)
+    _lib.check(_lib.load().emloco_sample_actions(_ptr(mu), mu.stride(0), _ptr(logstd), _ptr(noise), _ptr(actions),
+                                                 _ptr(neglogp), M, A, _stream()), "emloco_sample_actions")
+    return actions, neglogp
+
+
+def disc_reward(logit, task_rew=None, scale=2.0, w_task=0.5, w_disc=0.5):
+    """(_calc_disc_rewards, _combine_rewards): returns (disc_r, combined or None), same shape as logit."""
+    lg = logit.contiguous()
+    disc = torch.empty_like(lg)
+    comb = None
+    tr = None
+    if task_rew is not None:
+        tr = task_rew.contiguous()
+        assert tr.numel() == lg.numel()
+        comb = torch.empty_like(lg)
+    _lib.check(_lib.load().emloco_disc_reward(_ptr(lg), _ptr(tr), _ptr(disc), _ptr(comb), lg.numel(), scale, w_task, w_disc,
+                                              _stream()), "emloco_disc_reward")
+    return disc, comb
+
+
+LOG_2PI_HALF = 0.5 * math.log(2.0 * math.pi)

@@ -1,0 +1,178 @@
+"""The rollout hot loop on one GPU: `AMPValueAgent.play_steps` of the reference
+(pacer/pacer/learning/amp_continuous_value.py:34-178) over `EmlocoSim` + `RolloutNets`.
+
+Per control step, for all N envs of this rank (every item is a kernel of libemloco_b200.so):
+  env_reset(done)            emloco_reset_done            :45
+  get_action_values          emloco_linear x10, emloco_normalize, emloco_sample_actions   :53
+  env_step                   emloco_step (physics + fused post-step)                        :61
+  _eval_critic(next obs)     emloco_linear x5, emloco_normalize                             :85
+  _calc_amp_rewards          emloco_linear x3                                               :93
+  rewards/values/bookkeeping emloco_rollout_record                                          :63-118
+and once per horizon: discriminator over the stored [T,N,3090] AMP observations, reward combine, GAE
+(emloco_linear x3 per chunk, emloco_disc_reward, emloco_gae)  :150-163.
+
+Experience rows are written in place ([T,N,...] tensors, as rl_games' ExperienceBuffer lays them out); the caller
+reads them after `play_steps` exactly as `batch_dict` of the reference.  Envs are rank-local: no collective here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from .policy import (ACTIONS, AMP_OBS, OBS, AMPSeptValueNetwork, RolloutNets, RunningMeanStd)
+from .sim import EmlocoSim, _ptr, _stream, gae
+from .synthetic import synthetic_env_state
+
+
+class Rollout:
+    def __init__(self, num_envs, device=0, horizon=32, seed=0, tensor_cores=False, gamma=0.99, tau=0.95,
+                 task_reward_w=0.5, disc_reward_w=0.5, disc_reward_scale=2.0, inversion_penalty_scale=0.3,
+                 step_to_pred=144, normalize_value=True, net=None, obs_norm=None, amp_norm=None, value_norm=None,
+                 recompute_disc=True, valuenet=None):
+        self.N, self.T, self.device = int(num_envs), int(horizon), int(device)
+        self.gamma, self.tau = gamma, tau
+        self.task_reward_w, self.disc_reward_w, self.disc_reward_scale = task_reward_w, disc_reward_w, disc_reward_scale
+        self.recompute_disc = recompute_disc
+        dev = torch.device("cuda", device)
+        torch.cuda.set_device(dev)
+        self.sim = EmlocoSim(self.N, device=device)
+        if net is None:
+            torch.manual_seed(seed)
+            net = AMPSeptValueNetwork()
+        self.net = net.to(dev)
+        self.obs_norm = (obs_norm or RunningMeanStd(OBS)).to(dev)
+        self.amp_norm = (amp_norm or RunningMeanStd(AMP_OBS)).to(dev)
+        self.value_norm = (value_norm or RunningMeanStd(1)).to(dev)
+        self.nets = RolloutNets(self.net, self.obs_norm, self.amp_norm, self.N, tensor_cores=tensor_cores)
+        self.gen = torch.Generator(device=dev).manual_seed(seed + 1)
+
+        # synthetic initial state + JTA-shaped trajectories; rank-local seed like run.py:65
+        st = synthetic_env_state(self.N, seed=seed, root_height=self.sim.rest_height)
+        self.init_root = torch.from_numpy(st["root"]).to(dev)
+        self.init_dof = torch.from_numpy(st["dof"]).to(dev)
+        self.sim.traj_verts.copy_(torch.from_numpy(st["verts"]).to(dev))
+        self.sim.reset.fill_(1)
+        self.sim.reset_done(self.init_root, self.init_dof)
+
+        # LocoVal inputs captured at reset (humanoid_pedestrain_terrain.py:509-515, vec_task_wrappers.py:47-66)
+        self.waypoint_traj = torch.from_numpy(st["waypoints"]).to(dev)                  # [N,13,2], origin-relative
+        rb = self.sim.rb_state.view(self.N, 24, 13)
+        self.init_pose = (rb[:, :, 0:3] - rb[:, :1, 0:3]).contiguous()
+        self.init_vel = self.init_root[:, 7:9].contiguous()
+        if valuenet is None:
+            from .value_pose_net import ValuePoseNet
+            valuenet = ValuePoseNet(True, True, mutate_pose=False)
+        self.valuenet = valuenet.to(dev).eval()
+        self._marks = None
+
+        f = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
+        T, N = self.T, self.N
+        self.mb = dict(obses=f(T, N, OBS), actions=f(T, N, ACTIONS), neglogpacs=f(T, N), values=f(T, N, 1), mus=f(T, N, ACTIONS),
+                       task_values=f(T, N, 1), rewards=f(T, N, 1), next_values=f(T, N, 1), dones=f(T, N), amp_obs=f(T, N, AMP_OBS),
+                       amp_rewards=f(T, N, 1), next_obses=None)
+        self.state = f(6, N)
+        self.state[3].fill_(1.0)      # discount_coefs start at 1
+        self.noise = f(N, ACTIONS)
+        self.rcfg = _lib.RolloutCfg(inversion_penalty_scale, 1.0, 0.0, 1.0, disc_reward_scale, gamma, step_to_pred,
+                                    int(bool(normalize_value)))
+        self._refresh_value_norm()
+        self.launches_per_step = 0
+
+    def _refresh_value_norm(self):
+        self.rcfg.value_mean = float(self.value_norm.running_mean.float().item())
+        self.rcfg.value_std = float(torch.sqrt(self.value_norm.running_var.float() + self.value_norm.epsilon).item())
+
+    SEGMENTS = ("reset", "policy", "physics", "post_step", "critic", "disc", "record")
+
+    def enable_segment_timing(self, on=True):
+        """Record a CUDA event on the launching stream at every segment boundary of step(); read with segment_ms()."""
+        self._marks = [] if on else None
+
+    def _mark(self):
+        if self._marks is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self._marks.append(e)
+
+    def segment_ms(self):
+        """Mean device time per segment over the steps recorded since enable_segment_timing(); call after a sync."""
+        k = len(self.SEGMENTS) + 1
+        ev = self._marks
+        steps = len(ev) // k
+        out = {s: 0.0 for s in self.SEGMENTS}
+        for i in range(steps):
+            for j, s in enumerate(self.SEGMENTS):
+                out[s] += ev[i * k + j].elapsed_time(ev[i * k + j + 1])
+        return {s: v / max(steps, 1) for s, v in out.items()}, steps
+
+    # ---- one control step: everything inside the `for n in range(horizon_length)` body ----
+    def step(self, n, noise=None):
+        sim, nets, mb = self.sim, self.nets, self.mb
+        self._mark()
+        sim.reset_done(self.init_root, self.init_dof)                                   # env_reset(done_indices)
+        mb["obses"][n].copy_(sim.obs)
+        if noise is None:
+            noise = self.noise.normal_(generator=self.gen)
+        self._mark()
+        # the heads write straight into row n of the experience tensors (experience_buffer.update_data, :47-56)
+        res = nets.action_values(sim.obs, noise, mu_out=mb["mus"][n], task_value_out=mb["task_values"][n],
+                                 actions_out=mb["actions"][n], neglogp_out=mb["neglogpacs"][n])
+        self._mark()
+        sim.physics_step(res["actions"])                                                # env_step: pre_physics + simulate
+        self._mark()
+        sim.post_step(True)                                                             #           post_physics_step
+        mb["amp_obs"][n].copy_(sim.amp_obs.view(self.N, AMP_OBS))
+        self._mark()
+        nv = nets.critic(sim.obs)                                                       # _eval_critic(next obs)
+        self._mark()
+        logit = nets.disc_logits(sim.amp_obs.view(self.N, AMP_OBS))                     # _calc_amp_rewards
+        self._mark()
+        # values are un-normalised (get_action_values, normalize_value) together with next_values in the record kernel
+        _lib.check(_lib.load().emloco_rollout_record(
+            C.byref(self.rcfg), _ptr(sim.rew), _ptr(sim.reset), _ptr(sim.terminate), _ptr(res["values"]), _ptr(nv), _ptr(logit),
+            None, _ptr(mb["values"][n]), _ptr(mb["rewards"][n]), _ptr(mb["dones"][n]), _ptr(mb["next_values"][n]),
+            _ptr(mb["amp_rewards"][n]), _ptr(self.state), self.N, _stream()), "emloco_rollout_record")
+        # LocoVal scoring of every env's (waypoints, initial pose, initial velocity) - valuenet(...) of :123-127
+        self.locoval_scores = self.valuenet(self.waypoint_traj, self.init_pose, self.init_vel)
+        self._mark()
+
+    # ---- after the horizon: disc over the stored AMP obs, combine, GAE (:150-163) ----
+    def finish(self):
+        mb, T, N = self.mb, self.T, self.N
+        if self.recompute_disc:
+            for t in range(T):        # [T*N,3090] in N-row chunks through the same workspace
+                self.nets.disc_logits(mb["amp_obs"][t], out=self._logits_TN()[t])
+            lg = self._logits_TN()
+            _lib.check(_lib.load().emloco_disc_reward(_ptr(lg), _ptr(mb["rewards"]), _ptr(mb["amp_rewards"]), _ptr(self._comb()),
+                                                      T * N, self.disc_reward_scale, self.task_reward_w, self.disc_reward_w,
+                                                      _stream()), "emloco_disc_reward")
+        else:
+            # the per-step AMP rewards are the same numbers (same rows, same weights, eval-mode normaliser): combine only
+            _lib.check(_lib.load().emloco_disc_reward(None, _ptr(mb["rewards"]), _ptr(mb["amp_rewards"]), _ptr(self._comb()),
+                                                      T * N, self.disc_reward_scale, self.task_reward_w, self.disc_reward_w,
+                                                      _stream()), "emloco_disc_reward")
+        adv, ret = gae(mb["dones"], mb["values"], self._comb(), mb["next_values"], self.gamma, self.tau)
+        self.mb_advs, self.mb_returns = adv, ret
+        return dict(returns=ret, advantages=adv, rewards=self._comb(), **{k: v for k, v in mb.items() if v is not None})
+
+    def _logits_TN(self):
+        if not hasattr(self, "_lg"):
+            self._lg = torch.empty(self.T, self.N, 1, device=self.state.device)
+        return self._lg
+
+    def _comb(self):
+        if not hasattr(self, "_cb"):
+            self._cb = torch.empty(self.T, self.N, 1, device=self.state.device)
+        return self._cb
+
+    def play_steps(self):
+        for n in range(self.T):
+            self.step(n)
+        return self.finish()
+
+    def close(self):
+        self.sim.close()

@@ -62,6 +62,8 @@ class EmlocoSim:
         self._h = h
         self.num_envs = int(num_envs)
         self.device = int(device)
+        from .model import rest_root_height
+        self.rest_height = float(rest_root_height(self.model_arrays))
         self._tensors = {}
         for name in _lib.T_IDS:
             self._tensors[name] = self._acquire(name)
@@ -106,6 +108,13 @@ class EmlocoSim:
             return
         _lib.check(self.lib.emloco_reset_indexed(self._h, _ptr(ids), ids.numel(), _stream()), "emloco_reset_indexed")
 
+    def reset_done(self, init_root, init_dof):
+        """env_reset(done_indices) on the device: envs with reset_buf set restart from init_root [N,13] / init_dof [N*69,2]."""
+        for t, shp in ((init_root, (self.num_envs, 13)), (init_dof, (self.num_envs * _lib.ND, 2))):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == shp):
+                raise _lib.EmlocoError(f"reset_done: initial state must be contiguous float32 CUDA of shape {shp}")
+        _lib.check(self.lib.emloco_reset_done(self._h, _ptr(init_root), _ptr(init_dof), _stream()), "emloco_reset_done")
+
     def post_step(self, advance_progress=True):
         _lib.check(self.lib.emloco_post_step(self._h, int(bool(advance_progress)), _stream()), "emloco_post_step")
 
@@ -115,6 +124,13 @@ class EmlocoSim:
                 and tuple(actions.shape) == (self.num_envs, _lib.ND)):
             raise _lib.EmlocoError("actions must be a contiguous float32 CUDA tensor of shape [num_envs, 69]")
         _lib.check(self.lib.emloco_step(self._h, _ptr(actions), _stream()), "emloco_step")
+
+    def physics_step(self, actions):
+        """pre_physics_step + control_freq_inv x simulate only; follow with post_step()."""
+        if not (actions.is_cuda and actions.dtype == torch.float32 and actions.is_contiguous()
+                and tuple(actions.shape) == (self.num_envs, _lib.ND)):
+            raise _lib.EmlocoError("actions must be a contiguous float32 CUDA tensor of shape [num_envs, 69]")
+        _lib.check(self.lib.emloco_physics_step(self._h, _ptr(actions), _stream()), "emloco_physics_step")
 
     def step_host(self, actions, obs=None, rew=None, reset=None, amp_obs=None):
         """Host-buffer step (numpy arrays); copies inside the call."""

@@ -1,0 +1,84 @@
+"""Seeded synthetic inputs for the benchmark and smoke runs: there is no network for the AMASS / JTA /
+JRDB data the reference resets from, so initial states and trajectories are generated here with the same
+distributions the reference samples from.  Host-side numpy, run once per reset batch - not on the hot path.
+
+  * trajectories: the random-walk polylines of TrajGenerator.reset (pacer/pacer/env/util/traj_generator.py:60-113):
+    101 vertices, per-vertex turn U(-1,1)*dtheta_max*dt with 2 % sharp turns U(-pi,pi), speed random walk with
+    |accel| <= 2 m/s^2 clipped to [0.0005, 3] m/s (pacer.yaml:55-61), initial heading U(-pi,pi);
+  * initial state: upright rest pose at the rest height, root xy uniform in the 8 x 8 m patch behind the 50 m border of the
+    default terrain (humanoid_pedestrain_terrain.py:1142-1165), heading = first trajectory segment
+    (--random_heading), root speed U(1,1.5) m/s along the heading (..terrain.py:568);
+  * LocoVal batches: 13 waypoints at 0.4 s spacing sampled from such polylines, origin-relative; pose = rest-pose
+    joint positions + N(0,0.05); vel = (w1-w0)*2.5  (social-transmotion/load_jta_traj.py:66-120 shapes).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+EPISODE_LEN, NUM_VERTS, CONTROL_DT = 168, 101, 2.0 / 60.0
+DTHETA_MAX, SPEED_MIN, SPEED_MAX, ACCEL_MAX, SHARP_PROB = 2.0, 0.0005, 3.0, 2.0, 0.02
+
+
+def random_walk_verts(n, init_xy, rng, num_verts=NUM_VERTS, episode_dur=EPISODE_LEN * CONTROL_DT):
+    dt = episode_dur / (num_verts - 1)
+    dtheta = (2 * rng.random((n, num_verts - 1)) - 1.0) * DTHETA_MAX * dt
+    sharp = np.pi * (2 * rng.random((n, num_verts - 1)) - 1.0)
+    mask = rng.random((n, num_verts - 1)) < SHARP_PROB
+    dtheta[mask] = sharp[mask]
+    dtheta[:, 0] = np.pi * (2 * rng.random(n) - 1.0)
+    dspeed = (2 * rng.random((n, num_verts - 1)) - 1.0) * ACCEL_MAX * dt
+    dspeed[:, 0] = (SPEED_MAX - SPEED_MIN) * rng.random(n) + SPEED_MIN
+    speed = np.zeros_like(dspeed)
+    speed[:, 0] = dspeed[:, 0]
+    for i in range(1, num_verts - 1):
+        speed[:, i] = np.clip(speed[:, i - 1] + dspeed[:, i], SPEED_MIN, SPEED_MAX)
+    theta = np.cumsum(dtheta, -1)
+    dpos = np.stack([np.cos(theta), -np.sin(theta), np.zeros_like(theta)], -1) * (speed * dt)[..., None]
+    dpos[:, 0, 0:2] += init_xy
+    verts = np.zeros((n, num_verts, 3), np.float32)
+    verts[:, 0, 0:2] = init_xy
+    verts[:, 1:] = np.cumsum(dpos, -2)
+    return verts, -theta[:, 0]
+
+
+def synthetic_env_state(n, seed=0, root_height=0.93, border=50.0, patch=8.0):
+    """-> dict(root [n,13] f32, dof [n*69,2] f32, verts [n,101,3] f32)."""
+    rng = np.random.default_rng(seed)
+    xy = border + patch * rng.random((n, 2))
+    verts, heading = random_walk_verts(n, xy, rng)
+    root = np.zeros((n, 13), np.float32)
+    root[:, 0:2] = xy
+    root[:, 2] = root_height
+    root[:, 5] = np.sin(heading / 2)
+    root[:, 6] = np.cos(heading / 2)
+    speed = rng.uniform(1.0, 1.5, n)
+    root[:, 7] = speed * np.cos(heading)
+    root[:, 8] = speed * np.sin(heading)
+    dof = np.zeros((n * 69, 2), np.float32)
+    return dict(root=root, dof=dof, verts=verts, waypoints=waypoints_from_verts(verts))
+
+
+def waypoints_from_verts(verts, num=13, sample_dt=0.4):
+    """_fetch_traj_samples at progress 0 (humanoid_traj.py:208-224 via TrajGenerator.calc_pos :278-296), xy only,
+    relative to the first waypoint (vec_task_wrappers.py:47-52).  Note calc_pos spreads the 101 vertices over
+    num_verts * dt (traj_generator.py:269-272)."""
+    nv = verts.shape[1]
+    dur = nv * (EPISODE_LEN * CONTROL_DT / (nv - 1))
+    seg = np.clip(np.arange(num) * sample_dt / dur, 0, 1) * (nv - 1)
+    i0 = np.floor(seg).astype(int); i1 = np.ceil(seg).astype(int); fr = (seg - i0).astype(np.float32)
+    w = verts[:, i0, :2] * (1 - fr)[None, :, None] + verts[:, i1, :2] * fr[None, :, None]
+    return (w - w[:, :1]).astype(np.float32)
+
+
+def synthetic_locoval_batch(b, seed=0, rest_joint_pos=None):
+    """JTA-shaped LocoVal inputs: traj [b,13,2], pose [b,24,3], vel [b,2] (float32)."""
+    rng = np.random.default_rng(seed)
+    verts, _ = random_walk_verts(b, np.zeros((b, 2)), rng)
+    traj = waypoints_from_verts(verts)
+    if rest_joint_pos is None:
+        from .model import build_model_arrays, rest_joint_positions
+        rest_joint_pos = rest_joint_positions(build_model_arrays())
+    pose = (np.asarray(rest_joint_pos, np.float32)[None] + rng.normal(0, 0.05, (b, 24, 3))).astype(np.float32)
+    pose -= pose[:, :1].copy()
+    vel = ((traj[:, 1] - traj[:, 0]) * 2.5).astype(np.float32)
+    return traj, pose, vel

@@ -130,10 +130,21 @@ int emloco_post_step(emloco_sim* sim, int32_t advance_progress, void* stream);
  * control_freq_inv x simulate, post_physics_step.  d_actions [N,69]. */
 int emloco_step(emloco_sim* sim, const float* d_actions, void* stream);
 
+/* The first half of emloco_step on its own - pre_physics_step + control_freq_inv x gym.simulate in one kernel -
+ * so that a caller can place its own work (or a timing event) between physics and emloco_post_step(sim, 1, stream). */
+int emloco_physics_step(emloco_sim* sim, const float* d_actions, void* stream);
+
 /* Same through HOST buffers (the vec-env call a CPU-side user makes, run.py:148-160): copies
  * actions in, steps, copies obs/rew/reset out, synchronises.  Any output pointer may be NULL. */
 int emloco_step_host(emloco_sim* sim, const float* h_actions, float* h_obs, float* h_rew,
                      int64_t* h_reset, float* h_amp_obs);
+
+/* env_reset(done_indices) of play_steps (pacer/pacer/learning/amp_continuous_value.py:45 -> vec_task_wrappers.py:36-39 ->
+ * humanoid.py:455-481, humanoid_amp.py:284-293,499-502) entirely on the device: every env whose reset_buf is set takes
+ * its root/DOF state from d_init_root [N,13] / d_init_dof [N*69,2], rigid-body state by forward kinematics, progress = 0,
+ * reset/terminate cleared, contact forces zeroed, observations recomputed, AMP history filled with the current step
+ * (_init_amp_obs_default).  The mocap-sampled initial state of _reset_ref_state_init is the caller's to put in d_init_*. */
+int emloco_reset_done(emloco_sim* sim, const float* d_init_root, const float* d_init_dof, void* stream);
 
 /* ---- LocoVal: ValuePoseNet (pacer/pacer/learning/value_pose_net.py:10-159) ----
  * weights: fc1.weight[H1,IN] fc1.bias[H1] fc2.weight[H2,H1] fc2.bias[H2] fc3.weight[1,H2] fc3.bias[1]
@@ -170,6 +181,42 @@ int emloco_gae(const float* d_dones, const float* d_values, const float* d_rewar
 int emloco_linear(const float* d_x, int64_t ldx, const float* d_w, const float* d_b, float* d_y, int64_t ldy,
                   int64_t M, int32_t N, int32_t K, const float* d_mean, const float* d_var, float eps,
                   int32_t relu, int32_t use_tensor_cores, void* stream);
+
+/* ---- per-step rollout arithmetic of play_steps (amp_continuous_value.py:34-178) ---- */
+/* Gaussian policy head: a = mu + exp(logstd)*noise, neglogp = 0.5*sum(((a-mu)/sigma)^2) + 0.5*log(2pi)*A + sum(logstd)
+ * (rl_games==1.1.4 ModelA2CContinuousLogStd, pinned in pacer/requirements.txt, not vendored; fixed logstd -2.9,
+ * amp_humanoid_smpl_sept_task.yaml:19-27).  mu rows have stride ldmu; noise/actions [N,A]; neglogp [N] or NULL. */
+int emloco_sample_actions(const float* d_mu, int64_t ldmu, const float* d_logstd, const float* d_noise, float* d_actions,
+                          float* d_neglogp, int64_t N, int32_t A, void* stream);
+/* _calc_disc_rewards + _combine_rewards (learning/amp_continuous.py:675-692, 659-664):
+ * disc = -log(max(1 - sigmoid(logit), 1e-4)) * scale; combined = w_task*task + w_disc*disc.  Either output may be NULL;
+ * d_logit == NULL means d_disc already holds the AMP rewards (combine only). */
+int emloco_disc_reward(const float* d_logit, const float* d_task_rew, float* d_disc, float* d_combined, int64_t M,
+                       float scale, float w_task, float w_disc, void* stream);
+/* Everything play_steps does per env after the nets of step n (:63-118): inversion penalty, reward shaper scale,
+ * value un-normalisation (utils/running_mean_std.py:77-79) of the pre-step critic output (d_value_raw -> d_mb_values,
+ * may be NULL) and of the next-obs critic output with `next_vals *= 1 - terminated`, AMP reward, and the
+ * discounted-return bookkeeping that produces the LocoVal regression target.  d_state is [6,N]:
+ * current_rewards, current_lengths, current_combined_rewards, discount_coefs, game_combined_rewards, terminated_flags. */
+typedef struct emloco_rollout_cfg {
+    float inversion_penalty_scale;   /* 0.3 */
+    float reward_scale;              /* reward_shaper.scale_value 1 */
+    float value_mean, value_std;     /* value_mean_std running stats: std = sqrt(var + 1e-5) */
+    float disc_reward_scale;         /* 2 */
+    float gamma;                     /* 0.99 */
+    int32_t step_to_pred;            /* 144 */
+    int32_t unnorm_value;            /* normalize_value */
+} emloco_rollout_cfg;
+int emloco_rollout_record(const emloco_rollout_cfg* cfg, const float* d_rew, const int64_t* d_reset,
+                          const int64_t* d_terminate, const float* d_value_raw, const float* d_next_value_raw,
+                          const float* d_disc_logit, const uint8_t* d_inverted, float* d_mb_values, float* d_mb_rewards,
+                          float* d_mb_dones, float* d_mb_next_values, float* d_mb_amp_rewards, float* d_state, int64_t N,
+                          void* stream);
+
+/* RunningMeanStd.forward, eval branch (pacer/pacer/utils/running_mean_std.py:82-84): y = clamp((x-mean)/sqrt(var+eps), +-5)
+ * on a [M,K] slice with row strides ldx/ldy (the self-obs part of the actor/critic input, amp_network_sept_builder.py:75,95). */
+int emloco_normalize(const float* d_x, int64_t ldx, float* d_y, int64_t ldy, int64_t M, int32_t K, const float* d_mean,
+                     const float* d_var, float eps, void* stream);
 
 int emloco_sync(emloco_sim* sim);
 const char* emloco_last_error(void);

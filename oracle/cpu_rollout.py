@@ -1,0 +1,115 @@
+"""TEST INFRASTRUCTURE ONLY - the whole rollout step on the CPU, assembled from the oracle pieces
+(oracle_np.py restatements of the reference's torch code + physics_oracle.c).  Used by
+  * tests/ as the end-to-end checker of `emloco_b200.rollout.Rollout`,
+  * bench.py's `cpu_baseline` leg and `--impl reference` arm (the reference's Isaac Gym CPU pipeline cannot run: its
+    binaries are absent, SURVEY 8c - so this "port" is the CPU number that can be had).
+The product never imports this module.
+
+One step = the body of the `for n in range(horizon_length)` loop of AMPValueAgent.play_steps
+(pacer/pacer/learning/amp_continuous_value.py:44-118) for n envs.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import oracle_np as O
+from . import physics_oracle as PO
+
+F = np.float32
+
+
+def weights_from_state_dict(sd):
+    """`a2c_network.*`-named tensors (torch or numpy) -> the P (policy) and D (discriminator) dicts of oracle_np."""
+    g = lambda k: np.asarray(sd[k].detach().cpu().numpy() if hasattr(sd[k], "detach") else sd[k], F)
+    lay = lambda p, i: (g(f"{p}.{i}.weight"), g(f"{p}.{i}.bias"))
+    lin = lambda p: (g(f"{p}.weight"), g(f"{p}.bias"))
+    P = dict(task=[lay("_task_mlp", 0), lay("_task_mlp", 2)], actor=[lay("actor_mlp", 0), lay("actor_mlp", 2)],
+             mu=lin("mu"), sigma=g("sigma"), critic=[lay("critic_mlp", 0), lay("critic_mlp", 2)], value=lin("value"),
+             tv=[lay("_task_value_mlp", 0), lay("_task_value_mlp", 2)], tv_out=lin("_value_logits"))
+    D = dict(mlp=[lay("_disc_mlp", 0), lay("_disc_mlp", 2)], logit=lin("_disc_logits"))
+    return P, D
+
+
+class CpuRollout:
+    def __init__(self, model_arrays, state, P, D, obs_stats=None, amp_stats=None, value_stats=(0.0, 1.0), gamma=0.99,
+                 disc_scale=2.0, step_to_pred=144, inv_penalty=0.3):
+        A = model_arrays
+        self.A = A
+        self.M = PO.make_model(A["parent"], A["offset"], A["mass"], A["com"], A["inertia6"], A["kp_joint"], A["kd_joint"],
+                               A["arm_joint"], A["geom_type"], A["geom_a"], A["geom_b"], A["geom_r"])
+        self.cfg = PO.make_cfg(1.0 / 120.0)
+        n = state["root"].shape[0]
+        self.n = n
+        self.init_root = state["root"].astype(np.float64)
+        self.init_dof = state["dof"].reshape(n, 69, 2).astype(np.float64)
+        self.verts = state["verts"].astype(F)
+        self.P, self.D = dict(P), dict(D)
+        self.P["mean"], self.P["var"] = obs_stats if obs_stats is not None else (np.zeros(1422), np.ones(1422))
+        self.D["mean"], self.D["var"] = amp_stats if amp_stats is not None else (np.zeros(3090), np.ones(3090))
+        self.v_mean, self.v_std = F(value_stats[0]), F(np.sqrt(F(value_stats[1]) + F(1e-5)))
+        self.gamma, self.disc_scale, self.step_to_pred, self.inv_penalty = F(gamma), disc_scale, step_to_pred, inv_penalty
+        self.height = np.zeros((1080, 1080), np.int16)
+        self.betas = np.zeros((n, 17), F)
+        # sim state
+        self.root = np.zeros((n, 13)); self.jq = np.zeros((n, 23, 4)); self.jw = np.zeros((n, 69))
+        self.progress = np.zeros(n, np.int64)
+        self.reset = np.ones(n, np.int64); self.terminate = np.zeros(n, np.int64)
+        self.amp_buf = np.zeros((n, 15, 206), F)
+        self.contact = np.zeros((n, 24, 3)); self.dof_force = np.zeros((n, 69))
+        self.state = np.zeros((6, n), F); self.state[3] = 1
+        self.obs = np.zeros((n, 1422), F)
+        self.reset_done()
+
+    # env_reset(done_indices): humanoid.py:455-481 + humanoid_amp.py:284-293,499-502 with a fixed initial state
+    def reset_done(self):
+        ids = np.nonzero(self.reset)[0]
+        if len(ids) == 0:
+            return
+        self.root[ids] = self.init_root[ids]
+        self.jq[ids] = PO.expmap_to_quat(self.init_dof[ids, :, 0]).reshape(len(ids), 23, 4)
+        self.jw[ids] = self.init_dof[ids, :, 1]
+        self.progress[ids] = 0; self.reset[ids] = 0; self.terminate[ids] = 0
+        self.contact[ids] = 0; self.dof_force[ids] = 0
+        rb, dp = PO.refresh(self.M, self.root[ids], self.jq[ids], self.jw[ids])
+        out = self._post(ids, rb, dp, advance=False)
+        self.obs[ids] = out["obs"]
+        self.amp_buf[ids] = out["amp_obs"].reshape(len(ids), 15, 206)[:, :1]      # history := current step
+
+    def _post(self, ids, rb, dof_pos, advance):
+        ds = np.stack([dof_pos, self.jw[ids]], -1).astype(F)
+        prog = self.progress[ids] + (1 if advance else 0)
+        return O.post_physics_step(rb.astype(F), ds, self.contact[ids].astype(F), self.dof_force[ids].astype(F), prog,
+                                   self.verts[ids], self.betas[ids], self.height, self.amp_buf[ids])
+
+    def step(self, noise):
+        n = self.n
+        self.reset_done()
+        obs = self.obs.copy()
+        pol = O.policy_forward(obs, self.P, noise=noise)
+        tgt = O.action_to_pd_targets(pol["actions"], self.A["pd_offset"], self.A["pd_scale"]).astype(np.float64)
+        rb, dp, ct, df = PO.step(self.M, self.cfg, 4, self.root, self.jq, self.jw, tgt, height=self.height)
+        self.contact, self.dof_force = ct, df
+        all_ids = np.arange(n)
+        out = self._post(all_ids, rb, dp, advance=True)
+        self.progress += 1
+        self.obs = out["obs"]; self.amp_buf = out["amp_obs"].reshape(n, 15, 206)
+        self.reset, self.terminate = out["reset"], out["terminate"]
+        nv_raw = O.critic_forward(self.obs, self.P)[:, 0]
+        amp_r, logit = O.disc_reward(out["amp_obs"], self.D, self.disc_scale)
+        amp_r = amp_r[:, 0]
+        # :63-118
+        r = out["rew"].astype(F)
+        done = (self.reset != 0).astype(F); term = self.terminate.astype(F)
+        unn = lambda v: self.v_std * np.clip(v, F(-5), F(5)) + self.v_mean
+        values = unn(pol["value"][:, 0]); next_values = unn(nv_raw) * (F(1) - term)
+        st = self.state
+        cr = st[0] + r; ln = st[1] + F(1); coef = st[3].copy()
+        cc = st[2] + (r + amp_r) * coef
+        nd = F(1) - done
+        sel = ((ln <= self.step_to_pred) & (done != 0)) | ((ln == self.step_to_pred) & (nd != 0))
+        st[4] += cc * sel.astype(F); st[2] = cc * nd
+        st[3] = np.where(done != 0, F(1), coef * self.gamma)
+        st[0] = cr * nd; st[1] = ln * nd; st[5] += term
+        return dict(obs=obs, actions=pol["actions"], neglogp=pol["neglogp"], mu=pol["mu"], values=values,
+                    task_values=pol["task_value"], rewards=r, dones=done, next_values=next_values, amp_rewards=amp_r,
+                    next_obs=self.obs, amp_obs=out["amp_obs"], rb=rb, disc_logit=logit)

@@ -1,0 +1,141 @@
+"""GPU: the rollout step (nets + env step + bookkeeping) through the C ABI against the CPU oracle assembly
+(oracle/cpu_rollout.py = oracle_np restatements pinned to the reference goldens + the fp64 physics restatement).
+Tolerance: north_star's 1e-3 relative for floats (with absolute floors scaled to each quantity), bit-exact masks."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-3
+
+
+def _pair(n, seed=0, **kw):
+    from emloco_b200.model import build_model_arrays, rest_root_height
+    from emloco_b200.policy import AMPSeptValueNetwork
+    from emloco_b200.rollout import Rollout
+    from emloco_b200.synthetic import synthetic_env_state
+    from oracle.cpu_rollout import CpuRollout, weights_from_state_dict
+    torch.manual_seed(seed)
+    net = AMPSeptValueNetwork()
+    P, D = weights_from_state_dict(net.state_dict())
+    A = build_model_arrays()
+    st = synthetic_env_state(n, seed, rest_root_height(A))
+    cpu = CpuRollout(A, st, P, D)
+    gpu = Rollout(n, seed=seed, net=net, **kw)
+    return gpu, cpu
+
+
+@pytest.mark.parametrize("tc", [False])
+def test_first_steps_match_cpu_oracle(tc):
+    n = 64
+    gpu, cpu = _pair(n, seed=3, tensor_cores=tc)
+    np.testing.assert_allclose(gpu.sim.obs.cpu().numpy()[:, :398], cpu.obs[:, :398], rtol=RTOL, atol=2e-5)
+    rng = np.random.default_rng(0)
+    for k in range(2):
+        noise = rng.standard_normal((n, 69)).astype(np.float32)
+        o = cpu.step(noise)
+        gpu.step(k, noise=torch.from_numpy(noise).cuda())
+        torch.cuda.synchronize()
+        mb = {key: v[k].cpu().numpy() for key, v in gpu.mb.items() if v is not None}
+        loose = 1.0 if k == 0 else 20.0       # step 2 starts from states that already differ by fp32-vs-fp64 round-off
+        np.testing.assert_allclose(mb["mus"], o["mu"], rtol=RTOL, atol=2e-4 * loose)
+        np.testing.assert_allclose(mb["actions"], o["actions"], rtol=RTOL, atol=2e-4 * loose)
+        np.testing.assert_allclose(mb["neglogpacs"], o["neglogp"], rtol=RTOL, atol=1e-3 * loose)
+        np.testing.assert_allclose(mb["values"][:, 0], o["values"], rtol=RTOL, atol=2e-4 * loose)
+        np.testing.assert_allclose(mb["task_values"], o["task_values"], rtol=RTOL, atol=2e-4 * loose)
+        np.testing.assert_allclose(gpu.sim.rb_state.view(n, 24, 13).cpu().numpy(), o["rb"], rtol=RTOL, atol=5e-3 * loose)
+        np.testing.assert_allclose(mb["rewards"][:, 0], o["rewards"], rtol=5e-3, atol=2e-2 * loose)
+        np.testing.assert_array_equal(mb["dones"], o["dones"])
+        np.testing.assert_allclose(mb["next_values"][:, 0], o["next_values"], rtol=RTOL, atol=5e-4 * loose)
+        np.testing.assert_allclose(mb["amp_rewards"][:, 0], o["amp_rewards"], rtol=RTOL, atol=2e-3 * loose)
+        np.testing.assert_allclose(gpu.state.cpu().numpy(), cpu.state, rtol=5e-3, atol=3e-2 * loose)
+    gpu.close()
+
+
+def test_nets_match_oracle_on_identical_obs():
+    """The networks alone on random (not simulated) observations: isolates the GEMM path from physics round-off."""
+    from emloco_b200.policy import AMPSeptValueNetwork, RolloutNets, RunningMeanStd
+    from oracle import oracle_np as O
+    from oracle.cpu_rollout import weights_from_state_dict
+    torch.manual_seed(1)
+    net = AMPSeptValueNetwork().cuda()
+    P, D = weights_from_state_dict(net.state_dict())
+    rng = np.random.default_rng(2)
+    M = 200
+    on, an = RunningMeanStd(1422).cuda(), RunningMeanStd(3090).cuda()
+    on.running_mean.copy_(torch.from_numpy(rng.normal(0, 0.5, 1422))); on.running_var.copy_(torch.from_numpy(rng.uniform(0.2, 3, 1422)))
+    an.running_mean.copy_(torch.from_numpy(rng.normal(0, 0.5, 3090))); an.running_var.copy_(torch.from_numpy(rng.uniform(0.2, 3, 3090)))
+    P["mean"], P["var"] = on.running_mean.cpu().numpy(), on.running_var.cpu().numpy()
+    D["mean"], D["var"] = an.running_mean.cpu().numpy(), an.running_var.cpu().numpy()
+    obs = rng.normal(0, 2, (M, 1422)).astype(np.float32)
+    amp = rng.normal(0, 2, (M, 3090)).astype(np.float32)
+    noise = rng.standard_normal((M, 69)).astype(np.float32)
+    ref = O.policy_forward(obs, P, noise=noise)
+    ref_c = O.critic_forward(obs, P)
+    ref_r, ref_l = O.disc_reward(amp, D)
+    for tc in (False,):
+        nets = RolloutNets(net, on, an, M, tensor_cores=tc)
+        res = nets.action_values(torch.from_numpy(obs).cuda(), torch.from_numpy(noise).cuda())
+        tol = dict(rtol=RTOL, atol=2e-4)
+        np.testing.assert_allclose(res["mus"].cpu().numpy(), ref["mu"], **tol)
+        np.testing.assert_allclose(res["values"].cpu().numpy(), ref["value"], **tol)
+        np.testing.assert_allclose(res["task_values"].cpu().numpy(), ref["task_value"], **tol)
+        np.testing.assert_allclose(res["actions"].cpu().numpy(), ref["actions"], **tol)
+        np.testing.assert_allclose(res["neglogpacs"].cpu().numpy(), ref["neglogp"], rtol=RTOL, atol=1e-3)
+        np.testing.assert_allclose(nets.critic(torch.from_numpy(obs).cuda()).cpu().numpy(), ref_c, **tol)
+        lg = nets.disc_logits(torch.from_numpy(amp).cuda())
+        np.testing.assert_allclose(lg.cpu().numpy(), ref_l, rtol=RTOL, atol=1e-3)
+        from emloco_b200.policy import disc_reward
+        r, comb = disc_reward(lg, torch.ones_like(lg))
+        np.testing.assert_allclose(r.cpu().numpy(), ref_r, rtol=RTOL, atol=2e-3)
+        np.testing.assert_allclose(comb.cpu().numpy(), 0.5 + 0.5 * ref_r, rtol=RTOL, atol=1e-3)
+
+
+def test_reset_done_restores_flagged_envs_only():
+    from emloco_b200.rollout import Rollout
+    n = 32
+    R = Rollout(n, seed=5)
+    noise = torch.zeros(n, 69, device="cuda")
+    for k in range(3):
+        R.step(k, noise=noise)
+    torch.cuda.synchronize()
+    before_rb = R.sim.rb_state.clone(); before_prog = R.sim.progress.clone(); before_amp = R.sim.amp_obs.clone()
+    R.sim.reset.zero_(); R.sim.reset[[1, 7]] = 1
+    R.sim.reset_done(R.init_root, R.init_dof)
+    torch.cuda.synchronize()
+    ch = (R.sim.rb_state.view(n, -1) != before_rb.view(n, -1)).any(1).cpu().numpy()
+    assert ch.tolist() == [i in (1, 7) for i in range(n)]
+    prog = R.sim.progress.cpu().numpy()
+    assert prog[1] == 0 and prog[7] == 0 and np.all(np.delete(prog, [1, 7]) == before_prog.cpu().numpy()[0] )
+    assert R.sim.reset.sum().item() == 0
+    amp = R.sim.amp_obs.cpu().numpy()
+    assert np.all(amp[1] == amp[1, :1]) and np.all(amp[7] == amp[7, :1])           # history filled with the current step
+    np.testing.assert_array_equal(np.delete(amp, [1, 7], 0), np.delete(before_amp.cpu().numpy(), [1, 7], 0))
+    np.testing.assert_allclose(R.sim.root_state[1].cpu().numpy(), R.init_root[1].cpu().numpy(), atol=1e-6)
+    R.close()
+
+
+def test_play_steps_horizon_and_gae_consistency():
+    """Full 32-step horizon at a small size: finite outputs, GAE recurrence holds on the stored rows, and the
+    post-horizon discriminator pass reproduces the per-step AMP rewards bit for bit (same rows, same weights)."""
+    from emloco_b200.rollout import Rollout
+    n = 128
+    R = Rollout(n, seed=2, horizon=32)
+    per_step = []
+    for k in range(32):
+        R.step(k)
+        per_step.append(R.mb["amp_rewards"][k].clone())
+    out = R.finish()
+    torch.cuda.synchronize()
+    for k, v in out.items():
+        assert torch.isfinite(v).all(), k
+    np.testing.assert_array_equal(torch.stack(per_step).cpu().numpy(), out["amp_rewards"].cpu().numpy())
+    d, v, r, nv, adv = (out[k].cpu().numpy().reshape(32, n) for k in ("dones", "values", "rewards", "next_values", "advantages"))
+    last = np.zeros(n, np.float32)
+    for t in reversed(range(32)):
+        last = (r[t] + 0.99 * nv[t] - v[t]) + 0.99 * 0.95 * (1 - d[t]) * last
+        np.testing.assert_allclose(adv[t], last, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(out["returns"].cpu().numpy().reshape(32, n), adv + v, rtol=1e-6, atol=1e-6)
+    assert 0 < R.locoval_scores.min().item() and R.locoval_scores.max().item() < 1
+    R.close()
