@@ -16,7 +16,8 @@ SYMBOLS = [
     "emloco_set_pd_targets", "emloco_simulate", "emloco_reset_indexed", "emloco_post_step", "emloco_step",
     "emloco_step_host", "emloco_locoval_forward", "emloco_locoval_backward", "emloco_locoval_forward_host",
     "emloco_plausibl_mlp_forward", "emloco_gae", "emloco_reset_done", "emloco_sample_actions",
-    "emloco_disc_reward", "emloco_rollout_record", "emloco_normalize", "emloco_physics_step", "emloco_linear", "emloco_sync", "emloco_last_error", "emloco_version",
+    "emloco_disc_reward", "emloco_rollout_record", "emloco_normalize", "emloco_physics_step", "emloco_split_bf16",
+    "emloco_linear_bf16x3", "emloco_linear", "emloco_sync", "emloco_last_error", "emloco_version",
 ]
 
 
@@ -89,6 +90,8 @@ def load():
     lib.emloco_disc_reward.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, vp]
     lib.emloco_rollout_record.argtypes = [C.POINTER(RolloutCfg), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
     lib.emloco_normalize.argtypes = [vp, i64, vp, i64, i64, i32, vp, vp, f32, vp]
+    lib.emloco_split_bf16.argtypes = [vp, i64, i64, i32, vp, vp, f32, vp, vp, i64, vp]
+    lib.emloco_linear_bf16x3.argtypes = [vp, vp, i64, vp, vp, i64, vp, i64, i32, i32, i32, vp, i64, vp, vp, i64, vp]
     lib.emloco_sync.argtypes = [vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
@@ -103,7 +106,7 @@ LAUNCHES = {"emloco_step": 2, "emloco_physics_step": 1, "emloco_post_step": 1, "
             "emloco_reset_indexed": 1, "emloco_linear": 1, "emloco_normalize": 1, "emloco_sample_actions": 1,
             "emloco_disc_reward": 1, "emloco_rollout_record": 1, "emloco_gae": 1, "emloco_locoval_forward": 1,
             "emloco_locoval_backward": 1, "emloco_plausibl_mlp_forward": 1, "emloco_step_host": 2,
-            "emloco_locoval_forward_host": 1}
+            "emloco_locoval_forward_host": 1, "emloco_split_bf16": 1, "emloco_linear_bf16x3": 1}
 launch_count = 0
 
 

@@ -350,6 +350,32 @@ int emloco_rollout_record(const emloco_rollout_cfg* c, const float* d_rew, const
     return EMLOCO_OK;
 }
 
+int emloco_split_bf16(const float* d_x, int64_t ldx, int64_t M, int32_t K, const float* d_mean, const float* d_var, float eps,
+                      uint16_t* d_hi, uint16_t* d_lo, int64_t ld16, void* stream) {
+    if (!d_x || !d_hi || !d_lo || M < 0 || K <= 0 || ldx < K || ld16 < K || (ld16 & 7) || ((uintptr_t)d_hi & 15) || ((uintptr_t)d_lo & 15))
+        return fail(EMLOCO_EINVAL, "emloco_split_bf16: bad argument (pitch must be a multiple of 8, pointers 16-byte aligned)");
+    if ((d_mean == nullptr) != (d_var == nullptr)) return fail(EMLOCO_EINVAL, "emloco_split_bf16: mean and var must come together");
+    CK(eml_split_bf16(d_x, ldx, M, K, d_mean, d_var, eps, d_hi, d_lo, ld16, (cudaStream_t)stream), "split bf16");
+    return EMLOCO_OK;
+}
+
+int emloco_linear_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, const uint16_t* w_hi, const uint16_t* w_lo,
+                         int64_t ldw, const float* d_bias, int64_t M, int32_t N, int32_t K, int32_t relu, float* d_y32, int64_t ldy,
+                         uint16_t* y_hi, uint16_t* y_lo, int64_t ldy16, void* stream) {
+    if (!a_hi || !a_lo || !w_hi || !w_lo || M < 0 || N <= 0 || K <= 0 || lda < K || ldw < K || (lda & 7) || (ldw & 7))
+        return fail(EMLOCO_EINVAL, "emloco_linear_bf16x3: bad operand");
+    if (((uintptr_t)a_hi | (uintptr_t)a_lo | (uintptr_t)w_hi | (uintptr_t)w_lo) & 15)
+        return fail(EMLOCO_EINVAL, "emloco_linear_bf16x3: operand pointers must be 16-byte aligned");
+    if (!d_y32 && !y_hi) return fail(EMLOCO_EINVAL, "emloco_linear_bf16x3: no output");
+    if (d_y32 && ldy < N) return fail(EMLOCO_EINVAL, "emloco_linear_bf16x3: ldy < N");
+    if ((y_hi == nullptr) != (y_lo == nullptr)) return fail(EMLOCO_EINVAL, "emloco_linear_bf16x3: y_hi and y_lo must come together");
+    if (y_hi && ((N & 31) || ldy16 < N || (ldy16 & 7) || (((uintptr_t)y_hi | (uintptr_t)y_lo) & 15)))
+        return fail(EMLOCO_EINVAL, "emloco_linear_bf16x3: split output needs N % 32 == 0, pitch % 8 == 0, 16-byte aligned pointers");
+    CK(eml_linear_bf16x3(a_hi, a_lo, lda, w_hi, w_lo, ldw, d_bias, M, N, K, relu, d_y32, ldy, y_hi, y_lo, ldy16, (cudaStream_t)stream),
+       "linear bf16x3 (tcgen05)");
+    return EMLOCO_OK;
+}
+
 int emloco_normalize(const float* d_x, int64_t ldx, float* d_y, int64_t ldy, int64_t M, int32_t K, const float* d_mean,
                      const float* d_var, float eps, void* stream) {
     if (!d_x || !d_y || !d_mean || !d_var || M < 0 || K <= 0 || ldx < K || ldy < K) return fail(EMLOCO_EINVAL, "emloco_normalize: bad argument");

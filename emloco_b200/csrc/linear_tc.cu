@@ -1,6 +1,388 @@
-// placeholder until the tcgen05 path lands (next commit): refuse loudly rather than fall back silently
+// Dense layers of the actor / critic / discriminator on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), sm_100a only.
+// Reference: the nn.Linear stacks of pacer/pacer/learning/amp_network_sept_builder.py:69-111, amp_network_builder.py:81-84
+// (SURVEY 8a rows a11-a13), which the reference runs as fp32 cuBLAS GEMMs (mixed_precision: False).
+//
+// PRECISION.  north_star asks for 1e-3 relative parity with the fp32 reference.  One bf16 pass (8-bit mantissa) gives
+// ~4e-3 and TF32 ~7e-4 after three layers - neither clears the bar element-wise - so every fp32 operand is split into
+// two bf16 terms  x = hi + lo  (hi = bf16(x), lo = bf16(x - hi), 16 mantissa bits together) and the product is formed as
+//      A*W ~= Ah*Wh + Ah*Wl + Al*Wh          (the dropped Al*Wl term is 2^-16 relative)
+// i.e. THREE kind::f16 MMAs per k-step into one fp32 TMEM accumulator ("bf16x3").  Measured error vs fp32: ~1e-5 relative.
+//
+// KERNEL.  Persistent, warp-specialised, one CTA per SM:
+//   warp 0 (one lane)  TMA producer: four 128B-swizzled K-major tiles per stage (Ah, Al: 128 x 64; Wh, Wl: BN x 64 bf16),
+//                      out-of-range rows / K-tail zero-filled by the TMA unit
+//   warp 1 (one lane)  MMA issuer: 4 k-steps x 3 tcgen05.mma (M=128, N=BN, K=16) per stage, tcgen05.commit frees the
+//                      stage and, after the last k-block, publishes the accumulator
+//   warps 2-5          epilogue: tcgen05.ld 32 lanes x 32 columns -> +bias, ReLU -> fp32 rows and/or the bf16 hi/lo split
+//                      that is the NEXT layer's A operand (the intermediate activations never exist as fp32 in HBM)
+//   TMEM: two BN-column accumulators, so the epilogue of tile i overlaps the main loop of tile i+1.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <mutex>
+#include <unordered_map>
 #include "sim.h"
-cudaError_t eml_linear_tc(const float*, long long, const float*, const float*, float*, long long, long long, int, int,
-                          const float*, const float*, float, int, cudaStream_t) {
-    return cudaErrorNotSupported;
+
+namespace tc {
+
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
+constexpr int NUM_THREADS = 192;   // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+
+template <int BN> struct Tile {
+    static constexpr int STAGES = BN == 128 ? 3 : 2;
+    static constexpr int A_BYTES = BM * BK * 2;            // one bf16 tile of A (hi or lo)
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int TMEM_COLS = 2 * BN;               // power of two: 256 or 512
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, issued by ONE thread for the CTA
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// K-major operand tile, 128-byte swizzle: rows of 64 bf16 (128 B), 8-row atoms 1024 B apart (SBO); LBO unused.
+// Bit layout: [0,14) addr>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version = 1 (sm_100), [61,64) layout = 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// instruction descriptor: D fp32 ([4,6) = 1), A and B bf16 ([7,10) = [10,13) = 1), both K-major, N>>3 at [17,23), M>>4 at [24,29)
+template <int BN> __device__ __forceinline__ constexpr uint32_t make_idesc() {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32"
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+                 " %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct GemmArgs {
+    const float* bias;       // [N] or NULL
+    float* y32; long long ldy;                       // fp32 output (optional)
+    __nv_bfloat16* y_hi; __nv_bfloat16* y_lo; long long ldy16;   // split output (optional; N % 32 == 0)
+    int M, N, K, relu;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+linear_bf16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+                     const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl, GemmArgs g) {
+    using T = Tile<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;            // SWIZZLE_128B tiles need 1024 B alignment
+    const uint32_t bars = base + T::STAGES * T::STAGE_BYTES;                // 8-byte mbarriers
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (T::STAGES + s); };
+    auto tfull_bar = [&](int a) { return bars + 8u * (2 * T::STAGES + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (2 * T::STAGES + 2 + a); };
+    const uint32_t tmem_slot = bars + 8u * (2 * T::STAGES + 4);
+    uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_m = (g.M + BM - 1) / BM, tiles_n = (g.N + BN - 1) / BN;
+    const int num_tiles = tiles_m * tiles_n;
+    const int num_kb = (g.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ah));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_al));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wh));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wl));
+        for (int s = 0; s < T::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    } else if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(T::TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== TMA producer =====================
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    const uint32_t sa = base + stage * T::STAGE_BYTES;
+                    mbar_expect_tx(full_bar(stage), T::STAGE_BYTES);
+                    tma_load_2d(sa, &map_ah, full_bar(stage), kb * BK, m0);
+                    tma_load_2d(sa + T::A_BYTES, &map_al, full_bar(stage), kb * BK, m0);
+                    tma_load_2d(sa + 2 * T::A_BYTES, &map_wh, full_bar(stage), kb * BK, n0);
+                    tma_load_2d(sa + 2 * T::A_BYTES + T::B_BYTES, &map_wl, full_bar(stage), kb * BK, n0);
+                    if (++stage == T::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===================== MMA issuer =====================
+            constexpr uint32_t idesc = make_idesc<BN>();
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);                  // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = base + stage * T::STAGE_BYTES;
+                    const uint64_t d_ah = make_smem_desc(sa), d_al = make_smem_desc(sa + T::A_BYTES);
+                    const uint64_t d_wh = make_smem_desc(sa + 2 * T::A_BYTES), d_wl = make_smem_desc(sa + 2 * T::A_BYTES + T::B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t ko = (uint64_t)((k * UMMA_K * 2) >> 4);   // advance inside the 128 B swizzle row
+                        umma_bf16(d_tmem, d_al + ko, d_wh + ko, idesc, (kb | k) != 0);   // small terms first
+                        umma_bf16(d_tmem, d_ah + ko, d_wl + ko, idesc, 1);
+                        umma_bf16(d_tmem, d_ah + ko, d_wh + ko, idesc, 1);
+                    }
+                    umma_commit(empty_bar(stage));                          // frees the smem stage when the MMAs retire
+                    if (++stage == T::STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tfull_bar(acc));                                // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5 -> TMEM lane quadrants 2,3,0,1) =====================
+        const int quad = warp & 3;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const int row = m0 + quad * 32 + lane;
+            const bool row_ok = row < g.M;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(taddr + c * 32, r);
+                tmem_ld_wait();
+                const int nb = n0 + c * 32;
+                if (nb >= g.N) continue;                                    // warp-uniform
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float x = __uint_as_float(r[j]);
+                    if (g.bias && nb + j < g.N) x += __ldg(g.bias + nb + j);
+                    v[j] = g.relu ? fmaxf(x, 0.f) : x;
+                }
+                if (row_ok) {
+                    if (g.y32) {
+                        float* o = g.y32 + (long long)row * g.ldy + nb;
+                        if (nb + 32 <= g.N && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (nb + j < g.N) o[j] = v[j];
+                        }
+                    }
+                    if (g.y_hi) {                                           // next layer's operand: x = hi + lo
+                        uint32_t ph[16], pl[16];
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            __nv_bfloat16 h0 = __float2bfloat16_rn(v[j]), h1 = __float2bfloat16_rn(v[j + 1]);
+                            __nv_bfloat16 l0 = __float2bfloat16_rn(v[j] - __bfloat162float(h0));
+                            __nv_bfloat16 l1 = __float2bfloat16_rn(v[j + 1] - __bfloat162float(h1));
+                            ph[j / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                            pl[j / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                        }
+                        uint4* oh = reinterpret_cast<uint4*>(g.y_hi + (long long)row * g.ldy16 + nb);
+                        uint4* ol = reinterpret_cast<uint4*>(g.y_lo + (long long)row * g.ldy16 + nb);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            oh[j] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
+                            ol[j] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty_bar(acc));                                   // 128 arrivals release the accumulator
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(T::TMEM_COLS));
+    }
+}
+
+// ---- fp32 -> (optional running-mean-std normalisation, utils/running_mean_std.py:82-84) -> bf16 hi/lo split ----
+// Only columns [0,K) are written: the TMA tensor maps carry the exact K, so pad columns of the pitch are never read.
+__global__ void split_bf16_kernel(const float* __restrict__ x, long long ldx, long long M, int K, const float* __restrict__ mean,
+                                  const float* __restrict__ var, float eps, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo, long long ld16) {
+    const int pairs = (K + 1) / 2;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * pairs) return;
+    long long r = i / pairs; int k = (int)(i - r * pairs) * 2;
+    float v[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        float a = 0.f;
+        if (k + u < K) {
+            a = x[r * ldx + k + u];
+            if (mean) { a = (a - mean[k + u]) / sqrtf(var[k + u] + eps); a = fminf(fmaxf(a, -5.0f), 5.0f); }
+        }
+        v[u] = a;
+    }
+    __nv_bfloat16 h0 = __float2bfloat16_rn(v[0]), h1 = __float2bfloat16_rn(v[1]);
+    __nv_bfloat16 l0 = __float2bfloat16_rn(v[0] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v[1] - __bfloat162float(h1));
+    if (k + 1 < K) {   // ld16 and k are even: 4-byte aligned pair store
+        *reinterpret_cast<uint32_t*>(hi + r * ld16 + k) = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        *reinterpret_cast<uint32_t*>(lo + r * ld16 + k) = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    } else {
+        hi[r * ld16 + k] = h0; lo[r * ld16 + k] = l0;
+    }
+}
+
+// ---- host side: tensor maps ----
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeFn get_encode() {
+    static EncodeFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeFn)p;
+    });
+    return fn;
+}
+
+// [rows, K] bf16, row pitch ld elements (ld % 8 == 0, base 16-byte aligned), box = box_rows x 64, 128B swizzle, zero OOB fill
+static bool make_map(CUtensorMap* m, const void* ptr, long long rows, int K, long long ld, int box_rows) {
+    EncodeFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int g_num_sms = 0;
+
+template <int BN>
+static cudaError_t launch(const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, long long lda, const __nv_bfloat16* w_hi,
+                          const __nv_bfloat16* w_lo, long long ldw, const GemmArgs& g, cudaStream_t st) {
+    using T = Tile<BN>;
+    CUtensorMap mah, mal, mwh, mwl;
+    if (!make_map(&mah, a_hi, g.M, g.K, lda, BM) || !make_map(&mal, a_lo, g.M, g.K, lda, BM) ||
+        !make_map(&mwh, w_hi, g.N, g.K, ldw, BN) || !make_map(&mwl, w_lo, g.N, g.K, ldw, BN))
+        return cudaErrorInvalidValue;
+    auto kern = linear_bf16x3_kernel<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    if (!g_num_sms) {
+        int dev = 0; cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
+    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    kern<<<grid, NUM_THREADS, T::SMEM, st>>>(mah, mal, mwh, mwl, g);
+    return cudaGetLastError();
+}
+
+}  // namespace tc
+
+cudaError_t eml_split_bf16(const float* x, long long ldx, long long M, int K, const float* mean, const float* var, float eps,
+                           void* hi, void* lo, long long ld16, cudaStream_t st) {
+    if (M <= 0 || K <= 0) return cudaSuccess;
+    long long n = M * ((K + 1) / 2);
+    tc::split_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, ldx, M, K, mean, var, eps, (__nv_bfloat16*)hi,
+                                                                        (__nv_bfloat16*)lo, ld16);
+    return cudaGetLastError();
+}
+
+cudaError_t eml_linear_bf16x3(const void* a_hi, const void* a_lo, long long lda, const void* w_hi, const void* w_lo, long long ldw,
+                              const float* bias, long long M, int N, int K, int relu, float* y32, long long ldy, void* y_hi,
+                              void* y_lo, long long ldy16, cudaStream_t st) {
+    if (M <= 0 || N <= 0) return cudaSuccess;
+    tc::GemmArgs g;
+    g.bias = bias; g.y32 = y32; g.ldy = ldy; g.y_hi = (__nv_bfloat16*)y_hi; g.y_lo = (__nv_bfloat16*)y_lo; g.ldy16 = ldy16;
+    g.M = (int)M; g.N = N; g.K = K; g.relu = relu;
+    return tc::launch<128>((const __nv_bfloat16*)a_hi, (const __nv_bfloat16*)a_lo, lda, (const __nv_bfloat16*)w_hi,
+                           (const __nv_bfloat16*)w_lo, ldw, g, st);
+}
+
+// fp32-in / fp32-out convenience path behind emloco_linear(use_tensor_cores = 1): splits both operands into stream-ordered
+// scratch, then runs the tcgen05 GEMM.  The rollout uses the explicit split / bf16x3 entry points with persistent buffers.
+cudaError_t eml_linear_tc(const float* x, long long ldx, const float* w, const float* b, float* y, long long ldy, long long M,
+                          int N, int K, const float* mean, const float* var, float eps, int relu, cudaStream_t st) {
+    if (M <= 0 || N <= 0) return cudaSuccess;
+    const long long kp = (K + 63) / 64 * 64;
+    __nv_bfloat16* scratch = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&scratch, (size_t)(2 * (M + N) * kp) * sizeof(__nv_bfloat16), st);
+    if (e != cudaSuccess) return e;
+    __nv_bfloat16 *ah = scratch, *al = ah + M * kp, *wh = al + M * kp, *wl = wh + (long long)N * kp;
+    if ((e = eml_split_bf16(x, ldx, M, K, mean, var, eps, ah, al, kp, st)) == cudaSuccess &&
+        (e = eml_split_bf16(w, K, N, K, nullptr, nullptr, 0.f, wh, wl, kp, st)) == cudaSuccess)
+        e = eml_linear_bf16x3(ah, al, kp, wh, wl, kp, b, M, N, K, relu, y, ldy, nullptr, nullptr, 0, st);
+    cudaError_t e2 = cudaFreeAsync(scratch, st);
+    return e != cudaSuccess ? e : e2;
 }

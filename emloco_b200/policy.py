@@ -101,6 +101,11 @@ class RolloutNets:
         self.d1, self.d2, self.logit = f(M, d1), f(M, d2), f(M, 1)
         self.actions, self.neglogp = f(M, ACTIONS), f(M)
         self._stacked = None
+        if self.tc:
+            S = lambda k: _Split(M, k, dev)
+            self.s_tin, self.s_t1, self.s_ain, self.s_ac1 = S(TASK_OBS), S(t1), S(SELF_OBS + t2), S(2 * a1)
+            self.s_a2, self.s_c2, self.s_amp, self.s_d1, self.s_d2 = S(a2), S(a2), S(AMP_OBS), S(d1), S(d2)
+            self.w16 = _TcWeights()
 
     def _w_ac1(self):
         n = self.net
@@ -113,12 +118,20 @@ class RolloutNets:
 
     def _lin(self, x, layer, relu, out, mean=None, var=None):
         return linear(x, layer.weight.detach(), layer.bias.detach(), relu=relu, mean=mean, var=var, out=out,
-                      eps=self.obs_norm.epsilon, tensor_cores=self.tc)
+                      eps=self.obs_norm.epsilon)
 
     def _trunk(self, obs):
         """normalise -> task MLP -> [norm(self obs) | task_out] (amp_network_sept_builder.py:69-76,82-96)."""
         n = self.net
         mean, var = self.obs_norm.f32()
+        if self.tc:
+            W, eps = self.w16.get, self.obs_norm.epsilon
+            split_bf16(obs[:, :SELF_OBS], self.s_ain.cols(0, SELF_OBS), mean[:SELF_OBS], var[:SELF_OBS], eps)
+            split_bf16(obs[:, SELF_OBS:], self.s_tin, mean[SELF_OBS:], var[SELF_OBS:], eps)
+            linear_bf16x3(self.s_tin, W("t0", n._task_mlp[0].weight), n._task_mlp[0].bias.detach(), True, y16=self.s_t1)
+            linear_bf16x3(self.s_t1, W("t2", n._task_mlp[2].weight), n._task_mlp[2].bias.detach(), True,
+                          y16=self.s_ain.cols(SELF_OBS, self.s_ain.K))
+            return mean, var
         normalize(obs[:, :SELF_OBS], mean[:SELF_OBS], var[:SELF_OBS], self.obs_norm.epsilon, out=self.ain[:, :SELF_OBS])
         self._lin(obs[:, SELF_OBS:], n._task_mlp[0], True, self.t1, mean[SELF_OBS:], var[SELF_OBS:])
         self._lin(self.t1, n._task_mlp[2], True, self.ain[:, SELF_OBS:])
@@ -135,12 +148,20 @@ class RolloutNets:
         neglogp_out = self.neglogp if neglogp_out is None else neglogp_out
         mean, var = self._trunk(obs)
         w, b = self._w_ac1()
-        linear(self.ain, w, b, relu=True, out=self.ac1, tensor_cores=self.tc)
         h = n.actor_mlp[0].out_features
-        self._lin(self.ac1[:, :h], n.actor_mlp[2], True, self.a2)
-        self._lin(self.ac1[:, h:], n.critic_mlp[2], True, self.c2)
-        self._lin(self.a2, n.mu, False, mu_out)
-        self._lin(self.c2, n.value, False, self.value)
+        if self.tc:
+            W = self.w16.get
+            linear_bf16x3(self.s_ain, W("ac1", w), b, True, y16=self.s_ac1)
+            linear_bf16x3(self.s_ac1.cols(0, h), W("a2", n.actor_mlp[2].weight), n.actor_mlp[2].bias.detach(), True, y16=self.s_a2)
+            linear_bf16x3(self.s_ac1.cols(h, 2 * h), W("c2", n.critic_mlp[2].weight), n.critic_mlp[2].bias.detach(), True, y16=self.s_c2)
+            linear_bf16x3(self.s_a2, W("mu", n.mu.weight), n.mu.bias.detach(), False, y32=mu_out)
+            linear_bf16x3(self.s_c2, W("value", n.value.weight), n.value.bias.detach(), False, y32=self.value)
+        else:
+            linear(self.ain, w, b, relu=True, out=self.ac1)
+            self._lin(self.ac1[:, :h], n.actor_mlp[2], True, self.a2)
+            self._lin(self.ac1[:, h:], n.critic_mlp[2], True, self.c2)
+            self._lin(self.a2, n.mu, False, mu_out)
+            self._lin(self.c2, n.value, False, self.value)
         # eval_task_value (amp_network_sept_value_builder.py:31-46): the 30 normalised trajectory features
         self._lin(obs[:, SELF_OBS:SELF_OBS + TRAJ_OBS], n._task_value_mlp[0], True, self.v1,
                   mean[SELF_OBS:SELF_OBS + TRAJ_OBS], var[SELF_OBS:SELF_OBS + TRAJ_OBS])
@@ -155,6 +176,12 @@ class RolloutNets:
         n = self.net
         self._trunk(obs)
         h = n.critic_mlp[0].out_features
+        if self.tc:
+            W = self.w16.get
+            linear_bf16x3(self.s_ain, W("c0", n.critic_mlp[0].weight), n.critic_mlp[0].bias.detach(), True, y16=self.s_ac1.cols(h, 2 * h))
+            linear_bf16x3(self.s_ac1.cols(h, 2 * h), W("c2", n.critic_mlp[2].weight), n.critic_mlp[2].bias.detach(), True, y16=self.s_c2)
+            linear_bf16x3(self.s_c2, W("value", n.value.weight), n.value.bias.detach(), False, y32=self.next_value)
+            return self.next_value
         self._lin(self.ain, n.critic_mlp[0], True, self.ac1[:, h:])
         self._lin(self.ac1[:, h:], n.critic_mlp[2], True, self.c2)
         self._lin(self.c2, n.value, False, self.next_value)
@@ -166,11 +193,80 @@ class RolloutNets:
         m = amp_obs.shape[0]
         mean, var = self.amp_norm.f32()
         out = self.logit[:m] if out is None else out
+        if self.tc:
+            W = self.w16.get
+            split_bf16(amp_obs, self.s_amp.rows_view(m), mean, var, self.amp_norm.epsilon)
+            linear_bf16x3(self.s_amp.rows_view(m), W("d0", n._disc_mlp[0].weight), n._disc_mlp[0].bias.detach(), True,
+                          y16=self.s_d1.rows_view(m))
+            linear_bf16x3(self.s_d1.rows_view(m), W("d2", n._disc_mlp[2].weight), n._disc_mlp[2].bias.detach(), True,
+                          y16=self.s_d2.rows_view(m))
+            linear_bf16x3(self.s_d2.rows_view(m), W("dl", n._disc_logits.weight), n._disc_logits.bias.detach(), False, y32=out)
+            return out
         linear(amp_obs, n._disc_mlp[0].weight.detach(), n._disc_mlp[0].bias.detach(), relu=True, mean=mean, var=var,
-               eps=self.amp_norm.epsilon, out=self.d1[:m], tensor_cores=self.tc)
+               eps=self.amp_norm.epsilon, out=self.d1[:m])
         self._lin(self.d1[:m], n._disc_mlp[2], True, self.d2[:m])
         self._lin(self.d2[:m], n._disc_logits, False, out)
         return out
+
+
+def _pad64(k):
+    return (k + 63) // 64 * 64
+
+
+class _Split:
+    """An fp32 [rows, K] matrix carried as two bf16 terms (x = hi + lo), row pitch padded to 64 elements for the TMA boxes."""
+
+    def __init__(self, rows, K, dev):
+        self.rows, self.K, self.ld = rows, K, _pad64(K)
+        self.hi = torch.zeros(rows, self.ld, device=dev, dtype=torch.bfloat16)
+        self.lo = torch.zeros(rows, self.ld, device=dev, dtype=torch.bfloat16)
+
+    def cols(self, a, b):
+        v = _Split.__new__(_Split)
+        v.rows, v.K, v.ld, v.hi, v.lo = self.rows, b - a, self.ld, self.hi[:, a:b], self.lo[:, a:b]
+        return v
+
+    def rows_view(self, m):
+        v = _Split.__new__(_Split)
+        v.rows, v.K, v.ld, v.hi, v.lo = m, self.K, self.ld, self.hi[:m], self.lo[:m]
+        return v
+
+
+def split_bf16(x, dst: _Split, mean=None, var=None, eps=1e-5):
+    M, K = x.shape
+    assert K == dst.K and M == dst.rows and x.stride(1) == 1
+    _lib.check(_lib.load().emloco_split_bf16(_ptr(x), x.stride(0), M, K, _ptr(mean), _ptr(var), eps, _ptr(dst.hi), _ptr(dst.lo),
+                                             dst.ld, _stream()), "emloco_split_bf16")
+    return dst
+
+
+def linear_bf16x3(a: _Split, w: _Split, bias, relu, y32=None, y16: _Split = None):
+    """y = act(a w^T + bias) on the tcgen05 path; fp32 output and/or split output for the next layer."""
+    M, K, N = a.rows, a.K, w.rows
+    assert w.K == K
+    if y32 is not None:
+        assert y32.shape == (M, N) and y32.stride(1) == 1
+    _lib.check(_lib.load().emloco_linear_bf16x3(
+        _ptr(a.hi), _ptr(a.lo), a.ld, _ptr(w.hi), _ptr(w.lo), w.ld, _ptr(bias), M, N, K, int(relu),
+        _ptr(y32), 0 if y32 is None else y32.stride(0), None if y16 is None else _ptr(y16.hi),
+        None if y16 is None else _ptr(y16.lo), 0 if y16 is None else y16.ld, _stream()), "emloco_linear_bf16x3")
+
+
+class _TcWeights:
+    """bf16 hi/lo copies of the nn.Linear weights, rebuilt when a parameter changes (optimizer step / load_state_dict)."""
+
+    def __init__(self):
+        self._c = {}
+
+    def get(self, name, weight):
+        key = (weight.data_ptr(), weight._version)
+        ent = self._c.get(name)
+        if ent is None or ent[0] != key:
+            w = weight.detach().float().contiguous()
+            sp = _Split(w.shape[0], w.shape[1], w.device)
+            split_bf16(w, sp)
+            self._c[name] = ent = (key, sp)
+        return ent[1]
 
 
 # ---- thin wrappers over the stateless C entry points -------------------------------------------------------

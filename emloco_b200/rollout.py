@@ -157,7 +157,9 @@ class Rollout:
                                                       _stream()), "emloco_disc_reward")
         adv, ret = gae(mb["dones"], mb["values"], self._comb(), mb["next_values"], self.gamma, self.tau)
         self.mb_advs, self.mb_returns = adv, ret
-        return dict(returns=ret, advantages=adv, rewards=self._comb(), **{k: v for k, v in mb.items() if v is not None})
+        out = {k: v for k, v in mb.items() if v is not None}
+        out.update(returns=ret, advantages=adv, task_rewards=mb["rewards"], rewards=self._comb())   # mb_rewards := combined (:160)
+        return out
 
     def _logits_TN(self):
         if not hasattr(self, "_lg"):

@@ -45,8 +45,7 @@ class _LocoValFn(torch.autograd.Function):
                                                       flags, _stream()), "emloco_locoval_forward")
         ctx.save_for_backward(traj, pose_saved, vel, wpack)
         ctx.flags, ctx.T = flags, T
-        if pose is not None and (flags & F_WRITEBACK):
-            ctx.mark_dirty(pose)
+        # the in-place rotation of `pose` (reference side effect) is not differentiated: pose is a plain input there too
         return value
 
     @staticmethod

@@ -177,7 +177,7 @@ int emloco_gae(const float* d_dones, const float* d_values, const float* d_rewar
  * y[M,N] = act( norm(x)[M,K] @ W[N,K]^T + b ), optional input normalisation
  * clamp((x-mean)/sqrt(var+eps),+-5) (utils/running_mean_std.py:60-84) folded into the operand load.
  * x row stride ldx, y row stride ldy (lets callers concatenate without a copy).  relu: 0/1.
- * mean/var may be NULL.  fp32 in/out; products in TF32 on the tensor cores when `use_tensor_cores`, else fp32 FMA. */
+ * mean/var may be NULL.  fp32 in/out; products by bf16x3 tcgen05 MMAs (see below) when `use_tensor_cores`, else fp32 FMA. */
 int emloco_linear(const float* d_x, int64_t ldx, const float* d_w, const float* d_b, float* d_y, int64_t ldy,
                   int64_t M, int32_t N, int32_t K, const float* d_mean, const float* d_var, float eps,
                   int32_t relu, int32_t use_tensor_cores, void* stream);
@@ -212,6 +212,22 @@ int emloco_rollout_record(const emloco_rollout_cfg* cfg, const float* d_rew, con
                           const float* d_disc_logit, const uint8_t* d_inverted, float* d_mb_values, float* d_mb_rewards,
                           float* d_mb_dones, float* d_mb_next_values, float* d_mb_amp_rewards, float* d_state, int64_t N,
                           void* stream);
+
+/* ---- tensor-core path of the same dense layers: fp32 operands carried as two bf16 terms (x = hi + lo), three tcgen05
+ * bf16 MMAs per k-step into an fp32 TMEM accumulator (A*W ~= Ah*Wh + Ah*Wl + Al*Wh): fp32-grade products at tensor-core
+ * rate, which is what keeps the 1e-3 parity bar of north_star (csrc/linear_tc.cu).  bf16 values are raw uint16_t bits.
+ *
+ * emloco_split_bf16: x[M,K] fp32 (row stride ldx), optional normalisation clamp((x-mean)/sqrt(var+eps),+-5)
+ * (utils/running_mean_std.py:82-84) -> hi/lo [M,K] bf16 with row pitch ld16 (ld16 % 8 == 0; pad columns are never read).
+ * emloco_linear_bf16x3: y = act(A W^T + b) with A = a_hi+a_lo [M,K] (pitch lda), W = w_hi+w_lo [N,K] (pitch ldw);
+ * writes fp32 y32 [M,N] (pitch ldy) and/or the split of y as the next layer's operand y_hi/y_lo (pitch ldy16, N % 32 == 0).
+ * All bf16 base pointers 16-byte aligned, pitches multiples of 8 elements. */
+int emloco_split_bf16(const float* d_x, int64_t ldx, int64_t M, int32_t K, const float* d_mean, const float* d_var, float eps,
+                      uint16_t* d_hi, uint16_t* d_lo, int64_t ld16, void* stream);
+int emloco_linear_bf16x3(const uint16_t* d_a_hi, const uint16_t* d_a_lo, int64_t lda, const uint16_t* d_w_hi,
+                         const uint16_t* d_w_lo, int64_t ldw, const float* d_bias, int64_t M, int32_t N, int32_t K,
+                         int32_t relu, float* d_y32, int64_t ldy, uint16_t* d_y_hi, uint16_t* d_y_lo, int64_t ldy16,
+                         void* stream);
 
 /* RunningMeanStd.forward, eval branch (pacer/pacer/utils/running_mean_std.py:82-84): y = clamp((x-mean)/sqrt(var+eps), +-5)
  * on a [M,K] slice with row strides ldx/ldy (the self-obs part of the actor/critic input, amp_network_sept_builder.py:75,95). */

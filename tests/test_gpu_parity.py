@@ -209,3 +209,47 @@ def test_linear_fma_matches_oracle():
                mean=torch.from_numpy(mean[368:]).cuda(), var=torch.from_numpy(var[368:]).cuda())
     ref = np.maximum(O.rms_normalize(x, mean, var)[:, 368:] @ w.T + b, 0)
     np.testing.assert_allclose(y.cpu().numpy(), ref, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("M,N,K,relu", [(128, 128, 64, False), (300, 512, 1054, True), (4096, 69, 1024, False),
+                                        (1000, 1, 512, False), (257, 1024, 3090, True), (64, 256, 624, True)])
+def test_linear_bf16x3_tensor_core_matches_fp64(M, N, K, relu):
+    """tcgen05 path: fp32 operands split into bf16 hi+lo, three MMAs per k-step.  Checked against float64 numpy; the
+    documented error of the split is ~2^-16 relative to sum|a||w|, far inside north_star's 1e-3."""
+    from emloco_b200.sim import linear
+    rng = np.random.default_rng(M + N + K)
+    x = rng.normal(0, 1.5, (M, K)).astype(np.float32)
+    w = (rng.normal(0, 1, (N, K)) / np.sqrt(K)).astype(np.float32)
+    b = rng.normal(0, 0.1, N).astype(np.float32)
+    y = linear(torch.from_numpy(x).cuda(), torch.from_numpy(w).cuda(), torch.from_numpy(b).cuda(), relu=relu, tensor_cores=True)
+    ref = x.astype(np.float64) @ w.astype(np.float64).T + b
+    if relu:
+        ref = np.maximum(ref, 0)
+    err = np.abs(y.cpu().numpy() - ref)
+    scale = np.abs(x).astype(np.float64) @ np.abs(w).astype(np.float64).T + np.abs(b)
+    assert (err / scale).max() < 1e-4, (err / scale).max()
+    np.testing.assert_allclose(y.cpu().numpy(), ref, rtol=1e-3, atol=1e-4)
+
+
+def test_linear_bf16x3_split_output_chains_layers():
+    """Two chained layers through the split (hi/lo) epilogue output, with input normalisation, against float64."""
+    from emloco_b200.policy import _Split, linear_bf16x3, split_bf16
+    rng = np.random.default_rng(5)
+    M, K, H, N = 500, 1054, 512, 256
+    x = rng.normal(0, 2, (M, K)).astype(np.float32)
+    mean = rng.normal(0, 1, K).astype(np.float32); var = rng.uniform(0.1, 4, K).astype(np.float32)
+    w1 = (rng.normal(0, 1, (H, K)) / np.sqrt(K)).astype(np.float32); b1 = rng.normal(0, 0.1, H).astype(np.float32)
+    w2 = (rng.normal(0, 1, (N, H)) / np.sqrt(H)).astype(np.float32); b2 = rng.normal(0, 0.1, N).astype(np.float32)
+    T = lambda a: torch.from_numpy(a).cuda()
+    sx, s1, sw1, sw2 = _Split(M, K, "cuda"), _Split(M, H, "cuda"), _Split(H, K, "cuda"), _Split(N, H, "cuda")
+    split_bf16(T(x), sx, T(mean), T(var), 1e-5); split_bf16(T(w1), sw1); split_bf16(T(w2), sw2)
+    y = torch.empty(M, N, device="cuda")
+    linear_bf16x3(sx, sw1, T(b1), True, y16=s1)
+    linear_bf16x3(s1, sw2, T(b2), True, y32=y)
+    xn = np.clip((x.astype(np.float64) - mean) / np.sqrt(var.astype(np.float64) + 1e-5), -5, 5)
+    h = np.maximum(xn @ w1.T.astype(np.float64) + b1, 0)
+    ref = np.maximum(h @ w2.T.astype(np.float64) + b2, 0)
+    np.testing.assert_allclose(y.cpu().numpy(), ref, rtol=1e-3, atol=1e-4)
+    # the split itself: hi + lo reproduces the fp32 value to 2^-16
+    rec = (sx.hi.float() + sx.lo.float())[:, :K].cpu().numpy()
+    np.testing.assert_allclose(rec, xn, rtol=2e-5, atol=1e-6)

@@ -26,7 +26,7 @@ def _pair(n, seed=0, **kw):
     return gpu, cpu
 
 
-@pytest.mark.parametrize("tc", [False])
+@pytest.mark.parametrize("tc", [False, True])
 def test_first_steps_match_cpu_oracle(tc):
     n = 64
     gpu, cpu = _pair(n, seed=3, tensor_cores=tc)
@@ -74,7 +74,7 @@ def test_nets_match_oracle_on_identical_obs():
     ref = O.policy_forward(obs, P, noise=noise)
     ref_c = O.critic_forward(obs, P)
     ref_r, ref_l = O.disc_reward(amp, D)
-    for tc in (False,):
+    for tc in (False, True):
         nets = RolloutNets(net, on, an, M, tensor_cores=tc)
         res = nets.action_values(torch.from_numpy(obs).cuda(), torch.from_numpy(noise).cuda())
         tol = dict(rtol=RTOL, atol=2e-4)
