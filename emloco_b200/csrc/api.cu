@@ -39,6 +39,8 @@ void emloco_default_cfg(emloco_cfg* c) {
     c->contact_offset = 0.02f; c->max_ang_vel = 100.0f; c->angular_damping = 0.01f;
     c->episode_length = 168; c->power_coefficient = 0.0005f; c->location_coefficient = 1.0f;
     c->fail_dist = 4.0f; c->traj_sample_dt = 0.4f;
+    c->max_effort = 500.0f;                                                 // smpl_humanoid.xml:171-233 motor gear
+    c->max_turn = 0.1f;
 }
 
 int emloco_create(const emloco_cfg* cfg, const emloco_model* model, emloco_sim** out) {
@@ -243,6 +245,7 @@ int emloco_step_host(emloco_sim* s, const float* h_actions, float* h_obs, float*
 
 int emloco_locoval_forward(const float* d_traj, int32_t traj_stride, int32_t T, float* d_pose, const float* d_vel,
                            const float* d_weights, float* d_value, int64_t batch, int32_t flags, void* stream) {
+    if (batch == 0) return EMLOCO_OK;
     if (!d_traj || !d_weights || !d_value) return fail(EMLOCO_EINVAL, "emloco_locoval_forward: null argument");
     if ((flags & 1) && !d_pose) return fail(EMLOCO_EINVAL, "emloco_locoval_forward: init_pose should be included");   // value_pose_net.py:114,136
     if ((flags & 2) && !d_vel) return fail(EMLOCO_EINVAL, "emloco_locoval_forward: init_vel should be included");
@@ -254,6 +257,7 @@ int emloco_locoval_forward(const float* d_traj, int32_t traj_stride, int32_t T, 
 int emloco_locoval_backward(const float* d_traj, int32_t traj_stride, int32_t T, const float* d_pose, const float* d_vel,
                             const float* d_weights, const float* d_grad_value, float* d_grad_traj, int64_t batch, int32_t flags,
                             void* stream) {
+    if (batch == 0) return EMLOCO_OK;
     if (!d_traj || !d_weights || !d_grad_value || !d_grad_traj) return fail(EMLOCO_EINVAL, "emloco_locoval_backward: null argument");
     if ((flags & 1) && !d_pose) return fail(EMLOCO_EINVAL, "emloco_locoval_backward: init_pose should be included");
     if ((flags & 2) && !d_vel) return fail(EMLOCO_EINVAL, "emloco_locoval_backward: init_vel should be included");

@@ -96,7 +96,7 @@ struct PhysParams {
     const float* init_root;             // FK-only mode: take the state from these buffers instead of root/dof
     const float* init_dof;
     int N; int n_sub; float dt;
-    float gz, kn, cn, ct, mu, max_w;
+    float gz, kn, cn, ct, mu, max_w, max_effort, max_turn;
     int fk_only;
 };
 
@@ -165,16 +165,21 @@ __global__ void __launch_bounds__(PH_WARPS * 32) physics_kernel(PhysParams P) {
             }
         }
     }
-    const float dt = P.dt;
-    const float dd_pd = dt * (kd + kp * dt);              // implicit PD: extra joint-space inertia
     f3 fsum = mk3(0, 0, 0);                               // contact force accumulated over the sub-steps
     f3 drive = mk3(0, 0, 0);                              // last drive torque, child frame
+    f4 qtgt = mk4(0, 0, 0, 1);
+    if (joint && !P.fk_only) qtgt = exp_quat(target);     // drive target as a rotation
 
     const int n_sub = P.fk_only ? 0 : P.n_sub;
+    // Adaptive refinement: the explicit velocity-product terms gain energy like (|w| dt)^2, so a nominal sub-step is split
+    // into `parts` equal pieces until no body turns more than max_turn radians per piece (parts <= 8).  One warp = one env,
+    // so the trip count is warp-uniform.
+    int sub = 0, part = 0, parts = 1;
+    float dt = P.dt;
 #pragma unroll 1
-    for (int sub = 0; sub < n_sub; ++sub) {
-        // ================= pass 1: kinematics =================
-        f4 qw = q0; f3 x = mk3(0, 0, 0); f3 vw = w0, vl = v0;       // lane 0 (and template for the others)
+    while (sub < n_sub) {
+        // ================= pass 1: kinematics (in the inertial frame translating with the pelvis velocity v0) =================
+        f4 qw = q0; f3 x = mk3(0, 0, 0); f3 vw = w0, vl = mk3(0, 0, 0);   // lane 0 (and template for the others)
         f3 cw_ = mk3(0, 0, 0), cl_ = mk3(0, 0, 0);                  // velocity-product acceleration c_i
         f3 ww = mk3(0, 0, 0);
 #pragma unroll 1
@@ -190,6 +195,18 @@ __global__ void __launch_bounds__(PH_WARPS * 32) physics_kernel(PhysParams P) {
                 cl_ = cross3(wp, jl) + cross3(lp, ww);
             }
         }
+        if (part == 0) {
+            parts = 1; dt = P.dt;
+            if (P.max_turn > 0.f) {
+                float wm = body ? sqrtf(dot3(vw, vw)) : 0.f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(FULL, wm, o));
+                int k = (int)ceilf(wm * P.dt / P.max_turn);
+                parts = k < 1 ? 1 : (k > 8 ? 8 : k);
+                dt = P.dt / (float)parts;
+            }
+        }
+        const float dd_pd_full = dt * (kd + kp * dt);         // implicit PD: extra joint-space inertia
         const M3 R = quat_to_mat(qw);
         // ================= rigid-body inertia about O, bias force, gravity =================
         S3 A, Mm; M3 Bm; f3 pn, pf;
@@ -237,7 +254,7 @@ __global__ void __launch_bounds__(PH_WARPS * 32) physics_kernel(PhysParams P) {
                 r.z -= drop;
                 float gap = p0.z + r.z - ground_height(P, p0.x + r.x, p0.y + r.y);
                 if (gap >= 0.f) continue;
-                f3 vp = vl + cross3(vw, r);
+                f3 vp = v0 + vl + cross3(vw, r);                    // absolute velocity of the contact point
                 float fn = -P.kn * gap - bn * vp.z;
                 if (fn <= 0.f) continue;                             // separating: no adhesion
                 float vt = sqrtf(vp.x * vp.x + vp.y * vp.y);
@@ -259,11 +276,18 @@ __global__ void __launch_bounds__(PH_WARPS * 32) physics_kernel(PhysParams P) {
         }
         // ================= implicit PD drive =================
         f3 tau0 = mk3(0, 0, 0);
+        float dd_pd = dd_pd_full;
         if (joint) {
-            f3 qe = log_quat(jq);
+            // position error on SO(3): e = log(q^-1 * exp(target)), child frame; = target - log q to first order, defined
+            // for every target (component-wise targets of norm > pi are legal actions), zero exactly at the target
+            f3 e = log_quat(qmul(qconj(jq), qtgt));
+            // effort limit (MJCF motor gear -> DOF effort): scale the whole drive, implicit part included
+            float tm = fmaxf(fmaxf(fabsf(kp * e.x - kd * jw.x), fabsf(kp * e.y - kd * jw.y)), fabsf(kp * e.z - kd * jw.z));
+            float sat = (P.max_effort > 0.f && tm > P.max_effort) ? P.max_effort / tm : 1.0f;
             float kk = kd + kp * dt;
-            f3 t0 = mk3(kp * (target.x - qe.x) - kk * jw.x, kp * (target.y - qe.y) - kk * jw.y, kp * (target.z - qe.z) - kk * jw.z);
+            f3 t0 = mk3(sat * (kp * e.x - kk * jw.x), sat * (kp * e.y - kk * jw.y), sat * (kp * e.z - kk * jw.z));
             tau0 = mv(R, t0);
+            dd_pd = sat * dd_pd_full;
         }
         // ================= pass 2: articulated inertias, leaves -> root =================
         M3 Ut, Ub; S3 Di; f3 u = mk3(0, 0, 0);
@@ -349,10 +373,11 @@ __global__ void __launch_bounds__(PH_WARPS * 32) physics_kernel(PhysParams P) {
         }
         // ================= contact force at the end-of-step velocity, drive torque =================
         {
-            f3 wn = vw + aw * dt, ln = vl + al * dt;
-            fsum.x += -Sbt * ln.x + (-Stz * wn.y + Sty * wn.z);
-            fsum.y += -Sbt * ln.y + (Stz * wn.x - Stx * wn.z);
-            fsum.z += F0z - Sbn * ln.z + (-Sny * wn.x + Snx * wn.y);
+            f3 wn = vw + aw * dt, ln = v0 + vl + al * dt;
+            const float wgt = 1.0f / (float)parts;
+            fsum.x += wgt * (-Sbt * ln.x + (-Stz * wn.y + Sty * wn.z));
+            fsum.y += wgt * (-Sbt * ln.y + (Stz * wn.x - Stx * wn.z));
+            fsum.z += wgt * (F0z - Sbn * ln.z + (-Sny * wn.x + Snx * wn.y));
         }
         // ================= integrate =================
         if (joint) {
@@ -364,13 +389,16 @@ __global__ void __launch_bounds__(PH_WARPS * 32) physics_kernel(PhysParams P) {
         }
         {   // root, computed redundantly by every lane from lane 0's acceleration
             f3 a0w = shfl3(aw, 0), a0l = shfl3(al, 0);
-            f3 wn = w0 + a0w * dt, vO = v0 + a0l * dt;
+            f3 wn = w0 + a0w * dt, vO = a0l * dt;                    // vO: in-frame velocity gained by the pelvis point
+            float n2 = dot3(wn, wn);
+            if (n2 > P.max_w * P.max_w) wn = wn * (P.max_w * rsqrtf(n2));    // maxAngularVelocity (humanoid.py:685-688)
             q0 = qnormalize(qmul(exp_quat(wn * dt), q0));
-            f3 dp = vO * dt;
-            p0 = p0 + dp;
-            v0 = vO + cross3(wn, dp);                                // re-reference the spatial velocity to the new origin
+            f3 vn = v0 + vO;
+            p0 = p0 + vn * dt;
+            v0 = vn + cross3(wn, vO * dt);                           // re-reference to the moved origin (second order)
             w0 = wn;
         }
+        if (++part == parts) { part = 0; ++sub; }
     }
 
     // ================= refresh: forward kinematics -> rigid-body state, DOF state =================
@@ -435,6 +463,7 @@ static void fill_params(emloco_sim* s, PhysParams& P) {
     P.env_ids = nullptr; P.reset_mask = nullptr; P.init_root = nullptr; P.init_dof = nullptr; P.N = s->N; P.n_sub = 0; P.dt = s->cfg.sim_dt / (float)s->cfg.substeps;
     P.gz = s->cfg.gravity_z; P.kn = s->cfg.contact_stiffness; P.cn = s->cfg.contact_damping;
     P.ct = s->cfg.friction_damping; P.mu = s->cfg.friction_mu; P.max_w = s->cfg.max_ang_vel;
+    P.max_effort = s->cfg.max_effort; P.max_turn = s->cfg.max_turn;
     P.fk_only = 0;
 }
 

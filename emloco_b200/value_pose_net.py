@@ -37,6 +37,10 @@ class _LocoValFn(torch.autograd.Function):
         B = traj.shape[0]
         stride = traj.shape[-1]
         value = torch.empty(B, 1, device=traj.device, dtype=torch.float32)
+        if B == 0:                                  # empty batch: nothing to launch (data_ptr() of an empty tensor is NULL)
+            ctx.save_for_backward(traj, None, vel, wpack)
+            ctx.flags, ctx.T = flags, T
+            return value
         need_grad = traj.requires_grad
         pose_saved = None
         if pose is not None and need_grad:
@@ -53,6 +57,8 @@ class _LocoValFn(torch.autograd.Function):
         traj, pose, vel, wpack = ctx.saved_tensors
         g = gvalue.contiguous().float()
         gtraj = torch.empty_like(traj)
+        if traj.shape[0] == 0:
+            return gtraj, None, None, None, None, None
         _lib.check(_lib.load().emloco_locoval_backward(_p(traj), traj.shape[-1], ctx.T, _p(pose), _p(vel), _p(wpack), _p(g),
                                                        _p(gtraj), traj.shape[0], ctx.flags & ~F_WRITEBACK, _stream()),
                    "emloco_locoval_backward")

@@ -46,7 +46,9 @@ typedef struct emloco_cfg {
     float   location_coefficient; /* 1 */
     float   fail_dist;            /* 4.0 (humanoid_traj.py:31) */
     float   traj_sample_dt;       /* 0.4 */
-    int32_t reserved[8];
+    float   max_effort;           /* 500: drive torque limit per DOF (MJCF motor gear -> Isaac Gym DOF `effort`); <= 0 off */
+    float   max_turn;             /* 0.1 rad: a sub-step is refined until no body turns more than this per piece; <= 0 off */
+    int32_t reserved[6];
 } emloco_cfg;
 
 /* Articulation + collision model: what gym.load_asset/create_actor build from

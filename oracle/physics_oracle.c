@@ -46,6 +46,8 @@ typedef struct {
     double gravity_z;
     double kn, cn, ct, mu;
     double max_ang_vel;
+    double max_turn;           /* adaptive refinement threshold: largest body rotation per integration part [rad]; <= 0: off */
+    double max_effort;         /* drive torque limit per DOF (MJCF motor gear 500 -> Isaac Gym DOF `effort`); <= 0: unlimited */
     int    hf_rows, hf_cols;
 } OCfg;
 
@@ -165,14 +167,18 @@ static void substep(const OModel* m, const OCfg* c, double* root, double* jq, do
                     const int16_t* hf, double* contact, double* dof_force) {
     const double dt = c->dt;
     double R[NB][3][3], x[NB][3], v[NB][6], cj[NB][6], ww[NB][3];
-    double IA[NB][6][6], pA[NB][6], U[NB][6][3], Dinv[NB][3][3], u[NB][3], tau0[NB][3];
+    double IA[NB][6][6], pA[NB][6], U[NB][6][3], Dinv[NB][3][3], u[NB][3], tau0[NB][3], sat[NB];
     double fc0[NB][8][3], Bc[NB][8][3], rc[NB][8][3]; int nact[NB];
     const double* O = root;   /* reference point: pelvis position, fixed during the sub-step */
 
     /* ---- pass 1: kinematics, root -> leaves ---- */
     quat_to_mat(root + 3, R[0]);
     x[0][0] = x[0][1] = x[0][2] = 0;
-    for (int k = 0; k < 3; ++k) { v[0][k] = root[10 + k]; v[0][3 + k] = root[7 + k]; }
+    /* Dynamics are evaluated in the inertial frame that translates with the pelvis' velocity V at the start of the sub-step
+     * (Galilean invariance): spatial velocities stay O(relative motion), so the velocity-product terms never contain the
+     * large, mutually cancelling  w x V  pieces.  V re-enters only where absolute velocities matter (contacts). */
+    const double V[3] = {root[7], root[8], root[9]};
+    for (int k = 0; k < 3; ++k) { v[0][k] = root[10 + k]; v[0][3 + k] = 0.0; }
     memset(cj[0], 0, sizeof cj[0]);
     for (int i = 1; i < NB; ++i) {
         int p = m->parent[i];
@@ -231,7 +237,7 @@ static void substep(const OModel* m, const OCfg* c, double* root, double* jq, do
             if (gap >= 0) continue;
             double vp[3], wr[3];
             cross(v[i], r, wr);
-            for (int a = 0; a < 3; ++a) vp[a] = v[i][3 + a] + wr[a];
+            for (int a = 0; a < 3; ++a) vp[a] = V[a] + v[i][3 + a] + wr[a];
             double bn = c->kn * dt + c->cn;
             double fn_est = -c->kn * gap - bn * vp[2];
             if (fn_est <= 0) continue;                      /* separating: no adhesion */
@@ -257,10 +263,24 @@ static void substep(const OModel* m, const OCfg* c, double* root, double* jq, do
             }
         }
         if (i > 0) {   /* implicit PD: tau = kp (tgt - q - dt w') - kd w',  w' = w + dt wdot */
-            double qe[3], t0[3];
-            log_quat(jq + 4 * (i - 1), qe);
+            /* position error on SO(3): the rotation that takes the joint from q to exp(target), as a rotation vector in
+             * the child frame, e = log(q^-1 * exp(target)).  Equal to (target - log q) to first order, but defined for
+             * every target (component-wise targets of norm > pi are legal actions) and zero exactly at the target. */
+            double qt[4], qi[4], qd[4], e[3], t0[3];
+            exp_quat(target + 3 * (i - 1), qt);
+            qi[0] = -jq[4 * (i - 1)]; qi[1] = -jq[4 * (i - 1) + 1]; qi[2] = -jq[4 * (i - 1) + 2]; qi[3] = jq[4 * (i - 1) + 3];
+            qmul(qi, qt, qd);
+            log_quat(qd, e);
+            /* effort limit: when the PD torque at the current state exceeds max_effort on any axis, the whole drive
+             * (spring, damper and their implicit part) is scaled back so that the largest component equals the limit */
+            double tmax = 0;
+            for (int k = 0; k < 3; ++k) {
+                double te = m->kp[i] * e[k] - m->kd[i] * jw[3 * (i - 1) + k];
+                if (fabs(te) > tmax) tmax = fabs(te);
+            }
+            sat[i] = (c->max_effort > 0 && tmax > c->max_effort) ? c->max_effort / tmax : 1.0;
             for (int k = 0; k < 3; ++k)
-                t0[k] = m->kp[i] * (target[3 * (i - 1) + k] - qe[k]) - (m->kd[i] + m->kp[i] * dt) * jw[3 * (i - 1) + k];
+                t0[k] = sat[i] * (m->kp[i] * e[k] - (m->kd[i] + m->kp[i] * dt) * jw[3 * (i - 1) + k]);
             mat3_vec(R[i], t0, tau0[i]);
         }
     }
@@ -273,7 +293,7 @@ static void substep(const OModel* m, const OCfg* c, double* root, double* jq, do
         for (int a = 0; a < 6; ++a) for (int b = 0; b < 3; ++b) { U[i][a][b] = 0; for (int k = 0; k < 6; ++k) U[i][a][b] += IA[i][a][k] * S[k][b]; }
         double D[3][3];
         for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { D[a][b] = 0; for (int k = 0; k < 6; ++k) D[a][b] += S[k][a] * U[i][k][b]; }
-        double dd = m->arm[i] + dt * (m->kd[i] + m->kp[i] * dt);
+        double dd = m->arm[i] + sat[i] * dt * (m->kd[i] + m->kp[i] * dt);
         for (int a = 0; a < 3; ++a) D[a][a] += dd;
         inv3(D, Dinv[i]);
         for (int a = 0; a < 3; ++a) { u[i][a] = tau0[i][a]; for (int k = 0; k < 6; ++k) u[i][a] -= S[k][a] * pA[i][k]; }
@@ -313,11 +333,11 @@ static void substep(const OModel* m, const OCfg* c, double* root, double* jq, do
         for (int a = 0; a < 6; ++a) vn[a] = v[i][a] + dt * acc[i][a];
         if (contact) for (int q = 0; q < nact[i]; ++q) {
             double wr[3]; cross(vn, rc[i][q], wr);
-            for (int a = 0; a < 3; ++a) contact[3 * i + a] += fc0[i][q][a] - Bc[i][q][a] * (vn[3 + a] + wr[a]);
+            for (int a = 0; a < 3; ++a) contact[3 * i + a] += fc0[i][q][a] - Bc[i][q][a] * (V[a] + vn[3 + a] + wr[a]);
         }
         if (i > 0) {
             double tw[3], tb[3];
-            double dd = dt * (m->kd[i] + m->kp[i] * dt);
+            double dd = sat[i] * dt * (m->kd[i] + m->kp[i] * dt);
             for (int a = 0; a < 3; ++a) tw[a] = tau0[i][a] - dd * wdot[i][a];
             mat3T_vec(R[i], tw, tb);
             if (dof_force) for (int a = 0; a < 3; ++a) dof_force[3 * (i - 1) + a] = tb[a];
@@ -339,13 +359,19 @@ static void substep(const OModel* m, const OCfg* c, double* root, double* jq, do
     {
         double wn[3], vO[3], h[3], dq[4], t[3];
         for (int a = 0; a < 3; ++a) { wn[a] = v[0][a] + dt * acc[0][a]; vO[a] = v[0][3 + a] + dt * acc[0][3 + a]; }
+        double wlen = sqrt(wn[0] * wn[0] + wn[1] * wn[1] + wn[2] * wn[2]);
+        if (wlen > c->max_ang_vel) for (int a = 0; a < 3; ++a) wn[a] *= c->max_ang_vel / wlen;   /* maxAngularVelocity, humanoid.py:685-688 */
         for (int a = 0; a < 3; ++a) h[a] = dt * wn[a];
         exp_quat(h, dq);
         qmul(dq, root + 3, root + 3);
         qnormalize(root + 3);
-        double dp[3] = {dt * vO[0], dt * vO[1], dt * vO[2]};
+        double dp[3] = {dt * vO[0], dt * vO[1], dt * vO[2]};   /* in-frame displacement of the pelvis (second order) */
         cross(wn, dp, t);                                   /* re-reference the spatial velocity to the new origin */
-        for (int a = 0; a < 3; ++a) { root[a] += dp[a]; root[7 + a] = vO[a] + t[a]; root[10 + a] = wn[a]; }
+        for (int a = 0; a < 3; ++a) {
+            root[7 + a] = V[a] + vO[a] + t[a];
+            root[a] += dt * (V[a] + vO[a]);
+            root[10 + a] = wn[a];
+        }
     }
 }
 
@@ -374,6 +400,26 @@ static void refresh(const OModel* m, const double* root, const double* jq, const
     }
 }
 
+/* largest rigid-body angular speed of the current state */
+static double max_body_ang_vel(const OModel* m, const double* root, const double* jq, const double* jw) {
+    double q[NB][4], w[NB][3], best = 0;
+    memcpy(q[0], root + 3, 32);
+    for (int k = 0; k < 3; ++k) w[0][k] = root[10 + k];
+    for (int i = 0; i < NB; ++i) {
+        if (i > 0) {
+            int p = m->parent[i];
+            double R[3][3], ww[3];
+            qmul(q[p], jq + 4 * (i - 1), q[i]);
+            quat_to_mat(q[i], R);
+            mat3_vec(R, jw + 3 * (i - 1), ww);
+            for (int k = 0; k < 3; ++k) w[i][k] = w[p][k] + ww[k];
+        }
+        double n = sqrt(w[i][0] * w[i][0] + w[i][1] * w[i][1] + w[i][2] * w[i][2]);
+        if (n > best) best = n;
+    }
+    return best;
+}
+
 /* Public: n_sub sub-steps for N envs (OpenMP over envs).  contact = mean force over the sub-steps. */
 void emloco_oracle_step(const OModel* m, const OCfg* c, int N, int n_sub, double* root, double* jq, double* jw,
                         const double* target, const int16_t* hf, double* rb, double* dof_pos, double* contact,
@@ -382,9 +428,22 @@ void emloco_oracle_step(const OModel* m, const OCfg* c, int N, int n_sub, double
     for (int e = 0; e < N; ++e) {
         double* ct = contact + (size_t)e * NB * 3;
         memset(ct, 0, sizeof(double) * NB * 3);
-        for (int s = 0; s < n_sub; ++s)
-            substep(m, c, root + (size_t)e * 13, jq + (size_t)e * 92, jw + (size_t)e * ND, target + (size_t)e * ND, hf, ct,
-                    dof_force + (size_t)e * ND);
+        for (int s = 0; s < n_sub; ++s) {
+            /* adaptive refinement: the explicit velocity-product terms gain energy like (|w| dt)^2, so a sub-step is
+             * split into k equal parts until no body turns more than max_turn radians in one part (k <= 8) */
+            double* rt = root + (size_t)e * 13; double* q = jq + (size_t)e * 92; double* w = jw + (size_t)e * ND;
+            int k = 1;
+            if (c->max_turn > 0) {
+                double wmax = max_body_ang_vel(m, rt, q, w);
+                k = (int)ceil(wmax * c->dt / c->max_turn);
+                k = k < 1 ? 1 : (k > 8 ? 8 : k);
+            }
+            OCfg cc = *c; cc.dt = c->dt / k;
+            double part[NB * 3];
+            memset(part, 0, sizeof part);
+            for (int j = 0; j < k; ++j) substep(m, &cc, rt, q, w, target + (size_t)e * ND, hf, part, dof_force + (size_t)e * ND);
+            for (int j = 0; j < NB * 3; ++j) ct[j] += part[j] / k;
+        }
         for (int k = 0; k < NB * 3; ++k) ct[k] /= (double)n_sub;
         refresh(m, root + (size_t)e * 13, jq + (size_t)e * 92, jw + (size_t)e * ND, rb + (size_t)e * NB * 13,
                 dof_pos + (size_t)e * ND);

@@ -25,7 +25,7 @@ class OModel(C.Structure):
 
 class OCfg(C.Structure):
     _fields_ = [("dt", C.c_double), ("gravity_z", C.c_double), ("kn", C.c_double), ("cn", C.c_double),
-                ("ct", C.c_double), ("mu", C.c_double), ("max_ang_vel", C.c_double),
+                ("ct", C.c_double), ("mu", C.c_double), ("max_ang_vel", C.c_double), ("max_turn", C.c_double), ("max_effort", C.c_double),
                 ("hf_rows", C.c_int), ("hf_cols", C.c_int)]
 
 
@@ -68,8 +68,8 @@ def make_model(parent, offset, mass, com, inertia6, kp_joint, kd_joint, arm_join
     return m
 
 
-def make_cfg(dt, gravity_z=-9.81, kn=5e4, cn=1e3, ct=2e3, mu=1.0, max_ang_vel=100.0, hf_shape=(0, 0)):
-    return OCfg(dt, gravity_z, kn, cn, ct, mu, max_ang_vel, hf_shape[0], hf_shape[1])
+def make_cfg(dt, gravity_z=-9.81, kn=5e4, cn=1e3, ct=2e3, mu=1.0, max_ang_vel=100.0, max_effort=500.0, max_turn=0.1, hf_shape=(0, 0)):
+    return OCfg(dt, gravity_z, kn, cn, ct, mu, max_ang_vel, max_turn, max_effort, hf_shape[0], hf_shape[1])
 
 
 def _p(a, t=C.c_double):
