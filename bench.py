@@ -170,21 +170,24 @@ def run_ours(args):
 
     step_i = [0]
 
+    graphs = not args.eager
+
     def one_step():
         n = step_i[0] % HORIZON
-        R.step(n)
+        (R.step_graphed if graphs else R.step)(n)
         if n == HORIZON - 1:
-            R.finish()
+            (R.finish_graphed if graphs else R.finish)()
         step_i[0] += 1
 
-    for _ in range(W):
+    for _ in range(3):                      # eager: every lazy one-time initialisation happens here
+        R.step(0)
+    for _ in range(max(W, HORIZON if graphs else 0)):   # with graphs: every slot's graph is captured during warm-up
         one_step()
     step_i[0] = 0
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    R.enable_segment_timing(True)
     l0 = _lib.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -195,9 +198,18 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+    # per-segment device times: the same step replayed as seven per-segment graphs (8 slots) with an event between them
+    seg_step = (lambda i: R.step_segments_graphed(i % 8)) if graphs else (lambda i: R.step(i % HORIZON))
+    for i in range(8):
+        seg_step(i)
+    torch.cuda.synchronize()
+    R.enable_segment_timing(True)
+    for i in range(24):
+        seg_step(i)
+    torch.cuda.synchronize()
     seg, _ = R.segment_ms()
     R.enable_segment_timing(False)
-    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -219,15 +231,15 @@ def run_ours(args):
         d_obs_in.copy_(h_obs, non_blocking=True)
         R.noise.copy_(h_noise, non_blocking=True)
         R.sim.obs.copy_(d_obs_in)                       # the policy reads the obs the host handed over
-        R.step(n, noise=R.noise)
+        (R.step_graphed_host_noise if graphs else (lambda k: R.step(k, noise=R.noise)))(n)
         if n == HORIZON - 1:
-            R.finish()
+            (R.finish_graphed if graphs else R.finish)()
         h_out["obs"].copy_(R.sim.obs, non_blocking=True); h_out["rew"].copy_(R.sim.rew, non_blocking=True)
         h_out["reset"].copy_(R.sim.reset, non_blocking=True); h_out["actions"].copy_(R.mb["actions"][n], non_blocking=True)
         h_out["neglogp"].copy_(R.mb["neglogpacs"][n], non_blocking=True); h_out["values"].copy_(R.mb["values"][n], non_blocking=True)
         torch.cuda.current_stream().synchronize()       # the host consumes the results before issuing the next step
         h_obs.copy_(h_out["obs"])
-    for i in range(3):
+    for i in range(HORIZON if graphs else 3):
         e2e_step(i)
     barrier()
     e0.record()
@@ -289,11 +301,11 @@ def run_ours(args):
         out = {
             "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if not args.tensor_cores else "f32 (tf32/bf16x3 tensor-core products)", "data": "synthetic",
+            "dtype": "f32" if not args.tensor_cores else "f32 (dense layers: bf16x3 split products on tcgen05, fp32 accumulate)", "data": "synthetic",
             "config": {"workload": f"{N} SMPL-humanoid envs per GPU, PACER AMP rollout step + LocoVal scoring (configs[1])",
                        "horizon": HORIZON, "l2": "per-step working set (obs 23 MB + AMP obs 2x51 MB + experience rows + 45 MB weights) exceeds the 126 MB L2; experience rows rotate over 32 slots",
                        "post_horizon_disc_pass": "recomputed" if not args.dedup_disc else "reused per-step logits",
-                       "tensor_cores": bool(args.tensor_cores)},
+                       "tensor_cores": bool(args.tensor_cores), "cuda_graphs": graphs},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
             "roofline": roof, "kernels": kern, "segments_ms": seg,
@@ -315,10 +327,12 @@ def main():
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--tensor-cores", dest="tensor_cores", action="store_true", default=False)
+    ap.add_argument("--tensor-cores", dest="tensor_cores", action="store_true", default=True)
+    ap.add_argument("--fma", dest="tensor_cores", action="store_false", help="fp32 FMA dense layers instead of the tcgen05 bf16x3 path")
     ap.add_argument("--dedup-disc", action="store_true", default=False)
     ap.add_argument("--locoval-batch", type=int, default=1 << 20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="launch every kernel from the host instead of replaying CUDA graphs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

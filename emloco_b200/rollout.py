@@ -68,6 +68,8 @@ class Rollout:
             valuenet = ValuePoseNet(True, True, mutate_pose=False)
         self.valuenet = valuenet.to(dev).eval()
         self._marks = None
+        self._graphs = {}
+        self._cur = {}
 
         f = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
         T, N = self.T, self.N
@@ -109,35 +111,49 @@ class Rollout:
                 out[s] += ev[i * k + j].elapsed_time(ev[i * k + j + 1])
         return {s: v / max(steps, 1) for s, v in out.items()}, steps
 
-    # ---- one control step: everything inside the `for n in range(horizon_length)` body ----
+    # ---- one control step: everything inside the `for n in range(horizon_length)` body, as seven segments ----
+    def _segment_fns(self, n, noise=None):
+        sim, nets, mb, cur = self.sim, self.nets, self.mb, self._cur
+
+        def seg_reset():                                                               # env_reset(done_indices), :45-46
+            sim.reset_done(self.init_root, self.init_dof)
+            mb["obses"][n].copy_(sim.obs)
+            cur["noise"] = self.noise.normal_(generator=self.gen) if noise is None else noise
+
+        def seg_policy():                                                              # get_action_values, :53
+            # the heads write straight into row n of the experience tensors (experience_buffer.update_data, :47-56)
+            cur["res"] = nets.action_values(sim.obs, cur["noise"], mu_out=mb["mus"][n], task_value_out=mb["task_values"][n],
+                                            actions_out=mb["actions"][n], neglogp_out=mb["neglogpacs"][n])
+
+        def seg_physics():                                                             # env_step: pre_physics + simulate
+            sim.physics_step(cur["res"]["actions"])
+
+        def seg_post():                                                                #           post_physics_step
+            sim.post_step(True)
+            mb["amp_obs"][n].copy_(sim.amp_obs.view(self.N, AMP_OBS))
+
+        def seg_critic():                                                              # _eval_critic(next obs), :85
+            cur["nv"] = nets.critic(sim.obs)
+
+        def seg_disc():                                                                # _calc_amp_rewards, :93
+            cur["logit"] = nets.disc_logits(sim.amp_obs.view(self.N, AMP_OBS))
+
+        def seg_record():
+            # values are un-normalised (get_action_values, normalize_value) together with next_values in the record kernel
+            _lib.check(_lib.load().emloco_rollout_record(
+                C.byref(self.rcfg), _ptr(sim.rew), _ptr(sim.reset), _ptr(sim.terminate), _ptr(cur["res"]["values"]),
+                _ptr(cur["nv"]), _ptr(cur["logit"]), None, _ptr(mb["values"][n]), _ptr(mb["rewards"][n]), _ptr(mb["dones"][n]),
+                _ptr(mb["next_values"][n]), _ptr(mb["amp_rewards"][n]), _ptr(self.state), self.N, _stream()),
+                "emloco_rollout_record")
+            # LocoVal scoring of every env's (waypoints, initial pose, initial velocity) - valuenet(...) of :123-127
+            self.locoval_scores = self.valuenet(self.waypoint_traj, self.init_pose, self.init_vel)
+
+        return [seg_reset, seg_policy, seg_physics, seg_post, seg_critic, seg_disc, seg_record]
+
     def step(self, n, noise=None):
-        sim, nets, mb = self.sim, self.nets, self.mb
-        self._mark()
-        sim.reset_done(self.init_root, self.init_dof)                                   # env_reset(done_indices)
-        mb["obses"][n].copy_(sim.obs)
-        if noise is None:
-            noise = self.noise.normal_(generator=self.gen)
-        self._mark()
-        # the heads write straight into row n of the experience tensors (experience_buffer.update_data, :47-56)
-        res = nets.action_values(sim.obs, noise, mu_out=mb["mus"][n], task_value_out=mb["task_values"][n],
-                                 actions_out=mb["actions"][n], neglogp_out=mb["neglogpacs"][n])
-        self._mark()
-        sim.physics_step(res["actions"])                                                # env_step: pre_physics + simulate
-        self._mark()
-        sim.post_step(True)                                                             #           post_physics_step
-        mb["amp_obs"][n].copy_(sim.amp_obs.view(self.N, AMP_OBS))
-        self._mark()
-        nv = nets.critic(sim.obs)                                                       # _eval_critic(next obs)
-        self._mark()
-        logit = nets.disc_logits(sim.amp_obs.view(self.N, AMP_OBS))                     # _calc_amp_rewards
-        self._mark()
-        # values are un-normalised (get_action_values, normalize_value) together with next_values in the record kernel
-        _lib.check(_lib.load().emloco_rollout_record(
-            C.byref(self.rcfg), _ptr(sim.rew), _ptr(sim.reset), _ptr(sim.terminate), _ptr(res["values"]), _ptr(nv), _ptr(logit),
-            None, _ptr(mb["values"][n]), _ptr(mb["rewards"][n]), _ptr(mb["dones"][n]), _ptr(mb["next_values"][n]),
-            _ptr(mb["amp_rewards"][n]), _ptr(self.state), self.N, _stream()), "emloco_rollout_record")
-        # LocoVal scoring of every env's (waypoints, initial pose, initial velocity) - valuenet(...) of :123-127
-        self.locoval_scores = self.valuenet(self.waypoint_traj, self.init_pose, self.init_vel)
+        for f in self._segment_fns(n, noise):
+            self._mark()
+            f()
         self._mark()
 
     # ---- after the horizon: disc over the stored AMP obs, combine, GAE (:150-163) ----
@@ -159,6 +175,7 @@ class Rollout:
         self.mb_advs, self.mb_returns = adv, ret
         out = {k: v for k, v in mb.items() if v is not None}
         out.update(returns=ret, advantages=adv, task_rewards=mb["rewards"], rewards=self._comb())   # mb_rewards := combined (:160)
+        self._finish_out = out
         return out
 
     def _logits_TN(self):
@@ -171,10 +188,54 @@ class Rollout:
             self._cb = torch.empty(self.T, self.N, 1, device=self.state.device)
         return self._cb
 
-    def play_steps(self):
+    # ---- CUDA graphs: one captured graph per horizon slot (the experience-row pointers differ per slot) ----
+    def _capture(self, fn):
+        g = torch.cuda.CUDAGraph()
+        g.register_generator_state(self.gen)          # the policy-noise generator advances inside the graph
+        l0 = _lib.launch_count
+        marks, self._marks = self._marks, None        # timing events cannot be recorded into a capture
+        with torch.cuda.graph(g):
+            fn()
+        self._marks = marks
+        launches = _lib.launch_count - l0             # kernels of ours inside this graph (counted again on every replay)
+        _lib.launch_count = l0
+        return g, launches
+
+    def _replay(self, key, fn):
+        ent = self._graphs.get(key)
+        if ent is None:
+            ent = self._graphs[key] = self._capture(fn)
+        ent[0].replay()
+        _lib.launch_count += ent[1]
+
+    def step_graphed(self, n):
+        """Same work as step(n) replayed from a CUDA graph (captured on first use; run a few eager steps first so that
+        every lazy one-time initialisation - constant tables, weight splits, function attributes - has happened)."""
+        self._replay(n, lambda: self.step(n))
+
+    def step_graphed_host_noise(self, n):
+        """step(n) with the policy noise taken from self.noise as the caller filled it (no generator call in the graph)."""
+        self._replay(("hn", n), lambda: self.step(n, noise=self.noise))
+
+    def step_segments_graphed(self, n):
+        """step(n) as seven per-segment graphs with a timing event between them: per-segment device time without host
+        launch gaps inside a segment (used by bench.py for the roofline numbers)."""
+        fns = None
+        for i, name in enumerate(self.SEGMENTS):
+            self._mark()
+            if ("seg", n, i) not in self._graphs and fns is None:
+                fns = self._segment_fns(n)
+            self._replay(("seg", n, i), fns[i] if fns else None)
+        self._mark()
+
+    def finish_graphed(self):
+        self._replay("finish", self.finish)
+        return self._finish_out
+
+    def play_steps(self, graphed=False):
         for n in range(self.T):
-            self.step(n)
-        return self.finish()
+            (self.step_graphed if graphed else self.step)(n)
+        return self.finish_graphed() if graphed else self.finish()
 
     def close(self):
         self.sim.close()

@@ -139,3 +139,26 @@ def test_play_steps_horizon_and_gae_consistency():
     np.testing.assert_allclose(out["returns"].cpu().numpy().reshape(32, n), adv + v, rtol=1e-6, atol=1e-6)
     assert 0 < R.locoval_scores.min().item() and R.locoval_scores.max().item() < 1
     R.close()
+
+
+def test_graphed_steps_equal_eager_steps():
+    """CUDA-graph replay of a step must produce exactly what the eager launches produce (same kernels, same order)."""
+    from emloco_b200.policy import AMPSeptValueNetwork
+    from emloco_b200.rollout import Rollout
+    n = 96
+    torch.manual_seed(4)
+    net = AMPSeptValueNetwork()
+    A = Rollout(n, seed=9, net=net, tensor_cores=True, horizon=4)
+    B = Rollout(n, seed=9, net=net, tensor_cores=True, horizon=4)
+    for k in range(4):
+        A.step(k); B.step(k)            # eager warm-up on both (identical generators -> identical noise)
+    for rep in range(2):
+        for k in range(4):
+            A.step(k)
+            B.step_graphed(k)
+        oa, ob = A.finish(), B.finish_graphed()
+        torch.cuda.synchronize()
+        for key in ("obses", "actions", "values", "rewards", "dones", "amp_rewards", "returns", "advantages"):
+            np.testing.assert_array_equal(oa[key].cpu().numpy(), ob[key].cpu().numpy(), err_msg=f"{key} rep {rep}")
+    np.testing.assert_array_equal(A.sim.rb_state.cpu().numpy(), B.sim.rb_state.cpu().numpy())
+    A.close(); B.close()
