@@ -40,7 +40,7 @@ void emloco_default_cfg(emloco_cfg* c) {
     c->episode_length = 168; c->power_coefficient = 0.0005f; c->location_coefficient = 1.0f;
     c->fail_dist = 4.0f; c->traj_sample_dt = 0.4f;
     c->max_effort = 500.0f;                                                 // smpl_humanoid.xml:171-233 motor gear
-    c->max_turn = 0.1f;
+    c->max_turn = 0.3f;
 }
 
 int emloco_create(const emloco_cfg* cfg, const emloco_model* model, emloco_sim** out) {
@@ -375,8 +375,10 @@ int emloco_linear_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda
     if ((y_hi == nullptr) != (y_lo == nullptr)) return fail(EMLOCO_EINVAL, "emloco_linear_bf16x3: y_hi and y_lo must come together");
     if (y_hi && ((N & 31) || ldy16 < N || (ldy16 & 7) || (((uintptr_t)y_hi | (uintptr_t)y_lo) & 15)))
         return fail(EMLOCO_EINVAL, "emloco_linear_bf16x3: split output needs N % 32 == 0, pitch % 8 == 0, 16-byte aligned pointers");
-    CK(eml_linear_bf16x3(a_hi, a_lo, lda, w_hi, w_lo, ldw, d_bias, M, N, K, relu, d_y32, ldy, y_hi, y_lo, ldy16, (cudaStream_t)stream),
-       "linear bf16x3 (tcgen05)");
+    const int tile_n = (relu >> 8) & 0xfff;     // bits 8..19 of `relu`: 0 = automatic tile choice, 128 / 256 = forced (tests, tuning)
+    if (tile_n != 0 && tile_n != 128 && tile_n != 256) return fail(EMLOCO_EINVAL, "emloco_linear_bf16x3: tile must be 0, 128 or 256");
+    CK(eml_linear_bf16x3(a_hi, a_lo, lda, w_hi, w_lo, ldw, d_bias, M, N, K, relu & 1, d_y32, ldy, y_hi, y_lo, ldy16, tile_n,
+                         (cudaStream_t)stream), "linear bf16x3 (tcgen05)");
     return EMLOCO_OK;
 }
 

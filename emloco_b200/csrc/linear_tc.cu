@@ -24,15 +24,23 @@
 
 namespace tc {
 
-constexpr int BM = 128, BK = 64, UMMA_K = 16;
-constexpr int NUM_THREADS = 192;   // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int BM = 128, UMMA_K = 16;
+constexpr int NUM_EPI_WARPS = 8;                           // two per TMEM lane quadrant, each takes half of the tile's columns
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;       // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
+// Two tile shapes.  Operand rows are K-major and span exactly one swizzle atom along K:
+//   BN = 128: BK = 64 (128-byte swizzle), 3 stages x 64 KB      - small-N layers and the heads
+//   BN = 256: BK = 32 ( 64-byte swizzle), 4 stages x 48 KB      - the wide layers: 1.33x the flops per smem/L2 byte
 template <int BN> struct Tile {
-    static constexpr int STAGES = BN == 128 ? 3 : 2;
+    static constexpr int BK = BN == 128 ? 64 : 32;
+    static constexpr int STAGES = BN == 128 ? 3 : 4;
+    static constexpr int SWIZZLE_BYTES = BK * 2;           // 128 or 64
     static constexpr int A_BYTES = BM * BK * 2;            // one bf16 tile of A (hi or lo)
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int BIAS_BYTES = 2 * BN * 4;          // bias slice of the tile, double-buffered with the accumulator
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + BAR_BYTES + BIAS_BYTES;
     static constexpr int TMEM_COLS = 2 * BN;               // power of two: 256 or 512
 };
 
@@ -75,14 +83,15 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-// K-major operand tile, 128-byte swizzle: rows of 64 bf16 (128 B), 8-row atoms 1024 B apart (SBO); LBO unused.
-// Bit layout: [0,14) addr>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version = 1 (sm_100), [61,64) layout = 2 (SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+// K-major operand tile whose rows are one swizzle atom wide (SW = 128 or 64 bytes): 8-row atoms are 8*SW bytes apart (SBO);
+// LBO unused.  Bit layout: [0,14) addr>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version = 1 (sm_100),
+// [61,64) layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B.
+template <int SW> __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)((8 * SW) >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)(SW == 128 ? 2 : 4) << 61;
     return d;
 }
 
@@ -101,7 +110,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
                    "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                  : "r"(taddr));
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait for the thread's outstanding tcgen05.ld; the loaded registers are listed as in/out operands so that the compiler
+// cannot schedule a use of them above the wait
+__device__ __forceinline__ void tmem_ld_wait(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
+}
 
 struct GemmArgs {
     const float* bias;       // [N] or NULL
@@ -110,13 +128,58 @@ struct GemmArgs {
     int M, N, K, relu;
 };
 
+// One 32-column chunk of one accumulator row: +bias, ReLU, then fp32 store and/or bf16 hi/lo split store.
+__device__ __forceinline__ void epilogue_chunk(const uint32_t* r, const float* __restrict__ s_bias, int nb, int row, bool row_ok,
+                                               const GemmArgs& g) {
+    if (nb >= g.N) return;                                                  // warp-uniform
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(s_bias + j);     // same address in every lane: broadcast
+        float x0 = __uint_as_float(r[j]) + b4.x, x1 = __uint_as_float(r[j + 1]) + b4.y;
+        float x2 = __uint_as_float(r[j + 2]) + b4.z, x3 = __uint_as_float(r[j + 3]) + b4.w;
+        v[j] = g.relu ? fmaxf(x0, 0.f) : x0; v[j + 1] = g.relu ? fmaxf(x1, 0.f) : x1;
+        v[j + 2] = g.relu ? fmaxf(x2, 0.f) : x2; v[j + 3] = g.relu ? fmaxf(x3, 0.f) : x3;
+    }
+    if (!row_ok) return;
+    if (g.y32) {
+        float* o = g.y32 + (long long)row * g.ldy + nb;
+        if (nb + 32 <= g.N && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (nb + j < g.N) o[j] = v[j];
+        }
+    }
+    if (g.y_hi) {                                                           // next layer's operand: x = hi + lo
+        uint32_t ph[16], pl[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+            __nv_bfloat16 h0 = __float2bfloat16_rn(v[j]), h1 = __float2bfloat16_rn(v[j + 1]);
+            __nv_bfloat16 l0 = __float2bfloat16_rn(v[j] - __bfloat162float(h0));
+            __nv_bfloat16 l1 = __float2bfloat16_rn(v[j + 1] - __bfloat162float(h1));
+            ph[j / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            pl[j / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        }
+        uint4* oh = reinterpret_cast<uint4*>(g.y_hi + (long long)row * g.ldy16 + nb);
+        uint4* ol = reinterpret_cast<uint4*>(g.y_lo + (long long)row * g.ldy16 + nb);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            oh[j] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
+            ol[j] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+        }
+    }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 linear_bf16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                      const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl, GemmArgs g) {
     using T = Tile<BN>;
+    constexpr int BK = T::BK, SW = T::SWIZZLE_BYTES;
     extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;            // SWIZZLE_128B tiles need 1024 B alignment
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;            // swizzled tiles need 1024 B alignment
     const uint32_t bars = base + T::STAGES * T::STAGE_BYTES;                // 8-byte mbarriers
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (T::STAGES + s); };
@@ -124,6 +187,7 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_co
     auto tempty_bar = [&](int a) { return bars + 8u * (2 * T::STAGES + 2 + a); };
     const uint32_t tmem_slot = bars + 8u * (2 * T::STAGES + 4);
     uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
+    float* s_bias = reinterpret_cast<float*>(smem_gen + T::STAGES * T::STAGE_BYTES + T::BAR_BYTES);   // [2][BN]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_m = (g.M + BM - 1) / BM, tiles_n = (g.N + BN - 1) / BN;
@@ -136,7 +200,7 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_co
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wh));
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wl));
         for (int s = 0; s < T::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 32 * NUM_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     } else if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(T::TMEM_COLS));
@@ -179,11 +243,12 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_co
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     const uint32_t sa = base + stage * T::STAGE_BYTES;
-                    const uint64_t d_ah = make_smem_desc(sa), d_al = make_smem_desc(sa + T::A_BYTES);
-                    const uint64_t d_wh = make_smem_desc(sa + 2 * T::A_BYTES), d_wl = make_smem_desc(sa + 2 * T::A_BYTES + T::B_BYTES);
+                    const uint64_t d_ah = make_smem_desc<SW>(sa), d_al = make_smem_desc<SW>(sa + T::A_BYTES);
+                    const uint64_t d_wh = make_smem_desc<SW>(sa + 2 * T::A_BYTES);
+                    const uint64_t d_wl = make_smem_desc<SW>(sa + 2 * T::A_BYTES + T::B_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t ko = (uint64_t)((k * UMMA_K * 2) >> 4);   // advance inside the 128 B swizzle row
+                        const uint64_t ko = (uint64_t)((k * UMMA_K * 2) >> 4);   // advance inside the swizzle row
                         umma_bf16(d_tmem, d_al + ko, d_wh + ko, idesc, (kb | k) != 0);   // small terms first
                         umma_bf16(d_tmem, d_ah + ko, d_wl + ko, idesc, 1);
                         umma_bf16(d_tmem, d_ah + ko, d_wh + ko, idesc, 1);
@@ -196,63 +261,37 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_co
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5 -> TMEM lane quadrants 2,3,0,1) =====================
-        const int quad = warp & 3;
+        // ===================== epilogue: warps 2..9; warp w reads TMEM lane quadrant w % 4, column half (w - 2) / 4 ==========
+        const int quad = warp & 3, half = (warp - 2) >> 2;
+        const int et = threadIdx.x - 64;                                    // 0..255
+        constexpr int NC = BN / 64;                                         // 32-column chunks per warp (2 or 4)
         int acc = 0; uint32_t acc_phase = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
+            // bias slice of this tile -> smem (one element per epilogue thread), visible after the epilogue-only barrier
+            if (et < BN) s_bias[acc * BN + et] = (g.bias && n0 + et < g.N) ? __ldg(g.bias + n0 + et) : 0.f;
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const int row = m0 + quad * 32 + lane;
             const bool row_ok = row < g.M;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld32(taddr + c * 32, r);
-                tmem_ld_wait();
-                const int nb = n0 + c * 32;
-                if (nb >= g.N) continue;                                    // warp-uniform
-                float v[32];
+            const int c0 = half * (BN / 2);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c0;
+            const float* sb = s_bias + acc * BN + c0;
+            uint32_t ra[32], rb[32];
+            tmem_ld32(taddr, ra);
+            tmem_ld_wait(ra);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float x = __uint_as_float(r[j]);
-                    if (g.bias && nb + j < g.N) x += __ldg(g.bias + nb + j);
-                    v[j] = g.relu ? fmaxf(x, 0.f) : x;
-                }
-                if (row_ok) {
-                    if (g.y32) {
-                        float* o = g.y32 + (long long)row * g.ldy + nb;
-                        if (nb + 32 <= g.N && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) if (nb + j < g.N) o[j] = v[j];
-                        }
-                    }
-                    if (g.y_hi) {                                           // next layer's operand: x = hi + lo
-                        uint32_t ph[16], pl[16];
-#pragma unroll
-                        for (int j = 0; j < 32; j += 2) {
-                            __nv_bfloat16 h0 = __float2bfloat16_rn(v[j]), h1 = __float2bfloat16_rn(v[j + 1]);
-                            __nv_bfloat16 l0 = __float2bfloat16_rn(v[j] - __bfloat162float(h0));
-                            __nv_bfloat16 l1 = __float2bfloat16_rn(v[j + 1] - __bfloat162float(h1));
-                            ph[j / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                            pl[j / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-                        }
-                        uint4* oh = reinterpret_cast<uint4*>(g.y_hi + (long long)row * g.ldy16 + nb);
-                        uint4* ol = reinterpret_cast<uint4*>(g.y_lo + (long long)row * g.ldy16 + nb);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            oh[j] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
-                            ol[j] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
-                        }
-                    }
-                }
+            for (int c = 0; c < NC; c += 2) {                               // two register buffers: the next TMEM load is in
+                tmem_ld32(taddr + (c + 1) * 32, rb);                        // flight while this chunk is converted and stored
+                epilogue_chunk(ra, sb + c * 32, n0 + c0 + c * 32, row, row_ok, g);
+                tmem_ld_wait(rb);
+                if (c + 2 < NC) tmem_ld32(taddr + (c + 2) * 32, ra);
+                epilogue_chunk(rb, sb + (c + 1) * 32, n0 + c0 + (c + 1) * 32, row, row_ok, g);
+                if (c + 2 < NC) tmem_ld_wait(ra);
             }
             tc_fence_before();
-            mbar_arrive(tempty_bar(acc));                                   // 128 arrivals release the accumulator
+            mbar_arrive(tempty_bar(acc));                                   // 256 arrivals release the accumulator
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -309,30 +348,32 @@ static EncodeFn get_encode() {
     return fn;
 }
 
-// [rows, K] bf16, row pitch ld elements (ld % 8 == 0, base 16-byte aligned), box = box_rows x 64, 128B swizzle, zero OOB fill
-static bool make_map(CUtensorMap* m, const void* ptr, long long rows, int K, long long ld, int box_rows) {
+// [rows, K] bf16, row pitch ld elements (ld % 8 == 0, base 16-byte aligned), box = box_rows x bk (one swizzle atom wide),
+// zero fill outside [rows, K]
+static bool make_map(CUtensorMap* m, const void* ptr, long long rows, int K, long long ld, int box_rows, int bk) {
     EncodeFn enc = get_encode();
     if (!enc) return false;
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+               bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static int g_num_sms = 0;
+int g_num_sms = 0;
 
 template <int BN>
 static cudaError_t launch(const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, long long lda, const __nv_bfloat16* w_hi,
                           const __nv_bfloat16* w_lo, long long ldw, const GemmArgs& g, cudaStream_t st) {
     using T = Tile<BN>;
     CUtensorMap mah, mal, mwh, mwl;
-    if (!make_map(&mah, a_hi, g.M, g.K, lda, BM) || !make_map(&mal, a_lo, g.M, g.K, lda, BM) ||
-        !make_map(&mwh, w_hi, g.N, g.K, ldw, BN) || !make_map(&mwl, w_lo, g.N, g.K, ldw, BN))
+    if (!make_map(&mah, a_hi, g.M, g.K, lda, BM, T::BK) || !make_map(&mal, a_lo, g.M, g.K, lda, BM, T::BK) ||
+        !make_map(&mwh, w_hi, g.N, g.K, ldw, BN, T::BK) || !make_map(&mwl, w_lo, g.N, g.K, ldw, BN, T::BK))
         return cudaErrorInvalidValue;
     auto kern = linear_bf16x3_kernel<BN>;
-    static bool attr_set = false;
+    static bool attr_set = false;   // one flag per template instantiation
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM);
         if (e != cudaSuccess) return e;
@@ -361,11 +402,19 @@ cudaError_t eml_split_bf16(const float* x, long long ldx, long long M, int K, co
 
 cudaError_t eml_linear_bf16x3(const void* a_hi, const void* a_lo, long long lda, const void* w_hi, const void* w_lo, long long ldw,
                               const float* bias, long long M, int N, int K, int relu, float* y32, long long ldy, void* y_hi,
-                              void* y_lo, long long ldy16, cudaStream_t st) {
+                              void* y_lo, long long ldy16, int tile_n, cudaStream_t st) {
     if (M <= 0 || N <= 0) return cudaSuccess;
     tc::GemmArgs g;
     g.bias = bias; g.y32 = y32; g.ldy = ldy; g.y_hi = (__nv_bfloat16*)y_hi; g.y_lo = (__nv_bfloat16*)y_lo; g.ldy16 = ldy16;
     g.M = (int)M; g.N = N; g.K = K; g.relu = relu;
+    // tile choice: the 128 x 256 tile does 1.33x the flops per operand byte, but needs enough tiles to fill the 148 SMs
+    int sms = tc::g_num_sms;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); tc::g_num_sms = sms; }
+    const long long tiles256 = ((M + tc::BM - 1) / tc::BM) * ((N + 255) / 256);
+    const bool wide = tile_n == 256 || (tile_n == 0 && N >= 256 && tiles256 * 8 >= (long long)sms * 7);
+    if (wide)
+        return tc::launch<256>((const __nv_bfloat16*)a_hi, (const __nv_bfloat16*)a_lo, lda, (const __nv_bfloat16*)w_hi,
+                               (const __nv_bfloat16*)w_lo, ldw, g, st);
     return tc::launch<128>((const __nv_bfloat16*)a_hi, (const __nv_bfloat16*)a_lo, lda, (const __nv_bfloat16*)w_hi,
                            (const __nv_bfloat16*)w_lo, ldw, g, st);
 }
@@ -382,7 +431,7 @@ cudaError_t eml_linear_tc(const float* x, long long ldx, const float* w, const f
     __nv_bfloat16 *ah = scratch, *al = ah + M * kp, *wh = al + M * kp, *wl = wh + (long long)N * kp;
     if ((e = eml_split_bf16(x, ldx, M, K, mean, var, eps, ah, al, kp, st)) == cudaSuccess &&
         (e = eml_split_bf16(w, K, N, K, nullptr, nullptr, 0.f, wh, wl, kp, st)) == cudaSuccess)
-        e = eml_linear_bf16x3(ah, al, kp, wh, wl, kp, b, M, N, K, relu, y, ldy, nullptr, nullptr, 0, st);
+        e = eml_linear_bf16x3(ah, al, kp, wh, wl, kp, b, M, N, K, relu, y, ldy, nullptr, nullptr, 0, 0, st);
     cudaError_t e2 = cudaFreeAsync(scratch, st);
     return e != cudaSuccess ? e : e2;
 }

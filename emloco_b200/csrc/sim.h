@@ -96,4 +96,4 @@ cudaError_t eml_split_bf16(const float* x, long long ldx, long long M, int K, co
                            void* hi, void* lo, long long ld16, cudaStream_t st);
 cudaError_t eml_linear_bf16x3(const void* a_hi, const void* a_lo, long long lda, const void* w_hi, const void* w_lo, long long ldw,
                               const float* bias, long long M, int N, int K, int relu, float* y32, long long ldy, void* y_hi,
-                              void* y_lo, long long ldy16, cudaStream_t st);
+                              void* y_lo, long long ldy16, int tile_n, cudaStream_t st);

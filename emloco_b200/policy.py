@@ -240,14 +240,15 @@ def split_bf16(x, dst: _Split, mean=None, var=None, eps=1e-5):
     return dst
 
 
-def linear_bf16x3(a: _Split, w: _Split, bias, relu, y32=None, y16: _Split = None):
-    """y = act(a w^T + bias) on the tcgen05 path; fp32 output and/or split output for the next layer."""
+def linear_bf16x3(a: _Split, w: _Split, bias, relu, y32=None, y16: _Split = None, tile=0):
+    """y = act(a w^T + bias) on the tcgen05 path; fp32 output and/or split output for the next layer.
+    tile: 0 = library picks the output-tile width, 128 / 256 = forced."""
     M, K, N = a.rows, a.K, w.rows
     assert w.K == K
     if y32 is not None:
         assert y32.shape == (M, N) and y32.stride(1) == 1
     _lib.check(_lib.load().emloco_linear_bf16x3(
-        _ptr(a.hi), _ptr(a.lo), a.ld, _ptr(w.hi), _ptr(w.lo), w.ld, _ptr(bias), M, N, K, int(relu),
+        _ptr(a.hi), _ptr(a.lo), a.ld, _ptr(w.hi), _ptr(w.lo), w.ld, _ptr(bias), M, N, K, int(bool(relu)) | (int(tile) << 8),
         _ptr(y32), 0 if y32 is None else y32.stride(0), None if y16 is None else _ptr(y16.hi),
         None if y16 is None else _ptr(y16.lo), 0 if y16 is None else y16.ld, _stream()), "emloco_linear_bf16x3")
 

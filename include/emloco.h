@@ -47,7 +47,7 @@ typedef struct emloco_cfg {
     float   fail_dist;            /* 4.0 (humanoid_traj.py:31) */
     float   traj_sample_dt;       /* 0.4 */
     float   max_effort;           /* 500: drive torque limit per DOF (MJCF motor gear -> Isaac Gym DOF `effort`); <= 0 off */
-    float   max_turn;             /* 0.1 rad: a sub-step is refined until no body turns more than this per piece; <= 0 off */
+    float   max_turn;             /* 0.3 rad: a sub-step is refined until no body turns more than this per piece; <= 0 off */
     int32_t reserved[6];
 } emloco_cfg;
 
@@ -223,7 +223,8 @@ int emloco_rollout_record(const emloco_rollout_cfg* cfg, const float* d_rew, con
  * (utils/running_mean_std.py:82-84) -> hi/lo [M,K] bf16 with row pitch ld16 (ld16 % 8 == 0; pad columns are never read).
  * emloco_linear_bf16x3: y = act(A W^T + b) with A = a_hi+a_lo [M,K] (pitch lda), W = w_hi+w_lo [N,K] (pitch ldw);
  * writes fp32 y32 [M,N] (pitch ldy) and/or the split of y as the next layer's operand y_hi/y_lo (pitch ldy16, N % 32 == 0).
- * All bf16 base pointers 16-byte aligned, pitches multiples of 8 elements. */
+ * All bf16 base pointers 16-byte aligned, pitches multiples of 8 elements.  `relu`: bit 0 = ReLU; bits 8..19 optionally force
+ * the N-extent of the output tile (128 or 256; 0 = chosen from the shape) - used by the tests and for tuning. */
 int emloco_split_bf16(const float* d_x, int64_t ldx, int64_t M, int32_t K, const float* d_mean, const float* d_var, float eps,
                       uint16_t* d_hi, uint16_t* d_lo, int64_t ld16, void* stream);
 int emloco_linear_bf16x3(const uint16_t* d_a_hi, const uint16_t* d_a_lo, int64_t lda, const uint16_t* d_w_hi,

@@ -68,7 +68,7 @@ def make_model(parent, offset, mass, com, inertia6, kp_joint, kd_joint, arm_join
     return m
 
 
-def make_cfg(dt, gravity_z=-9.81, kn=5e4, cn=1e3, ct=2e3, mu=1.0, max_ang_vel=100.0, max_effort=500.0, max_turn=0.1, hf_shape=(0, 0)):
+def make_cfg(dt, gravity_z=-9.81, kn=5e4, cn=1e3, ct=2e3, mu=1.0, max_ang_vel=100.0, max_effort=500.0, max_turn=0.3, hf_shape=(0, 0)):
     return OCfg(dt, gravity_z, kn, cn, ct, mu, max_ang_vel, max_turn, max_effort, hf_shape[0], hf_shape[1])
 
 

@@ -231,8 +231,10 @@ def test_linear_bf16x3_tensor_core_matches_fp64(M, N, K, relu):
     np.testing.assert_allclose(y.cpu().numpy(), ref, rtol=1e-3, atol=1e-4)
 
 
-def test_linear_bf16x3_split_output_chains_layers():
-    """Two chained layers through the split (hi/lo) epilogue output, with input normalisation, against float64."""
+@pytest.mark.parametrize("tile", [128, 256])
+def test_linear_bf16x3_split_output_chains_layers(tile):
+    """Two chained layers through the split (hi/lo) epilogue output, with input normalisation, against float64;
+    both output-tile shapes (128 x 128 x 64 / 128B swizzle and 128 x 256 x 32 / 64B swizzle)."""
     from emloco_b200.policy import _Split, linear_bf16x3, split_bf16
     rng = np.random.default_rng(5)
     M, K, H, N = 500, 1054, 512, 256
@@ -244,8 +246,8 @@ def test_linear_bf16x3_split_output_chains_layers():
     sx, s1, sw1, sw2 = _Split(M, K, "cuda"), _Split(M, H, "cuda"), _Split(H, K, "cuda"), _Split(N, H, "cuda")
     split_bf16(T(x), sx, T(mean), T(var), 1e-5); split_bf16(T(w1), sw1); split_bf16(T(w2), sw2)
     y = torch.empty(M, N, device="cuda")
-    linear_bf16x3(sx, sw1, T(b1), True, y16=s1)
-    linear_bf16x3(s1, sw2, T(b2), True, y32=y)
+    linear_bf16x3(sx, sw1, T(b1), True, y16=s1, tile=tile)
+    linear_bf16x3(s1, sw2, T(b2), True, y32=y, tile=tile)
     xn = np.clip((x.astype(np.float64) - mean) / np.sqrt(var.astype(np.float64) + 1e-5), -5, 5)
     h = np.maximum(xn @ w1.T.astype(np.float64) + b1, 0)
     ref = np.maximum(h @ w2.T.astype(np.float64) + b2, 0)
@@ -253,3 +255,21 @@ def test_linear_bf16x3_split_output_chains_layers():
     # the split itself: hi + lo reproduces the fp32 value to 2^-16
     rec = (sx.hi.float() + sx.lo.float())[:, :K].cpu().numpy()
     np.testing.assert_allclose(rec, xn, rtol=2e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("tile", [128, 256])
+@pytest.mark.parametrize("M,N,K", [(128, 69, 100), (4096, 1024, 2048), (130, 257, 33), (1000, 4096, 624)])
+def test_linear_bf16x3_tiles_and_ragged_shapes(tile, M, N, K):
+    """Forced tile shapes on ragged M / N / K (TMA zero fill of the out-of-range rows and of the K tail), fp32 output."""
+    from emloco_b200.policy import _Split, linear_bf16x3, split_bf16
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    x = rng.normal(0, 1.5, (M, K)).astype(np.float32)
+    w = (rng.normal(0, 1, (N, K)) / np.sqrt(K)).astype(np.float32)
+    b = rng.normal(0, 0.1, N).astype(np.float32)
+    T = lambda a: torch.from_numpy(a).cuda()
+    sx, sw = _Split(M, K, "cuda"), _Split(N, K, "cuda")
+    split_bf16(T(x), sx); split_bf16(T(w), sw)
+    y = torch.full((M, N), float("nan"), device="cuda")
+    linear_bf16x3(sx, sw, T(b), False, y32=y, tile=tile)
+    ref = x.astype(np.float64) @ w.astype(np.float64).T + b
+    np.testing.assert_allclose(y.cpu().numpy(), ref, rtol=1e-3, atol=1e-4)
