@@ -32,7 +32,7 @@ class Cfg(C.Structure):
                 ("contact_offset", C.c_float), ("max_ang_vel", C.c_float), ("angular_damping", C.c_float),
                 ("episode_length", C.c_int32), ("power_coefficient", C.c_float), ("location_coefficient", C.c_float),
                 ("fail_dist", C.c_float), ("traj_sample_dt", C.c_float), ("max_effort", C.c_float), ("max_turn", C.c_float),
-                ("reserved", C.c_int32 * 6)]
+                ("physics_impl", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
 class RolloutCfg(C.Structure):

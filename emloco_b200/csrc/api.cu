@@ -90,6 +90,13 @@ int emloco_create(const emloco_cfg* cfg, const emloco_model* model, emloco_sim**
     emloco_sim* s = (emloco_sim*)calloc(1, sizeof(emloco_sim));
     if (!s) return fail(EMLOCO_ENOMEM, "emloco_create: out of host memory");
     s->cfg = *cfg; s->N = cfg->num_envs; s->device = cfg->device;
+    {   // the lane-per-env kernel hard-codes the SMPL kinematic chains (legs, spine + head, arms)
+        static const int smpl_parent[EML_NB] = {-1, 0, 1, 2, 3, 0, 5, 6, 7, 0, 9, 10, 11, 12, 11, 14, 15, 16, 17, 11, 19, 20, 21, 22};
+        bool smpl = true;
+        for (int i = 0; i < EML_NB; ++i) smpl &= model->parent[i] == smpl_parent[i];
+        if (cfg->physics_impl != 0 && cfg->physics_impl != 1) { free(s); return fail(EMLOCO_EINVAL, "emloco_create: physics_impl must be 0 or 1"); }
+        s->physics_impl = smpl ? cfg->physics_impl : 1;
+    }
     const size_t N = (size_t)s->N;
 #define ALLOC(ptr, count, type) do { CK(cudaMalloc((void**)&(ptr), (count) * sizeof(type)), "cudaMalloc " #ptr); \
                                      CK(cudaMemset((ptr), 0, (count) * sizeof(type)), "cudaMemset " #ptr); } while (0)

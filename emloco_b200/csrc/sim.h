@@ -31,6 +31,7 @@ struct emloco_sim {
     emloco_cfg cfg;
     int N;
     int device;
+    int physics_impl;       // 0: lane-per-env kernel (physics_soa.cu), 1: warp-per-env kernel (physics.cu)
     // --- state owned by the sim; addresses are stable for its lifetime (gymtorch.wrap_tensor aliases) ---
     float*   root_state;    // [N,13]   pos3 quat4 lin3 ang3
     float*   dof_state;     // [N*69,2] (exp-map pos, vel) interleaved

@@ -48,7 +48,8 @@ typedef struct emloco_cfg {
     float   traj_sample_dt;       /* 0.4 */
     float   max_effort;           /* 500: drive torque limit per DOF (MJCF motor gear -> Isaac Gym DOF `effort`); <= 0 off */
     float   max_turn;             /* 0.3 rad: a sub-step is refined until no body turns more than this per piece; <= 0 off */
-    int32_t reserved[6];
+    int32_t physics_impl;         /* 0: lane-per-env step kernel (default, needs the SMPL tree), 1: warp-per-env kernel */
+    int32_t reserved[5];
 } emloco_cfg;
 
 /* Articulation + collision model: what gym.load_asset/create_actor build from
