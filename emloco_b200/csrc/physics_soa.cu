@@ -42,7 +42,8 @@ enum {
 #define SOA_XCHG (SOA_ROOT + 2 * 13 * 32)          // 4 chains x 27 x 32: chain totals (legs -> pelvis, arms -> chest)
 #define SOA_ACC (SOA_XCHG + 4 * 27 * 32)           // 2 x 6 x 32: pelvis and chest accelerations
 #define SOA_WMAX (SOA_ACC + 2 * 6 * 32)            // 5 x 32: per-chain max body angular speed
-#define SOA_FLOATS (SOA_WMAX + 5 * 32)
+#define SOA_KMAX (SOA_WMAX + 5 * 32)               // 8 ints: per-warp largest piece count
+#define SOA_FLOATS (SOA_KMAX + 8)
 #define SOA_SMEM_BYTES (SOA_FLOATS * 4)
 
 __constant__ int c_chain_len[5] = {4, 4, 5, 5, 5};
@@ -303,8 +304,14 @@ __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams 
                 parts = k < 1 ? 1 : (k > 8 ? 8 : k);
             }
             dt = P.dt / (float)parts;
-            const int bits = __syncthreads_or(1 << (parts - 1));
-            kmax = 32 - __clz(bits);
+            // CTA-wide maximum (note: __syncthreads_or is a LOGICAL or, it cannot carry a bit mask)
+            const int wk = __reduce_max_sync(FULL, parts);
+            int* s_k = reinterpret_cast<int*>(smem + SOA_KMAX);
+            if (lane == 0) s_k[warp] = wk;
+            __syncthreads();
+            kmax = 1;
+#pragma unroll
+            for (int w = 0; w < SOA_WARPS; ++w) kmax = max(kmax, s_k[w]);
         }
         SoaStep st; st.dt = dt; st.wgt = 1.0f / (float)parts; st.live = part < parts;
 
