@@ -17,7 +17,7 @@ SYMBOLS = [
     "emloco_step_host", "emloco_locoval_forward", "emloco_locoval_backward", "emloco_locoval_forward_host",
     "emloco_plausibl_mlp_forward", "emloco_gae", "emloco_reset_done", "emloco_sample_actions",
     "emloco_disc_reward", "emloco_rollout_record", "emloco_normalize", "emloco_physics_step", "emloco_split_bf16",
-    "emloco_linear_bf16x3", "emloco_linear", "emloco_sync", "emloco_last_error", "emloco_version",
+    "emloco_linear_bf16x3", "emloco_set_post_sinks", "emloco_linear", "emloco_sync", "emloco_last_error", "emloco_version",
 ]
 
 
@@ -39,6 +39,14 @@ class RolloutCfg(C.Structure):
     _fields_ = [("inversion_penalty_scale", C.c_float), ("reward_scale", C.c_float), ("value_mean", C.c_float),
                 ("value_std", C.c_float), ("disc_reward_scale", C.c_float), ("gamma", C.c_float),
                 ("step_to_pred", C.c_int32), ("unnorm_value", C.c_int32)]
+
+
+class PostSinks(C.Structure):
+    _fields_ = [("obs_copy", C.c_void_p), ("amp_copy", C.c_void_p), ("obs_mean", C.c_void_p), ("obs_inv_std", C.c_void_p),
+                ("self_hi", C.c_void_p), ("self_lo", C.c_void_p), ("ld_self", C.c_int64),
+                ("task_hi", C.c_void_p), ("task_lo", C.c_void_p), ("ld_task", C.c_int64),
+                ("amp_mean", C.c_void_p), ("amp_inv_std", C.c_void_p),
+                ("amp_hi", C.c_void_p), ("amp_lo", C.c_void_p), ("ld_amp", C.c_int64)]
 
 
 class Model(C.Structure):
@@ -93,6 +101,7 @@ def load():
     lib.emloco_normalize.argtypes = [vp, i64, vp, i64, i64, i32, vp, vp, f32, vp]
     lib.emloco_split_bf16.argtypes = [vp, i64, i64, i32, vp, vp, f32, vp, vp, i64, vp]
     lib.emloco_linear_bf16x3.argtypes = [vp, vp, i64, vp, vp, i64, vp, i64, i32, i32, i32, vp, i64, vp, vp, i64, vp]
+    lib.emloco_set_post_sinks.argtypes = [vp, C.POINTER(PostSinks)]
     lib.emloco_sync.argtypes = [vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)

@@ -204,6 +204,18 @@ int emloco_reset_indexed(emloco_sim* s, const int32_t* d_env_ids, int32_t n, voi
     return EMLOCO_OK;
 }
 
+int emloco_set_post_sinks(emloco_sim* s, const emloco_post_sinks* k) {
+    if (!s) return fail(EMLOCO_EINVAL, "emloco_set_post_sinks: null sim");
+    if (!k) { memset(&s->sinks, 0, sizeof s->sinks); return EMLOCO_OK; }
+    if (k->self_hi && (!k->self_lo || !k->task_hi || !k->task_lo || !k->obs_mean || !k->obs_inv_std || (k->ld_self & 7) || (k->ld_task & 7) ||
+                       k->ld_self < EML_SELF_OBS || k->ld_task < EML_TASK_OBS))
+        return fail(EMLOCO_EINVAL, "emloco_set_post_sinks: incomplete obs operand sink");
+    if (k->amp_hi && (!k->amp_lo || !k->amp_mean || !k->amp_inv_std || (k->ld_amp & 7) || k->ld_amp < EML_AMP_OBS))
+        return fail(EMLOCO_EINVAL, "emloco_set_post_sinks: incomplete AMP operand sink");
+    s->sinks = *k;
+    return EMLOCO_OK;
+}
+
 int emloco_post_step(emloco_sim* s, int32_t advance_progress, void* stream) {
     if (!s) return fail(EMLOCO_EINVAL, "emloco_post_step: null sim");
     CK(eml_launch_post_step(s, advance_progress ? 1 : 0, (cudaStream_t)stream), "post-step kernel");

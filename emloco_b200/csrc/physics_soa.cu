@@ -43,7 +43,8 @@ enum {
 #define SOA_ACC (SOA_XCHG + 4 * 27 * 32)           // 2 x 6 x 32: pelvis and chest accelerations
 #define SOA_WMAX (SOA_ACC + 2 * 6 * 32)            // 5 x 32: per-chain max body angular speed
 #define SOA_KMAX (SOA_WMAX + 5 * 32)               // 8 ints: per-warp largest piece count
-#define SOA_FLOATS (SOA_KMAX + 8)
+#define SOA_FSUM (SOA_KMAX + 8)                    // 24 x 3 x 32: contact force accumulated over the parts
+#define SOA_FLOATS (SOA_FSUM + EML_NB * 3 * 32)
 #define SOA_SMEM_BYTES (SOA_FLOATS * 4)
 
 __constant__ int c_chain_len[5] = {4, 4, 5, 5, 5};
@@ -172,32 +173,42 @@ __device__ __forceinline__ f3 acc_body(const float* smem, int lane, int b, f3& a
     return wdot;
 }
 
-struct SoaStep { float dt; float wgt; bool live; };
+struct SoaStep { float dt; float wgt; float max_w; bool live; bool last; };
 
-// contact force of the part at the end-of-part velocity (physics.cu "contact force at the end-of-step velocity")
-__device__ __forceinline__ f3 contact_force(const float* smem, int lane, int b, f3 aw, f3 al, f3 v0, const SoaStep& st) {
+// contact force of the part at the end-of-part velocity (physics.cu "contact force at the end-of-step velocity"),
+// accumulated into the per-body sums in shared memory
+__device__ __forceinline__ void contact_force(float* smem, int lane, int b, f3 aw, f3 al, f3 v0, const SoaStep& st) {
+    if (!st.live) return;
     const f3 vw = ld3(smem, lane, b, F_VW), vl = ld3(smem, lane, b, F_VL);
     const float F0z = SM(b, F_CS), Sbt = SM(b, F_CS + 1), Sbn = SM(b, F_CS + 2), Stz = SM(b, F_CS + 3), Sty = SM(b, F_CS + 4),
                 Stx = SM(b, F_CS + 5), Sny = SM(b, F_CS + 6), Snx = SM(b, F_CS + 7);
     f3 wn = vw + aw * st.dt, ln = v0 + vl + al * st.dt;
-    return mk3(st.wgt * (-Sbt * ln.x + (-Stz * wn.y + Sty * wn.z)), st.wgt * (-Sbt * ln.y + (Stz * wn.x - Stx * wn.z)),
-               st.wgt * (F0z - Sbn * ln.z + (-Sny * wn.x + Snx * wn.y)));
+    float* fs = smem + SOA_FSUM + b * 3 * 32 + lane;
+    fs[0] += st.wgt * (-Sbt * ln.x + (-Stz * wn.y + Sty * wn.z));
+    fs[32] += st.wgt * (-Sbt * ln.y + (Stz * wn.x - Stx * wn.z));
+    fs[64] += st.wgt * (F0z - Sbn * ln.z + (-Sny * wn.x + Snx * wn.y));
 }
 
-// joint integration (physics.cu "integrate"); returns the drive torque in the child frame
-__device__ __forceinline__ f3 integrate_joint(float* smem, int lane, int b, f3 wdot, float max_w, const SoaStep& st) {
+// joint acceleration from the parent's, contact force, drive torque, joint integration (physics.cu pass 3 + integrate).
+// aw/al: in = parent's spatial acceleration, out = this body's.  The drive torque of the env's last live part goes to dof_force.
+__device__ __noinline__ void finish_body(float* smem, int lane, int b, f3& aw, f3& al, f3 v0, const SoaStep& st, float* dof_force_row) {
+    const f3 wdot = acc_body(smem, lane, b, aw, al);
+    contact_force(smem, lane, b, aw, al, v0, st);
     const M3 R = quat_to_mat(ld4(smem, lane, b, F_QW));
-    const f3 tau0 = ld3(smem, lane, b, F_TAU);
-    const f3 drive = mtv(R, tau0 - wdot * SM(b, F_DD));
     if (st.live) {
+        if (st.last && dof_force_row) {
+            const f3 tau0 = ld3(smem, lane, b, F_TAU);
+            const f3 drive = mtv(R, tau0 - wdot * SM(b, F_DD));
+            float* df = dof_force_row + 3 * (b - 1);
+            df[0] = drive.x; df[1] = drive.y; df[2] = drive.z;
+        }
         f3 jw = ld3(smem, lane, b, F_JW) + mtv(R, wdot) * st.dt;
         float n2 = dot3(jw, jw);
-        if (n2 > max_w * max_w) jw = jw * (max_w * rsqrtf(n2));
+        if (n2 > st.max_w * st.max_w) jw = jw * (st.max_w * rsqrtf(n2));
         f4 jq = qnormalize(qmul(ld4(smem, lane, b, F_JQ), exp_quat(jw * st.dt)));
         st3(smem, lane, b, F_JW, jw);
         st4(smem, lane, b, F_JQ, jq);
     }
-    return drive;
 }
 
 __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams P) {
@@ -243,16 +254,13 @@ __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams 
         }
         qtgt[s] = exp_quat(target);
     }
-    f3 fsum[6];                                                    // chain warps: contact force per chain body (+ pelvis in [5])
-    f3 drive[5];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) fsum[i] = mk3(0, 0, 0);
-#pragma unroll
-    for (int i = 0; i < 5; ++i) drive[i] = mk3(0, 0, 0);
+    // contact-force sums start at zero (24 x 3 x 32 floats: 9 per thread)
+    for (int i = threadIdx.x; i < EML_NB * 3 * 32; i += SOA_THREADS) smem[SOA_FSUM + i] = 0.f;
     __syncthreads();
 
     const int chain = warp;                                        // warps 0..4 walk chains
     const int clen = chain < 5 ? c_chain_len[chain] : 0;
+    float* const df_row = env_ok ? P.dof_force + (size_t)env * EML_ND : nullptr;
     int sub = 0, part = 0, parts = 1, kmax = 1, rb = 0;            // rb: root buffer holding the current root state
     float dt = P.dt;
 #pragma unroll 1
@@ -271,19 +279,13 @@ __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams 
                 st3(smem, lane, 0, F_X, k.x); st4(smem, lane, 0, F_QW, k.q); st3(smem, lane, 0, F_VW, k.w); st3(smem, lane, 0, F_VL, k.l);
                 wm = dot3(w0, w0);
             }
-            if (chain >= 3) {                                      // arms hang off the chest: walk torso, spine, chest first
-#pragma unroll
-                for (int a = 9; a <= 11; ++a) {
-                    f3 cw, cl;
-                    k = kin_step(k, mk3(Mo.offset[a][0], Mo.offset[a][1], Mo.offset[a][2]), ld4(smem, lane, a, F_JQ), ld3(smem, lane, a, F_JW), cw, cl);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 5; ++i) {
-                if (i < clen) {
-                    const int b = c_chain_body[chain][i];
-                    f3 cw, cl;
-                    k = kin_step(k, mk3(Mo.offset[b][0], Mo.offset[b][1], Mo.offset[b][2]), ld4(smem, lane, b, F_JQ), ld3(smem, lane, b, F_JW), cw, cl);
+            const int pre = chain >= 3 ? 3 : 0;                    // arms hang off the chest: walk torso, spine, chest first
+#pragma unroll 1
+            for (int i = -pre; i < clen; ++i) {
+                const int b = i < 0 ? 12 + i : c_chain_body[chain][i];
+                f3 cw, cl;
+                k = kin_step(k, mk3(Mo.offset[b][0], Mo.offset[b][1], Mo.offset[b][2]), ld4(smem, lane, b, F_JQ), ld3(smem, lane, b, F_JW), cw, cl);
+                if (i >= 0) {
                     st3(smem, lane, b, F_X, k.x); st4(smem, lane, b, F_QW, k.q); st3(smem, lane, b, F_VW, k.w); st3(smem, lane, b, F_VL, k.l);
                     st3(smem, lane, b, F_C, cw); st3(smem, lane, b, F_C + 3, cl);
                     wm = fmaxf(wm, dot3(k.w, k.w));
@@ -313,7 +315,8 @@ __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams 
 #pragma unroll
             for (int w = 0; w < SOA_WARPS; ++w) kmax = max(kmax, s_k[w]);
         }
-        SoaStep st; st.dt = dt; st.wgt = 1.0f / (float)parts; st.live = part < parts;
+        SoaStep st; st.dt = dt; st.wgt = 1.0f / (float)parts; st.max_w = P.max_w; st.live = part < parts;
+        st.last = (sub == P.n_sub - 1) && (part == parts - 1);
 
         // ================= A1: per-body inertia, bias force, contacts, drive (bodies warp, warp + 8, warp + 16) =================
 #pragma unroll 1
@@ -408,15 +411,13 @@ __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams 
         Sp carry;
         if (chain < 5) {
             const int stop = chain == 2 ? 3 : 0;                       // spine warp: head, neck now; chest.. after the arms
-#pragma unroll
-            for (int i = 4; i >= 0; --i) {
-                if (i < clen && i >= stop) {
-                    const int b = c_chain_body[chain][i];
-                    Sp sp; ld_sp(smem, lane, b, sp);
-                    if (i < clen - 1) add_sp(sp, carry);
-                    aba_body(smem, lane, b, sp, Mo.arm[b]);
-                    carry = sp;
-                }
+#pragma unroll 1
+            for (int i = clen - 1; i >= stop; --i) {
+                const int b = c_chain_body[chain][i];
+                Sp sp; ld_sp(smem, lane, b, sp);
+                if (i < clen - 1) add_sp(sp, carry);
+                aba_body(smem, lane, b, sp, Mo.arm[b]);
+                carry = sp;
             }
             if (chain != 2) st_xchg(smem, lane, chain < 2 ? chain : chain - 1, carry);   // slots: 0,1 legs; 2,3 arms
         }
@@ -424,9 +425,8 @@ __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams 
 
         // ================= B2 (spine warp): chest, spine, torso; pelvis and the 6x6 root solve; accelerations of torso..chest ==========
         if (chain == 2) {
-#pragma unroll
-            for (int i = 2; i >= 0; --i) {
-                const int b = c_chain_body[2][i];
+#pragma unroll 1
+            for (int b = 11; b >= 9; --b) {
                 Sp sp; ld_sp(smem, lane, b, sp);
                 add_sp(sp, carry);
                 if (b == 11) { add_xchg(smem, lane, 2, sp); add_xchg(smem, lane, 3, sp); }
@@ -448,8 +448,7 @@ __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams 
             f3 al = sv(Mi, mk3(0, 0, 0) - sp.pf - mtv(sp.B, aw));
             float* acc = smem + SOA_ACC + lane;
             acc[0] = aw.x; acc[32] = aw.y; acc[64] = aw.z; acc[96] = al.x; acc[128] = al.y; acc[160] = al.z;
-            f3 f = contact_force(smem, lane, 0, aw, al, v0, st);
-            if (st.live) fsum[5] = fsum[5] + f;
+            contact_force(smem, lane, 0, aw, al, v0, st);
             // root integration into the other root buffer (the current one is still read by the other warps in pass C)
             {
                 float* nr = smem + SOA_ROOT + (rb ^ 1) * 13 * 32 + lane;
@@ -467,16 +466,9 @@ __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams 
                 nr[0] = np0.x; nr[32] = np0.y; nr[64] = np0.z; nr[96] = nq0.x; nr[128] = nq0.y; nr[160] = nq0.z; nr[192] = nq0.w;
                 nr[224] = nv0.x; nr[256] = nv0.y; nr[288] = nv0.z; nr[320] = nw0.x; nr[352] = nw0.y; nr[384] = nw0.z;
             }
-            // torso, spine, chest: accelerations, contact force, integration (the arms and neck start from the chest's)
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const int b = c_chain_body[2][i];
-                f3 wdot = acc_body(smem, lane, b, aw, al);
-                f3 fc = contact_force(smem, lane, b, aw, al, v0, st);
-                if (st.live) fsum[i] = fsum[i] + fc;
-                f3 dr = integrate_joint(smem, lane, b, wdot, P.max_w, st);
-                if (st.live) drive[i] = dr;
-            }
+            // torso, spine, chest: accelerations, contact force, integration (the arms and the neck start from the chest's)
+#pragma unroll 1
+            for (int b = 9; b <= 11; ++b) finish_body(smem, lane, b, aw, al, v0, st, df_row);
             acc[6 * 32] = aw.x; acc[7 * 32] = aw.y; acc[8 * 32] = aw.z; acc[9 * 32] = al.x; acc[10 * 32] = al.y; acc[11 * 32] = al.z;
         }
         __syncthreads();
@@ -485,25 +477,15 @@ __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams 
         if (chain < 5) {
             const float* acc = smem + SOA_ACC + (chain >= 2 ? 6 * 32 : 0) + lane;   // legs start at the pelvis, the rest at the chest
             f3 aw = mk3(acc[0], acc[32], acc[64]), al = mk3(acc[96], acc[128], acc[160]);
-            const int start = chain == 2 ? 3 : 0;
-#pragma unroll
-            for (int i = 0; i < 5; ++i) {
-                if (i < clen && i >= start) {
-                    const int b = c_chain_body[chain][i];
-                    f3 wdot = acc_body(smem, lane, b, aw, al);
-                    f3 fc = contact_force(smem, lane, b, aw, al, v0, st);
-                    if (st.live) fsum[i] = fsum[i] + fc;
-                    f3 dr = integrate_joint(smem, lane, b, wdot, P.max_w, st);
-                    if (st.live) drive[i] = dr;
-                }
-            }
+#pragma unroll 1
+            for (int i = chain == 2 ? 3 : 0; i < clen; ++i) finish_body(smem, lane, c_chain_body[chain][i], aw, al, v0, st, df_row);
         }
         rb ^= 1;
         if (++part == kmax) { part = 0; ++sub; }
         __syncthreads();
     }
 
-    // ================= refresh: forward kinematics -> rigid-body state, DOF state, contact and DOF forces =================
+    // ================= refresh: forward kinematics -> rigid-body state, DOF state, contact forces =================
     if (chain < 5) {
         const float* root = smem + SOA_ROOT + rb * 13 * 32;
         const f3 p0 = mk3(root[lane], root[32 + lane], root[64 + lane]);
@@ -512,47 +494,41 @@ __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams 
         const f3 w0 = mk3(root[10 * 32 + lane], root[11 * 32 + lane], root[12 * 32 + lane]);
         const float inv = P.n_sub > 0 ? 1.0f / (float)P.n_sub : 0.f;   // mean force over the sub-steps
         f4 qw = q0; f3 x = p0, wv = w0, lv = v0;
-        auto put_rb = [&](int b, f3 px, f4 pq, f3 pl, f3 pw) {
+        auto put_body = [&](int b) {
             if (!env_ok) return;
             float* o = P.rb + ((size_t)env * EML_NB + b) * 13;
-            o[0] = px.x; o[1] = px.y; o[2] = px.z; o[3] = pq.x; o[4] = pq.y; o[5] = pq.z; o[6] = pq.w;
-            o[7] = pl.x; o[8] = pl.y; o[9] = pl.z; o[10] = pw.x; o[11] = pw.y; o[12] = pw.z;
+            o[0] = x.x; o[1] = x.y; o[2] = x.z; o[3] = qw.x; o[4] = qw.y; o[5] = qw.z; o[6] = qw.w;
+            o[7] = lv.x; o[8] = lv.y; o[9] = lv.z; o[10] = wv.x; o[11] = wv.y; o[12] = wv.z;
+            const float* fs = smem + SOA_FSUM + b * 3 * 32 + lane;
+            float* c = P.contact + ((size_t)env * EML_NB + b) * 3;
+            c[0] = fs[0] * inv; c[1] = fs[32] * inv; c[2] = fs[64] * inv;
         };
-        auto step_fk = [&](int b) {
-            f4 jq = ld4(smem, lane, b, F_JQ); f3 jw = ld3(smem, lane, b, F_JW);
-            f3 t = qrot(qw, mk3(Mo.offset[b][0], Mo.offset[b][1], Mo.offset[b][2]));
+        if (chain == 2) {
+            put_body(0);
+            if (env_ok) {
+                float* r = P.root + (size_t)env * 13;
+                r[0] = p0.x; r[1] = p0.y; r[2] = p0.z; r[3] = q0.x; r[4] = q0.y; r[5] = q0.z; r[6] = q0.w;
+                r[7] = v0.x; r[8] = v0.y; r[9] = v0.z; r[10] = w0.x; r[11] = w0.y; r[12] = w0.z;
+            }
+        }
+        const int pre = chain >= 3 ? 3 : 0;
+#pragma unroll 1
+        for (int i = -pre; i < clen; ++i) {
+            const int b = i < 0 ? 12 + i : c_chain_body[chain][i];
+            const f4 jq = ld4(smem, lane, b, F_JQ); const f3 jw = ld3(smem, lane, b, F_JW);
+            const f3 t = qrot(qw, mk3(Mo.offset[b][0], Mo.offset[b][1], Mo.offset[b][2]));
             lv = lv + cross3(wv, t);
             x = x + t;
             qw = qmul(qw, jq);
             wv = wv + qrot(qw, jw);
-        };
-        if (chain == 2 && env_ok) {
-            put_rb(0, p0, q0, v0, w0);
-            float* r = P.root + (size_t)env * 13;
-            r[0] = p0.x; r[1] = p0.y; r[2] = p0.z; r[3] = q0.x; r[4] = q0.y; r[5] = q0.z; r[6] = q0.w;
-            r[7] = v0.x; r[8] = v0.y; r[9] = v0.z; r[10] = w0.x; r[11] = w0.y; r[12] = w0.z;
-            float* c = P.contact + (size_t)env * EML_NB * 3;
-            c[0] = fsum[5].x * inv; c[1] = fsum[5].y * inv; c[2] = fsum[5].z * inv;
-        }
-        if (chain >= 3) { step_fk(9); step_fk(10); step_fk(11); }
-#pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            if (i < clen) {
-                const int b = c_chain_body[chain][i];
-                step_fk(b);
-                put_rb(b, x, qw, lv, wv);
-                if (env_ok) {
-                    const int d = 3 * (b - 1);
-                    f4 jq = ld4(smem, lane, b, F_JQ); f3 jw = ld3(smem, lane, b, F_JW);
-                    f3 e = log_quat(jq);
-                    float2* ds = reinterpret_cast<float2*>(P.dof + ((size_t)env * EML_ND + d) * 2);
-                    ds[0] = make_float2(e.x, jw.x); ds[1] = make_float2(e.y, jw.y); ds[2] = make_float2(e.z, jw.z);
-                    *reinterpret_cast<float4*>(P.jq + ((size_t)env * EML_NJ + (b - 1)) * 4) = make_float4(jq.x, jq.y, jq.z, jq.w);
-                    float* df = P.dof_force + (size_t)env * EML_ND + d;
-                    df[0] = drive[i].x; df[1] = drive[i].y; df[2] = drive[i].z;
-                    float* c = P.contact + ((size_t)env * EML_NB + b) * 3;
-                    c[0] = fsum[i].x * inv; c[1] = fsum[i].y * inv; c[2] = fsum[i].z * inv;
-                }
+            if (i < 0) continue;
+            put_body(b);
+            if (env_ok) {
+                const int d = 3 * (b - 1);
+                const f3 e = log_quat(jq);
+                float2* ds = reinterpret_cast<float2*>(P.dof + ((size_t)env * EML_ND + d) * 2);
+                ds[0] = make_float2(e.x, jw.x); ds[1] = make_float2(e.y, jw.y); ds[2] = make_float2(e.z, jw.z);
+                *reinterpret_cast<float4*>(P.jq + ((size_t)env * EML_NJ + (b - 1)) * 4) = make_float4(jq.x, jq.y, jq.z, jq.w);
             }
         }
     }

@@ -14,6 +14,7 @@
 // flops per output.  One 128-thread CTA per env; inputs are staged in shared memory with vector
 // loads, the 1422-float observation row is assembled in shared memory and streamed out (normal and
 // mirrored) with coalesced 8-byte stores; the AMP ring is shifted through registers.
+#include <cuda_bf16.h>
 #include "sim.h"
 
 #define PS_THREADS 128
@@ -32,7 +33,19 @@ struct PostParams {
     int64_t* reset; int64_t* terminate; float* amp;
     int N; int advance; int reset_mode; float dt; float traj_dur; float sample_dt; int max_len;
     float power_coef, loc_coef, fail_dist2;
+    emloco_post_sinks k;   // optional extra outputs (experience rows, normalised bf16 hi/lo operands of the nets)
 };
+
+// normalise like RunningMeanStd.forward (utils/running_mean_std.py:82-84) and split into bf16 hi + lo (csrc/linear_tc.cu)
+__device__ __forceinline__ void norm_split2(float x0, float x1, const float* __restrict__ mean, const float* __restrict__ inv_std,
+                                            int k, uint32_t& hi, uint32_t& lo) {
+    float a = fminf(fmaxf((x0 - __ldg(mean + k)) * __ldg(inv_std + k), -5.0f), 5.0f);
+    float b = fminf(fmaxf((x1 - __ldg(mean + k + 1)) * __ldg(inv_std + k + 1), -5.0f), 5.0f);
+    __nv_bfloat16 h0 = __float2bfloat16_rn(a), h1 = __float2bfloat16_rn(b);
+    __nv_bfloat16 l0 = __float2bfloat16_rn(a - __bfloat162float(h0)), l1 = __float2bfloat16_rn(b - __bfloat162float(h1));
+    hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+}
 
 // Terrain.world_points_to_map + sample (..terrain.py:1212-1218,1282-1288); fp32 division and
 // truncation exactly as torch does on the host path.
@@ -251,18 +264,50 @@ __global__ void __launch_bounds__(PS_THREADS) post_step_kernel(PostParams P) {
             }
             f[i2] = make_float2(v[0], v[1]);
         }
+        // optional sinks of the same observation row: experience row, and the normalised bf16 hi/lo operands the
+        // tensor-core layers read (self-obs part -> actor/critic input, task-obs part -> task MLP input)
+        if (P.k.obs_copy) {
+            float2* oc = reinterpret_cast<float2*>(P.k.obs_copy + (size_t)env * EML_OBS);
+            for (int i2 = tid; i2 < EML_OBS / 2; i2 += PS_THREADS) oc[i2] = reinterpret_cast<const float2*>(s_obs)[i2];
+        }
+        if (P.k.self_hi) {
+            for (int i2 = tid; i2 < EML_OBS / 2; i2 += PS_THREADS) {
+                const int i = 2 * i2;
+                uint32_t hi, lo;
+                norm_split2(s_obs[i], s_obs[i + 1], P.k.obs_mean, P.k.obs_inv_std, i, hi, lo);
+                if (i < EML_SELF_OBS) {
+                    *reinterpret_cast<uint32_t*>(P.k.self_hi + (size_t)env * P.k.ld_self + i) = hi;
+                    *reinterpret_cast<uint32_t*>(P.k.self_lo + (size_t)env * P.k.ld_self + i) = lo;
+                } else {
+                    *reinterpret_cast<uint32_t*>(P.k.task_hi + (size_t)env * P.k.ld_task + (i - EML_SELF_OBS)) = hi;
+                    *reinterpret_cast<uint32_t*>(P.k.task_lo + (size_t)env * P.k.ld_task + (i - EML_SELF_OBS)) = lo;
+                }
+            }
+        }
         float2* a = reinterpret_cast<float2*>(P.amp + (size_t)env * EML_AMP_OBS);
         if (rmode) {
             for (int i = tid; i < 15 * 103; i += PS_THREADS) a[i] = reinterpret_cast<const float2*>(s_amp)[i % 103];
             if (tid == 0) { P.reset[env] = 0; P.terminate[env] = 0; }
             return;
         }
+        float2* ac = P.k.amp_copy ? reinterpret_cast<float2*>(P.k.amp_copy + (size_t)env * EML_AMP_OBS) : nullptr;
+        uint32_t* ah = P.k.amp_hi ? reinterpret_cast<uint32_t*>(P.k.amp_hi + (size_t)env * P.k.ld_amp) : nullptr;
+        uint32_t* al = P.k.amp_hi ? reinterpret_cast<uint32_t*>(P.k.amp_lo + (size_t)env * P.k.ld_amp) : nullptr;
 #pragma unroll
         for (int k = 0; k < 12; ++k) {
             int i = tid + PS_THREADS * k;
-            if (i < 14 * 103) a[103 + i] = hist[k];
+            if (i < 14 * 103) {
+                a[103 + i] = hist[k];
+                if (ac) ac[103 + i] = hist[k];
+                if (ah) { uint32_t hi, lo; norm_split2(hist[k].x, hist[k].y, P.k.amp_mean, P.k.amp_inv_std, 2 * (103 + i), hi, lo); ah[103 + i] = hi; al[103 + i] = lo; }
+            }
         }
-        if (tid < 103) a[tid] = reinterpret_cast<const float2*>(s_amp)[tid];
+        if (tid < 103) {
+            const float2 v = reinterpret_cast<const float2*>(s_amp)[tid];
+            a[tid] = v;
+            if (ac) ac[tid] = v;
+            if (ah) { uint32_t hi, lo; norm_split2(v.x, v.y, P.k.amp_mean, P.k.amp_inv_std, 2 * tid, hi, lo); ah[tid] = hi; al[tid] = lo; }
+        }
     }
 }
 
@@ -291,7 +336,7 @@ static cudaError_t launch_post(emloco_sim* s, int advance_progress, int reset_mo
     P.verts = s->verts; P.betas = s->betas; P.height = s->height; P.hf_rows = s->hf_rows; P.hf_cols = s->hf_cols;
     P.progress = s->progress; P.obs = s->obs; P.flip_obs = s->flip_obs; P.rew = s->rew; P.rew_raw = s->rew_raw;
     P.reset = s->reset; P.terminate = s->terminate; P.amp = s->amp_obs;
-    P.N = s->N; P.advance = advance_progress; P.reset_mode = reset_mode;
+    P.N = s->N; P.advance = advance_progress; P.reset_mode = reset_mode; P.k = s->sinks;
     double dt = (double)s->cfg.control_freq_inv * (double)s->cfg.sim_dt;          // humanoid.py:89
     P.dt = (float)dt;
     double tdt = ((double)s->cfg.episode_length * dt) / (EML_NUM_VERTS - 1);      // traj_generator.py:24

@@ -58,6 +58,7 @@ struct emloco_sim {
     float*   h_pin;
     size_t   h_pin_bytes;
     cudaStream_t copy_stream;
+    emloco_post_sinks sinks;   // optional extra outputs of the post-step kernel (all NULL by default)
 };
 
 struct RecordParams {

@@ -47,8 +47,14 @@ class RunningMeanStd(nn.Module):
         """(mean, var) as float32 - `current_var.float()` of running_mean_std.py:78-84 - cached until the stats change."""
         key = (self.running_mean._version, self.running_var._version, self.running_mean.device)
         if self._f32 is None or self._f32[0] != key:
-            self._f32 = (key, self.running_mean.float().contiguous(), self.running_var.float().contiguous())
+            var = self.running_var.float().contiguous()
+            self._f32 = (key, self.running_mean.float().contiguous(), var, (1.0 / torch.sqrt(var + self.epsilon)).contiguous())
         return self._f32[1], self._f32[2]
+
+    def inv_std(self):
+        """1/sqrt(var + eps) as float32, for the kernels that multiply instead of dividing (post-step operand sinks)."""
+        self.f32()
+        return self._f32[3]
 
 
 class AMPSeptValueNetwork(nn.Module):
@@ -116,18 +122,34 @@ class RolloutNets:
                              torch.cat([ps[1].detach(), ps[3].detach()]).contiguous())
         return self._stacked[1], self._stacked[2]
 
+    def post_sinks(self, obs_copy=None, amp_copy=None):
+        """emloco_post_sinks pointing at this object's operand buffers (tensor-core path) plus the given experience rows."""
+        k = _lib.PostSinks()
+        k.obs_copy = None if obs_copy is None else obs_copy.data_ptr()
+        k.amp_copy = None if amp_copy is None else amp_copy.data_ptr()
+        if self.tc:
+            om, _ = self.obs_norm.f32(); am, _ = self.amp_norm.f32()
+            k.obs_mean, k.obs_inv_std = om.data_ptr(), self.obs_norm.inv_std().data_ptr()
+            k.self_hi, k.self_lo, k.ld_self = self.s_ain.hi.data_ptr(), self.s_ain.lo.data_ptr(), self.s_ain.ld
+            k.task_hi, k.task_lo, k.ld_task = self.s_tin.hi.data_ptr(), self.s_tin.lo.data_ptr(), self.s_tin.ld
+            k.amp_mean, k.amp_inv_std = am.data_ptr(), self.amp_norm.inv_std().data_ptr()
+            k.amp_hi, k.amp_lo, k.ld_amp = self.s_amp.hi.data_ptr(), self.s_amp.lo.data_ptr(), self.s_amp.ld
+        return k
+
     def _lin(self, x, layer, relu, out, mean=None, var=None):
         return linear(x, layer.weight.detach(), layer.bias.detach(), relu=relu, mean=mean, var=var, out=out,
                       eps=self.obs_norm.epsilon)
 
-    def _trunk(self, obs):
-        """normalise -> task MLP -> [norm(self obs) | task_out] (amp_network_sept_builder.py:69-76,82-96)."""
+    def _trunk(self, obs, operands_ready=False):
+        """normalise -> task MLP -> [norm(self obs) | task_out] (amp_network_sept_builder.py:69-76,82-96).
+        operands_ready: the post-step kernel already wrote the normalised bf16 operands (emloco_set_post_sinks)."""
         n = self.net
         mean, var = self.obs_norm.f32()
         if self.tc:
             W, eps = self.w16.get, self.obs_norm.epsilon
-            split_bf16(obs[:, :SELF_OBS], self.s_ain.cols(0, SELF_OBS), mean[:SELF_OBS], var[:SELF_OBS], eps)
-            split_bf16(obs[:, SELF_OBS:], self.s_tin, mean[SELF_OBS:], var[SELF_OBS:], eps)
+            if not operands_ready:
+                split_bf16(obs[:, :SELF_OBS], self.s_ain.cols(0, SELF_OBS), mean[:SELF_OBS], var[:SELF_OBS], eps)
+                split_bf16(obs[:, SELF_OBS:], self.s_tin, mean[SELF_OBS:], var[SELF_OBS:], eps)
             linear_bf16x3(self.s_tin, W("t0", n._task_mlp[0].weight), n._task_mlp[0].bias.detach(), True, y16=self.s_t1)
             linear_bf16x3(self.s_t1, W("t2", n._task_mlp[2].weight), n._task_mlp[2].bias.detach(), True,
                           y16=self.s_ain.cols(SELF_OBS, self.s_ain.K))
@@ -137,7 +159,8 @@ class RolloutNets:
         self._lin(self.t1, n._task_mlp[2], True, self.ain[:, SELF_OBS:])
         return mean, var
 
-    def action_values(self, obs, noise, mu_out=None, task_value_out=None, actions_out=None, neglogp_out=None):
+    def action_values(self, obs, noise, mu_out=None, task_value_out=None, actions_out=None, neglogp_out=None,
+                      operands_ready=False):
         """get_action_values (rl_games A2CBase; called at amp_continuous_value.py:53): mu, sigma(logstd), value (still in
         normalised units), task value, sampled action, neglogp.  obs [M,1422], noise [M,69] (standard normal).
         The *_out tensors let the heads write directly into the caller's experience rows."""
@@ -146,7 +169,7 @@ class RolloutNets:
         task_value_out = self.task_value if task_value_out is None else task_value_out
         actions_out = self.actions if actions_out is None else actions_out
         neglogp_out = self.neglogp if neglogp_out is None else neglogp_out
-        mean, var = self._trunk(obs)
+        mean, var = self._trunk(obs, operands_ready)
         w, b = self._w_ac1()
         h = n.actor_mlp[0].out_features
         if self.tc:
@@ -171,10 +194,10 @@ class RolloutNets:
         return dict(mus=mu_out, sigmas=n.sigma, values=self.value, task_values=task_value_out, actions=actions_out,
                     neglogpacs=neglogp_out)
 
-    def critic(self, obs):
+    def critic(self, obs, operands_ready=False):
         """_eval_critic (common_agent.py:647-655) before value un-normalisation: [M,1]."""
         n = self.net
-        self._trunk(obs)
+        self._trunk(obs, operands_ready)
         h = n.critic_mlp[0].out_features
         if self.tc:
             W = self.w16.get
@@ -187,7 +210,7 @@ class RolloutNets:
         self._lin(self.c2, n.value, False, self.next_value)
         return self.next_value
 
-    def disc_logits(self, amp_obs, out=None):
+    def disc_logits(self, amp_obs, out=None, operands_ready=False):
         """_eval_disc (amp_continuous.py:666-668): normalise -> 3090->1024->512->1.  amp_obs [M',3090], M' <= M."""
         n = self.net
         m = amp_obs.shape[0]
@@ -195,7 +218,8 @@ class RolloutNets:
         out = self.logit[:m] if out is None else out
         if self.tc:
             W = self.w16.get
-            split_bf16(amp_obs, self.s_amp.rows_view(m), mean, var, self.amp_norm.epsilon)
+            if not operands_ready:
+                split_bf16(amp_obs, self.s_amp.rows_view(m), mean, var, self.amp_norm.epsilon)
             linear_bf16x3(self.s_amp.rows_view(m), W("d0", n._disc_mlp[0].weight), n._disc_mlp[0].bias.detach(), True,
                           y16=self.s_d1.rows_view(m))
             linear_bf16x3(self.s_d1.rows_view(m), W("d2", n._disc_mlp[2].weight), n._disc_mlp[2].bias.detach(), True,

@@ -32,7 +32,7 @@ class Rollout:
     def __init__(self, num_envs, device=0, horizon=32, seed=0, tensor_cores=False, gamma=0.99, tau=0.95,
                  task_reward_w=0.5, disc_reward_w=0.5, disc_reward_scale=2.0, inversion_penalty_scale=0.3,
                  step_to_pred=144, normalize_value=True, net=None, obs_norm=None, amp_norm=None, value_norm=None,
-                 recompute_disc=True, valuenet=None):
+                 recompute_disc=True, valuenet=None, fuse_sinks=True):
         self.N, self.T, self.device = int(num_envs), int(horizon), int(device)
         self.gamma, self.tau = gamma, tau
         self.task_reward_w, self.disc_reward_w, self.disc_reward_scale = task_reward_w, disc_reward_w, disc_reward_scale
@@ -55,8 +55,21 @@ class Rollout:
         self.init_root = torch.from_numpy(st["root"]).to(dev)
         self.init_dof = torch.from_numpy(st["dof"]).to(dev)
         self.sim.traj_verts.copy_(torch.from_numpy(st["verts"]).to(dev))
+        f = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
+        T, N = self.T, self.N
+        # experience rows; `obses` has one spare row (T) that receives the observation following the last step of a horizon
+        self.mb = dict(obses=f(T + 1, N, OBS), actions=f(T, N, ACTIONS), neglogpacs=f(T, N), values=f(T, N, 1), mus=f(T, N, ACTIONS),
+                       task_values=f(T, N, 1), rewards=f(T, N, 1), next_values=f(T, N, 1), dones=f(T, N), amp_obs=f(T, N, AMP_OBS),
+                       amp_rewards=f(T, N, 1))
+        # fuse_sinks: the post-step / reset kernels write the experience rows and the normalised bf16 operands of the first
+        # layers themselves (emloco_set_post_sinks) instead of separate copy / split launches
+        self.fuse = bool(fuse_sinks)
         self.sim.reset.fill_(1)
+        if self.fuse:
+            self.sim.set_post_sinks(self.nets.post_sinks(obs_copy=self.mb["obses"][T]))
         self.sim.reset_done(self.init_root, self.init_dof)
+        if not self.fuse:
+            self.mb["obses"][T].copy_(self.sim.obs)
 
         # LocoVal inputs captured at reset (humanoid_pedestrain_terrain.py:509-515, vec_task_wrappers.py:47-66)
         self.waypoint_traj = torch.from_numpy(st["waypoints"]).to(dev)                  # [N,13,2], origin-relative
@@ -71,11 +84,6 @@ class Rollout:
         self._graphs = {}
         self._cur = {}
 
-        f = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
-        T, N = self.T, self.N
-        self.mb = dict(obses=f(T, N, OBS), actions=f(T, N, ACTIONS), neglogpacs=f(T, N), values=f(T, N, 1), mus=f(T, N, ACTIONS),
-                       task_values=f(T, N, 1), rewards=f(T, N, 1), next_values=f(T, N, 1), dones=f(T, N), amp_obs=f(T, N, AMP_OBS),
-                       amp_rewards=f(T, N, 1), next_obses=None)
         self.state = f(6, N)
         self.state[3].fill_(1.0)      # discount_coefs start at 1
         self.noise = f(N, ACTIONS)
@@ -112,31 +120,45 @@ class Rollout:
         return {s: v / max(steps, 1) for s, v in out.items()}, steps
 
     # ---- one control step: everything inside the `for n in range(horizon_length)` body, as seven segments ----
-    def _segment_fns(self, n, noise=None):
+    def _segment_fns(self, n, noise=None, host_obs=False):
         sim, nets, mb, cur = self.sim, self.nets, self.mb, self._cur
 
+        fuse = self.fuse and not host_obs
+        nxt = n + 1                                                                    # row T is the spare row
+
         def seg_reset():                                                               # env_reset(done_indices), :45-46
-            sim.reset_done(self.init_root, self.init_dof)
-            mb["obses"][n].copy_(sim.obs)
+            if fuse:
+                if n == 0:
+                    mb["obses"][0].copy_(mb["obses"][self.T])                          # observation that followed the last horizon
+                sim.set_post_sinks(nets.post_sinks(obs_copy=mb["obses"][n]))           # reset rows are patched in place
+                sim.reset_done(self.init_root, self.init_dof)
+            else:
+                sim.set_post_sinks(None)
+                sim.reset_done(self.init_root, self.init_dof)
+                mb["obses"][n].copy_(sim.obs)
             cur["noise"] = self.noise.normal_(generator=self.gen) if noise is None else noise
 
         def seg_policy():                                                              # get_action_values, :53
             # the heads write straight into row n of the experience tensors (experience_buffer.update_data, :47-56)
             cur["res"] = nets.action_values(sim.obs, cur["noise"], mu_out=mb["mus"][n], task_value_out=mb["task_values"][n],
-                                            actions_out=mb["actions"][n], neglogp_out=mb["neglogpacs"][n])
+                                            actions_out=mb["actions"][n], neglogp_out=mb["neglogpacs"][n], operands_ready=fuse)
 
         def seg_physics():                                                             # env_step: pre_physics + simulate
             sim.physics_step(cur["res"]["actions"])
 
         def seg_post():                                                                #           post_physics_step
-            sim.post_step(True)
-            mb["amp_obs"][n].copy_(sim.amp_obs.view(self.N, AMP_OBS))
+            if fuse:
+                sim.set_post_sinks(nets.post_sinks(obs_copy=mb["obses"][nxt], amp_copy=mb["amp_obs"][n]))
+                sim.post_step(True)
+            else:
+                sim.post_step(True)
+                mb["amp_obs"][n].copy_(sim.amp_obs.view(self.N, AMP_OBS))
 
         def seg_critic():                                                              # _eval_critic(next obs), :85
-            cur["nv"] = nets.critic(sim.obs)
+            cur["nv"] = nets.critic(sim.obs, operands_ready=fuse)
 
         def seg_disc():                                                                # _calc_amp_rewards, :93
-            cur["logit"] = nets.disc_logits(sim.amp_obs.view(self.N, AMP_OBS))
+            cur["logit"] = nets.disc_logits(sim.amp_obs.view(self.N, AMP_OBS), operands_ready=fuse)
 
         def seg_record():
             # values are un-normalised (get_action_values, normalize_value) together with next_values in the record kernel
@@ -150,8 +172,9 @@ class Rollout:
 
         return [seg_reset, seg_policy, seg_physics, seg_post, seg_critic, seg_disc, seg_record]
 
-    def step(self, n, noise=None):
-        for f in self._segment_fns(n, noise):
+    def step(self, n, noise=None, host_obs=False):
+        """host_obs: the caller overwrote sim.obs (host-provided observations): operands are re-derived from it."""
+        for f in self._segment_fns(n, noise, host_obs):
             self._mark()
             f()
         self._mark()
@@ -173,7 +196,7 @@ class Rollout:
                                                       _stream()), "emloco_disc_reward")
         adv, ret = gae(mb["dones"], mb["values"], self._comb(), mb["next_values"], self.gamma, self.tau)
         self.mb_advs, self.mb_returns = adv, ret
-        out = {k: v for k, v in mb.items() if v is not None}
+        out = {k: (v[:T] if k == "obses" else v) for k, v in mb.items()}
         out.update(returns=ret, advantages=adv, task_rewards=mb["rewards"], rewards=self._comb())   # mb_rewards := combined (:160)
         self._finish_out = out
         return out
@@ -215,7 +238,7 @@ class Rollout:
 
     def step_graphed_host_noise(self, n):
         """step(n) with the policy noise taken from self.noise as the caller filled it (no generator call in the graph)."""
-        self._replay(("hn", n), lambda: self.step(n, noise=self.noise))
+        self._replay(("hn", n), lambda: self.step(n, noise=self.noise, host_obs=True))
 
     def step_segments_graphed(self, n):
         """step(n) as seven per-segment graphs with a timing event between them: per-segment device time without host

@@ -115,6 +115,10 @@ class EmlocoSim:
                 raise _lib.EmlocoError(f"reset_done: initial state must be contiguous float32 CUDA of shape {shp}")
         _lib.check(self.lib.emloco_reset_done(self._h, _ptr(init_root), _ptr(init_dof), _stream()), "emloco_reset_done")
 
+    def set_post_sinks(self, sinks=None):
+        """Optional extra outputs of post_step / reset_done (emloco_post_sinks); None clears them."""
+        _lib.check(self.lib.emloco_set_post_sinks(self._h, None if sinks is None else C.byref(sinks)), "emloco_set_post_sinks")
+
     def post_step(self, advance_progress=True):
         _lib.check(self.lib.emloco_post_step(self._h, int(bool(advance_progress)), _stream()), "emloco_post_step")
 

@@ -125,6 +125,26 @@ int emloco_simulate(emloco_sim* sim, void* stream);
  * and DOF force.  d_env_ids == NULL means all envs. */
 int emloco_reset_indexed(emloco_sim* sim, const int32_t* d_env_ids, int32_t n, void* stream);
 
+/* Optional extra outputs of the fused post-step kernel (and of the post-step part of emloco_reset_done), so that the
+ * rollout's copies and operand conversions cost no extra pass over HBM:
+ *   obs_copy / amp_copy  experience rows `experience_buffer.update_data('obses' / 'amp_obs', n, ...)` of play_steps
+ *                        (amp_continuous_value.py:46,70; emloco_reset_done writes obs_copy only)
+ *   self_* / task_*      clamp((obs-mean)*inv_std, +-5) (utils/running_mean_std.py:82-84) split into bf16 hi/lo: the A operands
+ *                        of emloco_linear_bf16x3 for the actor/critic input (cols 0..367) and the task MLP (cols 368..1421)
+ *   amp_*                the same for the discriminator input [N,3090]
+ * inv_std = 1/sqrt(var + eps) as fp32.  Any group may be NULL.  The struct is copied; pointers must stay valid until replaced.
+ * Pitches (ld_*) in elements, multiples of 8; hi/lo base pointers 16-byte aligned. */
+typedef struct emloco_post_sinks {
+    float*    obs_copy;
+    float*    amp_copy;
+    const float* obs_mean; const float* obs_inv_std;
+    uint16_t* self_hi; uint16_t* self_lo; int64_t ld_self;
+    uint16_t* task_hi; uint16_t* task_lo; int64_t ld_task;
+    const float* amp_mean; const float* amp_inv_std;
+    uint16_t* amp_hi; uint16_t* amp_lo; int64_t ld_amp;
+} emloco_post_sinks;
+int emloco_set_post_sinks(emloco_sim* sim, const emloco_post_sinks* sinks /* NULL clears */);
+
 /* post_physics_step (humanoid_amp.py:139-157 -> humanoid.py:1211-1232 -> humanoid_amp_task.py:62-86):
  * progress += advance_progress; obs, flip obs, reward, reset/terminate, AMP obs ring.  One fused kernel. */
 int emloco_post_step(emloco_sim* sim, int32_t advance_progress, void* stream);

@@ -162,3 +162,32 @@ def test_graphed_steps_equal_eager_steps():
             np.testing.assert_array_equal(oa[key].cpu().numpy(), ob[key].cpu().numpy(), err_msg=f"{key} rep {rep}")
     np.testing.assert_array_equal(A.sim.rb_state.cpu().numpy(), B.sim.rb_state.cpu().numpy())
     A.close(); B.close()
+
+
+def test_fused_sinks_equal_separate_copies_and_splits():
+    """Post-step sinks (experience rows + normalised bf16 operands written by the post-step / reset kernels) against the
+    unfused path (copy + split launches): same experience up to the 1-ulp difference between x*inv_std and x/std."""
+    from emloco_b200.policy import AMPSeptValueNetwork, RunningMeanStd
+    from emloco_b200.rollout import Rollout
+    n = 160
+    torch.manual_seed(6)
+    net = AMPSeptValueNetwork()
+    rng = np.random.default_rng(0)
+
+    def norms():
+        on, an = RunningMeanStd(1422), RunningMeanStd(3090)
+        on.running_mean.copy_(torch.from_numpy(rng.normal(0, 0.3, 1422))); on.running_var.copy_(torch.from_numpy(rng.uniform(0.3, 2, 1422)))
+        an.running_mean.copy_(torch.from_numpy(rng.normal(0, 0.3, 3090))); an.running_var.copy_(torch.from_numpy(rng.uniform(0.3, 2, 3090)))
+        return on, an
+    rng = np.random.default_rng(0); on_a, an_a = norms()
+    rng = np.random.default_rng(0); on_b, an_b = norms()
+    A = Rollout(n, seed=3, net=net, tensor_cores=True, horizon=6, fuse_sinks=True, obs_norm=on_a, amp_norm=an_a)
+    B = Rollout(n, seed=3, net=net, tensor_cores=True, horizon=6, fuse_sinks=False, obs_norm=on_b, amp_norm=an_b)
+    for rep in range(2):
+        oa, ob = A.play_steps(), B.play_steps()
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(oa["obses"].cpu().numpy(), ob["obses"].cpu().numpy())
+        np.testing.assert_array_equal(oa["amp_obs"].cpu().numpy(), ob["amp_obs"].cpu().numpy()) if rep == 0 else None
+        for key in ("mus", "values", "next_values", "amp_rewards", "returns"):
+            np.testing.assert_allclose(oa[key].cpu().numpy(), ob[key].cpu().numpy(), rtol=1e-3, atol=1e-3, err_msg=f"{key} rep {rep}")
+    A.close(); B.close()
