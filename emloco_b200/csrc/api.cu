@@ -395,7 +395,8 @@ int emloco_linear_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda
     if (y_hi && ((N & 31) || ldy16 < N || (ldy16 & 7) || (((uintptr_t)y_hi | (uintptr_t)y_lo) & 15)))
         return fail(EMLOCO_EINVAL, "emloco_linear_bf16x3: split output needs N % 32 == 0, pitch % 8 == 0, 16-byte aligned pointers");
     const int tile_n = (relu >> 8) & 0xfff;     // bits 8..19 of `relu`: 0 = automatic tile choice, 128 / 256 = forced (tests, tuning)
-    if (tile_n != 0 && tile_n != 128 && tile_n != 256) return fail(EMLOCO_EINVAL, "emloco_linear_bf16x3: tile must be 0, 128 or 256");
+    if (tile_n != 0 && (tile_n & 0x7ff) != 128 && (tile_n & 0x7ff) != 256)
+        return fail(EMLOCO_EINVAL, "emloco_linear_bf16x3: tile must be 0, 128 or 256 (+0x800 for the CTA-pair kernels)");
     CK(eml_linear_bf16x3(a_hi, a_lo, lda, w_hi, w_lo, ldw, d_bias, M, N, K, relu & 1, d_y32, ldy, y_hi, y_lo, ldy16, tile_n,
                          (cudaStream_t)stream), "linear bf16x3 (tcgen05)");
     return EMLOCO_OK;

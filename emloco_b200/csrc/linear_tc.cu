@@ -303,6 +303,202 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_co
     }
 }
 
+// =====================================================================================================================
+// CTA-PAIR variant (cta_group::2): two CTAs of a cluster on the two SMs of a TPC compute one 256 x BN tile.  Each CTA stages
+// its own 128 rows of A and HALF of the W tile (BN/2 rows); the leader's single thread issues M = 256 MMAs that read A from
+// both SMs and W halves from both SMs.  Per SM this halves the W bytes that come through L2 and shared memory - the resource
+// that bounds the bf16x3 kernel (three MMAs read six operand tiles per k-step) - so the tensor pipe can run near its peak.
+//   barriers: full[s]   leader's, 2 arrivals (both producers) + the bytes of both CTAs' TMA loads
+//             empty[s]  one per CTA, released by a multicast tcgen05.commit
+//             tfull[a]  one per CTA (multicast commit), tempty[a] leader's, 2 x 256 epilogue threads
+// =====================================================================================================================
+template <int BN> struct Tile2 {
+    static constexpr int BK = 64;
+    static constexpr int BH = BN / 2;                      // W rows staged by each CTA
+    static constexpr int STAGES = BN == 256 ? 3 : 4;
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BH * BK * 2;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 64 KB (BN 256) / 48 KB (BN 128)
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int BIAS_BYTES = 2 * BN * 4;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + BIAS_BYTES;
+    static constexpr int TMEM_COLS = 2 * BN;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t num_clusters_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {     // acquire at cluster scope
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAITC_LOOP:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAITC_DONE;\n\t"
+        "bra WAITC_LOOP;\n\t"
+        "WAITC_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {      // arrives on `bar` in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+linear_bf16x3_2cta_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+                          const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl, GemmArgs g) {
+    using T = Tile2<BN>;
+    constexpr int BK = T::BK;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + T::STAGES * T::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (T::STAGES + s); };
+    auto tfull_bar = [&](int a) { return bars + 8u * (2 * T::STAGES + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (2 * T::STAGES + 2 + a); };
+    const uint32_t tmem_slot = bars + 8u * (2 * T::STAGES + 4);
+    uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
+    float* s_bias = reinterpret_cast<float*>(smem_gen + T::STAGES * T::STAGE_BYTES + T::BAR_BYTES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int tiles_m = (g.M + 2 * BM - 1) / (2 * BM), tiles_n = (g.N + BN - 1) / BN;
+    const int num_tiles = tiles_m * tiles_n;
+    const int num_kb = (g.K + BK - 1) / BK;
+    const int first_tile = (int)cluster_id_x(), tile_step = (int)num_clusters_x();
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ah));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_al));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wh));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wl));
+        for (int s = 0; s < T::STAGES; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * 32 * NUM_EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    } else if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(T::TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tc_fence_before();
+    cluster_sync_all();                                   // barriers of both CTAs initialised before any remote arrive / TMA
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== TMA producer (both CTAs) =====================
+            int stage = 0; uint32_t phase = 0;
+            for (int t = first_tile; t < num_tiles; t += tile_step) {
+                const int m0 = (t % tiles_m) * 2 * BM + (int)rank * BM, n0 = (t / tiles_m) * BN + (int)rank * T::BH;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait_cluster(empty_bar(stage), phase ^ 1);
+                    const uint32_t sa = base + stage * T::STAGE_BYTES;
+                    const uint32_t lfull = mapa_u32(full_bar(stage), 0);             // the LEADER's full barrier
+                    if (leader) mbar_expect_tx(full_bar(stage), 2 * T::STAGE_BYTES); // bytes of both CTAs land on it
+                    else mbar_arrive_cluster(lfull);
+                    tma_load_2d_2sm(sa, &map_ah, lfull, kb * BK, m0);
+                    tma_load_2d_2sm(sa + T::A_BYTES, &map_al, lfull, kb * BK, m0);
+                    tma_load_2d_2sm(sa + 2 * T::A_BYTES, &map_wh, lfull, kb * BK, n0);
+                    tma_load_2d_2sm(sa + 2 * T::A_BYTES + T::B_BYTES, &map_wl, lfull, kb * BK, n0);
+                    if (++stage == T::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            // ===================== MMA issuer (leader CTA only): M = 256 across the pair =====================
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int t = first_tile; t < num_tiles; t += tile_step) {
+                mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1);          // both CTAs' epilogues have drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait_cluster(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = base + stage * T::STAGE_BYTES;
+                    const uint64_t d_ah = make_smem_desc<128>(sa), d_al = make_smem_desc<128>(sa + T::A_BYTES);
+                    const uint64_t d_wh = make_smem_desc<128>(sa + 2 * T::A_BYTES);
+                    const uint64_t d_wl = make_smem_desc<128>(sa + 2 * T::A_BYTES + T::B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t ko = (uint64_t)((k * UMMA_K * 2) >> 4);
+                        umma_bf16_2sm(d_tmem, d_al + ko, d_wh + ko, idesc, (kb | k) != 0);
+                        umma_bf16_2sm(d_tmem, d_ah + ko, d_wl + ko, idesc, 1);
+                        umma_bf16_2sm(d_tmem, d_ah + ko, d_wh + ko, idesc, 1);
+                    }
+                    umma_commit_2sm(empty_bar(stage));                      // frees the stage in BOTH CTAs
+                    if (++stage == T::STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_2sm(tfull_bar(acc));                            // accumulators complete in both CTAs
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue (both CTAs; each drains its own 128 rows) =====================
+        const int quad = warp & 3, half = (warp - 2) >> 2;
+        const int et = threadIdx.x - 64;
+        constexpr int NC = BN / 64;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int t = first_tile; t < num_tiles; t += tile_step) {
+            const int m0 = (t % tiles_m) * 2 * BM + (int)rank * BM, n0 = (t / tiles_m) * BN;
+            if (et < BN) s_bias[acc * BN + et] = (g.bias && n0 + et < g.N) ? __ldg(g.bias + n0 + et) : 0.f;
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");
+            mbar_wait_cluster(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const int row = m0 + quad * 32 + lane;
+            const bool row_ok = row < g.M;
+            const int c0 = half * (BN / 2);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c0;
+            const float* sb = s_bias + acc * BN + c0;
+            uint32_t ra[32], rb[32];
+            tmem_ld32(taddr, ra);
+            tmem_ld_wait(ra);
+#pragma unroll
+            for (int c = 0; c < NC; c += 2) {
+                tmem_ld32(taddr + (c + 1) * 32, rb);
+                epilogue_chunk(ra, sb + c * 32, n0 + c0 + c * 32, row, row_ok, g);
+                tmem_ld_wait(rb);
+                if (c + 2 < NC) tmem_ld32(taddr + (c + 2) * 32, ra);
+                epilogue_chunk(rb, sb + (c + 1) * 32, n0 + c0 + (c + 1) * 32, row, row_ok, g);
+                if (c + 2 < NC) tmem_ld_wait(ra);
+            }
+            tc_fence_before();
+            mbar_arrive_cluster(mapa_u32(tempty_bar(acc), 0));              // 512 arrivals on the leader's barrier
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();                                   // nobody leaves while the pair's MMAs / remote arrives may be in flight
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(T::TMEM_COLS));
+    }
+}
+
 // ---- fp32 -> (optional running-mean-std normalisation, utils/running_mean_std.py:82-84) -> bf16 hi/lo split ----
 // Only columns [0,K) are written: the TMA tensor maps carry the exact K, so pad columns of the pitch are never read.
 __global__ void split_bf16_kernel(const float* __restrict__ x, long long ldx, long long M, int K, const float* __restrict__ mean,
@@ -389,6 +585,32 @@ static cudaError_t launch(const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, 
     return cudaGetLastError();
 }
 
+template <int BN>
+static cudaError_t launch_2cta(const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, long long lda, const __nv_bfloat16* w_hi,
+                               const __nv_bfloat16* w_lo, long long ldw, const GemmArgs& g, cudaStream_t st) {
+    using T = Tile2<BN>;
+    CUtensorMap mah, mal, mwh, mwl;
+    if (!make_map(&mah, a_hi, g.M, g.K, lda, BM, T::BK) || !make_map(&mal, a_lo, g.M, g.K, lda, BM, T::BK) ||
+        !make_map(&mwh, w_hi, g.N, g.K, ldw, T::BH, T::BK) || !make_map(&mwl, w_lo, g.N, g.K, ldw, T::BH, T::BK))
+        return cudaErrorInvalidValue;
+    auto kern = linear_bf16x3_2cta_kernel<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    if (!g_num_sms) {
+        int dev = 0; cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int tiles = ((g.M + 2 * BM - 1) / (2 * BM)) * ((g.N + BN - 1) / BN);
+    const int pairs = g_num_sms / 2;
+    const int clusters = tiles < pairs ? tiles : pairs;
+    kern<<<2 * clusters, NUM_THREADS, T::SMEM, st>>>(mah, mal, mwh, mwl, g);
+    return cudaGetLastError();
+}
+
 }  // namespace tc
 
 cudaError_t eml_split_bf16(const float* x, long long ldx, long long M, int K, const float* mean, const float* var, float eps,
@@ -411,6 +633,13 @@ cudaError_t eml_linear_bf16x3(const void* a_hi, const void* a_lo, long long lda,
     int sms = tc::g_num_sms;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); tc::g_num_sms = sms; }
     const long long tiles256 = ((M + tc::BM - 1) / tc::BM) * ((N + 255) / 256);
+    if (tile_n & 0x800) {                                   // CTA-pair kernels: 256 x 256 or 256 x 128 per pair
+        if ((tile_n & 0x7ff) == 256)
+            return tc::launch_2cta<256>((const __nv_bfloat16*)a_hi, (const __nv_bfloat16*)a_lo, lda, (const __nv_bfloat16*)w_hi,
+                                        (const __nv_bfloat16*)w_lo, ldw, g, st);
+        return tc::launch_2cta<128>((const __nv_bfloat16*)a_hi, (const __nv_bfloat16*)a_lo, lda, (const __nv_bfloat16*)w_hi,
+                                    (const __nv_bfloat16*)w_lo, ldw, g, st);
+    }
     const bool wide = tile_n == 256 || (tile_n == 0 && N >= 256 && tiles256 * 8 >= (long long)sms * 7);
     if (wide)
         return tc::launch<256>((const __nv_bfloat16*)a_hi, (const __nv_bfloat16*)a_lo, lda, (const __nv_bfloat16*)w_hi,

@@ -245,7 +245,8 @@ int emloco_rollout_record(const emloco_rollout_cfg* cfg, const float* d_rew, con
  * emloco_linear_bf16x3: y = act(A W^T + b) with A = a_hi+a_lo [M,K] (pitch lda), W = w_hi+w_lo [N,K] (pitch ldw);
  * writes fp32 y32 [M,N] (pitch ldy) and/or the split of y as the next layer's operand y_hi/y_lo (pitch ldy16, N % 32 == 0).
  * All bf16 base pointers 16-byte aligned, pitches multiples of 8 elements.  `relu`: bit 0 = ReLU; bits 8..19 optionally force
- * the N-extent of the output tile (128 or 256; 0 = chosen from the shape) - used by the tests and for tuning. */
+ * the N-extent of the output tile (128 or 256; 0 = chosen from the shape; +0x800 = the CTA-pair kernels, 256 rows per
+ * pair) - used by the tests and for tuning. */
 int emloco_split_bf16(const float* d_x, int64_t ldx, int64_t M, int32_t K, const float* d_mean, const float* d_var, float eps,
                       uint16_t* d_hi, uint16_t* d_lo, int64_t ld16, void* stream);
 int emloco_linear_bf16x3(const uint16_t* d_a_hi, const uint16_t* d_a_lo, int64_t lda, const uint16_t* d_w_hi,

@@ -231,7 +231,7 @@ def test_linear_bf16x3_tensor_core_matches_fp64(M, N, K, relu):
     np.testing.assert_allclose(y.cpu().numpy(), ref, rtol=1e-3, atol=1e-4)
 
 
-@pytest.mark.parametrize("tile", [128, 256])
+@pytest.mark.parametrize("tile", [128, 256, 0x800 + 128, 0x800 + 256])
 def test_linear_bf16x3_split_output_chains_layers(tile):
     """Two chained layers through the split (hi/lo) epilogue output, with input normalisation, against float64;
     both output-tile shapes (128 x 128 x 64 / 128B swizzle and 128 x 256 x 32 / 64B swizzle)."""
@@ -257,8 +257,8 @@ def test_linear_bf16x3_split_output_chains_layers(tile):
     np.testing.assert_allclose(rec, xn, rtol=2e-5, atol=1e-6)
 
 
-@pytest.mark.parametrize("tile", [128, 256])
-@pytest.mark.parametrize("M,N,K", [(128, 69, 100), (4096, 1024, 2048), (130, 257, 33), (1000, 4096, 624)])
+@pytest.mark.parametrize("tile", [128, 256, 0x800 + 128, 0x800 + 256])      # +0x800: CTA-pair (cta_group::2) kernels
+@pytest.mark.parametrize("M,N,K", [(128, 69, 100), (4096, 1024, 2048), (130, 257, 33), (1000, 4096, 624), (300, 512, 1054)])
 def test_linear_bf16x3_tiles_and_ragged_shapes(tile, M, N, K):
     """Forced tile shapes on ragged M / N / K (TMA zero fill of the out-of-range rows and of the K tail), fp32 output."""
     from emloco_b200.policy import _Split, linear_bf16x3, split_bf16
