@@ -160,7 +160,8 @@ def run_ours(args):
     from emloco_b200.value_pose_net import ValuePoseNet
 
     N, K, W = args.envs, args.steps, args.warmup
-    R = Rollout(N, device=local_rank, seed=args.seed + rank, tensor_cores=args.tensor_cores, recompute_disc=not args.dedup_disc)
+    R = Rollout(N, device=local_rank, seed=args.seed + rank, tensor_cores=args.tensor_cores, recompute_disc=not args.dedup_disc,
+                concurrent=not args.serial)
     pk = peaks()
 
     def barrier():
@@ -275,7 +276,7 @@ def run_ours(args):
         lv_rate = B / (lv_ms * 1e-3)
 
         # ---- rooflines from the live segment timings ----
-        nets_ms = seg["policy"] + seg["critic"] + seg["disc"]
+        nets_ms = seg["policy"] + (seg["critic+disc+locoval"] if "critic+disc+locoval" in seg else seg["critic"] + seg["disc"])
         kern = {
             "physics": {"bound": "hbm", "ms": seg["physics"], "achieved": N * BYTES_PHYSICS / (seg["physics"] * 1e-3) / 1e9,
                         "peak": pk["hbm"], "unit": "GB/s"},
@@ -305,7 +306,7 @@ def run_ours(args):
             "config": {"workload": f"{N} SMPL-humanoid envs per GPU, PACER AMP rollout step + LocoVal scoring (configs[1])",
                        "horizon": HORIZON, "l2": "per-step working set (obs 23 MB + AMP obs 2x51 MB + experience rows + 45 MB weights) exceeds the 126 MB L2; experience rows rotate over 32 slots",
                        "post_horizon_disc_pass": "recomputed" if not args.dedup_disc else "reused per-step logits",
-                       "tensor_cores": bool(args.tensor_cores), "cuda_graphs": graphs},
+                       "tensor_cores": bool(args.tensor_cores), "cuda_graphs": graphs, "parallel_branches": not args.serial},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
             "roofline": roof, "kernels": kern, "segments_ms": seg,
@@ -332,6 +333,7 @@ def main():
     ap.add_argument("--dedup-disc", action="store_true", default=False)
     ap.add_argument("--locoval-batch", type=int, default=1 << 20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--serial", action="store_true", help="no parallel graph branches (critic / discriminator / LocoVal / heads)")
     ap.add_argument("--eager", action="store_true", help="launch every kernel from the host instead of replaying CUDA graphs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -84,11 +84,33 @@ class AMPSeptValueNetwork(nn.Module):
         nn.init.zeros_(self._value_logits.bias)
 
 
+class Fork:
+    """Runs independent launch groups on side streams and joins them: parallel branches of the CUDA graph under capture,
+    plain stream concurrency otherwise.  Small layers (heads, task-value MLP, LocoVal) occupy a fraction of the 148 SMs;
+    branches let them overlap instead of serialising."""
+
+    def __init__(self, device, n=3):
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(n)]
+
+    def run(self, *fns):
+        cur = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        side = self.streams[:len(fns) - 1]
+        for st, fn in zip(side, fns[1:]):
+            st.wait_event(ev)
+            with torch.cuda.stream(st):
+                fn()
+        fns[0]()
+        for st in side:
+            cur.wait_stream(st)
+
+
 class RolloutNets:
     """Evaluates the networks for a fixed row count with preallocated workspaces (CUDA-graph friendly)."""
 
     def __init__(self, net: AMPSeptValueNetwork, obs_norm: RunningMeanStd, amp_norm: RunningMeanStd, rows: int,
-                 tensor_cores: bool = False):
+                 tensor_cores: bool = False, concurrent: bool = False):
         self.net, self.obs_norm, self.amp_norm, self.M, self.tc = net, obs_norm, amp_norm, int(rows), bool(tensor_cores)
         dev = net.mu.weight.device
         if dev.type != "cuda":
@@ -107,6 +129,7 @@ class RolloutNets:
         self.d1, self.d2, self.logit = f(M, d1), f(M, d2), f(M, 1)
         self.actions, self.neglogp = f(M, ACTIONS), f(M)
         self._stacked = None
+        self.fork = Fork(dev) if concurrent else None
         if self.tc:
             S = lambda k: _Split(M, k, dev)
             self.s_tin, self.s_t1, self.s_ain, self.s_ac1 = S(TASK_OBS), S(t1), S(SELF_OBS + t2), S(2 * a1)
@@ -169,28 +192,46 @@ class RolloutNets:
         task_value_out = self.task_value if task_value_out is None else task_value_out
         actions_out = self.actions if actions_out is None else actions_out
         neglogp_out = self.neglogp if neglogp_out is None else neglogp_out
-        mean, var = self._trunk(obs, operands_ready)
+        mean, var = self.obs_norm.f32()
         w, b = self._w_ac1()
         h = n.actor_mlp[0].out_features
-        if self.tc:
-            W = self.w16.get
-            linear_bf16x3(self.s_ain, W("ac1", w), b, True, y16=self.s_ac1)
-            linear_bf16x3(self.s_ac1.cols(0, h), W("a2", n.actor_mlp[2].weight), n.actor_mlp[2].bias.detach(), True, y16=self.s_a2)
-            linear_bf16x3(self.s_ac1.cols(h, 2 * h), W("c2", n.critic_mlp[2].weight), n.critic_mlp[2].bias.detach(), True, y16=self.s_c2)
-            linear_bf16x3(self.s_a2, W("mu", n.mu.weight), n.mu.bias.detach(), False, y32=mu_out)
-            linear_bf16x3(self.s_c2, W("value", n.value.weight), n.value.bias.detach(), False, y32=self.value)
+        W = self.w16.get if self.tc else None
+
+        def trunk_ac1():
+            self._trunk(obs, operands_ready)
+            if self.tc:
+                linear_bf16x3(self.s_ain, W("ac1", w), b, True, y16=self.s_ac1)
+            else:
+                linear(self.ain, w, b, relu=True, out=self.ac1)
+
+        def actor():
+            if self.tc:
+                linear_bf16x3(self.s_ac1.cols(0, h), W("a2", n.actor_mlp[2].weight), n.actor_mlp[2].bias.detach(), True, y16=self.s_a2)
+                linear_bf16x3(self.s_a2, W("mu", n.mu.weight), n.mu.bias.detach(), False, y32=mu_out)
+            else:
+                self._lin(self.ac1[:, :h], n.actor_mlp[2], True, self.a2)
+                self._lin(self.a2, n.mu, False, mu_out)
+            sample_actions(mu_out, n.sigma, noise, actions_out, neglogp_out)
+
+        def critic():
+            if self.tc:
+                linear_bf16x3(self.s_ac1.cols(h, 2 * h), W("c2", n.critic_mlp[2].weight), n.critic_mlp[2].bias.detach(), True, y16=self.s_c2)
+                linear_bf16x3(self.s_c2, W("value", n.value.weight), n.value.bias.detach(), False, y32=self.value)
+            else:
+                self._lin(self.ac1[:, h:], n.critic_mlp[2], True, self.c2)
+                self._lin(self.c2, n.value, False, self.value)
+
+        def task_value():   # eval_task_value (amp_network_sept_value_builder.py:31-46): the 30 normalised trajectory features
+            self._lin(obs[:, SELF_OBS:SELF_OBS + TRAJ_OBS], n._task_value_mlp[0], True, self.v1,
+                      mean[SELF_OBS:SELF_OBS + TRAJ_OBS], var[SELF_OBS:SELF_OBS + TRAJ_OBS])
+            self._lin(self.v1, n._task_value_mlp[2], True, self.v2)
+            self._lin(self.v2, n._value_logits, False, task_value_out)
+
+        if self.fork is not None:
+            trunk_ac1()
+            self.fork.run(actor, critic, task_value)
         else:
-            linear(self.ain, w, b, relu=True, out=self.ac1)
-            self._lin(self.ac1[:, :h], n.actor_mlp[2], True, self.a2)
-            self._lin(self.ac1[:, h:], n.critic_mlp[2], True, self.c2)
-            self._lin(self.a2, n.mu, False, mu_out)
-            self._lin(self.c2, n.value, False, self.value)
-        # eval_task_value (amp_network_sept_value_builder.py:31-46): the 30 normalised trajectory features
-        self._lin(obs[:, SELF_OBS:SELF_OBS + TRAJ_OBS], n._task_value_mlp[0], True, self.v1,
-                  mean[SELF_OBS:SELF_OBS + TRAJ_OBS], var[SELF_OBS:SELF_OBS + TRAJ_OBS])
-        self._lin(self.v1, n._task_value_mlp[2], True, self.v2)
-        self._lin(self.v2, n._value_logits, False, task_value_out)
-        sample_actions(mu_out, n.sigma, noise, actions_out, neglogp_out)
+            trunk_ac1(); actor(); critic(); task_value()
         return dict(mus=mu_out, sigmas=n.sigma, values=self.value, task_values=task_value_out, actions=actions_out,
                     neglogpacs=neglogp_out)
 

@@ -32,7 +32,7 @@ class Rollout:
     def __init__(self, num_envs, device=0, horizon=32, seed=0, tensor_cores=False, gamma=0.99, tau=0.95,
                  task_reward_w=0.5, disc_reward_w=0.5, disc_reward_scale=2.0, inversion_penalty_scale=0.3,
                  step_to_pred=144, normalize_value=True, net=None, obs_norm=None, amp_norm=None, value_norm=None,
-                 recompute_disc=True, valuenet=None, fuse_sinks=True):
+                 recompute_disc=True, valuenet=None, fuse_sinks=True, concurrent=True):
         self.N, self.T, self.device = int(num_envs), int(horizon), int(device)
         self.gamma, self.tau = gamma, tau
         self.task_reward_w, self.disc_reward_w, self.disc_reward_scale = task_reward_w, disc_reward_w, disc_reward_scale
@@ -47,7 +47,8 @@ class Rollout:
         self.obs_norm = (obs_norm or RunningMeanStd(OBS)).to(dev)
         self.amp_norm = (amp_norm or RunningMeanStd(AMP_OBS)).to(dev)
         self.value_norm = (value_norm or RunningMeanStd(1)).to(dev)
-        self.nets = RolloutNets(self.net, self.obs_norm, self.amp_norm, self.N, tensor_cores=tensor_cores)
+        self.nets = RolloutNets(self.net, self.obs_norm, self.amp_norm, self.N, tensor_cores=tensor_cores, concurrent=concurrent)
+        self.concurrent = bool(concurrent)
         self.gen = torch.Generator(device=dev).manual_seed(seed + 1)
 
         # synthetic initial state + JTA-shaped trajectories; rank-local seed like run.py:65
@@ -96,7 +97,11 @@ class Rollout:
         self.rcfg.value_mean = float(self.value_norm.running_mean.float().item())
         self.rcfg.value_std = float(torch.sqrt(self.value_norm.running_var.float() + self.value_norm.epsilon).item())
 
-    SEGMENTS = ("reset", "policy", "physics", "post_step", "critic", "disc", "record")
+    @property
+    def SEGMENTS(self):
+        if self.concurrent:
+            return ("reset", "policy", "physics", "post_step", "critic+disc+locoval", "record")
+        return ("reset", "policy", "physics", "post_step", "critic", "disc", "record")
 
     def enable_segment_timing(self, on=True):
         """Record a CUDA event on the launching stream at every segment boundary of step(); read with segment_ms()."""
@@ -167,10 +172,16 @@ class Rollout:
                 _ptr(cur["nv"]), _ptr(cur["logit"]), None, _ptr(mb["values"][n]), _ptr(mb["rewards"][n]), _ptr(mb["dones"][n]),
                 _ptr(mb["next_values"][n]), _ptr(mb["amp_rewards"][n]), _ptr(self.state), self.N, _stream()),
                 "emloco_rollout_record")
-            # LocoVal scoring of every env's (waypoints, initial pose, initial velocity) - valuenet(...) of :123-127
+
+        def seg_locoval():
             self.locoval_scores = self.valuenet(self.waypoint_traj, self.init_pose, self.init_vel)
 
-        return [seg_reset, seg_policy, seg_physics, seg_post, seg_critic, seg_disc, seg_record]
+        def seg_nets2():   # critic(next obs), discriminator and LocoVal scoring are independent: three graph branches
+            nets.fork.run(seg_critic, seg_disc, seg_locoval)
+
+        if self.concurrent:
+            return [seg_reset, seg_policy, seg_physics, seg_post, seg_nets2, seg_record]
+        return [seg_reset, seg_policy, seg_physics, seg_post, seg_critic, seg_disc, lambda: (seg_record(), seg_locoval())]
 
     def step(self, n, noise=None, host_obs=False):
         """host_obs: the caller overwrote sim.obs (host-provided observations): operands are re-derived from it."""
