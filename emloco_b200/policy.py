@@ -110,7 +110,7 @@ class RolloutNets:
     """Evaluates the networks for a fixed row count with preallocated workspaces (CUDA-graph friendly)."""
 
     def __init__(self, net: AMPSeptValueNetwork, obs_norm: RunningMeanStd, amp_norm: RunningMeanStd, rows: int,
-                 tensor_cores: bool = False, concurrent: bool = False):
+                 tensor_cores: bool = False, concurrent: bool = False, amp_slots: int = 1):
         self.net, self.obs_norm, self.amp_norm, self.M, self.tc = net, obs_norm, amp_norm, int(rows), bool(tensor_cores)
         dev = net.mu.weight.device
         if dev.type != "cuda":
@@ -133,7 +133,12 @@ class RolloutNets:
         if self.tc:
             S = lambda k: _Split(M, k, dev)
             self.s_tin, self.s_t1, self.s_ain, self.s_ac1 = S(TASK_OBS), S(t1), S(SELF_OBS + t2), S(2 * a1)
-            self.s_a2, self.s_c2, self.s_amp, self.s_d1, self.s_d2 = S(a2), S(a2), S(AMP_OBS), S(d1), S(d2)
+            self.s_a2, self.s_c2, self.s_d1, self.s_d2 = S(a2), S(a2), S(d1), S(d2)
+            # discriminator operands of every step of the horizon are kept (slot n = rows [n*M, (n+1)*M)), so the post-horizon
+            # discriminator pass of play_steps (:157) runs as ONE M*T-row GEMM chain without re-reading the fp32 AMP rows
+            self.amp_slots = int(amp_slots)
+            self.s_amp = _Split(M * self.amp_slots, AMP_OBS, dev)
+            self._all = None
             self.w16 = _TcWeights()
 
     def _w_ac1(self):
@@ -145,7 +150,7 @@ class RolloutNets:
                              torch.cat([ps[1].detach(), ps[3].detach()]).contiguous())
         return self._stacked[1], self._stacked[2]
 
-    def post_sinks(self, obs_copy=None, amp_copy=None):
+    def post_sinks(self, obs_copy=None, amp_copy=None, slot=0):
         """emloco_post_sinks pointing at this object's operand buffers (tensor-core path) plus the given experience rows."""
         k = _lib.PostSinks()
         k.obs_copy = None if obs_copy is None else obs_copy.data_ptr()
@@ -156,7 +161,8 @@ class RolloutNets:
             k.self_hi, k.self_lo, k.ld_self = self.s_ain.hi.data_ptr(), self.s_ain.lo.data_ptr(), self.s_ain.ld
             k.task_hi, k.task_lo, k.ld_task = self.s_tin.hi.data_ptr(), self.s_tin.lo.data_ptr(), self.s_tin.ld
             k.amp_mean, k.amp_inv_std = am.data_ptr(), self.amp_norm.inv_std().data_ptr()
-            k.amp_hi, k.amp_lo, k.ld_amp = self.s_amp.hi.data_ptr(), self.s_amp.lo.data_ptr(), self.s_amp.ld
+            sa = self.s_amp.rows_view(self.M, slot * self.M)
+            k.amp_hi, k.amp_lo, k.ld_amp = sa.hi.data_ptr(), sa.lo.data_ptr(), sa.ld
         return k
 
     def _lin(self, x, layer, relu, out, mean=None, var=None):
@@ -251,17 +257,30 @@ class RolloutNets:
         self._lin(self.c2, n.value, False, self.next_value)
         return self.next_value
 
-    def disc_logits(self, amp_obs, out=None, operands_ready=False):
-        """_eval_disc (amp_continuous.py:666-668): normalise -> 3090->1024->512->1.  amp_obs [M',3090], M' <= M."""
+    def disc_logits_all(self, out):
+        """The discriminator over the operands of ALL slots at once (rows = M * amp_slots): out [M*amp_slots, 1]."""
+        n, W, rows = self.net, self.w16.get, self.M * self.amp_slots
+        if self._all is None:
+            self._all = (_Split(rows, n._disc_mlp[0].out_features, out.device), _Split(rows, n._disc_mlp[2].out_features, out.device))
+        d1, d2 = self._all
+        linear_bf16x3(self.s_amp, W("d0", n._disc_mlp[0].weight), n._disc_mlp[0].bias.detach(), True, y16=d1)
+        linear_bf16x3(d1, W("d2", n._disc_mlp[2].weight), n._disc_mlp[2].bias.detach(), True, y16=d2)
+        linear_bf16x3(d2, W("dl", n._disc_logits.weight), n._disc_logits.bias.detach(), False, y32=out)
+        return out
+
+    def disc_logits(self, amp_obs, out=None, operands_ready=False, slot=0):
+        """_eval_disc (amp_continuous.py:666-668): normalise -> 3090->1024->512->1.  amp_obs [M',3090], M' <= M.
+        slot: which block of the stored discriminator operands this call's rows occupy."""
         n = self.net
         m = amp_obs.shape[0]
         mean, var = self.amp_norm.f32()
         out = self.logit[:m] if out is None else out
         if self.tc:
             W = self.w16.get
+            s_amp = self.s_amp.rows_view(m, slot * self.M)
             if not operands_ready:
-                split_bf16(amp_obs, self.s_amp.rows_view(m), mean, var, self.amp_norm.epsilon)
-            linear_bf16x3(self.s_amp.rows_view(m), W("d0", n._disc_mlp[0].weight), n._disc_mlp[0].bias.detach(), True,
+                split_bf16(amp_obs, s_amp, mean, var, self.amp_norm.epsilon)
+            linear_bf16x3(s_amp, W("d0", n._disc_mlp[0].weight), n._disc_mlp[0].bias.detach(), True,
                           y16=self.s_d1.rows_view(m))
             linear_bf16x3(self.s_d1.rows_view(m), W("d2", n._disc_mlp[2].weight), n._disc_mlp[2].bias.detach(), True,
                           y16=self.s_d2.rows_view(m))
@@ -291,9 +310,9 @@ class _Split:
         v.rows, v.K, v.ld, v.hi, v.lo = self.rows, b - a, self.ld, self.hi[:, a:b], self.lo[:, a:b]
         return v
 
-    def rows_view(self, m):
+    def rows_view(self, m, start=0):
         v = _Split.__new__(_Split)
-        v.rows, v.K, v.ld, v.hi, v.lo = m, self.K, self.ld, self.hi[:m], self.lo[:m]
+        v.rows, v.K, v.ld, v.hi, v.lo = m, self.K, self.ld, self.hi[start:start + m], self.lo[start:start + m]
         return v
 
 

@@ -47,7 +47,8 @@ class Rollout:
         self.obs_norm = (obs_norm or RunningMeanStd(OBS)).to(dev)
         self.amp_norm = (amp_norm or RunningMeanStd(AMP_OBS)).to(dev)
         self.value_norm = (value_norm or RunningMeanStd(1)).to(dev)
-        self.nets = RolloutNets(self.net, self.obs_norm, self.amp_norm, self.N, tensor_cores=tensor_cores, concurrent=concurrent)
+        self.nets = RolloutNets(self.net, self.obs_norm, self.amp_norm, self.N, tensor_cores=tensor_cores, concurrent=concurrent,
+                                amp_slots=self.T if (tensor_cores and recompute_disc) else 1)
         self.concurrent = bool(concurrent)
         self.gen = torch.Generator(device=dev).manual_seed(seed + 1)
 
@@ -130,6 +131,7 @@ class Rollout:
 
         fuse = self.fuse and not host_obs
         nxt = n + 1                                                                    # row T is the spare row
+        slot = n if getattr(nets, "amp_slots", 1) > 1 else 0                           # block of the stored discriminator operands
 
         def seg_reset():                                                               # env_reset(done_indices), :45-46
             if fuse:
@@ -153,7 +155,7 @@ class Rollout:
 
         def seg_post():                                                                #           post_physics_step
             if fuse:
-                sim.set_post_sinks(nets.post_sinks(obs_copy=mb["obses"][nxt], amp_copy=mb["amp_obs"][n]))
+                sim.set_post_sinks(nets.post_sinks(obs_copy=mb["obses"][nxt], amp_copy=mb["amp_obs"][n], slot=slot))
                 sim.post_step(True)
             else:
                 sim.post_step(True)
@@ -163,7 +165,7 @@ class Rollout:
             cur["nv"] = nets.critic(sim.obs, operands_ready=fuse)
 
         def seg_disc():                                                                # _calc_amp_rewards, :93
-            cur["logit"] = nets.disc_logits(sim.amp_obs.view(self.N, AMP_OBS), operands_ready=fuse)
+            cur["logit"] = nets.disc_logits(sim.amp_obs.view(self.N, AMP_OBS), operands_ready=fuse, slot=slot)
 
         def seg_record():
             # values are un-normalised (get_action_values, normalize_value) together with next_values in the record kernel
@@ -194,8 +196,12 @@ class Rollout:
     def finish(self):
         mb, T, N = self.mb, self.T, self.N
         if self.recompute_disc:
-            for t in range(T):        # [T*N,3090] in N-row chunks through the same workspace
-                self.nets.disc_logits(mb["amp_obs"][t], out=self._logits_TN()[t])
+            if getattr(self.nets, "amp_slots", 1) == T:
+                # the normalised operands of all T steps are still in place: one [T*N]-row GEMM chain
+                self.nets.disc_logits_all(self._logits_TN().view(T * N, 1))
+            else:
+                for t in range(T):    # [T*N,3090] in N-row chunks through the same workspace
+                    self.nets.disc_logits(mb["amp_obs"][t], out=self._logits_TN()[t])
             lg = self._logits_TN()
             _lib.check(_lib.load().emloco_disc_reward(_ptr(lg), _ptr(mb["rewards"]), _ptr(mb["amp_rewards"]), _ptr(self._comb()),
                                                       T * N, self.disc_reward_scale, self.task_reward_w, self.disc_reward_w,
