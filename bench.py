@@ -91,7 +91,8 @@ class ClockSampler:
 
 
 def dist_env():
-    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    from emloco_b200.dist import env_rank
+    return env_rank()
 
 
 # =====================================================================================================
@@ -147,26 +148,24 @@ def run_reference(args):
 # =====================================================================================================
 def run_ours(args):
     import torch
-    import torch.distributed as dist
     rank, local_rank, world = dist_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from emloco_b200 import dist as D
+    D.init("nccl")
     from emloco_b200 import _lib
     from emloco_b200.rollout import Rollout
     from emloco_b200.synthetic import synthetic_locoval_batch
     from emloco_b200.value_pose_net import ValuePoseNet
 
     N, K, W = args.envs, args.steps, args.warmup
-    R = Rollout(N, device=local_rank, seed=args.seed + rank, tensor_cores=args.tensor_cores, recompute_disc=not args.dedup_disc,
+    R = Rollout(N, device=local_rank, seed=D.rank_seed(args.seed, rank), tensor_cores=args.tensor_cores, recompute_disc=not args.dedup_disc,
                 concurrent=not args.serial)
     pk = peaks()
 
     def barrier():
-        if world > 1:
-            dist.barrier()
+        D.barrier()
         torch.cuda.synchronize()
 
     step_i = [0]
@@ -211,10 +210,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     seg, _ = R.segment_ms()
     R.enable_segment_timing(False)
-    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms = D.max_over_ranks(ms, device="cuda")           # slowest rank
     value = world * N * K / (ms * 1e-3)
 
     # ---- end to end: the vec-env / agent boundary with HOST buffers (rl_device = cpu): every step copies the step's
@@ -248,10 +244,7 @@ def run_ours(args):
         e2e_step(i)
     e1.record()
     barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * N * Ke / (float(t.item()) * 1e-3)
+    e2e_value = world * N * Ke / (D.max_over_ranks(e0.elapsed_time(e1), device="cuda") * 1e-3)
     h2d = h_obs.numel() * 4 + h_noise.numel() * 4
     d2h = sum(v.numel() * v.element_size() for v in h_out.values())
 
@@ -315,9 +308,7 @@ def run_ours(args):
         }
         print(json.dumps(out), flush=True)
     R.close()
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    D.finalize()
 
 
 def main():

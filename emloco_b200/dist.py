@@ -1,0 +1,74 @@
+"""Data parallelism of the rollout: one process per GPU, envs are rank-local, no data-path collective.
+
+Reference: Horovod through rl_games (`pacer/pacer/run.py:57-72`: `rank = hvd.rank()`, seed += rank; rl_games `self.hvd`
+in `learning/common_agent.py:165-180,308-328`).  Environments never exchange state (own collision group, no inter-env
+observations), so the only collectives of the hot path are the bookkeeping ones below; the gradient all-reduce of the
+reference lives in the optimiser step, outside this path.  Backend "nccl" on GPUs, "gloo" in the CPU tests.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def env_rank():
+    """(rank, local_rank, world_size) from the torchrun environment; (0, 0, 1) when launched plainly."""
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def init(backend=None):
+    rank, local_rank, world = env_rank()
+    if world > 1 and not dist.is_initialized():
+        backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+        kw = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            kw["device_id"] = torch.device("cuda", local_rank)
+        dist.init_process_group(backend, **kw)
+    return rank, local_rank, world
+
+
+def rank_seed(seed, rank):
+    """run.py:65: every rank simulates its own envs with its own random stream."""
+    return int(seed) + int(rank)
+
+
+def shard_envs(total_envs, rank, world):
+    """[lo, hi) of the envs owned by `rank` when a global env count is split (weak scaling keeps envs per rank fixed)."""
+    per, rem = divmod(int(total_envs), int(world))
+    lo = rank * per + min(rank, rem)
+    return lo, lo + per + (1 if rank < rem else 0)
+
+
+def barrier():
+    if dist.is_initialized():
+        dist.barrier()
+
+
+def max_over_ranks(value, device="cpu"):
+    """Slowest rank's time: the number every multi-GPU throughput is quoted on."""
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    if dist.is_initialized():
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value, device="cpu"):
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    if dist.is_initialized():
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def average_scalar(value, device="cpu"):
+    """hvd.average_value (common_agent.py:308-310,327-328): e.g. the KL divergence across ranks."""
+    _, _, world = env_rank()
+    return sum_over_ranks(value, device) / max(world if dist.is_initialized() else 1, 1)
+
+
+def finalize():
+    if dist.is_initialized():
+        dist.barrier()
+        dist.destroy_process_group()

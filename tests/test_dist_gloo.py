@@ -1,0 +1,54 @@
+"""CPU: the N>1 plumbing (world_size 2, gloo): rank seeds, env sharding, max-over-ranks timing, scalar averaging, and the
+bench's reference arm under a 2-rank launch (rank 0 prints one JSON line, the others exit 0 without work)."""
+import json
+import os
+import subprocess
+import sys
+
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    from emloco_b200 import dist as D
+    r, lr, w = D.init("gloo")
+    lo, hi = D.shard_envs(4097, r, w)
+    out = dict(rank=r, world=w, seed=D.rank_seed(7, r), shard=(lo, hi), tmax=D.max_over_ranks(10.0 + r),
+               tsum=D.sum_over_ranks(1.0 + r), kl=D.average_scalar(0.5 * (r + 1)))
+    D.finalize()
+    q.put(out)
+
+
+def test_two_rank_gloo_plumbing():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in ps), key=lambda d: d["rank"])
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [d["seed"] for d in res] == [7, 8]
+    assert res[0]["shard"] == (0, 2049) and res[1]["shard"] == (2049, 4097)      # disjoint, covering
+    assert all(d["tmax"] == 11.0 for d in res) and all(d["tsum"] == 3.0 for d in res)
+    assert all(abs(d["kl"] - 0.75) < 1e-12 for d in res)
+
+
+def test_bench_reference_arm_under_two_ranks():
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(31500 + os.getpid() % 2000), WORLD_SIZE="2", OMP_NUM_THREADS="2")
+    outs = []
+    for rank in (0, 1):
+        e = dict(env, RANK=str(rank), LOCAL_RANK=str(rank))
+        outs.append(subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2",
+                                    "--warmup", "1", "--envs", "16"], env=e, capture_output=True, text=True, timeout=600))
+    assert all(o.returncode == 0 for o in outs), [o.stderr[-500:] for o in outs]
+    lines = [l for l in outs[0].stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1 and outs[1].stdout.strip() == ""
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["unit"] == "env-steps/s"

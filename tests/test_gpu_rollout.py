@@ -195,3 +195,32 @@ def test_fused_sinks_equal_separate_copies_and_splits():
                 np.testing.assert_allclose(oa[key].cpu().numpy(), ob[key].cpu().numpy(), rtol=1e-3, atol=5e-3, err_msg=key)
         assert all(torch.isfinite(v).all() for v in oa.values())
     A.close(); B.close()
+
+
+def test_vec_env_surface_matches_reference_adapter_contract():
+    """RLGPUEnv-shaped adapter (run.py:135-182, vec_task.py:125-134): shapes, dtypes, aliasing and reset semantics."""
+    from emloco_b200.vec_env import RLGPUEnv
+    n = 48
+    env = RLGPUEnv(n, seed=1)
+    info = env.get_env_info()
+    assert info["observation_space"].shape == (1422,) and info["action_space"].shape == (69,) and info["amp_observation_space"].shape == (3090,)
+    assert env.get_number_of_agents() == 1
+    obs0 = env.reset()
+    assert obs0.shape == (n, 1422) and obs0.is_cuda
+    a = torch.zeros(n, 69, device="cuda")
+    for _ in range(3):
+        obs, rew, done, infos = env.step(a)
+    assert obs.shape == (n, 1422) and rew.shape == (n,) and done.shape == (n,) and done.dtype == torch.int64
+    assert infos["amp_obs"].shape == (n, 3090) and infos["terminate"].dtype == torch.int64 and infos["reward_raw"].shape == (n, 2)
+    assert (env.sim.progress == 3).all()
+    env.reset(torch.tensor([0, 5]))
+    prog = env.sim.progress.cpu().numpy()
+    assert prog[0] == 0 and prog[5] == 0 and (np.delete(prog, [0, 5]) == 3).all()
+    w, p, v = env.get_waypoint_traj(), env.get_init_pose(), env.get_init_vel()
+    assert w.shape == (n, 13, 2) and p.shape == (n, 24, 3) and v.shape == (n, 2)
+    assert float(w[:, 0].abs().max()) == 0 and float(p[:, 0].abs().max()) == 0
+    # rl_device = cpu moves obs / rewards / dones like `.to(self.rl_device)` does
+    env2 = RLGPUEnv(8, rl_device="cpu")
+    o, r, d, _ = env2.step(torch.zeros(8, 69))
+    assert not o.is_cuda and not r.is_cuda and not d.is_cuda
+    env.close(); env2.close()
