@@ -216,8 +216,14 @@ static cudaError_t lv_dispatch(const float* traj, int stride, int T, float* pose
     return cudaErrorInvalidValue;
 }
 
+cudaError_t eml_locoval_forward_tc(const float* traj, int stride, float* pose, const float* vel, const float* w, float* value,
+                                   long long B, int flags, cudaStream_t st);
+
 cudaError_t eml_locoval_forward(const float* traj, int stride, int T, float* pose, const float* vel, const float* w,
                                 float* value, long long B, int flags, cudaStream_t st) {
+    // large batches of the full variant go to the tensor-core kernel (locoval_tc.cu); flag bit 6 forces the CUDA-core kernel
+    if (T == 13 && (flags & 3) == 3 && !(flags & 64) && B >= 1024 && (reinterpret_cast<uintptr_t>(pose) & 15) == 0)
+        return eml_locoval_forward_tc(traj, stride, pose, vel, w, value, B, flags, st);
     return lv_dispatch<false>(traj, stride, T, pose, vel, w, value, nullptr, nullptr, B, flags, st);
 }
 cudaError_t eml_locoval_backward(const float* traj, int stride, int T, const float* pose, const float* vel, const float* w,

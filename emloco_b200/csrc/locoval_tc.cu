@@ -1,0 +1,289 @@
+// LocoVal scoring on the tensor cores: ValuePoseNet.forward (reference pacer/pacer/learning/value_pose_net.py:105-149) for the
+// full variant (13 waypoints + pose + velocity: 100 -> 49 -> 24 -> 1) at large batch - the "1M synthetic 12-step futures"
+// configuration of BASELINE.json and the value filter of social-transmotion/evaluate_jta.py:298-302.
+//
+// The CUDA-core kernel (locoval.cu) is bound by FP32 issue (6 100 MAC per score, 18 TFLOP/s); here the two wide layers run as
+// bf16x3 tcgen05 MMAs (same split-precision scheme as linear_tc.cu: x = hi + lo, Al*Wh + Ah*Wl + Ah*Wh into fp32 TMEM), which
+// leaves the kernel bound by its 404 B/score of HBM traffic and the per-row feature generation.
+//
+// CTA = 128 threads = 128 samples (thread = row = TMEM lane), persistent over 128-row tiles, two CTAs per SM:
+//   1. each thread reads its row (waypoints, pose, velocity), applies the heading normalisation (:73-103) and the toe / spine
+//      masks (:141-144), and writes the 100 features as bf16 hi / lo into the K-major 128B-swizzled A tile (written by hand
+//      with the same XOR pattern TMA would apply), then fence.proxy.async
+//   2. thread 0: 7 k-steps x 3 MMAs (M=128, N=64, K=16) -> D1 in TMEM; tcgen05.commit -> mbarrier
+//   3. each thread: tcgen05.ld its D1 row, + b1, ReLU, split, write the A tile of layer 2 (over the consumed A tile of layer 1)
+//   4. thread 0: 4 k-steps x 3 MMAs (N=32) -> D2
+//   5. each thread: tcgen05.ld its D2 row, + b2, ReLU, dot w3, + b3, sigmoid -> value
+// Weights are split and staged once per CTA (W1 64 x 128, W2 32 x 64, zero padded).
+#include <cuda_bf16.h>
+#include "sim.h"
+
+namespace lvtc {
+
+constexpr int IN = 100, H1 = 49, H2 = 24;
+constexpr int K1 = 112;                     // IN padded to the MMA K step (7 x 16); the tile itself is two 64-wide swizzle atoms
+constexpr int N1 = 64, N2 = 32;
+constexpr int A_ATOM = 128 * 128;           // one 128-row x 64-bf16 atom: 16 KB
+constexpr int OFF_A_HI = 0, OFF_A_LO = 2 * A_ATOM;          // layer-1 A: hi atoms 0,1 then lo atoms 0,1 (64 KB)
+constexpr int OFF_A2_HI = 0, OFF_A2_LO = A_ATOM;            // layer-2 A (K = 64: one atom each) reuses the space
+constexpr int W1_ATOM = N1 * 128;           // 8 KB
+constexpr int OFF_W1_HI = 4 * A_ATOM, OFF_W1_LO = OFF_W1_HI + 2 * W1_ATOM;
+constexpr int W2_ATOM = N2 * 128;           // 4 KB
+constexpr int OFF_W2_HI = OFF_W1_LO + 2 * W1_ATOM, OFF_W2_LO = OFF_W2_HI + W2_ATOM;
+constexpr int OFF_F32 = OFF_W2_LO + W2_ATOM;                // b1[64] b2[32] w3[32] b3[1]
+constexpr int OFF_BAR = OFF_F32 + (64 + 32 + 32 + 4) * 4;
+constexpr int SMEM_BYTES = OFF_BAR + 16 + 1024;             // + alignment slack  (~107 KB: two CTAs per SM)
+constexpr int TMEM_COLS = 128;              // D1: columns 0..63, D2: columns 64..95
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// byte offset of element (row, k) inside a K-major tile made of 64-element (128 B) wide atoms of `rows` rows, 128B swizzle:
+// the 16-byte chunk index is XORed with the row index modulo 8 (what TMA's SWIZZLE_128B does)
+__device__ __forceinline__ uint32_t sw128(int rows, int row, int k) {
+    const int atom = k >> 6, kk = k & 63;
+    return (uint32_t)(atom * rows * 128 + row * 128 + ((((kk >> 3) ^ (row & 7)) << 4) | ((kk & 7) << 1)));
+}
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {       // K-major, SWIZZLE_128B, SBO = 1024 (see linear_tc.cu)
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tLVW_LOOP:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra LVW_DONE;\n\tbra LVW_LOOP;\n\tLVW_DONE:\n\t}"
+                 ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32"
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+                 " %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
+}
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    __nv_bfloat16 h0 = __float2bfloat16_rn(a), h1 = __float2bfloat16_rn(b);
+    __nv_bfloat16 l0 = __float2bfloat16_rn(a - __bfloat162float(h0)), l1 = __float2bfloat16_rn(b - __bfloat162float(h1));
+    hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+}
+
+__global__ void __launch_bounds__(128, 2)
+locoval_tc_kernel(const float* __restrict__ traj, int stride, float* pose_rw, const float* __restrict__ vel,
+                  const float* __restrict__ weights, float* __restrict__ value, long long B, int flags) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);        // 1024-byte aligned tile base
+    const uint32_t sbase = smem_u32(sm);
+    float* s_b1 = reinterpret_cast<float*>(sm + OFF_F32);
+    float* s_b2 = s_b1 + 64; float* s_w3 = s_b2 + 32; float* s_b3 = s_w3 + 32;
+    const uint32_t bar = sbase + OFF_BAR;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(sm + OFF_BAR + 8);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const bool hide_toe = flags & 4, hide_spine = flags & 8, normalize = flags & 16, writeback = flags & 32;
+
+    // ---- one-time: weights -> bf16 hi/lo, K-major swizzled, zero padded; biases; barrier; TMEM ----
+    {
+        const float* w1 = weights; const float* b1 = w1 + IN * H1;
+        const float* w2 = b1 + H1; const float* b2 = w2 + H1 * H2;
+        const float* w3 = b2 + H2; const float* b3 = w3 + H2;
+        for (int i = tid; i < N1 * 128 / 2; i += 128) {                    // pairs (n, k..k+1) of the 64 x 128 padded W1
+            const int n = i / 64, k = (i % 64) * 2;
+            float a = (n < H1 && k < IN) ? w1[n * IN + k] : 0.f, b = (n < H1 && k + 1 < IN) ? w1[n * IN + k + 1] : 0.f;
+            uint32_t h, l; split2(a, b, h, l);
+            const uint32_t off = sw128(N1, n, k);
+            *reinterpret_cast<uint32_t*>(sm + OFF_W1_HI + off) = h; *reinterpret_cast<uint32_t*>(sm + OFF_W1_LO + off) = l;
+        }
+        for (int i = tid; i < N2 * 64 / 2; i += 128) {                     // 32 x 64 padded W2
+            const int n = i / 32, k = (i % 32) * 2;
+            float a = (n < H2 && k < H1) ? w2[n * H1 + k] : 0.f, b = (n < H2 && k + 1 < H1) ? w2[n * H1 + k + 1] : 0.f;
+            uint32_t h, l; split2(a, b, h, l);
+            const uint32_t off = sw128(N2, n, k);
+            *reinterpret_cast<uint32_t*>(sm + OFF_W2_HI + off) = h; *reinterpret_cast<uint32_t*>(sm + OFF_W2_LO + off) = l;
+        }
+        if (tid < 64) s_b1[tid] = tid < H1 ? b1[tid] : 0.f;
+        if (tid < 32) { s_b2[tid] = tid < H2 ? b2[tid] : 0.f; s_w3[tid] = tid < H2 ? w3[tid] : 0.f; }
+        if (tid == 0) {
+            s_b3[0] = b3[0];
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        if (warp == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // weight tiles are read by the async proxy (MMA)
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(s_tmem);
+    const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N1 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N2 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    uint32_t phase = 0;
+
+    const long long tiles = (B + 127) / 128;
+    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const long long b = t * 128 + tid;
+        const bool ok = b < B;
+        const long long bb = ok ? b : B - 1;                               // tail rows recompute the last sample, stores masked
+
+        // ---- 1. features of this row -> layer-1 A tile ----
+        {
+            const float* tr = traj + bb * 13 * stride;
+            float c = 1.f, s = 0.f;
+            if (normalize) {                                               // _rotate_normalization (:76-84)
+                const float x1 = tr[stride], y1 = tr[stride + 1];
+                const float xe = fabsf(x1) < 1e-10f ? 1e-10f : x1;
+                sincosf(atan2f(y1, xe), &s, &c);
+            }
+            float f[K1];                                                   // the row's features, statically indexed
+#pragma unroll
+            for (int n = 0; n < 13; ++n) {                                 // row-vector times [[c,-s],[s,c]] (:85-100)
+                const float x = tr[n * stride], y = tr[n * stride + 1];
+                f[2 * n] = x * c + y * s; f[2 * n + 1] = y * c - x * s;
+            }
+            float* pp = pose_rw + bb * 72;
+            const float4* p4 = reinterpret_cast<const float4*>(pp);
+#pragma unroll
+            for (int i = 0; i < 18; ++i) { float4 v = __ldg(p4 + i); f[26 + 4 * i] = v.x; f[27 + 4 * i] = v.y; f[28 + 4 * i] = v.z; f[29 + 4 * i] = v.w; }
+#pragma unroll
+            for (int j = 0; j < 24; ++j) {
+                float xr = f[26 + 3 * j] * c + f[27 + 3 * j] * s, yr = f[27 + 3 * j] * c - f[26 + 3 * j] * s, z = f[28 + 3 * j];
+                if ((hide_toe && (j == 4 || j == 8)) || (hide_spine && j >= 9 && j <= 11)) { xr = 0.f; yr = 0.f; z = 0.f; }
+                f[26 + 3 * j] = xr; f[27 + 3 * j] = yr; f[28 + 3 * j] = z;
+            }
+            if (writeback && ok) {                                         // the reference rotates / zeroes init_pose in place (:97,141-144)
+                float4* o4 = reinterpret_cast<float4*>(pp);
+#pragma unroll
+                for (int i = 0; i < 18; ++i) o4[i] = make_float4(f[26 + 4 * i], f[27 + 4 * i], f[28 + 4 * i], f[29 + 4 * i]);
+            }
+            const float vx = vel[bb * 2], vy = vel[bb * 2 + 1];
+            f[98] = vx * c + vy * s; f[99] = vy * c - vx * s;
+#pragma unroll
+            for (int k = IN; k < K1; ++k) f[k] = 0.f;                      // K padding (the layer-2 tile overwrites this space)
+#pragma unroll
+            for (int ch = 0; ch < K1 / 8; ++ch) {                          // 14 chunks of 8 bf16 = 16 bytes, hi and lo
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) split2(f[ch * 8 + 2 * i], f[ch * 8 + 2 * i + 1], h[i], l[i]);
+                const uint32_t off = sw128(128, tid, ch * 8);
+                *reinterpret_cast<uint4*>(sm + OFF_A_HI + off) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(sm + OFF_A_LO + off) = make_uint4(l[0], l[1], l[2], l[3]);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        // ---- 2. layer 1 on the tensor core ----
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < K1 / 16; ++j) {
+                const uint32_t ao = (uint32_t)((j >> 2) * A_ATOM + (j & 3) * 32), wo = (uint32_t)((j >> 2) * W1_ATOM + (j & 3) * 32);
+                const uint64_t ah = make_desc(sbase + OFF_A_HI + ao), al = make_desc(sbase + OFF_A_LO + ao);
+                const uint64_t wh = make_desc(sbase + OFF_W1_HI + wo), wl = make_desc(sbase + OFF_W1_LO + wo);
+                umma(tmem, al, wh, idesc1, j != 0);
+                umma(tmem, ah, wl, idesc1, 1);
+                umma(tmem, ah, wh, idesc1, 1);
+            }
+            commit(bar);
+        }
+        mbar_wait(bar, phase); phase ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---- 3. hidden layer 1: + b1, ReLU, split -> layer-2 A tile (K = 64, columns 49..63 zero) ----
+        {
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+            uint32_t r0[32], r1[32];
+            tmem_ld32(taddr, r0); tmem_ld32(taddr + 32, r1);
+            tmem_wait(r0); tmem_wait(r1);
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int j = ch * 8 + 2 * i;
+                    const float a = j < H1 ? fmaxf(__uint_as_float(j < 32 ? r0[j & 31] : r1[j & 31]) + s_b1[j], 0.f) : 0.f;
+                    const float bq = j + 1 < H1 ? fmaxf(__uint_as_float(j + 1 < 32 ? r0[(j + 1) & 31] : r1[(j + 1) & 31]) + s_b1[j + 1], 0.f) : 0.f;
+                    split2(a, bq, h[i], l[i]);
+                }
+                const uint32_t off = sw128(128, tid, ch * 8);
+                *reinterpret_cast<uint4*>(sm + OFF_A2_HI + off) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(sm + OFF_A2_LO + off) = make_uint4(l[0], l[1], l[2], l[3]);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        // ---- 4. layer 2 on the tensor core ----
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t ko = (uint32_t)(j * 32);
+                const uint64_t ah = make_desc(sbase + OFF_A2_HI + ko), al = make_desc(sbase + OFF_A2_LO + ko);
+                const uint64_t wh = make_desc(sbase + OFF_W2_HI + ko), wl = make_desc(sbase + OFF_W2_LO + ko);
+                umma(tmem + 64, al, wh, idesc2, j != 0);
+                umma(tmem + 64, ah, wl, idesc2, 1);
+                umma(tmem + 64, ah, wh, idesc2, 1);
+            }
+            commit(bar);
+        }
+        mbar_wait(bar, phase); phase ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---- 5. hidden layer 2, output layer, sigmoid ----
+        {
+            uint32_t r[32];
+            tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + 64, r);
+            tmem_wait(r);
+            float z = s_b3[0];
+#pragma unroll
+            for (int o = 0; o < H2; ++o) z += s_w3[o] * fmaxf(__uint_as_float(r[o]) + s_b2[o], 0.f);
+            if (ok) value[b] = 1.0f / (1.0f + expf(-z));
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();            // D1 / D2 and the A tile are free again
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
+    }
+}
+
+}  // namespace lvtc
+
+cudaError_t eml_locoval_forward_tc(const float* traj, int stride, float* pose, const float* vel, const float* w, float* value,
+                                   long long B, int flags, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(lvtc::locoval_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lvtc::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    if (B <= 0) return cudaSuccess;
+    const long long tiles = (B + 127) / 128;
+    const int grid = (int)(tiles < 148 * 2 ? tiles : 148 * 2);
+    lvtc::locoval_tc_kernel<<<grid, 128, lvtc::SMEM_BYTES, st>>>(traj, stride, pose, vel, w, value, B, flags);
+    return cudaGetLastError();
+}

@@ -173,7 +173,8 @@ int emloco_reset_done(emloco_sim* sim, const float* d_init_root, const float* d_
  * weights: fc1.weight[H1,IN] fc1.bias[H1] fc2.weight[H2,H1] fc2.bias[H2] fc3.weight[1,H2] fc3.bias[1]
  * packed in that order (state-dict order of `_network.fc{1,2,3}.{weight,bias}`).
  * flags: bit0 use_pose, bit1 use_vel, bit2 hide_toe, bit3 hide_spine, bit4 normalize,
- *        bit5 write the rotated/zeroed pose back into d_pose (the reference's in-place side effect, :97,:141-144).
+ *        bit5 write the rotated/zeroed pose back into d_pose (the reference's in-place side effect, :97,:141-144),
+ *        bit6 force the CUDA-core kernel (batches >= 1024 of the full variant otherwise run on the tensor cores).
  * traj [B,T,traj_stride] (only x,y read; T = 13 or 5), pose [B,24,3], vel [B,2], value [B]. */
 int emloco_locoval_forward(const float* d_traj, int32_t traj_stride, int32_t num_waypoints, float* d_pose,
                            const float* d_vel, const float* d_weights, float* d_value, int64_t batch,

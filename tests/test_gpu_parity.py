@@ -273,3 +273,42 @@ def test_linear_bf16x3_tiles_and_ragged_shapes(tile, M, N, K):
     linear_bf16x3(sx, sw, T(b), False, y32=y, tile=tile)
     ref = x.astype(np.float64) @ w.astype(np.float64).T + b
     np.testing.assert_allclose(y.cpu().numpy(), ref, rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("stride,B", [(2, 5000), (3, 1024), (2, 131072 + 77)])
+def test_locoval_tensor_core_kernel_matches_cuda_core_kernel_and_oracle(stride, B):
+    """Batches >= 1024 of the full variant run on the tcgen05 kernel (locoval_tc.cu); flag bit 6 forces the CUDA-core kernel.
+    Both against each other and against the numpy oracle, incl. the in-place pose side effect and ragged tiles."""
+    import ctypes as C
+    from emloco_b200 import _lib
+    from emloco_b200.value_pose_net import ValuePoseNet
+    from oracle import oracle_np as O
+    torch.manual_seed(3)
+    net = ValuePoseNet(True, True).cuda().eval()
+    with torch.no_grad():
+        for m in net._network:
+            if hasattr(m, "bias"):
+                m.bias.uniform_(-0.3, 0.3)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    traj = torch.randn(B, 13, stride, device="cuda", generator=g).cumsum(1) * 0.3
+    traj[:, 0] = 0
+    traj[::7, 1, 0] = 0.0                                     # x == 0 at the heading waypoint: the 1e-10 epsilon branch (:79-84)
+    pose = torch.randn(B, 24, 3, device="cuda", generator=g) * 0.3
+    vel = torch.randn(B, 2, device="cuda", generator=g)
+    w = net._weights()
+    p = lambda t: C.c_void_p(t.data_ptr())
+    out = {}
+    for name, extra in (("tc", 0), ("cc", 64)):
+        v = torch.empty(B, device="cuda"); pp = pose.clone()
+        flags = 1 | 2 | 4 | 8 | 16 | 32 | extra
+        _lib.check(_lib.load().emloco_locoval_forward(p(traj), stride, 13, p(pp), p(vel), p(w), p(v), B, flags, None), "emloco_locoval_forward")
+        torch.cuda.synchronize()
+        out[name] = (v.cpu().numpy(), pp.cpu().numpy())
+    np.testing.assert_allclose(out["tc"][0], out["cc"][0], rtol=1e-3, atol=2e-6)
+    np.testing.assert_allclose(out["tc"][1], out["cc"][1], rtol=1e-5, atol=1e-6)       # rotated / zeroed pose written back
+    n = min(B, 4096)
+    W = {k: (getattr(net._network, k).weight.detach().cpu().numpy(), getattr(net._network, k).bias.detach().cpu().numpy())
+         for k in ("fc1", "fc2", "fc3")}
+    ref, pose_after = O.locoval_forward(traj[:n, :, :2].cpu().numpy(), pose[:n].cpu().numpy(), vel[:n].cpu().numpy(), W)
+    np.testing.assert_allclose(out["tc"][0][:n], ref[:, 0], rtol=1e-3, atol=2e-6)
+    np.testing.assert_allclose(out["tc"][1][:n], pose_after, rtol=1e-3, atol=1e-5)
