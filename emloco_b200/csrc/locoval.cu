@@ -222,7 +222,8 @@ cudaError_t eml_locoval_forward_tc(const float* traj, int stride, float* pose, c
 cudaError_t eml_locoval_forward(const float* traj, int stride, int T, float* pose, const float* vel, const float* w,
                                 float* value, long long B, int flags, cudaStream_t st) {
     // large batches of the full variant go to the tensor-core kernel (locoval_tc.cu); flag bit 6 forces the CUDA-core kernel
-    if (T == 13 && (flags & 3) == 3 && !(flags & 64) && B >= 1024 && (reinterpret_cast<uintptr_t>(pose) & 15) == 0)
+    if (T == 13 && (flags & 3) == 3 && !(flags & 64) && B >= 1024 && stride <= 3 &&
+        ((reinterpret_cast<uintptr_t>(pose) | reinterpret_cast<uintptr_t>(traj) | reinterpret_cast<uintptr_t>(vel)) & 15) == 0)
         return eml_locoval_forward_tc(traj, stride, pose, vel, w, value, B, flags, st);
     return lv_dispatch<false>(traj, stride, T, pose, vel, w, value, nullptr, nullptr, B, flags, st);
 }

@@ -33,6 +33,7 @@ constexpr int OFF_W2_HI = OFF_W1_LO + 2 * W1_ATOM, OFF_W2_LO = OFF_W2_HI + W2_AT
 constexpr int OFF_F32 = OFF_W2_LO + W2_ATOM;                // b1[64] b2[32] w3[32] b3[1]
 constexpr int OFF_BAR = OFF_F32 + (64 + 32 + 32 + 4) * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 16 + 1024;             // + alignment slack  (~107 KB: two CTAs per SM)
+constexpr int ST_TRAJ = 0, ST_POSE = 20480, ST_VEL = ST_POSE + 128 * 72 * 4;   // raw-row staging inside the A-tile bytes (< 64 KB)
 constexpr int TMEM_COLS = 128;              // D1: columns 0..63, D2: columns 64..95
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -145,27 +146,44 @@ locoval_tc_kernel(const float* __restrict__ traj, int stride, float* pose_rw, co
     for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
         const long long b = t * 128 + tid;
         const bool ok = b < B;
-        const long long bb = ok ? b : B - 1;                               // tail rows recompute the last sample, stores masked
 
-        // ---- 1. features of this row -> layer-1 A tile ----
+        // ---- 1a. the tile's raw rows -> shared memory with coalesced 16-byte loads.  The staging area aliases the A tile:
+        //          rows are pulled into registers before the tile is written (per-row global loads would cost one LSU
+        //          wavefront per lane: 58 uncoalesced loads x 32 lanes per warp dominated the first version of this kernel)
         {
-            const float* tr = traj + bb * 13 * stride;
+            const long long r0 = t * 128;
+            const int rows = (int)((B - r0) < 128 ? (B - r0) : 128);
+            auto stage = [&](const float* src, int row_len, int byte_off) {
+                const int nfl = rows * row_len;
+                float* dst = reinterpret_cast<float*>(sm + byte_off);
+                const float4* g4 = reinterpret_cast<const float4*>(src);
+                for (int i = tid; i < nfl / 4; i += 128) reinterpret_cast<float4*>(dst)[i] = __ldg(g4 + i);
+                for (int i = (nfl & ~3) + tid; i < nfl; i += 128) dst[i] = src[i];
+            };
+            stage(traj + r0 * 13 * stride, 13 * stride, ST_TRAJ);
+            stage(pose_rw + r0 * 72, 72, ST_POSE);
+            stage(vel + r0 * 2, 2, ST_VEL);
+        }
+        __syncthreads();
+        // ---- 1b. features of this row (registers) ----
+        float f[K1];                                                       // statically indexed
+        {
+            const int row = ok ? tid : (int)(B - 1 - t * 128);             // tail rows recompute the last valid row
+            const float* tr = reinterpret_cast<const float*>(sm + ST_TRAJ) + row * 13 * stride;
             float c = 1.f, s = 0.f;
             if (normalize) {                                               // _rotate_normalization (:76-84)
                 const float x1 = tr[stride], y1 = tr[stride + 1];
                 const float xe = fabsf(x1) < 1e-10f ? 1e-10f : x1;
                 sincosf(atan2f(y1, xe), &s, &c);
             }
-            float f[K1];                                                   // the row's features, statically indexed
 #pragma unroll
             for (int n = 0; n < 13; ++n) {                                 // row-vector times [[c,-s],[s,c]] (:85-100)
                 const float x = tr[n * stride], y = tr[n * stride + 1];
                 f[2 * n] = x * c + y * s; f[2 * n + 1] = y * c - x * s;
             }
-            float* pp = pose_rw + bb * 72;
-            const float4* p4 = reinterpret_cast<const float4*>(pp);
+            const float4* p4 = reinterpret_cast<const float4*>(sm + ST_POSE) + row * 18;
 #pragma unroll
-            for (int i = 0; i < 18; ++i) { float4 v = __ldg(p4 + i); f[26 + 4 * i] = v.x; f[27 + 4 * i] = v.y; f[28 + 4 * i] = v.z; f[29 + 4 * i] = v.w; }
+            for (int i = 0; i < 18; ++i) { float4 v = p4[i]; f[26 + 4 * i] = v.x; f[27 + 4 * i] = v.y; f[28 + 4 * i] = v.z; f[29 + 4 * i] = v.w; }
 #pragma unroll
             for (int j = 0; j < 24; ++j) {
                 float xr = f[26 + 3 * j] * c + f[27 + 3 * j] * s, yr = f[27 + 3 * j] * c - f[26 + 3 * j] * s, z = f[28 + 3 * j];
@@ -173,23 +191,25 @@ locoval_tc_kernel(const float* __restrict__ traj, int stride, float* pose_rw, co
                 f[26 + 3 * j] = xr; f[27 + 3 * j] = yr; f[28 + 3 * j] = z;
             }
             if (writeback && ok) {                                         // the reference rotates / zeroes init_pose in place (:97,141-144)
-                float4* o4 = reinterpret_cast<float4*>(pp);
+                float4* o4 = reinterpret_cast<float4*>(pose_rw + b * 72);
 #pragma unroll
                 for (int i = 0; i < 18; ++i) o4[i] = make_float4(f[26 + 4 * i], f[27 + 4 * i], f[28 + 4 * i], f[29 + 4 * i]);
             }
-            const float vx = vel[bb * 2], vy = vel[bb * 2 + 1];
-            f[98] = vx * c + vy * s; f[99] = vy * c - vx * s;
+            const float2 vv = reinterpret_cast<const float2*>(sm + ST_VEL)[row];
+            f[98] = vv.x * c + vv.y * s; f[99] = vv.y * c - vv.x * s;
 #pragma unroll
-            for (int k = IN; k < K1; ++k) f[k] = 0.f;                      // K padding (the layer-2 tile overwrites this space)
+            for (int k = IN; k < K1; ++k) f[k] = 0.f;                      // K padding
+        }
+        __syncthreads();                                                   // everybody has its row: the staging bytes may go
+        // ---- 1c. bf16 hi / lo -> layer-1 A tile (14 chunks of 8 bf16 = 16 bytes per row, swizzled) ----
 #pragma unroll
-            for (int ch = 0; ch < K1 / 8; ++ch) {                          // 14 chunks of 8 bf16 = 16 bytes, hi and lo
-                uint32_t h[4], l[4];
+        for (int ch = 0; ch < K1 / 8; ++ch) {
+            uint32_t h[4], l[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) split2(f[ch * 8 + 2 * i], f[ch * 8 + 2 * i + 1], h[i], l[i]);
-                const uint32_t off = sw128(128, tid, ch * 8);
-                *reinterpret_cast<uint4*>(sm + OFF_A_HI + off) = make_uint4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<uint4*>(sm + OFF_A_LO + off) = make_uint4(l[0], l[1], l[2], l[3]);
-            }
+            for (int i = 0; i < 4; ++i) split2(f[ch * 8 + 2 * i], f[ch * 8 + 2 * i + 1], h[i], l[i]);
+            const uint32_t off = sw128(128, tid, ch * 8);
+            *reinterpret_cast<uint4*>(sm + OFF_A_HI + off) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(sm + OFF_A_LO + off) = make_uint4(l[0], l[1], l[2], l[3]);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
