@@ -83,10 +83,11 @@ __device__ __forceinline__ void tmem_wait(uint32_t* r) {
                  :: "memory");
 }
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    __nv_bfloat16 h0 = __float2bfloat16_rn(a), h1 = __float2bfloat16_rn(b);
-    __nv_bfloat16 l0 = __float2bfloat16_rn(a - __bfloat162float(h0)), l1 = __float2bfloat16_rn(b - __bfloat162float(h1));
-    hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    // packed conversions (one F2FP per pair); a bf16 widened to fp32 is its bits shifted into the high half
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+    lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 __global__ void __launch_bounds__(128, 2)
@@ -157,12 +158,16 @@ locoval_tc_kernel(const float* __restrict__ traj, int stride, float* pose_rw, co
                 const int nfl = rows * row_len;
                 float* dst = reinterpret_cast<float*>(sm + byte_off);
                 const float4* g4 = reinterpret_cast<const float4*>(src);
-                for (int i = tid; i < nfl / 4; i += 128) reinterpret_cast<float4*>(dst)[i] = __ldg(g4 + i);
+                // cp.async: every 16-byte piece of the tile is in flight at once (51 KB per CTA), no register round trip
+                for (int i = tid; i < nfl / 4; i += 128)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(reinterpret_cast<float4*>(dst) + i)), "l"(g4 + i) : "memory");
                 for (int i = (nfl & ~3) + tid; i < nfl; i += 128) dst[i] = src[i];
             };
             stage(traj + r0 * 13 * stride, 13 * stride, ST_TRAJ);
             stage(pose_rw + r0 * 72, 72, ST_POSE);
             stage(vel + r0 * 2, 2, ST_VEL);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
         // ---- 1b. features of this row (registers) ----
