@@ -81,6 +81,7 @@ struct PhysParams {
     int N; int n_sub; float dt;
     float gz, kn, cn, ct, mu, max_w, max_effort, max_turn;
     int fk_only;
+    int epb;                            // lane-per-env kernel: envs per CTA (<= 32)
 };
 
 __device__ __forceinline__ float ground_height(const PhysParams& P, float x, float y) {

@@ -44,7 +44,8 @@ enum {
 #define SOA_WMAX (SOA_ACC + 2 * 6 * 32)            // 5 x 32: per-chain max body angular speed
 #define SOA_KMAX (SOA_WMAX + 5 * 32)               // 8 ints: per-warp largest piece count
 #define SOA_FSUM (SOA_KMAX + 8)                    // 24 x 3 x 32: contact force accumulated over the parts
-#define SOA_FLOATS (SOA_FSUM + EML_NB * 3 * 32)
+#define SOA_KIN (SOA_FSUM + EML_NB * 3 * 32)         // 13 x 32: the chest's kinematic state of the coming part, for the arm chains
+#define SOA_FLOATS (SOA_KIN + 13 * 32)
 #define SOA_SMEM_BYTES (SOA_FLOATS * 4)
 
 __constant__ int c_chain_len[5] = {4, 4, 5, 5, 5};
@@ -112,6 +113,22 @@ __device__ __forceinline__ Kin kin_step(const Kin& p, f3 offset, f4 jq, f3 jw, f
     k.w = p.w + ww; k.l = p.l + jl;
     cw = cross3(p.w, ww);                                // c = v_parent x vJ
     cl = cross3(p.w, jl) + cross3(p.l, ww);
+    return k;
+}
+
+__device__ __forceinline__ void store_kin(float* smem, int lane, int b, const Kin& k, f3 cw, f3 cl) {
+    st3(smem, lane, b, F_X, k.x); st4(smem, lane, b, F_QW, k.q); st3(smem, lane, b, F_VW, k.w); st3(smem, lane, b, F_VL, k.l);
+    st3(smem, lane, b, F_C, cw); st3(smem, lane, b, F_C + 3, cl);
+}
+__device__ __forceinline__ void put_kin(float* smem, int lane, const Kin& k) {
+    float* p = smem + SOA_KIN + lane;
+    p[0] = k.q.x; p[32] = k.q.y; p[64] = k.q.z; p[96] = k.q.w; p[128] = k.x.x; p[160] = k.x.y; p[192] = k.x.z;
+    p[224] = k.w.x; p[256] = k.w.y; p[288] = k.w.z; p[320] = k.l.x; p[352] = k.l.y; p[384] = k.l.z;
+}
+__device__ __forceinline__ Kin get_kin(const float* smem, int lane) {
+    const float* p = smem + SOA_KIN + lane;
+    Kin k; k.q = mk4(p[0], p[32], p[64], p[96]); k.x = mk3(p[128], p[160], p[192]);
+    k.w = mk3(p[224], p[256], p[288]); k.l = mk3(p[320], p[352], p[384]);
     return k;
 }
 
@@ -214,8 +231,10 @@ __device__ __noinline__ void finish_body(float* smem, int lane, int b, f3& aw, f
 __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams P) {
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int env_raw = blockIdx.x * 32 + lane;
-    const bool env_ok = env_raw < P.N;
+    // envs per CTA: 32 lanes, of which P.epb are used - chosen by the launcher so that the CTAs cover all SMs in one wave
+    // (4096 envs: 147 CTAs x 28 envs instead of 128 x 32)
+    const int env_raw = blockIdx.x * P.epb + lane;
+    const bool env_ok = env_raw < P.N && lane < P.epb;
     const int env = env_ok ? env_raw : P.N - 1;                    // clamped: tail lanes recompute the last env, stores masked
     const EmlModelDev& Mo = *P.model;
 
@@ -263,15 +282,11 @@ __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams 
     float* const df_row = env_ok ? P.dof_force + (size_t)env * EML_ND : nullptr;
     int sub = 0, part = 0, parts = 1, kmax = 1, rb = 0;            // rb: root buffer holding the current root state
     float dt = P.dt;
-#pragma unroll 1
-    while (sub < P.n_sub) {
-        const float* root = smem + SOA_ROOT + rb * 13 * 32;
-        const f3 p0 = mk3(root[lane], root[32 + lane], root[64 + lane]);
+    // ---- kinematics of the initial state (afterwards pass C computes the next part's kinematics right after integrating) ----
+    {
+        const float* root = smem + SOA_ROOT;
         const f4 q0 = mk4(root[3 * 32 + lane], root[4 * 32 + lane], root[5 * 32 + lane], root[6 * 32 + lane]);
-        const f3 v0 = mk3(root[7 * 32 + lane], root[8 * 32 + lane], root[9 * 32 + lane]);
         const f3 w0 = mk3(root[10 * 32 + lane], root[11 * 32 + lane], root[12 * 32 + lane]);
-
-        // ================= A0: kinematics by chains =================
         if (chain < 5) {
             Kin k; k.q = q0; k.x = mk3(0, 0, 0); k.w = w0; k.l = mk3(0, 0, 0);
             float wm = 0.f;
@@ -293,7 +308,16 @@ __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams 
             }
             smem[SOA_WMAX + chain * 32 + lane] = wm;
         }
-        __syncthreads();
+    }
+    __syncthreads();
+#pragma unroll 1
+    while (sub < P.n_sub) {
+        const float* root = smem + SOA_ROOT + rb * 13 * 32;
+        const f3 p0 = mk3(root[lane], root[32 + lane], root[64 + lane]);
+        const f4 q0 = mk4(root[3 * 32 + lane], root[4 * 32 + lane], root[5 * 32 + lane], root[6 * 32 + lane]);
+        const f3 v0 = mk3(root[7 * 32 + lane], root[8 * 32 + lane], root[9 * 32 + lane]);
+        const f3 w0 = mk3(root[10 * 32 + lane], root[11 * 32 + lane], root[12 * 32 + lane]);
+
         if (part == 0) {
             // adaptive refinement: split the sub-step until no body turns more than max_turn per piece (<= 8 pieces); the
             // piece count is per env (lane), the CTA loops to the largest and finished lanes stop updating their state
@@ -467,8 +491,24 @@ __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams 
                 nr[224] = nv0.x; nr[256] = nv0.y; nr[288] = nv0.z; nr[320] = nw0.x; nr[352] = nw0.y; nr[384] = nw0.z;
             }
             // torso, spine, chest: accelerations, contact force, integration (the arms and the neck start from the chest's)
+            Kin k;                                                         // kinematics of the COMING part, from the new state
+            {
+                const float* nr = smem + SOA_ROOT + (rb ^ 1) * 13 * 32 + lane;
+                k.q = mk4(nr[96], nr[128], nr[160], nr[192]); k.x = mk3(0, 0, 0);
+                k.w = mk3(nr[320], nr[352], nr[384]); k.l = mk3(0, 0, 0);
+            }
+            float wm = dot3(k.w, k.w);
+            st3(smem, lane, 0, F_X, k.x); st4(smem, lane, 0, F_QW, k.q); st3(smem, lane, 0, F_VW, k.w); st3(smem, lane, 0, F_VL, k.l);
 #pragma unroll 1
-            for (int b = 9; b <= 11; ++b) finish_body(smem, lane, b, aw, al, v0, st, df_row);
+            for (int b = 9; b <= 11; ++b) {
+                finish_body(smem, lane, b, aw, al, v0, st, df_row);
+                f3 cw, cl;
+                k = kin_step(k, mk3(Mo.offset[b][0], Mo.offset[b][1], Mo.offset[b][2]), ld4(smem, lane, b, F_JQ), ld3(smem, lane, b, F_JW), cw, cl);
+                store_kin(smem, lane, b, k, cw, cl);
+                wm = fmaxf(wm, dot3(k.w, k.w));
+            }
+            put_kin(smem, lane, k);                                        // the arms and the neck continue from the chest
+            smem[SOA_WMAX + 2 * 32 + lane] = wm;                           // (the spine warp adds neck and head in pass C)
             acc[6 * 32] = aw.x; acc[7 * 32] = aw.y; acc[8 * 32] = aw.z; acc[9 * 32] = al.x; acc[10 * 32] = al.y; acc[11 * 32] = al.z;
         }
         __syncthreads();
@@ -477,8 +517,26 @@ __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams 
         if (chain < 5) {
             const float* acc = smem + SOA_ACC + (chain >= 2 ? 6 * 32 : 0) + lane;   // legs start at the pelvis, the rest at the chest
             f3 aw = mk3(acc[0], acc[32], acc[64]), al = mk3(acc[96], acc[128], acc[160]);
+            Kin k;
+            float wm = 0.f;
+            if (chain >= 2) {
+                k = get_kin(smem, lane);
+                if (chain == 2) wm = smem[SOA_WMAX + 2 * 32 + lane];
+            } else {
+                const float* nr = smem + SOA_ROOT + (rb ^ 1) * 13 * 32 + lane;
+                k.q = mk4(nr[96], nr[128], nr[160], nr[192]); k.x = mk3(0, 0, 0);
+                k.w = mk3(nr[320], nr[352], nr[384]); k.l = mk3(0, 0, 0);
+            }
 #pragma unroll 1
-            for (int i = chain == 2 ? 3 : 0; i < clen; ++i) finish_body(smem, lane, c_chain_body[chain][i], aw, al, v0, st, df_row);
+            for (int i = chain == 2 ? 3 : 0; i < clen; ++i) {
+                const int b = c_chain_body[chain][i];
+                finish_body(smem, lane, b, aw, al, v0, st, df_row);
+                f3 cw, cl;                                                 // kinematics of the coming part
+                k = kin_step(k, mk3(Mo.offset[b][0], Mo.offset[b][1], Mo.offset[b][2]), ld4(smem, lane, b, F_JQ), ld3(smem, lane, b, F_JW), cw, cl);
+                store_kin(smem, lane, b, k, cw, cl);
+                wm = fmaxf(wm, dot3(k.w, k.w));
+            }
+            smem[SOA_WMAX + chain * 32 + lane] = wm;
         }
         rb ^= 1;
         if (++part == kmax) { part = 0; ++sub; }
@@ -546,7 +604,14 @@ cudaError_t eml_launch_physics_soa(emloco_sim* s, const float* d_actions, int n_
     }
     PhysParams P; eml_fill_phys_params(s, P);
     P.actions = d_actions; P.actions_copy = d_actions ? s->actions : nullptr; P.n_sub = n_substeps;
-    const int blocks = (s->N + 31) / 32;
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    // one CTA per SM is resident (214 KB of shared memory): spread the envs over as many SMs as possible, <= 32 per CTA
+    int epb = (s->N + sms - 1) / sms;
+    epb = epb < 1 ? 1 : (epb > 32 ? 32 : epb);
+    if ((s->N + epb - 1) / epb > sms && epb < 32) epb = 32;      // more than one wave anyway: use full warps
+    P.epb = epb;
+    const int blocks = (s->N + epb - 1) / epb;
     physics_soa_kernel<<<blocks, SOA_THREADS, SOA_SMEM_BYTES, st>>>(P);
     return cudaGetLastError();
 }
