@@ -285,7 +285,7 @@ def run_ours(args):
         # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ----
         cores = os.cpu_count() or 1
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:     # reported at N = 1 only
             rate, done, dt = cpu_rollout_rate(64, 40, 1, seed=args.seed, budget_s=20.0)
             cpu = {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
                    "sample": f"64 envs x {done} steps in {dt:.1f} s (configs[0] size; fp64 C physics oracle with OpenMP + numpy nets/post-step)"}
@@ -310,6 +310,9 @@ def run_ours(args):
 
 
 def main():
+    # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=64)
