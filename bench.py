@@ -34,6 +34,9 @@ BYTES_POST = 28264            # per env-step: state/contact/force/verts in, obs 
 FLOP_NETS_STEP = 2 * (7.493154e6 + 4.046848e6 + 3.688960e6)
 BYTES_LOCOVAL = 404           # per score
 HORIZON = 32
+# DRAM traffic per launch from the committed `ncu --set full` capture (profiles/r01c_full.md; cold caches under ncu, so an
+# upper bound of what a warm step moves): dram__bytes_read.sum + dram__bytes_write.sum
+NCU_TRAFFIC = {"physics": 5.3e6, "post_step": 253.0e6, "nets": 15 * 27.2e6, "locoval": None}
 
 
 def peaks():
@@ -280,7 +283,13 @@ def run_ours(args):
         for k in kern.values():
             k["frac"] = k["achieved"] / k["peak"]
         dom = max(("physics", "post_step", "nets"), key=lambda k: kern[k]["ms"])
-        roof = dict(kern[dom]); roof.update(kernel=dom, traffic=None, peak_source=pk["src"])
+        names = {"nets": "tc::linear_bf16x3_kernel (the 15 dense-layer launches of a step)", "physics": "physics_soa_kernel",
+                 "post_step": "post_step_kernel"}
+        roof = dict(kern[dom]); roof.update(kernel=names[dom], traffic=NCU_TRAFFIC[dom], peak_source=pk["src"],
+                                            traffic_source="profiles/r01c_full.md (ncu --set full, per step for nets / per launch otherwise)")
+        if dom == "nets":
+            roof["note"] = ("fp32 operands are carried as bf16 hi+lo and every k-step issues 3 MMAs (bf16x3, fp32-grade products): "
+                            "frac counts algorithmic FLOPs once, so its ceiling is 1/3; MMA-issue rate = 3 x achieved")
 
         # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ----
         cores = os.cpu_count() or 1
