@@ -1,0 +1,75 @@
+"""CPU: the formats either side of the path: rl_games checkpoint dict, saved-trajectory pkl, mode filter."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+
+def test_rl_games_checkpoint_round_trip(tmp_path):
+    from emloco_b200.formats import load_rl_games_checkpoint, save_rl_games_checkpoint
+    from emloco_b200.policy import AMPSeptValueNetwork, RunningMeanStd
+    torch.manual_seed(0)
+    net = AMPSeptValueNetwork()
+    on, an, vn = RunningMeanStd(1422), RunningMeanStd(3090), RunningMeanStd(1)
+    on.running_mean.normal_(); on.running_var.uniform_(0.5, 2); an.running_mean.normal_(); vn.running_var.fill_(3.0); on.count.fill_(1234.0)
+    p = os.path.join(tmp_path, "Humanoid.pth")
+    ck = save_rl_games_checkpoint(p, net, on, an, vn, epoch=25000, frame=123)
+    assert all(k.startswith("a2c_network.") for k in ck["model"])
+    assert {"a2c_network.actor_mlp.0.weight", "a2c_network._task_mlp.2.bias", "a2c_network._disc_logits.weight", "a2c_network.sigma",
+            "a2c_network._value_logits.bias"} <= set(ck["model"])
+    net2, on2, an2, vn2, meta = load_rl_games_checkpoint(p)
+    for (k, a), (_, b) in zip(net.state_dict().items(), net2.state_dict().items()):
+        assert torch.equal(a, b), k
+    assert torch.equal(on.running_mean, on2.running_mean) and torch.equal(on.running_var, on2.running_var) and on2.count.item() == 1234.0
+    assert torch.equal(an.running_mean, an2.running_mean) and vn2.running_var.item() == 3.0
+    assert meta == {"epoch": 25000, "frame": 123}
+    # normalisers kept inside the model dict (later rl_games layouts) and a shape mismatch
+    ck2 = {"model": dict(ck["model"])}
+    ck2["model"]["running_mean_std.running_mean"] = on.running_mean + 1
+    ck2["model"]["running_mean_std.running_var"] = on.running_var
+    ck2["model"]["value_mean_std.running_mean"] = torch.tensor([0.5]); ck2["model"]["value_mean_std.running_var"] = torch.tensor([2.0])
+    _, on3, _, vn3, _ = load_rl_games_checkpoint(ck2)
+    assert torch.allclose(on3.running_mean, on.running_mean + 1) and vn3.running_mean.item() == 0.5
+    bad = {"model": dict(ck["model"])}
+    bad["model"]["a2c_network.mu.weight"] = torch.zeros(3, 3)
+    with pytest.raises(ValueError):
+        load_rl_games_checkpoint(bad)
+    del bad["model"]["a2c_network.mu.weight"]
+    with pytest.raises(KeyError):
+        load_rl_games_checkpoint(bad)
+
+
+def test_saved_traj_pkl_and_assignment(tmp_path):
+    from emloco_b200.formats import assign_trajs_to_envs, load_saved_trajs
+    rng = np.random.default_rng(0)
+    d = {i: {"pose": (rng.normal(size=(24, 3)) if i % 3 else None), "traj": rng.normal(size=(101, 3)).cumsum(0)} for i in range(20)}
+    p = os.path.join(tmp_path, "jta_trajs.pkl")
+    with open(p, "wb") as f:
+        pickle.dump(d, f)
+    traj, pose, ids = load_saved_trajs(p)
+    assert traj.shape == (20, 101, 3) and pose.shape == (20, 24, 3) and ids == list(range(20))
+    assert np.isnan(pose[0]).all() and not np.isnan(pose[1]).any()
+    np.testing.assert_allclose(traj[5], d[5]["traj"].astype(np.float32))
+    xy = rng.uniform(50, 58, (8, 2))
+    verts, rid = assign_trajs_to_envs(traj, xy, np.random.default_rng(1))
+    assert verts.shape == (8, 101, 3) and len(set(rid.tolist())) == 8
+    np.testing.assert_allclose(verts[:, 0, :2], xy, atol=1e-5)                         # starts at the env's root
+    np.testing.assert_allclose(verts[:, 1:, :2] - verts[:, :1, :2], traj[rid][:, 1:, :2] - traj[rid][:, :1, :2], atol=1e-4)
+    with pytest.raises(ValueError):
+        assign_trajs_to_envs(traj, rng.uniform(50, 58, (30, 2)), np.random.default_rng(1))
+    with pytest.raises(ValueError):
+        load_saved_trajs({0: {"pose": None, "traj": np.zeros((50, 3))}})
+
+
+def test_filter_modes_matches_reference_loop():
+    from emloco_b200.formats import filter_modes
+    rng = np.random.default_rng(3)
+    v = rng.uniform(0, 1, (200, 5)); v[:10] *= 0.5                                     # some scenes with no mode above threshold
+    keep = filter_modes(torch.from_numpy(v), 0.7).numpy()
+    for s in range(v.shape[0]):                                                        # evaluate_jta.py:316-340
+        filt = [m for m in range(5) if v[s, m] >= 0.7]
+        if not filt:
+            filt = [int(np.argmax(v[s]))]
+        assert sorted(np.nonzero(keep[s])[0].tolist()) == filt

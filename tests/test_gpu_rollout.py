@@ -224,3 +224,59 @@ def test_vec_env_surface_matches_reference_adapter_contract():
     o, r, d, _ = env2.step(torch.zeros(8, 69))
     assert not o.is_cuda and not r.is_cuda and not d.is_cuda
     env.close(); env2.close()
+
+
+def test_gym_shim_tensor_api():
+    """The gymapi / gymtorch subset: acquire -> wrap aliases sim memory, PD targets + simulate x2 advance the
+    state exactly like one fused emloco_step, indexed state sets re-read the aliases."""
+    from emloco_b200 import gym_shim as G
+    from emloco_b200.sim import EmlocoSim
+    n = 40
+    gym = G.acquire_gym()
+    sim = gym.create_sim(0, num_envs=n, sim_params=G.SimParams())
+    gym.prepare_sim(sim)
+    root = G.wrap_tensor(gym.acquire_actor_root_state_tensor(sim))
+    dof = G.wrap_tensor(gym.acquire_dof_state_tensor(sim))
+    rb = G.wrap_tensor(gym.acquire_rigid_body_state_tensor(sim))
+    assert root.shape == (n, 13) and dof.shape == (n * 69, 2) and rb.shape == (n * 24, 13)
+    assert root.data_ptr() == sim.root_state.data_ptr()                      # alias, not a copy
+    root[:, 2] = 1.5; root[:, 6] = 1.0
+    ids = torch.arange(n, dtype=torch.int32, device="cuda")
+    gym.set_actor_root_state_tensor_indexed(sim, G.unwrap_tensor(root), G.unwrap_tensor(ids), n)
+    gym.set_dof_state_tensor_indexed(sim, G.unwrap_tensor(dof), G.unwrap_tensor(ids), n)
+    torch.cuda.synchronize()
+    assert torch.allclose(rb.view(n, 24, 13)[:, 0, 2], torch.full((n,), 1.5, device="cuda"))
+    # reference sequence: set targets, simulate x controlFrequencyInv, fetch  ==  one emloco_step with the matching actions
+    ref = EmlocoSim(n)
+    ref.root_state.copy_(root); ref.reset_indexed(None)
+    act = torch.rand(n, 69, device="cuda") * 0.2 - 0.1
+    ref.step(act)
+    gym.set_dof_position_target_tensor(sim, G.unwrap_tensor(ref.pd_target.clone()))
+    for _ in range(2):
+        gym.simulate(sim)
+    gym.fetch_results(sim, True)
+    gym.refresh_rigid_body_state_tensor(sim)
+    np.testing.assert_allclose(rb.cpu().numpy(), ref.rb_state.cpu().numpy(), rtol=1e-4, atol=1e-5)
+    with pytest.raises(Exception):
+        G.unwrap_tensor(torch.zeros(4, 4, device="cuda").t())
+    assert gym.get_asset_dof_count() == 69 and gym.find_actor_rigid_body_handle(sim, name="Head") == 13
+    gym.destroy_sim(sim); ref.close()
+
+
+def test_batched_locoval_filter_equals_batch_of_one_loop():
+    """evaluate_jta.py:298-340: S scenes x M modes scored in one launch == the batch-of-1 loop, then the same filter."""
+    from emloco_b200.formats import score_and_filter
+    from emloco_b200.value_pose_net import ValuePoseNet
+    torch.manual_seed(0)
+    S, M = 300, 5
+    net = ValuePoseNet(True, True).cuda().eval()
+    trajs = (torch.randn(S, M, 13, 2, device="cuda") * 0.4).cumsum(2); trajs[:, :, 0] = 0
+    pose = torch.randn(S, 24, 3, device="cuda") * 0.3
+    vel = torch.randn(S, 2, device="cuda")
+    values, keep = score_and_filter(net, trajs, pose, vel, threshold=0.5)
+    assert values.shape == (S, M) and keep.shape == (S, M) and keep.any(1).all()
+    for s in range(0, S, 37):
+        for m in range(M):
+            v, _ = net.calc_embodied_motion_loss(trajs[s, m][None].contiguous(), pose[s][None].clone(), vel[s][None].clone())
+            assert abs(v.item() - values[s, m].item()) < 2e-4          # batch-of-1 goes to the CUDA-core kernel, the batch to tcgen05
+    assert net.mutate_pose is True
