@@ -369,7 +369,50 @@ int emloco_rollout_record(const emloco_rollout_cfg* c, const float* d_rew, const
     P.N = N; P.inv_penalty = c->inversion_penalty_scale; P.reward_scale = c->reward_scale; P.v_mean = c->value_mean;
     P.v_std = c->value_std; P.disc_scale = c->disc_reward_scale; P.gamma = c->gamma; P.step_to_pred = (float)c->step_to_pred;
     P.unnorm_value = c->unnorm_value;
+    P.c_value_raw = nullptr; P.c_idx = nullptr; P.c_count = nullptr; P.prev_dones = nullptr; P.prev_next_values = nullptr;
     CK(eml_rollout_record(P, (cudaStream_t)stream), "rollout record");
+    return EMLOCO_OK;
+}
+
+int emloco_rollout_record_deferred(const emloco_rollout_cfg* c, const float* d_rew, const int64_t* d_reset, const int64_t* d_terminate,
+                                   const float* d_value_raw, const float* d_disc_logit, const uint8_t* d_inverted, float* d_mb_values,
+                                   float* d_mb_rewards, float* d_mb_dones, float* d_mb_next_values, float* d_mb_amp_rewards,
+                                   float* d_state, int64_t N, const float* d_c_value_raw, const int32_t* d_c_idx,
+                                   const int32_t* d_c_count, const float* d_prev_dones, float* d_prev_next_values, void* stream) {
+    if (!c || !d_rew || !d_reset || !d_terminate || !d_value_raw || !d_disc_logit || !d_mb_values || !d_mb_rewards || !d_mb_dones ||
+        !d_mb_next_values || !d_state || N < 0 || !d_c_value_raw || !d_c_idx || !d_c_count || ((d_prev_dones == nullptr) != (d_prev_next_values == nullptr)))
+        return fail(EMLOCO_EINVAL, "emloco_rollout_record_deferred: bad argument");
+    RecordParams P;
+    P.rew = d_rew; P.reset = d_reset; P.terminate = d_terminate; P.value_raw = d_value_raw; P.mb_values = d_mb_values;
+    P.next_value_raw = nullptr; P.disc_logit = d_disc_logit; P.inverted = d_inverted;
+    P.mb_rewards = d_mb_rewards; P.mb_dones = d_mb_dones; P.mb_next_values = d_mb_next_values; P.mb_amp_rewards = d_mb_amp_rewards;
+    P.current_rewards = d_state; P.current_lengths = d_state + N; P.current_combined = d_state + 2 * N;
+    P.discount_coefs = d_state + 3 * N; P.game_combined = d_state + 4 * N; P.terminated_flags = d_state + 5 * N;
+    P.N = N; P.inv_penalty = c->inversion_penalty_scale; P.reward_scale = c->reward_scale; P.v_mean = c->value_mean;
+    P.v_std = c->value_std; P.disc_scale = c->disc_reward_scale; P.gamma = c->gamma; P.step_to_pred = (float)c->step_to_pred;
+    P.unnorm_value = c->unnorm_value;
+    P.c_value_raw = d_c_value_raw; P.c_idx = d_c_idx; P.c_count = d_c_count; P.prev_dones = d_prev_dones; P.prev_next_values = d_prev_next_values;
+    CK(eml_rollout_record(P, (cudaStream_t)stream), "rollout record (deferred next values)");
+    return EMLOCO_OK;
+}
+
+int emloco_fill_next_values(const emloco_rollout_cfg* c, const float* d_value_raw, const float* d_prev_dones, float* d_prev_next_values,
+                            int64_t N, void* stream) {
+    if (!c || !d_value_raw || !d_prev_dones || !d_prev_next_values || N < 0) return fail(EMLOCO_EINVAL, "emloco_fill_next_values: bad argument");
+    CK(eml_fill_next_values(d_value_raw, d_prev_dones, d_prev_next_values, N, c->value_mean, c->value_std, c->unnorm_value,
+                            (cudaStream_t)stream), "fill next values");
+    return EMLOCO_OK;
+}
+
+int emloco_timeout_gather(const int64_t* d_reset, const int64_t* d_terminate, int64_t N, const uint16_t* self_hi, const uint16_t* self_lo,
+                          int64_t ld_self, const uint16_t* task_hi, const uint16_t* task_lo, int64_t ld_task, uint16_t* c_self_hi,
+                          uint16_t* c_self_lo, int64_t ld_cself, uint16_t* c_task_hi, uint16_t* c_task_lo, int64_t ld_ctask, int32_t* d_idx,
+                          int32_t* d_count, void* stream) {
+    if (!d_reset || !d_terminate || !self_hi || !self_lo || !task_hi || !task_lo || !c_self_hi || !c_self_lo || !c_task_hi || !c_task_lo ||
+        !d_idx || !d_count || N < 0 || (ld_self & 7) || (ld_task & 7) || (ld_cself & 7) || (ld_ctask & 7) || ld_ctask < ld_task)
+        return fail(EMLOCO_EINVAL, "emloco_timeout_gather: bad argument");
+    CK(eml_timeout_gather(d_reset, d_terminate, N, self_hi, self_lo, ld_self, task_hi, task_lo, ld_task, c_self_hi, c_self_lo, ld_cself,
+                          c_task_hi, c_task_lo, ld_ctask, d_idx, d_count, (cudaStream_t)stream), "timeout gather");
     return EMLOCO_OK;
 }
 
@@ -382,7 +425,7 @@ int emloco_split_bf16(const float* d_x, int64_t ldx, int64_t M, int32_t K, const
     return EMLOCO_OK;
 }
 
-int emloco_linear_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, const uint16_t* w_hi, const uint16_t* w_lo,
+static int linear_bf16x3_impl(const int32_t* d_rows, const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, const uint16_t* w_hi, const uint16_t* w_lo,
                          int64_t ldw, const float* d_bias, int64_t M, int32_t N, int32_t K, int32_t relu, float* d_y32, int64_t ldy,
                          uint16_t* y_hi, uint16_t* y_lo, int64_t ldy16, void* stream) {
     if (!a_hi || !a_lo || !w_hi || !w_lo || M < 0 || N <= 0 || K <= 0 || lda < K || ldw < K || (lda & 7) || (ldw & 7))
@@ -398,8 +441,21 @@ int emloco_linear_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda
     if (tile_n != 0 && (tile_n & 0x7ff) != 128 && (tile_n & 0x7ff) != 256)
         return fail(EMLOCO_EINVAL, "emloco_linear_bf16x3: tile must be 0, 128 or 256 (+0x800 for the CTA-pair kernels)");
     CK(eml_linear_bf16x3(a_hi, a_lo, lda, w_hi, w_lo, ldw, d_bias, M, N, K, relu & 1, d_y32, ldy, y_hi, y_lo, ldy16, tile_n,
-                         (cudaStream_t)stream), "linear bf16x3 (tcgen05)");
+                         d_rows, (cudaStream_t)stream), "linear bf16x3 (tcgen05)");
     return EMLOCO_OK;
+}
+
+int emloco_linear_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, const uint16_t* w_hi, const uint16_t* w_lo,
+                         int64_t ldw, const float* d_bias, int64_t M, int32_t N, int32_t K, int32_t relu, float* d_y32, int64_t ldy,
+                         uint16_t* y_hi, uint16_t* y_lo, int64_t ldy16, void* stream) {
+    return linear_bf16x3_impl(nullptr, a_hi, a_lo, lda, w_hi, w_lo, ldw, d_bias, M, N, K, relu, d_y32, ldy, y_hi, y_lo, ldy16, stream);
+}
+
+int emloco_linear_bf16x3_rows(const int32_t* d_rows, const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, const uint16_t* w_hi,
+                              const uint16_t* w_lo, int64_t ldw, const float* d_bias, int64_t M, int32_t N, int32_t K, int32_t relu,
+                              float* d_y32, int64_t ldy, uint16_t* y_hi, uint16_t* y_lo, int64_t ldy16, void* stream) {
+    if (!d_rows) return fail(EMLOCO_EINVAL, "emloco_linear_bf16x3_rows: null row count");
+    return linear_bf16x3_impl(d_rows, a_hi, a_lo, lda, w_hi, w_lo, ldw, d_bias, M, N, K, relu, d_y32, ldy, y_hi, y_lo, ldy16, stream);
 }
 
 int emloco_normalize(const float* d_x, int64_t ldx, float* d_y, int64_t ldy, int64_t M, int32_t K, const float* d_mean,

@@ -126,6 +126,7 @@ struct GemmArgs {
     float* y32; long long ldy;                       // fp32 output (optional)
     __nv_bfloat16* y_hi; __nv_bfloat16* y_lo; long long ldy16;   // split output (optional; N % 32 == 0)
     int M, N, K, relu;
+    const int* m_dev;        // optional device-side row count (<= M): tiles beyond it are skipped (compacted row sets)
 };
 
 // One 32-column chunk of one accumulator row: +bias, ReLU, then fp32 store and/or bf16 hi/lo split store.
@@ -190,6 +191,7 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_co
     float* s_bias = reinterpret_cast<float*>(smem_gen + T::STAGES * T::STAGE_BYTES + T::BAR_BYTES);   // [2][BN]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (g.m_dev) { const int m = __ldg(g.m_dev); g.M = m < g.M ? m : g.M; }     // uniform: every thread reads the same word
     const int tiles_m = (g.M + BM - 1) / BM, tiles_n = (g.N + BN - 1) / BN;
     const int num_tiles = tiles_m * tiles_n;
     const int num_kb = (g.K + BK - 1) / BK;
@@ -384,6 +386,7 @@ linear_bf16x3_2cta_kernel(const __grid_constant__ CUtensorMap map_ah, const __gr
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
+    if (g.m_dev) { const int m = __ldg(g.m_dev); g.M = m < g.M ? m : g.M; }
     const int tiles_m = (g.M + 2 * BM - 1) / (2 * BM), tiles_n = (g.N + BN - 1) / BN;
     const int num_tiles = tiles_m * tiles_n;
     const int num_kb = (g.K + BK - 1) / BK;
@@ -624,9 +627,10 @@ cudaError_t eml_split_bf16(const float* x, long long ldx, long long M, int K, co
 
 cudaError_t eml_linear_bf16x3(const void* a_hi, const void* a_lo, long long lda, const void* w_hi, const void* w_lo, long long ldw,
                               const float* bias, long long M, int N, int K, int relu, float* y32, long long ldy, void* y_hi,
-                              void* y_lo, long long ldy16, int tile_n, cudaStream_t st) {
+                              void* y_lo, long long ldy16, int tile_n, const int* m_dev, cudaStream_t st) {
     if (M <= 0 || N <= 0) return cudaSuccess;
     tc::GemmArgs g;
+    g.m_dev = m_dev;
     g.bias = bias; g.y32 = y32; g.ldy = ldy; g.y_hi = (__nv_bfloat16*)y_hi; g.y_lo = (__nv_bfloat16*)y_lo; g.ldy16 = ldy16;
     g.M = (int)M; g.N = N; g.K = K; g.relu = relu;
     // tile choice: the 128 x 256 tile does 1.33x the flops per operand byte, but needs enough tiles to fill the 148 SMs
@@ -660,7 +664,7 @@ cudaError_t eml_linear_tc(const float* x, long long ldx, const float* w, const f
     __nv_bfloat16 *ah = scratch, *al = ah + M * kp, *wh = al + M * kp, *wl = wh + (long long)N * kp;
     if ((e = eml_split_bf16(x, ldx, M, K, mean, var, eps, ah, al, kp, st)) == cudaSuccess &&
         (e = eml_split_bf16(w, K, N, K, nullptr, nullptr, 0.f, wh, wl, kp, st)) == cudaSuccess)
-        e = eml_linear_bf16x3(ah, al, kp, wh, wl, kp, b, M, N, K, relu, y, ldy, nullptr, nullptr, 0, 0, st);
+        e = eml_linear_bf16x3(ah, al, kp, wh, wl, kp, b, M, N, K, relu, y, ldy, nullptr, nullptr, 0, 0, nullptr, st);
     cudaError_t e2 = cudaFreeAsync(scratch, st);
     return e != cudaSuccess ? e : e2;
 }

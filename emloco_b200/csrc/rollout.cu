@@ -69,16 +69,33 @@ __global__ void rollout_record_kernel(RecordParams P) {
     float shaped = r * P.reward_scale;                                    // rewards_shaper (scale_value 1)
     float done = P.reset[i] != 0 ? 1.0f : 0.0f;
     float term = (float)P.terminate[i];
-    float nv = P.next_value_raw[i];
-    if (P.unnorm_value) nv = P.v_std * fminf(fmaxf(nv, -5.0f), 5.0f) + P.v_mean;   // running_mean_std.py:77-79
+    float v_now = 0.f;
     if (P.value_raw) {                                                    // res_dict['values'] of get_action_values
-        float v = P.value_raw[i];
-        if (P.unnorm_value) v = P.v_std * fminf(fmaxf(v, -5.0f), 5.0f) + P.v_mean;
-        P.mb_values[i] = v;
+        v_now = P.value_raw[i];
+        if (P.unnorm_value) v_now = P.v_std * fminf(fmaxf(v_now, -5.0f), 5.0f) + P.v_mean;   // running_mean_std.py:77-79
+        P.mb_values[i] = v_now;
     }
-    nv *= (1.0f - term);                                                  // :86-90
+    const bool deferred = P.next_value_raw == nullptr;
+    float nv = 0.f;
+    if (!deferred) {
+        nv = P.next_value_raw[i];
+        if (P.unnorm_value) nv = P.v_std * fminf(fmaxf(nv, -5.0f), 5.0f) + P.v_mean;
+        nv *= (1.0f - term);                                              // :86-90
+    } else {
+        // value reuse: critic(next obs) of an env that is NOT reset equals the critic output of the next step's policy pass
+        // on the very same observation row - it is filled then.  Complete step n-1 now:
+        if (P.prev_next_values && P.prev_dones[i] == 0.0f) P.prev_next_values[i] = v_now;
+        // timed-out envs (reset without termination) were evaluated by the compact critic pass on their terminal observation
+        if (P.c_count && i < (long long)*P.c_count) {
+            float cv = P.c_value_raw[i];
+            if (P.unnorm_value) cv = P.v_std * fminf(fmaxf(cv, -5.0f), 5.0f) + P.v_mean;
+            P.mb_next_values[P.c_idx[i]] = cv;                           // these envs have term == 0
+        }
+    }
     float amp = disc_r(P.disc_logit[i], P.disc_scale);                    // :93
-    P.mb_rewards[i] = shaped; P.mb_dones[i] = done; P.mb_next_values[i] = nv;
+    P.mb_rewards[i] = shaped; P.mb_dones[i] = done;
+    if (!deferred) P.mb_next_values[i] = nv;
+    else if (term != 0.0f) P.mb_next_values[i] = 0.f;                     // next_vals *= 1 - terminated
     if (P.mb_amp_rewards) P.mb_amp_rewards[i] = amp;
     P.terminated_flags[i] += term;
     // ---- LocoVal target bookkeeping (:94-118) ----
@@ -118,5 +135,58 @@ cudaError_t eml_normalize(const float* x, long long ldx, float* y, long long ldy
                           const float* var, float eps, cudaStream_t st) {
     if (M <= 0 || K <= 0) return cudaSuccess;
     normalize_kernel<<<(unsigned)((M * K + 255) / 256), 256, 0, st>>>(x, ldx, y, ldy, M, K, mean, var, eps);
+    return cudaGetLastError();
+}
+
+// ---- value reuse: compact the envs that were reset WITHOUT terminating (episode time-out) and gather their critic operands ----
+// One warp per env; rows keep their 16-byte chunks.  `count` is zeroed by the launcher (memset node) before the kernel runs.
+__global__ void timeout_gather_kernel(const int64_t* __restrict__ reset, const int64_t* __restrict__ terminate, long long N,
+                                      const uint4* __restrict__ self_hi, const uint4* __restrict__ self_lo, int self_ld4,
+                                      const uint4* __restrict__ task_hi, const uint4* __restrict__ task_lo, int task_ld4,
+                                      uint4* c_self_hi, uint4* c_self_lo, int cself_ld4, uint4* c_task_hi, uint4* c_task_lo, int ctask_ld4,
+                                      int32_t* idx, int32_t* count) {
+    const long long env = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (env >= N) return;
+    if (reset[env] == 0 || terminate[env] != 0) return;                  // warp-uniform
+    int slot = 0;
+    if (lane == 0) { slot = atomicAdd(count, 1); idx[slot] = (int32_t)env; }
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    for (int i = lane; i < EML_SELF_OBS / 8; i += 32) {                   // 368 bf16 = 46 chunks of 16 bytes
+        c_self_hi[(long long)slot * cself_ld4 + i] = self_hi[env * self_ld4 + i];
+        c_self_lo[(long long)slot * cself_ld4 + i] = self_lo[env * self_ld4 + i];
+    }
+    for (int i = lane; i < task_ld4; i += 32) {                           // whole padded pitch of the task row
+        c_task_hi[(long long)slot * ctask_ld4 + i] = task_hi[env * task_ld4 + i];
+        c_task_lo[(long long)slot * ctask_ld4 + i] = task_lo[env * task_ld4 + i];
+    }
+}
+
+cudaError_t eml_timeout_gather(const int64_t* reset, const int64_t* terminate, long long N, const uint16_t* self_hi,
+                               const uint16_t* self_lo, long long ld_self, const uint16_t* task_hi, const uint16_t* task_lo,
+                               long long ld_task, uint16_t* c_self_hi, uint16_t* c_self_lo, long long ld_cself, uint16_t* c_task_hi,
+                               uint16_t* c_task_lo, long long ld_ctask, int32_t* idx, int32_t* count, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(count, 0, sizeof(int32_t), st);
+    if (e != cudaSuccess || N <= 0) return e;
+    timeout_gather_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(
+        reset, terminate, N, (const uint4*)self_hi, (const uint4*)self_lo, (int)(ld_self / 8), (const uint4*)task_hi, (const uint4*)task_lo,
+        (int)(ld_task / 8), (uint4*)c_self_hi, (uint4*)c_self_lo, (int)(ld_cself / 8), (uint4*)c_task_hi, (uint4*)c_task_lo, (int)(ld_ctask / 8),
+        idx, count);
+    return cudaGetLastError();
+}
+
+// next_values of step n-1 for the envs that were not reset: this step's (un-normalised) critic output
+__global__ void fill_next_values_kernel(const float* __restrict__ value_raw, const float* __restrict__ prev_dones,
+                                        float* __restrict__ prev_next_values, long long N, float v_mean, float v_std, int unnorm) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N || prev_dones[i] != 0.0f) return;
+    float v = value_raw[i];
+    if (unnorm) v = v_std * fminf(fmaxf(v, -5.0f), 5.0f) + v_mean;
+    prev_next_values[i] = v;
+}
+cudaError_t eml_fill_next_values(const float* value_raw, const float* prev_dones, float* prev_next_values, long long N, float v_mean,
+                                 float v_std, int unnorm, cudaStream_t st) {
+    if (N <= 0) return cudaSuccess;
+    fill_next_values_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(value_raw, prev_dones, prev_next_values, N, v_mean, v_std, unnorm);
     return cudaGetLastError();
 }

@@ -78,6 +78,10 @@ struct RecordParams {
     long long N;
     float inv_penalty, reward_scale, v_mean, v_std, disc_scale, gamma, step_to_pred;
     int unnorm_value;
+    // deferred next-values (value reuse): next_value_raw == NULL.  Terminated envs get 0 now, timed-out envs (reset, not
+    // terminated) get the compact critic's value now, the others are filled one step later from that step's value_raw
+    const float* c_value_raw; const int32_t* c_idx; const int32_t* c_count;   // compact critic outputs
+    const float* prev_dones; float* prev_next_values;                          // step n-1 rows to complete (or NULL)
 };
 
 // kernel launchers (defined in the .cu files)
@@ -98,4 +102,10 @@ cudaError_t eml_split_bf16(const float* x, long long ldx, long long M, int K, co
                            void* hi, void* lo, long long ld16, cudaStream_t st);
 cudaError_t eml_linear_bf16x3(const void* a_hi, const void* a_lo, long long lda, const void* w_hi, const void* w_lo, long long ldw,
                               const float* bias, long long M, int N, int K, int relu, float* y32, long long ldy, void* y_hi,
-                              void* y_lo, long long ldy16, int tile_n, cudaStream_t st);
+                              void* y_lo, long long ldy16, int tile_n, const int* m_dev, cudaStream_t st);
+cudaError_t eml_timeout_gather(const int64_t* reset, const int64_t* terminate, long long N, const uint16_t* self_hi,
+                               const uint16_t* self_lo, long long ld_self, const uint16_t* task_hi, const uint16_t* task_lo,
+                               long long ld_task, uint16_t* c_self_hi, uint16_t* c_self_lo, long long ld_cself, uint16_t* c_task_hi,
+                               uint16_t* c_task_lo, long long ld_ctask, int32_t* idx, int32_t* count, cudaStream_t st);
+cudaError_t eml_fill_next_values(const float* value_raw, const float* prev_dones, float* prev_next_values, long long N, float v_mean,
+                                 float v_std, int unnorm, cudaStream_t st);

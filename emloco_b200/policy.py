@@ -139,6 +139,7 @@ class RolloutNets:
             self.amp_slots = int(amp_slots)
             self.s_amp = _Split(M * self.amp_slots, AMP_OBS, dev)
             self._all = None
+            self._cc = None
             self.w16 = _TcWeights()
 
     def _w_ac1(self):
@@ -257,6 +258,32 @@ class RolloutNets:
         self._lin(self.c2, n.value, False, self.next_value)
         return self.next_value
 
+    def critic_timeouts(self, reset, terminate):
+        """The critic on the terminal observation of the envs that were reset WITHOUT terminating (episode time-out) - the
+        only envs whose `_eval_critic(next obs)` is not the next step's own critic output (emloco_timeout_gather).  Uses the
+        operands the post-step sinks left in s_ain / s_tin.  -> (values [M,1] (rows 0..count-1 valid), idx int32 [M], count int32 [1])."""
+        n, W, M = self.net, self.w16.get, self.M
+        if self._cc is None:
+            dev = reset.device
+            S = lambda k: _Split(M, k, dev)
+            h = n.critic_mlp[0].out_features
+            self._cc = dict(ain=S(SELF_OBS + n._task_mlp[2].out_features), tin=S(TASK_OBS), t1=S(n._task_mlp[0].out_features), c1=S(h),
+                            c2=S(n.critic_mlp[2].out_features), val=torch.zeros(M, 1, device=dev),
+                            idx=torch.zeros(M, dtype=torch.int32, device=dev), count=torch.zeros(1, dtype=torch.int32, device=dev))
+        c = self._cc
+        _lib.check(_lib.load().emloco_timeout_gather(
+            _ptr(reset), _ptr(terminate), M, _ptr(self.s_ain.hi), _ptr(self.s_ain.lo), self.s_ain.ld, _ptr(self.s_tin.hi),
+            _ptr(self.s_tin.lo), self.s_tin.ld, _ptr(c["ain"].hi), _ptr(c["ain"].lo), c["ain"].ld, _ptr(c["tin"].hi), _ptr(c["tin"].lo),
+            c["tin"].ld, _ptr(c["idx"]), _ptr(c["count"]), _stream()), "emloco_timeout_gather")
+        r = c["count"]
+        linear_bf16x3(c["tin"], W("t0", n._task_mlp[0].weight), n._task_mlp[0].bias.detach(), True, y16=c["t1"], rows=r)
+        linear_bf16x3(c["t1"], W("t2", n._task_mlp[2].weight), n._task_mlp[2].bias.detach(), True,
+                      y16=c["ain"].cols(SELF_OBS, c["ain"].K), rows=r)
+        linear_bf16x3(c["ain"], W("c0", n.critic_mlp[0].weight), n.critic_mlp[0].bias.detach(), True, y16=c["c1"], rows=r)
+        linear_bf16x3(c["c1"], W("c2", n.critic_mlp[2].weight), n.critic_mlp[2].bias.detach(), True, y16=c["c2"], rows=r)
+        linear_bf16x3(c["c2"], W("value", n.value.weight), n.value.bias.detach(), False, y32=c["val"], rows=r)
+        return c["val"], c["idx"], c["count"]
+
     def disc_logits_all(self, out):
         """The discriminator over the operands of ALL slots at once (rows = M * amp_slots): out [M*amp_slots, 1]."""
         n, W, rows = self.net, self.w16.get, self.M * self.amp_slots
@@ -324,17 +351,21 @@ def split_bf16(x, dst: _Split, mean=None, var=None, eps=1e-5):
     return dst
 
 
-def linear_bf16x3(a: _Split, w: _Split, bias, relu, y32=None, y16: _Split = None, tile=0):
+def linear_bf16x3(a: _Split, w: _Split, bias, relu, y32=None, y16: _Split = None, tile=0, rows=None):
     """y = act(a w^T + bias) on the tcgen05 path; fp32 output and/or split output for the next layer.
-    tile: 0 = library picks the output-tile width, 128 / 256 = forced."""
+    tile: 0 = library picks the output-tile width, 128 / 256 = forced.
+    rows: optional int32 device scalar - only that many leading rows are valid (compacted row sets)."""
     M, K, N = a.rows, a.K, w.rows
     assert w.K == K
     if y32 is not None:
         assert y32.shape == (M, N) and y32.stride(1) == 1
-    _lib.check(_lib.load().emloco_linear_bf16x3(
-        _ptr(a.hi), _ptr(a.lo), a.ld, _ptr(w.hi), _ptr(w.lo), w.ld, _ptr(bias), M, N, K, int(bool(relu)) | (int(tile) << 8),
-        _ptr(y32), 0 if y32 is None else y32.stride(0), None if y16 is None else _ptr(y16.hi),
-        None if y16 is None else _ptr(y16.lo), 0 if y16 is None else y16.ld, _stream()), "emloco_linear_bf16x3")
+    args = (_ptr(a.hi), _ptr(a.lo), a.ld, _ptr(w.hi), _ptr(w.lo), w.ld, _ptr(bias), M, N, K, int(bool(relu)) | (int(tile) << 8),
+            _ptr(y32), 0 if y32 is None else y32.stride(0), None if y16 is None else _ptr(y16.hi),
+            None if y16 is None else _ptr(y16.lo), 0 if y16 is None else y16.ld, _stream())
+    if rows is None:
+        _lib.check(_lib.load().emloco_linear_bf16x3(*args), "emloco_linear_bf16x3")
+    else:
+        _lib.check(_lib.load().emloco_linear_bf16x3_rows(_ptr(rows), *args), "emloco_linear_bf16x3_rows")
 
 
 class _TcWeights:

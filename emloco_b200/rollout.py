@@ -32,7 +32,7 @@ class Rollout:
     def __init__(self, num_envs, device=0, horizon=32, seed=0, tensor_cores=False, gamma=0.99, tau=0.95,
                  task_reward_w=0.5, disc_reward_w=0.5, disc_reward_scale=2.0, inversion_penalty_scale=0.3,
                  step_to_pred=144, normalize_value=True, net=None, obs_norm=None, amp_norm=None, value_norm=None,
-                 recompute_disc=True, valuenet=None, fuse_sinks=True, concurrent=True):
+                 recompute_disc=True, valuenet=None, fuse_sinks=True, concurrent=True, reuse_values=False):
         self.N, self.T, self.device = int(num_envs), int(horizon), int(device)
         self.gamma, self.tau = gamma, tau
         self.task_reward_w, self.disc_reward_w, self.disc_reward_scale = task_reward_w, disc_reward_w, disc_reward_scale
@@ -50,6 +50,8 @@ class Rollout:
         self.nets = RolloutNets(self.net, self.obs_norm, self.amp_norm, self.N, tensor_cores=tensor_cores, concurrent=concurrent,
                                 amp_slots=self.T if (tensor_cores and recompute_disc) else 1)
         self.concurrent = bool(concurrent)
+        # value reuse needs the operand sinks (the compact critic reads the rows the post-step kernel wrote)
+        self.reuse_values = bool(reuse_values) and bool(tensor_cores) and bool(fuse_sinks)
         self.gen = torch.Generator(device=dev).manual_seed(seed + 1)
 
         # synthetic initial state + JTA-shaped trajectories; rank-local seed like run.py:65
@@ -161,13 +163,40 @@ class Rollout:
                 sim.post_step(True)
                 mb["amp_obs"][n].copy_(sim.amp_obs.view(self.N, AMP_OBS))
 
+        # value reuse: critic(next obs) is NOT recomputed for envs that are not reset - the next step's policy pass evaluates
+        # the critic on that very observation; only timed-out envs need their terminal observation evaluated now.  The last
+        # step of the horizon has no next step inside the horizon and runs the full pass.
+        reuse = self.reuse_values and fuse and n < self.T - 1
+
         def seg_critic():                                                              # _eval_critic(next obs), :85
-            cur["nv"] = nets.critic(sim.obs, operands_ready=fuse)
+            if reuse:
+                cur["cval"], cur["cidx"], cur["ccount"] = nets.critic_timeouts(sim.reset, sim.terminate)
+            else:
+                cur["nv"] = nets.critic(sim.obs, operands_ready=fuse)
 
         def seg_disc():                                                                # _calc_amp_rewards, :93
             cur["logit"] = nets.disc_logits(sim.amp_obs.view(self.N, AMP_OBS), operands_ready=fuse, slot=slot)
 
         def seg_record():
+            if reuse:
+                # deferred next values: terminated -> 0, timed-out -> compact critic, the rest is completed by step n+1;
+                # this step's critic output (policy pass) completes step n-1
+                prev = n > 0
+                _lib.check(_lib.load().emloco_rollout_record_deferred(
+                    C.byref(self.rcfg), _ptr(sim.rew), _ptr(sim.reset), _ptr(sim.terminate), _ptr(cur["res"]["values"]),
+                    _ptr(cur["logit"]), None, _ptr(mb["values"][n]), _ptr(mb["rewards"][n]), _ptr(mb["dones"][n]),
+                    _ptr(mb["next_values"][n]), _ptr(mb["amp_rewards"][n]), _ptr(self.state), self.N, _ptr(cur["cval"]),
+                    _ptr(cur["cidx"]), _ptr(cur["ccount"]), _ptr(mb["dones"][n - 1]) if prev else None,
+                    _ptr(mb["next_values"][n - 1]) if prev else None, _stream()), "emloco_rollout_record_deferred")
+                return
+            if self.reuse_values and fuse and n > 0:
+                # last step of the horizon (full critic pass below): it still has to complete step n-1
+                _lib.check(_lib.load().emloco_fill_next_values(
+                    C.byref(self.rcfg), _ptr(cur["res"]["values"]), _ptr(mb["dones"][n - 1]), _ptr(mb["next_values"][n - 1]), self.N,
+                    _stream()), "emloco_fill_next_values")
+            seg_record_plain()
+
+        def seg_record_plain():
             # values are un-normalised (get_action_values, normalize_value) together with next_values in the record kernel
             _lib.check(_lib.load().emloco_rollout_record(
                 C.byref(self.rcfg), _ptr(sim.rew), _ptr(sim.reset), _ptr(sim.terminate), _ptr(cur["res"]["values"]),

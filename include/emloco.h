@@ -255,6 +255,36 @@ int emloco_linear_bf16x3(const uint16_t* d_a_hi, const uint16_t* d_a_lo, int64_t
                          int32_t relu, float* d_y32, int64_t ldy, uint16_t* d_y_hi, uint16_t* d_y_lo, int64_t ldy16,
                          void* stream);
 
+/* emloco_linear_bf16x3 over a COMPACTED row set: *d_rows (device, <= M) rows are valid, output tiles beyond it are skipped. */
+int emloco_linear_bf16x3_rows(const int32_t* d_rows, const uint16_t* d_a_hi, const uint16_t* d_a_lo, int64_t lda,
+                              const uint16_t* d_w_hi, const uint16_t* d_w_lo, int64_t ldw, const float* d_bias, int64_t M,
+                              int32_t N, int32_t K, int32_t relu, float* d_y32, int64_t ldy, uint16_t* d_y_hi, uint16_t* d_y_lo,
+                              int64_t ldy16, void* stream);
+
+/* ---- value reuse (optional): `_eval_critic(next obs)` of play_steps (amp_continuous_value.py:85-90) without a second full
+ * critic pass.  For an env that is not reset, the next observation IS the observation of the following step, whose policy
+ * pass evaluates the critic on it anyway; terminated envs get next_value = 0; only envs reset by the episode time-out
+ * (reset && !terminate, ~N/168 per step) need their terminal observation evaluated.
+ * emloco_timeout_gather compacts those envs: their actor/critic-input and task-MLP operand rows (bf16 hi/lo, as produced
+ * by emloco_set_post_sinks / emloco_split_bf16) are copied to rows 0..count-1 of the c_* buffers, d_idx[i] = env, *d_count.
+ * emloco_rollout_record_deferred is emloco_rollout_record with next values handled as described: terminated -> 0 now,
+ * timed-out -> from the compact critic output d_c_value_raw[i] (env d_c_idx[i]) now, the others one step later
+ * (d_prev_dones / d_prev_next_values = rows of step n-1, completed from this step's d_value_raw; NULL at the first step). */
+int emloco_timeout_gather(const int64_t* d_reset, const int64_t* d_terminate, int64_t N, const uint16_t* d_self_hi,
+                          const uint16_t* d_self_lo, int64_t ld_self, const uint16_t* d_task_hi, const uint16_t* d_task_lo,
+                          int64_t ld_task, uint16_t* d_c_self_hi, uint16_t* d_c_self_lo, int64_t ld_cself, uint16_t* d_c_task_hi,
+                          uint16_t* d_c_task_lo, int64_t ld_ctask, int32_t* d_idx, int32_t* d_count, void* stream);
+int emloco_rollout_record_deferred(const emloco_rollout_cfg* cfg, const float* d_rew, const int64_t* d_reset,
+                                   const int64_t* d_terminate, const float* d_value_raw, const float* d_disc_logit,
+                                   const uint8_t* d_inverted, float* d_mb_values, float* d_mb_rewards, float* d_mb_dones,
+                                   float* d_mb_next_values, float* d_mb_amp_rewards, float* d_state, int64_t N,
+                                   const float* d_c_value_raw, const int32_t* d_c_idx, const int32_t* d_c_count,
+                                   const float* d_prev_dones, float* d_prev_next_values, void* stream);
+
+/* the deferred completion on its own (used at the last step of a horizon, which runs the full critic pass itself). */
+int emloco_fill_next_values(const emloco_rollout_cfg* cfg, const float* d_value_raw, const float* d_prev_dones,
+                            float* d_prev_next_values, int64_t N, void* stream);
+
 /* RunningMeanStd.forward, eval branch (pacer/pacer/utils/running_mean_std.py:82-84): y = clamp((x-mean)/sqrt(var+eps), +-5)
  * on a [M,K] slice with row strides ldx/ldy (the self-obs part of the actor/critic input, amp_network_sept_builder.py:75,95). */
 int emloco_normalize(const float* d_x, int64_t ldx, float* d_y, int64_t ldy, int64_t M, int32_t K, const float* d_mean,

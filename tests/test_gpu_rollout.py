@@ -280,3 +280,40 @@ def test_batched_locoval_filter_equals_batch_of_one_loop():
             v, _ = net.calc_embodied_motion_loss(trajs[s, m][None].contiguous(), pose[s][None].clone(), vel[s][None].clone())
             assert abs(v.item() - values[s, m].item()) < 2e-4          # batch-of-1 goes to the CUDA-core kernel, the batch to tcgen05
     assert net.mutate_pose is True
+
+
+def test_value_reuse_is_bit_identical_to_the_second_critic_pass():
+    """reuse_values: critic(next obs) taken from the next step's policy pass (non-reset envs), 0 (terminated envs) or a compact
+    critic pass over the timed-out envs - every experience tensor must equal the plain two-pass rollout bit for bit.
+    Short episodes (episode_length 6) make time-outs frequent so that the compact path is exercised."""
+    from emloco_b200.policy import AMPSeptValueNetwork
+    from emloco_b200.rollout import Rollout
+    n = 200
+    torch.manual_seed(8)
+    net = AMPSeptValueNetwork()
+    with torch.no_grad():
+        net.value.bias.fill_(0.3)
+    A = Rollout(n, seed=4, net=net, tensor_cores=True, horizon=8, reuse_values=True)
+    B = Rollout(n, seed=4, net=net, tensor_cores=True, horizon=8, reuse_values=False)
+    for R in (A, B):
+        R.sim.close()
+    # same sims but with a 6-step episode so that `reset && !terminate` happens every few steps
+    from emloco_b200.sim import EmlocoSim
+    for R in (A, B):
+        R.sim = EmlocoSim(n, episode_length=6)
+        R.sim.traj_verts.copy_(torch.from_numpy(__import__("emloco_b200.synthetic", fromlist=["x"]).synthetic_env_state(n, seed=4, root_height=R.sim.rest_height)["verts"]).cuda())
+        R.sim.reset.fill_(1)
+        if R.fuse:
+            R.sim.set_post_sinks(R.nets.post_sinks(obs_copy=R.mb["obses"][R.T]))
+        R.sim.reset_done(R.init_root, R.init_dof)
+    assert A.reuse_values and not B.reuse_values
+    timeouts = 0
+    for rep in range(3):
+        oa, ob = A.play_steps(), B.play_steps()
+        torch.cuda.synchronize()
+        d = ob["dones"].cpu().numpy()
+        timeouts += int(d.sum())
+        for key in ("obses", "actions", "values", "next_values", "rewards", "dones", "amp_rewards", "returns", "advantages"):
+            np.testing.assert_array_equal(oa[key].cpu().numpy(), ob[key].cpu().numpy(), err_msg=f"{key} rep {rep}")
+    assert timeouts > 50, "the test must exercise resets"
+    A.close(); B.close()
