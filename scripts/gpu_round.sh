@@ -14,7 +14,7 @@ timeout 300 python bench.py --impl reference --steps 10 --warmup 2 > gpurun_out/
 cat gpurun_out/${TAG}_bench_ref.json
 # ncu launch list of the bench command (cold-cache, serialised: shares only) and one full capture of our top kernels
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 600 -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
-    python bench.py --steps 8 --warmup 32 --no-cpu-baseline --locoval-batch 65536 > gpurun_out/${TAG}_ncu_bench.log 2>&1
+    python bench.py --steps 8 --warmup 32 --no-cpu-baseline --no-variants --locoval-batch 65536 > gpurun_out/${TAG}_ncu_bench.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'physics_kernel|post_step_kernel|linear_fma_kernel|locoval_kernel|linear_tc' \
-    -s 200 -c 24 -o gpurun_out/${TAG}_prof python bench.py --steps 4 --warmup 8 --no-cpu-baseline --locoval-batch 1048576 > gpurun_out/${TAG}_ncu_full.log 2>&1
+    -s 200 -c 24 -o gpurun_out/${TAG}_prof python bench.py --steps 4 --warmup 8 --no-cpu-baseline --no-variants --locoval-batch 1048576 > gpurun_out/${TAG}_ncu_full.log 2>&1
 ls -la gpurun_out/
