@@ -39,13 +39,17 @@ struct PostParams {
 // normalise like RunningMeanStd.forward (utils/running_mean_std.py:82-84) and split into bf16 hi + lo (csrc/linear_tc.cu)
 __device__ __forceinline__ void norm_split2(float x0, float x1, const float* __restrict__ mean, const float* __restrict__ inv_std,
                                             int k, uint32_t& hi, uint32_t& lo) {
-    float a = fminf(fmaxf((x0 - __ldg(mean + k)) * __ldg(inv_std + k), -5.0f), 5.0f);
-    float b = fminf(fmaxf((x1 - __ldg(mean + k + 1)) * __ldg(inv_std + k + 1), -5.0f), 5.0f);
-    __nv_bfloat16 h0 = __float2bfloat16_rn(a), h1 = __float2bfloat16_rn(b);
-    __nv_bfloat16 l0 = __float2bfloat16_rn(a - __bfloat162float(h0)), l1 = __float2bfloat16_rn(b - __bfloat162float(h1));
-    hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    const float2 m = __ldg(reinterpret_cast<const float2*>(mean + k)), is = __ldg(reinterpret_cast<const float2*>(inv_std + k));   // k even
+    const float a = fminf(fmaxf((x0 - m.x) * is.x, -5.0f), 5.0f), b = fminf(fmaxf((x1 - m.y) * is.y, -5.0f), 5.0f);
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);                 // packed conversions: one F2FP per pair
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+    lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+
+// mirrored observation (humanoid.py:1066-1108, ..terrain.py:455-491) as a gather: flip_obs[i] = +-obs[src(i)];
+// entry = src | (negate << 15), built once on the host from the left/right body permutation
+__device__ uint16_t g_flip_src[EML_OBS];
 
 // Terrain.world_points_to_map + sample (..terrain.py:1212-1218,1282-1288); fp32 division and
 // truncation exactly as torch does on the host path.
@@ -248,21 +252,9 @@ __global__ void __launch_bounds__(PS_THREADS) post_step_kernel(PostParams P) {
         float2* f = reinterpret_cast<float2*>(P.flip_obs + (size_t)env * EML_OBS);
         for (int i2 = tid; i2 < EML_OBS / 2; i2 += PS_THREADS) {
             o[i2] = reinterpret_cast<const float2*>(s_obs)[i2];
-            float v[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                int i = 2 * i2 + u;
-                float r;
-                if (i < 69) { int b = i / 3 + 1, c = i % 3; r = s_obs[(c_l2r[b] - 1) * 3 + c]; if (c == 1) r = -r; }
-                else if (i < 213) { int j = i - 69, b = j / 6, c = j % 6; r = s_obs[69 + c_l2r[b] * 6 + c]; if (c % 3 == 1) r = -r; }
-                else if (i < 285) { int j = i - 213, b = j / 3, c = j % 3; r = s_obs[213 + c_l2r[b] * 3 + c]; if (c == 1) r = -r; }
-                else if (i < 357) { int j = i - 285, b = j / 3, c = j % 3; r = s_obs[285 + c_l2r[b] * 3 + c]; if (c != 1) r = -r; }
-                else if (i < 368) { r = s_obs[i]; }
-                else if (i < 398) { r = s_obs[i]; if ((i - 368) & 1) r = -r; }
-                else { int j = i - 398; r = s_obs[398 + (j & ~31) + (31 - (j & 31))]; }
-                v[u] = r;
-            }
-            f[i2] = make_float2(v[0], v[1]);
+            const uint32_t e = __ldg(reinterpret_cast<const uint32_t*>(g_flip_src) + i2);      // two table entries
+            const float r0 = s_obs[e & 0x7fffu], r1 = s_obs[(e >> 16) & 0x7fffu];
+            f[i2] = make_float2((e & 0x8000u) ? -r0 : r0, (e & 0x80000000u) ? -r1 : r1);
         }
         // optional sinks of the same observation row: experience row, and the normalised bf16 hi/lo operands the
         // tensor-core layers read (self-obs part -> actor/critic input, task-obs part -> task MLP input)
@@ -326,6 +318,22 @@ static cudaError_t launch_post(emloco_sim* s, int advance_progress, int reset_mo
         for (int i = 0; i < 3; ++i) { cx[i] = (float)(-0.1 + sx * i); cy[i] = (float)(-0.2 + sy * i); }
         cx[2] = 0.1f; cy[2] = 0.2f;
         cudaError_t e;
+        {   // mirrored-observation gather table
+            static const int l2r[EML_NB] = {0, 5, 6, 7, 8, 1, 2, 3, 4, 9, 10, 11, 12, 13, 19, 20, 21, 22, 23, 14, 15, 16, 17, 18};
+            uint16_t tab[EML_OBS];
+            for (int i = 0; i < EML_OBS; ++i) {
+                int src = i, neg = 0;
+                if (i < 69) { int b = i / 3 + 1, c = i % 3; src = (l2r[b] - 1) * 3 + c; neg = c == 1; }                         // local body pos: y negated
+                else if (i < 213) { int j = i - 69, b = j / 6, c = j % 6; src = 69 + l2r[b] * 6 + c; neg = c % 3 == 1; }        // tan/norm: y components
+                else if (i < 285) { int j = i - 213, b = j / 3, c = j % 3; src = 213 + l2r[b] * 3 + c; neg = c == 1; }          // linear velocity
+                else if (i < 357) { int j = i - 285, b = j / 3, c = j % 3; src = 285 + l2r[b] * 3 + c; neg = c != 1; }          // angular velocity (pseudo-vector)
+                else if (i < 368) { src = i; }                                                                                  // shape parameters
+                else if (i < 398) { src = i; neg = (i - 368) & 1; }                                                             // trajectory samples: y negated
+                else { int j = i - 398; src = 398 + (j & ~31) + (31 - (j & 31)); }                                              // height map flipped along y
+                tab[i] = (uint16_t)(src | (neg << 15));
+            }
+            if ((e = cudaMemcpyToSymbol(g_flip_src, tab, sizeof(tab))) != cudaSuccess) return e;
+        }
         if ((e = cudaMemcpyToSymbol(c_grid32, g32, sizeof(g32))) != cudaSuccess) return e;
         if ((e = cudaMemcpyToSymbol(c_cgx, cx, sizeof(cx))) != cudaSuccess) return e;
         if ((e = cudaMemcpyToSymbol(c_cgy, cy, sizeof(cy))) != cudaSuccess) return e;

@@ -87,6 +87,7 @@ class Rollout:
         self._marks = None
         self._graphs = {}
         self._cur = {}
+        self._warmed = False
 
         self.state = f(6, N)
         self.state[3].fill_(1.0)      # discount_coefs start at 1
@@ -216,6 +217,7 @@ class Rollout:
 
     def step(self, n, noise=None, host_obs=False):
         """host_obs: the caller overwrote sim.obs (host-provided observations): operands are re-derived from it."""
+        self._warmed = True
         for f in self._segment_fns(n, noise, host_obs):
             self._mark()
             f()
@@ -280,6 +282,9 @@ class Rollout:
     def step_graphed(self, n):
         """Same work as step(n) replayed from a CUDA graph (captured on first use; run a few eager steps first so that
         every lazy one-time initialisation - constant tables, weight splits, function attributes - has happened)."""
+        if not self._warmed:          # the very first step runs eagerly: one-time initialisations must not land in a capture
+            self.step(n)
+            return
         self._replay(n, lambda: self.step(n))
 
     def step_graphed_host_noise(self, n):
@@ -298,6 +303,9 @@ class Rollout:
         self._mark()
 
     def finish_graphed(self):
+        if not getattr(self, "_finish_warm", False):
+            self._finish_warm = True
+            return self.finish()
         self._replay("finish", self.finish)
         return self._finish_out
 
