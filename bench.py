@@ -184,6 +184,7 @@ def run_ours(args):
 
     for n in range(3):                      # eager: every lazy one-time initialisation happens here
         R.step(n)
+    R.finish()
     step_i[0] = 3
     for _ in range(max(W, HORIZON if graphs else 0)):   # with graphs: every slot's graph is captured during warm-up
         one_step()
@@ -262,6 +263,7 @@ def run_ours(args):
                      concurrent=not args.serial, reuse_values=True)
         for n in range(3):
             R2.step(n)
+        R2.finish()
         c = [3]
 
         def step2():

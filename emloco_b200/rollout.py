@@ -225,6 +225,7 @@ class Rollout:
 
     # ---- after the horizon: disc over the stored AMP obs, combine, GAE (:150-163) ----
     def finish(self):
+        self._finish_warm = True
         mb, T, N = self.mb, self.T, self.N
         if self.recompute_disc:
             if getattr(self.nets, "amp_slots", 1) == T:
@@ -303,8 +304,7 @@ class Rollout:
         self._mark()
 
     def finish_graphed(self):
-        if not getattr(self, "_finish_warm", False):
-            self._finish_warm = True
+        if not getattr(self, "_finish_warm", False):      # first call eager: workspaces are allocated outside a capture
             return self.finish()
         self._replay("finish", self.finish)
         return self._finish_out
