@@ -43,7 +43,7 @@ class RolloutCfg(C.Structure):
 
 
 class PostSinks(C.Structure):
-    _fields_ = [("obs_copy", C.c_void_p), ("amp_copy", C.c_void_p), ("obs_mean", C.c_void_p), ("obs_inv_std", C.c_void_p),
+    _fields_ = [("obs_copy", C.c_void_p), ("amp_copy", C.c_void_p), ("flip_copy", C.c_void_p), ("obs_mean", C.c_void_p), ("obs_inv_std", C.c_void_p),
                 ("self_hi", C.c_void_p), ("self_lo", C.c_void_p), ("ld_self", C.c_int64),
                 ("task_hi", C.c_void_p), ("task_lo", C.c_void_p), ("ld_task", C.c_int64),
                 ("amp_mean", C.c_void_p), ("amp_inv_std", C.c_void_p),

@@ -250,11 +250,14 @@ __global__ void __launch_bounds__(PS_THREADS) post_step_kernel(PostParams P) {
     {
         float2* o = reinterpret_cast<float2*>(P.obs + (size_t)env * EML_OBS);
         float2* f = reinterpret_cast<float2*>(P.flip_obs + (size_t)env * EML_OBS);
+        float2* fc = (P.k.flip_copy && !rmode) ? reinterpret_cast<float2*>(P.k.flip_copy + (size_t)env * EML_OBS) : nullptr;
         for (int i2 = tid; i2 < EML_OBS / 2; i2 += PS_THREADS) {
             o[i2] = reinterpret_cast<const float2*>(s_obs)[i2];
             const uint32_t e = __ldg(reinterpret_cast<const uint32_t*>(g_flip_src) + i2);      // two table entries
             const float r0 = s_obs[e & 0x7fffu], r1 = s_obs[(e >> 16) & 0x7fffu];
-            f[i2] = make_float2((e & 0x8000u) ? -r0 : r0, (e & 0x80000000u) ? -r1 : r1);
+            const float2 fv = make_float2((e & 0x8000u) ? -r0 : r0, (e & 0x80000000u) ? -r1 : r1);
+            f[i2] = fv;
+            if (fc) fc[i2] = fv;
         }
         // optional sinks of the same observation row: experience row, and the normalised bf16 hi/lo operands the
         // tensor-core layers read (self-obs part -> actor/critic input, task-obs part -> task MLP input)

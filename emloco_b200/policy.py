@@ -151,11 +151,12 @@ class RolloutNets:
                              torch.cat([ps[1].detach(), ps[3].detach()]).contiguous())
         return self._stacked[1], self._stacked[2]
 
-    def post_sinks(self, obs_copy=None, amp_copy=None, slot=0):
+    def post_sinks(self, obs_copy=None, amp_copy=None, slot=0, flip_copy=None):
         """emloco_post_sinks pointing at this object's operand buffers (tensor-core path) plus the given experience rows."""
         k = _lib.PostSinks()
         k.obs_copy = None if obs_copy is None else obs_copy.data_ptr()
         k.amp_copy = None if amp_copy is None else amp_copy.data_ptr()
+        k.flip_copy = None if flip_copy is None else flip_copy.data_ptr()
         if self.tc:
             om, _ = self.obs_norm.f32(); am, _ = self.amp_norm.f32()
             k.obs_mean, k.obs_inv_std = om.data_ptr(), self.obs_norm.inv_std().data_ptr()

@@ -64,7 +64,7 @@ class Rollout:
         # experience rows; `obses` has one spare row (T) that receives the observation following the last step of a horizon
         self.mb = dict(obses=f(T + 1, N, OBS), actions=f(T, N, ACTIONS), neglogpacs=f(T, N), values=f(T, N, 1), mus=f(T, N, ACTIONS),
                        task_values=f(T, N, 1), rewards=f(T, N, 1), next_values=f(T, N, 1), dones=f(T, N), amp_obs=f(T, N, AMP_OBS),
-                       amp_rewards=f(T, N, 1))
+                       amp_rewards=f(T, N, 1), flip_obs=f(T, N, OBS))      # flip_obs: motion_sym_loss rows (:74-75)
         # fuse_sinks: the post-step / reset kernels write the experience rows and the normalised bf16 operands of the first
         # layers themselves (emloco_set_post_sinks) instead of separate copy / split launches
         self.fuse = bool(fuse_sinks)
@@ -158,11 +158,13 @@ class Rollout:
 
         def seg_post():                                                                #           post_physics_step
             if fuse:
-                sim.set_post_sinks(nets.post_sinks(obs_copy=mb["obses"][nxt], amp_copy=mb["amp_obs"][n], slot=slot))
+                sim.set_post_sinks(nets.post_sinks(obs_copy=mb["obses"][nxt], amp_copy=mb["amp_obs"][n], slot=slot,
+                                                   flip_copy=mb["flip_obs"][n]))
                 sim.post_step(True)
             else:
                 sim.post_step(True)
                 mb["amp_obs"][n].copy_(sim.amp_obs.view(self.N, AMP_OBS))
+                mb["flip_obs"][n].copy_(sim.flip_obs)
 
         # value reuse: critic(next obs) is NOT recomputed for envs that are not reset - the next step's policy pass evaluates
         # the critic on that very observation; only timed-out envs need their terminal observation evaluated now.  The last

@@ -127,8 +127,8 @@ int emloco_reset_indexed(emloco_sim* sim, const int32_t* d_env_ids, int32_t n, v
 
 /* Optional extra outputs of the fused post-step kernel (and of the post-step part of emloco_reset_done), so that the
  * rollout's copies and operand conversions cost no extra pass over HBM:
- *   obs_copy / amp_copy  experience rows `experience_buffer.update_data('obses' / 'amp_obs', n, ...)` of play_steps
- *                        (amp_continuous_value.py:46,70; emloco_reset_done writes obs_copy only)
+ *   obs_copy / amp_copy / flip_copy   experience rows `experience_buffer.update_data('obses' / 'amp_obs' / 'flip_obs', n, ...)`
+ *                        of play_steps (amp_continuous_value.py:46,70,74-75; emloco_reset_done writes obs_copy only)
  *   self_* / task_*      clamp((obs-mean)*inv_std, +-5) (utils/running_mean_std.py:82-84) split into bf16 hi/lo: the A operands
  *                        of emloco_linear_bf16x3 for the actor/critic input (cols 0..367) and the task MLP (cols 368..1421)
  *   amp_*                the same for the discriminator input [N,3090]
@@ -137,6 +137,7 @@ int emloco_reset_indexed(emloco_sim* sim, const int32_t* d_env_ids, int32_t n, v
 typedef struct emloco_post_sinks {
     float*    obs_copy;
     float*    amp_copy;
+    float*    flip_copy;      /* experience row of the mirrored observation (motion_sym_loss, amp_continuous_value.py:74-75) */
     const float* obs_mean; const float* obs_inv_std;
     uint16_t* self_hi; uint16_t* self_lo; int64_t ld_self;
     uint16_t* task_hi; uint16_t* task_lo; int64_t ld_task;

@@ -191,6 +191,9 @@ def test_fused_sinks_equal_separate_copies_and_splits():
         if rep == 0:
             np.testing.assert_allclose(oa["obses"][..., :398].cpu().numpy(), ob["obses"][..., :398].cpu().numpy(), rtol=1e-3, atol=5e-3)
             np.testing.assert_allclose(oa["amp_obs"].cpu().numpy(), ob["amp_obs"].cpu().numpy(), rtol=1e-3, atol=5e-3)
+            np.testing.assert_allclose(oa["flip_obs"][..., :398].cpu().numpy(), ob["flip_obs"][..., :398].cpu().numpy(), rtol=1e-3, atol=5e-3)
+            fo, oo = oa["flip_obs"].cpu().numpy(), oa["obses"].cpu().numpy()
+            np.testing.assert_array_equal(fo[:-1, :, 369:398:2], -oo[1:, :, 369:398:2])     # row n of flip_obs mirrors the obs AFTER step n
             for key in ("mus", "values", "next_values", "amp_rewards", "returns"):
                 np.testing.assert_allclose(oa[key].cpu().numpy(), ob[key].cpu().numpy(), rtol=1e-3, atol=5e-3, err_msg=key)
         assert all(torch.isfinite(v).all() for v in oa.values())
