@@ -101,6 +101,11 @@ def dist_env():
 # =====================================================================================================
 # CPU arm: the oracle port on the host cores (the Isaac Gym CPU pipeline itself cannot run here)
 # =====================================================================================================
+# README training command: --real_path JTA+JRDB --adjust_root_vel --init_heading (emloco TRAJ_* bits 1|2|4); the pool
+# stands in for the JTA/JRDB pickles (not redistributable)
+TRAJ_FLAGS, TRAJ_POOL = 1 | 2 | 4, 2048
+
+
 def cpu_rollout_rate(envs, steps, warmup, seed=0, budget_s=None):
     """env-steps/s of oracle/cpu_rollout.py on `envs` envs; stops early when `budget_s` is exceeded."""
     import numpy as np
@@ -112,7 +117,9 @@ def cpu_rollout_rate(envs, steps, warmup, seed=0, budget_s=None):
     A = build_model_arrays()
     torch.manual_seed(seed)
     P, D = weights_from_state_dict(AMPSeptValueNetwork().state_dict())
-    R = CpuRollout(A, synthetic_env_state(envs, seed, rest_root_height(A)), P, D)
+    from emloco_b200.synthetic import synthetic_traj_pool
+    R = CpuRollout(A, synthetic_env_state(envs, seed, rest_root_height(A)), P, D, traj_flags=TRAJ_FLAGS,
+                   traj_pool=synthetic_traj_pool(TRAJ_POOL, seed), traj_seed=seed)
     rng = np.random.default_rng(seed)
     for _ in range(warmup):
         R.step(rng.standard_normal((envs, 69)).astype(np.float32))
@@ -163,8 +170,10 @@ def run_ours(args):
     from emloco_b200.value_pose_net import ValuePoseNet
 
     N, K, W = args.envs, args.steps, args.warmup
+    from emloco_b200.synthetic import synthetic_traj_pool
+    pool = synthetic_traj_pool(TRAJ_POOL, args.seed)
     R = Rollout(N, device=local_rank, seed=D.rank_seed(args.seed, rank), tensor_cores=args.tensor_cores, recompute_disc=not args.dedup_disc,
-                concurrent=not args.serial)
+                concurrent=not args.serial, traj_flags=TRAJ_FLAGS, traj_pool=pool)
     pk = peaks()
 
     def barrier():
@@ -260,7 +269,7 @@ def run_ours(args):
         R.close(); del R
         torch.cuda.empty_cache()
         R2 = Rollout(N, device=local_rank, seed=D.rank_seed(args.seed, rank), tensor_cores=True, recompute_disc=not args.dedup_disc,
-                     concurrent=not args.serial, reuse_values=True)
+                     concurrent=not args.serial, reuse_values=True, traj_flags=TRAJ_FLAGS, traj_pool=pool)
         for n in range(3):
             R2.step(n)
         R2.finish()
@@ -340,6 +349,8 @@ def run_ours(args):
             "config": {"workload": f"{N} SMPL-humanoid envs per GPU, PACER AMP rollout step + LocoVal scoring (configs[1])",
                        "horizon": HORIZON, "l2": "per-step working set (obs 23 MB + AMP obs 2x51 MB + experience rows + 45 MB weights) exceeds the 126 MB L2; experience rows rotate over 32 slots",
                        "post_horizon_disc_pass": "recomputed" if not args.dedup_disc else "reused per-step logits",
+                       "env_reset": "on device: state reset + TrajGenerator.reset (--real_path pool of %d synthetic polylines, "
+                                    "--adjust_root_vel, --init_heading) for the envs that finish, every step" % TRAJ_POOL,
                        "tensor_cores": bool(args.tensor_cores), "cuda_graphs": graphs, "parallel_branches": not args.serial},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},

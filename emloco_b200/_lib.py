@@ -18,7 +18,7 @@ SYMBOLS = [
     "emloco_plausibl_mlp_forward", "emloco_gae", "emloco_reset_done", "emloco_sample_actions",
     "emloco_disc_reward", "emloco_rollout_record", "emloco_normalize", "emloco_physics_step", "emloco_split_bf16",
     "emloco_linear_bf16x3", "emloco_set_post_sinks", "emloco_linear_bf16x3_rows", "emloco_timeout_gather",
-    "emloco_rollout_record_deferred", "emloco_fill_next_values", "emloco_linear", "emloco_sync", "emloco_last_error", "emloco_version",
+    "emloco_rollout_record_deferred", "emloco_fill_next_values", "emloco_traj_reset", "emloco_set_traj_reset", "emloco_linear", "emloco_sync", "emloco_last_error", "emloco_version",
 ]
 
 
@@ -48,6 +48,18 @@ class PostSinks(C.Structure):
                 ("task_hi", C.c_void_p), ("task_lo", C.c_void_p), ("ld_task", C.c_int64),
                 ("amp_mean", C.c_void_p), ("amp_inv_std", C.c_void_p),
                 ("amp_hi", C.c_void_p), ("amp_lo", C.c_void_p), ("ld_amp", C.c_int64)]
+
+
+class TrajCfg(C.Structure):
+    """emloco_traj_cfg (include/emloco.h): TrajGenerator.reset parameters, pacer.yaml:45,55-61 defaults."""
+    _fields_ = [("dtheta_max", C.c_float), ("speed_min", C.c_float), ("speed_max", C.c_float), ("accel_max", C.c_float),
+                ("sharp_turn_prob", C.c_float), ("hybrid_init_prob", C.c_float), ("flags", C.c_int32), ("origin_relative", C.c_int32),
+                ("seed", C.c_uint64), ("pool", C.c_void_p), ("pool_count", C.c_int64), ("uniform", C.c_void_p), ("ld_uniform", C.c_int64),
+                ("waypoint_traj", C.c_void_p), ("init_pose", C.c_void_p), ("init_vel", C.c_void_p), ("inverted", C.c_void_p),
+                ("num_waypoints", C.c_int32), ("reserved", C.c_int32)]
+
+
+TRAJ_REAL_PATH, TRAJ_ADJUST_ROOT_VEL, TRAJ_INIT_HEADING, TRAJ_HEADING_INVERSION, TRAJ_SLOW, TRAJ_RAND_COLS = 1, 2, 4, 8, 16, 405
 
 
 class Model(C.Structure):
@@ -118,7 +130,7 @@ def load():
 
 # kernels launched per successful ABI call (the bench's `gpu_launches` claim is counted here, not estimated)
 LAUNCHES = {"emloco_step": 2, "emloco_physics_step": 1, "emloco_post_step": 1, "emloco_simulate": 1, "emloco_reset_done": 2,
-            "emloco_reset_indexed": 1, "emloco_linear": 1, "emloco_normalize": 1, "emloco_sample_actions": 1,
+            "emloco_reset_indexed": 1, "emloco_traj_reset": 1, "emloco_linear": 1, "emloco_normalize": 1, "emloco_sample_actions": 1,
             "emloco_disc_reward": 1, "emloco_rollout_record": 1, "emloco_gae": 1, "emloco_locoval_forward": 1,
             "emloco_locoval_backward": 1, "emloco_plausibl_mlp_forward": 1, "emloco_step_host": 2,
             "emloco_locoval_forward_host": 1, "emloco_split_bf16": 1, "emloco_linear_bf16x3": 1, "emloco_linear_bf16x3_rows": 1,

@@ -106,6 +106,7 @@ int emloco_create(const emloco_cfg* cfg, const emloco_model* model, emloco_sim**
     ALLOC(s->obs, N * EML_OBS, float); ALLOC(s->flip_obs, N * EML_OBS, float); ALLOC(s->rew, N, float); ALLOC(s->rew_raw, N * 2, float);
     ALLOC(s->reset, N, int64_t); ALLOC(s->terminate, N, int64_t); ALLOC(s->progress, N, int64_t);
     ALLOC(s->amp_obs, N * EML_AMP_OBS, float); ALLOC(s->verts, N * EML_NUM_VERTS * 3, float); ALLOC(s->betas, N * 17, float);
+    ALLOC(s->traj_epoch, N, uint32_t);
     // default terrain: flat 1080 x 1080 (8 m map + 50 m border at 0.1 m, humanoid_pedestrain_terrain.py:1142-1165)
     s->hf_rows = 1080; s->hf_cols = 1080;
     ALLOC(s->height, (size_t)s->hf_rows * s->hf_cols, int16_t);
@@ -131,7 +132,7 @@ int emloco_destroy(emloco_sim* s) {
     cudaSetDevice(s->device);
     void* ptrs[] = {s->root_state, s->dof_state, s->rb_state, s->contact, s->dof_force, s->pd_target, s->joint_quat, s->actions,
                     s->obs, s->flip_obs, s->rew, s->rew_raw, s->reset, s->terminate, s->progress, s->amp_obs, s->verts, s->betas,
-                    s->height};
+                    s->height, s->traj_epoch};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (s->h_pin) cudaFreeHost(s->h_pin);
     free(s);
@@ -334,6 +335,29 @@ int emloco_linear(const float* d_x, int64_t ldx, const float* d_w, const float* 
 int emloco_reset_done(emloco_sim* s, const float* d_init_root, const float* d_init_dof, void* stream) {
     if (!s || !d_init_root || !d_init_dof) return fail(EMLOCO_EINVAL, "emloco_reset_done: null argument");
     CK(eml_reset_done(s, d_init_root, d_init_dof, (cudaStream_t)stream), "reset-done kernels");
+    return EMLOCO_OK;
+}
+
+static int check_traj_cfg(const emloco_traj_cfg* c) {
+    if (c->uniform && c->ld_uniform < EMLOCO_TRAJ_RAND_COLS) return fail(EMLOCO_EINVAL, "trajectory reset: ld_uniform < 405");
+    if ((c->flags & EMLOCO_TRAJ_REAL_PATH) && (!c->pool || c->pool_count <= 0)) return fail(EMLOCO_EINVAL, "trajectory reset: real_path needs a trajectory pool");
+    if (c->num_waypoints < 0 || c->num_waypoints > EML_TRAJ_SAMPLES) return fail(EMLOCO_EINVAL, "trajectory reset: num_waypoints must be 0..15");
+    if (!(c->speed_max >= c->speed_min) || !(c->speed_min > 0.0f)) return fail(EMLOCO_EINVAL, "trajectory reset: need 0 < speed_min <= speed_max");
+    return EMLOCO_OK;
+}
+
+int emloco_traj_reset(emloco_sim* s, const emloco_traj_cfg* c, void* stream) {
+    if (!s || !c) return fail(EMLOCO_EINVAL, "emloco_traj_reset: null argument");
+    if (int e = check_traj_cfg(c)) return e;
+    CK(eml_traj_reset(s, *c, 0, (cudaStream_t)stream), "trajectory reset kernel");
+    return EMLOCO_OK;
+}
+
+int emloco_set_traj_reset(emloco_sim* s, const emloco_traj_cfg* c) {
+    if (!s) return fail(EMLOCO_EINVAL, "emloco_set_traj_reset: null sim");
+    if (!c) { s->traj_on = 0; return EMLOCO_OK; }
+    if (int e = check_traj_cfg(c)) return e;
+    s->traj = *c; s->traj_on = 1;
     return EMLOCO_OK;
 }
 

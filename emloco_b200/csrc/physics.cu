@@ -414,5 +414,7 @@ cudaError_t eml_reset_done(emloco_sim* s, const float* d_init_root, const float*
     physics_kernel<<<blocks, PH_WARPS * 32, 0, st>>>(P);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    return eml_launch_post_reset(s, st);
+    e = eml_launch_post_reset(s, s->traj_on, st);
+    if (e != cudaSuccess || !s->traj_on) return e;
+    return eml_traj_reset(s, s->traj, 1, st);       // _reset_task runs after the observations (humanoid_amp_task.py:54-57)
 }

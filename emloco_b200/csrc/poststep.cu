@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(PS_THREADS) post_step_kernel(PostParams P) {
         float2* a = reinterpret_cast<float2*>(P.amp + (size_t)env * EML_AMP_OBS);
         if (rmode) {
             for (int i = tid; i < 15 * 103; i += PS_THREADS) a[i] = reinterpret_cast<const float2*>(s_amp)[i % 103];
-            if (tid == 0) { P.reset[env] = 0; P.terminate[env] = 0; }
+            if (tid == 0 && P.reset_mode == 1) { P.reset[env] = 0; P.terminate[env] = 0; }
             return;
         }
         float2* ac = P.k.amp_copy ? reinterpret_cast<float2*>(P.k.amp_copy + (size_t)env * EML_AMP_OBS) : nullptr;
@@ -310,7 +310,7 @@ static bool g_tables_ready = false;
 
 static cudaError_t launch_post(emloco_sim* s, int advance_progress, int reset_mode, cudaStream_t st);
 cudaError_t eml_launch_post_step(emloco_sim* s, int advance_progress, cudaStream_t st) { return launch_post(s, advance_progress, 0, st); }
-cudaError_t eml_launch_post_reset(emloco_sim* s, cudaStream_t st) { return launch_post(s, 0, 1, st); }
+cudaError_t eml_launch_post_reset(emloco_sim* s, int keep_flags, cudaStream_t st) { return launch_post(s, 0, keep_flags ? 2 : 1, st); }
 
 static cudaError_t launch_post(emloco_sim* s, int advance_progress, int reset_mode, cudaStream_t st) {
     if (!g_tables_ready) {

@@ -59,6 +59,9 @@ struct emloco_sim {
     size_t   h_pin_bytes;
     cudaStream_t copy_stream;
     emloco_post_sinks sinks;   // optional extra outputs of the post-step kernel (all NULL by default)
+    uint32_t* traj_epoch;      // [N] per-env count of device-side trajectory resets (Philox counter word)
+    emloco_traj_cfg traj;      // stage appended to emloco_reset_done when traj_on
+    int traj_on;
 };
 
 struct RecordParams {
@@ -90,7 +93,8 @@ cudaError_t eml_launch_post_step(emloco_sim* s, int advance_progress, cudaStream
 cudaError_t eml_launch_physics(emloco_sim* s, const float* d_actions, int n_substeps, int fuse_post, cudaStream_t st);
 cudaError_t eml_launch_fk(emloco_sim* s, const int32_t* d_env_ids, int n, cudaStream_t st);
 cudaError_t eml_reset_done(emloco_sim* s, const float* d_init_root, const float* d_init_dof, cudaStream_t st);
-cudaError_t eml_launch_post_reset(emloco_sim* s, cudaStream_t st);
+cudaError_t eml_launch_post_reset(emloco_sim* s, int keep_flags, cudaStream_t st);
+cudaError_t eml_traj_reset(emloco_sim* s, const emloco_traj_cfg& c, int clear_flags, cudaStream_t st);
 cudaError_t eml_sample_actions(const float* mu, long long ldmu, const float* logstd, const float* noise, float* actions,
                                float* neglogp, long long N, int A, cudaStream_t st);
 cudaError_t eml_disc_reward(const float* logit, const float* task_rew, float* disc, float* combined, long long M, float scale,

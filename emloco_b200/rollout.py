@@ -32,7 +32,8 @@ class Rollout:
     def __init__(self, num_envs, device=0, horizon=32, seed=0, tensor_cores=False, gamma=0.99, tau=0.95,
                  task_reward_w=0.5, disc_reward_w=0.5, disc_reward_scale=2.0, inversion_penalty_scale=0.3,
                  step_to_pred=144, normalize_value=True, net=None, obs_norm=None, amp_norm=None, value_norm=None,
-                 recompute_disc=True, valuenet=None, fuse_sinks=True, concurrent=True, reuse_values=False):
+                 recompute_disc=True, valuenet=None, fuse_sinks=True, concurrent=True, reuse_values=False, traj_flags=None,
+                 traj_pool=None):
         self.N, self.T, self.device = int(num_envs), int(horizon), int(device)
         self.gamma, self.tau = gamma, tau
         self.task_reward_w, self.disc_reward_w, self.disc_reward_scale = task_reward_w, disc_reward_w, disc_reward_scale
@@ -76,10 +77,19 @@ class Rollout:
             self.mb["obses"][T].copy_(self.sim.obs)
 
         # LocoVal inputs captured at reset (humanoid_pedestrain_terrain.py:509-515, vec_task_wrappers.py:47-66)
-        self.waypoint_traj = torch.from_numpy(st["waypoints"]).to(dev)                  # [N,13,2], origin-relative
+        self.waypoint_traj = f(N, 13, 3)                                                # origin-relative, z = 0
+        self.waypoint_traj[:, :, 0:2] = torch.from_numpy(st["waypoints"]).to(dev)
         rb = self.sim.rb_state.view(self.N, 24, 13)
         self.init_pose = (rb[:, :, 0:3] - rb[:, :1, 0:3]).contiguous()
         self.init_vel = self.init_root[:, 7:9].contiguous()
+        # traj_flags (emloco TRAJ_* bits, None = off): every later env reset regenerates the env's trajectory and these
+        # three LocoVal inputs on the device (emloco_set_traj_reset: TrajGenerator.reset + _reset_task)
+        self.inverted = None
+        if traj_flags is not None:
+            self.inverted = torch.zeros(N, device=dev, dtype=torch.uint8)
+            self.traj_pool = None if traj_pool is None else torch.as_tensor(traj_pool, dtype=torch.float32).to(dev).contiguous()
+            self.sim.set_traj_reset(self.sim.traj_cfg(flags=traj_flags, seed=seed, pool=self.traj_pool, waypoint_traj=self.waypoint_traj,
+                                                      init_pose=self.init_pose, init_vel=self.init_vel, inverted=self.inverted))
         if valuenet is None:
             from .value_pose_net import ValuePoseNet
             valuenet = ValuePoseNet(True, True, mutate_pose=False)
@@ -180,6 +190,8 @@ class Rollout:
         def seg_disc():                                                                # _calc_amp_rewards, :93
             cur["logit"] = nets.disc_logits(sim.amp_obs.view(self.N, AMP_OBS), operands_ready=fuse, slot=slot)
 
+        inv = None if self.inverted is None else _ptr(self.inverted)      # task.inverted -> inversion penalty (:78-83)
+
         def seg_record():
             if reuse:
                 # deferred next values: terminated -> 0, timed-out -> compact critic, the rest is completed by step n+1;
@@ -187,7 +199,7 @@ class Rollout:
                 prev = n > 0
                 _lib.check(_lib.load().emloco_rollout_record_deferred(
                     C.byref(self.rcfg), _ptr(sim.rew), _ptr(sim.reset), _ptr(sim.terminate), _ptr(cur["res"]["values"]),
-                    _ptr(cur["logit"]), None, _ptr(mb["values"][n]), _ptr(mb["rewards"][n]), _ptr(mb["dones"][n]),
+                    _ptr(cur["logit"]), inv, _ptr(mb["values"][n]), _ptr(mb["rewards"][n]), _ptr(mb["dones"][n]),
                     _ptr(mb["next_values"][n]), _ptr(mb["amp_rewards"][n]), _ptr(self.state), self.N, _ptr(cur["cval"]),
                     _ptr(cur["cidx"]), _ptr(cur["ccount"]), _ptr(mb["dones"][n - 1]) if prev else None,
                     _ptr(mb["next_values"][n - 1]) if prev else None, _stream()), "emloco_rollout_record_deferred")
@@ -203,7 +215,7 @@ class Rollout:
             # values are un-normalised (get_action_values, normalize_value) together with next_values in the record kernel
             _lib.check(_lib.load().emloco_rollout_record(
                 C.byref(self.rcfg), _ptr(sim.rew), _ptr(sim.reset), _ptr(sim.terminate), _ptr(cur["res"]["values"]),
-                _ptr(cur["nv"]), _ptr(cur["logit"]), None, _ptr(mb["values"][n]), _ptr(mb["rewards"][n]), _ptr(mb["dones"][n]),
+                _ptr(cur["nv"]), _ptr(cur["logit"]), inv, _ptr(mb["values"][n]), _ptr(mb["rewards"][n]), _ptr(mb["dones"][n]),
                 _ptr(mb["next_values"][n]), _ptr(mb["amp_rewards"][n]), _ptr(self.state), self.N, _stream()),
                 "emloco_rollout_record")
 

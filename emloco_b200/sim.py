@@ -60,6 +60,7 @@ class EmlocoSim:
         torch.cuda.init()
         _lib.check(self.lib.emloco_create(C.byref(self.cfg), C.byref(self._model), C.byref(h)), "emloco_create")
         self._h = h
+        self._traj_on, self._traj_keep = 0, None
         self.num_envs = int(num_envs)
         self.device = int(device)
         from .model import rest_root_height
@@ -114,6 +115,53 @@ class EmlocoSim:
             if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == shp):
                 raise _lib.EmlocoError(f"reset_done: initial state must be contiguous float32 CUDA of shape {shp}")
         _lib.check(self.lib.emloco_reset_done(self._h, _ptr(init_root), _ptr(init_dof), _stream()), "emloco_reset_done")
+        _lib.launch_count += self._traj_on            # the appended trajectory-reset stage
+
+    def traj_cfg(self, flags=0, seed=0, pool=None, uniform=None, waypoint_traj=None, init_pose=None, init_vel=None,
+                 inverted=None, origin_relative=True, **over):
+        """emloco_traj_cfg with the pacer.yaml defaults (TrajGenerator args, humanoid_traj.py:113-119).  Tensors are CUDA,
+        contiguous: pool [P,101,3] f32, uniform [N,>=405] f32, waypoint_traj [N,<=15,3], init_pose [N,24,3], init_vel [N,2]
+        f32, inverted [N] uint8.  The sim keeps references to them."""
+        c = _lib.TrajCfg(dtheta_max=2.0, speed_min=0.0005, speed_max=3.0, accel_max=2.0, sharp_turn_prob=0.02,
+                         hybrid_init_prob=0.5, flags=int(flags), origin_relative=int(bool(origin_relative)), seed=int(seed))
+        for k, v in over.items():
+            if not hasattr(c, k):
+                raise _lib.EmlocoError(f"unknown traj cfg field {k}")
+            setattr(c, k, v)
+        N = self.num_envs
+        want = dict(pool=(pool, torch.float32, None), uniform=(uniform, torch.float32, None),
+                    waypoint_traj=(waypoint_traj, torch.float32, None), init_pose=(init_pose, torch.float32, (N, _lib.NB, 3)),
+                    init_vel=(init_vel, torch.float32, (N, 2)), inverted=(inverted, torch.uint8, (N,)))
+        keep = []
+        for k, (t, dt, shp) in want.items():
+            if t is None:
+                continue
+            if not (t.is_cuda and t.dtype == dt and t.is_contiguous() and (shp is None or tuple(t.shape) == shp)):
+                raise _lib.EmlocoError(f"traj cfg: {k} must be contiguous {dt} CUDA" + (f" of shape {shp}" if shp else ""))
+            setattr(c, k, t.data_ptr()); keep.append(t)
+        if pool is not None:
+            if pool.dim() != 3 or tuple(pool.shape[1:]) != (101, 3):
+                raise _lib.EmlocoError("traj cfg: pool must be [P,101,3]")
+            c.pool_count = pool.shape[0]
+        if waypoint_traj is not None:
+            if waypoint_traj.dim() != 3 or waypoint_traj.shape[0] != N or waypoint_traj.shape[2] != 3 or not 1 <= waypoint_traj.shape[1] <= 15:
+                raise _lib.EmlocoError("traj cfg: waypoint_traj must be [N, 1..15, 3]")
+            c.num_waypoints = waypoint_traj.shape[1]
+        if uniform is not None:
+            if uniform.dim() != 2 or uniform.shape[0] != N:
+                raise _lib.EmlocoError("traj cfg: uniform must be [N, >=405]")
+            c.ld_uniform = uniform.shape[1]
+        c._keep = keep
+        return c
+
+    def traj_reset(self, cfg):
+        """TrajGenerator.reset + _reset_task outputs for the envs whose reset_buf is set right now."""
+        _lib.check(self.lib.emloco_traj_reset(self._h, C.byref(cfg), _stream()), "emloco_traj_reset")
+
+    def set_traj_reset(self, cfg=None):
+        """reset_done regenerates the trajectories of the envs it resets (None: off)."""
+        _lib.check(self.lib.emloco_set_traj_reset(self._h, None if cfg is None else C.byref(cfg)), "emloco_set_traj_reset")
+        self._traj_keep, self._traj_on = cfg, int(cfg is not None)
 
     def set_post_sinks(self, sinks=None):
         """Optional extra outputs of post_step / reset_done (emloco_post_sinks); None clears them."""

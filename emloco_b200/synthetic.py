@@ -58,6 +58,14 @@ def synthetic_env_state(n, seed=0, root_height=0.93, border=50.0, patch=8.0):
     return dict(root=root, dof=dof, verts=verts, waypoints=waypoints_from_verts(verts))
 
 
+def synthetic_traj_pool(p, seed=0):
+    """Stand-in for the saved JTA / JRDB trajectory pickles (`{id: {'traj': [101,3]}}`, traj_generator.py:44-52): p
+    origin-relative random-walk polylines, float32 [p,101,3]."""
+    rng = np.random.default_rng(seed + 7919)
+    verts, _ = random_walk_verts(p, np.zeros((p, 2)), rng)
+    return np.ascontiguousarray(verts, np.float32)
+
+
 def waypoints_from_verts(verts, num=13, sample_dt=0.4):
     """_fetch_traj_samples at progress 0 (humanoid_traj.py:208-224 via TrajGenerator.calc_pos :278-296), xy only,
     relative to the first waypoint (vec_task_wrappers.py:47-52).  Note calc_pos spreads the 101 vertices over

@@ -170,6 +170,46 @@ int emloco_step_host(emloco_sim* sim, const float* h_actions, float* h_obs, floa
  * (_init_amp_obs_default).  The mocap-sampled initial state of _reset_ref_state_init is the caller's to put in d_init_*. */
 int emloco_reset_done(emloco_sim* sim, const float* d_init_root, const float* d_init_dof, void* stream);
 
+/* Device-side `_reset_task` for the envs that reset: TrajGenerator.reset
+ * (pacer/pacer/env/util/traj_generator.py:60-237) + the LocoVal inputs captured at reset
+ * (humanoid_pedestrain_terrain.py:493-516, exposed by vec_task_wrappers.py:47-63).  One warp regenerates one env:
+ * random-walk polyline (:63-118), optional real trajectory from a device-resident pool [P,101,3] (:116-160; the
+ * reference re-reads a pickle and loops in python), optional speed matching (--adjust_root_vel :98-104,:149-155),
+ * first-segment alignment with the root velocity (--init_heading :176-234) and heading inversion (:195-200).
+ * Random draws: `uniform` [N, ld_uniform >= 405] replays explicit U[0,1) draws in the reference's order (cols 0-99
+ * dtheta, 100-199 sharp angle, 200-299 bernoulli, 300 heading, 301-400 dspeed, 401 speed, 402 real-data draw,
+ * 403 pool pick, 404 inversion); NULL = Philox4x32-10 keyed by (seed, env, per-env reset count).
+ * Differences from the reference, both in the random stream only: pool picks are independent (random.sample draws
+ * without replacement); --add_noise / --fixed_path / --pred_path are not implemented.
+ * Outputs (any may be NULL): waypoint_traj [N,num_waypoints,3] (num_waypoints <= 15; 0 means 15; LocoVal reads the first 13,
+ * amp_continuous_value.py:127), init_pose [N,24,3], init_vel [N,2], inverted [N];
+ * origin_relative != 0 stores waypoints / pose relative to their first row, as the vec-env getters return them. */
+#define EMLOCO_TRAJ_REAL_PATH          1
+#define EMLOCO_TRAJ_ADJUST_ROOT_VEL    2
+#define EMLOCO_TRAJ_INIT_HEADING       4
+#define EMLOCO_TRAJ_HEADING_INVERSION  8
+#define EMLOCO_TRAJ_SLOW              16
+#define EMLOCO_TRAJ_RAND_COLS        405
+typedef struct emloco_traj_cfg {
+    float    dtheta_max, speed_min, speed_max, accel_max, sharp_turn_prob;   /* 2, 0.0005, 3, 2, 0.02 (pacer.yaml:55-61) */
+    float    hybrid_init_prob;                                               /* 0.5 (pacer.yaml:45) */
+    int32_t  flags;
+    int32_t  origin_relative;
+    uint64_t seed;
+    const float* pool; int64_t pool_count;
+    const float* uniform; int64_t ld_uniform;
+    float*   waypoint_traj; float* init_pose; float* init_vel; uint8_t* inverted;
+    int32_t  num_waypoints; int32_t reserved;
+} emloco_traj_cfg;
+
+/* Regenerates the trajectories of the envs whose reset_buf is set RIGHT NOW (flags are left as they are). */
+int emloco_traj_reset(emloco_sim* sim, const emloco_traj_cfg* cfg, void* stream);
+
+/* Makes emloco_reset_done run the trajectory reset as its last stage - after the observations of the reset envs were
+ * recomputed from the OLD polyline, which is the reference's order (humanoid_amp_task.py:54-57: `super()._reset_envs`
+ * computes observations, then `_reset_task`).  NULL switches it off.  The struct is copied. */
+int emloco_set_traj_reset(emloco_sim* sim, const emloco_traj_cfg* cfg);
+
 /* ---- LocoVal: ValuePoseNet (pacer/pacer/learning/value_pose_net.py:10-159) ----
  * weights: fc1.weight[H1,IN] fc1.bias[H1] fc2.weight[H2,H1] fc2.bias[H2] fc3.weight[1,H2] fc3.bias[1]
  * packed in that order (state-dict order of `_network.fc{1,2,3}.{weight,bias}`).

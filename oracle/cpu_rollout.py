@@ -32,7 +32,8 @@ def weights_from_state_dict(sd):
 
 class CpuRollout:
     def __init__(self, model_arrays, state, P, D, obs_stats=None, amp_stats=None, value_stats=(0.0, 1.0), gamma=0.99,
-                 disc_scale=2.0, step_to_pred=144, inv_penalty=0.3):
+                 disc_scale=2.0, step_to_pred=144, inv_penalty=0.3, traj_flags=None, traj_pool=None,
+                 traj_seed=0):
         A = model_arrays
         self.A = A
         self.M = PO.make_model(A["parent"], A["offset"], A["mass"], A["com"], A["inertia6"], A["kp_joint"], A["kd_joint"],
@@ -58,7 +59,10 @@ class CpuRollout:
         self.contact = np.zeros((n, 24, 3)); self.dof_force = np.zeros((n, 69))
         self.state = np.zeros((6, n), F); self.state[3] = 1
         self.obs = np.zeros((n, 1422), F)
+        self.traj_flags = None
         self.reset_done()
+        # TrajGenerator.reset for the envs that reset from now on (numpy draws; the device path uses Philox - same distribution)
+        self.traj_flags, self.traj_pool, self.traj_rng = traj_flags, traj_pool, np.random.default_rng(traj_seed)
 
     # env_reset(done_indices): humanoid.py:455-481 + humanoid_amp.py:284-293,499-502 with a fixed initial state
     def reset_done(self):
@@ -74,6 +78,9 @@ class CpuRollout:
         out = self._post(ids, rb, dp, advance=False)
         self.obs[ids] = out["obs"]
         self.amp_buf[ids] = out["amp_obs"].reshape(len(ids), 15, 206)[:, :1]      # history := current step
+        if self.traj_flags is not None:                                           # _reset_task AFTER the observations (humanoid_amp_task.py:54-57)
+            U = self.traj_rng.random((len(ids), O.TRAJ_RAND_COLS)).astype(F)
+            O.traj_reset(self.verts, ids, self.root[ids, 0:3].astype(F), self.root[ids, 7:10].astype(F), U, self.traj_flags, self.traj_pool)
 
     def _post(self, ids, rb, dof_pos, advance):
         ds = np.stack([dof_pos, self.jw[ids]], -1).astype(F)

@@ -12,6 +12,7 @@ import os
 
 import numpy as np
 
+from . import oracle_np as O
 from . import ref_extract
 from .oracle_np import (AMP_STEP_DIM, AMP_STEPS, CONTACT_BODIES, CONTROL_DT, DOF_SUBSET, EPISODE_LEN, HEAD,
                         KEY_BODIES, NB, ND, NUM_TRAJ_SAMPLES, NUM_VERTS, TRAJ_SAMPLE_DT, center_height_points,
@@ -209,8 +210,83 @@ def reference_rms(x, mean, var):
     return m(torch.from_numpy(x)).numpy()
 
 
+def reference_traj_reset(N, n_reset, seed, flags, pool_size=7):
+    """TrajGenerator.reset + the _reset_task outputs driven with recorded uniform draws (torch.rand / torch.bernoulli /
+    random.sample of the hosted module are replaced by replay proxies - the arithmetic is the reference's)."""
+    import types
+    R = ref_extract.load()
+    torch = R.torch
+    mod = R.trajreset
+    rng = np.random.default_rng(seed)
+    f = np.float32
+    U = rng.random((n_reset, O.TRAJ_RAND_COLS)).astype(f)
+    U[:, 200:300] = np.where(rng.random((n_reset, 100)) < 0.1, 0.01, U[:, 200:300])     # make sharp turns common enough to matter
+    env_ids = np.sort(rng.choice(N, n_reset, replace=False))
+    verts0 = rng.normal(0, 1, (N, NUM_VERTS, 3)).astype(f)
+    init_pos = np.concatenate([50 + 8 * rng.random((n_reset, 2)), np.full((n_reset, 1), 0.9)], 1).astype(f)
+    root_vel = rng.normal(0, 1, (n_reset, 3)).astype(f)
+    root_vel[0] = 0                                                                      # the zero-velocity branch (:184)
+    pool = np.cumsum(rng.normal(0, 0.03, (pool_size, NUM_VERTS, 3)), 1).astype(f)
+    pool[..., 2] = 0
+    pool[1, 1] = pool[1, 0]                                                              # zero first segment (:185, :150)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    S = NUM_VERTS - 1
+    queue = [T(U[:, 0:S]), T(U[:, 100:100 + S]), None, T(U[:, 300]), T(U[:, 301:301 + S]), T(U[:, 401]), T(U[:, 402]), T(U[:, 404])]
+    order = iter([0, 1, 3, 4, 5, 6, 7])
+
+    class TorchProxy:
+        def __getattr__(self, k):
+            return getattr(torch, k)
+
+        def rand(self, *a, **kw):
+            t = queue[next(order)].clone()
+            shape = list(a[0]) if a and isinstance(a[0], (list, tuple)) else list(a)
+            assert list(t.shape) == shape, (t.shape, shape)
+            return t
+
+        def bernoulli(self, p):
+            return (T(U[:, 200:200 + S]) < p).float()
+
+    picks = np.minimum((U[:, 403] * f(pool_size)).astype(np.int64), pool_size - 1)
+
+    class RandomProxy:
+        def sample(self, population, k):
+            real = U[:, 402] > f(0.5)
+            assert k == int(real.sum())
+            return [int(i) for i in picks[real]]
+
+    mod.torch, mod.random = TorchProxy(), RandomProxy()
+    h = mod.TrajResetHolder()
+    h._device = "cpu"
+    h._dt = (EPISODE_LEN * CONTROL_DT) / (NUM_VERTS - 1)
+    h._dtheta_max, h._speed_min, h._speed_max, h._accel_max, h._sharp_turn_prob = 2.0, 0.0005, 3.0, 2.0, 0.02
+    h._hybrid_init_prob = 0.5
+    h._verts = T(verts0.copy()); h._verts_flat = h._verts.view(-1, 3)
+    h.inverted = torch.zeros(N, dtype=torch.bool)
+    data = [{"traj": pool[i].copy()} for i in range(pool_size)]
+    h.traj_data = [data]; h.traj_data_jta = data
+    F_ = lambda b: bool(flags & b)
+    h._flags = types.SimpleNamespace(fixed_path=False, slow=F_(O.TRAJ_F_SLOW), adjust_root_vel=F_(O.TRAJ_F_ADJUST_VEL),
+                                     real_path=F_(O.TRAJ_F_REAL), jta_path=True, jrdb_path=False, pred_path=False,
+                                     init_heading=F_(O.TRAJ_F_INIT_HEADING), heading_inversion=F_(O.TRAJ_F_INVERSION),
+                                     add_noise=False)
+    import contextlib, io, warnings
+    with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()) as so:
+        warnings.simplefilter("ignore")
+        h.reset(T(env_ids), T(init_pos), T(root_vel))
+    assert "alignment failed" not in so.getvalue(), so.getvalue()
+    mod.torch, mod.random = torch, __import__("random")
+    return dict(U=U, env_ids=env_ids, verts0=verts0, init_pos=init_pos, root_vel=root_vel, pool=pool, flags=flags,
+                verts=h._verts.numpy().copy(), inverted=h.inverted.numpy()[env_ids].copy())
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    for name, fl in (("traj_reset_plain", 0), ("traj_reset_train", O.TRAJ_F_REAL | O.TRAJ_F_ADJUST_VEL | O.TRAJ_F_INIT_HEADING),
+                     ("traj_reset_inv", O.TRAJ_F_REAL | O.TRAJ_F_INIT_HEADING | O.TRAJ_F_INVERSION | O.TRAJ_F_SLOW)):
+        g = reference_traj_reset(24, 10, 11 + fl, fl)
+        np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **g)
+        print(name, g["verts"].shape)
     for name, N, seed, rough in (("post_step_rough", 8, 0, True), ("post_step_flat", 6, 1, False)):
         st = synth_state(N, seed, map_shape=(700, 700), rough=rough)
         out = reference_post_step(st)

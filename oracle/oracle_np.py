@@ -202,6 +202,90 @@ def calc_pos(verts, traj_ids, times):
     return ((F(1.0) - lerp) * p0 + lerp * p1).astype(F)
 
 
+TRAJ_RAND_COLS = 405   # uniform draws consumed per reset env, in the order TrajGenerator.reset draws them (see traj_reset)
+TRAJ_F_REAL, TRAJ_F_ADJUST_VEL, TRAJ_F_INIT_HEADING, TRAJ_F_INVERSION, TRAJ_F_SLOW = 1, 2, 4, 8, 16
+
+
+def traj_reset(verts, env_ids, init_pos, root_vel, U, flags, pool=None, dtheta_max=2.0, speed_min=0.0005, speed_max=3.0,
+               accel_max=2.0, sharp_turn_prob=0.02, hybrid_init_prob=0.5):
+    """TrajGenerator.reset (env/util/traj_generator.py:60-237) with the random draws made explicit.
+
+    U [n, 405] uniform [0,1): cols 0-99 torch.rand dtheta (:63), 100-199 sharp angles (:66), 200-299 the bernoulli draw
+    (:68, mask = u < p), 300 heading (:71), 301-400 dspeed (:74), 401 initial speed (:76), 402 real-data draw (:118),
+    403 pool pick (random.sample :128, here floor(u*P) - with replacement), 404 heading inversion (:196).
+    Flags: real_path (:116), adjust_root_vel (:98,:149), init_heading (:176), heading_inversion (:195), slow (:94).
+    Updates verts [N,101,3] in place for env_ids; returns inverted [n] bool."""
+    f = np.float32
+    n = len(env_ids)
+    nv = verts.shape[1]
+    S = nv - 1
+    dt = f(traj_dt())
+    U = U.astype(f)
+    init_pos = init_pos.astype(f); root_vel = root_vel.astype(f)
+    dtheta = (f(2) * U[:, 0:S] - f(1)) * f(dtheta_max) * dt
+    sharp = f(np.pi) * (f(2) * U[:, 100:100 + S] - f(1))
+    mask = U[:, 200:200 + S] < f(sharp_turn_prob)
+    dtheta[mask] = sharp[mask]
+    dtheta[:, 0] = f(np.pi) * (f(2) * U[:, 300] - f(1))
+    dspeed = (f(2) * U[:, 301:301 + S] - f(1)) * f(accel_max) * dt
+    dspeed[:, 0] = f(speed_max - speed_min) * U[:, 401] + f(speed_min)
+    speed = np.zeros_like(dspeed)
+    speed[:, 0] = dspeed[:, 0]
+    for i in range(1, S):
+        speed[:, i] = np.clip(speed[:, i - 1] + dspeed[:, i], f(speed_min), f(speed_max))
+    if flags & TRAJ_F_SLOW:
+        speed = speed / f(4)
+    if flags & TRAJ_F_ADJUST_VEL:
+        root_speed = np.linalg.norm(root_vel[:, :2], axis=-1)
+        speed = np.clip((root_speed / speed[:, 0])[:, None] * speed, f(speed_min), f(speed_max))
+    theta = np.cumsum(dtheta, -1, dtype=f)
+    dpos = np.stack([np.cos(theta), -np.sin(theta), np.zeros_like(theta)], -1) * (speed * dt)[..., None]
+    dpos[:, 0, 0:2] += init_pos[:, 0:2]
+    verts[env_ids, 0, 0:2] = init_pos[:, 0:2]
+    verts[env_ids, 1:] = np.cumsum(dpos, -2, dtype=f)
+    if flags & TRAJ_F_REAL:
+        real = U[:, 402] > f(hybrid_init_prob)
+        P = pool.shape[0]
+        pick = np.minimum((U[:, 403] * f(P)).astype(np.int64), P - 1)[real]
+        traj = pool[pick][:, :nv].astype(f).copy()
+        traj[..., 0:2] -= traj[:, :1, 0:2].copy()
+        if flags & TRAJ_F_ADJUST_VEL:
+            init_speed = np.maximum(np.linalg.norm(traj[:, 1] - traj[:, 0], axis=-1), f(speed_min) * dt)
+            ratio = np.linalg.norm(root_vel[real, :2], axis=-1) / init_speed * dt
+            traj[..., 0:2] *= ratio[:, None, None]
+        traj[..., 0:2] += init_pos[real, None, 0:2]
+        verts[np.asarray(env_ids)[real]] = traj
+    inverted = np.zeros(n, bool)
+    if flags & TRAJ_F_INIT_HEADING:
+        v = verts[env_ids].copy()
+        dinit = v[:, 1, :2] - v[:, 0, :2]
+        rmag = np.sqrt((root_vel ** 2).sum(1)); dmag = np.sqrt((dinit ** 2).sum(1))
+        root_rot = np.where(rmag > 0, np.arctan2(root_vel[:, 1], root_vel[:, 0]), f(0))
+        init_heading = np.where(dmag > 0, np.arctan2(dinit[:, 1], dinit[:, 0]), f(0))
+        rot = (init_heading - root_rot).astype(f)
+        if flags & TRAJ_F_INVERSION:
+            inverted = U[:, 404] > f(0.5)
+            rot[inverted] = init_heading[inverted] - root_rot[inverted] + f(np.pi)
+        origin = v[:, :1, 0:2].copy()
+        xy = v[:, :, 0:2] - origin
+        c, s_ = np.cos(rot)[:, None], np.sin(rot)[:, None]
+        v[:, :, 0] = xy[..., 0] * c + xy[..., 1] * s_ + origin[..., 0]        # bmm(xy, [[c,-s],[s,c]]) (:211-216)
+        v[:, :, 1] = -xy[..., 0] * s_ + xy[..., 1] * c + origin[..., 1]
+        verts[env_ids] = v
+    return inverted
+
+
+def reset_task_outputs(verts, env_ids, rb_pos, root_vel):
+    """HumanoidPedestrianTerrain._reset_task (:493-516) after the generator: waypoint_traj = _fetch_traj_samples at progress 0,
+    init_pose = rigid-body positions, init_vel = root xy velocity; returned as the vec-env getters expose them
+    (vec_task_wrappers.py:47-63: origin-relative waypoints and pose)."""
+    n = len(env_ids)
+    ids = np.repeat(np.asarray(env_ids), NUM_TRAJ_SAMPLES)
+    t = np.tile(np.arange(NUM_TRAJ_SAMPLES, dtype=np.float32) * np.float32(TRAJ_SAMPLE_DT), n)
+    w = calc_pos(verts, ids, t).reshape(n, NUM_TRAJ_SAMPLES, 3)
+    return (w - w[:, :1]).astype(np.float32), (rb_pos - rb_pos[:, :1]).astype(np.float32), root_vel[:, :2].astype(np.float32)
+
+
 def progress_time(progress):
     """`self.progress_buf * self.dt` (int64 tensor * python float -> float32)."""
     return (progress.astype(F) * F(CONTROL_DT)).astype(F)

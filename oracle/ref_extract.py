@@ -106,6 +106,14 @@ def load():
         f.write(meth)
     methm = _import_path("emloco_ref_meth", p2)
 
+    # TrajGenerator.reset (traj_generator.py:60-237) on a holder class; its module-level `torch` / `random` names are
+    # swapped by make_golden for proxies that replay recorded uniform draws
+    p3 = os.path.join(tmp, "emloco_ref_trajreset.py")
+    with open(p3, "w") as f:
+        f.write("import numpy as np\nimport random\nimport torch\n\nclass TrajResetHolder:\n" + _lines(tg, 60, 237)
+                + "\n" + _lines(tg, 261, 262))
+    trajreset = _import_path("emloco_ref_trajreset", p3)
+
     # ValuePoseNet with a stub matplotlib
     if "matplotlib" not in sys.modules:
         mpl = types.ModuleType("matplotlib")
@@ -118,7 +126,7 @@ def load():
     rms = _import_path("emloco_ref_rms", os.path.join(PACER, "utils/running_mean_std.py"))
 
     ns = types.SimpleNamespace(
-        torch=torch, itu=itu, ptu=ptu, jit=jit, meth=methm,
+        torch=torch, itu=itu, ptu=ptu, jit=jit, meth=methm, trajreset=trajreset,
         ValuePoseNet=vpn.ValuePoseNet, RunningMeanStd=rms.RunningMeanStd,
         left_to_right_index=[0, 5, 6, 7, 8, 1, 2, 3, 4, 9, 10, 11, 12, 13, 19, 20, 21, 22, 23,
                              14, 15, 16, 17, 18],  # humanoid.py:334
