@@ -59,7 +59,8 @@ class TrajCfg(C.Structure):
                 ("num_waypoints", C.c_int32), ("reserved", C.c_int32)]
 
 
-TRAJ_REAL_PATH, TRAJ_ADJUST_ROOT_VEL, TRAJ_INIT_HEADING, TRAJ_HEADING_INVERSION, TRAJ_SLOW, TRAJ_RAND_COLS = 1, 2, 4, 8, 16, 405
+TRAJ_REAL_PATH, TRAJ_ADJUST_ROOT_VEL, TRAJ_INIT_HEADING, TRAJ_HEADING_INVERSION, TRAJ_SLOW, TRAJ_DEFERRED = 1, 2, 4, 8, 16, 32
+TRAJ_RAND_COLS = 405
 
 
 class Model(C.Structure):

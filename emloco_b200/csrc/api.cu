@@ -347,7 +347,12 @@ static int check_traj_cfg(const emloco_traj_cfg* c) {
 }
 
 int emloco_traj_reset(emloco_sim* s, const emloco_traj_cfg* c, void* stream) {
-    if (!s || !c) return fail(EMLOCO_EINVAL, "emloco_traj_reset: null argument");
+    if (!s) return fail(EMLOCO_EINVAL, "emloco_traj_reset: null sim");
+    if (!c) {
+        if (s->traj_on != 2) return fail(EMLOCO_EINVAL, "emloco_traj_reset: no deferred stage stored (emloco_set_traj_reset with EMLOCO_TRAJ_DEFERRED)");
+        CK(eml_traj_reset(s, s->traj, 1, (cudaStream_t)stream), "trajectory reset kernel");
+        return EMLOCO_OK;
+    }
     if (int e = check_traj_cfg(c)) return e;
     CK(eml_traj_reset(s, *c, 0, (cudaStream_t)stream), "trajectory reset kernel");
     return EMLOCO_OK;
@@ -357,7 +362,7 @@ int emloco_set_traj_reset(emloco_sim* s, const emloco_traj_cfg* c) {
     if (!s) return fail(EMLOCO_EINVAL, "emloco_set_traj_reset: null sim");
     if (!c) { s->traj_on = 0; return EMLOCO_OK; }
     if (int e = check_traj_cfg(c)) return e;
-    s->traj = *c; s->traj_on = 1;
+    s->traj = *c; s->traj_on = (c->flags & EMLOCO_TRAJ_DEFERRED) ? 2 : 1;
     return EMLOCO_OK;
 }
 

@@ -415,6 +415,6 @@ cudaError_t eml_reset_done(emloco_sim* s, const float* d_init_root, const float*
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     e = eml_launch_post_reset(s, s->traj_on, st);
-    if (e != cudaSuccess || !s->traj_on) return e;
+    if (e != cudaSuccess || s->traj_on != 1) return e;   // 2 = deferred: the caller runs the stage (emloco_traj_reset(sim, NULL))
     return eml_traj_reset(s, s->traj, 1, st);       // _reset_task runs after the observations (humanoid_amp_task.py:54-57)
 }

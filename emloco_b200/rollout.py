@@ -23,7 +23,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .policy import (ACTIONS, AMP_OBS, OBS, AMPSeptValueNetwork, RolloutNets, RunningMeanStd)
+from .policy import (ACTIONS, AMP_OBS, OBS, AMPSeptValueNetwork, Fork, RolloutNets, RunningMeanStd)
 from .sim import EmlocoSim, _ptr, _stream, gae
 from .synthetic import synthetic_env_state
 
@@ -33,7 +33,7 @@ class Rollout:
                  task_reward_w=0.5, disc_reward_w=0.5, disc_reward_scale=2.0, inversion_penalty_scale=0.3,
                  step_to_pred=144, normalize_value=True, net=None, obs_norm=None, amp_norm=None, value_norm=None,
                  recompute_disc=True, valuenet=None, fuse_sinks=True, concurrent=True, reuse_values=False, traj_flags=None,
-                 traj_pool=None):
+                 traj_pool=None, traj_deferred=None):
         self.N, self.T, self.device = int(num_envs), int(horizon), int(device)
         self.gamma, self.tau = gamma, tau
         self.task_reward_w, self.disc_reward_w, self.disc_reward_scale = task_reward_w, disc_reward_w, disc_reward_scale
@@ -51,6 +51,7 @@ class Rollout:
         self.nets = RolloutNets(self.net, self.obs_norm, self.amp_norm, self.N, tensor_cores=tensor_cores, concurrent=concurrent,
                                 amp_slots=self.T if (tensor_cores and recompute_disc) else 1)
         self.concurrent = bool(concurrent)
+        self._side = Fork(dev, 1) if concurrent else None      # outer branches (noise draw, trajectory reset) around the nets' own fork
         # value reuse needs the operand sinks (the compact critic reads the rows the post-step kernel wrote)
         self.reuse_values = bool(reuse_values) and bool(tensor_cores) and bool(fuse_sinks)
         self.gen = torch.Generator(device=dev).manual_seed(seed + 1)
@@ -84,11 +85,13 @@ class Rollout:
         self.init_vel = self.init_root[:, 7:9].contiguous()
         # traj_flags (emloco TRAJ_* bits, None = off): every later env reset regenerates the env's trajectory and these
         # three LocoVal inputs on the device (emloco_set_traj_reset: TrajGenerator.reset + _reset_task)
-        self.inverted = None
+        self.inverted, self._traj_deferred = None, False
         if traj_flags is not None:
             self.inverted = torch.zeros(N, device=dev, dtype=torch.uint8)
             self.traj_pool = None if traj_pool is None else torch.as_tensor(traj_pool, dtype=torch.float32).to(dev).contiguous()
-            self.sim.set_traj_reset(self.sim.traj_cfg(flags=traj_flags, seed=seed, pool=self.traj_pool, waypoint_traj=self.waypoint_traj,
+            # with parallel branches the stage is deferred: it overlaps the policy pass (nothing before post_step reads it)
+            self._traj_deferred = bool(concurrent) if traj_deferred is None else (bool(traj_deferred) and bool(concurrent))
+            self.sim.set_traj_reset(self.sim.traj_cfg(flags=traj_flags | (_lib.TRAJ_DEFERRED if self._traj_deferred else 0), seed=seed, pool=self.traj_pool, waypoint_traj=self.waypoint_traj,
                                                       init_pose=self.init_pose, init_vel=self.init_vel, inverted=self.inverted))
         if valuenet is None:
             from .value_pose_net import ValuePoseNet
@@ -146,7 +149,16 @@ class Rollout:
         nxt = n + 1                                                                    # row T is the spare row
         slot = n if getattr(nets, "amp_slots", 1) > 1 else 0                           # block of the stored discriminator operands
 
+        def draw_noise():
+            cur["noise"] = self.noise.normal_(generator=self.gen) if noise is None else noise
+
         def seg_reset():                                                               # env_reset(done_indices), :45-46
+            if self.concurrent:
+                self._side.run(reset_main, draw_noise)
+            else:
+                reset_main(); draw_noise()
+
+        def reset_main():
             if fuse:
                 if n == 0:
                     mb["obses"][0].copy_(mb["obses"][self.T])                          # observation that followed the last horizon
@@ -156,9 +168,14 @@ class Rollout:
                 sim.set_post_sinks(None)
                 sim.reset_done(self.init_root, self.init_dof)
                 mb["obses"][n].copy_(sim.obs)
-            cur["noise"] = self.noise.normal_(generator=self.gen) if noise is None else noise
 
         def seg_policy():                                                              # get_action_values, :53
+            if self._traj_deferred:
+                self._side.run(policy_main, sim.traj_reset)                             # _reset_task overlaps the policy pass
+            else:
+                policy_main()
+
+        def policy_main():
             # the heads write straight into row n of the experience tensors (experience_buffer.update_data, :47-56)
             cur["res"] = nets.action_values(sim.obs, cur["noise"], mu_out=mb["mus"][n], task_value_out=mb["task_values"][n],
                                             actions_out=mb["actions"][n], neglogp_out=mb["neglogpacs"][n], operands_ready=fuse)

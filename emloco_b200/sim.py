@@ -115,7 +115,7 @@ class EmlocoSim:
             if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == shp):
                 raise _lib.EmlocoError(f"reset_done: initial state must be contiguous float32 CUDA of shape {shp}")
         _lib.check(self.lib.emloco_reset_done(self._h, _ptr(init_root), _ptr(init_dof), _stream()), "emloco_reset_done")
-        _lib.launch_count += self._traj_on            # the appended trajectory-reset stage
+        _lib.launch_count += int(self._traj_on == 1)  # the appended trajectory-reset stage
 
     def traj_cfg(self, flags=0, seed=0, pool=None, uniform=None, waypoint_traj=None, init_pose=None, init_vel=None,
                  inverted=None, origin_relative=True, **over):
@@ -154,14 +154,16 @@ class EmlocoSim:
         c._keep = keep
         return c
 
-    def traj_reset(self, cfg):
-        """TrajGenerator.reset + _reset_task outputs for the envs whose reset_buf is set right now."""
-        _lib.check(self.lib.emloco_traj_reset(self._h, C.byref(cfg), _stream()), "emloco_traj_reset")
+    def traj_reset(self, cfg=None):
+        """TrajGenerator.reset + _reset_task outputs for the envs whose reset_buf is set right now.  cfg None: the deferred
+        stage stored by set_traj_reset(cfg with TRAJ_DEFERRED), which also clears reset/terminate."""
+        _lib.check(self.lib.emloco_traj_reset(self._h, None if cfg is None else C.byref(cfg), _stream()), "emloco_traj_reset")
 
     def set_traj_reset(self, cfg=None):
         """reset_done regenerates the trajectories of the envs it resets (None: off)."""
         _lib.check(self.lib.emloco_set_traj_reset(self._h, None if cfg is None else C.byref(cfg)), "emloco_set_traj_reset")
-        self._traj_keep, self._traj_on = cfg, int(cfg is not None)
+        self._traj_keep = cfg
+        self._traj_on = 0 if cfg is None else (2 if cfg.flags & _lib.TRAJ_DEFERRED else 1)
 
     def set_post_sinks(self, sinks=None):
         """Optional extra outputs of post_step / reset_done (emloco_post_sinks); None clears them."""

@@ -189,6 +189,7 @@ int emloco_reset_done(emloco_sim* sim, const float* d_init_root, const float* d_
 #define EMLOCO_TRAJ_INIT_HEADING       4
 #define EMLOCO_TRAJ_HEADING_INVERSION  8
 #define EMLOCO_TRAJ_SLOW              16
+#define EMLOCO_TRAJ_DEFERRED          32   /* emloco_set_traj_reset only, see there */
 #define EMLOCO_TRAJ_RAND_COLS        405
 typedef struct emloco_traj_cfg {
     float    dtheta_max, speed_min, speed_max, accel_max, sharp_turn_prob;   /* 2, 0.0005, 3, 2, 0.02 (pacer.yaml:55-61) */
@@ -202,12 +203,16 @@ typedef struct emloco_traj_cfg {
     int32_t  num_waypoints; int32_t reserved;
 } emloco_traj_cfg;
 
-/* Regenerates the trajectories of the envs whose reset_buf is set RIGHT NOW (flags are left as they are). */
+/* Regenerates the trajectories of the envs whose reset_buf is set RIGHT NOW (flags are left as they are).
+ * cfg == NULL runs the stage stored by emloco_set_traj_reset(..EMLOCO_TRAJ_DEFERRED..) and clears reset/terminate. */
 int emloco_traj_reset(emloco_sim* sim, const emloco_traj_cfg* cfg, void* stream);
 
 /* Makes emloco_reset_done run the trajectory reset as its last stage - after the observations of the reset envs were
  * recomputed from the OLD polyline, which is the reference's order (humanoid_amp_task.py:54-57: `super()._reset_envs`
- * computes observations, then `_reset_task`).  NULL switches it off.  The struct is copied. */
+ * computes observations, then `_reset_task`).  NULL switches it off.  The struct is copied.
+ * With EMLOCO_TRAJ_DEFERRED in cfg->flags emloco_reset_done leaves reset/terminate set and does NOT run the stage: the
+ * caller runs it with emloco_traj_reset(sim, NULL, stream) - on another stream if it likes, nothing before the next
+ * emloco_post_step reads the polylines - any time before that post-step. */
 int emloco_set_traj_reset(emloco_sim* sim, const emloco_traj_cfg* cfg);
 
 /* ---- LocoVal: ValuePoseNet (pacer/pacer/learning/value_pose_net.py:10-159) ----

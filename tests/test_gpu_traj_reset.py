@@ -89,7 +89,7 @@ def test_philox_stream_properties():
     np.testing.assert_allclose(a[:, 0, :2], root[:, 0:2].cpu().numpy(), rtol=0, atol=0)
     seg = np.linalg.norm(np.diff(a[:, :, :2], axis=1), axis=-1)
     dt = 168 * (2 / 60) / 100
-    assert seg.max() <= 3.0 * dt * (1 + 1e-4) and seg.min() >= 0.0005 * dt * (1 - 1e-2)
+    assert seg.max() <= 3.0 * dt * (1 + 1e-4) and seg.min() >= 0.0005 * dt - 1e-5     # positions ~50 m: fp32 ulp 4e-6
     head = np.arctan2(a[:, 1, 1] - a[:, 0, 1], a[:, 1, 0] - a[:, 0, 0])
     hist = np.histogram(head, bins=8, range=(-np.pi, np.pi))[0]
     assert hist.min() > N / 8 * 0.5 and hist.max() < N / 8 * 1.6                   # U(-pi, pi) initial heading
@@ -137,3 +137,31 @@ def test_reset_done_runs_traj_reset_after_the_observations():
     np.testing.assert_allclose(pose.cpu().numpy()[ids], rb[ids] - rb[ids][:, :1], atol=1e-6)
     sim.set_traj_reset(None)
     R.close()
+
+
+def test_rollout_with_device_traj_reset_deferred_equals_inline():
+    """The deferred stage (overlapping the policy pass on a side branch) gives the same rollout as the inline stage."""
+    from emloco_b200.rollout import Rollout
+    from emloco_b200.synthetic import synthetic_traj_pool
+    n, outs = 128, []
+    pool = synthetic_traj_pool(16, 0)
+    for deferred in (False, True):
+        R = Rollout(n, seed=2, tensor_cores=True, concurrent=True, traj_deferred=deferred, traj_flags=1 | 2 | 4 | 8, traj_pool=pool,
+                    horizon=8)
+        assert R._traj_deferred == deferred
+        R.sim.progress.fill_(160)                     # every env times out inside the horizon
+        R.sim.progress[: n // 2] = 163
+        torch.manual_seed(0)
+        for k in range(8):
+            R.step(k, noise=torch.randn(n, 69, device="cuda", generator=torch.Generator(device="cuda").manual_seed(k)))
+        torch.cuda.synchronize()
+        outs.append(dict(verts=R.sim.traj_verts.cpu().numpy().copy(), way=R.waypoint_traj.cpu().numpy().copy(),
+                         pose=R.init_pose.cpu().numpy().copy(), vel=R.init_vel.cpu().numpy().copy(), inv=R.inverted.cpu().numpy().copy(),
+                         dones=R.mb["dones"].cpu().numpy().copy(), rewards=R.mb["rewards"].cpu().numpy().copy(),
+                         obs=R.mb["obses"].cpu().numpy().copy()))
+        R.close()
+    a, b = outs
+    assert a["dones"].sum() >= n                                       # the resets happened
+    for k in a:
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+    assert 0 < a["inv"].sum() < n                                      # heading inversion drew both ways
