@@ -233,22 +233,35 @@ def run_ours(args):
     h_obs, h_noise = pin(N, 1422), pin(N, 69).normal_()
     h_out = dict(obs=pin(N, 1422), rew=pin(N), reset=pin(N, dt=torch.int64), actions=pin(N, 69), neglogp=pin(N), values=pin(N, 1))
     h_obs.copy_(R.sim.obs)
-    d_obs_in = torch.empty(N, 1422, device="cuda")
     Ke = max(HORIZON, min(K, 2 * HORIZON))
+    copy_stream, env_done = torch.cuda.Stream(), torch.cuda.Event()
+    host = {"obs": h_obs}                               # the two pinned observation buffers swap roles every step
+
+    def read_back_env():
+        # the env step is done: next obs / reward / dones travel back on a copy stream while critic, discriminator and the
+        # bookkeeping of the same step still run (VecTaskPython.step returns them to the rl_device, vec_task.py:125-134)
+        env_done.record()
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(env_done)
+            h_out["obs"].copy_(R.sim.obs, non_blocking=True); h_out["rew"].copy_(R.sim.rew, non_blocking=True)
+            h_out["reset"].copy_(R.sim.reset, non_blocking=True)
 
     def e2e_step(i):
         n = i % HORIZON
-        d_obs_in.copy_(h_obs, non_blocking=True)
+        R.sim.obs.copy_(host["obs"], non_blocking=True)  # the policy reads the obs the host handed over
         R.noise.copy_(h_noise, non_blocking=True)
-        R.sim.obs.copy_(d_obs_in)                       # the policy reads the obs the host handed over
-        (R.step_graphed_host_noise if graphs else (lambda k: R.step(k, noise=R.noise)))(n)
+        if graphs:
+            R.step_graphed_host_noise(n, after_env_step=read_back_env)
+        else:
+            R.step(n, noise=R.noise, host_obs=True)
+            read_back_env()
         if n == HORIZON - 1:
             (R.finish_graphed if graphs else R.finish)()
-        h_out["obs"].copy_(R.sim.obs, non_blocking=True); h_out["rew"].copy_(R.sim.rew, non_blocking=True)
-        h_out["reset"].copy_(R.sim.reset, non_blocking=True); h_out["actions"].copy_(R.mb["actions"][n], non_blocking=True)
+        h_out["actions"].copy_(R.mb["actions"][n], non_blocking=True)
         h_out["neglogp"].copy_(R.mb["neglogpacs"][n], non_blocking=True); h_out["values"].copy_(R.mb["values"][n], non_blocking=True)
+        copy_stream.synchronize()
         torch.cuda.current_stream().synchronize()       # the host consumes the results before issuing the next step
-        h_obs.copy_(h_out["obs"])
+        host["obs"], h_out["obs"] = h_out["obs"], host["obs"]      # what came back is what the next step is fed (no host memcpy)
     for i in range(HORIZON if graphs else 3):
         e2e_step(i)
     barrier()

@@ -145,7 +145,8 @@ class Rollout:
     def _segment_fns(self, n, noise=None, host_obs=False):
         sim, nets, mb, cur = self.sim, self.nets, self.mb, self._cur
 
-        fuse = self.fuse and not host_obs
+        fuse = self.fuse                                # post-step side: experience rows + operands of critic(next obs) / disc
+        fuse_in = self.fuse and not host_obs            # policy side: host-provided observations need their operands re-derived
         nxt = n + 1                                                                    # row T is the spare row
         slot = n if getattr(nets, "amp_slots", 1) > 1 else 0                           # block of the stored discriminator operands
 
@@ -159,7 +160,7 @@ class Rollout:
                 reset_main(); draw_noise()
 
         def reset_main():
-            if fuse:
+            if fuse_in:
                 if n == 0:
                     mb["obses"][0].copy_(mb["obses"][self.T])                          # observation that followed the last horizon
                 sim.set_post_sinks(nets.post_sinks(obs_copy=mb["obses"][n]))           # reset rows are patched in place
@@ -178,7 +179,7 @@ class Rollout:
         def policy_main():
             # the heads write straight into row n of the experience tensors (experience_buffer.update_data, :47-56)
             cur["res"] = nets.action_values(sim.obs, cur["noise"], mu_out=mb["mus"][n], task_value_out=mb["task_values"][n],
-                                            actions_out=mb["actions"][n], neglogp_out=mb["neglogpacs"][n], operands_ready=fuse)
+                                            actions_out=mb["actions"][n], neglogp_out=mb["neglogpacs"][n], operands_ready=fuse_in)
 
         def seg_physics():                                                             # env_step: pre_physics + simulate
             sim.physics_step(cur["res"]["actions"])
@@ -196,7 +197,7 @@ class Rollout:
         # value reuse: critic(next obs) is NOT recomputed for envs that are not reset - the next step's policy pass evaluates
         # the critic on that very observation; only timed-out envs need their terminal observation evaluated now.  The last
         # step of the horizon has no next step inside the horizon and runs the full pass.
-        reuse = self.reuse_values and fuse and n < self.T - 1
+        reuse = self.reuse_values and fuse_in and n < self.T - 1
 
         def seg_critic():                                                              # _eval_critic(next obs), :85
             if reuse:
@@ -221,7 +222,7 @@ class Rollout:
                     _ptr(cur["cidx"]), _ptr(cur["ccount"]), _ptr(mb["dones"][n - 1]) if prev else None,
                     _ptr(mb["next_values"][n - 1]) if prev else None, _stream()), "emloco_rollout_record_deferred")
                 return
-            if self.reuse_values and fuse and n > 0:
+            if self.reuse_values and fuse_in and n > 0:
                 # last step of the horizon (full critic pass below): it still has to complete step n-1
                 _lib.check(_lib.load().emloco_fill_next_values(
                     C.byref(self.rcfg), _ptr(cur["res"]["values"]), _ptr(mb["dones"][n - 1]), _ptr(mb["next_values"][n - 1]), self.N,
@@ -319,9 +320,18 @@ class Rollout:
             return
         self._replay(n, lambda: self.step(n))
 
-    def step_graphed_host_noise(self, n):
-        """step(n) with the policy noise taken from self.noise as the caller filled it (no generator call in the graph)."""
-        self._replay(("hn", n), lambda: self.step(n, noise=self.noise, host_obs=True))
+    def step_graphed_host_noise(self, n, after_env_step=None):
+        """step(n) on observations and policy noise the caller put into sim.obs / self.noise (no generator call in the graph).
+        after_env_step: called between the env step (reset .. post_step) and the critic / discriminator / bookkeeping part, so
+        that a vec-env style caller can start reading the step's observations back while the rest of the step runs."""
+        if after_env_step is None:
+            self._replay(("hn", n), lambda: self.step(n, noise=self.noise, host_obs=True))
+            return
+        fns = lambda: self._segment_fns(n, self.noise, True)
+        k = 4                                                                           # reset, policy, physics, post_step
+        self._replay(("hnA", n), lambda: [f() for f in fns()[:k]])
+        after_env_step()
+        self._replay(("hnB", n), lambda: [f() for f in fns()[k:]])
 
     def step_segments_graphed(self, n):
         """step(n) as seven per-segment graphs with a timing event between them: per-segment device time without host

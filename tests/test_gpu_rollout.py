@@ -320,3 +320,44 @@ def test_value_reuse_is_bit_identical_to_the_second_critic_pass():
             np.testing.assert_array_equal(oa[key].cpu().numpy(), ob[key].cpu().numpy(), err_msg=f"{key} rep {rep}")
     assert timeouts > 50, "the test must exercise resets"
     A.close(); B.close()
+
+
+def test_host_observation_step_matches_device_step():
+    """The vec-env boundary with host buffers (rl_device = cpu, vec_task.py:125-134): sim.obs is overwritten with the
+    observations the host hands back (here: the same values after a D2H/H2D round trip) and the policy operands are re-derived
+    from it; the split replay (env step | read-back hook | critic, discriminator, bookkeeping) does the same work as one graph."""
+    from emloco_b200.policy import AMPSeptValueNetwork
+    from emloco_b200.rollout import Rollout
+    n, T = 96, 4
+    torch.manual_seed(8)
+    net = AMPSeptValueNetwork()
+    A = Rollout(n, seed=4, net=net, tensor_cores=True, horizon=T)
+    B = Rollout(n, seed=4, net=net, tensor_cores=True, horizon=T)
+    C_ = Rollout(n, seed=4, net=net, tensor_cores=True, horizon=T)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    seen = []
+    for rep in range(2):                      # rep 0 warms up (eager), rep 1 replays graphs in B and C_
+        for k in range(T):
+            noise = torch.randn(n, 69, device="cuda", generator=g)
+            A.step(k, noise=noise)
+            for R, hook in ((B, None), (C_, lambda: seen.append(C_.sim.obs.clone()))):
+                h = R.sim.obs.cpu()                                        # D2H
+                R.sim.obs.copy_(h.cuda())                                  # H2D
+                R.noise.copy_(noise)
+                if rep == 0:
+                    R.step(k, noise=R.noise, host_obs=True)
+                else:
+                    R.step_graphed_host_noise(k, after_env_step=hook)
+        oa, ob, oc = A.finish(), B.finish(), C_.finish()
+        torch.cuda.synchronize()
+        for key in ("obses", "actions", "mus", "values", "next_values", "rewards", "amp_rewards", "dones", "returns", "flip_obs"):
+            a, b, c = oa[key].cpu().numpy(), ob[key].cpu().numpy(), oc[key].cpu().numpy()
+            np.testing.assert_array_equal(b, c, err_msg=key)               # one graph == split graphs
+            if key == "dones":
+                np.testing.assert_array_equal(a, b)
+            else:
+                np.testing.assert_allclose(a[0], b[0], rtol=1e-3, atol=1e-3, err_msg=key)      # first step: same state, 1-ulp operand difference
+                np.testing.assert_allclose(a, b, rtol=2e-2, atol=5e-2, err_msg=key)            # later steps drift through the physics
+    assert len(seen) == T                                                  # the hook ran between the two halves of every step
+    np.testing.assert_array_equal(seen[-1].cpu().numpy(), C_.sim.obs.cpu().numpy())   # ... after post_step wrote the observations
+    A.close(); B.close(); C_.close()
