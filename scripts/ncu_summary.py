@@ -28,6 +28,20 @@ def launches(tag, path):
         out.append(f"| `{k}` | {n} | {t / 1e3:.1f} | {t / n / 1e3:.1f} | {100 * t / tot:.1f}% |")
     open(os.path.join(ROOT, "profiles", f"{tag}_launches.md"), "w").write("\n".join(out) + "\n")
     print("\n".join(out))
+    # one control step in launch order: from one physics launch to the next
+    rows = list(csv.DictReader(lines))
+    ph = [i for i, r in enumerate(rows) if "physics_soa_kernel" in r["Kernel Name"]]
+    if len(ph) >= 3:
+        a, b = ph[-3], ph[-2]
+        o2 = [f"# {tag}: one control step in launch order (eager, serialised; ncu gpu__time_duration, cold cache)", "",
+              "| # | kernel | grid | block | us |", "|---|---|---|---|---|"]
+        tot2 = 0.0
+        for i, r in enumerate(rows[a:b]):
+            v = float(r["Metric Value"].replace(",", "")) * (1e3 if r.get("Metric Unit", "ns") in ("us", "usecond") else 1)
+            tot2 += v
+            o2.append(f"| {i} | `{r['Kernel Name'].split('(')[0][:70]}` | {r.get('Grid Size', '')} | {r.get('Block Size', '')} | {v / 1e3:.1f} |")
+        o2.append(f"\nsum {tot2 / 1e3:.1f} us")
+        open(os.path.join(ROOT, "profiles", f"{tag}_step.md"), "w").write("\n".join(o2) + "\n")
 
 
 WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
