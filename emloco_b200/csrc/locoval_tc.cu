@@ -6,7 +6,7 @@
 // bf16x3 tcgen05 MMAs (same split-precision scheme as linear_tc.cu: x = hi + lo, Al*Wh + Ah*Wl + Ah*Wh into fp32 TMEM), which
 // leaves the kernel bound by its 404 B/score of HBM traffic and the per-row feature generation.
 //
-// CTA = 128 threads = 128 samples (thread = row = TMEM lane), persistent over 128-row tiles, two CTAs per SM:
+// CTA = 128 rows (row = TMEM lane), two threads per row, persistent over 128-row tiles, two CTAs per SM:
 //   1. each thread reads its row (waypoints, pose, velocity), applies the heading normalisation (:73-103) and the toe / spine
 //      masks (:141-144), and writes the 100 features as bf16 hi / lo into the K-major 128B-swizzled A tile (written by hand
 //      with the same XOR pattern TMA would apply), then fence.proxy.async
@@ -33,7 +33,8 @@ constexpr int OFF_W2_HI = OFF_W1_LO + 2 * W1_ATOM, OFF_W2_LO = OFF_W2_HI + W2_AT
 constexpr int OFF_F32 = OFF_W2_LO + W2_ATOM;                // b1[64] b2[32] w3[32] b3[1]
 constexpr int OFF_BAR = OFF_F32 + (64 + 32 + 32 + 4) * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 16 + 1024;             // + alignment slack  (~107 KB: two CTAs per SM)
-constexpr int ST_TRAJ = 0, ST_POSE = 20480, ST_VEL = ST_POSE + 128 * 72 * 4;   // raw-row staging inside the A-tile bytes (< 64 KB)
+constexpr int POSE_PITCH = 19;             // float4 per staged pose row (18 used): 76-float pitch, conflict-free LDS.128
+constexpr int ST_TRAJ = 0, ST_POSE = 20480, ST_VEL = ST_POSE + 128 * POSE_PITCH * 16;   // raw-row staging inside the A-tile bytes (< 64 KB)
 constexpr int TMEM_COLS = 128;              // D1: columns 0..63, D2: columns 64..95
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -90,7 +91,10 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-__global__ void __launch_bounds__(128, 2)
+// CTA = 256 threads = 128 rows x 2 halves (thread pair per row: half 0 = warps 0-3 builds features 0..55 and reads D1 columns
+// 0..31, half 1 = warps 4-7 features 56..111 and D1 columns 32..63; both halves of a row sit on the same TMEM lanes).  Two CTAs
+// per SM = 16 warps: the per-row work is a long dependent chain, so the kernel is latency-bound and lives off warps in flight.
+__global__ void __launch_bounds__(256, 2)
 locoval_tc_kernel(const float* __restrict__ traj, int stride, float* pose_rw, const float* __restrict__ vel,
                   const float* __restrict__ weights, float* __restrict__ value, long long B, int flags) {
     extern __shared__ uint8_t smem_raw[];
@@ -100,7 +104,7 @@ locoval_tc_kernel(const float* __restrict__ traj, int stride, float* pose_rw, co
     float* s_b2 = s_b1 + 64; float* s_w3 = s_b2 + 32; float* s_b3 = s_w3 + 32;
     const uint32_t bar = sbase + OFF_BAR;
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(sm + OFF_BAR + 8);
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, half = tid >> 7, rt = tid & 127;
     const bool hide_toe = flags & 4, hide_spine = flags & 8, normalize = flags & 16, writeback = flags & 32;
 
     // ---- one-time: weights -> bf16 hi/lo, K-major swizzled, zero padded; biases; barrier; TMEM ----
@@ -108,14 +112,14 @@ locoval_tc_kernel(const float* __restrict__ traj, int stride, float* pose_rw, co
         const float* w1 = weights; const float* b1 = w1 + IN * H1;
         const float* w2 = b1 + H1; const float* b2 = w2 + H1 * H2;
         const float* w3 = b2 + H2; const float* b3 = w3 + H2;
-        for (int i = tid; i < N1 * 128 / 2; i += 128) {                    // pairs (n, k..k+1) of the 64 x 128 padded W1
+        for (int i = tid; i < N1 * 128 / 2; i += 256) {                    // pairs (n, k..k+1) of the 64 x 128 padded W1
             const int n = i / 64, k = (i % 64) * 2;
             float a = (n < H1 && k < IN) ? w1[n * IN + k] : 0.f, b = (n < H1 && k + 1 < IN) ? w1[n * IN + k + 1] : 0.f;
             uint32_t h, l; split2(a, b, h, l);
             const uint32_t off = sw128(N1, n, k);
             *reinterpret_cast<uint32_t*>(sm + OFF_W1_HI + off) = h; *reinterpret_cast<uint32_t*>(sm + OFF_W1_LO + off) = l;
         }
-        for (int i = tid; i < N2 * 64 / 2; i += 128) {                     // 32 x 64 padded W2
+        for (int i = tid; i < N2 * 64 / 2; i += 256) {                     // 32 x 64 padded W2
             const int n = i / 32, k = (i % 32) * 2;
             float a = (n < H2 && k < H1) ? w2[n * H1 + k] : 0.f, b = (n < H2 && k + 1 < H1) ? w2[n * H1 + k + 1] : 0.f;
             uint32_t h, l; split2(a, b, h, l);
@@ -133,86 +137,118 @@ locoval_tc_kernel(const float* __restrict__ traj, int stride, float* pose_rw, co
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(TMEM_COLS));
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // weight tiles are read by the async proxy (MMA)
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
+    const long long tiles = (B + 127) / 128;
+    // the tile's raw rows -> shared memory with coalesced 16-byte cp.async (every piece of the 52 KB in flight at once, no
+    // register round trip); issued by half 1.  The staging area aliases the A tile.  Pose rows are placed at a 76-float pitch
+    // so that the per-row LDS.128 reads below are bank-conflict free (72 would be 2-way)
+    auto stage_tile = [&](long long t) {
+        const int i0 = tid - 128;
+        const long long r0 = t * 128;
+        const int rows = (int)((B - r0) < 128 ? (B - r0) : 128);
+        {
+            const float* src = traj + r0 * 13 * stride;
+            const int nfl = rows * 13 * stride;
+            float* dst = reinterpret_cast<float*>(sm + ST_TRAJ);
+            for (int i = i0; i < nfl / 4; i += 128)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(reinterpret_cast<float4*>(dst) + i)), "l"(reinterpret_cast<const float4*>(src) + i) : "memory");
+            for (int i = (nfl & ~3) + i0; i < nfl; i += 128) dst[i] = src[i];
+        }
+        {
+            const float4* src = reinterpret_cast<const float4*>(pose_rw + r0 * 72);
+            for (int i = i0; i < rows * 18; i += 128) {
+                const int r = i / 18, c4 = i - r * 18;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + ST_POSE + (uint32_t)(r * POSE_PITCH + c4) * 16u), "l"(src + i) : "memory");
+            }
+        }
+        {
+            const float* src = vel + r0 * 2;
+            const int nfl = rows * 2;
+            float* dst = reinterpret_cast<float*>(sm + ST_VEL);
+            for (int i = i0; i < nfl / 4; i += 128)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(reinterpret_cast<float4*>(dst) + i)), "l"(reinterpret_cast<const float4*>(src) + i) : "memory");
+            for (int i = (nfl & ~3) + i0; i < nfl; i += 128) dst[i] = src[i];
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    };
+    if (half == 1 && (long long)blockIdx.x < tiles) stage_tile(blockIdx.x);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // weight tiles are read by the async proxy (MMA)
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(s_tmem);
     const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N1 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N2 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     uint32_t phase = 0;
 
-    const long long tiles = (B + 127) / 128;
     for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
-        const long long b = t * 128 + tid;
+        const long long b = t * 128 + rt;
         const bool ok = b < B;
-
-        // ---- 1a. the tile's raw rows -> shared memory with coalesced 16-byte loads.  The staging area aliases the A tile:
-        //          rows are pulled into registers before the tile is written (per-row global loads would cost one LSU
-        //          wavefront per lane: 58 uncoalesced loads x 32 lanes per warp dominated the first version of this kernel)
+        // ---- 1b. this thread's 56 features of its row (registers, statically indexed) ----
+        float f[56];
         {
-            const long long r0 = t * 128;
-            const int rows = (int)((B - r0) < 128 ? (B - r0) : 128);
-            auto stage = [&](const float* src, int row_len, int byte_off) {
-                const int nfl = rows * row_len;
-                float* dst = reinterpret_cast<float*>(sm + byte_off);
-                const float4* g4 = reinterpret_cast<const float4*>(src);
-                // cp.async: every 16-byte piece of the tile is in flight at once (51 KB per CTA), no register round trip
-                for (int i = tid; i < nfl / 4; i += 128)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(reinterpret_cast<float4*>(dst) + i)), "l"(g4 + i) : "memory");
-                for (int i = (nfl & ~3) + tid; i < nfl; i += 128) dst[i] = src[i];
-            };
-            stage(traj + r0 * 13 * stride, 13 * stride, ST_TRAJ);
-            stage(pose_rw + r0 * 72, 72, ST_POSE);
-            stage(vel + r0 * 2, 2, ST_VEL);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
-        __syncthreads();
-        // ---- 1b. features of this row (registers) ----
-        float f[K1];                                                       // statically indexed
-        {
-            const int row = ok ? tid : (int)(B - 1 - t * 128);             // tail rows recompute the last valid row
+            const int row = ok ? rt : (int)(B - 1 - t * 128);              // tail rows recompute the last valid row
             const float* tr = reinterpret_cast<const float*>(sm + ST_TRAJ) + row * 13 * stride;
             float c = 1.f, s = 0.f;
-            if (normalize) {                                               // _rotate_normalization (:76-84)
+            if (normalize) {                                               // _rotate_normalization (:76-84): theta = atan2(y1, x1)
                 const float x1 = tr[stride], y1 = tr[stride + 1];
                 const float xe = fabsf(x1) < 1e-10f ? 1e-10f : x1;
-                sincosf(atan2f(y1, xe), &s, &c);
+                const float rn = rsqrtf(xe * xe + y1 * y1);                // cos / sin of atan2(y, x) without the angle
+                c = xe * rn; s = y1 * rn;
             }
+            const float4* p4 = reinterpret_cast<const float4*>(sm + ST_POSE) + row * POSE_PITCH;
+            if (half == 0) {
 #pragma unroll
-            for (int n = 0; n < 13; ++n) {                                 // row-vector times [[c,-s],[s,c]] (:85-100)
-                const float x = tr[n * stride], y = tr[n * stride + 1];
-                f[2 * n] = x * c + y * s; f[2 * n + 1] = y * c - x * s;
+                for (int n = 0; n < 13; ++n) {                             // row-vector times [[c,-s],[s,c]] (:85-100)
+                    const float x = tr[n * stride], y = tr[n * stride + 1];
+                    f[2 * n] = x * c + y * s; f[2 * n + 1] = y * c - x * s;
+                }
+                // pose floats 0..29 = joints 0..9 -> features 26..55
+#pragma unroll
+                for (int i = 0; i < 7; ++i) { float4 v = p4[i]; f[26 + 4 * i] = v.x; f[27 + 4 * i] = v.y; f[28 + 4 * i] = v.z; f[29 + 4 * i] = v.w; }
+                { const float2 v = *reinterpret_cast<const float2*>(p4 + 7); f[54] = v.x; f[55] = v.y; }
+#pragma unroll
+                for (int j = 0; j < 10; ++j) {
+                    float xr = f[26 + 3 * j] * c + f[27 + 3 * j] * s, yr = f[27 + 3 * j] * c - f[26 + 3 * j] * s, z = f[28 + 3 * j];
+                    if ((hide_toe && (j == 4 || j == 8)) || (hide_spine && j == 9)) { xr = 0.f; yr = 0.f; z = 0.f; }
+                    f[26 + 3 * j] = xr; f[27 + 3 * j] = yr; f[28 + 3 * j] = z;
+                }
+                if (writeback && ok) {                                     // the reference rotates / zeroes init_pose in place (:97,141-144)
+                    float2* o2 = reinterpret_cast<float2*>(pose_rw + b * 72);
+#pragma unroll
+                    for (int i = 0; i < 15; ++i) o2[i] = make_float2(f[26 + 2 * i], f[27 + 2 * i]);
+                }
+            } else {
+                // pose floats 30..71 = joints 10..23 -> features 56..97 (local 0..41); vel -> local 42,43; K padding 44..55
+                { const float2 v = *(reinterpret_cast<const float2*>(p4 + 7) + 1); f[0] = v.x; f[1] = v.y; }
+#pragma unroll
+                for (int i = 0; i < 10; ++i) { float4 v = p4[8 + i]; f[2 + 4 * i] = v.x; f[3 + 4 * i] = v.y; f[4 + 4 * i] = v.z; f[5 + 4 * i] = v.w; }
+#pragma unroll
+                for (int j = 0; j < 14; ++j) {                             // joint 10 + j
+                    float xr = f[3 * j] * c + f[3 * j + 1] * s, yr = f[3 * j + 1] * c - f[3 * j] * s, z = f[3 * j + 2];
+                    if (hide_spine && j <= 1) { xr = 0.f; yr = 0.f; z = 0.f; }
+                    f[3 * j] = xr; f[3 * j + 1] = yr; f[3 * j + 2] = z;
+                }
+                if (writeback && ok) {
+                    float2* o2 = reinterpret_cast<float2*>(pose_rw + b * 72 + 30);
+#pragma unroll
+                    for (int i = 0; i < 21; ++i) o2[i] = make_float2(f[2 * i], f[2 * i + 1]);
+                }
+                const float2 vv = reinterpret_cast<const float2*>(sm + ST_VEL)[row];
+                f[42] = vv.x * c + vv.y * s; f[43] = vv.y * c - vv.x * s;
+#pragma unroll
+                for (int k = 44; k < 56; ++k) f[k] = 0.f;
             }
-            const float4* p4 = reinterpret_cast<const float4*>(sm + ST_POSE) + row * 18;
-#pragma unroll
-            for (int i = 0; i < 18; ++i) { float4 v = p4[i]; f[26 + 4 * i] = v.x; f[27 + 4 * i] = v.y; f[28 + 4 * i] = v.z; f[29 + 4 * i] = v.w; }
-#pragma unroll
-            for (int j = 0; j < 24; ++j) {
-                float xr = f[26 + 3 * j] * c + f[27 + 3 * j] * s, yr = f[27 + 3 * j] * c - f[26 + 3 * j] * s, z = f[28 + 3 * j];
-                if ((hide_toe && (j == 4 || j == 8)) || (hide_spine && j >= 9 && j <= 11)) { xr = 0.f; yr = 0.f; z = 0.f; }
-                f[26 + 3 * j] = xr; f[27 + 3 * j] = yr; f[28 + 3 * j] = z;
-            }
-            if (writeback && ok) {                                         // the reference rotates / zeroes init_pose in place (:97,141-144)
-                float4* o4 = reinterpret_cast<float4*>(pose_rw + b * 72);
-#pragma unroll
-                for (int i = 0; i < 18; ++i) o4[i] = make_float4(f[26 + 4 * i], f[27 + 4 * i], f[28 + 4 * i], f[29 + 4 * i]);
-            }
-            const float2 vv = reinterpret_cast<const float2*>(sm + ST_VEL)[row];
-            f[98] = vv.x * c + vv.y * s; f[99] = vv.y * c - vv.x * s;
-#pragma unroll
-            for (int k = IN; k < K1; ++k) f[k] = 0.f;                      // K padding
         }
         __syncthreads();                                                   // everybody has its row: the staging bytes may go
-        // ---- 1c. bf16 hi / lo -> layer-1 A tile (14 chunks of 8 bf16 = 16 bytes per row, swizzled) ----
+        // ---- 1c. bf16 hi / lo -> layer-1 A tile (7 chunks of 8 bf16 = 16 bytes per thread, swizzled) ----
 #pragma unroll
-        for (int ch = 0; ch < K1 / 8; ++ch) {
+        for (int ch = 0; ch < 7; ++ch) {
             uint32_t h[4], l[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) split2(f[ch * 8 + 2 * i], f[ch * 8 + 2 * i + 1], h[i], l[i]);
-            const uint32_t off = sw128(128, tid, ch * 8);
+            const uint32_t off = sw128(128, rt, (half * 7 + ch) * 8);
             *reinterpret_cast<uint4*>(sm + OFF_A_HI + off) = make_uint4(h[0], h[1], h[2], h[3]);
             *reinterpret_cast<uint4*>(sm + OFF_A_LO + off) = make_uint4(l[0], l[1], l[2], l[3]);
         }
@@ -235,23 +271,23 @@ locoval_tc_kernel(const float* __restrict__ traj, int stride, float* pose_rw, co
         }
         mbar_wait(bar, phase); phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- 3. hidden layer 1: + b1, ReLU, split -> layer-2 A tile (K = 64, columns 49..63 zero) ----
+        // ---- 3. hidden layer 1: + b1, ReLU, split -> layer-2 A tile (K = 64, columns 49..63 zero); 32 columns per thread ----
         {
-            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
-            uint32_t r0[32], r1[32];
-            tmem_ld32(taddr, r0); tmem_ld32(taddr + 32, r1);
-            tmem_wait(r0); tmem_wait(r1);
+            const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(half * 32);
+            uint32_t r0[32];
+            tmem_ld32(taddr, r0);
+            tmem_wait(r0);
 #pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {
+            for (int ch = 0; ch < 4; ++ch) {
                 uint32_t h[4], l[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const int j = ch * 8 + 2 * i;
-                    const float a = j < H1 ? fmaxf(__uint_as_float(j < 32 ? r0[j & 31] : r1[j & 31]) + s_b1[j], 0.f) : 0.f;
-                    const float bq = j + 1 < H1 ? fmaxf(__uint_as_float(j + 1 < 32 ? r0[(j + 1) & 31] : r1[(j + 1) & 31]) + s_b1[j + 1], 0.f) : 0.f;
+                    const int jl = ch * 8 + 2 * i, j = half * 32 + jl;
+                    const float a = j < H1 ? fmaxf(__uint_as_float(r0[jl]) + s_b1[j], 0.f) : 0.f;
+                    const float bq = j + 1 < H1 ? fmaxf(__uint_as_float(r0[jl + 1]) + s_b1[j + 1], 0.f) : 0.f;
                     split2(a, bq, h[i], l[i]);
                 }
-                const uint32_t off = sw128(128, tid, ch * 8);
+                const uint32_t off = sw128(128, rt, (half * 4 + ch) * 8);
                 *reinterpret_cast<uint4*>(sm + OFF_A2_HI + off) = make_uint4(h[0], h[1], h[2], h[3]);
                 *reinterpret_cast<uint4*>(sm + OFF_A2_LO + off) = make_uint4(l[0], l[1], l[2], l[3]);
             }
@@ -275,18 +311,20 @@ locoval_tc_kernel(const float* __restrict__ traj, int stride, float* pose_rw, co
         }
         mbar_wait(bar, phase); phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- 5. hidden layer 2, output layer, sigmoid ----
-        {
+        // ---- 5. half 0: hidden layer 2, output layer, sigmoid; half 1: the A tile is consumed - stage the next tile ----
+        if (half == 0) {
             uint32_t r[32];
             tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + 64, r);
             tmem_wait(r);
             float z = s_b3[0];
 #pragma unroll
             for (int o = 0; o < H2; ++o) z += s_w3[o] * fmaxf(__uint_as_float(r[o]) + s_b2[o], 0.f);
-            if (ok) value[b] = 1.0f / (1.0f + expf(-z));
+            if (ok) value[b] = 1.0f / (1.0f + __expf(-z));
+        } else if (t + gridDim.x < tiles) {
+            stage_tile(t + gridDim.x);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();            // D1 / D2 and the A tile are free again
+        __syncthreads();            // D1 / D2 are free again; the next tile's rows are staged
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -309,6 +347,6 @@ cudaError_t eml_locoval_forward_tc(const float* traj, int stride, float* pose, c
     if (B <= 0) return cudaSuccess;
     const long long tiles = (B + 127) / 128;
     const int grid = (int)(tiles < 148 * 2 ? tiles : 148 * 2);
-    lvtc::locoval_tc_kernel<<<grid, 128, lvtc::SMEM_BYTES, st>>>(traj, stride, pose, vel, w, value, B, flags);
+    lvtc::locoval_tc_kernel<<<grid, 256, lvtc::SMEM_BYTES, st>>>(traj, stride, pose, vel, w, value, B, flags);
     return cudaGetLastError();
 }

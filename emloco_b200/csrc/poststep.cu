@@ -37,9 +37,7 @@ struct PostParams {
 };
 
 // normalise like RunningMeanStd.forward (utils/running_mean_std.py:82-84) and split into bf16 hi + lo (csrc/linear_tc.cu)
-__device__ __forceinline__ void norm_split2(float x0, float x1, const float* __restrict__ mean, const float* __restrict__ inv_std,
-                                            int k, uint32_t& hi, uint32_t& lo) {
-    const float2 m = __ldg(reinterpret_cast<const float2*>(mean + k)), is = __ldg(reinterpret_cast<const float2*>(inv_std + k));   // k even
+__device__ __forceinline__ void norm_split2(float x0, float x1, const float2 m, const float2 is, uint32_t& hi, uint32_t& lo) {
     const float a = fminf(fmaxf((x0 - m.x) * is.x, -5.0f), 5.0f), b = fminf(fmaxf((x1 - m.y) * is.y, -5.0f), 5.0f);
     const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);                 // packed conversions: one F2FP per pair
     hi = *reinterpret_cast<const uint32_t*>(&h);
@@ -118,7 +116,7 @@ __global__ void __launch_bounds__(PS_THREADS) post_step_kernel(PostParams P) {
 #pragma unroll
         for (int k = 0; k < 12; ++k) {
             int i = tid + PS_THREADS * k;
-            if (i < 14 * 103) hist[k] = a[i];
+            if (i < 14 * 103) hist[k] = __ldcs(a + i);      // streamed once: keep it out of the way of the statistics in L1
         }
     }
     long long prog = rmode ? 0 : P.progress[env] + P.advance;
@@ -251,31 +249,56 @@ __global__ void __launch_bounds__(PS_THREADS) post_step_kernel(PostParams P) {
         float2* o = reinterpret_cast<float2*>(P.obs + (size_t)env * EML_OBS);
         float2* f = reinterpret_cast<float2*>(P.flip_obs + (size_t)env * EML_OBS);
         float2* fc = (P.k.flip_copy && !rmode) ? reinterpret_cast<float2*>(P.k.flip_copy + (size_t)env * EML_OBS) : nullptr;
-        for (int i2 = tid; i2 < EML_OBS / 2; i2 += PS_THREADS) {
-            o[i2] = reinterpret_cast<const float2*>(s_obs)[i2];
-            const uint32_t e = __ldg(reinterpret_cast<const uint32_t*>(g_flip_src) + i2);      // two table entries
-            const float r0 = s_obs[e & 0x7fffu], r1 = s_obs[(e >> 16) & 0x7fffu];
-            const float2 fv = make_float2((e & 0x8000u) ? -r0 : r0, (e & 0x80000000u) ? -r1 : r1);
-            f[i2] = fv;
-            if (fc) fc[i2] = fv;
+        // The table entries and normalisation statistics are the same for every env: their (L1/L2) loads are issued for all
+        // of a thread's elements first, so that the stores below never wait on a load issued one instruction earlier
+        constexpr int OB_IT = (EML_OBS / 2 + PS_THREADS - 1) / PS_THREADS;            // 6
+        {
+            uint32_t e[OB_IT];
+#pragma unroll
+            for (int k = 0; k < OB_IT; ++k) {
+                const int i2 = tid + PS_THREADS * k;
+                e[k] = i2 < EML_OBS / 2 ? __ldg(reinterpret_cast<const uint32_t*>(g_flip_src) + i2) : 0u;      // two table entries
+            }
+            float2* oc = P.k.obs_copy ? reinterpret_cast<float2*>(P.k.obs_copy + (size_t)env * EML_OBS) : nullptr;
+#pragma unroll
+            for (int k = 0; k < OB_IT; ++k) {
+                const int i2 = tid + PS_THREADS * k;
+                if (i2 < EML_OBS / 2) {
+                    const float2 v = reinterpret_cast<const float2*>(s_obs)[i2];
+                    o[i2] = v;
+                    if (oc) oc[i2] = v;                                    // experience row of the same observation
+                    const float r0 = s_obs[e[k] & 0x7fffu], r1 = s_obs[(e[k] >> 16) & 0x7fffu];
+                    const float2 fv = make_float2((e[k] & 0x8000u) ? -r0 : r0, (e[k] & 0x80000000u) ? -r1 : r1);
+                    f[i2] = fv;
+                    if (fc) fc[i2] = fv;
+                }
+            }
         }
-        // optional sinks of the same observation row: experience row, and the normalised bf16 hi/lo operands the
-        // tensor-core layers read (self-obs part -> actor/critic input, task-obs part -> task MLP input)
-        if (P.k.obs_copy) {
-            float2* oc = reinterpret_cast<float2*>(P.k.obs_copy + (size_t)env * EML_OBS);
-            for (int i2 = tid; i2 < EML_OBS / 2; i2 += PS_THREADS) oc[i2] = reinterpret_cast<const float2*>(s_obs)[i2];
-        }
+        // optional sink: the normalised bf16 hi/lo operands the tensor-core layers read (self-obs part -> actor/critic input,
+        // task-obs part -> task MLP input)
         if (P.k.self_hi) {
-            for (int i2 = tid; i2 < EML_OBS / 2; i2 += PS_THREADS) {
-                const int i = 2 * i2;
-                uint32_t hi, lo;
-                norm_split2(s_obs[i], s_obs[i + 1], P.k.obs_mean, P.k.obs_inv_std, i, hi, lo);
-                if (i < EML_SELF_OBS) {
-                    *reinterpret_cast<uint32_t*>(P.k.self_hi + (size_t)env * P.k.ld_self + i) = hi;
-                    *reinterpret_cast<uint32_t*>(P.k.self_lo + (size_t)env * P.k.ld_self + i) = lo;
-                } else {
-                    *reinterpret_cast<uint32_t*>(P.k.task_hi + (size_t)env * P.k.ld_task + (i - EML_SELF_OBS)) = hi;
-                    *reinterpret_cast<uint32_t*>(P.k.task_lo + (size_t)env * P.k.ld_task + (i - EML_SELF_OBS)) = lo;
+            float2 m[OB_IT], is[OB_IT];
+#pragma unroll
+            for (int k = 0; k < OB_IT; ++k) {
+                const int i2 = tid + PS_THREADS * k;
+                if (i2 < EML_OBS / 2) {
+                    m[k] = __ldg(reinterpret_cast<const float2*>(P.k.obs_mean) + i2);
+                    is[k] = __ldg(reinterpret_cast<const float2*>(P.k.obs_inv_std) + i2);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < OB_IT; ++k) {
+                const int i2 = tid + PS_THREADS * k, i = 2 * i2;
+                if (i2 < EML_OBS / 2) {
+                    uint32_t hi, lo;
+                    norm_split2(s_obs[i], s_obs[i + 1], m[k], is[k], hi, lo);
+                    if (i < EML_SELF_OBS) {
+                        *reinterpret_cast<uint32_t*>(P.k.self_hi + (size_t)env * P.k.ld_self + i) = hi;
+                        *reinterpret_cast<uint32_t*>(P.k.self_lo + (size_t)env * P.k.ld_self + i) = lo;
+                    } else {
+                        *reinterpret_cast<uint32_t*>(P.k.task_hi + (size_t)env * P.k.ld_task + (i - EML_SELF_OBS)) = hi;
+                        *reinterpret_cast<uint32_t*>(P.k.task_lo + (size_t)env * P.k.ld_task + (i - EML_SELF_OBS)) = lo;
+                    }
                 }
             }
         }
@@ -288,20 +311,39 @@ __global__ void __launch_bounds__(PS_THREADS) post_step_kernel(PostParams P) {
         float2* ac = P.k.amp_copy ? reinterpret_cast<float2*>(P.k.amp_copy + (size_t)env * EML_AMP_OBS) : nullptr;
         uint32_t* ah = P.k.amp_hi ? reinterpret_cast<uint32_t*>(P.k.amp_hi + (size_t)env * P.k.ld_amp) : nullptr;
         uint32_t* al = P.k.amp_hi ? reinterpret_cast<uint32_t*>(P.k.amp_lo + (size_t)env * P.k.ld_amp) : nullptr;
+        // statistics for the thread's 12 ring elements, fetched in groups of 4 ahead of their use
 #pragma unroll
-        for (int k = 0; k < 12; ++k) {
-            int i = tid + PS_THREADS * k;
-            if (i < 14 * 103) {
-                a[103 + i] = hist[k];
-                if (ac) ac[103 + i] = hist[k];
-                if (ah) { uint32_t hi, lo; norm_split2(hist[k].x, hist[k].y, P.k.amp_mean, P.k.amp_inv_std, 2 * (103 + i), hi, lo); ah[103 + i] = hi; al[103 + i] = lo; }
+        for (int g = 0; g < 3; ++g) {
+            float2 m[4], is[4];
+            if (ah) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int i = tid + PS_THREADS * (4 * g + j);
+                    if (i < 14 * 103) {
+                        m[j] = __ldg(reinterpret_cast<const float2*>(P.k.amp_mean) + 103 + i);
+                        is[j] = __ldg(reinterpret_cast<const float2*>(P.k.amp_inv_std) + 103 + i);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = 4 * g + j, i = tid + PS_THREADS * k;
+                if (i < 14 * 103) {
+                    a[103 + i] = hist[k];
+                    if (ac) ac[103 + i] = hist[k];
+                    if (ah) { uint32_t hi, lo; norm_split2(hist[k].x, hist[k].y, m[j], is[j], hi, lo); ah[103 + i] = hi; al[103 + i] = lo; }
+                }
             }
         }
         if (tid < 103) {
             const float2 v = reinterpret_cast<const float2*>(s_amp)[tid];
             a[tid] = v;
             if (ac) ac[tid] = v;
-            if (ah) { uint32_t hi, lo; norm_split2(v.x, v.y, P.k.amp_mean, P.k.amp_inv_std, 2 * tid, hi, lo); ah[tid] = hi; al[tid] = lo; }
+            if (ah) {
+                uint32_t hi, lo;
+                norm_split2(v.x, v.y, __ldg(reinterpret_cast<const float2*>(P.k.amp_mean) + tid), __ldg(reinterpret_cast<const float2*>(P.k.amp_inv_std) + tid), hi, lo);
+                ah[tid] = hi; al[tid] = lo;
+            }
         }
     }
 }

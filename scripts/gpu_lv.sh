@@ -1,21 +1,10 @@
 #!/bin/bash
+# LocoVal iteration: parity tests + 1 M-batch timing (no L2 flush: the 424 MB of inputs exceed the L2) + optional ncu capture
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "locoval" > gpurun_out/lv_pytest.log 2>&1; echo "exit $?" >> gpurun_out/lv_pytest.log
 tail -30 gpurun_out/lv_pytest.log | cut -c1-250
-timeout 300 python - <<'PY'
-import torch, sys
-sys.path.insert(0, ".")
-from emloco_b200.value_pose_net import ValuePoseNet
-from emloco_b200.synthetic import synthetic_locoval_batch
-B = 1 << 20
-traj, pose, vel = (torch.from_numpy(a).cuda() for a in synthetic_locoval_batch(B, seed=0))
-net = ValuePoseNet(True, True, mutate_pose=False).cuda().eval()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-for _ in range(3): net(traj, pose, vel)
-tot = 0
-for _ in range(10):
-    flush.zero_(); e0.record(); net(traj, pose, vel); e1.record(); torch.cuda.synchronize(); tot += e0.elapsed_time(e1)
-ms = tot / 10
-print(f"locoval 1M: {ms:.3f} ms  {B / ms / 1e6:.2f} G scores/s  {B * 404 / ms / 1e6:.0f} GB/s")
-PY
+timeout 300 python scripts/lv_bench.py
+if [ "$1" = "ncu" ]; then
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:locoval_tc -s 3 -c 1 -o gpurun_out/lv_prof python scripts/lv_bench.py > gpurun_out/lv_ncu.log 2>&1
+  tail -2 gpurun_out/lv_ncu.log
+fi
