@@ -185,6 +185,14 @@ locoval_tc_kernel(const float* __restrict__ traj, int stride, float* pose_rw, co
     for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
         const long long b = t * 128 + rt;
         const bool ok = b < B;
+        // the NEXT tile's rows start moving DRAM -> L2 now; their cp.async staging at the end of this iteration then hits L2
+        if (tid == 128 && t + gridDim.x < tiles) {
+            const long long r0 = (t + gridDim.x) * 128;
+            const unsigned rows = (unsigned)((B - r0) < 128 ? (B - r0) : 128);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(traj + r0 * 13 * stride), "r"((rows * 13u * (unsigned)stride * 4u) & ~15u) : "memory");
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pose_rw + r0 * 72), "r"(rows * 288u) : "memory");
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(vel + r0 * 2), "r"((rows * 8u) & ~15u) : "memory");
+        }
         // ---- 1b. this thread's 56 features of its row (registers, statically indexed) ----
         float f[56];
         {
@@ -199,10 +207,18 @@ locoval_tc_kernel(const float* __restrict__ traj, int stride, float* pose_rw, co
             }
             const float4* p4 = reinterpret_cast<const float4*>(sm + ST_POSE) + row * POSE_PITCH;
             if (half == 0) {
+                if (stride == 2) {                                         // 8-byte rows: LDS.64 at a 26-word pitch is conflict free
 #pragma unroll
-                for (int n = 0; n < 13; ++n) {                             // row-vector times [[c,-s],[s,c]] (:85-100)
-                    const float x = tr[n * stride], y = tr[n * stride + 1];
-                    f[2 * n] = x * c + y * s; f[2 * n + 1] = y * c - x * s;
+                    for (int n = 0; n < 13; ++n) {                         // row-vector times [[c,-s],[s,c]] (:85-100)
+                        const float2 w = reinterpret_cast<const float2*>(tr)[n];
+                        f[2 * n] = w.x * c + w.y * s; f[2 * n + 1] = w.y * c - w.x * s;
+                    }
+                } else {
+#pragma unroll
+                    for (int n = 0; n < 13; ++n) {
+                        const float x = tr[n * stride], y = tr[n * stride + 1];
+                        f[2 * n] = x * c + y * s; f[2 * n + 1] = y * c - x * s;
+                    }
                 }
                 // pose floats 0..29 = joints 0..9 -> features 26..55
 #pragma unroll

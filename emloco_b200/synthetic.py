@@ -75,7 +75,7 @@ def waypoints_from_verts(verts, num=13, sample_dt=0.4):
     seg = np.clip(np.arange(num) * sample_dt / dur, 0, 1) * (nv - 1)
     i0 = np.floor(seg).astype(int); i1 = np.ceil(seg).astype(int); fr = (seg - i0).astype(np.float32)
     w = verts[:, i0, :2] * (1 - fr)[None, :, None] + verts[:, i1, :2] * fr[None, :, None]
-    return (w - w[:, :1]).astype(np.float32)
+    return np.ascontiguousarray(w - w[:, :1], dtype=np.float32)     # fancy indexing above leaves a permuted memory layout
 
 
 def synthetic_locoval_batch(b, seed=0, rest_joint_pos=None):
