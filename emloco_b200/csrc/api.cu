@@ -6,7 +6,7 @@
 #include "sim.h"
 
 cudaError_t eml_locoval_forward(const float*, int, int, float*, const float*, const float*, float*, long long, int, cudaStream_t);
-cudaError_t eml_locoval_backward(const float*, int, int, const float*, const float*, const float*, const float*, float*, long long, int, cudaStream_t);
+cudaError_t eml_locoval_backward(const float*, int, int, const float*, const float*, const float*, const float*, float*, const float*, float*, long long, int, cudaStream_t);
 cudaError_t eml_plausibl_forward(const float*, const float*, float*, long long, cudaStream_t);
 cudaError_t eml_gae(const float*, const float*, const float*, const float*, float*, float*, int, long long, float, float, cudaStream_t);
 cudaError_t eml_linear_fma(const float*, long long, const float*, const float*, float*, long long, long long, int, int,
@@ -274,16 +274,25 @@ int emloco_locoval_forward(const float* d_traj, int32_t traj_stride, int32_t T, 
     return EMLOCO_OK;
 }
 
-int emloco_locoval_backward(const float* d_traj, int32_t traj_stride, int32_t T, const float* d_pose, const float* d_vel,
-                            const float* d_weights, const float* d_grad_value, float* d_grad_traj, int64_t batch, int32_t flags,
-                            void* stream) {
+int emloco_locoval_backward_pose(const float* d_traj, int32_t traj_stride, int32_t T, const float* d_pose, const float* d_vel,
+                                 const float* d_weights, const float* d_grad_value, float* d_grad_traj, const float* d_grad_pose_out,
+                                 float* d_grad_pose_in, int64_t batch, int32_t flags, void* stream) {
     if (batch == 0) return EMLOCO_OK;
     if (!d_traj || !d_weights || !d_grad_value || !d_grad_traj) return fail(EMLOCO_EINVAL, "emloco_locoval_backward: null argument");
     if ((flags & 1) && !d_pose) return fail(EMLOCO_EINVAL, "emloco_locoval_backward: init_pose should be included");
     if ((flags & 2) && !d_vel) return fail(EMLOCO_EINVAL, "emloco_locoval_backward: init_vel should be included");
+    if (!(flags & 1) && (d_grad_pose_out || d_grad_pose_in)) return fail(EMLOCO_EINVAL, "emloco_locoval_backward: pose gradients without use_pose");
     if (traj_stride < 2 || (T != 13 && T != 5) || batch < 0) return fail(EMLOCO_EINVAL, "emloco_locoval_backward: bad shape");
-    CK(eml_locoval_backward(d_traj, traj_stride, T, d_pose, d_vel, d_weights, d_grad_value, d_grad_traj, batch, flags, (cudaStream_t)stream), "locoval backward");
+    CK(eml_locoval_backward(d_traj, traj_stride, T, d_pose, d_vel, d_weights, d_grad_value, d_grad_traj, d_grad_pose_out, d_grad_pose_in,
+                            batch, flags, (cudaStream_t)stream), "locoval backward");
     return EMLOCO_OK;
+}
+
+int emloco_locoval_backward(const float* d_traj, int32_t traj_stride, int32_t T, const float* d_pose, const float* d_vel,
+                            const float* d_weights, const float* d_grad_value, float* d_grad_traj, int64_t batch, int32_t flags,
+                            void* stream) {
+    return emloco_locoval_backward_pose(d_traj, traj_stride, T, d_pose, d_vel, d_weights, d_grad_value, d_grad_traj, nullptr, nullptr,
+                                        batch, flags, stream);
 }
 
 static int locoval_nweights(int T, int flags) {

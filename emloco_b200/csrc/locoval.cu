@@ -52,7 +52,8 @@ template <int T, bool POSE, bool VEL, bool BWD>
 __global__ void __launch_bounds__(LV_THREADS) locoval_kernel(const float* __restrict__ traj, int stride, float* pose_rw,
                                                              const float* __restrict__ vel, const float* __restrict__ weights,
                                                              float* __restrict__ value, const float* __restrict__ gvalue,
-                                                             float* __restrict__ gtraj, long long B, int flags) {
+                                                             float* __restrict__ gtraj, const float* __restrict__ gpose_out,
+                                                             float* __restrict__ gpose_in, long long B, int flags) {
     using D = LvDims<T, POSE, VEL>;
     extern __shared__ __align__(16) float smem[];
     float* s_w1t = smem;
@@ -167,13 +168,26 @@ __global__ void __launch_bounds__(LV_THREADS) locoval_kernel(const float* __rest
             for (int u = 2; u < stride; ++u) gt[n * stride + u] = 0.f;
         }
         if (POSE) {
+            // The reference rotates / zeroes init_pose IN PLACE with autograd history (:97,141-144): the tensor the caller
+            // holds afterwards depends on theta and on the incoming pose, and a later call that reuses it (the multi-modal
+            // loop of social-transmotion/train_jta.py:294-296) sends gradient back through it.  gpose_out is that gradient
+            // w.r.t. the rotated / zeroed pose, gpose_in the gradient w.r.t. the pose as it came in.
             const float* pp = pose_rw + b * 72;
 #pragma unroll 1
             for (int j = 0; j < 24; ++j) {
-                if ((hide_toe && (j == 4 || j == 8)) || (hide_spine && j >= 9 && j <= 11)) continue;
-                float x = pp[3 * j], y = pp[3 * j + 1];
-                float xr = x * c + y * s, yr = y * c - x * s;
-                dtheta += dx(2 * T + 3 * j) * yr - dx(2 * T + 3 * j + 1) * xr;
+                const bool hidden = (hide_toe && (j == 4 || j == 8)) || (hide_spine && j >= 9 && j <= 11);
+                float Gx = 0.f, Gy = 0.f, Gz = 0.f;
+                if (!hidden) {
+                    Gx = dx(2 * T + 3 * j); Gy = dx(2 * T + 3 * j + 1);
+                    if (gpose_in) Gz = dx(2 * T + 3 * j + 2);
+                    if (gpose_out) { Gx += gpose_out[b * 72 + 3 * j]; Gy += gpose_out[b * 72 + 3 * j + 1]; Gz += gpose_out[b * 72 + 3 * j + 2]; }
+                    float x = pp[3 * j], y = pp[3 * j + 1];
+                    float xr = x * c + y * s, yr = y * c - x * s;
+                    dtheta += Gx * yr - Gy * xr;
+                }
+                if (gpose_in) {
+                    gpose_in[b * 72 + 3 * j] = Gx * c - Gy * s; gpose_in[b * 72 + 3 * j + 1] = Gx * s + Gy * c; gpose_in[b * 72 + 3 * j + 2] = Gz;
+                }
             }
         }
         if (VEL) {
@@ -191,7 +205,7 @@ __global__ void __launch_bounds__(LV_THREADS) locoval_kernel(const float* __rest
 
 template <int T, bool POSE, bool VEL, bool BWD>
 static cudaError_t lv_launch(const float* traj, int stride, float* pose, const float* vel, const float* w, float* value,
-                             const float* gv, float* gt, long long B, int flags, cudaStream_t st) {
+                             const float* gv, float* gt, const float* gpo, float* gpi, long long B, int flags, cudaStream_t st) {
     using D = LvDims<T, POSE, VEL>;
     auto k = locoval_kernel<T, POSE, VEL, BWD>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, D::SMEM);
@@ -201,15 +215,16 @@ static cudaError_t lv_launch(const float* traj, int stride, float* pose, const f
     // persistent-ish grid: weights are staged once per CTA, so cap at a few CTAs per SM (148 SMs)
     long long cap = 148LL * 8;
     int grid = (int)(blocks < cap ? blocks : cap);
-    k<<<grid, LV_THREADS, D::SMEM, st>>>(traj, stride, pose, vel, w, value, gv, gt, B, flags);
+    k<<<grid, LV_THREADS, D::SMEM, st>>>(traj, stride, pose, vel, w, value, gv, gt, gpo, gpi, B, flags);
     return cudaGetLastError();
 }
 
 template <bool BWD>
 static cudaError_t lv_dispatch(const float* traj, int stride, int T, float* pose, const float* vel, const float* w,
-                               float* value, const float* gv, float* gt, long long B, int flags, cudaStream_t st) {
+                               float* value, const float* gv, float* gt, const float* gpo, float* gpi, long long B, int flags,
+                               cudaStream_t st) {
     bool P = flags & 1, V = flags & 2;
-#define LV_CASE(TT, PP, VV) if (T == TT && P == PP && V == VV) return lv_launch<TT, PP, VV, BWD>(traj, stride, pose, vel, w, value, gv, gt, B, flags, st)
+#define LV_CASE(TT, PP, VV) if (T == TT && P == PP && V == VV) return lv_launch<TT, PP, VV, BWD>(traj, stride, pose, vel, w, value, gv, gt, gpo, gpi, B, flags, st)
     LV_CASE(13, true, true); LV_CASE(13, true, false); LV_CASE(13, false, true); LV_CASE(13, false, false);
     LV_CASE(5, true, true); LV_CASE(5, true, false); LV_CASE(5, false, true); LV_CASE(5, false, false);
 #undef LV_CASE
@@ -225,11 +240,12 @@ cudaError_t eml_locoval_forward(const float* traj, int stride, int T, float* pos
     if (T == 13 && (flags & 3) == 3 && !(flags & 64) && B >= 1024 && stride <= 3 &&
         ((reinterpret_cast<uintptr_t>(pose) | reinterpret_cast<uintptr_t>(traj) | reinterpret_cast<uintptr_t>(vel)) & 15) == 0)
         return eml_locoval_forward_tc(traj, stride, pose, vel, w, value, B, flags, st);
-    return lv_dispatch<false>(traj, stride, T, pose, vel, w, value, nullptr, nullptr, B, flags, st);
+    return lv_dispatch<false>(traj, stride, T, pose, vel, w, value, nullptr, nullptr, nullptr, nullptr, B, flags, st);
 }
 cudaError_t eml_locoval_backward(const float* traj, int stride, int T, const float* pose, const float* vel, const float* w,
-                                 const float* gv, float* gt, long long B, int flags, cudaStream_t st) {
-    return lv_dispatch<true>(traj, stride, T, const_cast<float*>(pose), vel, w, nullptr, gv, gt, B, flags, st);
+                                 const float* gv, float* gt, const float* gpose_out, float* gpose_in, long long B, int flags,
+                                 cudaStream_t st) {
+    return lv_dispatch<true>(traj, stride, T, const_cast<float*>(pose), vel, w, nullptr, gv, gt, gpose_out, gpose_in, B, flags, st);
 }
 
 // ---- plausibl/test_value_mlp.py:24-113: Linear(24,12)-ReLU-Linear(12,6)-ReLU-Linear(6,1) ----

@@ -32,37 +32,45 @@ def _stream():
 
 
 class _LocoValFn(torch.autograd.Function):
+    """value = LocoVal(traj, pose, vel).  With F_WRITEBACK the kernel rotates / zeroes `pose` in place like the reference
+    (value_pose_net.py:97,141-144) and the tensor is returned as a second, dirty output: like in the reference it then carries
+    autograd history, so a later call that reuses it (multi-modal loop, train_jta.py:294-296) back-propagates through it."""
+
     @staticmethod
     def forward(ctx, traj, pose, vel, wpack, flags, T):
         B = traj.shape[0]
         stride = traj.shape[-1]
         value = torch.empty(B, 1, device=traj.device, dtype=torch.float32)
+        dirty = pose is not None and bool(flags & F_WRITEBACK)
+        ctx.flags, ctx.T, ctx.dirty = flags, T, dirty
+        if dirty:
+            ctx.mark_dirty(pose)
         if B == 0:                                  # empty batch: nothing to launch (data_ptr() of an empty tensor is NULL)
             ctx.save_for_backward(traj, None, vel, wpack)
-            ctx.flags, ctx.T = flags, T
-            return value
-        need_grad = traj.requires_grad
+            return (value, pose) if dirty else value
+        need_grad = any(ctx.needs_input_grad[:2])
         pose_saved = None
         if pose is not None and need_grad:
-            pose_saved = pose.detach().clone() if (flags & F_WRITEBACK) else pose.detach()
+            pose_saved = pose.detach().clone() if dirty else pose.detach()      # the pose as it came in
         _lib.check(_lib.load().emloco_locoval_forward(_p(traj), stride, T, _p(pose), _p(vel), _p(wpack), _p(value), B,
                                                       flags, _stream()), "emloco_locoval_forward")
         ctx.save_for_backward(traj, pose_saved, vel, wpack)
-        ctx.flags, ctx.T = flags, T
-        # the in-place rotation of `pose` (reference side effect) is not differentiated: pose is a plain input there too
-        return value
+        return (value, pose) if dirty else value
 
     @staticmethod
-    def backward(ctx, gvalue):
+    def backward(ctx, gvalue, gpose_out=None):
         traj, pose, vel, wpack = ctx.saved_tensors
         g = gvalue.contiguous().float()
         gtraj = torch.empty_like(traj)
+        want_pose = ctx.needs_input_grad[1] and pose is not None
         if traj.shape[0] == 0:
-            return gtraj, None, None, None, None, None
-        _lib.check(_lib.load().emloco_locoval_backward(_p(traj), traj.shape[-1], ctx.T, _p(pose), _p(vel), _p(wpack), _p(g),
-                                                       _p(gtraj), traj.shape[0], ctx.flags & ~F_WRITEBACK, _stream()),
-                   "emloco_locoval_backward")
-        return gtraj, None, None, None, None, None
+            return gtraj, (torch.zeros_like(pose) if want_pose else None), None, None, None, None
+        gpo = gpose_out.contiguous().float() if (gpose_out is not None and pose is not None) else None
+        gpi = torch.empty_like(pose) if want_pose else None
+        _lib.check(_lib.load().emloco_locoval_backward_pose(_p(traj), traj.shape[-1], ctx.T, _p(pose), _p(vel), _p(wpack), _p(g),
+                                                            _p(gtraj), _p(gpo), _p(gpi), traj.shape[0], ctx.flags & ~F_WRITEBACK,
+                                                            _stream()), "emloco_locoval_backward_pose")
+        return gtraj, gpi, None, None, None, None
 
 
 class ValuePoseNet(nn.Module):
@@ -134,7 +142,8 @@ class ValuePoseNet(nn.Module):
             assert pose.shape[-2:] == (24, 3) and pose.shape[0] == traj.shape[0]
         if self.use_vel:
             vel = init_vel[:, :2].float().contiguous()
-        return _LocoValFn.apply(traj, pose, vel, self._weights(), self._flags(), T)
+        out = _LocoValFn.apply(traj, pose, vel, self._weights(), self._flags(), T)
+        return out[0] if isinstance(out, tuple) else out
 
     def _forward_autograd(self, traj, pose, vel):
         """Weight-gradient path (LocoVal fine-tuning only): plain torch ops, same math as the kernel."""

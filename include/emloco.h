@@ -231,6 +231,14 @@ int emloco_locoval_forward(const float* d_traj, int32_t traj_stride, int32_t num
 int emloco_locoval_backward(const float* d_traj, int32_t traj_stride, int32_t num_waypoints, const float* d_pose,
                             const float* d_vel, const float* d_weights, const float* d_grad_value,
                             float* d_grad_traj, int64_t batch, int32_t flags, void* stream);
+/* The same with the gradient chain through the mutated pose.  The reference rotates / zeroes init_pose in place WITH autograd
+ * history (value_pose_net.py:97,141-144), so in the multi-modal loop of social-transmotion/train_jta.py:294-296 (one call per
+ * mode, same init_pose tensor) the loss of mode i also reaches the trajectories of modes < i through the pose.
+ * grad_pose_out [B,24,3] (or NULL): gradient w.r.t. the pose as this call left it; grad_pose_in [B,24,3] (or NULL): gradient
+ * w.r.t. the pose as it came in (feeds the previous call's grad_pose_out).  d_pose = the pose as it came in. */
+int emloco_locoval_backward_pose(const float* d_traj, int32_t traj_stride, int32_t num_waypoints, const float* d_pose,
+                                 const float* d_vel, const float* d_weights, const float* d_grad_value, float* d_grad_traj,
+                                 const float* d_grad_pose_out, float* d_grad_pose_in, int64_t batch, int32_t flags, void* stream);
 /* Host-buffer scoring (the batch-of-1 filter loop of social-transmotion/evaluate_jta.py:298-302, batched). */
 int emloco_locoval_forward_host(const float* h_traj, int32_t traj_stride, int32_t num_waypoints, const float* h_pose,
                                 const float* h_vel, const float* h_weights, float* h_value, int64_t batch,

@@ -185,6 +185,43 @@ def reference_locoval(traj, pose, vel, seed=0):
                    pose_after=p.detach().numpy())
 
 
+def reference_locoval_multimodal(B=256, modes=5, seed=5):
+    """BASELINE configs[4]: the multi-modal EmLoco loss of social-transmotion/train_jta.py:289-299 - one
+    calc_embodied_motion_loss call per mode on the non-contiguous slice pred_trajs[:, :, i], the SAME init_pose tensor
+    passed every time (so mode i sees the pose already rotated / zeroed by modes 0..i-1, value_pose_net.py:97,141-144),
+    losses summed, scaled and averaged, gradient taken w.r.t. the predictor output."""
+    R = ref_extract.load()
+    torch = R.torch
+    torch.manual_seed(seed)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = R.ValuePoseNet(use_pose=True, use_vel=True)
+    with torch.no_grad():
+        for m in net._network:
+            if hasattr(m, "bias"):
+                m.bias.uniform_(-0.1, 0.1)
+    W = {k: v.detach().numpy().copy() for k, v in net.state_dict().items()}
+    rng = np.random.default_rng(seed)
+    f = np.float32
+    step = rng.normal(0.35, 0.25, (B, 12, modes, 2)).astype(f) * rng.choice([-1, 1], (B, 1, modes, 2)).astype(f)
+    pred = np.cumsum(step, 1).astype(f)                                   # [B,12,modes,2] predicted future positions
+    _, pose, vel = synth_locoval(B, seed + 1)
+    p = torch.from_numpy(pose.copy()); v = torch.from_numpy(vel.copy())
+    out = torch.from_numpy(pred.copy()).requires_grad_(True)              # "pred_joints[:, in_F:]"
+    trajs = torch.cat([torch.zeros(B, 1, modes, 2), out], dim=1)          # :291
+    weight = 0.5                                                          # config TRAIN.valuenet_weight
+    losses, values = 0, []
+    for i in range(modes):                                                # :294-296
+        val, l = net.calc_embodied_motion_loss(trajs[:, :, i], p, v)
+        losses = losses + l
+        values.append(val.detach().numpy().copy())
+    losses = losses * weight / modes                                      # :297-298
+    losses.backward()
+    return dict(pred=pred, pose=pose, vel=vel, weight=f(weight), **{f"w_{k}": a for k, a in W.items()},
+                out_values=np.stack(values, 0), out_loss=losses.detach().numpy(), out_grad_pred=out.grad.numpy(),
+                out_pose_after=p.detach().numpy())
+
+
 def reference_gae(T_, N, seed):
     R = ref_extract.load()
     torch = R.torch
@@ -297,6 +334,7 @@ def main():
     W, out = reference_locoval(traj, pose, vel)
     np.savez_compressed(os.path.join(OUT, "locoval.npz"), traj=traj, pose=pose, vel=vel,
                         **{f"w_{k}": v for k, v in W.items()}, **{f"out_{k}": v for k, v in out.items()})
+    np.savez_compressed(os.path.join(OUT, "locoval_mm5.npz"), **reference_locoval_multimodal())
     g = reference_gae(32, 16, 3)
     np.savez_compressed(os.path.join(OUT, "gae.npz"), **g)
     rng = np.random.default_rng(4)

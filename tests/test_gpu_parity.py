@@ -312,3 +312,32 @@ def test_locoval_tensor_core_kernel_matches_cuda_core_kernel_and_oracle(stride, 
     ref, pose_after = O.locoval_forward(traj[:n, :, :2].cpu().numpy(), pose[:n].cpu().numpy(), vel[:n].cpu().numpy(), W)
     np.testing.assert_allclose(out["tc"][0][:n], ref[:, 0], rtol=1e-3, atol=2e-6)
     np.testing.assert_allclose(out["tc"][1][:n], pose_after, rtol=1e-3, atol=1e-5)
+
+
+def test_locoval_multimodal_loss_matches_reference_golden():
+    """BASELINE configs[4]: train_jta.py:289-299 with MULTI_MODAL = 5, batch 256 - one calc_embodied_motion_loss call per
+    mode on the non-contiguous slice pred_trajs[:, :, i] with the SAME init_pose tensor.  The reference mutates that tensor in
+    place with autograd history, so the gradient of mode i's loss also reaches the trajectories of the earlier modes through
+    the pose; the golden gradient (reference autograd) contains that chain (it is ~19 % of the gradient norm)."""
+    from emloco_b200.value_pose_net import ValuePoseNet
+    g = np.load(os.path.join(GOLDEN, "locoval_mm5.npz"))
+    net = ValuePoseNet(True, True).cuda().eval()
+    net.load_state_dict({k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("w_")})
+    B, _, modes, _ = g["pred"].shape
+    out = torch.from_numpy(g["pred"]).cuda().requires_grad_(True)
+    trajs = torch.cat([torch.zeros(B, 1, modes, 2, device="cuda"), out], dim=1)
+    pose = torch.from_numpy(g["pose"]).cuda()
+    vel = torch.from_numpy(g["vel"]).cuda()
+    losses, values = 0, []
+    for i in range(modes):
+        val, l = net.calc_embodied_motion_loss(trajs[:, :, i], pose, vel)
+        losses = losses + l
+        values.append(val.detach().cpu().numpy())
+    losses = losses * float(g["weight"]) / modes
+    losses.backward()
+    np.testing.assert_allclose(np.stack(values, 0), g["out_values"], rtol=RTOL, atol=1e-6)
+    np.testing.assert_allclose(losses.item(), g["out_loss"], rtol=RTOL)
+    np.testing.assert_allclose(pose.detach().cpu().numpy(), g["out_pose_after"], rtol=RTOL, atol=2e-6)
+    gr, ref = out.grad.cpu().numpy(), g["out_grad_pred"]
+    np.testing.assert_allclose(gr, ref, rtol=2e-3, atol=2e-3 * np.abs(ref).max() * 1e-2)
+    assert np.linalg.norm(gr - ref) / np.linalg.norm(ref) < 1e-3
