@@ -112,7 +112,8 @@ def test_locoval_matches_reference_golden():
     np.testing.assert_allclose(loss.item(), g["out_loss"], rtol=RTOL)
     np.testing.assert_allclose(traj.grad.cpu().numpy(), g["out_grad_traj"], rtol=2e-3, atol=1e-7)
     # the reference rotates / zeroes the caller's pose in place; so do we
-    np.testing.assert_allclose(pose.cpu().numpy(), g["out_pose_after"], rtol=RTOL, atol=1e-6)
+    assert pose.requires_grad            # ... with autograd history, like the reference's in-place bmm (value_pose_net.py:97)
+    np.testing.assert_allclose(pose.detach().cpu().numpy(), g["out_pose_after"], rtol=RTOL, atol=1e-6)
 
 
 @pytest.mark.parametrize("use_pose,use_vel,vru", [(True, True, False), (False, False, False), (False, True, False),
