@@ -361,3 +361,63 @@ def test_host_observation_step_matches_device_step():
     assert len(seen) == T                                                  # the hook ran between the two halves of every step
     np.testing.assert_array_equal(seen[-1].cpu().numpy(), C_.sim.obs.cpu().numpy())   # ... after post_step wrote the observations
     A.close(); B.close(); C_.close()
+
+
+def test_64_envs_100_steps_lockstep_with_cpu_oracle():
+    """BASELINE configs[0] (64 envs, 100 steps): every one of the 100 control steps is checked against the CPU oracle started
+    from the GPU's own state of that step (re-synchronised each step, so fp32-vs-fp64 round-off cannot accumulate through the
+    chaotic contact dynamics): 6 400 env-steps over the state distribution a rollout actually visits - standing, stumbling,
+    fallen, reset.  Tolerances: 1e-3 relative, absolute floors per quantity; masks may differ only where the fp32 and fp64
+    contact forces straddle the 50 N fall threshold (budget: 3 of 6 400)."""
+    n, steps = 64, 100
+    gpu, cpu = _pair(n, seed=5, tensor_cores=True)
+    T = gpu.T
+    sim = gpu.sim
+    rng = np.random.default_rng(1)
+    worst = {}
+    mask_mismatch = 0
+    n_resets = 0
+
+    def upd(key, a, b, atol):
+        err = np.abs(a - b) / (atol + RTOL * np.abs(b))
+        worst[key] = max(worst.get(key, 0.0), float(err.max()))
+
+    for k in range(steps):
+        torch.cuda.synchronize()
+        f64 = lambda t: t.detach().cpu().numpy().astype(np.float64)
+        cpu.root = f64(sim.root_state).reshape(n, 13).copy()
+        cpu.jq = f64(sim.joint_quat).reshape(n, 23, 4).copy()
+        cpu.jw = f64(sim.dof_state).reshape(n, 69, 2)[..., 1].copy()
+        cpu.progress = sim.progress.cpu().numpy().copy(); cpu.reset = sim.reset.cpu().numpy().copy()
+        cpu.terminate = sim.terminate.cpu().numpy().copy()
+        cpu.amp_buf = sim.amp_obs.cpu().numpy().reshape(n, 15, 206).copy()
+        cpu.contact = f64(sim.contact).reshape(n, 24, 3).copy(); cpu.dof_force = f64(sim.dof_force).reshape(n, 69).copy()
+        cpu.obs = sim.obs.cpu().numpy().copy()
+        cpu.state = gpu.state.cpu().numpy().copy()
+        n_resets += int(cpu.reset.sum())
+        noise = rng.standard_normal((n, 69)).astype(np.float32)
+        o = cpu.step(noise)
+        slot = k % T
+        gpu.step(slot, noise=torch.from_numpy(noise).cuda())
+        torch.cuda.synchronize()
+        mb = {key: v[slot].cpu().numpy() for key, v in gpu.mb.items() if v is not None}
+        upd("mus", mb["mus"], o["mu"], 5e-5); upd("actions", mb["actions"], o["actions"], 5e-5)
+        upd("values", mb["values"][:, 0], o["values"], 5e-5)
+        rb = sim.rb_state.view(n, 24, 13).cpu().numpy()
+        upd("rb_pos", rb[..., 0:3], o["rb"][..., 0:3], 1e-3); upd("rb_rot", rb[..., 3:7], o["rb"][..., 3:7], 1e-3)
+        upd("rb_vel", rb[..., 7:13], o["rb"][..., 7:13], 1e-2)
+        same = mb["dones"] == o["dones"]
+        mask_mismatch += int((~same).sum())
+        upd("rewards", mb["rewards"][same, 0], o["rewards"][same], 5e-3)
+        upd("next_values", mb["next_values"][same, 0], o["next_values"][same], 1e-4)
+        upd("amp_rewards", mb["amp_rewards"][:, 0], o["amp_rewards"], 1e-3)
+        upd("self_obs", sim.obs.cpu().numpy()[:, :368], o["next_obs"][:, :368], 5e-3)
+        if slot == T - 1:
+            gpu.finish()
+    print("lockstep worst error / tolerance:", {k_: round(v, 3) for k_, v in worst.items()}, "mask mismatches", mask_mismatch,
+          "resets", n_resets)
+    assert n_resets > n                       # beyond the initial reset: episodes ended and restarted inside the 100 steps
+    assert mask_mismatch <= 3
+    for key, v in worst.items():
+        assert v <= 1.0, (key, v)
+    gpu.close()
