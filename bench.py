@@ -34,9 +34,11 @@ BYTES_POST = 28264            # per env-step: state/contact/force/verts in, obs 
 FLOP_NETS_STEP = 2 * (7.493154e6 + 4.046848e6 + 3.688960e6)
 BYTES_LOCOVAL = 404           # per score
 HORIZON = 32
-# DRAM traffic per launch from the committed `ncu --set full` capture (profiles/r01c_full.md; cold caches under ncu, so an
-# upper bound of what a warm step moves): dram__bytes_read.sum + dram__bytes_write.sum
-NCU_TRAFFIC = {"physics": 5.3e6, "post_step": 253.0e6, "nets": 15 * 27.2e6, "locoval": None}
+# DRAM traffic per launch from the committed `ncu --set full` captures (cold caches under ncu, so an upper bound of what a
+# warm step moves): dram__bytes_read.sum + dram__bytes_write.sum.  physics / post_step: profiles/r01e_full.md (post_step now
+# also writes the mirrored-observation experience row); nets: profiles/r01c_full.md, summed over the 15 dense launches of a
+# step; locoval: profiles/r01e_locoval.md, the 1 M-score launch
+NCU_TRAFFIC = {"physics": 5.36e6, "post_step": 277.0e6, "nets": 15 * 27.2e6, "locoval": 429.7e6}
 
 
 def peaks():
@@ -343,13 +345,14 @@ def run_ours(args):
             "locoval": {"bound": "hbm", "ms": lv_ms, "achieved": B * BYTES_LOCOVAL / (lv_ms * 1e-3) / 1e9, "peak": pk["hbm"],
                         "unit": "GB/s"},
         }
-        for k in kern.values():
+        for name, k in kern.items():
             k["frac"] = k["achieved"] / k["peak"]
+            k["traffic"] = NCU_TRAFFIC[name] if (name != "locoval" or B == 1 << 20) else None
         dom = max(("physics", "post_step", "nets"), key=lambda k: kern[k]["ms"])
         names = {"nets": "tc::linear_bf16x3_kernel (the 15 dense-layer launches of a step)", "physics": "physics_soa_kernel",
                  "post_step": "post_step_kernel"}
         roof = dict(kern[dom]); roof.update(kernel=names[dom], traffic=NCU_TRAFFIC[dom], peak_source=pk["src"],
-                                            traffic_source="profiles/r01c_full.md (ncu --set full, per step for nets / per launch otherwise)")
+                                            traffic_source="profiles/r01e_full.md, r01c_full.md (ncu --set full; per step for nets, per launch otherwise)")
         if dom == "nets":
             roof["note"] = ("fp32 operands are carried as bf16 hi+lo and every k-step issues 3 MMAs (bf16x3, fp32-grade products): "
                             "frac counts algorithmic FLOPs once, so its ceiling is 1/3; MMA-issue rate = 3 x achieved")
