@@ -18,7 +18,7 @@ SYMBOLS = [
     "emloco_plausibl_mlp_forward", "emloco_gae", "emloco_reset_done", "emloco_sample_actions",
     "emloco_disc_reward", "emloco_rollout_record", "emloco_normalize", "emloco_physics_step", "emloco_split_bf16",
     "emloco_linear_bf16x3", "emloco_set_post_sinks", "emloco_linear_bf16x3_rows", "emloco_timeout_gather",
-    "emloco_rollout_record_deferred", "emloco_fill_next_values", "emloco_traj_reset", "emloco_set_traj_reset", "emloco_locoval_backward_pose", "emloco_linear", "emloco_sync", "emloco_last_error", "emloco_version",
+    "emloco_rollout_record_deferred", "emloco_fill_next_values", "emloco_traj_reset", "emloco_set_traj_reset", "emloco_locoval_backward_pose", "emloco_locoval_train_step", "emloco_locoval_train_workspace_bytes", "emloco_linear", "emloco_sync", "emloco_last_error", "emloco_version",
 ]
 
 
@@ -105,6 +105,9 @@ def load():
     lib.emloco_locoval_forward.argtypes = [vp, i32, i32, vp, vp, vp, vp, i64, i32, vp]
     lib.emloco_locoval_backward.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, i64, i32, vp]
     lib.emloco_locoval_backward_pose.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp]
+    lib.emloco_locoval_train_workspace_bytes.argtypes = [i64]
+    lib.emloco_locoval_train_workspace_bytes.restype = i64
+    lib.emloco_locoval_train_step.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64] + [C.c_float] * 7 + [i32, vp]
     lib.emloco_locoval_forward_host.argtypes = [vp, i32, i32, vp, vp, vp, vp, i64, i32, i32]
     lib.emloco_plausibl_mlp_forward.argtypes = [vp, vp, vp, i64, vp]
     lib.emloco_gae.argtypes = [vp, vp, vp, vp, vp, vp, i32, i64, f32, f32, vp]
@@ -124,7 +127,7 @@ def load():
     lib.emloco_sync.argtypes = [vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
-        if name not in ("emloco_last_error", "emloco_version", "emloco_default_cfg"):
+        if name not in ("emloco_last_error", "emloco_version", "emloco_default_cfg", "emloco_locoval_train_workspace_bytes"):
             fn.restype = C.c_int
     _lib = lib
     return lib
@@ -134,7 +137,7 @@ def load():
 LAUNCHES = {"emloco_step": 2, "emloco_physics_step": 1, "emloco_post_step": 1, "emloco_simulate": 1, "emloco_reset_done": 2,
             "emloco_reset_indexed": 1, "emloco_traj_reset": 1, "emloco_linear": 1, "emloco_normalize": 1, "emloco_sample_actions": 1,
             "emloco_disc_reward": 1, "emloco_rollout_record": 1, "emloco_gae": 1, "emloco_locoval_forward": 1,
-            "emloco_locoval_backward": 1, "emloco_locoval_backward_pose": 1, "emloco_plausibl_mlp_forward": 1, "emloco_step_host": 2,
+            "emloco_locoval_backward": 1, "emloco_locoval_backward_pose": 1, "emloco_locoval_train_step": 2, "emloco_plausibl_mlp_forward": 1, "emloco_step_host": 2,
             "emloco_locoval_forward_host": 1, "emloco_split_bf16": 1, "emloco_linear_bf16x3": 1, "emloco_linear_bf16x3_rows": 1,
             "emloco_timeout_gather": 1, "emloco_rollout_record_deferred": 1, "emloco_fill_next_values": 1}
 launch_count = 0

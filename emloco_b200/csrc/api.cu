@@ -295,6 +295,27 @@ int emloco_locoval_backward(const float* d_traj, int32_t traj_stride, int32_t T,
                                         batch, flags, stream);
 }
 
+size_t eml_locoval_train_workspace_bytes(long long N);
+cudaError_t eml_locoval_train_step(const float* traj, int stride, int T, const float* pose, const float* vel, float* gc, float* w,
+                                   float* m, float* v, float* step, float* stats, void* workspace, long long N, float lr, float beta1,
+                                   float beta2, float eps, float wd, float r_min, float r_max, int flags, cudaStream_t st);
+
+int64_t emloco_locoval_train_workspace_bytes(int64_t N) { return N < 0 ? 0 : (int64_t)eml_locoval_train_workspace_bytes(N); }
+
+int emloco_locoval_train_step(const float* d_traj, int32_t traj_stride, int32_t T, const float* d_pose, const float* d_vel,
+                              float* d_gc, float* d_w, float* d_m, float* d_v, float* d_step, float* d_stats, void* d_ws, int64_t N,
+                              float lr, float beta1, float beta2, float eps, float wd, float r_min, float r_max, int32_t flags,
+                              void* stream) {
+    if (N == 0) return EMLOCO_OK;
+    if (!d_traj || !d_gc || !d_w || !d_m || !d_v || !d_step || !d_stats || !d_ws) return fail(EMLOCO_EINVAL, "emloco_locoval_train_step: null argument");
+    if ((flags & 1) && !d_pose) return fail(EMLOCO_EINVAL, "emloco_locoval_train_step: init_pose should be included");
+    if ((flags & 2) && !d_vel) return fail(EMLOCO_EINVAL, "emloco_locoval_train_step: init_vel should be included");
+    if (traj_stride < 2 || (T != 13 && T != 5) || N < 0 || !(r_max > r_min)) return fail(EMLOCO_EINVAL, "emloco_locoval_train_step: bad shape or reward range");
+    CK(eml_locoval_train_step(d_traj, traj_stride, T, d_pose, d_vel, d_gc, d_w, d_m, d_v, d_step, d_stats, d_ws, N, lr, beta1, beta2, eps,
+                              wd, r_min, r_max, flags, (cudaStream_t)stream), "locoval train step");
+    return EMLOCO_OK;
+}
+
 static int locoval_nweights(int T, int flags) {
     int in = 2 * T + ((flags & 1) ? 72 : 0) + ((flags & 2) ? 2 : 0);
     int h1 = in / 2 - 1, h2 = h1 / 2;

@@ -145,6 +145,63 @@ class ValuePoseNet(nn.Module):
         out = _LocoValFn.apply(traj, pose, vel, self._weights(), self._flags(), T)
         return out[0] if isinstance(out, tuple) else out
 
+    # ---- fine-tuning inside the rollout (amp_continuous_value.py:122-146, optimiser common_agent.py:94-96) ----
+    def enable_finetune(self):
+        """Re-homes the six parameters as views of ONE packed fp32 buffer (the layout the kernels read) so that the fused
+        AdamW step updates them in place, and allocates the optimiser state."""
+        ps = [self._network.fc1.weight, self._network.fc1.bias, self._network.fc2.weight, self._network.fc2.bias,
+              self._network.fc3.weight, self._network.fc3.bias]
+        if not ps[0].is_cuda:
+            raise _lib.EmlocoError("ValuePoseNet.enable_finetune needs the module on a CUDA device; there is no CPU fallback")
+        flat = torch.cat([p.detach().reshape(-1).float() for p in ps]).contiguous()
+        off = 0
+        for p in ps:
+            n = p.numel()
+            p.data = flat[off:off + n].view_as(p)
+            off += n
+        self._pack, self._pack_key = flat, tuple((p.data_ptr(), p._version, p.device) for p in ps)
+        ft = getattr(self, "_ft", None)
+        if ft is None or ft["m"].device != flat.device:
+            z = lambda n: torch.zeros(n, device=flat.device, dtype=torch.float32)
+            ft = dict(m=z(flat.numel()), v=z(flat.numel()), step=z(1), stats=z(4), ws=None)
+        ft["flat"] = flat
+        self._ft = ft
+        return self
+
+    def finetune_step(self, waypoint_traj, init_pose, init_vel, game_combined_rewards, lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
+                      weight_decay=1e-4, min_cum_rewards=-10.0, max_cum_rewards=100.0):
+        """One `_do_finetune` block: MSE(sum) of the scores of the envs with game_combined_rewards != 0 against their
+        normalised rewards, backward, AdamW step, game_combined_rewards zeroed for those envs - two launches, no host sync.
+        Inputs are CUDA float32 contiguous: traj [N,T,>=2], pose [N,24,3], vel [N,2], game_combined_rewards [N]."""
+        ft = getattr(self, "_ft", None)
+        if ft is None or self._network.fc1.weight.data_ptr() != ft["flat"].data_ptr():
+            self.enable_finetune()
+            ft = self._ft
+        N, T = waypoint_traj.shape[0], self.traj_size // 2
+        for name, t, shp in (("waypoint_traj", waypoint_traj, None), ("init_pose", init_pose, (N, 24, 3) if self.use_pose else None),
+                             ("init_vel", init_vel, (N, 2) if self.use_vel else None), ("game_combined_rewards", game_combined_rewards, (N,))):
+            if t is None:
+                continue
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and (shp is None or tuple(t.shape) == shp)):
+                raise _lib.EmlocoError(f"finetune_step: {name} must be contiguous float32 CUDA" + (f" of shape {shp}" if shp else ""))
+        assert waypoint_traj.dim() == 3 and waypoint_traj.shape[1] == T and waypoint_traj.shape[2] >= 2
+        need = _lib.load().emloco_locoval_train_workspace_bytes(N)
+        if ft["ws"] is None or ft["ws"].numel() < need:
+            ft["ws"] = torch.empty(need, device=ft["flat"].device, dtype=torch.uint8)
+        _lib.check(_lib.load().emloco_locoval_train_step(
+            _p(waypoint_traj), waypoint_traj.shape[-1], T, _p(init_pose) if self.use_pose else None,
+            _p(init_vel) if self.use_vel else None, _p(game_combined_rewards), _p(ft["flat"]), _p(ft["m"]), _p(ft["v"]), _p(ft["step"]),
+            _p(ft["stats"]), _p(ft["ws"]), N, lr, betas[0], betas[1], eps, weight_decay, min_cum_rewards, max_cum_rewards,
+            self._flags() & ~F_WRITEBACK, _stream()), "emloco_locoval_train_step")
+
+    def finetune_stats(self, reset=True):
+        """(vnet_loss, mean vnet_pred, mean vnet_gt, count) accumulated since the last reset (common_agent.py:204-207,241-243)."""
+        s = self._ft["stats"].tolist()
+        if reset:
+            self._ft["stats"].zero_()
+        n = max(s[3], 1.0)
+        return s[0] / n, s[1] / n, s[2] / n, int(s[3])
+
     def _forward_autograd(self, traj, pose, vel):
         """Weight-gradient path (LocoVal fine-tuning only): plain torch ops, same math as the kernel."""
         xy = traj[..., :2]

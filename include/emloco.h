@@ -239,6 +239,20 @@ int emloco_locoval_backward(const float* d_traj, int32_t traj_stride, int32_t nu
 int emloco_locoval_backward_pose(const float* d_traj, int32_t traj_stride, int32_t num_waypoints, const float* d_pose,
                                  const float* d_vel, const float* d_weights, const float* d_grad_value, float* d_grad_traj,
                                  const float* d_grad_pose_out, float* d_grad_pose_in, int64_t batch, int32_t flags, void* stream);
+/* LocoVal fine-tuning step of the rollout: the `_do_finetune` block of AMPValueAgent.play_steps
+ * (pacer/pacer/learning/amp_continuous_value.py:122-146) with the optimiser of common_agent.py:94-96 -
+ *   valid = nonzero(game_combined); pred = valuenet(traj, pose, vel)[valid];
+ *   target = (game_combined[valid] - r_min) / (r_max - r_min); loss = sum((pred - target)^2); backward; AdamW; game_combined = 0
+ * - entirely on the device (the reference syncs with the host for `valid` every control step).  Nothing happens when no env
+ * is valid.  d_weights [NW] packed as for emloco_locoval_forward, updated in place; d_m / d_v: AdamW moments [NW]; d_step [1]:
+ * optimiser step count (float); d_stats [4] += {loss, sum pred, sum target, count} (vnet_loss / vnet_pred / vnet_gt, :141-144).
+ * d_pose is NOT mutated (the reference passes clones here, vec_task_wrappers.py:54-59).  d_workspace:
+ * emloco_locoval_train_workspace_bytes(N) bytes.  Deterministic (ordered compaction, fixed reduction order). */
+int64_t emloco_locoval_train_workspace_bytes(int64_t num_envs);
+int emloco_locoval_train_step(const float* d_traj, int32_t traj_stride, int32_t num_waypoints, const float* d_pose,
+                              const float* d_vel, float* d_game_combined, float* d_weights, float* d_m, float* d_v, float* d_step,
+                              float* d_stats, void* d_workspace, int64_t num_envs, float lr, float beta1, float beta2, float eps,
+                              float weight_decay, float r_min, float r_max, int32_t flags, void* stream);
 /* Host-buffer scoring (the batch-of-1 filter loop of social-transmotion/evaluate_jta.py:298-302, batched). */
 int emloco_locoval_forward_host(const float* h_traj, int32_t traj_stride, int32_t num_waypoints, const float* h_pose,
                                 const float* h_vel, const float* h_weights, float* h_value, int64_t batch,

@@ -222,6 +222,45 @@ def reference_locoval_multimodal(B=256, modes=5, seed=5):
                 out_pose_after=p.detach().numpy())
 
 
+def reference_locoval_finetune(N=96, seed=9):
+    """The `_do_finetune` block of play_steps (amp_continuous_value.py:122-146) driven on the reference ValuePoseNet with the
+    optimiser and criterion of common_agent.py:94-96; four rounds, the third with no valid env (no optimiser step)."""
+    R = ref_extract.load()
+    torch = R.torch
+    torch.manual_seed(seed)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = R.ValuePoseNet(use_pose=True, use_vel=True)
+    net.train()
+    W0 = {k: v.detach().numpy().copy() for k, v in net.state_dict().items()}
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-3, weight_decay=0.0001)              # common_agent.py:94
+    crit = torch.nn.MSELoss(reduction='sum')                                             # :96
+    opt.zero_grad()
+    rng = np.random.default_rng(seed)
+    f = np.float32
+    rmin, rmax = -10.0, 100.0                                                            # :154-155
+    out = dict(N=N, r_min=f(rmin), r_max=f(rmax), **{f"w0_{k}": a for k, a in W0.items()})
+    for r, frac in enumerate((0.3, 1.0, 0.0, 0.05)):
+        traj2, pose, vel = synth_locoval(N, seed + 10 + r)
+        traj = np.concatenate([traj2, rng.normal(0, 1, (N, 13, 1)).astype(f)], -1)        # waypoint_traj[:, :13, :] is [N,13,3]
+        gc = (rng.uniform(5, 80, N) * (rng.random(N) < frac)).astype(f)
+        t, p, v = torch.from_numpy(traj.copy()), torch.from_numpy(pose.copy()), torch.from_numpy(vel.copy())
+        game = torch.from_numpy(gc.copy())
+        valid = torch.nonzero(game, as_tuple=True)                                       # :123
+        loss_v = 0.0
+        if len(valid[0]) > 0:                                                            # :124
+            pred = net(t[:, :13, :], p, v).squeeze()                                     # :129
+            norm = (game[valid] - rmin) / (rmax - rmin)                                  # :135
+            loss = crit(pred[valid], norm)                                               # :137
+            loss.backward(); opt.step(); opt.zero_grad()                                 # :138-140
+            loss_v = loss.item()
+            out[f"r{r}_pred_sum"] = f(pred[valid].sum().item()); out[f"r{r}_gt_sum"] = f(norm.sum().item())
+        out.update({f"r{r}_traj": traj, f"r{r}_pose": pose, f"r{r}_vel": vel, f"r{r}_gc": gc, f"r{r}_loss": f(loss_v),
+                    f"r{r}_count": len(valid[0])})
+        out.update({f"r{r}_w_{k}": a.detach().numpy().copy() for k, a in net.state_dict().items()})
+    return out
+
+
 def reference_gae(T_, N, seed):
     R = ref_extract.load()
     torch = R.torch
@@ -335,6 +374,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "locoval.npz"), traj=traj, pose=pose, vel=vel,
                         **{f"w_{k}": v for k, v in W.items()}, **{f"out_{k}": v for k, v in out.items()})
     np.savez_compressed(os.path.join(OUT, "locoval_mm5.npz"), **reference_locoval_multimodal())
+    np.savez_compressed(os.path.join(OUT, "locoval_finetune.npz"), **reference_locoval_finetune())
     g = reference_gae(32, 16, 3)
     np.savez_compressed(os.path.join(OUT, "gae.npz"), **g)
     rng = np.random.default_rng(4)

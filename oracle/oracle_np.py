@@ -614,6 +614,45 @@ def locoval_forward(traj, pose, vel, W):
     return (F(1) / (F(1) + np.exp(-z))).astype(F), pose_r
 
 
+def locoval_finetune_step(W, opt, traj, pose, vel, game_combined, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4,
+                          r_min=-10.0, r_max=100.0):
+    """The `_do_finetune` block of AMPValueAgent.play_steps (learning/amp_continuous_value.py:122-146) with
+    torch.optim.AdamW(lr=1e-3, weight_decay=1e-4) and MSELoss(reduction='sum') (learning/common_agent.py:94-96), backward
+    written out by hand in float64.  W: dict fc1/fc2/fc3 -> [weight, bias] (updated in place); opt: dict(step, m, v) with m / v
+    shaped like W.  Returns (loss, sum pred, sum target, count); zeroes game_combined like :145."""
+    valid = np.nonzero(game_combined)[0]
+    if len(valid) == 0:
+        return 0.0, 0.0, 0.0, 0
+    traj_r, pose_r, vel_r, _ = locoval_normalize(traj[valid][..., :2], pose[valid], vel[valid])
+    pose_r[:, [4, 8]] = 0
+    pose_r[:, [9, 10, 11]] = 0
+    B = len(valid)
+    d = np.float64
+    x = np.concatenate([traj_r.reshape(B, 26), pose_r.reshape(B, 72), vel_r.reshape(B, 2)], axis=-1).astype(d)
+    (w1, b1), (w2, b2), (w3, b3) = [[a.astype(d) for a in W[k]] for k in ("fc1", "fc2", "fc3")]
+    h1 = np.maximum(x @ w1.T + b1, 0); h2 = np.maximum(h1 @ w2.T + b2, 0)
+    v = 1 / (1 + np.exp(-(h2 @ w3.T + b3)))[:, 0]
+    target = (game_combined[valid].astype(d) - r_min) / (r_max - r_min)
+    diff = v - target
+    dz = (2 * diff * v * (1 - v))[:, None]
+    g3w, g3b = dz.T @ h2, dz.sum(0)
+    dh2 = (dz @ w3) * (h2 > 0)
+    g2w, g2b = dh2.T @ h1, dh2.sum(0)
+    dh1 = (dh2 @ w2) * (h1 > 0)
+    g1w, g1b = dh1.T @ x, dh1.sum(0)
+    opt["step"] += 1
+    t = opt["step"]
+    bc1, bc2 = 1 - betas[0] ** t, 1 - betas[1] ** t
+    for k, gs in (("fc1", (g1w, g1b)), ("fc2", (g2w, g2b)), ("fc3", (g3w, g3b))):
+        for i, g in enumerate(gs):
+            p = W[k][i].astype(d) * (1 - lr * weight_decay)
+            m = opt["m"][k][i] = betas[0] * opt["m"][k][i] + (1 - betas[0]) * g
+            vv = opt["v"][k][i] = betas[1] * opt["v"][k][i] + (1 - betas[1]) * g * g
+            W[k][i] = (p - (lr / bc1) * m / (np.sqrt(vv) / np.sqrt(bc2) + eps)).astype(F)
+    game_combined[:] = 0
+    return float((diff ** 2).sum()), float(v.sum()), float(target.sum()), B
+
+
 def locoval_loss(value):
     """calc_embodied_motion_loss, learning/value_pose_net.py:151-159: MSE(value, 1)."""
     return np.mean((value - F(1)) ** 2, dtype=F)

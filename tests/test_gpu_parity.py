@@ -342,3 +342,77 @@ def test_locoval_multimodal_loss_matches_reference_golden():
     gr, ref = out.grad.cpu().numpy(), g["out_grad_pred"]
     np.testing.assert_allclose(gr, ref, rtol=2e-3, atol=2e-3 * np.abs(ref).max() * 1e-2)
     assert np.linalg.norm(gr - ref) / np.linalg.norm(ref) < 1e-3
+
+
+def test_locoval_finetune_step_matches_reference_golden():
+    """The `_do_finetune` block of play_steps (amp_continuous_value.py:122-146; AdamW + MSELoss(sum), common_agent.py:94-96)
+    as emloco_locoval_train_step, against four rounds run by the reference ValuePoseNet + torch.optim.AdamW.  Round 2 has no
+    valid env: no optimiser step.  fc1 columns 3 and 99 are excluded from the tight check: those inputs are zero up to
+    round-off after the heading normalisation, so their gradients are noise that Adam normalises to +-lr."""
+    from emloco_b200.value_pose_net import ValuePoseNet
+    g = np.load(os.path.join(GOLDEN, "locoval_finetune.npz"))
+    net = ValuePoseNet(True, True).cuda()
+    net.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("w0_")})
+    net.enable_finetune()
+    steps = 0
+    for r in range(4):
+        traj, pose, vel, gc = (torch.from_numpy(g[f"r{r}_{k}"]).cuda().contiguous() for k in ("traj", "pose", "vel", "gc"))
+        pose0 = pose.clone()
+        net.finetune_step(traj, pose, vel, gc, min_cum_rewards=float(g["r_min"]), max_cum_rewards=float(g["r_max"]))
+        torch.cuda.synchronize()
+        n = int(g[f"r{r}_count"]); steps += n > 0
+        loss, pred, gt, cnt = net.finetune_stats()
+        assert cnt == n and float(gc.abs().sum()) == 0.0 and torch.equal(pose, pose0)
+        if n:
+            np.testing.assert_allclose(loss * n, g[f"r{r}_loss"], rtol=1e-4)
+            np.testing.assert_allclose(pred * n, g[f"r{r}_pred_sum"], rtol=1e-4); np.testing.assert_allclose(gt * n, g[f"r{r}_gt_sum"], rtol=1e-4)
+        sd = {k: v.detach().cpu().numpy() for k, v in net.state_dict().items()}
+        for k in sd:
+            w, ref = sd[k], g[f"r{r}_w_{k}"]
+            if k == "_network.fc1.weight":
+                noise = [3, 99]
+                assert np.abs(w[:, noise] - ref[:, noise]).max() <= 2 * 1e-3 * max(steps, 1) * 1.01
+                w, ref = np.delete(w, noise, 1), np.delete(ref, noise, 1)
+            np.testing.assert_allclose(w, ref, rtol=RTOL, atol=5e-6, err_msg=f"round {r} {k}")
+        assert int(net._ft["step"].item()) == steps
+    # the updated parameters are what the scoring kernels read (same storage)
+    with torch.no_grad():
+        net.eval()
+        traj, pose, vel = (torch.from_numpy(g[f"r3_{k}"]).cuda() for k in ("traj", "pose", "vel"))
+        v_kernel = net(traj.contiguous(), pose.clone(), vel).cpu().numpy()
+    from oracle import oracle_np as O
+    W = {k: (g[f"r3_w__network.{k}.weight"], g[f"r3_w__network.{k}.bias"]) for k in ("fc1", "fc2", "fc3")}
+    v_ref, _ = O.locoval_forward(g["r3_traj"][..., :2], g["r3_pose"].copy(), g["r3_vel"], W)
+    np.testing.assert_allclose(v_kernel, v_ref, rtol=RTOL, atol=1e-5)
+
+
+def test_locoval_finetune_all_envs_valid_at_once():
+    """Step 144 of a synchronised start: every env is valid in the same step (4096 samples, 64 tiles over 64 CTAs); the
+    update equals the fp64 oracle's and is bit-reproducible."""
+    from emloco_b200.synthetic import synthetic_locoval_batch
+    from emloco_b200.value_pose_net import ValuePoseNet
+    from oracle import oracle_np as O
+    N = 4096
+    traj2, pose, vel = synthetic_locoval_batch(N, seed=3)
+    traj = np.concatenate([traj2, np.zeros((N, 13, 1), np.float32)], -1)
+    rng = np.random.default_rng(0)
+    gc = rng.uniform(5, 80, N).astype(np.float32)
+    outs = []
+    for rep in range(2):
+        torch.manual_seed(1)
+        net = ValuePoseNet(True, True).cuda()
+        sd0 = {k: v.detach().cpu().numpy().copy() for k, v in net.state_dict().items()}
+        net.finetune_step(*(torch.from_numpy(a).cuda().contiguous() for a in (traj, pose, vel, gc)))
+        torch.cuda.synchronize()
+        outs.append({k: v.detach().cpu().numpy().copy() for k, v in net.state_dict().items()})
+    for k in outs[0]:
+        np.testing.assert_array_equal(outs[0][k], outs[1][k])
+    W = {k: [sd0[f"_network.{k}.weight"].copy(), sd0[f"_network.{k}.bias"].copy()] for k in ("fc1", "fc2", "fc3")}
+    opt = dict(step=0, m={k: [0.0, 0.0] for k in W}, v={k: [0.0, 0.0] for k in W})
+    O.locoval_finetune_step(W, opt, traj, pose.copy(), vel, gc.copy())
+    for k in W:
+        w, ref = outs[0][f"_network.{k}.weight"], W[k][0]
+        if k == "fc1":
+            w, ref = np.delete(w, [3, 99], 1), np.delete(ref, [3, 99], 1)
+        np.testing.assert_allclose(w, ref, rtol=RTOL, atol=5e-6)
+        np.testing.assert_allclose(outs[0][f"_network.{k}.bias"], W[k][1], rtol=RTOL, atol=5e-6)
