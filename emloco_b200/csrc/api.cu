@@ -7,6 +7,11 @@
 
 cudaError_t eml_locoval_forward(const float*, int, int, float*, const float*, const float*, float*, long long, int, cudaStream_t);
 cudaError_t eml_locoval_backward(const float*, int, int, const float*, const float*, const float*, const float*, float*, const float*, float*, long long, int, cudaStream_t);
+size_t eml_locoval_train_workspace_bytes(long long N);
+cudaError_t eml_locoval_train_step(const float* traj, int stride, int T, const float* pose, const float* vel, float* gc, float* w,
+                                   float* m, float* v, float* step, float* stats, void* workspace, long long N, float lr, float beta1,
+                                   float beta2, float eps, float wd, float r_min, float r_max, int flags, cudaStream_t st);
+
 cudaError_t eml_plausibl_forward(const float*, const float*, float*, long long, cudaStream_t);
 cudaError_t eml_gae(const float*, const float*, const float*, const float*, float*, float*, int, long long, float, float, cudaStream_t);
 cudaError_t eml_linear_fma(const float*, long long, const float*, const float*, float*, long long, long long, int, int,
@@ -294,11 +299,6 @@ int emloco_locoval_backward(const float* d_traj, int32_t traj_stride, int32_t T,
     return emloco_locoval_backward_pose(d_traj, traj_stride, T, d_pose, d_vel, d_weights, d_grad_value, d_grad_traj, nullptr, nullptr,
                                         batch, flags, stream);
 }
-
-size_t eml_locoval_train_workspace_bytes(long long N);
-cudaError_t eml_locoval_train_step(const float* traj, int stride, int T, const float* pose, const float* vel, float* gc, float* w,
-                                   float* m, float* v, float* step, float* stats, void* workspace, long long N, float lr, float beta1,
-                                   float beta2, float eps, float wd, float r_min, float r_max, int flags, cudaStream_t st);
 
 int64_t emloco_locoval_train_workspace_bytes(int64_t N) { return N < 0 ? 0 : (int64_t)eml_locoval_train_workspace_bytes(N); }
 
