@@ -33,7 +33,8 @@ class Rollout:
                  task_reward_w=0.5, disc_reward_w=0.5, disc_reward_scale=2.0, inversion_penalty_scale=0.3,
                  step_to_pred=144, normalize_value=True, net=None, obs_norm=None, amp_norm=None, value_norm=None,
                  recompute_disc=True, valuenet=None, fuse_sinks=True, concurrent=True, reuse_values=False, traj_flags=None,
-                 traj_pool=None, traj_deferred=None):
+                 traj_pool=None, traj_deferred=None, finetune=False, value_lr=1e-3,
+                 min_cum_rewards=-10.0, max_cum_rewards=100.0):
         self.N, self.T, self.device = int(num_envs), int(horizon), int(device)
         self.gamma, self.tau = gamma, tau
         self.task_reward_w, self.disc_reward_w, self.disc_reward_scale = task_reward_w, disc_reward_w, disc_reward_scale
@@ -97,6 +98,12 @@ class Rollout:
             from .value_pose_net import ValuePoseNet
             valuenet = ValuePoseNet(True, True, mutate_pose=False)
         self.valuenet = valuenet.to(dev).eval()
+        # finetune: the `_do_finetune` block of play_steps (:122-146) - LocoVal learns from the discounted returns of the
+        # episodes that just finished, every control step, on the device (ValuePoseNet.finetune_step)
+        self.finetune, self.value_lr = bool(finetune), float(value_lr)
+        self.cum_reward_range = (float(min_cum_rewards), float(max_cum_rewards))          # common_agent.py:154-155
+        if self.finetune:
+            self.valuenet.enable_finetune()
         self._marks = None
         self._graphs = {}
         self._cur = {}
@@ -243,9 +250,15 @@ class Rollout:
         def seg_nets2():   # critic(next obs), discriminator and LocoVal scoring are independent: three graph branches
             nets.fork.run(seg_critic, seg_disc, seg_locoval)
 
+        def seg_record_ft():
+            seg_record()
+            if self.finetune:                                                      # :122-146, after the bookkeeping of this step
+                self.valuenet.finetune_step(self.waypoint_traj, self.init_pose, self.init_vel, self.state[4], lr=self.value_lr,
+                                            min_cum_rewards=self.cum_reward_range[0], max_cum_rewards=self.cum_reward_range[1])
+
         if self.concurrent:
-            return [seg_reset, seg_policy, seg_physics, seg_post, seg_nets2, seg_record]
-        return [seg_reset, seg_policy, seg_physics, seg_post, seg_critic, seg_disc, lambda: (seg_record(), seg_locoval())]
+            return [seg_reset, seg_policy, seg_physics, seg_post, seg_nets2, seg_record_ft]
+        return [seg_reset, seg_policy, seg_physics, seg_post, seg_critic, seg_disc, lambda: (seg_record_ft(), seg_locoval())]
 
     def step(self, n, noise=None, host_obs=False):
         """host_obs: the caller overwrote sim.obs (host-provided observations): operands are re-derived from it."""

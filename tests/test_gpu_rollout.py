@@ -421,3 +421,55 @@ def test_64_envs_100_steps_lockstep_with_cpu_oracle():
     for key, v in worst.items():
         assert v <= 1.0, (key, v)
     gpu.close()
+
+
+def test_rollout_finetunes_locoval_like_the_reference_block():
+    """Rollout(finetune=True): after the bookkeeping of every control step LocoVal takes one AdamW step on the envs whose
+    game_combined_rewards became non-zero (amp_continuous_value.py:122-146).  A twin rollout without fine-tuning supplies the
+    per-step inputs for the fp64 oracle of that block; weights must agree after 12 steps with episodes ending at several
+    different steps (and at one step for many envs at once)."""
+    from emloco_b200.policy import AMPSeptValueNetwork
+    from emloco_b200.rollout import Rollout
+    from emloco_b200.value_pose_net import ValuePoseNet
+    from oracle import oracle_np as O
+    n, K = 96, 12
+    torch.manual_seed(11)
+    net = AMPSeptValueNetwork()
+    torch.manual_seed(12)
+    va, vb = ValuePoseNet(True, True, mutate_pose=False), ValuePoseNet(True, True, mutate_pose=False)
+    vb.load_state_dict(va.state_dict())
+    A = Rollout(n, seed=6, net=net, tensor_cores=True, horizon=K, valuenet=va, finetune=True, traj_flags=4)
+    B = Rollout(n, seed=6, net=net, tensor_cores=True, horizon=K, valuenet=vb, finetune=False, traj_flags=4)
+    for R in (A, B):
+        R.sim.progress[: n // 3] = 160            # these time out inside the horizon (episode length 168)
+        R.sim.progress[n // 3: n // 2] = 164
+        R.state[1].fill_(140.0)                   # current_lengths: everybody crosses step_to_pred = 144 at the same step
+    sd = {k: v.detach().cpu().numpy().copy() for k, v in vb.state_dict().items()}
+    W = {k: [sd[f"_network.{k}.weight"], sd[f"_network.{k}.bias"]] for k in ("fc1", "fc2", "fc3")}
+    opt = dict(step=0, m={k: [0.0, 0.0] for k in W}, v={k: [0.0, 0.0] for k in W})
+    g = torch.Generator(device="cuda").manual_seed(3)
+    used = 0
+    for k in range(K):
+        noise = torch.randn(n, 69, device="cuda", generator=g)
+        B.step(k, noise=noise)
+        torch.cuda.synchronize()
+        gc = B.state[4].cpu().numpy().copy()
+        _, _, _, cnt = O.locoval_finetune_step(W, opt, B.waypoint_traj.cpu().numpy(), B.init_pose.cpu().numpy().copy(),
+                                                B.init_vel.cpu().numpy(), gc)
+        used += cnt
+        B.state[4].zero_()                        # :145
+        A.step(k, noise=noise)
+    torch.cuda.synchronize()
+    assert used > n and opt["step"] >= 3          # all envs at the step_to_pred crossing, plus the time-outs
+    assert int(A.valuenet._ft["step"].item()) == opt["step"]
+    assert float(A.state[4].abs().sum()) == 0.0
+    got = {k: v.detach().cpu().numpy() for k, v in A.valuenet.state_dict().items()}
+    for k in W:
+        w, ref = got[f"_network.{k}.weight"], W[k][0]
+        if k == "fc1":
+            w, ref = np.delete(w, [3, 99], 1), np.delete(ref, [3, 99], 1)      # round-off-noise inputs, see test_gpu_parity
+        np.testing.assert_allclose(w, ref, rtol=RTOL, atol=2e-5, err_msg=k)
+        np.testing.assert_allclose(got[f"_network.{k}.bias"], W[k][1], rtol=RTOL, atol=2e-5, err_msg=k)
+    loss, pred, gt, cnt = A.valuenet.finetune_stats()
+    assert cnt == used and 0.0 <= gt <= 1.5 and 0.0 < pred < 1.0
+    A.close(); B.close()
