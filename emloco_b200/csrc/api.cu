@@ -486,12 +486,13 @@ int emloco_split_bf16(const float* d_x, int64_t ldx, int64_t M, int32_t K, const
 
 static int linear_bf16x3_impl(const int32_t* d_rows, const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, const uint16_t* w_hi, const uint16_t* w_lo,
                          int64_t ldw, const float* d_bias, int64_t M, int32_t N, int32_t K, int32_t relu, float* d_y32, int64_t ldy,
-                         uint16_t* y_hi, uint16_t* y_lo, int64_t ldy16, void* stream) {
+                         uint16_t* y_hi, uint16_t* y_lo, int64_t ldy16, void* stream, const float* head_w = nullptr,
+                         float* head_part = nullptr) {
     if (!a_hi || !a_lo || !w_hi || !w_lo || M < 0 || N <= 0 || K <= 0 || lda < K || ldw < K || (lda & 7) || (ldw & 7))
         return fail(EMLOCO_EINVAL, "emloco_linear_bf16x3: bad operand");
     if (((uintptr_t)a_hi | (uintptr_t)a_lo | (uintptr_t)w_hi | (uintptr_t)w_lo) & 15)
         return fail(EMLOCO_EINVAL, "emloco_linear_bf16x3: operand pointers must be 16-byte aligned");
-    if (!d_y32 && !y_hi) return fail(EMLOCO_EINVAL, "emloco_linear_bf16x3: no output");
+    if (!d_y32 && !y_hi && !head_w) return fail(EMLOCO_EINVAL, "emloco_linear_bf16x3: no output");
     if (d_y32 && ldy < N) return fail(EMLOCO_EINVAL, "emloco_linear_bf16x3: ldy < N");
     if ((y_hi == nullptr) != (y_lo == nullptr)) return fail(EMLOCO_EINVAL, "emloco_linear_bf16x3: y_hi and y_lo must come together");
     if (y_hi && ((N & 31) || ldy16 < N || (ldy16 & 7) || (((uintptr_t)y_hi | (uintptr_t)y_lo) & 15)))
@@ -499,8 +500,20 @@ static int linear_bf16x3_impl(const int32_t* d_rows, const uint16_t* a_hi, const
     const int tile_n = (relu >> 8) & 0xfff;     // bits 8..19 of `relu`: 0 = automatic tile choice, 128 / 256 = forced (tests, tuning)
     if (tile_n != 0 && (tile_n & 0x7ff) != 128 && (tile_n & 0x7ff) != 256)
         return fail(EMLOCO_EINVAL, "emloco_linear_bf16x3: tile must be 0, 128 or 256 (+0x800 for the CTA-pair kernels)");
+    if (head_w && (tile_n & 0x800)) return fail(EMLOCO_EINVAL, "emloco_linear_bf16x3_head: not available with the CTA-pair kernels");
     CK(eml_linear_bf16x3(a_hi, a_lo, lda, w_hi, w_lo, ldw, d_bias, M, N, K, relu & 1, d_y32, ldy, y_hi, y_lo, ldy16, tile_n,
-                         d_rows, (cudaStream_t)stream), "linear bf16x3 (tcgen05)");
+                         d_rows, head_w, head_part, (N + 63) / 64, (cudaStream_t)stream), "linear bf16x3 (tcgen05)");
+    return EMLOCO_OK;
+}
+
+int emloco_linear_bf16x3_head(const int32_t* d_rows, const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, const uint16_t* w_hi,
+                              const uint16_t* w_lo, int64_t ldw, const float* d_bias, int64_t M, int32_t N, int32_t K, int32_t relu,
+                              float* d_y32, int64_t ldy, uint16_t* y_hi, uint16_t* y_lo, int64_t ldy16, const float* d_head_w,
+                              const float* d_head_bias, float* d_head_part, float* d_head_out, void* stream) {
+    if (!d_head_w || !d_head_part || !d_head_out) return fail(EMLOCO_EINVAL, "emloco_linear_bf16x3_head: null head argument");
+    if (int e = linear_bf16x3_impl(d_rows, a_hi, a_lo, lda, w_hi, w_lo, ldw, d_bias, M, N, K, relu, d_y32, ldy, y_hi, y_lo, ldy16, stream,
+                                   d_head_w, d_head_part)) return e;
+    CK(eml_head_reduce(d_head_part, (N + 63) / 64, d_head_bias, d_head_out, M, (cudaStream_t)stream), "head reduce");
     return EMLOCO_OK;
 }
 

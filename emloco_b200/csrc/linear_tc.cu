@@ -40,7 +40,7 @@ template <int BN> struct Tile {
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int BAR_BYTES = 256;
     static constexpr int BIAS_BYTES = 2 * BN * 4;          // bias slice of the tile, double-buffered with the accumulator
-    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + BAR_BYTES + BIAS_BYTES;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + BAR_BYTES + 2 * BIAS_BYTES;   // + fused-head weights
     static constexpr int TMEM_COLS = 2 * BN;               // power of two: 256 or 512
 };
 
@@ -127,12 +127,15 @@ struct GemmArgs {
     __nv_bfloat16* y_hi; __nv_bfloat16* y_lo; long long ldy16;   // split output (optional; N % 32 == 0)
     int M, N, K, relu;
     const int* m_dev;        // optional device-side row count (<= M): tiles beyond it are skipped (compacted row sets)
+    // fused single-output head (value / logit layers, N_head = 1): head_part[row][n / 64] = sum over the 64-column group of
+    // act(y[row][n]) * head_w[n]; the caller adds the groups in order (+ bias).  The layer's own output may then be omitted.
+    const float* head_w; float* head_part; int head_ld;
 };
 
 // One 32-column chunk of one accumulator row: +bias, ReLU, then fp32 store and/or bf16 hi/lo split store.
-__device__ __forceinline__ void epilogue_chunk(const uint32_t* r, const float* __restrict__ s_bias, int nb, int row, bool row_ok,
-                                               const GemmArgs& g) {
-    if (nb >= g.N) return;                                                  // warp-uniform
+__device__ __forceinline__ float epilogue_chunk(const uint32_t* r, const float* __restrict__ s_bias, const float* __restrict__ s_head,
+                                                int nb, int row, bool row_ok, const GemmArgs& g) {
+    if (nb >= g.N) return 0.f;                                              // warp-uniform
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
@@ -142,7 +145,12 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t* r, const float* _
         v[j] = g.relu ? fmaxf(x0, 0.f) : x0; v[j + 1] = g.relu ? fmaxf(x1, 0.f) : x1;
         v[j + 2] = g.relu ? fmaxf(x2, 0.f) : x2; v[j + 3] = g.relu ? fmaxf(x3, 0.f) : x3;
     }
-    if (!row_ok) return;
+    float hd = 0.f;
+    if (g.head_w) {                                                         // head weights are zero beyond N
+#pragma unroll
+        for (int j = 0; j < 32; ++j) hd += v[j] * s_head[j];
+    }
+    if (!row_ok) return hd;
     if (g.y32) {
         float* o = g.y32 + (long long)row * g.ldy + nb;
         if (nb + 32 <= g.N && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
@@ -171,6 +179,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t* r, const float* _
             ol[j] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
         }
     }
+    return hd;
 }
 
 template <int BN>
@@ -189,6 +198,7 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_co
     const uint32_t tmem_slot = bars + 8u * (2 * T::STAGES + 4);
     uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
     float* s_bias = reinterpret_cast<float*>(smem_gen + T::STAGES * T::STAGE_BYTES + T::BAR_BYTES);   // [2][BN]
+    float* s_head = s_bias + 2 * BN;                                                                 // [2][BN]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (g.m_dev) { const int m = __ldg(g.m_dev); g.M = m < g.M ? m : g.M; }     // uniform: every thread reads the same word
@@ -271,7 +281,10 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_co
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
             // bias slice of this tile -> smem (one element per epilogue thread), visible after the epilogue-only barrier
-            if (et < BN) s_bias[acc * BN + et] = (g.bias && n0 + et < g.N) ? __ldg(g.bias + n0 + et) : 0.f;
+            if (et < BN) {
+                s_bias[acc * BN + et] = (g.bias && n0 + et < g.N) ? __ldg(g.bias + n0 + et) : 0.f;
+                if (g.head_w) s_head[acc * BN + et] = n0 + et < g.N ? __ldg(g.head_w + n0 + et) : 0.f;
+            }
             asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
@@ -280,17 +293,20 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_co
             const int c0 = half * (BN / 2);
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c0;
             const float* sb = s_bias + acc * BN + c0;
+            const float* sh = s_head + acc * BN + c0;
             uint32_t ra[32], rb[32];
             tmem_ld32(taddr, ra);
             tmem_ld_wait(ra);
 #pragma unroll
             for (int c = 0; c < NC; c += 2) {                               // two register buffers: the next TMEM load is in
                 tmem_ld32(taddr + (c + 1) * 32, rb);                        // flight while this chunk is converted and stored
-                epilogue_chunk(ra, sb + c * 32, n0 + c0 + c * 32, row, row_ok, g);
+                float hd = epilogue_chunk(ra, sb + c * 32, sh + c * 32, n0 + c0 + c * 32, row, row_ok, g);
                 tmem_ld_wait(rb);
                 if (c + 2 < NC) tmem_ld32(taddr + (c + 2) * 32, ra);
-                epilogue_chunk(rb, sb + (c + 1) * 32, n0 + c0 + (c + 1) * 32, row, row_ok, g);
+                hd += epilogue_chunk(rb, sb + (c + 1) * 32, sh + (c + 1) * 32, n0 + c0 + (c + 1) * 32, row, row_ok, g);
                 if (c + 2 < NC) tmem_ld_wait(ra);
+                const int grp = (n0 + c0 + c * 32) >> 6;                    // the two chunks are one 64-column group
+                if (g.head_part && row_ok && grp < g.head_ld) g.head_part[(long long)row * g.head_ld + grp] = hd;
             }
             tc_fence_before();
             mbar_arrive(tempty_bar(acc));                                   // 256 arrivals release the accumulator
@@ -483,10 +499,10 @@ linear_bf16x3_2cta_kernel(const __grid_constant__ CUtensorMap map_ah, const __gr
 #pragma unroll
             for (int c = 0; c < NC; c += 2) {
                 tmem_ld32(taddr + (c + 1) * 32, rb);
-                epilogue_chunk(ra, sb + c * 32, n0 + c0 + c * 32, row, row_ok, g);
+                epilogue_chunk(ra, sb + c * 32, sb, n0 + c0 + c * 32, row, row_ok, g);      // (no fused head in the pair kernels)
                 tmem_ld_wait(rb);
                 if (c + 2 < NC) tmem_ld32(taddr + (c + 2) * 32, ra);
-                epilogue_chunk(rb, sb + (c + 1) * 32, n0 + c0 + (c + 1) * 32, row, row_ok, g);
+                epilogue_chunk(rb, sb + (c + 1) * 32, sb, n0 + c0 + (c + 1) * 32, row, row_ok, g);
                 if (c + 2 < NC) tmem_ld_wait(ra);
             }
             tc_fence_before();
@@ -627,10 +643,12 @@ cudaError_t eml_split_bf16(const float* x, long long ldx, long long M, int K, co
 
 cudaError_t eml_linear_bf16x3(const void* a_hi, const void* a_lo, long long lda, const void* w_hi, const void* w_lo, long long ldw,
                               const float* bias, long long M, int N, int K, int relu, float* y32, long long ldy, void* y_hi,
-                              void* y_lo, long long ldy16, int tile_n, const int* m_dev, cudaStream_t st) {
+                              void* y_lo, long long ldy16, int tile_n, const int* m_dev, const float* head_w, float* head_part,
+                              int head_ld, cudaStream_t st) {
     if (M <= 0 || N <= 0) return cudaSuccess;
     tc::GemmArgs g;
-    g.m_dev = m_dev;
+    g.m_dev = m_dev; g.head_w = head_w; g.head_part = head_part; g.head_ld = head_ld;
+    if (head_w && (tile_n & 0x800)) return cudaErrorInvalidValue;       // the pair kernels carry no fused head
     g.bias = bias; g.y32 = y32; g.ldy = ldy; g.y_hi = (__nv_bfloat16*)y_hi; g.y_lo = (__nv_bfloat16*)y_lo; g.ldy16 = ldy16;
     g.M = (int)M; g.N = N; g.K = K; g.relu = relu;
     // tile choice: the 128 x 256 tile does 1.33x the flops per operand byte, but needs enough tiles to fill the 148 SMs
@@ -664,7 +682,7 @@ cudaError_t eml_linear_tc(const float* x, long long ldx, const float* w, const f
     __nv_bfloat16 *ah = scratch, *al = ah + M * kp, *wh = al + M * kp, *wl = wh + (long long)N * kp;
     if ((e = eml_split_bf16(x, ldx, M, K, mean, var, eps, ah, al, kp, st)) == cudaSuccess &&
         (e = eml_split_bf16(w, K, N, K, nullptr, nullptr, 0.f, wh, wl, kp, st)) == cudaSuccess)
-        e = eml_linear_bf16x3(ah, al, kp, wh, wl, kp, b, M, N, K, relu, y, ldy, nullptr, nullptr, 0, 0, nullptr, st);
+        e = eml_linear_bf16x3(ah, al, kp, wh, wl, kp, b, M, N, K, relu, y, ldy, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr, 0, st);
     cudaError_t e2 = cudaFreeAsync(scratch, st);
     return e != cudaSuccess ? e : e2;
 }

@@ -190,3 +190,20 @@ cudaError_t eml_fill_next_values(const float* value_raw, const float* prev_dones
     fill_next_values_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(value_raw, prev_dones, prev_next_values, N, v_mean, v_std, unnorm);
     return cudaGetLastError();
 }
+
+// value / logit heads fused into the producing GEMM (emloco_linear_bf16x3_head): the epilogue leaves one partial dot product per
+// 64-column group; they are added here in column order (deterministic), plus the head's bias
+__global__ void head_reduce_kernel(const float* __restrict__ part, int groups, const float* __restrict__ bias, float* __restrict__ out,
+                                   long long M) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    float a = 0.f;
+    for (int g = 0; g < groups; ++g) a += part[i * groups + g];
+    out[i] = a + (bias ? __ldg(bias) : 0.f);
+}
+
+cudaError_t eml_head_reduce(const float* part, int groups, const float* bias, float* out, long long M, cudaStream_t st) {
+    if (M <= 0) return cudaSuccess;
+    head_reduce_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(part, groups, bias, out, M);
+    return cudaGetLastError();
+}

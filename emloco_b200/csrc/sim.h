@@ -106,7 +106,9 @@ cudaError_t eml_split_bf16(const float* x, long long ldx, long long M, int K, co
                            void* hi, void* lo, long long ld16, cudaStream_t st);
 cudaError_t eml_linear_bf16x3(const void* a_hi, const void* a_lo, long long lda, const void* w_hi, const void* w_lo, long long ldw,
                               const float* bias, long long M, int N, int K, int relu, float* y32, long long ldy, void* y_hi,
-                              void* y_lo, long long ldy16, int tile_n, const int* m_dev, cudaStream_t st);
+                              void* y_lo, long long ldy16, int tile_n, const int* m_dev, const float* head_w, float* head_part,
+                              int head_ld, cudaStream_t st);
+cudaError_t eml_head_reduce(const float* part, int groups, const float* bias, float* out, long long M, cudaStream_t st);
 cudaError_t eml_timeout_gather(const int64_t* reset, const int64_t* terminate, long long N, const uint16_t* self_hi,
                                const uint16_t* self_lo, long long ld_self, const uint16_t* task_hi, const uint16_t* task_lo,
                                long long ld_task, uint16_t* c_self_hi, uint16_t* c_self_lo, long long ld_cself, uint16_t* c_task_hi,

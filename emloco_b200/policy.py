@@ -134,6 +134,8 @@ class RolloutNets:
             S = lambda k: _Split(M, k, dev)
             self.s_tin, self.s_t1, self.s_ain, self.s_ac1 = S(TASK_OBS), S(t1), S(SELF_OBS + t2), S(2 * a1)
             self.s_a2, self.s_c2, self.s_d1, self.s_d2 = S(a2), S(a2), S(d1), S(d2)
+            # partial sums of the fused value / logit heads (one per 64 columns of the hidden layer that feeds them)
+            self.hp_c, self.hp_d = f(M, (a2 + 63) // 64), f(M, (d2 + 63) // 64)
             # discriminator operands of every step of the horizon are kept (slot n = rows [n*M, (n+1)*M)), so the post-horizon
             # discriminator pass of play_steps (:157) runs as ONE M*T-row GEMM chain without re-reading the fp32 AMP rows
             self.amp_slots = int(amp_slots)
@@ -223,8 +225,8 @@ class RolloutNets:
 
         def critic():
             if self.tc:
-                linear_bf16x3(self.s_ac1.cols(h, 2 * h), W("c2", n.critic_mlp[2].weight), n.critic_mlp[2].bias.detach(), True, y16=self.s_c2)
-                linear_bf16x3(self.s_c2, W("value", n.value.weight), n.value.bias.detach(), False, y32=self.value)
+                linear_bf16x3(self.s_ac1.cols(h, 2 * h), W("c2", n.critic_mlp[2].weight), n.critic_mlp[2].bias.detach(), True,
+                              head=(n.value, self.value, self.hp_c))            # value layer fused into the epilogue
             else:
                 self._lin(self.ac1[:, h:], n.critic_mlp[2], True, self.c2)
                 self._lin(self.c2, n.value, False, self.value)
@@ -251,8 +253,8 @@ class RolloutNets:
         if self.tc:
             W = self.w16.get
             linear_bf16x3(self.s_ain, W("c0", n.critic_mlp[0].weight), n.critic_mlp[0].bias.detach(), True, y16=self.s_ac1.cols(h, 2 * h))
-            linear_bf16x3(self.s_ac1.cols(h, 2 * h), W("c2", n.critic_mlp[2].weight), n.critic_mlp[2].bias.detach(), True, y16=self.s_c2)
-            linear_bf16x3(self.s_c2, W("value", n.value.weight), n.value.bias.detach(), False, y32=self.next_value)
+            linear_bf16x3(self.s_ac1.cols(h, 2 * h), W("c2", n.critic_mlp[2].weight), n.critic_mlp[2].bias.detach(), True,
+                          head=(n.value, self.next_value, self.hp_c))
             return self.next_value
         self._lin(self.ain, n.critic_mlp[0], True, self.ac1[:, h:])
         self._lin(self.ac1[:, h:], n.critic_mlp[2], True, self.c2)
@@ -269,7 +271,7 @@ class RolloutNets:
             S = lambda k: _Split(M, k, dev)
             h = n.critic_mlp[0].out_features
             self._cc = dict(ain=S(SELF_OBS + n._task_mlp[2].out_features), tin=S(TASK_OBS), t1=S(n._task_mlp[0].out_features), c1=S(h),
-                            c2=S(n.critic_mlp[2].out_features), val=torch.zeros(M, 1, device=dev),
+                            hp=torch.zeros(M, (n.critic_mlp[2].out_features + 63) // 64, device=dev), val=torch.zeros(M, 1, device=dev),
                             idx=torch.zeros(M, dtype=torch.int32, device=dev), count=torch.zeros(1, dtype=torch.int32, device=dev))
         c = self._cc
         _lib.check(_lib.load().emloco_timeout_gather(
@@ -281,19 +283,19 @@ class RolloutNets:
         linear_bf16x3(c["t1"], W("t2", n._task_mlp[2].weight), n._task_mlp[2].bias.detach(), True,
                       y16=c["ain"].cols(SELF_OBS, c["ain"].K), rows=r)
         linear_bf16x3(c["ain"], W("c0", n.critic_mlp[0].weight), n.critic_mlp[0].bias.detach(), True, y16=c["c1"], rows=r)
-        linear_bf16x3(c["c1"], W("c2", n.critic_mlp[2].weight), n.critic_mlp[2].bias.detach(), True, y16=c["c2"], rows=r)
-        linear_bf16x3(c["c2"], W("value", n.value.weight), n.value.bias.detach(), False, y32=c["val"], rows=r)
+        linear_bf16x3(c["c1"], W("c2", n.critic_mlp[2].weight), n.critic_mlp[2].bias.detach(), True, rows=r,
+                      head=(n.value, c["val"], c["hp"]))
         return c["val"], c["idx"], c["count"]
 
     def disc_logits_all(self, out):
         """The discriminator over the operands of ALL slots at once (rows = M * amp_slots): out [M*amp_slots, 1]."""
         n, W, rows = self.net, self.w16.get, self.M * self.amp_slots
         if self._all is None:
-            self._all = (_Split(rows, n._disc_mlp[0].out_features, out.device), _Split(rows, n._disc_mlp[2].out_features, out.device))
+            self._all = (_Split(rows, n._disc_mlp[0].out_features, out.device),
+                         torch.empty(rows, (n._disc_mlp[2].out_features + 63) // 64, device=out.device))      # d1, head partials
         d1, d2 = self._all
         linear_bf16x3(self.s_amp, W("d0", n._disc_mlp[0].weight), n._disc_mlp[0].bias.detach(), True, y16=d1)
-        linear_bf16x3(d1, W("d2", n._disc_mlp[2].weight), n._disc_mlp[2].bias.detach(), True, y16=d2)
-        linear_bf16x3(d2, W("dl", n._disc_logits.weight), n._disc_logits.bias.detach(), False, y32=out)
+        linear_bf16x3(d1, W("d2", n._disc_mlp[2].weight), n._disc_mlp[2].bias.detach(), True, head=(n._disc_logits, out, d2))
         return out
 
     def disc_logits(self, amp_obs, out=None, operands_ready=False, slot=0):
@@ -311,8 +313,7 @@ class RolloutNets:
             linear_bf16x3(s_amp, W("d0", n._disc_mlp[0].weight), n._disc_mlp[0].bias.detach(), True,
                           y16=self.s_d1.rows_view(m))
             linear_bf16x3(self.s_d1.rows_view(m), W("d2", n._disc_mlp[2].weight), n._disc_mlp[2].bias.detach(), True,
-                          y16=self.s_d2.rows_view(m))
-            linear_bf16x3(self.s_d2.rows_view(m), W("dl", n._disc_logits.weight), n._disc_logits.bias.detach(), False, y32=out)
+                          head=(n._disc_logits, out, self.hp_d))
             return out
         linear(amp_obs, n._disc_mlp[0].weight.detach(), n._disc_mlp[0].bias.detach(), relu=True, mean=mean, var=var,
                eps=self.amp_norm.epsilon, out=self.d1[:m])
@@ -352,17 +353,28 @@ def split_bf16(x, dst: _Split, mean=None, var=None, eps=1e-5):
     return dst
 
 
-def linear_bf16x3(a: _Split, w: _Split, bias, relu, y32=None, y16: _Split = None, tile=0, rows=None):
+def linear_bf16x3(a: _Split, w: _Split, bias, relu, y32=None, y16: _Split = None, tile=0, rows=None, head=None):
     """y = act(a w^T + bias) on the tcgen05 path; fp32 output and/or split output for the next layer.
     tile: 0 = library picks the output-tile width, 128 / 256 = forced.
-    rows: optional int32 device scalar - only that many leading rows are valid (compacted row sets)."""
+    rows: optional int32 device scalar - only that many leading rows are valid (compacted row sets).
+    head: optional (layer nn.Linear(N, 1), out [M,1], part [M, ceil(N/64)]) - the single-output layer that follows, fused
+          into the epilogue (emloco_linear_bf16x3_head); y32 / y16 may then be omitted."""
     M, K, N = a.rows, a.K, w.rows
     assert w.K == K
     if y32 is not None:
         assert y32.shape == (M, N) and y32.stride(1) == 1
     args = (_ptr(a.hi), _ptr(a.lo), a.ld, _ptr(w.hi), _ptr(w.lo), w.ld, _ptr(bias), M, N, K, int(bool(relu)) | (int(tile) << 8),
             _ptr(y32), 0 if y32 is None else y32.stride(0), None if y16 is None else _ptr(y16.hi),
-            None if y16 is None else _ptr(y16.lo), 0 if y16 is None else y16.ld, _stream())
+            None if y16 is None else _ptr(y16.lo), 0 if y16 is None else y16.ld)
+    if head is not None:
+        layer, out, part = head
+        hw = layer.weight.detach()
+        assert hw.shape == (1, N) and hw.is_contiguous() and out.shape == (M, 1) and out.is_contiguous()
+        assert part.is_contiguous() and part.shape[0] >= M and part.shape[1] == (N + 63) // 64
+        _lib.check(_lib.load().emloco_linear_bf16x3_head(_ptr(rows), *args, _ptr(hw), _ptr(layer.bias.detach()), _ptr(part), _ptr(out),
+                                                         _stream()), "emloco_linear_bf16x3_head")
+        return
+    args = args + (_stream(),)
     if rows is None:
         _lib.check(_lib.load().emloco_linear_bf16x3(*args), "emloco_linear_bf16x3")
     else:

@@ -329,6 +329,17 @@ int emloco_linear_bf16x3_rows(const int32_t* d_rows, const uint16_t* d_a_hi, con
                               int32_t N, int32_t K, int32_t relu, float* d_y32, int64_t ldy, uint16_t* d_y_hi, uint16_t* d_y_lo,
                               int64_t ldy16, void* stream);
 
+/* The same GEMM with a single-output head fused into its epilogue - the `value` / `_disc_logits` layers that follow the last
+ * hidden layer (amp_network_sept_builder.py:69-80, amp_network_builder.py:81-84): head_out[m] = head_bias[0] +
+ * sum_n act(y[m][n]) * head_w[n], taken from the fp32 accumulator (no rounding of the hidden layer to the split format).
+ * The epilogue writes one partial per 64-column group into d_head_part [M, ceil(N/64)]; a second small kernel adds them in
+ * column order (deterministic, independent of the tile choice).  d_y32 / y_hi may all be NULL when only the head is wanted.
+ * d_rows may be NULL (all M rows).  Not available with the CTA-pair tiles. */
+int emloco_linear_bf16x3_head(const int32_t* d_rows, const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, const uint16_t* w_hi,
+                              const uint16_t* w_lo, int64_t ldw, const float* d_bias, int64_t M, int32_t N, int32_t K, int32_t relu,
+                              float* d_y32, int64_t ldy, uint16_t* y_hi, uint16_t* y_lo, int64_t ldy16, const float* d_head_w,
+                              const float* d_head_bias, float* d_head_part, float* d_head_out, void* stream);
+
 /* ---- value reuse (optional): `_eval_critic(next obs)` of play_steps (amp_continuous_value.py:85-90) without a second full
  * critic pass.  For an env that is not reset, the next observation IS the observation of the following step, whose policy
  * pass evaluates the critic on it anyway; terminated envs get next_value = 0; only envs reset by the episode time-out

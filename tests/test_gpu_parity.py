@@ -416,3 +416,37 @@ def test_locoval_finetune_all_envs_valid_at_once():
             w, ref = np.delete(w, [3, 99], 1), np.delete(ref, [3, 99], 1)
         np.testing.assert_allclose(w, ref, rtol=RTOL, atol=5e-6)
         np.testing.assert_allclose(outs[0][f"_network.{k}.bias"], W[k][1], rtol=RTOL, atol=5e-6)
+
+
+@pytest.mark.parametrize("tile", [0, 128, 256])
+@pytest.mark.parametrize("M,N,K,with_y", [(4096, 1024, 2048, False), (300, 512, 1024, True), (129, 96, 200, False), (64, 1024, 624, True)])
+def test_linear_bf16x3_fused_head_matches_fp64(tile, M, N, K, with_y):
+    """The value / logit layer (nn.Linear(N, 1)) fused into the epilogue of the hidden layer that feeds it: per-row partial
+    dot products per 64-column group + an ordered reduction.  Same result for every tile shape (bit-identical), with or
+    without the hidden layer's own output, and for a compacted row count."""
+    from emloco_b200.policy import _Split, linear_bf16x3, split_bf16
+    rng = np.random.default_rng(M + N + K)
+    x = rng.normal(0, 1.5, (M, K)).astype(np.float32)
+    w = (rng.normal(0, 1, (N, K)) / np.sqrt(K)).astype(np.float32); b = rng.normal(0, 0.1, N).astype(np.float32)
+    T = lambda a: torch.from_numpy(a).cuda()
+    head = torch.nn.Linear(N, 1).cuda()
+    sx, sw = _Split(M, K, "cuda"), _Split(N, K, "cuda")
+    split_bf16(T(x), sx); split_bf16(T(w), sw)
+    out = torch.full((M, 1), 7.0, device="cuda"); part = torch.zeros(M, (N + 63) // 64, device="cuda")
+    y = torch.empty(M, N, device="cuda") if with_y else None
+    linear_bf16x3(sx, sw, T(b), True, y32=y, tile=tile, head=(head, out, part))
+    h = np.maximum(x.astype(np.float64) @ w.astype(np.float64).T + b, 0)
+    ref = h @ head.weight.detach().cpu().numpy().astype(np.float64).T + head.bias.item()
+    scale = np.abs(h) @ np.abs(head.weight.detach().cpu().numpy().astype(np.float64)).T + abs(head.bias.item())
+    assert (np.abs(out.cpu().numpy() - ref) / scale).max() < 1e-4
+    if with_y:
+        np.testing.assert_allclose(y.cpu().numpy(), h, rtol=1e-3, atol=1e-4)
+    # tile independence (what lets the compact critic of the value-reuse path stay bit-identical to the full pass)
+    out2 = torch.zeros(M, 1, device="cuda")
+    linear_bf16x3(sx, sw, T(b), True, tile=128 if tile != 128 else 256, head=(head, out2, part))
+    assert torch.equal(out, out2)
+    # device-side row count: rows beyond it are left alone
+    r = max(M // 3, 1)
+    out3 = torch.full((M, 1), -3.0, device="cuda")
+    linear_bf16x3(sx, sw, T(b), True, tile=tile, rows=torch.tensor([r], dtype=torch.int32, device="cuda"), head=(head, out3, part))
+    assert torch.equal(out3[:r], out[:r])
