@@ -18,6 +18,23 @@ def _worker(rank, world, port, q):
     lo, hi = D.shard_envs(4097, r, w)
     out = dict(rank=r, world=w, seed=D.rank_seed(7, r), shard=(lo, hi), tmax=D.max_over_ranks(10.0 + r),
                tsum=D.sum_over_ranks(1.0 + r), kl=D.average_scalar(0.5 * (r + 1)))
+    # the gradient average of the training step: one all-reduce over one flat buffer that the .grad views alias
+    import torch
+    torch.manual_seed(0)                                      # same weights on every rank (hvd broadcast)
+    from emloco_b200.policy import AMPSeptValueNetwork
+    net = AMPSeptValueNetwork()
+    fg = D.FlatGrads(net.parameters())
+    x = torch.full((4, 1422), 0.1 * (r + 1))                  # rank-local batch
+    loss = net.mu(net.actor_mlp(torch.cat([x[:, :368], net._task_mlp(x[:, 368:])], -1))).sum() + net.mu.bias.sum() * (r + 1)
+    loss.backward()
+    k = [i for i, p in enumerate(fg.params) if p is net.mu.weight][0]
+    assert net.mu.weight.grad.data_ptr() == fg.flat[sum(p.numel() for p in fg.params[:k]):].data_ptr()     # .grad aliases the bucket
+    local = fg.flat.clone()
+    fg.average()
+    out.update(nparams=fg.flat.numel(), local_sum=float(local.double().sum()), avg_sum=float(fg.flat.double().sum()),
+               sigma_grad=float(net.mu.bias.grad.mean()), nbytes=fg.nbytes())
+    fg.zero()
+    assert float(net.mu.weight.grad.abs().sum()) == 0.0       # the views survive zeroing
     D.finalize()
     q.put(out)
 
@@ -37,6 +54,11 @@ def test_two_rank_gloo_plumbing():
     assert res[0]["shard"] == (0, 2049) and res[1]["shard"] == (2049, 4097)      # disjoint, covering
     assert all(d["tmax"] == 11.0 for d in res) and all(d["tsum"] == 3.0 for d in res)
     assert all(abs(d["kl"] - 0.75) < 1e-12 for d in res)
+    # gradient average: both ranks hold the mean of the two local gradients
+    assert res[0]["nparams"] == res[1]["nparams"] > 11_000_000 and res[0]["nbytes"] == 4 * res[0]["nparams"]
+    mean = 0.5 * (res[0]["local_sum"] + res[1]["local_sum"])
+    assert all(abs(d["avg_sum"] - mean) <= 1e-6 * max(1.0, abs(mean)) for d in res)
+    assert all(abs(d["sigma_grad"] - 5.5) < 1e-5 for d in res)                   # 4 rows + (1 + 2) / 2
 
 
 def test_bench_reference_arm_under_two_ranks():
