@@ -213,6 +213,15 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count - l0
+    # the post-horizon pass on its own (discriminator over the [32 x N] stored AMP observations, reward combine, GAE): it runs
+    # once per 32 steps inside the timed loop above
+    ef0, ef1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ef0.record()
+    (R.finish_graphed if graphs else R.finish)()
+    ef1.record()
+    torch.cuda.synchronize()
+    finish_ms = ef0.elapsed_time(ef1)
     clocks = sampler.stop() if rank == 0 else None
     # per-segment device times: the same step replayed as seven per-segment graphs (8 slots) with an event between them
     seg_step = (lambda i: R.step_segments_graphed(i % 8)) if graphs else (lambda i: R.step(i % HORIZON))
@@ -378,6 +387,7 @@ def run_ours(args):
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
             "roofline": roof, "kernels": kern, "segments_ms": seg,
+            "post_horizon_ms": finish_ms,
             "locoval": {"metric": "locoval_scores_per_sec", "value": lv_rate, "unit": "scores/s", "batch": B, "ms": lv_ms},
             "cpu_baseline": cpu, "variants": variant,
         }

@@ -89,8 +89,10 @@ class Fork:
     plain stream concurrency otherwise.  Small layers (heads, task-value MLP, LocoVal) occupy a fraction of the 148 SMs;
     branches let them overlap instead of serialising."""
 
-    def __init__(self, device, n=3):
-        self.streams = [torch.cuda.Stream(device=device) for _ in range(n)]
+    def __init__(self, device, n=3, priority=0):
+        # priority -1: kernels of the side branches are dispatched ahead of the main branch's when both are pending (the
+        # priority of the capturing stream is recorded into the graph's kernel nodes)
+        self.streams = [torch.cuda.Stream(device=device, priority=priority) for _ in range(n)]
 
     def run(self, *fns):
         cur = torch.cuda.current_stream()
@@ -129,7 +131,7 @@ class RolloutNets:
         self.d1, self.d2, self.logit = f(M, d1), f(M, d2), f(M, 1)
         self.actions, self.neglogp = f(M, ACTIONS), f(M)
         self._stacked = None
-        self.fork = Fork(dev) if concurrent else None
+        self.fork = Fork(dev, priority=-1) if concurrent else None
         if self.tc:
             S = lambda k: _Split(M, k, dev)
             self.s_tin, self.s_t1, self.s_ain, self.s_ac1 = S(TASK_OBS), S(t1), S(SELF_OBS + t2), S(2 * a1)
@@ -239,7 +241,9 @@ class RolloutNets:
 
         if self.fork is not None:
             trunk_ac1()
-            self.fork.run(actor, critic, task_value)
+            # the actor branch (a2 -> mu -> sample) is the longer one and the physics step waits for it: it runs on a
+            # high-priority side stream so that a2's tiles are dispatched before c2's and mu / sample overlap c2's second wave
+            self.fork.run(critic, actor, task_value)
         else:
             trunk_ac1(); actor(); critic(); task_value()
         return dict(mus=mu_out, sigmas=n.sigma, values=self.value, task_values=task_value_out, actions=actions_out,
