@@ -475,3 +475,52 @@ def test_rollout_finetunes_locoval_like_the_reference_block():
     loss, pred, gt, cnt = A.valuenet.finetune_stats()
     assert cnt == used and 0.0 <= gt <= 1.5 and 0.0 < pred < 1.0
     A.close(); B.close()
+
+
+def test_gym_shim_env_creation_sequence():
+    """The env-creation calls of humanoid.py:643-946 (+ the terrain tri-mesh of ..terrain.py:866-877) recorded into a pending
+    sim and realised by prepare_sim: same sim as one built directly from the same gains, start poses and height field."""
+    from emloco_b200 import gym_shim as G
+    from emloco_b200.mjcf import default_model
+    from emloco_b200.model import build_model_arrays
+    from emloco_b200.sim import EmlocoSim
+    n = 12
+    gym = G.acquire_gym()
+    sim = gym.create_sim(0, -1, G.SIM_PHYSX, G.SimParams())                        # base_task.py:238
+    hs = np.zeros((700, 700), np.int16); hs[520:540, :] = 60                       # a 0.3 m ridge across the patch
+    x = np.arange(700) * 0.1
+    yy, xx = np.meshgrid(x, x)
+    verts = np.stack([xx.flatten(), yy.flatten(), hs.flatten() * 0.005], 1).astype(np.float32)
+    tm = G.TriangleMeshParams(); tm.nb_vertices = verts.shape[0]; tm.static_friction = 1.0
+    gym.add_triangle_mesh(sim, verts.flatten(), np.zeros(3, np.uint32), tm)
+    opt = G.AssetOptions(); opt.angular_damping = 0.01; opt.max_angular_velocity = 100.0
+    asset = gym.load_asset(sim, "data/assets/mjcf", "smpl_humanoid.xml", opt)
+    pd_scale = asset.model.total_mass / 77.0                                       # humanoid.py:905-910
+    for i in range(n):
+        env = gym.create_env(sim, G.Vec3(-5, -5, 0), G.Vec3(5, 5, 5), 4)
+        pose = G.Transform(); pose.p = G.Vec3(51.0 + 0.3 * i, 52.0 + 0.1 * i, 0.95); pose.r = G.Quat(0, 0, 0, 1)
+        h = gym.create_actor(env, asset, pose, "humanoid", i, 0, 0)
+        gym.enable_actor_dof_force_sensors(env, h)
+        prop = gym.get_asset_dof_properties(asset)
+        prop["driveMode"] = G.DOF_MODE_POS
+        prop["stiffness"] *= pd_scale; prop["damping"] *= pd_scale
+        gym.set_actor_dof_properties(env, h, prop)
+    gym.prepare_sim(sim)                                                           # base_task.py:128
+    root = G.wrap_tensor(gym.acquire_actor_root_state_tensor(sim))
+    rb = G.wrap_tensor(gym.acquire_rigid_body_state_tensor(sim))
+    assert root.shape == (n, 13)
+    np.testing.assert_allclose(root[:, 0].cpu().numpy(), 51.0 + 0.3 * np.arange(n), rtol=1e-6)
+    ref = EmlocoSim(n, model_arrays=build_model_arrays(default_model()))           # the default table carries the same mass scaling
+    ref.set_height_field(hs)
+    ref.root_state.copy_(root); ref.reset_indexed(None)
+    np.testing.assert_allclose(np.asarray(sim.real.model_arrays["kp"]), np.asarray(ref.model_arrays["kp"]), rtol=1e-6)
+    act = torch.rand(n, 69, device="cuda") * 0.2 - 0.1
+    for _ in range(5):
+        ref.step(act)
+        gym.set_dof_position_target_tensor(sim, G.unwrap_tensor(ref.pd_target.clone()))
+        for _ in range(2):
+            gym.simulate(sim)
+        gym.fetch_results(sim, True)
+    np.testing.assert_allclose(rb.cpu().numpy(), ref.rb_state.cpu().numpy(), rtol=1e-4, atol=1e-5)
+    assert gym.get_frame_count(sim) == 10 and gym.get_sim_params(sim).substeps == 2
+    gym.destroy_sim(sim); ref.close()
