@@ -370,9 +370,9 @@ def run_ours(args):
         cores = os.cpu_count() or 1
         cpu = None
         if not args.no_cpu_baseline and world == 1:     # reported at N = 1 only
-            rate, done, dt = cpu_rollout_rate(64, 40, 1, seed=args.seed, budget_s=20.0)
+            rate, done, dt = cpu_rollout_rate(256, 1000, 2, seed=args.seed, budget_s=15.0)
             cpu = {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                   "sample": f"64 envs x {done} steps in {dt:.1f} s (configs[0] size; fp64 C physics oracle with OpenMP + numpy nets/post-step)"}
+                   "sample": f"256 of {N} envs per step, {done} steps in {dt:.1f} s (fp64 C physics oracle with OpenMP + numpy nets/post-step)"}
 
         out = {
             "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
