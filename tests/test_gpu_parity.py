@@ -450,3 +450,66 @@ def test_linear_bf16x3_fused_head_matches_fp64(tile, M, N, K, with_y):
     out3 = torch.full((M, 1), -3.0, device="cuda")
     linear_bf16x3(sx, sw, T(b), True, tile=tile, rows=torch.tensor([r], dtype=torch.int32, device="cuda"), head=(head, out3, part))
     assert torch.equal(out3[:r], out[:r])
+
+
+@pytest.mark.parametrize("use_pose,use_vel,vru", [(True, True, False), (False, False, False), (False, True, False),
+                                                  (True, False, False), (True, True, True)])
+def test_locoval_variant_gradients_match_float64_autograd(use_pose, use_vel, vru):
+    """d loss / d traj of every ValuePoseNet variant, for two consecutive calls on ONE pose tensor (the second call's loss
+    reaches the first call's trajectory through the in-place rotated pose), against torch float64 autograd of an independent
+    restatement of value_pose_net.py:73-149 on the CPU."""
+    from emloco_b200.value_pose_net import ValuePoseNet
+    torch.manual_seed(3)
+    T, B = (5 if vru else 13), 300
+    net = ValuePoseNet(use_pose, use_vel, vru=vru).cuda().eval()
+    with torch.no_grad():
+        for m in net._network:
+            if hasattr(m, "bias"):
+                m.bias.uniform_(-0.2, 0.2)
+    tr = [torch.randn(B, T, 2) for _ in range(2)]
+    for t in tr:
+        t[:, 0] = 0
+    pose0 = torch.randn(B, 24, 3) * 0.3
+    vel = torch.randn(B, 2)
+
+    # --- kernels
+    kt = [t.clone().cuda().requires_grad_(True) for t in tr]
+    kp = pose0.clone().cuda()
+    loss = 0
+    for t in kt:
+        _, l = net.calc_embodied_motion_loss(t, kp if use_pose else None, vel.cuda() if use_vel else None)
+        loss = loss + l
+    loss.backward()
+
+    # --- float64 restatement
+    W = [(getattr(net._network, k).weight.detach().cpu().double(), getattr(net._network, k).bias.detach().cpu().double())
+         for k in ("fc1", "fc2", "fc3")]
+    rt = [t.clone().double().requires_grad_(True) for t in tr]
+    p = pose0.clone().double()
+    ref_loss = 0
+    for t in rt:
+        x1 = t[:, 1, 0]
+        near = x1.abs() < 1e-10
+        x1 = x1 * (~near) + near * 1e-10
+        ang = torch.atan2(t[:, 1, 1], x1)
+        c, s = torch.cos(ang), torch.sin(ang)
+        R = torch.stack([torch.stack([c, -s], -1), torch.stack([s, c], -1)], -2)
+        feats = [torch.bmm(t, R).reshape(B, -1)]
+        if use_pose:
+            p = torch.cat([torch.bmm(p[:, :, :2], R), p[:, :, 2:]], -1)          # functional form of the in-place update
+            mask = torch.ones(24, 1, dtype=torch.float64); mask[[4, 8, 9, 10, 11]] = 0
+            p = p * mask
+            feats.append(p.reshape(B, 72))
+        if use_vel:
+            feats.append(torch.bmm(vel.double().unsqueeze(1), R)[:, 0])
+        h = torch.relu(torch.cat(feats, -1) @ W[0][0].T + W[0][1])
+        h = torch.relu(h @ W[1][0].T + W[1][1])
+        v = torch.sigmoid(h @ W[2][0].T + W[2][1])
+        ref_loss = ref_loss + ((v - 1) ** 2).mean()
+    ref_loss.backward()
+    np.testing.assert_allclose(loss.item(), ref_loss.item(), rtol=RTOL)
+    for a, b in zip(kt, rt):
+        g, r = a.grad.cpu().numpy(), b.grad.numpy()
+        assert np.abs(g - r).max() <= 2e-3 * np.abs(r).max() + 1e-9, (np.abs(g - r).max(), np.abs(r).max())
+    if use_pose:
+        np.testing.assert_allclose(kp.detach().cpu().numpy(), p.detach().numpy(), rtol=RTOL, atol=2e-6)
