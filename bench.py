@@ -347,7 +347,10 @@ def run_ours(args):
         nets_ms = seg["policy"] + (seg["critic+disc+locoval"] if "critic+disc+locoval" in seg else seg["critic"] + seg["disc"])
         kern = {
             "physics": {"bound": "hbm", "ms": seg["physics"], "achieved": N * BYTES_PHYSICS / (seg["physics"] * 1e-3) / 1e9,
-                        "peak": pk["hbm"], "unit": "GB/s"},
+                        "peak": pk["hbm"], "unit": "GB/s",
+                        "note": "latency-bound, not HBM-bound: 4 sub-steps x 3 tree passes whose critical path is 9 dependent "
+                                "articulated-body updates (arm chain + spine); 840 M thread-instructions per launch (ncu), "
+                                "issue-active 22 %, one 8-warp CTA per SM because 4096 envs are 28 per SM"},
             "post_step": {"bound": "hbm", "ms": seg["post_step"], "achieved": N * BYTES_POST / (seg["post_step"] * 1e-3) / 1e9,
                           "peak": pk["hbm"], "unit": "GB/s", "note": "segment includes the 50 MB AMP-obs experience-row copy"},
             "nets": {"bound": "tensor", "ms": nets_ms, "achieved": N * FLOP_NETS_STEP / (nets_ms * 1e-3) / 1e12, "peak": pk["tf_sustained"], "unit": "TFLOP/s"},
