@@ -1,3 +1,4 @@
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o scripts/cu/lvtime scripts/cu/lvtime.cu emloco_b200/libemloco_b200.so -Xlinker -rpath -Xlinker '$ORIGIN/../../emloco_b200'
 // standalone timing of emloco_locoval_forward through the C ABI: cudaEvent pairs and %globaltimer stamps
 #include <cstdio>
 #include <cstdlib>
