@@ -102,6 +102,9 @@ class ValuePoseNet(nn.Module):
 
     # ---- weights packed in state-dict order for the kernel (cached until a parameter changes) ----
     def _weights(self):
+        ft = getattr(self, "_ft", None)
+        if ft is not None and self._network.fc1.weight.data_ptr() == ft["flat"].data_ptr():
+            return ft["flat"]                    # fine-tuning: the parameters ARE views of the packed buffer (enable_finetune)
         ps = [self._network.fc1.weight, self._network.fc1.bias, self._network.fc2.weight, self._network.fc2.bias,
               self._network.fc3.weight, self._network.fc3.bias]
         key = tuple((p.data_ptr(), p._version, p.device) for p in ps)

@@ -375,7 +375,8 @@ def test_locoval_finetune_step_matches_reference_golden():
                 w, ref = np.delete(w, noise, 1), np.delete(ref, noise, 1)
             np.testing.assert_allclose(w, ref, rtol=RTOL, atol=5e-6, err_msg=f"round {r} {k}")
         assert int(net._ft["step"].item()) == steps
-    # the updated parameters are what the scoring kernels read (same storage)
+    # the updated parameters are what the scoring kernels read (same storage), also after a load_state_dict in between
+    net.load_state_dict({k: v.clone() for k, v in net.state_dict().items()})
     with torch.no_grad():
         net.eval()
         traj, pose, vel = (torch.from_numpy(g[f"r3_{k}"]).cuda() for k in ("traj", "pose", "vel"))
