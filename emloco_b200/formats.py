@@ -146,3 +146,47 @@ def score_and_filter(valuenet, pred_trajs, init_pose, init_vel, threshold=0.7):
     finally:
         valuenet.mutate_pose = was
     return values, filter_modes(values, threshold)
+
+
+# ---- reference configuration files -> constructor arguments -----------------------------------------------------------
+def kwargs_from_reference_cfg(env_cfg, train_cfg, run_flags=None):
+    """Maps the reference's two YAML trees - `data/cfg/pacer.yaml` (env_cfg, the dict with the `env` key) and
+    `data/cfg/train/rlg/amp_humanoid_smpl_sept_task.yaml` (train_cfg, the dict with the `params` key) - and the run.py
+    command-line flags (`--real_path ... --adjust_root_vel --init_heading --heading_inversion --slow`, run.py:262-331) onto the
+    arguments of this package:  -> dict(net=..., rollout=..., sim=..., traj=..., num_envs=...)
+        AMPSeptValueNetwork(**net); Rollout(num_envs, net=..., **rollout, sim_cfg=sim, traj_cfg=traj)
+    Keys the hot path does not use (viewer, logging, optimiser) are ignored; unsupported settings raise ValueError."""
+    from . import _lib
+    env, prm = env_cfg["env"], train_cfg["params"]
+    cfg, nw = prm["config"], prm["network"]
+    if nw["space"]["continuous"].get("learn_sigma", False) or not nw["space"]["continuous"].get("fixed_sigma", True):
+        raise ValueError("only fixed_sigma / learn_sigma False is implemented (amp_humanoid_smpl_sept_task.yaml:19-27)")
+    if not env.get("pdControl", True):
+        raise ValueError("only pdControl is implemented (humanoid.py:905-910)")
+    if env.get("numAMPObsSteps", 15) != 15 or env.get("numTrajSamples", 15) != 15:
+        raise ValueError("kernels are specialised for 15 AMP steps and 15 trajectory samples (pacer.yaml:46,53)")
+    net = dict(mlp_units=tuple(nw["mlp"]["units"]), task_units=tuple(nw["task_mlp"]["units"]),
+               value_units=tuple(nw["value_mlp"]["units"]), disc_units=tuple(nw["disc"]["units"]),
+               sigma_init=float(nw["space"]["continuous"]["sigma_init"]["val"]))
+    rollout = dict(horizon=int(cfg["horizon_length"]), gamma=float(cfg["gamma"]), tau=float(cfg["tau"]),
+                   task_reward_w=float(cfg["task_reward_w"]), disc_reward_w=float(cfg["disc_reward_w"]),
+                   disc_reward_scale=float(cfg["disc_reward_scale"]),
+                   inversion_penalty_scale=float(cfg.get("inversion_penalty_scale", 0.3)),
+                   step_to_pred=int(env.get("stepToPred", 144)), normalize_value=bool(cfg.get("normalize_value", True)),
+                   finetune=bool(cfg.get("player", {}).get("finetune", False)))
+    sim = dict(episode_length=int(env["episodeLength"]), control_freq_inv=int(env["controlFrequencyInv"]),
+               power_coefficient=float(env.get("power_coefficient", 0.0005)),
+               location_coefficient=float(env.get("location_coefficient", 1.0)),
+               traj_sample_dt=float(env["trajSampleTimestep"]),
+               friction_mu=float(env.get("terrain", {}).get("staticFriction", 1.0)))
+    traj = dict(speed_min=float(env["speedMin"]), speed_max=float(env["speedMax"]), accel_max=float(env["accelMax"]),
+                sharp_turn_prob=float(env["sharpTurnProb"]), hybrid_init_prob=float(env.get("hybridInitProb", 0.5)))
+    f = run_flags or {}
+    flags = ((_lib.TRAJ_REAL_PATH if f.get("real_path") else 0) | (_lib.TRAJ_ADJUST_ROOT_VEL if f.get("adjust_root_vel") else 0)
+             | (_lib.TRAJ_INIT_HEADING if f.get("init_heading") else 0) | (_lib.TRAJ_HEADING_INVERSION if f.get("heading_inversion") else 0)
+             | (_lib.TRAJ_SLOW if f.get("slow") else 0))
+    for k in ("fixed_path", "pred_path", "add_noise"):
+        if f.get(k):
+            raise ValueError(f"run.py flag --{k} is not implemented by the device-side trajectory reset")
+    rollout["traj_flags"] = flags
+    return dict(net=net, rollout=rollout, sim=sim, traj=traj, num_envs=int(env["numEnvs"]))

@@ -34,14 +34,14 @@ class Rollout:
                  step_to_pred=144, normalize_value=True, net=None, obs_norm=None, amp_norm=None, value_norm=None,
                  recompute_disc=True, valuenet=None, fuse_sinks=True, concurrent=True, reuse_values=False, traj_flags=None,
                  traj_pool=None, traj_deferred=None, finetune=False, value_lr=1e-3,
-                 min_cum_rewards=-10.0, max_cum_rewards=100.0):
+                 min_cum_rewards=-10.0, max_cum_rewards=100.0, sim_cfg=None, traj_cfg=None):
         self.N, self.T, self.device = int(num_envs), int(horizon), int(device)
         self.gamma, self.tau = gamma, tau
         self.task_reward_w, self.disc_reward_w, self.disc_reward_scale = task_reward_w, disc_reward_w, disc_reward_scale
         self.recompute_disc = recompute_disc
         dev = torch.device("cuda", device)
         torch.cuda.set_device(dev)
-        self.sim = EmlocoSim(self.N, device=device)
+        self.sim = EmlocoSim(self.N, device=device, **(sim_cfg or {}))      # sim_cfg: emloco_cfg overrides (formats.kwargs_from_reference_cfg)
         if net is None:
             torch.manual_seed(seed)
             net = AMPSeptValueNetwork()
@@ -93,7 +93,7 @@ class Rollout:
             # with parallel branches the stage is deferred: it overlaps the policy pass (nothing before post_step reads it)
             self._traj_deferred = bool(concurrent) if traj_deferred is None else (bool(traj_deferred) and bool(concurrent))
             self.sim.set_traj_reset(self.sim.traj_cfg(flags=traj_flags | (_lib.TRAJ_DEFERRED if self._traj_deferred else 0), seed=seed, pool=self.traj_pool, waypoint_traj=self.waypoint_traj,
-                                                      init_pose=self.init_pose, init_vel=self.init_vel, inverted=self.inverted))
+                                                      init_pose=self.init_pose, init_vel=self.init_vel, inverted=self.inverted, **(traj_cfg or {})))
         if valuenet is None:
             from .value_pose_net import ValuePoseNet
             valuenet = ValuePoseNet(True, True, mutate_pose=False)

@@ -73,3 +73,50 @@ def test_filter_modes_matches_reference_loop():
         if not filt:
             filt = [int(np.argmax(v[s]))]
         assert sorted(np.nonzero(keep[s])[0].tolist()) == filt
+
+
+def test_reference_yaml_maps_onto_our_defaults():
+    """kwargs_from_reference_cfg on the reference's own YAML files (when the tree is present; an excerpt otherwise): the
+    constants this package hard-codes as defaults ARE the reference's configuration (pacer.yaml,
+    train/rlg/amp_humanoid_smpl_sept_task.yaml)."""
+    import inspect
+    import os
+    from emloco_b200 import _lib
+    from emloco_b200.formats import kwargs_from_reference_cfg
+    from emloco_b200.policy import AMPSeptValueNetwork
+    from emloco_b200.rollout import Rollout
+    root = "/root/reference/pacer/pacer/data/cfg"
+    if os.path.isdir(root):
+        import yaml
+        env_cfg = yaml.safe_load(open(os.path.join(root, "pacer.yaml")))
+        train_cfg = yaml.safe_load(open(os.path.join(root, "train/rlg/amp_humanoid_smpl_sept_task.yaml")))
+    else:
+        env_cfg = {"env": dict(numEnvs=1600, episodeLength=168, controlFrequencyInv=2, power_coefficient=0.0005, location_coefficient=1,
+                               trajSampleTimestep=0.4, stepToPred=144, speedMin=0.0005, speedMax=3.0, accelMax=2.0, sharpTurnProb=0.02,
+                               hybridInitProb=0.5, numAMPObsSteps=15, numTrajSamples=15, pdControl=True,
+                               terrain=dict(staticFriction=1.0))}
+        train_cfg = {"params": dict(
+            network=dict(space=dict(continuous=dict(sigma_init=dict(val=-2.9), fixed_sigma=True, learn_sigma=False)),
+                         mlp=dict(units=[2048, 1024]), task_mlp=dict(units=[512, 256]), value_mlp=dict(units=[15, 6]),
+                         disc=dict(units=[1024, 512])),
+            config=dict(horizon_length=32, gamma=0.99, tau=0.95, task_reward_w=0.5, disc_reward_w=0.5, disc_reward_scale=2,
+                        inversion_penalty_scale=0.3, normalize_value=True, player=dict(finetune=True)))}
+    k = kwargs_from_reference_cfg(env_cfg, train_cfg, dict(real_path=True, adjust_root_vel=True, init_heading=True))
+    # network: the defaults of AMPSeptValueNetwork
+    sig = inspect.signature(AMPSeptValueNetwork.__init__).parameters
+    for name, v in k["net"].items():
+        assert sig[name].default == v, (name, sig[name].default, v)
+    # rollout: the defaults of Rollout
+    sig = inspect.signature(Rollout.__init__).parameters
+    for name in ("horizon", "gamma", "tau", "task_reward_w", "disc_reward_w", "disc_reward_scale", "inversion_penalty_scale",
+                 "step_to_pred", "normalize_value"):
+        assert sig[name].default == k["rollout"][name], (name, sig[name].default, k["rollout"][name])
+    assert k["rollout"]["finetune"] is True and k["rollout"]["traj_flags"] == 1 | 2 | 4
+    # sim: emloco_default_cfg
+    d = _lib.default_cfg()
+    for name, v in k["sim"].items():
+        assert abs(getattr(d, name) - v) < 1e-7, (name, getattr(d, name), v)
+    # trajectory generator: the defaults of EmlocoSim.traj_cfg (pacer.yaml:45,55-61)
+    assert k["traj"] == dict(speed_min=0.0005, speed_max=3.0, accel_max=2.0, sharp_turn_prob=0.02, hybrid_init_prob=0.5)
+    with __import__("pytest").raises(ValueError):
+        kwargs_from_reference_cfg(env_cfg, train_cfg, dict(pred_path=True))
