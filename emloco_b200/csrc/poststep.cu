@@ -156,6 +156,9 @@ __global__ void __launch_bounds__(PS_THREADS) post_step_kernel(PostParams P) {
             f3 lw = quat_rotate(hinv, mk3(b[10], b[11], b[12]));
             float* ov = s_obs + 213 + lane * 3; ov[0] = lv.x; ov[1] = lv.y; ov[2] = lv.z;
             float* ow = s_obs + 285 + lane * 3; ow[0] = lw.x; ow[1] = lw.y; ow[2] = lw.z;
+            // (the compiler widens the 6-float copy below to aligned 128-bit loads that also touch neighbouring lanes' elements:
+            //  order them after those lanes' stores so that racecheck stays clean)
+            __syncwarp(0x00ffffffu);
             if (lane == 0) {   // AMP root block reuses the same quantities (humanoid_amp.py:924-938)
                 for (int k = 0; k < 6; ++k) s_amp[k] = s_obs[69 + k];
                 s_amp[6] = lv.x; s_amp[7] = lv.y; s_amp[8] = lv.z;
