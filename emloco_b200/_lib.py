@@ -47,7 +47,8 @@ class PostSinks(C.Structure):
                 ("self_hi", C.c_void_p), ("self_lo", C.c_void_p), ("ld_self", C.c_int64),
                 ("task_hi", C.c_void_p), ("task_lo", C.c_void_p), ("ld_task", C.c_int64),
                 ("amp_mean", C.c_void_p), ("amp_inv_std", C.c_void_p),
-                ("amp_hi", C.c_void_p), ("amp_lo", C.c_void_p), ("ld_amp", C.c_int64)]
+                ("amp_hi", C.c_void_p), ("amp_lo", C.c_void_p), ("ld_amp", C.c_int64),
+                ("rows_only", C.c_int32), ("reserved", C.c_int32)]
 
 
 class TrajCfg(C.Structure):

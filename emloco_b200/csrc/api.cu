@@ -1,4 +1,5 @@
 // C ABI of libemloco_b200.so (see include/emloco.h for the reference interface each entry replaces).
+#include <vector>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -111,7 +112,12 @@ int emloco_create(const emloco_cfg* cfg, const emloco_model* model, emloco_sim**
     ALLOC(s->obs, N * EML_OBS, float); ALLOC(s->flip_obs, N * EML_OBS, float); ALLOC(s->rew, N, float); ALLOC(s->rew_raw, N * 2, float);
     ALLOC(s->reset, N, int64_t); ALLOC(s->terminate, N, int64_t); ALLOC(s->progress, N, int64_t);
     ALLOC(s->amp_obs, N * EML_AMP_OBS, float); ALLOC(s->verts, N * EML_NUM_VERTS * 3, float); ALLOC(s->betas, N * 17, float);
-    ALLOC(s->traj_epoch, N, uint32_t);
+    ALLOC(s->traj_epoch, N, uint32_t); ALLOC(s->ring_ptr, N, const float*);
+    {
+        std::vector<const float*> h(N);
+        for (size_t i = 0; i < N; ++i) h[i] = s->amp_obs + i * EML_AMP_OBS;
+        CK(cudaMemcpy(s->ring_ptr, h.data(), N * sizeof(const float*), cudaMemcpyHostToDevice), "init ring_ptr");
+    }
     // default terrain: flat 1080 x 1080 (8 m map + 50 m border at 0.1 m, humanoid_pedestrain_terrain.py:1142-1165)
     s->hf_rows = 1080; s->hf_cols = 1080;
     ALLOC(s->height, (size_t)s->hf_rows * s->hf_cols, int16_t);
@@ -137,7 +143,7 @@ int emloco_destroy(emloco_sim* s) {
     cudaSetDevice(s->device);
     void* ptrs[] = {s->root_state, s->dof_state, s->rb_state, s->contact, s->dof_force, s->pd_target, s->joint_quat, s->actions,
                     s->obs, s->flip_obs, s->rew, s->rew_raw, s->reset, s->terminate, s->progress, s->amp_obs, s->verts, s->betas,
-                    s->height, s->traj_epoch};
+                    s->height, s->traj_epoch, (void*)s->ring_ptr};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (s->h_pin) cudaFreeHost(s->h_pin);
     free(s);

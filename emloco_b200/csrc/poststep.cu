@@ -31,6 +31,8 @@ struct PostParams {
     const float* verts; const float* betas; const int16_t* height; int hf_rows, hf_cols;
     int64_t* progress; float* obs; float* flip_obs; float* rew; float* rew_raw;
     int64_t* reset; int64_t* terminate; float* amp;
+    const float** ring_ptr; // [N] where each env's AMP ring currently lives: its row of `amp`, or of the experience row that the
+                            // last post-step wrote when the rows_only sink mode is on (see emloco_post_sinks)
     int N; int advance; int reset_mode; float dt; float traj_dur; float sample_dt; int max_len;
     float power_coef, loc_coef, fail_dist2;
     emloco_post_sinks k;   // optional extra outputs (experience rows, normalised bf16 hi/lo operands of the nets)
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(PS_THREADS) post_step_kernel(PostParams P) {
     // AMP history: hist[k+1] = old[k] (humanoid_amp.py:585-594); read now, store after the last barrier
     float2 hist[12];
     {
-        const float2* a = reinterpret_cast<const float2*>(P.amp + (size_t)env * EML_AMP_OBS);
+        const float2* a = reinterpret_cast<const float2*>(rmode ? P.amp + (size_t)env * EML_AMP_OBS : P.ring_ptr[env]);
 #pragma unroll
         for (int k = 0; k < 12; ++k) {
             int i = tid + PS_THREADS * k;
@@ -250,8 +252,9 @@ __global__ void __launch_bounds__(PS_THREADS) post_step_kernel(PostParams P) {
     // ---- stream out: obs, mirrored obs, AMP ring ----
     {
         float2* o = reinterpret_cast<float2*>(P.obs + (size_t)env * EML_OBS);
-        float2* f = reinterpret_cast<float2*>(P.flip_obs + (size_t)env * EML_OBS);
         float2* fc = (P.k.flip_copy && !rmode) ? reinterpret_cast<float2*>(P.k.flip_copy + (size_t)env * EML_OBS) : nullptr;
+        // rows_only: the experience rows are the only destination of the mirrored observation and of the AMP ring
+        float2* f = (fc && P.k.rows_only) ? nullptr : reinterpret_cast<float2*>(P.flip_obs + (size_t)env * EML_OBS);
         // The table entries and normalisation statistics are the same for every env: their (L1/L2) loads are issued for all
         // of a thread's elements first, so that the stores below never wait on a load issued one instruction earlier
         constexpr int OB_IT = (EML_OBS / 2 + PS_THREADS - 1) / PS_THREADS;            // 6
@@ -272,7 +275,7 @@ __global__ void __launch_bounds__(PS_THREADS) post_step_kernel(PostParams P) {
                     if (oc) oc[i2] = v;                                    // experience row of the same observation
                     const float r0 = s_obs[e[k] & 0x7fffu], r1 = s_obs[(e[k] >> 16) & 0x7fffu];
                     const float2 fv = make_float2((e[k] & 0x8000u) ? -r0 : r0, (e[k] & 0x80000000u) ? -r1 : r1);
-                    f[i2] = fv;
+                    if (f) f[i2] = fv;
                     if (fc) fc[i2] = fv;
                 }
             }
@@ -308,10 +311,19 @@ __global__ void __launch_bounds__(PS_THREADS) post_step_kernel(PostParams P) {
         float2* a = reinterpret_cast<float2*>(P.amp + (size_t)env * EML_AMP_OBS);
         if (rmode) {
             for (int i = tid; i < 15 * 103; i += PS_THREADS) a[i] = reinterpret_cast<const float2*>(s_amp)[i % 103];
-            if (tid == 0 && P.reset_mode == 1) { P.reset[env] = 0; P.terminate[env] = 0; }
+            if (tid == 0) {
+                P.ring_ptr[env] = P.amp + (size_t)env * EML_AMP_OBS;
+                if (P.reset_mode == 1) { P.reset[env] = 0; P.terminate[env] = 0; }
+            }
             return;
         }
         float2* ac = P.k.amp_copy ? reinterpret_cast<float2*>(P.k.amp_copy + (size_t)env * EML_AMP_OBS) : nullptr;
+        if (ac && P.k.rows_only) {                 // the next step finds the ring in this step's experience row
+            a = nullptr;
+            if (tid == 0) P.ring_ptr[env] = P.k.amp_copy + (size_t)env * EML_AMP_OBS;
+        } else if (tid == 0) {
+            P.ring_ptr[env] = P.amp + (size_t)env * EML_AMP_OBS;
+        }
         uint32_t* ah = P.k.amp_hi ? reinterpret_cast<uint32_t*>(P.k.amp_hi + (size_t)env * P.k.ld_amp) : nullptr;
         uint32_t* al = P.k.amp_hi ? reinterpret_cast<uint32_t*>(P.k.amp_lo + (size_t)env * P.k.ld_amp) : nullptr;
         // statistics for the thread's 12 ring elements, fetched in groups of 4 ahead of their use
@@ -332,7 +344,7 @@ __global__ void __launch_bounds__(PS_THREADS) post_step_kernel(PostParams P) {
             for (int j = 0; j < 4; ++j) {
                 const int k = 4 * g + j, i = tid + PS_THREADS * k;
                 if (i < 14 * 103) {
-                    a[103 + i] = hist[k];
+                    if (a) a[103 + i] = hist[k];
                     if (ac) ac[103 + i] = hist[k];
                     if (ah) { uint32_t hi, lo; norm_split2(hist[k].x, hist[k].y, m[j], is[j], hi, lo); ah[103 + i] = hi; al[103 + i] = lo; }
                 }
@@ -340,7 +352,7 @@ __global__ void __launch_bounds__(PS_THREADS) post_step_kernel(PostParams P) {
         }
         if (tid < 103) {
             const float2 v = reinterpret_cast<const float2*>(s_amp)[tid];
-            a[tid] = v;
+            if (a) a[tid] = v;
             if (ac) ac[tid] = v;
             if (ah) {
                 uint32_t hi, lo;
@@ -391,7 +403,7 @@ static cudaError_t launch_post(emloco_sim* s, int advance_progress, int reset_mo
     P.rb = s->rb_state; P.dof = s->dof_state; P.contact = s->contact; P.dof_force = s->dof_force;
     P.verts = s->verts; P.betas = s->betas; P.height = s->height; P.hf_rows = s->hf_rows; P.hf_cols = s->hf_cols;
     P.progress = s->progress; P.obs = s->obs; P.flip_obs = s->flip_obs; P.rew = s->rew; P.rew_raw = s->rew_raw;
-    P.reset = s->reset; P.terminate = s->terminate; P.amp = s->amp_obs;
+    P.reset = s->reset; P.terminate = s->terminate; P.amp = s->amp_obs; P.ring_ptr = s->ring_ptr;
     P.N = s->N; P.advance = advance_progress; P.reset_mode = reset_mode; P.k = s->sinks;
     double dt = (double)s->cfg.control_freq_inv * (double)s->cfg.sim_dt;          // humanoid.py:89
     P.dt = (float)dt;

@@ -59,6 +59,7 @@ struct emloco_sim {
     size_t   h_pin_bytes;
     cudaStream_t copy_stream;
     emloco_post_sinks sinks;   // optional extra outputs of the post-step kernel (all NULL by default)
+    const float** ring_ptr;    // [N] where each env's AMP ring currently lives (its amp_obs row or an experience row)
     uint32_t* traj_epoch;      // [N] per-env count of device-side trajectory resets (Philox counter word)
     emloco_traj_cfg traj;      // stage appended to emloco_reset_done when traj_on
     int traj_on;

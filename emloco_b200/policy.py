@@ -155,9 +155,11 @@ class RolloutNets:
                              torch.cat([ps[1].detach(), ps[3].detach()]).contiguous())
         return self._stacked[1], self._stacked[2]
 
-    def post_sinks(self, obs_copy=None, amp_copy=None, slot=0, flip_copy=None):
-        """emloco_post_sinks pointing at this object's operand buffers (tensor-core path) plus the given experience rows."""
+    def post_sinks(self, obs_copy=None, amp_copy=None, slot=0, flip_copy=None, rows_only=False):
+        """emloco_post_sinks pointing at this object's operand buffers (tensor-core path) plus the given experience rows.
+        rows_only: sim.flip_obs / sim.amp_obs are not refreshed, the experience rows are the only copies."""
         k = _lib.PostSinks()
+        k.rows_only = int(bool(rows_only))
         k.obs_copy = None if obs_copy is None else obs_copy.data_ptr()
         k.amp_copy = None if amp_copy is None else amp_copy.data_ptr()
         k.flip_copy = None if flip_copy is None else flip_copy.data_ptr()

@@ -34,7 +34,7 @@ class Rollout:
                  step_to_pred=144, normalize_value=True, net=None, obs_norm=None, amp_norm=None, value_norm=None,
                  recompute_disc=True, valuenet=None, fuse_sinks=True, concurrent=True, reuse_values=False, traj_flags=None,
                  traj_pool=None, traj_deferred=None, finetune=False, value_lr=1e-3,
-                 min_cum_rewards=-10.0, max_cum_rewards=100.0, sim_cfg=None, traj_cfg=None):
+                 min_cum_rewards=-10.0, max_cum_rewards=100.0, sim_cfg=None, traj_cfg=None, rows_only=True):
         self.N, self.T, self.device = int(num_envs), int(horizon), int(device)
         self.gamma, self.tau = gamma, tau
         self.task_reward_w, self.disc_reward_w, self.disc_reward_scale = task_reward_w, disc_reward_w, disc_reward_scale
@@ -71,6 +71,7 @@ class Rollout:
         # fuse_sinks: the post-step / reset kernels write the experience rows and the normalised bf16 operands of the first
         # layers themselves (emloco_set_post_sinks) instead of separate copy / split launches
         self.fuse = bool(fuse_sinks)
+        self.rows_only = bool(rows_only)
         self.sim.reset.fill_(1)
         if self.fuse:
             self.sim.set_post_sinks(self.nets.post_sinks(obs_copy=self.mb["obses"][T]))
@@ -193,8 +194,10 @@ class Rollout:
 
         def seg_post():                                                                #           post_physics_step
             if fuse:
+                # rows_only: the mirrored observation and the AMP ring are written once, into the experience rows (the ring of
+                # the next step is shifted out of row n); sim.flip_obs / sim.amp_obs stay stale while the rollout runs fused
                 sim.set_post_sinks(nets.post_sinks(obs_copy=mb["obses"][nxt], amp_copy=mb["amp_obs"][n], slot=slot,
-                                                   flip_copy=mb["flip_obs"][n]))
+                                                   flip_copy=mb["flip_obs"][n], rows_only=self.rows_only))
                 sim.post_step(True)
             else:
                 sim.post_step(True)
@@ -213,7 +216,7 @@ class Rollout:
                 cur["nv"] = nets.critic(sim.obs, operands_ready=fuse)
 
         def seg_disc():                                                                # _calc_amp_rewards, :93
-            cur["logit"] = nets.disc_logits(sim.amp_obs.view(self.N, AMP_OBS), operands_ready=fuse, slot=slot)
+            cur["logit"] = nets.disc_logits(mb["amp_obs"][n] if fuse else sim.amp_obs.view(self.N, AMP_OBS), operands_ready=fuse, slot=slot)
 
         inv = None if self.inverted is None else _ptr(self.inverted)      # task.inverted -> inversion penalty (:78-83)
 

@@ -143,6 +143,12 @@ typedef struct emloco_post_sinks {
     uint16_t* task_hi; uint16_t* task_lo; int64_t ld_task;
     const float* amp_mean; const float* amp_inv_std;
     uint16_t* amp_hi; uint16_t* amp_lo; int64_t ld_amp;
+    /* rows_only != 0: the experience rows are the ONLY destination of the mirrored observation (flip_copy) and of the AMP
+     * ring (amp_copy) - EMLOCO_T_FLIP_OBS / EMLOCO_T_AMP_OBS are then not refreshed by emloco_post_step (73 MB less written
+     * per 4096-env step).  The sim remembers, per env, which row holds its ring (the amp_copy row of its last post-step, or
+     * its EMLOCO_T_AMP_OBS row after a reset) and shifts from there: that row must stay intact until the env's next
+     * emloco_post_step. */
+    int32_t   rows_only; int32_t reserved;
 } emloco_post_sinks;
 int emloco_set_post_sinks(emloco_sim* sim, const emloco_post_sinks* sinks /* NULL clears */);
 

@@ -390,7 +390,9 @@ def test_64_envs_100_steps_lockstep_with_cpu_oracle():
         cpu.jw = f64(sim.dof_state).reshape(n, 69, 2)[..., 1].copy()
         cpu.progress = sim.progress.cpu().numpy().copy(); cpu.reset = sim.reset.cpu().numpy().copy()
         cpu.terminate = sim.terminate.cpu().numpy().copy()
-        cpu.amp_buf = sim.amp_obs.cpu().numpy().reshape(n, 15, 206).copy()
+        # the ring lives in the experience row of the previous step (rows_only sinks); after the initial reset in sim.amp_obs
+        ring = sim.amp_obs if k == 0 else gpu.mb["amp_obs"][(k - 1) % T]
+        cpu.amp_buf = ring.cpu().numpy().reshape(n, 15, 206).copy()
         cpu.contact = f64(sim.contact).reshape(n, 24, 3).copy(); cpu.dof_force = f64(sim.dof_force).reshape(n, 69).copy()
         cpu.obs = sim.obs.cpu().numpy().copy()
         cpu.state = gpu.state.cpu().numpy().copy()
@@ -524,3 +526,39 @@ def test_gym_shim_env_creation_sequence():
     np.testing.assert_allclose(rb.cpu().numpy(), ref.rb_state.cpu().numpy(), rtol=1e-4, atol=1e-5)
     assert gym.get_frame_count(sim) == 10 and gym.get_sim_params(sim).substeps == 2
     gym.destroy_sim(sim); ref.close()
+
+
+def test_rows_only_sinks_give_the_same_experience():
+    """rows_only (mirrored observation and AMP ring written once, into the experience rows; each env's ring is shifted out of
+    the row its last post-step wrote, or out of sim.amp_obs after a reset) against the mode that also refreshes
+    sim.flip_obs / sim.amp_obs: bit-identical experience over two horizons with resets, in a non-consecutive slot order too."""
+    from emloco_b200.policy import AMPSeptValueNetwork
+    from emloco_b200.rollout import Rollout
+    n, T = 96, 6
+    torch.manual_seed(2)
+    net = AMPSeptValueNetwork()
+    outs = []
+    for ro in (True, False):
+        R = Rollout(n, seed=9, net=net, tensor_cores=True, horizon=T, rows_only=ro)
+        R.sim.progress[: n // 2] = 163                     # time-outs inside the first horizon
+        g = torch.Generator(device="cuda").manual_seed(5)
+        rows = []
+        for rep in range(2):
+            for k in range(T):
+                R.step(k, noise=torch.randn(n, 69, device="cuda", generator=g))
+            o = R.finish()
+            torch.cuda.synchronize()
+            rows.append({k_: o[k_].cpu().numpy().copy() for k_ in ("amp_obs", "flip_obs", "obses", "amp_rewards", "rewards", "dones", "returns")})
+        # slots out of order (what bench.py's 8-slot segment loop does): 0, 1, 0, 1 ...
+        for k in (0, 1, 0, 1, 2):
+            R.step(k, noise=torch.randn(n, 69, device="cuda", generator=g))
+        torch.cuda.synchronize()
+        rows.append({"amp_obs": R.mb["amp_obs"][:3].cpu().numpy().copy(), "flip_obs": R.mb["flip_obs"][:3].cpu().numpy().copy()})
+        if not ro:
+            np.testing.assert_array_equal(R.sim.amp_obs.view(n, -1).cpu().numpy(), R.mb["amp_obs"][2].cpu().numpy())
+        outs.append(rows)
+        R.close()
+    assert outs[0][0]["dones"].sum() >= n // 2
+    for a, b in zip(*outs):
+        for k_ in a:
+            np.testing.assert_array_equal(a[k_], b[k_], err_msg=k_)
