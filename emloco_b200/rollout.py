@@ -167,15 +167,28 @@ class Rollout:
             else:
                 reset_main(); draw_noise()
 
+        # with parallel branches the state / forward-kinematics half of the reset already ran beside the networks of the previous
+        # step (fk_next below): only the observation half is left on the critical path
+        split_reset = self.concurrent
+
+        def reset_envs():
+            if split_reset:
+                sim.reset_done_stage(self.init_root, self.init_dof, 2)
+            else:
+                sim.reset_done(self.init_root, self.init_dof)
+
+        def fk_next():
+            sim.reset_done_stage(self.init_root, self.init_dof, 1)
+
         def reset_main():
             if fuse_in:
                 if n == 0:
                     mb["obses"][0].copy_(mb["obses"][self.T])                          # observation that followed the last horizon
                 sim.set_post_sinks(nets.post_sinks(obs_copy=mb["obses"][n]))           # reset rows are patched in place
-                sim.reset_done(self.init_root, self.init_dof)
+                reset_envs()
             else:
                 sim.set_post_sinks(None)
-                sim.reset_done(self.init_root, self.init_dof)
+                reset_envs()
                 mb["obses"][n].copy_(sim.obs)
 
         def seg_policy():                                                              # get_action_values, :53
@@ -251,7 +264,7 @@ class Rollout:
             self.locoval_scores = self.valuenet(self.waypoint_traj, self.init_pose, self.init_vel)
 
         def seg_nets2():   # critic(next obs), discriminator and LocoVal scoring are independent: three graph branches
-            nets.fork.run(seg_critic, seg_disc, seg_locoval)
+            nets.fork.run(seg_critic, seg_disc, seg_locoval, fk_next)
 
         def seg_record_ft():
             seg_record()
