@@ -370,14 +370,7 @@ int emloco_linear(const float* d_x, int64_t ldx, const float* d_w, const float* 
 
 int emloco_reset_done(emloco_sim* s, const float* d_init_root, const float* d_init_dof, void* stream) {
     if (!s || !d_init_root || !d_init_dof) return fail(EMLOCO_EINVAL, "emloco_reset_done: null argument");
-    CK(eml_reset_done(s, d_init_root, d_init_dof, 0, (cudaStream_t)stream), "reset-done kernels");
-    return EMLOCO_OK;
-}
-
-int emloco_reset_done_stage(emloco_sim* s, const float* d_init_root, const float* d_init_dof, int32_t stage, void* stream) {
-    if (!s || (stage != 2 && (!d_init_root || !d_init_dof))) return fail(EMLOCO_EINVAL, "emloco_reset_done_stage: null argument");
-    if (stage < 0 || stage > 2) return fail(EMLOCO_EINVAL, "emloco_reset_done_stage: stage must be 0, 1 or 2");
-    CK(eml_reset_done(s, d_init_root, d_init_dof, stage, (cudaStream_t)stream), "reset-done kernels");
+    CK(eml_reset_done(s, d_init_root, d_init_dof, (cudaStream_t)stream), "reset-done kernels");
     return EMLOCO_OK;
 }
 

@@ -407,17 +407,14 @@ cudaError_t eml_launch_fk(emloco_sim* s, const int32_t* d_env_ids, int n, cudaSt
 
 // Device-side reset of the envs whose reset flag is set (env_reset(done_indices) of play_steps,
 // amp_continuous_value.py:45 -> humanoid.py:455-481 with a fixed synthetic initial state): no host round trip.
-cudaError_t eml_reset_done(emloco_sim* s, const float* d_init_root, const float* d_init_dof, int stage, cudaStream_t st) {
-    // stage 0: everything; 1: state + forward kinematics only; 2: observations / AMP history (+ trajectory stage) only
-    if (stage != 2) {
-        PhysParams P; fill_params(s, P);
-        P.fk_only = 1; P.reset_mask = s->reset; P.init_root = d_init_root; P.init_dof = d_init_dof;
-        int blocks = (P.N + PH_WARPS - 1) / PH_WARPS;
-        physics_kernel<<<blocks, PH_WARPS * 32, 0, st>>>(P);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess || stage == 1) return e;
-    }
-    cudaError_t e = eml_launch_post_reset(s, s->traj_on, st);
+cudaError_t eml_reset_done(emloco_sim* s, const float* d_init_root, const float* d_init_dof, cudaStream_t st) {
+    PhysParams P; fill_params(s, P);
+    P.fk_only = 1; P.reset_mask = s->reset; P.init_root = d_init_root; P.init_dof = d_init_dof;
+    int blocks = (P.N + PH_WARPS - 1) / PH_WARPS;
+    physics_kernel<<<blocks, PH_WARPS * 32, 0, st>>>(P);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    e = eml_launch_post_reset(s, s->traj_on, st);
     if (e != cudaSuccess || s->traj_on != 1) return e;   // 2 = deferred: the caller runs the stage (emloco_traj_reset(sim, NULL))
     return eml_traj_reset(s, s->traj, 1, st);       // _reset_task runs after the observations (humanoid_amp_task.py:54-57)
 }

@@ -93,7 +93,7 @@ cudaError_t eml_upload_model(const EmlModelDev* m);
 cudaError_t eml_launch_post_step(emloco_sim* s, int advance_progress, cudaStream_t st);
 cudaError_t eml_launch_physics(emloco_sim* s, const float* d_actions, int n_substeps, int fuse_post, cudaStream_t st);
 cudaError_t eml_launch_fk(emloco_sim* s, const int32_t* d_env_ids, int n, cudaStream_t st);
-cudaError_t eml_reset_done(emloco_sim* s, const float* d_init_root, const float* d_init_dof, int stage, cudaStream_t st);
+cudaError_t eml_reset_done(emloco_sim* s, const float* d_init_root, const float* d_init_dof, cudaStream_t st);
 cudaError_t eml_launch_post_reset(emloco_sim* s, int keep_flags, cudaStream_t st);
 cudaError_t eml_traj_reset(emloco_sim* s, const emloco_traj_cfg& c, int clear_flags, cudaStream_t st);
 cudaError_t eml_sample_actions(const float* mu, long long ldmu, const float* logstd, const float* noise, float* actions,

@@ -167,28 +167,15 @@ class Rollout:
             else:
                 reset_main(); draw_noise()
 
-        # with parallel branches the state / forward-kinematics half of the reset already ran beside the networks of the previous
-        # step (fk_next below): only the observation half is left on the critical path
-        split_reset = self.concurrent
-
-        def reset_envs():
-            if split_reset:
-                sim.reset_done_stage(self.init_root, self.init_dof, 2)
-            else:
-                sim.reset_done(self.init_root, self.init_dof)
-
-        def fk_next():
-            sim.reset_done_stage(self.init_root, self.init_dof, 1)
-
         def reset_main():
             if fuse_in:
                 if n == 0:
                     mb["obses"][0].copy_(mb["obses"][self.T])                          # observation that followed the last horizon
                 sim.set_post_sinks(nets.post_sinks(obs_copy=mb["obses"][n]))           # reset rows are patched in place
-                reset_envs()
+                sim.reset_done(self.init_root, self.init_dof)
             else:
                 sim.set_post_sinks(None)
-                reset_envs()
+                sim.reset_done(self.init_root, self.init_dof)
                 mb["obses"][n].copy_(sim.obs)
 
         def seg_policy():                                                              # get_action_values, :53
@@ -264,7 +251,7 @@ class Rollout:
             self.locoval_scores = self.valuenet(self.waypoint_traj, self.init_pose, self.init_vel)
 
         def seg_nets2():   # critic(next obs), discriminator and LocoVal scoring are independent: three graph branches
-            nets.fork.run(seg_critic, seg_disc, seg_locoval, fk_next)
+            nets.fork.run(seg_critic, seg_disc, seg_locoval)
 
         def seg_record_ft():
             seg_record()

@@ -117,11 +117,6 @@ class EmlocoSim:
         _lib.check(self.lib.emloco_reset_done(self._h, _ptr(init_root), _ptr(init_dof), _stream()), "emloco_reset_done")
         _lib.launch_count += int(self._traj_on == 1)  # the appended trajectory-reset stage
 
-    def reset_done_stage(self, init_root, init_dof, stage):
-        """reset_done in two halves (emloco_reset_done_stage): 1 = state + forward kinematics, 2 = observations / AMP history."""
-        _lib.check(self.lib.emloco_reset_done_stage(self._h, _ptr(init_root), _ptr(init_dof), int(stage), _stream()), "emloco_reset_done_stage")
-        _lib.launch_count += int(stage == 2 and self._traj_on == 1)
-
     def traj_cfg(self, flags=0, seed=0, pool=None, uniform=None, waypoint_traj=None, init_pose=None, init_vel=None,
                  inverted=None, origin_relative=True, **over):
         """emloco_traj_cfg with the pacer.yaml defaults (TrajGenerator args, humanoid_traj.py:113-119).  Tensors are CUDA,

@@ -175,11 +175,6 @@ int emloco_step_host(emloco_sim* sim, const float* h_actions, float* h_obs, floa
  * reset/terminate cleared, contact forces zeroed, observations recomputed, AMP history filled with the current step
  * (_init_amp_obs_default).  The mocap-sampled initial state of _reset_ref_state_init is the caller's to put in d_init_*. */
 int emloco_reset_done(emloco_sim* sim, const float* d_init_root, const float* d_init_dof, void* stream);
-/* The same in two halves, so that a caller can overlap the first with other work: stage 1 = root / DOF state from d_init_* +
- * forward kinematics + contact / DOF force zeroed (touches no observation buffer: it may run while the networks still read
- * the observations of the step that just ended); stage 2 = observations, AMP history, progress / flags (+ the trajectory
- * stage); stage 0 = both (emloco_reset_done).  Both halves act on the envs whose reset_buf is set. */
-int emloco_reset_done_stage(emloco_sim* sim, const float* d_init_root, const float* d_init_dof, int32_t stage, void* stream);
 
 /* Device-side `_reset_task` for the envs that reset: TrajGenerator.reset
  * (pacer/pacer/env/util/traj_generator.py:60-237) + the LocoVal inputs captured at reset
