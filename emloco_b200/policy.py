@@ -13,7 +13,6 @@ head runs in this repo's CUDA kernels through the C ABI (``emloco_linear``, ``em
 from __future__ import annotations
 
 import ctypes as C
-import os
 import math
 
 import torch
@@ -133,7 +132,6 @@ class RolloutNets:
         self.actions, self.neglogp = f(M, ACTIONS), f(M)
         self._stacked = None
         self.fork = Fork(dev, priority=-1) if concurrent else None
-        self.split_ac1 = os.environ.get("EMLOCO_SPLIT_AC1", "0") == "1"      # experiment switch, see action_values
         if self.tc:
             S = lambda k: _Split(M, k, dev)
             self.s_tin, self.s_t1, self.s_ain, self.s_ac1 = S(TASK_OBS), S(t1), S(SELF_OBS + t2), S(2 * a1)
@@ -213,22 +211,14 @@ class RolloutNets:
         h = n.actor_mlp[0].out_features
         W = self.w16.get if self.tc else None
 
-        # with parallel branches the first actor / critic layers are two launches (each branch starts its second layer as soon
-        # as its own first layer is done); serially they are one stacked GEMM over the shared input
-        split = self.tc and self.fork is not None and self.split_ac1
-
         def trunk_ac1():
             self._trunk(obs, operands_ready)
-            if split:
-                return
             if self.tc:
                 linear_bf16x3(self.s_ain, W("ac1", w), b, True, y16=self.s_ac1)
             else:
                 linear(self.ain, w, b, relu=True, out=self.ac1)
 
         def actor():
-            if split:
-                linear_bf16x3(self.s_ain, W("a0", n.actor_mlp[0].weight), n.actor_mlp[0].bias.detach(), True, y16=self.s_ac1.cols(0, h))
             if self.tc:
                 linear_bf16x3(self.s_ac1.cols(0, h), W("a2", n.actor_mlp[2].weight), n.actor_mlp[2].bias.detach(), True, y16=self.s_a2)
                 linear_bf16x3(self.s_a2, W("mu", n.mu.weight), n.mu.bias.detach(), False, y32=mu_out)
@@ -238,8 +228,6 @@ class RolloutNets:
             sample_actions(mu_out, n.sigma, noise, actions_out, neglogp_out)
 
         def critic():
-            if split:
-                linear_bf16x3(self.s_ain, W("c0", n.critic_mlp[0].weight), n.critic_mlp[0].bias.detach(), True, y16=self.s_ac1.cols(h, 2 * h))
             if self.tc:
                 linear_bf16x3(self.s_ac1.cols(h, 2 * h), W("c2", n.critic_mlp[2].weight), n.critic_mlp[2].bias.detach(), True,
                               head=(n.value, self.value, self.hp_c))            # value layer fused into the epilogue
