@@ -11,8 +11,10 @@
 //      masks (:141-144), and writes the 100 features as bf16 hi / lo into the K-major 128B-swizzled A tile (written by hand
 //      with the same XOR pattern TMA would apply), then fence.proxy.async
 //   2. thread 0: 7 k-steps x 3 MMAs (M=128, N=64, K=16) -> D1 in TMEM; tcgen05.commit -> mbarrier
-//   3. each thread: tcgen05.ld its D1 row, + b1, ReLU, split, write the A tile of layer 2 (over the consumed A tile of layer 1)
-//   4. thread 0: 4 k-steps x 3 MMAs (N=32) -> D2
+//   3. each thread: tcgen05.ld its D1 row, + b1, ReLU, split, tcgen05.st the A operand of layer 2 into TENSOR memory (lane = row,
+//      one column = two K elements) - the shared-memory A tile is dead after layer 1, so the next tile's rows are staged into it
+//      from here on, under layer 2 and the output layer
+//   4. thread 0: 4 k-steps x 3 MMAs (N=32, A from TMEM) -> D2
 //   5. each thread: tcgen05.ld its D2 row, + b2, ReLU, dot w3, + b3, sigmoid -> value
 // Weights are split and staged once per CTA (W1 64 x 128, W2 32 x 64, zero padded).
 #include <cuda_bf16.h>
@@ -25,7 +27,6 @@ constexpr int K1 = 112;                     // IN padded to the MMA K step (7 x 
 constexpr int N1 = 64, N2 = 32;
 constexpr int A_ATOM = 128 * 128;           // one 128-row x 64-bf16 atom: 16 KB
 constexpr int OFF_A_HI = 0, OFF_A_LO = 2 * A_ATOM;          // layer-1 A: hi atoms 0,1 then lo atoms 0,1 (64 KB)
-constexpr int OFF_A2_HI = 0, OFF_A2_LO = A_ATOM;            // layer-2 A (K = 64: one atom each) reuses the space
 constexpr int W1_ATOM = N1 * 128;           // 8 KB
 constexpr int OFF_W1_HI = 4 * A_ATOM, OFF_W1_LO = OFF_W1_HI + 2 * W1_ATOM;
 constexpr int W2_ATOM = N2 * 128;           // 4 KB
@@ -35,7 +36,8 @@ constexpr int OFF_BAR = OFF_F32 + (64 + 32 + 32 + 4) * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 16 + 1024;             // + alignment slack  (~107 KB: two CTAs per SM)
 constexpr int POSE_PITCH = 19;             // float4 per staged pose row (18 used): 76-float pitch, conflict-free LDS.128
 constexpr int ST_TRAJ = 0, ST_POSE = 20480, ST_VEL = ST_POSE + 128 * POSE_PITCH * 16;   // raw-row staging inside the A-tile bytes (< 64 KB)
-constexpr int TMEM_COLS = 128;              // D1: columns 0..63, D2: columns 64..95
+constexpr int TMEM_COLS = 256;              // D1: columns 0..63, D2: 64..95, layer-2 A operand: hi 96..127, lo 128..159
+constexpr int TM_D2 = 64, TM_A2H = 96, TM_A2L = 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -57,6 +59,16 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {       // K-m
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+// A operand from tensor memory (lane = row, one 32-bit column = two consecutive K elements), B from shared memory
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                   "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
 __device__ __forceinline__ void commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -170,9 +182,8 @@ locoval_tc_kernel(const float* __restrict__ traj, int stride, float* pose_rw, co
             for (int i = (nfl & ~3) + i0; i < nfl; i += 128) dst[i] = src[i];
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
     };
-    if (half == 1 && (long long)blockIdx.x < tiles) stage_tile(blockIdx.x);
+    if (half == 1 && (long long)blockIdx.x < tiles) { stage_tile(blockIdx.x); asm volatile("cp.async.wait_group 0;" ::: "memory"); }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // weight tiles are read by the async proxy (MMA)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -287,57 +298,56 @@ locoval_tc_kernel(const float* __restrict__ traj, int stride, float* pose_rw, co
         }
         mbar_wait(bar, phase); phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- 3. hidden layer 1: + b1, ReLU, split -> layer-2 A tile (K = 64, columns 49..63 zero); 32 columns per thread ----
+        // layer 1 has consumed the A tile: its bytes are free again, and layer 2 takes its A operand from tensor memory, so the
+        // next tile's rows are staged NOW (half 1 issues the copies and waits for them only at the end of the iteration)
+        if (half == 1 && t + gridDim.x < tiles) stage_tile(t + gridDim.x);
+        // ---- 3. hidden layer 1: + b1, ReLU, split -> layer-2 A operand in TMEM (K = 64: 32 columns hi + 32 lo; K 49..63 zero) ----
         {
-            const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(half * 32);
+            const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
             uint32_t r0[32];
-            tmem_ld32(taddr, r0);
+            tmem_ld32(lane_base + (uint32_t)(half * 32), r0);
             tmem_wait(r0);
+            uint32_t h[16], l[16];
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                uint32_t h[4], l[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int jl = ch * 8 + 2 * i, j = half * 32 + jl;
-                    const float a = j < H1 ? fmaxf(__uint_as_float(r0[jl]) + s_b1[j], 0.f) : 0.f;
-                    const float bq = j + 1 < H1 ? fmaxf(__uint_as_float(r0[jl + 1]) + s_b1[j + 1], 0.f) : 0.f;
-                    split2(a, bq, h[i], l[i]);
-                }
-                const uint32_t off = sw128(128, rt, (half * 4 + ch) * 8);
-                *reinterpret_cast<uint4*>(sm + OFF_A2_HI + off) = make_uint4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<uint4*>(sm + OFF_A2_LO + off) = make_uint4(l[0], l[1], l[2], l[3]);
+            for (int i = 0; i < 16; ++i) {
+                const int jl = 2 * i, j = half * 32 + jl;
+                const float a = j < H1 ? fmaxf(__uint_as_float(r0[jl]) + s_b1[j], 0.f) : 0.f;
+                const float bq = j + 1 < H1 ? fmaxf(__uint_as_float(r0[jl + 1]) + s_b1[j + 1], 0.f) : 0.f;
+                split2(a, bq, h[i], l[i]);
             }
+            tmem_st16(lane_base + TM_A2H + (uint32_t)(half * 16), h);
+            tmem_st16(lane_base + TM_A2L + (uint32_t)(half * 16), l);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-        // ---- 4. layer 2 on the tensor core ----
+        // ---- 4. layer 2 on the tensor core (A from TMEM) ----
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const uint32_t ko = (uint32_t)(j * 32);
-                const uint64_t ah = make_desc(sbase + OFF_A2_HI + ko), al = make_desc(sbase + OFF_A2_LO + ko);
                 const uint64_t wh = make_desc(sbase + OFF_W2_HI + ko), wl = make_desc(sbase + OFF_W2_LO + ko);
-                umma(tmem + 64, al, wh, idesc2, j != 0);
-                umma(tmem + 64, ah, wl, idesc2, 1);
-                umma(tmem + 64, ah, wh, idesc2, 1);
+                const uint32_t ah = tmem + TM_A2H + (uint32_t)(j * 8), al = tmem + TM_A2L + (uint32_t)(j * 8);
+                umma_ts(tmem + TM_D2, al, wh, idesc2, j != 0);
+                umma_ts(tmem + TM_D2, ah, wl, idesc2, 1);
+                umma_ts(tmem + TM_D2, ah, wh, idesc2, 1);
             }
             commit(bar);
         }
         mbar_wait(bar, phase); phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- 5. half 0: hidden layer 2, output layer, sigmoid; half 1: the A tile is consumed - stage the next tile ----
+        // ---- 5. half 0: hidden layer 2, output layer, sigmoid; half 1: waits for the staged rows ----
         if (half == 0) {
             uint32_t r[32];
-            tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + 64, r);
+            tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + TM_D2, r);
             tmem_wait(r);
             float z = s_b3[0];
 #pragma unroll
             for (int o = 0; o < H2; ++o) z += s_w3[o] * fmaxf(__uint_as_float(r[o]) + s_b2[o], 0.f);
             if (ok) value[b] = 1.0f / (1.0f + __expf(-z));
-        } else if (t + gridDim.x < tiles) {
-            stage_tile(t + gridDim.x);
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();            // D1 / D2 are free again; the next tile's rows are staged
