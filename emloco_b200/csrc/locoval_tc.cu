@@ -6,17 +6,18 @@
 // bf16x3 tcgen05 MMAs (same split-precision scheme as linear_tc.cu: x = hi + lo, Al*Wh + Ah*Wl + Ah*Wh into fp32 TMEM), which
 // leaves the kernel bound by its 404 B/score of HBM traffic and the per-row feature generation.
 //
-// CTA = 128 rows (row = TMEM lane), two threads per row, persistent over 128-row tiles, two CTAs per SM:
-//   1. each thread reads its row (waypoints, pose, velocity), applies the heading normalisation (:73-103) and the toe / spine
-//      masks (:141-144), and writes the 100 features as bf16 hi / lo into the K-major 128B-swizzled A tile (written by hand
-//      with the same XOR pattern TMA would apply), then fence.proxy.async
-//   2. thread 0: 7 k-steps x 3 MMAs (M=128, N=64, K=16) -> D1 in TMEM; tcgen05.commit -> mbarrier
-//   3. each thread: tcgen05.ld its D1 row, + b1, ReLU, split, tcgen05.st the A operand of layer 2 into TENSOR memory (lane = row,
-//      one column = two K elements) - the shared-memory A tile is dead after layer 1, so the next tile's rows are staged into it
-//      from here on, under layer 2 and the output layer
+// CTA = 128 rows (row = TMEM lane), two threads per row, persistent over 128-row tiles, two CTAs per SM.  Activations never
+// touch shared memory: both layers take their A operand from TENSOR memory (TS-mode tcgen05.mma), shared memory holds only the
+// weights and the staging buffer of the raw rows.
+//   1. each thread reads its half of the staged row (waypoints, pose, velocity), applies the heading normalisation (:73-103)
+//      and the toe / spine masks (:141-144), and tcgen05.st's its 56 features as bf16 hi / lo pairs into its TMEM lane
+//   2. thread 0: 7 k-steps x 3 MMAs (M=128, N=64, K=16, A from TMEM) -> D1; tcgen05.commit -> mbarrier.  The staging buffer
+//      is free from here on: the second half-CTA starts the cp.async copies of the NEXT tile (they land under steps 2-5)
+//   3. each thread: tcgen05.ld half of its D1 row, + b1, ReLU, split, tcgen05.st the A operand of layer 2 (over the dead
+//      layer-1 columns)
 //   4. thread 0: 4 k-steps x 3 MMAs (N=32, A from TMEM) -> D2
-//   5. each thread: tcgen05.ld its D2 row, + b2, ReLU, dot w3, + b3, sigmoid -> value
-// Weights are split and staged once per CTA (W1 64 x 128, W2 32 x 64, zero padded).
+//   5. first half-CTA: tcgen05.ld the D2 row, + b2, ReLU, dot w3, + b3, sigmoid -> value; second half: waits for its copies
+// Weights are split and staged once per CTA (W1 64 x 128, W2 32 x 64, zero padded, K-major, 128B swizzle).
 #include <cuda_bf16.h>
 #include "sim.h"
 
@@ -25,8 +26,7 @@ namespace lvtc {
 constexpr int IN = 100, H1 = 49, H2 = 24;
 constexpr int K1 = 112;                     // IN padded to the MMA K step (7 x 16); the tile itself is two 64-wide swizzle atoms
 constexpr int N1 = 64, N2 = 32;
-constexpr int A_ATOM = 128 * 128;           // one 128-row x 64-bf16 atom: 16 KB
-constexpr int OFF_A_HI = 0, OFF_A_LO = 2 * A_ATOM;          // layer-1 A: hi atoms 0,1 then lo atoms 0,1 (64 KB)
+constexpr int A_ATOM = 128 * 128;           // 16 KB; the first 4 x 16 KB of shared memory are the staging buffer of the raw rows
 constexpr int W1_ATOM = N1 * 128;           // 8 KB
 constexpr int OFF_W1_HI = 4 * A_ATOM, OFF_W1_LO = OFF_W1_HI + 2 * W1_ATOM;
 constexpr int W2_ATOM = N2 * 128;           // 4 KB
@@ -35,9 +35,11 @@ constexpr int OFF_F32 = OFF_W2_LO + W2_ATOM;                // b1[64] b2[32] w3[
 constexpr int OFF_BAR = OFF_F32 + (64 + 32 + 32 + 4) * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 16 + 1024;             // + alignment slack  (~107 KB: two CTAs per SM)
 constexpr int POSE_PITCH = 19;             // float4 per staged pose row (18 used): 76-float pitch, conflict-free LDS.128
-constexpr int ST_TRAJ = 0, ST_POSE = 20480, ST_VEL = ST_POSE + 128 * POSE_PITCH * 16;   // raw-row staging inside the A-tile bytes (< 64 KB)
-constexpr int TMEM_COLS = 256;              // D1: columns 0..63, D2: 64..95, layer-2 A operand: hi 96..127, lo 128..159
-constexpr int TM_D2 = 64, TM_A2H = 96, TM_A2L = 128;
+constexpr int ST_TRAJ = 0, ST_POSE = 20480, ST_VEL = ST_POSE + 128 * POSE_PITCH * 16;   // raw-row staging buffer (< 64 KB)
+// tensor-memory map (columns; lane = row): layer-1 A operand hi 0..55 / lo 64..119 (K = 112 -> 56 columns of two bf16), D1
+// 128..191, D2 192..223; the layer-2 A operand (K = 64 -> 32 columns) reuses the dead layer-1 columns: hi 0..31, lo 64..95
+constexpr int TMEM_COLS = 256;
+constexpr int TM_A1H = 0, TM_A1L = 64, TM_D1 = 128, TM_D2 = 192, TM_A2H = 0, TM_A2L = 64;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -56,10 +58,6 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {       // K-m
     d |= (uint64_t)2 << 61;
     return d;
 }
-__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
-}
 // A operand from tensor memory (lane = row, one 32-bit column = two consecutive K elements), B from shared memory
 __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t acc) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
@@ -69,6 +67,14 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
                  ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
                    "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
 }
 __device__ __forceinline__ void commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -196,9 +202,9 @@ locoval_tc_kernel(const float* __restrict__ traj, int stride, float* pose_rw, co
     for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
         const long long b = t * 128 + rt;
         const bool ok = b < B;
-        // the NEXT tile's rows start moving DRAM -> L2 now; their cp.async staging at the end of this iteration then hits L2
-        if (tid == 128 && t + gridDim.x < tiles) {
-            const long long r0 = (t + gridDim.x) * 128;
+        // the rows of the tile after next start moving DRAM -> L2 now; their cp.async staging one iteration later hits L2
+        if (tid == 128 && t + 2 * (long long)gridDim.x < tiles) {
+            const long long r0 = (t + 2 * (long long)gridDim.x) * 128;
             const unsigned rows = (unsigned)((B - r0) < 128 ? (B - r0) : 128);
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(traj + r0 * 13 * stride), "r"((rows * 13u * (unsigned)stride * 4u) & ~15u) : "memory");
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pose_rw + r0 * 72), "r"(rows * 288u) : "memory");
@@ -268,44 +274,47 @@ locoval_tc_kernel(const float* __restrict__ traj, int stride, float* pose_rw, co
                 for (int k = 44; k < 56; ++k) f[k] = 0.f;
             }
         }
-        __syncthreads();                                                   // everybody has its row: the staging bytes may go
-        // ---- 1c. bf16 hi / lo -> layer-1 A tile (7 chunks of 8 bf16 = 16 bytes per thread, swizzled) ----
+        // ---- 1c. bf16 hi / lo -> layer-1 A operand in tensor memory: 28 columns (56 features) per thread and term ----
+        {
+            uint32_t h[28], l[28];
 #pragma unroll
-        for (int ch = 0; ch < 7; ++ch) {
-            uint32_t h[4], l[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) split2(f[ch * 8 + 2 * i], f[ch * 8 + 2 * i + 1], h[i], l[i]);
-            const uint32_t off = sw128(128, rt, (half * 7 + ch) * 8);
-            *reinterpret_cast<uint4*>(sm + OFF_A_HI + off) = make_uint4(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<uint4*>(sm + OFF_A_LO + off) = make_uint4(l[0], l[1], l[2], l[3]);
+            for (int i = 0; i < 28; ++i) split2(f[2 * i], f[2 * i + 1], h[i], l[i]);
+            const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+            // every store starts at a multiple of its own width: half 0 = 16 + 8 + 4 columns from 0, half 1 = 4 + 16 + 8 from 28
+            const uint32_t ch = lane_base + TM_A1H + (uint32_t)(half * 28), cl = lane_base + TM_A1L + (uint32_t)(half * 28);
+            if (half == 0) {
+                tmem_st16(ch, h); tmem_st8(ch + 16, h + 16); tmem_st4(ch + 24, h + 24);
+                tmem_st16(cl, l); tmem_st8(cl + 16, l + 16); tmem_st4(cl + 24, l + 24);
+            } else {
+                tmem_st4(ch, h); tmem_st16(ch + 4, h + 4); tmem_st8(ch + 20, h + 20);
+                tmem_st4(cl, l); tmem_st16(cl + 4, l + 4); tmem_st8(cl + 20, l + 20);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        // ---- 2. layer 1 on the tensor core ----
+        __syncthreads();                                                   // operands in place; everybody has read its staged row
+        // ---- 2. layer 1 on the tensor core (A from TMEM); the staging buffer is free: the next tile's rows start to arrive ----
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int j = 0; j < K1 / 16; ++j) {
-                const uint32_t ao = (uint32_t)((j >> 2) * A_ATOM + (j & 3) * 32), wo = (uint32_t)((j >> 2) * W1_ATOM + (j & 3) * 32);
-                const uint64_t ah = make_desc(sbase + OFF_A_HI + ao), al = make_desc(sbase + OFF_A_LO + ao);
+                const uint32_t wo = (uint32_t)((j >> 2) * W1_ATOM + (j & 3) * 32);
                 const uint64_t wh = make_desc(sbase + OFF_W1_HI + wo), wl = make_desc(sbase + OFF_W1_LO + wo);
-                umma(tmem, al, wh, idesc1, j != 0);
-                umma(tmem, ah, wl, idesc1, 1);
-                umma(tmem, ah, wh, idesc1, 1);
+                const uint32_t ah = tmem + TM_A1H + (uint32_t)(j * 8), al = tmem + TM_A1L + (uint32_t)(j * 8);
+                umma_ts(tmem + TM_D1, al, wh, idesc1, j != 0);
+                umma_ts(tmem + TM_D1, ah, wl, idesc1, 1);
+                umma_ts(tmem + TM_D1, ah, wh, idesc1, 1);
             }
             commit(bar);
         }
+        if (half == 1 && t + gridDim.x < tiles) stage_tile(t + gridDim.x);   // waited for at the end of the iteration
         mbar_wait(bar, phase); phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // layer 1 has consumed the A tile: its bytes are free again, and layer 2 takes its A operand from tensor memory, so the
-        // next tile's rows are staged NOW (half 1 issues the copies and waits for them only at the end of the iteration)
-        if (half == 1 && t + gridDim.x < tiles) stage_tile(t + gridDim.x);
         // ---- 3. hidden layer 1: + b1, ReLU, split -> layer-2 A operand in TMEM (K = 64: 32 columns hi + 32 lo; K 49..63 zero) ----
         {
             const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
             uint32_t r0[32];
-            tmem_ld32(lane_base + (uint32_t)(half * 32), r0);
+            tmem_ld32(lane_base + TM_D1 + (uint32_t)(half * 32), r0);
             tmem_wait(r0);
             uint32_t h[16], l[16];
 #pragma unroll
