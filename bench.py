@@ -37,8 +37,8 @@ HORIZON = 32
 # DRAM traffic per launch from the committed `ncu --set full` captures (cold caches under ncu, so an upper bound of what a
 # warm step moves): dram__bytes_read.sum + dram__bytes_write.sum.  physics / post_step: profiles/r01f_full.md (post_step with
 # the rows_only sinks: 63 MB read + 137 MB written back by the end of the launch); nets: profiles/r01c_full.md, summed over the
-# 15 dense launches of a step; locoval: profiles/r01e_locoval.md, the 1 M-score launch
-NCU_TRAFFIC = {"physics": 5.36e6, "post_step": 200.5e6, "nets": 15 * 27.2e6, "locoval": 429.7e6}
+# 15 dense launches of a step; locoval: profiles/r01f_locoval.md, the 1 M-score launch
+NCU_TRAFFIC = {"physics": 5.36e6, "post_step": 200.5e6, "nets": 15 * 27.2e6, "locoval": 427.1e6}
 
 
 def peaks():
