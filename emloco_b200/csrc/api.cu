@@ -80,6 +80,15 @@ int emloco_create(const emloco_cfg* cfg, const emloco_model* model, emloco_sim**
         }
         md.mass[i] = model->mass[i];
         md.geom_type[i] = model->geom_type[i]; md.geom_r[i] = model->geom_r[i];
+        {   // bound of the body's contact points (physics_soa.cu skips the contact loop of bodies that cannot reach the ground)
+            const float* a = model->geom_a[i]; const float* b = model->geom_b[i];
+            const int gt = model->geom_type[i];
+            float ext;
+            if (gt == 0) ext = sqrtf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]) + model->geom_r[i];
+            else if (gt == 1) ext = fmaxf(sqrtf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]), sqrtf(b[0] * b[0] + b[1] * b[1] + b[2] * b[2])) + model->geom_r[i];
+            else { const float cx = fabsf(a[0]) + fabsf(b[0]), cy = fabsf(a[1]) + fabsf(b[1]), cz = fabsf(a[2]) + fabsf(b[2]); ext = sqrtf(cx * cx + cy * cy + cz * cz); }
+            md.geom_bound[i] = ext * 1.0001f + 1e-5f;
+        }
         for (int k = 0; k < 3; ++k) {
             md.offset[i][k] = model->offset[i][k]; md.com[i][k] = model->com[i][k];
             md.geom_a[i][k] = model->geom_a[i][k]; md.geom_b[i][k] = model->geom_b[i][k];
@@ -192,6 +201,9 @@ int emloco_set_height_field(emloco_sim* s, const int16_t* h, int32_t rows, int32
     }
     s->hf_rows = rows; s->hf_cols = cols;
     CK(cudaMemcpy(s->height, h, (size_t)rows * cols * sizeof(int16_t), cudaMemcpyHostToDevice), "copy height field");
+    int16_t mx = h[0];
+    for (size_t i = 1; i < (size_t)rows * cols; ++i) mx = h[i] > mx ? h[i] : mx;
+    s->hf_max = (float)mx * 0.005f;
     return EMLOCO_OK;
 }
 

@@ -377,7 +377,7 @@ void eml_fill_phys_params(emloco_sim* s, PhysParams& P) {
     P.actions = nullptr; P.pd_target = s->pd_target; P.actions_copy = nullptr;
     P.root = s->root_state; P.dof = s->dof_state; P.jq = s->joint_quat; P.rb = s->rb_state;
     P.contact = s->contact; P.dof_force = s->dof_force;
-    P.height = s->height; P.hf_rows = s->hf_rows; P.hf_cols = s->hf_cols;
+    P.height = s->height; P.hf_rows = s->hf_rows; P.hf_cols = s->hf_cols; P.hf_max = s->hf_max;
     P.env_ids = nullptr; P.reset_mask = nullptr; P.init_root = nullptr; P.init_dof = nullptr; P.N = s->N; P.n_sub = 0; P.dt = s->cfg.sim_dt / (float)s->cfg.substeps;
     P.gz = s->cfg.gravity_z; P.kn = s->cfg.contact_stiffness; P.cn = s->cfg.contact_damping;
     P.ct = s->cfg.friction_damping; P.mu = s->cfg.friction_mu; P.max_w = s->cfg.max_ang_vel;

@@ -73,7 +73,7 @@ struct PhysParams {
     float* pd_target;                   // [N,69]
     float* actions_copy;                // [N,69] or NULL
     float* root; float* dof; float* jq; float* rb; float* contact; float* dof_force;
-    const int16_t* height; int hf_rows, hf_cols;
+    const int16_t* height; int hf_rows, hf_cols; float hf_max;
     const int32_t* env_ids;             // FK-only mode: optional env list
     const int64_t* reset_mask;          // FK-only mode: only envs whose flag is set (device-side reset of done envs)
     const float* init_root;             // FK-only mode: take the state from these buffers instead of root/dof

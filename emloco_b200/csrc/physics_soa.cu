@@ -3,10 +3,10 @@
 // (reference seam: gym.simulate x controlFrequencyInv, pacer/pacer/env/tasks/base_task.py:792-797, and pre_physics_step,
 // humanoid.py:1184-1209) - only the mapping onto the machine differs:
 //
-//   CTA = 32 envs x 8 warps.  LANE = ENV: every per-body quantity is a struct-of-arrays [field][32 envs] in shared memory
+//   CTA = 32 envs x 12 warps.  LANE = ENV: every per-body quantity is a struct-of-arrays [field][32 envs] in shared memory
 //   (bank-conflict free, no shuffles), so all 32 lanes of a warp do the same body of 32 different envs - the tree recursions
 //   run at full lane occupancy instead of the 2-5 active lanes per level of the warp-per-env mapping (7x fewer issue slots).
-//   WARPS = the 5 kinematic chains (legs, spine+head, arms) for the tree passes, all 8 warps x 3 bodies for the per-body
+//   WARPS = the 5 kinematic chains (legs, spine+head, arms) for the tree passes, all 12 warps x 2 bodies for the per-body
 //   work (inertia, contacts, drive).  ~211 KB of shared memory per CTA: one CTA per SM, 128 CTAs for 4096 envs.
 //
 // Per integration part (a sub-step, or a piece of one when the adaptive refinement triggers):
@@ -19,7 +19,8 @@
 #include "sim.h"
 #include "physics_math.cuh"
 
-#define SOA_WARPS 8
+#define SOA_WARPS 12        // 12 x 166 registers x 32 lanes just fit the register file; the per-body phases run 2 bodies per warp
+#define SOA_BPW (EML_NB / SOA_WARPS)
 #define SOA_THREADS (SOA_WARPS * 32)
 
 // floats per body in shared memory
@@ -42,8 +43,8 @@ enum {
 #define SOA_XCHG (SOA_ROOT + 2 * 13 * 32)          // 4 chains x 27 x 32: chain totals (legs -> pelvis, arms -> chest)
 #define SOA_ACC (SOA_XCHG + 4 * 27 * 32)           // 2 x 6 x 32: pelvis and chest accelerations
 #define SOA_WMAX (SOA_ACC + 2 * 6 * 32)            // 5 x 32: per-chain max body angular speed
-#define SOA_KMAX (SOA_WMAX + 5 * 32)               // 8 ints: per-warp largest piece count
-#define SOA_FSUM (SOA_KMAX + 8)                    // 24 x 3 x 32: contact force accumulated over the parts
+#define SOA_KMAX (SOA_WMAX + 5 * 32)               // SOA_WARPS ints: per-warp largest piece count
+#define SOA_FSUM (SOA_KMAX + SOA_WARPS)                    // 24 x 3 x 32: contact force accumulated over the parts
 #define SOA_KIN (SOA_FSUM + EML_NB * 3 * 32)         // 13 x 32: the chest's kinematic state of the coming part, for the arm chains
 #define SOA_FLOATS (SOA_KIN + 13 * 32)
 #define SOA_SMEM_BYTES (SOA_FLOATS * 4)
@@ -244,10 +245,10 @@ __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams 
 #pragma unroll
         for (int k = 0; k < 13; ++k) smem[SOA_ROOT + k * 32 + lane] = r[k];
     }
-    f4 qtgt[3];
+    f4 qtgt[SOA_BPW];
 #pragma unroll
-    for (int s = 0; s < 3; ++s) {
-        const int b = warp + 8 * s;
+    for (int s = 0; s < SOA_BPW; ++s) {
+        const int b = warp + SOA_WARPS * s;
         qtgt[s] = mk4(0, 0, 0, 1);
         if (b == 0) continue;
         const int d = 3 * (b - 1);
@@ -342,10 +343,10 @@ __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams 
         SoaStep st; st.dt = dt; st.wgt = 1.0f / (float)parts; st.max_w = P.max_w; st.live = part < parts;
         st.last = (sub == P.n_sub - 1) && (part == parts - 1);
 
-        // ================= A1: per-body inertia, bias force, contacts, drive (bodies warp, warp + 8, warp + 16) =================
+        // ================= A1: per-body inertia, bias force, contacts, drive (bodies warp, warp + SOA_WARPS, ...) =================
 #pragma unroll 1
-        for (int s = 0; s < 3; ++s) {
-            const int b = warp + 8 * s;
+        for (int s = 0; s < SOA_BPW; ++s) {
+            const int b = warp + SOA_WARPS * s;
             const f3 x = ld3(smem, lane, b, F_X), vw = ld3(smem, lane, b, F_VW), vl = ld3(smem, lane, b, F_VL);
             const M3 R = quat_to_mat(ld4(smem, lane, b, F_QW));
             const float mass = Mo.mass[b];
@@ -384,8 +385,12 @@ __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams 
                 const float drop = gt == 2 ? 0.f : Mo.geom_r[b];
                 const int np = gt == 0 ? 1 : (gt == 1 ? 2 : 8);
                 const float bn = P.kn * dt + P.cn;
+                // no contact point of this body can be below the highest terrain sample: skip the loop when that holds for
+                // every env of the warp (same result: each point would find gap >= 0)
+                const bool reach = p0.z + x.z - Mo.geom_bound[b] < P.hf_max;
+                const int npw = __any_sync(FULL, reach) ? np : 0;          // evaluated once, while the warp is converged
 #pragma unroll 1
-                for (int k = 0; k < np; ++k) {
+                for (int k = 0; k < npw; ++k) {
                     f3 pb;
                     if (gt == 2) pb = mk3(ga.x + ((k & 1) ? gb.x : -gb.x), ga.y + ((k & 2) ? gb.y : -gb.y), ga.z + ((k & 4) ? gb.z : -gb.z));
                     else pb = (k == 0) ? ga : gb;

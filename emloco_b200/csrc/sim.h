@@ -24,6 +24,7 @@ struct EmlModelDev {
     float geom_r[EML_NB];
     float pd_offset[EML_ND];
     float pd_scale[EML_ND];
+    float geom_bound[EML_NB];     // largest distance from the body origin to a contact point, + the primitive's radius
     int   max_level;
 };
 
@@ -54,6 +55,7 @@ struct emloco_sim {
     float*   betas;         // [N,17]
     int16_t* height;        // [rows,cols]
     int      hf_rows, hf_cols;
+    float    hf_max;        // highest terrain sample in metres (bounding test of the contact loops)
     // pinned host staging for the *_host entry points
     float*   h_pin;
     size_t   h_pin_bytes;

@@ -92,7 +92,7 @@ enum {
     EMLOCO_T_AMP_OBS,          /* f32 [N,15,206] _amp_obs_buf (humanoid_amp.py:92-98) */
     EMLOCO_T_TRAJ_VERTS,       /* f32 [N,101,3]  TrajGenerator._verts (traj_generator.py:35-36) */
     EMLOCO_T_BETAS,            /* f32 [N,17]     humanoid_betas */
-    EMLOCO_T_HEIGHT,           /* i16 [rows,cols] Terrain.heightsamples */
+    EMLOCO_T_HEIGHT,           /* i16 [rows,cols] Terrain.heightsamples (read-only alias: change it with emloco_set_height_field) */
     EMLOCO_T_JOINT_QUAT,       /* f32 [N,23,4]   internal joint rotations (xyzw) */
     EMLOCO_T_ACTIONS,          /* f32 [N,69]     self.actions */
     EMLOCO_T_COUNT
