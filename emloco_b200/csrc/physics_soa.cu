@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams 
         st.last = (sub == P.n_sub - 1) && (part == parts - 1);
 
         // ================= A1: per-body inertia, bias force, contacts, drive (bodies warp, warp + SOA_WARPS, ...) =================
-#pragma unroll 1
+#pragma unroll
         for (int s = 0; s < SOA_BPW; ++s) {
             const int b = warp + SOA_WARPS * s;
             const f3 x = ld3(smem, lane, b, F_X), vw = ld3(smem, lane, b, F_VW), vl = ld3(smem, lane, b, F_VL);
