@@ -360,9 +360,9 @@ def run_ours(args):
         kern = {
             "physics": {"bound": "hbm", "ms": seg["physics"], "achieved": N * BYTES_PHYSICS / (seg["physics"] * 1e-3) / 1e9,
                         "peak": pk["hbm"], "unit": "GB/s",
-                        "note": "latency-bound, not HBM-bound: 4 sub-steps x 3 tree passes whose critical path is 9 dependent "
-                                "articulated-body updates (arm chain + spine); 840 M thread-instructions per launch (ncu), "
-                                "issue-active 22 %, one 8-warp CTA per SM because 4096 envs are 28 per SM"},
+                        "note": "latency-bound, not HBM-bound: per sub-step the critical path is 16 dependent articulated-body "
+                                "updates (arm chain up, spine, root solve, and down again) of ~2.4 k cycles each = 83 % of the "
+                                "kernel; one 12-warp CTA per SM because 4096 envs are 28 per SM"},
             "post_step": {"bound": "hbm", "ms": seg["post_step"], "achieved": N * BYTES_POST / (seg["post_step"] * 1e-3) / 1e9,
                           "peak": pk["hbm"], "unit": "GB/s", "note": "the launch also writes the experience rows and the normalised bf16 operands of the first layers (sinks, not counted in the algorithmic bytes)"},
             "nets": {"bound": "tensor", "ms": nets_ms, "achieved": N * FLOP_NETS_STEP / (nets_ms * 1e-3) / 1e12, "peak": pk["tf_sustained"], "unit": "TFLOP/s"},
