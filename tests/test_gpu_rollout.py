@@ -562,3 +562,34 @@ def test_rows_only_sinks_give_the_same_experience():
     for a, b in zip(*outs):
         for k_ in a:
             np.testing.assert_array_equal(a[k_], b[k_], err_msg=k_)
+
+
+def test_rollout_from_reference_configuration():
+    """the reference's YAML trees + run.py flags -> Rollout, one horizon with fine-tuning and the
+    device-side trajectory reset switched on by them."""
+    from emloco_b200.formats import kwargs_from_reference_cfg
+    from emloco_b200.policy import AMPSeptValueNetwork
+    from emloco_b200.rollout import Rollout
+    from emloco_b200.synthetic import synthetic_traj_pool
+    env_cfg = {"env": dict(numEnvs=48, episodeLength=168, controlFrequencyInv=2, power_coefficient=0.0005, location_coefficient=1,
+                           trajSampleTimestep=0.4, stepToPred=144, speedMin=0.0005, speedMax=3.0, accelMax=2.0, sharpTurnProb=0.02,
+                           hybridInitProb=0.5, numAMPObsSteps=15, numTrajSamples=15, pdControl=True, terrain=dict(staticFriction=1.0))}
+    train_cfg = {"params": dict(
+        network=dict(space=dict(continuous=dict(sigma_init=dict(val=-2.9), fixed_sigma=True, learn_sigma=False)),
+                     mlp=dict(units=[2048, 1024]), task_mlp=dict(units=[512, 256]), value_mlp=dict(units=[15, 6]), disc=dict(units=[1024, 512])),
+        config=dict(horizon_length=4, gamma=0.99, tau=0.95, task_reward_w=0.5, disc_reward_w=0.5, disc_reward_scale=2,
+                    inversion_penalty_scale=0.3, normalize_value=True, player=dict(finetune=True)))}
+    k = kwargs_from_reference_cfg(env_cfg, train_cfg, dict(real_path=True, adjust_root_vel=True, init_heading=True))
+    torch.manual_seed(0)
+    R = Rollout(k["num_envs"], net=AMPSeptValueNetwork(**k["net"]), sim_cfg=k["sim"], traj_cfg=k["traj"],
+                traj_pool=synthetic_traj_pool(8, 0), tensor_cores=True, **k["rollout"])
+    assert R.T == 4 and R.finetune and R.sim.cfg.episode_length == 168
+    R.sim.progress.fill_(165)                      # everybody times out inside the horizon
+    R.state[1].fill_(100.0)
+    v0 = R.sim.traj_verts.clone()
+    out = R.play_steps(graphed=False)
+    torch.cuda.synchronize()
+    assert out["obses"].shape == (4, 48, 1422) and out["returns"].shape == (4, 48, 1) and torch.isfinite(out["returns"]).all()
+    assert out["dones"].sum() >= 48 and (R.sim.traj_verts != v0).any()               # resets regenerated trajectories
+    assert R.valuenet.finetune_stats()[3] >= 48                                     # done_early episodes fed LocoVal
+    R.close()
