@@ -36,9 +36,9 @@ BYTES_LOCOVAL = 404           # per score
 HORIZON = 32
 # DRAM traffic per launch from the committed `ncu --set full` captures (cold caches under ncu, so an upper bound of what a
 # warm step moves): dram__bytes_read.sum + dram__bytes_write.sum.  physics / post_step: profiles/r01g_full.md (post_step with
-# the rows_only sinks: 63 MB read + 137 MB written back by the end of the launch); nets: profiles/r01c_full.md, summed over the
-# 15 dense launches of a step; locoval: profiles/r01f_locoval.md, the 1 M-score launch
-NCU_TRAFFIC = {"physics": 5.36e6, "post_step": 200.5e6, "nets": 15 * 27.2e6, "locoval": 427.1e6}
+# the rows_only sinks: 63 MB read + 137 MB written back by the end of the launch); nets: the same capture, summed over the
+# 12 tcgen05 launches of one step; locoval: profiles/r01f_locoval.md, the 1 M-score launch
+NCU_TRAFFIC = {"physics": 5.36e6, "post_step": 200.5e6, "nets": 363.7e6, "locoval": 427.1e6}
 
 
 def peaks():
@@ -373,10 +373,10 @@ def run_ours(args):
             k["frac"] = k["achieved"] / k["peak"]
             k["traffic"] = NCU_TRAFFIC[name] if (name != "locoval" or B == 1 << 20) else None
         dom = max(("physics", "post_step", "nets"), key=lambda k: kern[k]["ms"])
-        names = {"nets": "tc::linear_bf16x3_kernel (the 15 dense-layer launches of a step)", "physics": "physics_soa_kernel",
+        names = {"nets": "tc::linear_bf16x3_kernel (the 12 tcgen05 dense-layer launches of a step)", "physics": "physics_soa_kernel",
                  "post_step": "post_step_kernel"}
         roof = dict(kern[dom]); roof.update(kernel=names[dom], traffic=NCU_TRAFFIC[dom], peak_source=pk["src"],
-                                            traffic_source="profiles/r01g_full.md, r01c_full.md (ncu --set full; per step for nets, per launch otherwise)")
+                                            traffic_source="profiles/r01g_full.md + gpurun r01g_prof.ncu-rep (ncu --set full; per step for nets, per launch otherwise)")
         if dom == "nets":
             roof["note"] = ("fp32 operands are carried as bf16 hi+lo and every k-step issues 3 MMAs (bf16x3, fp32-grade products): "
                             "frac counts algorithmic FLOPs once, so its ceiling is 1/3; MMA-issue rate = 3 x achieved")
