@@ -18,7 +18,7 @@ SYMBOLS = [
     "emloco_plausibl_mlp_forward", "emloco_gae", "emloco_reset_done", "emloco_sample_actions",
     "emloco_disc_reward", "emloco_rollout_record", "emloco_normalize", "emloco_physics_step", "emloco_split_bf16",
     "emloco_linear_bf16x3", "emloco_set_post_sinks", "emloco_linear_bf16x3_rows", "emloco_timeout_gather",
-    "emloco_rollout_record_deferred", "emloco_fill_next_values", "emloco_traj_reset", "emloco_set_traj_reset", "emloco_locoval_backward_pose", "emloco_locoval_train_step", "emloco_locoval_train_workspace_bytes", "emloco_linear_bf16x3_head", "emloco_linear", "emloco_sync", "emloco_last_error", "emloco_version",
+    "emloco_rollout_record_deferred", "emloco_fill_next_values", "emloco_traj_reset", "emloco_set_traj_reset", "emloco_locoval_backward_pose", "emloco_locoval_train_step", "emloco_locoval_train_workspace_bytes", "emloco_linear_bf16x3_head", "emloco_sample_actions_parts", "emloco_linear", "emloco_sync", "emloco_last_error", "emloco_version",
 ]
 
 
@@ -115,6 +115,7 @@ def load():
     lib.emloco_linear.argtypes = [vp, i64, vp, vp, vp, i64, i64, i32, i32, vp, vp, f32, i32, i32, vp]
     lib.emloco_reset_done.argtypes = [vp, vp, vp, vp]
     lib.emloco_sample_actions.argtypes = [vp, i64, vp, vp, vp, vp, i64, i32, vp]
+    lib.emloco_sample_actions_parts.argtypes = [vp, i64, i32, i64, vp, i64, vp, vp, vp, vp, i64, i32, vp]
     lib.emloco_disc_reward.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, vp]
     lib.emloco_rollout_record.argtypes = [C.POINTER(RolloutCfg), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
     lib.emloco_normalize.argtypes = [vp, i64, vp, i64, i64, i32, vp, vp, f32, vp]
@@ -137,7 +138,7 @@ def load():
 
 # kernels launched per successful ABI call (the bench's `gpu_launches` claim is counted here, not estimated)
 LAUNCHES = {"emloco_step": 2, "emloco_physics_step": 1, "emloco_post_step": 1, "emloco_simulate": 1, "emloco_reset_done": 2,
-            "emloco_reset_indexed": 1, "emloco_traj_reset": 1, "emloco_linear": 1, "emloco_normalize": 1, "emloco_sample_actions": 1,
+            "emloco_reset_indexed": 1, "emloco_traj_reset": 1, "emloco_linear": 1, "emloco_normalize": 1, "emloco_sample_actions": 1, "emloco_sample_actions_parts": 1,
             "emloco_disc_reward": 1, "emloco_rollout_record": 1, "emloco_gae": 1, "emloco_locoval_forward": 1,
             "emloco_locoval_backward": 1, "emloco_locoval_backward_pose": 1, "emloco_locoval_train_step": 2, "emloco_plausibl_mlp_forward": 1, "emloco_step_host": 2,
             "emloco_locoval_forward_host": 1, "emloco_split_bf16": 1, "emloco_linear_bf16x3": 1, "emloco_linear_bf16x3_rows": 1, "emloco_linear_bf16x3_head": 2,

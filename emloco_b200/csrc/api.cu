@@ -421,6 +421,16 @@ int emloco_sample_actions(const float* d_mu, int64_t ldmu, const float* d_logstd
     return EMLOCO_OK;
 }
 
+int emloco_sample_actions_parts(const float* d_mu_parts, int64_t ldmu, int32_t parts, int64_t part_stride, float* d_mu_out, int64_t ldout,
+                                const float* d_logstd, const float* d_noise, float* d_actions, float* d_neglogp, int64_t N, int32_t A,
+                                void* stream) {
+    if (!d_mu_parts || !d_logstd || !d_noise || !d_actions || N < 0 || A <= 0 || ldmu < A || parts < 1 || (d_mu_out && ldout < A))
+        return fail(EMLOCO_EINVAL, "emloco_sample_actions_parts: bad argument");
+    CK(eml_sample_actions_parts(d_mu_parts, ldmu, parts, part_stride, d_mu_out, ldout, d_logstd, d_noise, d_actions, d_neglogp, N, A,
+                                (cudaStream_t)stream), "sample actions");
+    return EMLOCO_OK;
+}
+
 int emloco_disc_reward(const float* d_logit, const float* d_task_rew, float* d_disc, float* d_combined, int64_t M, float scale,
                        float w_task, float w_disc, void* stream) {
     if ((!d_logit && !d_disc) || M < 0 || (d_combined && !d_task_rew)) return fail(EMLOCO_EINVAL, "emloco_disc_reward: bad argument");
@@ -515,9 +525,15 @@ static int linear_bf16x3_impl(const int32_t* d_rows, const uint16_t* a_hi, const
     if ((y_hi == nullptr) != (y_lo == nullptr)) return fail(EMLOCO_EINVAL, "emloco_linear_bf16x3: y_hi and y_lo must come together");
     if (y_hi && ((N & 31) || ldy16 < N || (ldy16 & 7) || (((uintptr_t)y_hi | (uintptr_t)y_lo) & 15)))
         return fail(EMLOCO_EINVAL, "emloco_linear_bf16x3: split output needs N % 32 == 0, pitch % 8 == 0, 16-byte aligned pointers");
-    const int tile_n = (relu >> 8) & 0xfff;     // bits 8..19 of `relu`: 0 = automatic tile choice, 128 / 256 = forced (tests, tuning)
+    int tile_n = (relu >> 8) & 0xfff;           // bits 8..19 of `relu`: 0 = automatic tile choice, 128 / 256 = forced (tests, tuning)
     if (tile_n != 0 && (tile_n & 0x7ff) != 128 && (tile_n & 0x7ff) != 256)
         return fail(EMLOCO_EINVAL, "emloco_linear_bf16x3: tile must be 0, 128 or 256 (+0x800 for the CTA-pair kernels)");
+    const int splits = (relu >> 20) & 0xf;      // bits 20..23: split-K count (0 / 1 = off)
+    if (splits > 1) {
+        if ((relu & 1) || y_hi || head_w || !d_y32 || (tile_n & 0x800) || d_rows)
+            return fail(EMLOCO_EINVAL, "emloco_linear_bf16x3: split-K needs a plain fp32 output (no ReLU, split output, fused head, row count or CTA-pair tile)");
+        tile_n |= splits << 12;
+    }
     if (head_w && (tile_n & 0x800)) return fail(EMLOCO_EINVAL, "emloco_linear_bf16x3_head: not available with the CTA-pair kernels");
     CK(eml_linear_bf16x3(a_hi, a_lo, lda, w_hi, w_lo, ldw, d_bias, M, N, K, relu & 1, d_y32, ldy, y_hi, y_lo, ldy16, tile_n,
                          d_rows, head_w, head_part, (N + 63) / 64, (cudaStream_t)stream), "linear bf16x3 (tcgen05)");

@@ -131,6 +131,9 @@ struct GemmArgs {
     // fused single-output head (value / logit layers, N_head = 1): head_part[row][n / 64] = sum over the 64-column group of
     // act(y[row][n]) * head_w[n]; the caller adds the groups in order (+ bias).  The layer's own output may then be omitted.
     const float* head_w; float* head_part; int head_ld;
+    // split-K (skinny layers whose tile count is far below the SM count): unit u = (tile, split) covers k-blocks
+    // [split * kb_per, ...); split s writes its partial sums to y32 + s * split_stride (bias in split 0 only); the consumer adds them
+    int k_splits; long long split_stride;
 };
 
 // One 32-column chunk of one accumulator row: +bias, ReLU, then fp32 store and/or bf16 hi/lo split store.
@@ -226,16 +229,21 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_co
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (g.m_dev) { const int m = __ldg(g.m_dev); g.M = m < g.M ? m : g.M; }     // uniform: every thread reads the same word
     const int tiles_m = (g.M + BM - 1) / BM, tiles_n = (g.N + BN - 1) / BN;
-    const int num_tiles = tiles_m * tiles_n;
     const int num_kb = (g.K + BK - 1) / BK;
+    const int splits = g.k_splits > 1 ? g.k_splits : 1;
+    const int kb_per = (num_kb + splits - 1) / splits;
+    const int mn_tiles = tiles_m * tiles_n;
+    const int num_tiles = mn_tiles * splits;                    // work units: (output tile, K split)
 
     if (warp == 0) {
         if (lane == 0) {
             // ===================== TMA producer =====================
             int stage = 0; uint32_t phase = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            for (int u = blockIdx.x; u < num_tiles; u += gridDim.x) {
+                const int t = u % mn_tiles, sp = u / mn_tiles;
                 const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int kb0 = sp * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t sa = base + stage * T::STAGE_BYTES;
                     mbar_expect_tx(full_bar(stage), T::STAGE_BYTES);
@@ -253,11 +261,12 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_co
             constexpr uint32_t idesc = make_idesc<BN>();
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            for (int u = blockIdx.x; u < num_tiles; u += gridDim.x) {
+                const int kb0 = (u / mn_tiles) * kb_per, kb1 = min(num_kb, kb0 + kb_per);
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1);                  // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     const uint32_t sa = base + stage * T::STAGE_BYTES;
@@ -267,7 +276,7 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_co
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t ko = (uint64_t)((k * UMMA_K * 2) >> 4);   // advance inside the swizzle row
-                        umma_bf16(d_tmem, d_al + ko, d_wh + ko, idesc, (kb | k) != 0);   // small terms first
+                        umma_bf16(d_tmem, d_al + ko, d_wh + ko, idesc, ((kb - kb0) | k) != 0);   // small terms first
                         umma_bf16(d_tmem, d_ah + ko, d_wl + ko, idesc, 1);
                         umma_bf16(d_tmem, d_ah + ko, d_wh + ko, idesc, 1);
                     }
@@ -284,11 +293,14 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_co
         const int et = threadIdx.x - 64;                                    // 0..255
         constexpr int NC = BN / 64;                                         // 32-column chunks per warp (2 or 4)
         int acc = 0; uint32_t acc_phase = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        float* const y32_base = g.y32;
+        for (int u = blockIdx.x; u < num_tiles; u += gridDim.x) {
+            const int t = u % mn_tiles, sp = u / mn_tiles;
             const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
+            if (splits > 1) g.y32 = y32_base + (long long)sp * g.split_stride;          // this split's partial matrix
             // bias slice of this tile -> smem (one element per epilogue thread), visible after the epilogue-only barrier
             if (et < BN) {
-                s_bias[acc * BN + et] = (g.bias && n0 + et < g.N) ? __ldg(g.bias + n0 + et) : 0.f;
+                s_bias[acc * BN + et] = (g.bias && sp == 0 && n0 + et < g.N) ? __ldg(g.bias + n0 + et) : 0.f;
                 if (g.head_w) s_head[acc * BN + et] = n0 + et < g.N ? __ldg(g.head_w + n0 + et) : 0.f;
             }
             asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");
@@ -604,7 +616,7 @@ static cudaError_t launch(const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, 
         int dev = 0; cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
+    const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * (g.k_splits > 1 ? g.k_splits : 1);
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
     // programmatic dependent launch (EMLOCO_PDL=1, off by default): this kernel's prologue (tensor-map prefetch, barrier init,
     // TMEM allocation) may run while the previous kernel of the stream is still draining; griddepcontrol.wait in the kernel
@@ -663,6 +675,12 @@ cudaError_t eml_linear_bf16x3(const void* a_hi, const void* a_lo, long long lda,
     if (M <= 0 || N <= 0) return cudaSuccess;
     tc::GemmArgs g;
     g.m_dev = m_dev; g.head_w = head_w; g.head_part = head_part; g.head_ld = head_ld;
+    g.k_splits = (tile_n >> 12) & 0xf; g.split_stride = (long long)M * ldy;      // bits 12..15 of the tile word: split-K count
+    tile_n &= 0xfff;
+    if (g.k_splits > 1 && (relu || y_hi || head_w || !y32 || (tile_n & 0x800))) return cudaErrorInvalidValue;
+    if (g.k_splits > 1) {                                   // every split must own at least one k-block (both tile shapes)
+        for (int bk : {64, 32}) { const int nkb = (K + bk - 1) / bk, per = (nkb + g.k_splits - 1) / g.k_splits; if ((g.k_splits - 1) * per >= nkb) return cudaErrorInvalidValue; }
+    }
     if (head_w && (tile_n & 0x800)) return cudaErrorInvalidValue;       // the pair kernels carry no fused head
     g.bias = bias; g.y32 = y32; g.ldy = ldy; g.y_hi = (__nv_bfloat16*)y_hi; g.y_lo = (__nv_bfloat16*)y_lo; g.ldy16 = ldy16;
     g.M = (int)M; g.N = N; g.K = K; g.relu = relu;

@@ -9,7 +9,10 @@
 
 // ---- a = mu + sigma * eps ; neglogp = 0.5*sum(((a-mu)/sigma)^2) + 0.5*log(2pi)*A + sum(logstd) ----
 // one warp per env row, lanes stride over the A action dims
-__global__ void __launch_bounds__(128) sample_actions_kernel(const float* __restrict__ mu, long long ldmu,
+// parts > 1: mu arrives as `parts` partial sums (split-K output of the mu layer, part p at mu + p * part_stride); they are added
+// in order and the sum is written to mu_out
+__global__ void __launch_bounds__(128) sample_actions_kernel(const float* __restrict__ mu, long long ldmu, int parts, long long part_stride,
+                                                             float* __restrict__ mu_out, long long ldout,
                                                              const float* __restrict__ logstd, const float* __restrict__ noise,
                                                              float* __restrict__ actions, float* __restrict__ neglogp,
                                                              long long N, int A) {
@@ -21,6 +24,8 @@ __global__ void __launch_bounds__(128) sample_actions_kernel(const float* __rest
         float l = logstd[j];
         float s = expf(l);
         float m = mu[row * ldmu + j];
+        for (int p = 1; p < parts; ++p) m += mu[p * part_stride + row * ldmu + j];
+        if (mu_out) mu_out[row * ldout + j] = m;
         float a = m + s * noise[row * A + j];
         actions[row * A + j] = a;
         float z = (a - m) / s;
@@ -34,7 +39,16 @@ __global__ void __launch_bounds__(128) sample_actions_kernel(const float* __rest
 cudaError_t eml_sample_actions(const float* mu, long long ldmu, const float* logstd, const float* noise, float* actions,
                                float* neglogp, long long N, int A, cudaStream_t st) {
     if (N <= 0) return cudaSuccess;
-    sample_actions_kernel<<<(unsigned)((N + 3) / 4), 128, 0, st>>>(mu, ldmu, logstd, noise, actions, neglogp, N, A);
+    sample_actions_kernel<<<(unsigned)((N + 3) / 4), 128, 0, st>>>(mu, ldmu, 1, 0, nullptr, 0, logstd, noise, actions, neglogp, N, A);
+    return cudaGetLastError();
+}
+
+cudaError_t eml_sample_actions_parts(const float* mu_parts, long long ldmu, int parts, long long part_stride, float* mu_out, long long ldout,
+                                     const float* logstd, const float* noise, float* actions, float* neglogp, long long N, int A,
+                                     cudaStream_t st) {
+    if (N <= 0) return cudaSuccess;
+    sample_actions_kernel<<<(unsigned)((N + 3) / 4), 128, 0, st>>>(mu_parts, ldmu, parts, part_stride, mu_out, ldout, logstd, noise, actions,
+                                                                  neglogp, N, A);
     return cudaGetLastError();
 }
 

@@ -100,6 +100,9 @@ cudaError_t eml_launch_post_reset(emloco_sim* s, int keep_flags, cudaStream_t st
 cudaError_t eml_traj_reset(emloco_sim* s, const emloco_traj_cfg& c, int clear_flags, cudaStream_t st);
 cudaError_t eml_sample_actions(const float* mu, long long ldmu, const float* logstd, const float* noise, float* actions,
                                float* neglogp, long long N, int A, cudaStream_t st);
+cudaError_t eml_sample_actions_parts(const float* mu_parts, long long ldmu, int parts, long long part_stride, float* mu_out, long long ldout,
+                                     const float* logstd, const float* noise, float* actions, float* neglogp, long long N, int A,
+                                     cudaStream_t st);
 cudaError_t eml_disc_reward(const float* logit, const float* task_rew, float* disc, float* combined, long long M, float scale,
                             float w_task, float w_disc, cudaStream_t st);
 cudaError_t eml_rollout_record(const RecordParams& P, cudaStream_t st);

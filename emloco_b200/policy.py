@@ -138,6 +138,9 @@ class RolloutNets:
             self.s_a2, self.s_c2, self.s_d1, self.s_d2 = S(a2), S(a2), S(d1), S(d2)
             # partial sums of the fused value / logit heads (one per 64 columns of the hidden layer that feeds them)
             self.hp_c, self.hp_d = f(M, (a2 + 63) // 64), f(M, (d2 + 63) // 64)
+            # the mu layer (a2 -> 69) is 32 tiles of 16 k-blocks: split-K x4 puts it on 128 SMs; sample_actions adds the partials
+            self.mu_splits = 4 if a2 % 256 == 0 else 1
+            self.mu_parts = f(self.mu_splits, M, ACTIONS)
             # discriminator operands of every step of the horizon are kept (slot n = rows [n*M, (n+1)*M)), so the post-horizon
             # discriminator pass of play_steps (:157) runs as ONE M*T-row GEMM chain without re-reading the fp32 AMP rows
             self.amp_slots = int(amp_slots)
@@ -221,6 +224,10 @@ class RolloutNets:
         def actor():
             if self.tc:
                 linear_bf16x3(self.s_ac1.cols(0, h), W("a2", n.actor_mlp[2].weight), n.actor_mlp[2].bias.detach(), True, y16=self.s_a2)
+                if self.mu_splits > 1:
+                    linear_bf16x3(self.s_a2, W("mu", n.mu.weight), n.mu.bias.detach(), False, y32=self.mu_parts[0], splits=self.mu_splits)
+                    sample_actions_parts(self.mu_parts, mu_out, n.sigma, noise, actions_out, neglogp_out)
+                    return
                 linear_bf16x3(self.s_a2, W("mu", n.mu.weight), n.mu.bias.detach(), False, y32=mu_out)
             else:
                 self._lin(self.ac1[:, :h], n.actor_mlp[2], True, self.a2)
@@ -359,17 +366,18 @@ def split_bf16(x, dst: _Split, mean=None, var=None, eps=1e-5):
     return dst
 
 
-def linear_bf16x3(a: _Split, w: _Split, bias, relu, y32=None, y16: _Split = None, tile=0, rows=None, head=None):
+def linear_bf16x3(a: _Split, w: _Split, bias, relu, y32=None, y16: _Split = None, tile=0, rows=None, head=None, splits=0):
     """y = act(a w^T + bias) on the tcgen05 path; fp32 output and/or split output for the next layer.
     tile: 0 = library picks the output-tile width, 128 / 256 = forced.
     rows: optional int32 device scalar - only that many leading rows are valid (compacted row sets).
+    splits: split-K count (> 1): y32 must be the first of `splits` consecutive [M, N] matrices, which receive partial sums.
     head: optional (layer nn.Linear(N, 1), out [M,1], part [M, ceil(N/64)]) - the single-output layer that follows, fused
           into the epilogue (emloco_linear_bf16x3_head); y32 / y16 may then be omitted."""
     M, K, N = a.rows, a.K, w.rows
     assert w.K == K
     if y32 is not None:
         assert y32.shape == (M, N) and y32.stride(1) == 1
-    args = (_ptr(a.hi), _ptr(a.lo), a.ld, _ptr(w.hi), _ptr(w.lo), w.ld, _ptr(bias), M, N, K, int(bool(relu)) | (int(tile) << 8),
+    args = (_ptr(a.hi), _ptr(a.lo), a.ld, _ptr(w.hi), _ptr(w.lo), w.ld, _ptr(bias), M, N, K, int(bool(relu)) | (int(tile) << 8) | (int(splits) << 20),
             _ptr(y32), 0 if y32 is None else y32.stride(0), None if y16 is None else _ptr(y16.hi),
             None if y16 is None else _ptr(y16.lo), 0 if y16 is None else y16.ld)
     if head is not None:
@@ -415,6 +423,16 @@ def normalize(x, mean, var, eps=1e-5, out=None):
     _lib.check(_lib.load().emloco_normalize(_ptr(x), x.stride(0), _ptr(out), out.stride(0), M, K, _ptr(mean), _ptr(var), eps,
                                             _stream()), "emloco_normalize")
     return out
+
+
+def sample_actions_parts(mu_parts, mu_out, logstd, noise, actions, neglogp):
+    """sample_actions on the split-K partial sums of the mu layer: mu_parts [S, M, A] contiguous, their sum goes to mu_out."""
+    S, M, A = mu_parts.shape
+    assert mu_parts.is_contiguous() and mu_out.shape == (M, A) and mu_out.stride(1) == 1 and noise.is_contiguous()
+    _lib.check(_lib.load().emloco_sample_actions_parts(_ptr(mu_parts), A, S, M * A, _ptr(mu_out), mu_out.stride(0), _ptr(logstd),
+                                                       _ptr(noise), _ptr(actions), _ptr(neglogp), M, A, _stream()),
+               "emloco_sample_actions_parts")
+    return actions, neglogp
 
 
 def sample_actions(mu, logstd, noise, actions=None, neglogp=None):

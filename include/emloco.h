@@ -286,6 +286,12 @@ int emloco_linear(const float* d_x, int64_t ldx, const float* d_w, const float* 
  * amp_humanoid_smpl_sept_task.yaml:19-27).  mu rows have stride ldmu; noise/actions [N,A]; neglogp [N] or NULL. */
 int emloco_sample_actions(const float* d_mu, int64_t ldmu, const float* d_logstd, const float* d_noise, float* d_actions,
                           float* d_neglogp, int64_t N, int32_t A, void* stream);
+/* The same with mu given as `parts` partial sums (the split-K output of the mu layer: emloco_linear_bf16x3 with a split count in
+ * bits 20..23 of `relu` leaves `parts` matrices [N, ldmu], part_stride floats apart); they are added in order, the sum goes to
+ * d_mu_out [N, ldout] (may be NULL) and is what the action is sampled around. */
+int emloco_sample_actions_parts(const float* d_mu_parts, int64_t ldmu, int32_t parts, int64_t part_stride, float* d_mu_out, int64_t ldout,
+                                const float* d_logstd, const float* d_noise, float* d_actions, float* d_neglogp, int64_t N, int32_t A,
+                                void* stream);
 /* _calc_disc_rewards + _combine_rewards (learning/amp_continuous.py:675-692, 659-664):
  * disc = -log(max(1 - sigmoid(logit), 1e-4)) * scale; combined = w_task*task + w_disc*disc.  Either output may be NULL;
  * d_logit == NULL means d_disc already holds the AMP rewards (combine only). */
@@ -321,7 +327,9 @@ int emloco_rollout_record(const emloco_rollout_cfg* cfg, const float* d_rew, con
  * writes fp32 y32 [M,N] (pitch ldy) and/or the split of y as the next layer's operand y_hi/y_lo (pitch ldy16, N % 32 == 0).
  * All bf16 base pointers 16-byte aligned, pitches multiples of 8 elements.  `relu`: bit 0 = ReLU; bits 8..19 optionally force
  * the N-extent of the output tile (128 or 256; 0 = chosen from the shape; +0x800 = the CTA-pair kernels, 256 rows per
- * pair) - used by the tests and for tuning. */
+ * pair) - used by the tests and for tuning; bits 20..23 = split-K count S > 1 for skinny layers whose tile count is far below
+ * the SM count: y32 then receives S partial matrices [M, ldy], M * ldy floats apart (bias in the first), to be added by the
+ * consumer (emloco_sample_actions_parts); needs a plain fp32 output - no ReLU, split output, fused head or row count. */
 int emloco_split_bf16(const float* d_x, int64_t ldx, int64_t M, int32_t K, const float* d_mean, const float* d_var, float eps,
                       uint16_t* d_hi, uint16_t* d_lo, int64_t ld16, void* stream);
 int emloco_linear_bf16x3(const uint16_t* d_a_hi, const uint16_t* d_a_lo, int64_t lda, const uint16_t* d_w_hi,

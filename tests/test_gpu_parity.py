@@ -514,3 +514,34 @@ def test_locoval_variant_gradients_match_float64_autograd(use_pose, use_vel, vru
         assert np.abs(g - r).max() <= 2e-3 * np.abs(r).max() + 1e-9, (np.abs(g - r).max(), np.abs(r).max())
     if use_pose:
         np.testing.assert_allclose(kp.detach().cpu().numpy(), p.detach().numpy(), rtol=RTOL, atol=2e-6)
+
+
+@pytest.mark.parametrize("tile", [0, 128, 256])
+def test_linear_bf16x3_split_k_and_sample_actions_parts(tile):
+    """Skinny layer (the mu head: 4096 x 69 x 1024) with split-K: the partial matrices add up to the fp64 product; the action
+    sampler that consumes the partials gives the same mu / actions / neglogp as the unsplit path."""
+    from emloco_b200.policy import _Split, linear_bf16x3, sample_actions, sample_actions_parts, split_bf16
+    rng = np.random.default_rng(7)
+    M, N, K, S = 1000, 69, 1024, 4
+    x = rng.normal(0, 1.5, (M, K)).astype(np.float32)
+    w = (rng.normal(0, 1, (N, K)) / np.sqrt(K)).astype(np.float32); b = rng.normal(0, 0.1, N).astype(np.float32)
+    T = lambda a: torch.from_numpy(a).cuda()
+    sx, sw = _Split(M, K, "cuda"), _Split(N, K, "cuda")
+    split_bf16(T(x), sx); split_bf16(T(w), sw)
+    parts = torch.full((S, M, N), 9.0, device="cuda")
+    linear_bf16x3(sx, sw, T(b), False, y32=parts[0], tile=tile, splits=S)
+    ref = x.astype(np.float64) @ w.astype(np.float64).T + b
+    scale = np.abs(x).astype(np.float64) @ np.abs(w).astype(np.float64).T + np.abs(b)
+    got = parts.sum(0).cpu().numpy()
+    assert (np.abs(got - ref) / scale).max() < 1e-4
+    y = torch.empty(M, N, device="cuda")
+    linear_bf16x3(sx, sw, T(b), False, y32=y, tile=tile)
+    np.testing.assert_allclose(got, y.cpu().numpy(), rtol=1e-5, atol=1e-5)
+    logstd = torch.full((N,), -2.9, device="cuda"); noise = torch.randn(M, N, device="cuda")
+    mu_o = torch.empty(M, N, device="cuda"); a1 = torch.empty(M, N, device="cuda"); n1 = torch.empty(M, device="cuda")
+    sample_actions_parts(parts, mu_o, logstd, noise, a1, n1)
+    a2, n2 = sample_actions(mu_o, logstd, noise)
+    np.testing.assert_allclose(mu_o.cpu().numpy(), got, rtol=1e-6, atol=1e-6)
+    assert torch.equal(a1, a2) and torch.allclose(n1, n2, rtol=1e-5, atol=1e-4)
+    with pytest.raises(Exception):
+        linear_bf16x3(sx, sw, T(b), True, y32=parts[0], tile=tile, splits=S)           # ReLU cannot be split
