@@ -138,8 +138,10 @@ class RolloutNets:
             self.s_a2, self.s_c2, self.s_d1, self.s_d2 = S(a2), S(a2), S(d1), S(d2)
             # partial sums of the fused value / logit heads (one per 64 columns of the hidden layer that feeds them)
             self.hp_c, self.hp_d = f(M, (a2 + 63) // 64), f(M, (d2 + 63) // 64)
-            # the mu layer (a2 -> 69) is 32 tiles of 16 k-blocks: split-K x4 puts it on 128 SMs; sample_actions adds the partials
-            self.mu_splits = 4 if a2 % 256 == 0 else 1
+            # the mu layer (a2 -> 69) is 32 tiles of 16 k-blocks; split-K x4 (mu_splits = 4: 128 CTAs, partials added by the action
+            # sampler) makes the layer itself faster but its CTAs then crowd out the critic branch's second wave: the policy pass
+            # got 13 us SLOWER (202 -> 216 us), so it stays off
+            self.mu_splits = 1
             self.mu_parts = f(self.mu_splits, M, ACTIONS)
             # discriminator operands of every step of the horizon are kept (slot n = rows [n*M, (n+1)*M)), so the post-horizon
             # discriminator pass of play_steps (:157) runs as ONE M*T-row GEMM chain without re-reading the fp32 AMP rows
