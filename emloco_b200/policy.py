@@ -135,7 +135,7 @@ class RolloutNets:
         if self.tc:
             S = lambda k: _Split(M, k, dev)
             self.s_tin, self.s_t1, self.s_ain, self.s_ac1 = S(TASK_OBS), S(t1), S(SELF_OBS + t2), S(2 * a1)
-            self.s_a2, self.s_c2, self.s_d1, self.s_d2 = S(a2), S(a2), S(d1), S(d2)
+            self.s_a2, self.s_d1 = S(a2), S(d1)      # (the last hidden layers of critic and discriminator are consumed in the epilogue: no buffer)
             # partial sums of the fused value / logit heads (one per 64 columns of the hidden layer that feeds them)
             self.hp_c, self.hp_d = f(M, (a2 + 63) // 64), f(M, (d2 + 63) // 64)
             # the mu layer (a2 -> 69) is 32 tiles of 16 k-blocks; split-K x4 (mu_splits = 4: 128 CTAs, partials added by the action
