@@ -134,6 +134,10 @@ struct GemmArgs {
     // split-K (skinny layers whose tile count is far below the SM count): unit u = (tile, split) covers k-blocks
     // [split * kb_per, ...); split s writes its partial sums to y32 + s * split_stride (bias in split 0 only); the consumer adds them
     int k_splits; long long split_stride;
+    // tile order: 0 = consecutive work units walk down M (they share a W tile), 1 = they walk across N (they share an A row
+    // block).  When A is much larger than the L2 (the 131 072-row post-horizon pass: 1.6 GB) the M-fast order streams it from
+    // DRAM once per N tile (6.8 GB read, ncu); N-fast keeps the co-scheduled CTAs on the same rows
+    int n_fast;
 };
 
 // One 32-column chunk of one accumulator row: +bias, ReLU, then fp32 store and/or bf16 hi/lo split store.
@@ -241,7 +245,7 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_co
             int stage = 0; uint32_t phase = 0;
             for (int u = blockIdx.x; u < num_tiles; u += gridDim.x) {
                 const int t = u % mn_tiles, sp = u / mn_tiles;
-                const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
+                const int m0 = (g.n_fast ? t / tiles_n : t % tiles_m) * BM, n0 = (g.n_fast ? t % tiles_n : t / tiles_m) * BN;
                 const int kb0 = sp * kb_per, kb1 = min(num_kb, kb0 + kb_per);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
@@ -296,7 +300,7 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_co
         float* const y32_base = g.y32;
         for (int u = blockIdx.x; u < num_tiles; u += gridDim.x) {
             const int t = u % mn_tiles, sp = u / mn_tiles;
-            const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
+            const int m0 = (g.n_fast ? t / tiles_n : t % tiles_m) * BM, n0 = (g.n_fast ? t % tiles_n : t / tiles_m) * BN;
             if (splits > 1) g.y32 = y32_base + (long long)sp * g.split_stride;          // this split's partial matrix
             // bias slice of this tile -> smem (one element per epilogue thread), visible after the epilogue-only barrier
             if (et < BN) {
@@ -676,6 +680,7 @@ cudaError_t eml_linear_bf16x3(const void* a_hi, const void* a_lo, long long lda,
     tc::GemmArgs g;
     g.m_dev = m_dev; g.head_w = head_w; g.head_part = head_part; g.head_ld = head_ld;
     g.k_splits = (tile_n >> 12) & 0xf; g.split_stride = (long long)M * ldy;      // bits 12..15 of the tile word: split-K count
+    g.n_fast = (double)M * (double)K * 4.0 > 48e6;                               // hi + lo bytes of A beyond ~L2 / 2
     tile_n &= 0xfff;
     if (g.k_splits > 1 && (relu || y_hi || head_w || !y32 || (tile_n & 0x800))) return cudaErrorInvalidValue;
     if (g.k_splits > 1) {                                   // every split must own at least one k-block (both tile shapes)
