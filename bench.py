@@ -123,12 +123,36 @@ def cpu_rollout_rate(envs, steps, warmup, seed=0, budget_s=None):
     R = CpuRollout(A, synthetic_env_state(envs, seed, rest_root_height(A)), P, D, traj_flags=TRAJ_FLAGS,
                    traj_pool=synthetic_traj_pool(TRAJ_POOL, seed), traj_seed=seed)
     rng = np.random.default_rng(seed)
+    # the rest of what the GPU arm's step does: LocoVal scoring of every env each step, and once per horizon the
+    # discriminator over the stored AMP observations + reward combine + GAE (amp_continuous_value.py:150-163)
+    from emloco_b200.synthetic import synthetic_locoval_batch
+    from oracle import oracle_np as O
+    lv_traj, lv_pose, lv_vel = synthetic_locoval_batch(envs, seed)
+    r2 = np.random.default_rng(seed + 1)
+    LW = {"fc1": (r2.normal(0, 0.1, (49, 100)).astype(np.float32), np.zeros(49, np.float32)),
+          "fc2": (r2.normal(0, 0.1, (24, 49)).astype(np.float32), np.zeros(24, np.float32)),
+          "fc3": (r2.normal(0, 0.1, (1, 24)).astype(np.float32), np.zeros(1, np.float32))}
+    hist = {k: [] for k in ("amp_obs", "rewards", "values", "next_values", "dones")}
+
+    def full_step():
+        o = R.step(rng.standard_normal((envs, 69)).astype(np.float32))
+        O.locoval_forward(lv_traj, lv_pose.copy(), lv_vel, LW)
+        for k in hist:
+            hist[k].append(o[k])
+        if len(hist["dones"]) == HORIZON:
+            amp = np.concatenate(hist["amp_obs"], 0)
+            amp_r, _ = O.disc_reward(amp, R.D, R.disc_scale)
+            comb = (0.5 * np.stack(hist["rewards"]) + 0.5 * amp_r.reshape(HORIZON, envs))[..., None].astype(np.float32)
+            O.discount_values(np.stack(hist["dones"]).astype(np.float32), np.stack(hist["values"])[..., None].astype(np.float32), comb,
+                              np.stack(hist["next_values"])[..., None].astype(np.float32))
+            for k in hist:
+                hist[k].clear()
     for _ in range(warmup):
-        R.step(rng.standard_normal((envs, 69)).astype(np.float32))
+        full_step()
     t0 = time.perf_counter()
     done = 0
     for _ in range(steps):
-        R.step(rng.standard_normal((envs, 69)).astype(np.float32))
+        full_step()
         done += 1
         if budget_s is not None and time.perf_counter() - t0 > budget_s:
             break
@@ -144,7 +168,7 @@ def run_reference(args):
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     envs = min(args.envs, 256)          # bounded sample of the 4096-env workload: ~0.3-1 s of host work per step
     rate, done, dt = cpu_rollout_rate(envs, args.steps, min(args.warmup, 2), budget_s=150.0)
-    sample = f"{envs} of {args.envs} envs per step, {done} steps in {dt:.1f} s (oracle port: fp64 C physics + numpy nets/post-step)"
+    sample = f"{envs} of {args.envs} envs per step, {done} steps in {dt:.1f} s (oracle port: fp64 C physics + numpy nets / post-step / LocoVal scoring / post-horizon pass)"
     print(json.dumps({
         "impl": "reference", "metric": "env_steps_per_sec", "value": rate, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": done, "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * dt / max(done, 1), "higher_is_better": True,
@@ -387,7 +411,7 @@ def run_ours(args):
         if not args.no_cpu_baseline and world == 1:     # reported at N = 1 only
             rate, done, dt = cpu_rollout_rate(256, 1000, 2, seed=args.seed, budget_s=15.0)
             cpu = {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                   "sample": f"256 of {N} envs per step, {done} steps in {dt:.1f} s (fp64 C physics oracle with OpenMP + numpy nets/post-step)"}
+                   "sample": f"256 of {N} envs per step, {done} steps in {dt:.1f} s (fp64 C physics oracle with OpenMP + numpy nets / post-step / LocoVal scoring / post-horizon pass)"}
 
         out = {
             "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
