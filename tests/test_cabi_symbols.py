@@ -67,3 +67,48 @@ def test_mjcf_model_table():
     assert a["names"][13] == "Head" and a["names"][7] == "R_Ankle"
     assert abs(a["pd_scale"][4] - 5) < 1e-6 and abs(a["pd_scale"][16] - 5) < 1e-6
     assert 60 < a["total_mass"] < 90
+
+
+def test_ctypes_struct_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors in emloco_b200/_lib.py have the size (and, for the plain ones, the field offsets) a C compiler gives
+    the structs of include/emloco.h - guards against the two drifting apart."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from emloco_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        import pytest
+        pytest.skip("no C compiler")
+    src = tmp_path / "sizes.c"
+    src.write_text('''#include <stdio.h>
+#include <stddef.h>
+#include "emloco.h"
+int main(void) {
+    printf("emloco_cfg %zu\\n", sizeof(emloco_cfg));
+    printf("emloco_model %zu\\n", sizeof(emloco_model));
+    printf("emloco_rollout_cfg %zu\\n", sizeof(emloco_rollout_cfg));
+    printf("emloco_post_sinks %zu\\n", sizeof(emloco_post_sinks));
+    printf("emloco_traj_cfg %zu\\n", sizeof(emloco_traj_cfg));
+    printf("cfg.max_effort %zu\\n", offsetof(emloco_cfg, max_effort));
+    printf("cfg.physics_impl %zu\\n", offsetof(emloco_cfg, physics_impl));
+    printf("sinks.rows_only %zu\\n", offsetof(emloco_post_sinks, rows_only));
+    printf("sinks.ld_amp %zu\\n", offsetof(emloco_post_sinks, ld_amp));
+    printf("traj.seed %zu\\n", offsetof(emloco_traj_cfg, seed));
+    printf("traj.num_waypoints %zu\\n", offsetof(emloco_traj_cfg, num_waypoints));
+    return 0;
+}
+''')
+    exe = tmp_path / "sizes"
+    inc = os.path.join(ROOT, "include")
+    subprocess.run([gcc, "-std=c99", "-I", inc, str(src), "-o", str(exe)], check=True)
+    out = dict(l.rsplit(" ", 1) for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().splitlines())
+    out = {k: int(v) for k, v in out.items()}
+    assert out["emloco_cfg"] == C.sizeof(_lib.Cfg)
+    assert out["emloco_model"] == C.sizeof(_lib.Model)
+    assert out["emloco_rollout_cfg"] == C.sizeof(_lib.RolloutCfg)
+    assert out["emloco_post_sinks"] == C.sizeof(_lib.PostSinks)
+    assert out["emloco_traj_cfg"] == C.sizeof(_lib.TrajCfg)
+    assert out["cfg.max_effort"] == _lib.Cfg.max_effort.offset and out["cfg.physics_impl"] == _lib.Cfg.physics_impl.offset
+    assert out["sinks.rows_only"] == _lib.PostSinks.rows_only.offset and out["sinks.ld_amp"] == _lib.PostSinks.ld_amp.offset
+    assert out["traj.seed"] == _lib.TrajCfg.seed.offset and out["traj.num_waypoints"] == _lib.TrajCfg.num_waypoints.offset
