@@ -39,7 +39,7 @@ class Cfg(C.Structure):
 class RolloutCfg(C.Structure):
     _fields_ = [("inversion_penalty_scale", C.c_float), ("reward_scale", C.c_float), ("value_mean", C.c_float),
                 ("value_std", C.c_float), ("disc_reward_scale", C.c_float), ("gamma", C.c_float),
-                ("step_to_pred", C.c_int32), ("unnorm_value", C.c_int32)]
+                ("step_to_pred", C.c_int32), ("unnorm_value", C.c_int32), ("d_value_stats", C.c_void_p)]
 
 
 class PostSinks(C.Structure):

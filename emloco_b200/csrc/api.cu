@@ -454,7 +454,7 @@ int emloco_rollout_record(const emloco_rollout_cfg* c, const float* d_rew, const
     P.current_rewards = d_state; P.current_lengths = d_state + N; P.current_combined = d_state + 2 * N;
     P.discount_coefs = d_state + 3 * N; P.game_combined = d_state + 4 * N; P.terminated_flags = d_state + 5 * N;
     P.N = N; P.inv_penalty = c->inversion_penalty_scale; P.reward_scale = c->reward_scale; P.v_mean = c->value_mean;
-    P.v_std = c->value_std; P.disc_scale = c->disc_reward_scale; P.gamma = c->gamma; P.step_to_pred = (float)c->step_to_pred;
+    P.v_std = c->value_std; P.v_stats = c->d_value_stats; P.disc_scale = c->disc_reward_scale; P.gamma = c->gamma; P.step_to_pred = (float)c->step_to_pred;
     P.unnorm_value = c->unnorm_value;
     P.c_value_raw = nullptr; P.c_idx = nullptr; P.c_count = nullptr; P.prev_dones = nullptr; P.prev_next_values = nullptr;
     CK(eml_rollout_record(P, (cudaStream_t)stream), "rollout record");
@@ -476,7 +476,7 @@ int emloco_rollout_record_deferred(const emloco_rollout_cfg* c, const float* d_r
     P.current_rewards = d_state; P.current_lengths = d_state + N; P.current_combined = d_state + 2 * N;
     P.discount_coefs = d_state + 3 * N; P.game_combined = d_state + 4 * N; P.terminated_flags = d_state + 5 * N;
     P.N = N; P.inv_penalty = c->inversion_penalty_scale; P.reward_scale = c->reward_scale; P.v_mean = c->value_mean;
-    P.v_std = c->value_std; P.disc_scale = c->disc_reward_scale; P.gamma = c->gamma; P.step_to_pred = (float)c->step_to_pred;
+    P.v_std = c->value_std; P.v_stats = c->d_value_stats; P.disc_scale = c->disc_reward_scale; P.gamma = c->gamma; P.step_to_pred = (float)c->step_to_pred;
     P.unnorm_value = c->unnorm_value;
     P.c_value_raw = d_c_value_raw; P.c_idx = d_c_idx; P.c_count = d_c_count; P.prev_dones = d_prev_dones; P.prev_next_values = d_prev_next_values;
     CK(eml_rollout_record(P, (cudaStream_t)stream), "rollout record (deferred next values)");
@@ -486,7 +486,7 @@ int emloco_rollout_record_deferred(const emloco_rollout_cfg* c, const float* d_r
 int emloco_fill_next_values(const emloco_rollout_cfg* c, const float* d_value_raw, const float* d_prev_dones, float* d_prev_next_values,
                             int64_t N, void* stream) {
     if (!c || !d_value_raw || !d_prev_dones || !d_prev_next_values || N < 0) return fail(EMLOCO_EINVAL, "emloco_fill_next_values: bad argument");
-    CK(eml_fill_next_values(d_value_raw, d_prev_dones, d_prev_next_values, N, c->value_mean, c->value_std, c->unnorm_value,
+    CK(eml_fill_next_values(d_value_raw, d_prev_dones, d_prev_next_values, N, c->value_mean, c->value_std, c->d_value_stats, c->unnorm_value,
                             (cudaStream_t)stream), "fill next values");
     return EMLOCO_OK;
 }

@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(TR_THREADS) lv_train_kernel(LvTrainParams P) {
     float* s_dz = s_d2 + TR_TILE * H2;                     //       dL/dz    [TILE]
     __shared__ float s_red[3][TR_THREADS / 32];
     __shared__ unsigned int s_last;
+    __shared__ float s_step;
     const int tid = threadIdx.x;
     const int count = *P.count;
     if (count == 0) return;                                // no valid env: no optimiser step (:124)
@@ -187,7 +188,9 @@ __global__ void __launch_bounds__(TR_THREADS) lv_train_kernel(LvTrainParams P) {
     __syncthreads();
     if (s_last != gridDim.x - 1) return;
     __threadfence();
-    const float t = *P.step + 1.0f;                                               // optimiser step count (torch AdamW)
+    if (tid == 0) s_step = *P.step + 1.0f;                                        // one reader, then a barrier: no thread may see
+    __syncthreads();                                                              // the count tid 4 stores below
+    const float t = s_step;                                                       // optimiser step count (torch AdamW)
     const float bc1 = 1.0f - powf(P.beta1, t), bc2 = 1.0f - powf(P.beta2, t);
     const float step_size = P.lr / bc1, rs_bc2 = rsqrtf(bc2);
     for (int i = tid; i < NW; i += TR_THREADS) {

@@ -79,6 +79,7 @@ __global__ void rollout_record_kernel(RecordParams P) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.N) return;
     float r = P.rew[i];
+    if (P.v_stats) { P.v_mean = __ldg(P.v_stats); P.v_std = __ldg(P.v_stats + 1); }
     if (P.inverted && P.inverted[i]) r *= -P.inv_penalty;                 // :63-64
     float shaped = r * P.reward_scale;                                    // rewards_shaper (scale_value 1)
     float done = P.reset[i] != 0 ? 1.0f : 0.0f;
@@ -191,17 +192,19 @@ cudaError_t eml_timeout_gather(const int64_t* reset, const int64_t* terminate, l
 
 // next_values of step n-1 for the envs that were not reset: this step's (un-normalised) critic output
 __global__ void fill_next_values_kernel(const float* __restrict__ value_raw, const float* __restrict__ prev_dones,
-                                        float* __restrict__ prev_next_values, long long N, float v_mean, float v_std, int unnorm) {
+                                        float* __restrict__ prev_next_values, long long N, float v_mean, float v_std,
+                                        const float* __restrict__ v_stats, int unnorm) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N || prev_dones[i] != 0.0f) return;
+    if (v_stats) { v_mean = __ldg(v_stats); v_std = __ldg(v_stats + 1); }
     float v = value_raw[i];
     if (unnorm) v = v_std * fminf(fmaxf(v, -5.0f), 5.0f) + v_mean;
     prev_next_values[i] = v;
 }
 cudaError_t eml_fill_next_values(const float* value_raw, const float* prev_dones, float* prev_next_values, long long N, float v_mean,
-                                 float v_std, int unnorm, cudaStream_t st) {
+                                 float v_std, const float* v_stats, int unnorm, cudaStream_t st) {
     if (N <= 0) return cudaSuccess;
-    fill_next_values_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(value_raw, prev_dones, prev_next_values, N, v_mean, v_std, unnorm);
+    fill_next_values_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(value_raw, prev_dones, prev_next_values, N, v_mean, v_std, v_stats, unnorm);
     return cudaGetLastError();
 }
 

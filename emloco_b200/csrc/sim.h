@@ -84,6 +84,7 @@ struct RecordParams {
     long long N;
     float inv_penalty, reward_scale, v_mean, v_std, disc_scale, gamma, step_to_pred;
     int unnorm_value;
+    const float* v_stats;        // device {mean, std} overriding v_mean / v_std when non-NULL (graph-safe value_mean_std updates)
     // deferred next-values (value reuse): next_value_raw == NULL.  Terminated envs get 0 now, timed-out envs (reset, not
     // terminated) get the compact critic's value now, the others are filled one step later from that step's value_raw
     const float* c_value_raw; const int32_t* c_idx; const int32_t* c_count;   // compact critic outputs
@@ -120,4 +121,4 @@ cudaError_t eml_timeout_gather(const int64_t* reset, const int64_t* terminate, l
                                long long ld_task, uint16_t* c_self_hi, uint16_t* c_self_lo, long long ld_cself, uint16_t* c_task_hi,
                                uint16_t* c_task_lo, long long ld_ctask, int32_t* idx, int32_t* count, cudaStream_t st);
 cudaError_t eml_fill_next_values(const float* value_raw, const float* prev_dones, float* prev_next_values, long long N, float v_mean,
-                                 float v_std, int unnorm, cudaStream_t st);
+                                 float v_std, const float* v_stats, int unnorm, cudaStream_t st);

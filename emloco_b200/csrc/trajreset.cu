@@ -113,6 +113,9 @@ __global__ void __launch_bounds__(TR_WARPS * 32) traj_reset_kernel(TrajParams P)
     __syncwarp();
     // --- real-world trajectory from the pool (:116-160)
     if ((c.flags & EMLOCO_TRAJ_REAL_PATH) && c.pool && c.pool_count > 0 && U(402) > c.hybrid_init_prob) {
+        // DEVIATION: every env draws its pool index independently (WITH replacement); the reference draws the indices of one
+        // reset batch with random.sample (traj_generator.py:122, without replacement inside the batch).  The marginal
+        // distribution per env is the same (uniform over the pool); two envs reset in the same step may share a trajectory.
         long long pick = (long long)(U(403) * (float)c.pool_count);
         if (pick > c.pool_count - 1) pick = c.pool_count - 1;
         const float* t = c.pool + (size_t)pick * NV * 3;

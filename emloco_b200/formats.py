@@ -130,14 +130,42 @@ def filter_modes(values, threshold=0.7):
     return keep
 
 
-def score_and_filter(valuenet, pred_trajs, init_pose, init_vel, threshold=0.7):
+def score_and_filter(valuenet, pred_trajs, init_pose, init_vel, threshold=0.7, reference_compat=False, gt_trajs=None):
     """pred_trajs [S, M, 13, 2] (origin prepended, evaluate_jta.py:293-296), init_pose [S,24,3], init_vel [S,2] ->
     (values [S,M], keep [S,M]).  One LocoVal launch over S*M rows instead of S*M batch-of-1 calls; pose / velocity are
-    shared by the M modes of a scene and never mutated here."""
+    shared by the M modes of a scene and never mutated here.
+
+    DEVIATION (default): every mode is scored against the scene's ORIGINAL pose.  The reference loop
+    (evaluate_jta.py:298-302) passes `init_pose.unsqueeze(0)` - a view - to `calc_embodied_motion_loss` twice per mode (the
+    prediction, then the ground truth), and ValuePoseNet rotates that pose in place by the heading of the trajectory it is
+    given (value_pose_net.py:97,141-144), so in the reference mode p of a scene is scored against the pose already rotated by
+    the headings of predictions 0..p-1 and p ground-truth calls.  Only mode 0 agrees with the default here.
+    reference_compat=True reproduces the reference numbers, still in one launch: the heading depends on the trajectory alone,
+    so the cumulative rotation each mode sees is applied to a private copy of the pose up front (gt_trajs [S,13,2] required:
+    its heading is part of the chain).  Values then match the sequential loop to float rounding."""
     S, M = pred_trajs.shape[:2]
     traj = pred_trajs.reshape(S * M, 13, -1).contiguous()
     pose = init_pose[:, None].expand(S, M, 24, 3).reshape(S * M, 24, 3).contiguous()
     vel = init_vel[:, None].expand(S, M, 2).reshape(S * M, 2).contiguous()
+    if reference_compat:
+        if gt_trajs is None:
+            raise ValueError("reference_compat=True needs gt_trajs: the reference also scores the ground truth on the same pose")
+
+        def heading(t):                                                   # value_pose_net.py:76-84
+            x = t[..., 1, 0]
+            x = torch.where(x.abs() < 1e-10, torch.full_like(x, 1e-10), x)
+            return torch.atan2(t[..., 1, 1], x)
+        th = heading(pred_trajs.float()) + heading(gt_trajs.float())[:, None]          # [S, M]: rotation added by mode p's two calls
+        before = (torch.cumsum(th, dim=1) - th).reshape(S * M)                          # what mode p's prediction call finds
+        c, sn = torch.cos(before)[:, None], torch.sin(before)[:, None]
+        x, y = pose[..., 0].clone(), pose[..., 1].clone()
+        pose[..., 0], pose[..., 1] = x * c + y * sn, -x * sn + y * c                    # row vector times [[c, -s], [s, c]] (:85-97)
+        if M > 1:                                                                       # zeroed by every earlier call (:141-144)
+            later = (torch.arange(S * M, device=pose.device) % M) > 0
+            hide = [j for j, on in ((4, valuenet.hide_toe), (8, valuenet.hide_toe), (9, valuenet.hide_spine), (10, valuenet.hide_spine),
+                                    (11, valuenet.hide_spine)) if on]
+            for j in hide:
+                pose[later, j] = 0
     was = valuenet.mutate_pose
     valuenet.mutate_pose = False
     try:

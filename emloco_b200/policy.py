@@ -44,17 +44,41 @@ class RunningMeanStd(nn.Module):
         self._f32 = None
 
     def f32(self):
-        """(mean, var) as float32 - `current_var.float()` of running_mean_std.py:78-84 - cached until the stats change."""
-        key = (self.running_mean._version, self.running_var._version, self.running_mean.device)
-        if self._f32 is None or self._f32[0] != key:
-            var = self.running_var.float().contiguous()
-            self._f32 = (key, self.running_mean.float().contiguous(), var, (1.0 / torch.sqrt(var + self.epsilon)).contiguous())
-        return self._f32[1], self._f32[2]
+        """(mean, var) as float32 - `current_var.float()` of running_mean_std.py:78-84.  The three fp32 copies (mean, var,
+        1/sqrt(var+eps)) live in buffers of fixed address that are REFRESHED IN PLACE when the statistics change - by an
+        in-place update (`_version`) or by attribute re-assignment, which is how the reference updates them
+        (running_mean_std.py:93-96: fresh tensors, `_version` 0 again, hence `data_ptr` in the key).  Kernels captured in a
+        CUDA graph therefore read current statistics after `refresh()` / `Rollout.sync_weights()`."""
+        m, v = self.running_mean, self.running_var
+        key = (m.data_ptr(), m._version, v.data_ptr(), v._version)
+        c = self._f32
+        if c is None or c[1].device != m.device or c[1].shape != m.shape:
+            var = v.float().contiguous()
+            c = self._f32 = [key, m.float().contiguous(), var, (1.0 / torch.sqrt(var + self.epsilon)).contiguous()]
+        elif c[0] != key:
+            c[1].copy_(m); c[2].copy_(v)
+            torch.rsqrt(c[2] + self.epsilon, out=c[3])
+            c[0] = key
+        return c[1], c[2]
+
+    refresh = f32
 
     def inv_std(self):
         """1/sqrt(var + eps) as float32, for the kernels that multiply instead of dividing (post-step operand sinks)."""
         self.f32()
         return self._f32[3]
+
+    def update(self, x):
+        """Training-mode moment update of RunningMeanStd.forward (utils/running_mean_std.py:86-96 ->
+        _update_mean_var_count_from_moments :33-43) in float64, written IN PLACE.  x [B, size] (any float dtype, same device)."""
+        x = x.reshape(-1, self.running_mean.numel() if self.running_mean.dim() else 1)
+        b = x.shape[0]
+        mean, var = x.mean(0).reshape(self.running_mean.shape), x.var(0).reshape(self.running_var.shape)
+        delta = mean - self.running_mean                       # type promotion as in the reference: batch moments stay in the
+        tot = self.count + b                                   # input's dtype until they meet the float64 buffers
+        new_mean = self.running_mean + delta * b / tot
+        m2 = self.running_var * self.count + var * b + delta ** 2 * self.count * b / tot
+        self.running_mean.copy_(new_mean); self.running_var.copy_(m2 / tot); self.count.copy_(tot)
 
 
 class AMPSeptValueNetwork(nn.Module):
@@ -152,13 +176,53 @@ class RolloutNets:
             self.w16 = _TcWeights()
 
     def _w_ac1(self):
+        """Actor and critic first layers stacked into one [2*h, 624] weight (buffers of fixed address, refreshed in place)."""
         n = self.net
         ps = (n.actor_mlp[0].weight, n.actor_mlp[0].bias, n.critic_mlp[0].weight, n.critic_mlp[0].bias)
         key = tuple((p.data_ptr(), p._version) for p in ps)
-        if self._stacked is None or self._stacked[0] != key:
-            self._stacked = (key, torch.cat([ps[0].detach(), ps[2].detach()]).contiguous(),
-                             torch.cat([ps[1].detach(), ps[3].detach()]).contiguous())
-        return self._stacked[1], self._stacked[2]
+        c = self._stacked
+        if c is None or c[1].device != ps[0].device:
+            c = self._stacked = [key, torch.cat([ps[0].detach(), ps[2].detach()]).contiguous(),
+                                 torch.cat([ps[1].detach(), ps[3].detach()]).contiguous()]
+        elif c[0] != key:
+            h = ps[0].shape[0]
+            c[1][:h].copy_(ps[0].detach()); c[1][h:].copy_(ps[2].detach())
+            c[2][:h].copy_(ps[1].detach()); c[2][h:].copy_(ps[3].detach())
+            c[0] = key
+        return c[1], c[2]
+
+    def sync_weights(self):
+        """Brings every derived copy the kernels read up to date with the parameters and normaliser statistics, IN PLACE (same
+        device addresses): fp32 normaliser copies, the stacked actor / critic first layer, the bf16 hi / lo weight splits.
+        Python does not run when a CUDA graph replays, so `Rollout` calls this eagerly before every horizon; afterwards the
+        captured kernels read the new values through the old pointers.  -> True when a buffer had to be re-allocated (the
+        caller must then drop its graphs)."""
+        n = self.net
+        self.obs_norm.f32(); self.amp_norm.f32()
+        w, _ = self._w_ac1()
+        if not self.tc:
+            return False
+        gen = self.w16.generation
+        W = self.w16.get
+        W("t0", n._task_mlp[0].weight); W("t2", n._task_mlp[2].weight); W("ac1", w); W("a2", n.actor_mlp[2].weight)
+        W("mu", n.mu.weight); W("c2", n.critic_mlp[2].weight); W("c0", n.critic_mlp[0].weight)
+        W("d0", n._disc_mlp[0].weight); W("d2", n._disc_mlp[2].weight)
+        return self.w16.generation != gen
+
+    def pointer_fingerprint(self):
+        """Addresses of everything a captured graph reads through a baked-in pointer (parameters used directly by the kernels,
+        derived copies).  A change means the graphs are stale and must be re-captured."""
+        n = self.net
+        direct = [n.sigma, n.value.weight, n.value.bias, n._disc_logits.weight, n._disc_logits.bias, n.mu.bias,
+                  n._value_logits.weight, n._value_logits.bias] + [p for m in (n._task_value_mlp, n._task_mlp, n.actor_mlp, n.critic_mlp,
+                                                                                 n._disc_mlp) for p in m.parameters()]
+        fp = [p.data_ptr() for p in direct]
+        fp += [t.data_ptr() for t in (self.obs_norm._f32 or [None])[1:]] + [t.data_ptr() for t in (self.amp_norm._f32 or [None])[1:]]
+        if self._stacked is not None:
+            fp += [self._stacked[1].data_ptr(), self._stacked[2].data_ptr()]
+        if self.tc:
+            fp.append(self.w16.generation)
+        return tuple(fp)
 
     def post_sinks(self, obs_copy=None, amp_copy=None, slot=0, flip_copy=None, rows_only=False):
         """emloco_post_sinks pointing at this object's operand buffers (tensor-core path) plus the given experience rows.
@@ -398,20 +462,31 @@ def linear_bf16x3(a: _Split, w: _Split, bias, relu, y32=None, y16: _Split = None
 
 
 class _TcWeights:
-    """bf16 hi/lo copies of the nn.Linear weights, rebuilt when a parameter changes (optimizer step / load_state_dict)."""
+    """bf16 hi/lo copies of the nn.Linear weights.  When a parameter changes (optimizer step / load_state_dict) the split is
+    redone INTO THE SAME BUFFERS, so pointers captured in a CUDA graph stay valid; `generation` counts re-allocations (shape or
+    device change) - the only event that invalidates a graph."""
 
     def __init__(self):
         self._c = {}
+        self.generation = 0
 
     def get(self, name, weight):
         key = (weight.data_ptr(), weight._version)
         ent = self._c.get(name)
-        if ent is None or ent[0] != key:
-            w = weight.detach().float().contiguous()
-            sp = _Split(w.shape[0], w.shape[1], w.device)
-            split_bf16(w, sp)
-            self._c[name] = ent = (key, sp)
-        return ent[1]
+        if ent is not None and ent[0] == key:
+            return ent[1]
+        w = weight.detach()
+        if w.dtype != torch.float32 or not w.is_contiguous():
+            w = w.float().contiguous()
+        if ent is not None and (ent[1].rows, ent[1].K) == tuple(w.shape) and ent[1].hi.device == w.device:
+            split_bf16(w, ent[1])
+            ent[0] = key
+            return ent[1]
+        sp = _Split(w.shape[0], w.shape[1], w.device)
+        split_bf16(w, sp)
+        self._c[name] = [key, sp]
+        self.generation += 1
+        return sp
 
 
 # ---- thin wrappers over the stateless C entry points -------------------------------------------------------

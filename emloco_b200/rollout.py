@@ -115,12 +115,27 @@ class Rollout:
         self.noise = f(N, ACTIONS)
         self.rcfg = _lib.RolloutCfg(inversion_penalty_scale, 1.0, 0.0, 1.0, disc_reward_scale, gamma, step_to_pred,
                                     int(bool(normalize_value)))
-        self._refresh_value_norm()
+        # value_mean_std as the record kernels read it: {mean, sqrt(var + eps)} in a device buffer of fixed address
+        self.value_stats = f(2)
+        self.rcfg.d_value_stats = self.value_stats.data_ptr()
+        self._fingerprint = None
+        self.sync_weights()
         self.launches_per_step = 0
 
-    def _refresh_value_norm(self):
-        self.rcfg.value_mean = float(self.value_norm.running_mean.float().item())
-        self.rcfg.value_std = float(torch.sqrt(self.value_norm.running_var.float() + self.value_norm.epsilon).item())
+    def sync_weights(self):
+        """Call after the parameters or any normaliser changed (optimiser step, load_state_dict, running-statistics update):
+        refreshes, in place, every derived buffer the kernels read - bf16 weight splits, stacked first layer, fp32 normaliser
+        copies and the value un-normalisation constants (`value_mean_std(value, True)`, common_agent.py:653-654).  `play_steps`
+        and step 0 of the graphed paths call it themselves, so a captured CUDA graph never replays on stale numbers; if a
+        parameter or buffer was re-allocated (its address changed) the graphs are dropped and captured again."""
+        vn = self.value_norm
+        self.value_stats[0:1].copy_(vn.running_mean.reshape(-1)[:1])
+        self.value_stats[1:2].copy_(torch.sqrt(vn.running_var.reshape(-1)[:1].float() + vn.epsilon))
+        realloc = self.nets.sync_weights()
+        fp = self.nets.pointer_fingerprint() + (self.value_stats.data_ptr(), self.valuenet._weights().data_ptr())
+        if realloc or fp != self._fingerprint:
+            self._graphs.clear()
+            self._fingerprint = fp
 
     @property
     def SEGMENTS(self):
@@ -267,6 +282,8 @@ class Rollout:
 
     def step(self, n, noise=None, host_obs=False):
         """host_obs: the caller overwrote sim.obs (host-provided observations): operands are re-derived from it."""
+        if n == 0 and not torch.cuda.is_current_stream_capturing():
+            self.sync_weights()
         self._warmed = True
         for f in self._segment_fns(n, noise, host_obs):
             self._mark()
@@ -333,6 +350,8 @@ class Rollout:
     def step_graphed(self, n):
         """Same work as step(n) replayed from a CUDA graph (captured on first use; run a few eager steps first so that
         every lazy one-time initialisation - constant tables, weight splits, function attributes - has happened)."""
+        if n == 0:
+            self.sync_weights()
         if not self._warmed:          # the very first step runs eagerly: one-time initialisations must not land in a capture
             self.step(n)
             return
@@ -342,6 +361,8 @@ class Rollout:
         """step(n) on observations and policy noise the caller put into sim.obs / self.noise (no generator call in the graph).
         after_env_step: called between the env step (reset .. post_step) and the critic / discriminator / bookkeeping part, so
         that a vec-env style caller can start reading the step's observations back while the rest of the step runs."""
+        if n == 0:
+            self.sync_weights()
         if after_env_step is None:
             self._replay(("hn", n), lambda: self.step(n, noise=self.noise, host_obs=True))
             return
@@ -355,6 +376,8 @@ class Rollout:
         """step(n) as seven per-segment graphs with a timing event between them: per-segment device time without host
         launch gaps inside a segment (used by bench.py for the roofline numbers)."""
         fns = None
+        if n == 0:
+            self.sync_weights()
         for i, name in enumerate(self.SEGMENTS):
             self._mark()
             if ("seg", n, i) not in self._graphs and fns is None:
@@ -369,6 +392,7 @@ class Rollout:
         return self._finish_out
 
     def play_steps(self, graphed=False):
+        self.sync_weights()
         for n in range(self.T):
             (self.step_graphed if graphed else self.step)(n)
         return self.finish_graphed() if graphed else self.finish()

@@ -310,6 +310,9 @@ typedef struct emloco_rollout_cfg {
     float gamma;                     /* 0.99 */
     int32_t step_to_pred;            /* 144 */
     int32_t unnorm_value;            /* normalize_value */
+    const float* d_value_stats;      /* optional device pointer to {mean, std} (fp32): when non-NULL it replaces value_mean /
+                                        value_std and is read by the kernels at run time, so that a value_mean_std update
+                                        (every epoch in the reference, common_agent.py:440-442) reaches a captured CUDA graph */
 } emloco_rollout_cfg;
 int emloco_rollout_record(const emloco_rollout_cfg* cfg, const float* d_rew, const int64_t* d_reset,
                           const int64_t* d_terminate, const float* d_value_raw, const float* d_next_value_raw,

@@ -47,7 +47,8 @@ class CpuRollout:
         self.P, self.D = dict(P), dict(D)
         self.P["mean"], self.P["var"] = obs_stats if obs_stats is not None else (np.zeros(1422), np.ones(1422))
         self.D["mean"], self.D["var"] = amp_stats if amp_stats is not None else (np.zeros(3090), np.ones(3090))
-        self.v_mean, self.v_std = F(value_stats[0]), F(np.sqrt(F(value_stats[1]) + F(1e-5)))
+        self.v_mean, self.v_var = F(value_stats[0]), F(value_stats[1])
+        self.inverted = None      # task.inverted (bool [n]); set by the caller when trajectories can be inverted
         self.gamma, self.disc_scale, self.step_to_pred, self.inv_penalty = F(gamma), disc_scale, step_to_pred, inv_penalty
         self.height = np.zeros((1080, 1080), np.int16)
         self.betas = np.zeros((n, 17), F)
@@ -80,7 +81,10 @@ class CpuRollout:
         self.amp_buf[ids] = out["amp_obs"].reshape(len(ids), 15, 206)[:, :1]      # history := current step
         if self.traj_flags is not None:                                           # _reset_task AFTER the observations (humanoid_amp_task.py:54-57)
             U = self.traj_rng.random((len(ids), O.TRAJ_RAND_COLS)).astype(F)
-            O.traj_reset(self.verts, ids, self.root[ids, 0:3].astype(F), self.root[ids, 7:10].astype(F), U, self.traj_flags, self.traj_pool)
+            inv = O.traj_reset(self.verts, ids, self.root[ids, 0:3].astype(F), self.root[ids, 7:10].astype(F), U, self.traj_flags, self.traj_pool)
+            if self.inverted is None:
+                self.inverted = np.zeros(self.n, bool)
+            self.inverted[ids] = inv                                                  # task.inverted -> inversion penalty (:62-64)
 
     def _post(self, ids, rb, dof_pos, advance):
         ds = np.stack([dof_pos, self.jw[ids]], -1).astype(F)
@@ -103,20 +107,16 @@ class CpuRollout:
         self.reset, self.terminate = out["reset"], out["terminate"]
         nv_raw = O.critic_forward(self.obs, self.P)[:, 0]
         amp_r, logit = O.disc_reward(out["amp_obs"], self.D, self.disc_scale)
-        amp_r = amp_r[:, 0]
-        # :63-118
-        r = out["rew"].astype(F)
-        done = (self.reset != 0).astype(F); term = self.terminate.astype(F)
-        unn = lambda v: self.v_std * np.clip(v, F(-5), F(5)) + self.v_mean
-        values = unn(pol["value"][:, 0]); next_values = unn(nv_raw) * (F(1) - term)
-        st = self.state
-        cr = st[0] + r; ln = st[1] + F(1); coef = st[3].copy()
-        cc = st[2] + (r + amp_r) * coef
-        nd = F(1) - done
-        sel = ((ln <= self.step_to_pred) & (done != 0)) | ((ln == self.step_to_pred) & (nd != 0))
-        st[4] += cc * sel.astype(F); st[2] = cc * nd
-        st[3] = np.where(done != 0, F(1), coef * self.gamma)
-        st[0] = cr * nd; st[1] = ln * nd; st[5] += term
+        # :61-118 (oracle_np.rollout_record; self.state rows: 0 current_rewards, 1 current_lengths, 2 current_combined,
+        # 3 discount, 4 game_combined, 5 terminated_flags)
+        names = ("current_rewards", "current_lengths", "current_combined", "discount", "game_combined", "terminated_flags")
+        d = {k: self.state[i] for i, k in enumerate(names)}
+        rows = O.rollout_record(d, out["rew"], self.reset, self.terminate, nv_raw, logit[:, 0], self.inverted, self.v_mean, self.v_var,
+                                self.inv_penalty, self.disc_scale, self.gamma, self.step_to_pred)
+        for i, k in enumerate(names):
+            self.state[i] = d[k]
+        r, done, next_values = rows["rewards"], rows["dones"], rows["next_values"]
+        values = O.value_unnormalize(pol["value"][:, 0], self.v_mean, self.v_var)
         return dict(obs=obs, actions=pol["actions"], neglogp=pol["neglogp"], mu=pol["mu"], values=values,
-                    task_values=pol["task_value"], rewards=r, dones=done, next_values=next_values, amp_rewards=amp_r,
+                    task_values=pol["task_value"], rewards=r, dones=done, next_values=next_values, amp_rewards=rows["amp_rewards"],
                     next_obs=self.obs, amp_obs=out["amp_obs"], rb=rb, disc_logit=logit)

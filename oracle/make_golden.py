@@ -356,6 +356,190 @@ def reference_traj_reset(N, n_reset, seed, flags, pool_size=7):
                 verts=h._verts.numpy().copy(), inverted=h.inverted.numpy()[env_ids].copy())
 
 
+def synth_state_branches(N, seed):
+    """synth_state on flat terrain with every branch of compute_humanoid_reset populated: contact sums on both sides of the 50 N
+    threshold, progress in the exempt range (<= 1), at the episode limit (>= 167) and in between, and trajectories nearer / farther
+    than the 4 m fail distance - so that alive, time-out-only, fallen and target-lost envs all occur (asserted by the generator)."""
+    st = synth_state(N, seed, map_shape=(700, 700), rough=False)
+    rng = np.random.default_rng(seed + 1000)
+    masked = st["contact"].copy(); masked[:, CONTACT_BODIES] = 0
+    norm = np.linalg.norm(masked.sum(1), axis=-1)
+    want = rng.uniform(0, 100, N)
+    want[: N // 8] = rng.uniform(49.5, 50.5, N // 8)                 # close to the threshold
+    st["contact"] = (st["contact"] * (want / norm)[:, None, None]).astype(np.float32)
+    prog = rng.integers(2, 166, N)
+    k = N // 8
+    prog[0:k] = rng.integers(0, 2, k)                                 # exempt from the contact test
+    prog[k:2 * k] = rng.integers(166, 169, k)                         # 166 alive, 167 / 168 timed out
+    st["progress"] = prog.astype(np.int64)
+    # bodies moved next to the trajectory point of the env's progress (a walker that follows its path), a few left behind
+    tar = O.calc_pos(st["verts"], np.arange(N), O.progress_time(st["progress"]))
+    shift = tar[:, :2] - st["rb"][:, 0, :2] + rng.normal(0, 1.0, (N, 2))
+    far = rng.random(N) < 0.15
+    shift[far] += rng.uniform(3.5, 6.0, (int(far.sum()), 1)) * np.array([[1.0, 0.0]])
+    st["rb"][:, :, 0:2] += shift[:, None, :].astype(np.float32)
+    return st
+
+
+def reference_nets(M=24, seed=21):
+    """a11-a13: the reference's own AMPSeptValueBuilder.Network (ref_extract.load_network) with the synthetic parameters of
+    oracle/netweights.py, driven as the agent drives it: running_mean_std (eval) -> eval_actor / eval_critic / eval_task_value
+    (amp_sept_value_models.py:22-30 -> amp_models.py:20-44), _eval_critic with value un-normalisation (common_agent.py:647-655),
+    _eval_disc / _calc_disc_rewards / _combine_rewards (amp_continuous.py:659-692)."""
+    from . import netweights
+    R = ref_extract.load()
+    torch = R.torch
+    net = ref_extract.load_network()
+    sd = netweights.synth_state_dict(seed)
+    missing = net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    rng = np.random.default_rng(seed)
+    f = np.float32
+    obs = rng.normal(0, 2.0, (M, 1422)).astype(f); obs[:, ::7] *= 4                    # some features beyond the +-5 clamp
+    amp = rng.normal(0, 2.0, (M, 3090)).astype(f); amp[:, ::11] *= 4
+    obs_mean, obs_var = rng.normal(0, 1, 1422), rng.uniform(0.05, 4, 1422)
+    amp_mean, amp_var = rng.normal(0, 1, 3090), rng.uniform(0.05, 4, 3090)
+    v_mean, v_var = np.array([0.7]), np.array([2.3])
+    task_r = rng.uniform(0, 1, (M, 1)).astype(f)
+    import contextlib, io
+    H = ref_extract.load_agent_blocks()
+    h = H()
+    with contextlib.redirect_stdout(io.StringIO()):
+        h.running_mean_std, h._amp_input_mean_std, h.value_mean_std = R.RunningMeanStd((1422,)), R.RunningMeanStd((3090,)), R.RunningMeanStd((1,))
+    for m, (mu_, var_) in ((h.running_mean_std, (obs_mean, obs_var)), (h._amp_input_mean_std, (amp_mean, amp_var)),
+                           (h.value_mean_std, (v_mean, v_var))):
+        m.running_mean[:] = torch.from_numpy(mu_); m.running_var[:] = torch.from_numpy(var_); m.eval()
+    import types
+    h.model = types.SimpleNamespace(a2c_network=net, eval=lambda: None)
+    h.normalize_input = h.normalize_value = h._normalize_amp_input = True
+    h._disc_reward_mean_std = None; h.ppo_device = "cpu"; h._disc_reward_scale = 2.0
+    h._task_reward_w = h._disc_reward_w = 0.5
+    with torch.no_grad():
+        x = h._preproc_obs(torch.from_numpy(obs))
+        mu, sigma = net.eval_actor(x)
+        value = net.eval_critic(x)
+        tv = net.eval_task_value(x)
+        next_value = h._eval_critic({"obs": torch.from_numpy(obs)})
+        logit = h._eval_disc(torch.from_numpy(amp))
+        amp_r = h._calc_amp_rewards(torch.from_numpy(amp))
+        comb = h._combine_rewards(torch.from_numpy(task_r), amp_r)
+    return dict(seed=seed, weights_checksum=netweights.checksum(sd), obs=obs, amp_obs=amp, obs_mean=obs_mean, obs_var=obs_var,
+                amp_mean=amp_mean, amp_var=amp_var, value_mean=v_mean, value_var=v_var, task_rewards=task_r,
+                out_mu=mu.numpy(), out_sigma=sigma.numpy(), out_value=value.numpy(), out_task_value=tv.numpy(),
+                out_next_value_unnorm=next_value.numpy(), out_disc_logit=logit.numpy(), out_disc_reward=amp_r["disc_rewards"].numpy(),
+                out_combined=comb.numpy())
+
+
+def reference_play_block(N=96, steps=8, seed=31):
+    """a14 (+ the reward / value plumbing around it): the body of the horizon loop of AMPValueAgent.play_steps from env_step to the
+    end of the no_grad block (amp_continuous_value.py:61-121, incl. the inversion penalty :62-64 and next_vals *= 1-terminated
+    :87-89) run `steps` times on a holder whose env, critic and discriminator return recorded tensors (the networks themselves
+    are pinned by nets.npz).  State after every step and the rows written to the experience buffer are the fixture."""
+    import types
+    R = ref_extract.load()
+    torch = R.torch
+    rng = np.random.default_rng(seed)
+    f = np.float32
+    H = ref_extract.load_agent_blocks()
+    h = H()
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        h.value_mean_std = R.RunningMeanStd((1,))
+    v_mean, v_var = 0.4, 1.7
+    h.value_mean_std.running_mean[:] = v_mean; h.value_mean_std.running_var[:] = v_var; h.value_mean_std.eval()
+    inverted = rng.random(N) < 0.3
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    rec = {}
+    cur = {}
+    h.vec_env = types.SimpleNamespace(env=types.SimpleNamespace(task=types.SimpleNamespace(inverted=T(inverted), viewer=None)))
+    h.env_step = lambda actions: (dict(obs=cur["obs"]), cur["rew"].clone(), cur["dones"], cur["infos"])
+    h.inversion_penalty_scale = 0.3
+    h.rewards_shaper = lambda r: r * 1.0                                # rl_games DefaultRewardsShaper(scale_value=1)
+    h.experience_buffer = types.SimpleNamespace(update_data=lambda k, n, v: rec.setdefault(k, []).append(v.clone().numpy()))
+    h.motion_sym_loss = True
+    h.normalize_input = False; h.normalize_value = True; h._normalize_amp_input = False
+    h.running_mean_std = None
+    h._preproc_obs = lambda o: o
+    h.model = types.SimpleNamespace(eval=lambda: None, a2c_network=types.SimpleNamespace(
+        eval_critic=lambda o: cur["critic_raw"].clone(), eval_disc=lambda a: cur["logit"].clone()))
+    h._disc_reward_mean_std = None; h.ppo_device = "cpu"; h._disc_reward_scale = 2.0
+    h.num_agents = 1; h.gamma = 0.99; h.step_to_pred = 144
+    h.game_rewards = h.game_lengths = types.SimpleNamespace(update=lambda x: None)
+    h.algo_observer = types.SimpleNamespace(process_infos=lambda i, d: None)
+    # state as CommonAgent.init_tensors leaves it (common_agent.py:137-141), lengths moved close to step_to_pred
+    len0 = rng.integers(0, 150, N).astype(f); len0[:12] = 143; len0[12:20] = 144; len0[20:26] = 142
+    h.current_rewards = T(rng.normal(0, 5, (N, 1)).astype(f)); h.current_lengths = T(len0.copy())
+    h.current_combined_rewards = T(rng.normal(0, 5, N).astype(f)); h.game_combined_rewards = torch.zeros(N)
+    h.discount_coefs = T((0.99 ** len0).astype(f))
+    state0 = dict(current_rewards=h.current_rewards.numpy().copy(), current_lengths=len0.copy(),
+                  current_combined=h.current_combined_rewards.numpy().copy(), discount=h.discount_coefs.numpy().copy())
+    ins = dict(rew=[], reset=[], terminate=[], critic_raw=[], logit=[])
+    outs = dict(game_combined=[], current_combined=[], discount=[], current_lengths=[], current_rewards=[], terminated_flags=[])
+    tf, rr = torch.zeros(N), torch.zeros(1)
+    for n in range(steps):
+        term = rng.random(N) < 0.08
+        reset = term | (rng.random(N) < 0.08)
+        if n == 1:
+            reset[:16] = [True, False] * 8; term[:16] = False
+        cur.update(obs=torch.zeros(N, 1), rew=T(rng.uniform(-0.2, 1.0, (N, 1)).astype(f)), dones=T(reset.astype(np.int64)),
+                   critic_raw=T(rng.normal(0, 3, (N, 1)).astype(f)), logit=T(rng.normal(0, 4, (N, 1)).astype(f)))
+        cur["logit"][:3, 0] = torch.tensor([12.0, -12.0, 9.3])                      # the 1e-4 floor of the log (:683-685)
+        cur["infos"] = dict(amp_obs=torch.zeros(N, 1), flip_obs=torch.zeros(N, 1), terminate=T(term.astype(np.int64)),
+                            reward_raw=torch.zeros(N, 2))
+        for k in ins:
+            src = dict(rew=cur["rew"], reset=cur["dones"], terminate=cur["infos"]["terminate"], critic_raw=cur["critic_raw"], logit=cur["logit"])[k]
+            ins[k].append(src.numpy().copy())
+        with torch.no_grad():
+            loc = h.play_block(n, dict(actions=None), tf, rr)
+        outs["game_combined"].append(h.game_combined_rewards.numpy().copy()); outs["current_combined"].append(h.current_combined_rewards.numpy().copy())
+        outs["discount"].append(h.discount_coefs.numpy().copy()); outs["current_lengths"].append(h.current_lengths.numpy().copy())
+        outs["current_rewards"].append(h.current_rewards.numpy().copy()); outs["terminated_flags"].append(tf.numpy().copy())
+        rec.setdefault("amp_rewards", []).append(loc["amp_rewards"].numpy().copy())
+        if n == 4:                                                                  # what the finetune block does after consuming them (:145)
+            h.game_combined_rewards = torch.zeros(N)
+    out = dict(N=N, steps=steps, inverted=inverted, value_mean=f(v_mean), value_var=f(v_var), zero_game_after_step=4,
+               **{f"state0_{k}": v for k, v in state0.items()}, **{f"in_{k}": np.stack(v) for k, v in ins.items()},
+               **{f"out_{k}": np.stack(v) for k, v in outs.items()})
+    for k in ("rewards", "dones", "next_values", "amp_rewards"):
+        out[f"row_{k}"] = np.stack(rec[k])
+    return out
+
+
+def reference_rms_update(seed=51):
+    """RunningMeanStd in training mode (utils/running_mean_std.py:86-96): statistics after each of three batches."""
+    R = ref_extract.load()
+    torch = R.torch
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = R.RunningMeanStd((7,))
+    m.train()
+    rng = np.random.default_rng(seed)
+    out = {}
+    for i, b in enumerate((16, 5, 64)):
+        x = (rng.normal(0, 1 + i, (b, 7)) + i).astype(np.float32)
+        m(torch.from_numpy(x))
+        out.update({f"x{i}": x, f"mean{i}": m.running_mean.numpy().copy(), f"var{i}": m.running_var.numpy().copy(),
+                    f"count{i}": np.asarray(m.count.numpy()).copy()})
+    return out
+
+
+def reference_plausibl(B=40, seed=41):
+    """a17: plausibl/test_value_mlp.py:24-113 `MLP` (24 -> 12 -> 6 -> 1, no sigmoid), biases randomised."""
+    R = ref_extract.load()
+    torch = R.torch
+    MLP = ref_extract.load_plausibl_mlp()
+    torch.manual_seed(seed)
+    m = MLP()
+    with torch.no_grad():
+        for lay in (m._value_mlp[0], m._value_mlp[2], m._value_logits):
+            lay.bias.uniform_(-0.3, 0.3)
+    x = np.random.default_rng(seed).normal(0, 2, (B, 24)).astype(np.float32)
+    with torch.no_grad():
+        y = m.forward(torch.from_numpy(x)).numpy()
+    sd = {f"_value_mlp.{k}": v.numpy().copy() for k, v in m._value_mlp.state_dict().items()}
+    sd.update({f"_value_logits.{k}": v.numpy().copy() for k, v in m._value_logits.state_dict().items()})
+    return dict(x=x, y=y, **{f"w_{k}": v for k, v in sd.items()})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     for name, fl in (("traj_reset_plain", 0), ("traj_reset_train", O.TRAJ_F_REAL | O.TRAJ_F_ADJUST_VEL | O.TRAJ_F_INIT_HEADING),
@@ -369,6 +553,22 @@ def main():
         np.savez_compressed(os.path.join(OUT, f"{name}.npz"), seed=seed, N=N, rough=rough,
                             **{f"in_{k}": v for k, v in st.items()}, **{f"out_{k}": v for k, v in out.items()})
         print(name, {k: v.shape for k, v in out.items()})
+    # every (reset, terminate) branch of compute_humanoid_reset at 256 envs; inputs are regenerated from the seed by the tests
+    # (synth_state_branches), the fixture holds the reference outputs (AMP ring: only the new step - the rest is a shifted copy)
+    st = synth_state_branches(256, 7)
+    out = reference_post_step(st)
+    fallen_only = (out["terminate"] == 1) & (((out["tar_pos"][:, :2] - st["rb"][:, 0, :2]) ** 2).sum(-1) <= 16)
+    lost_only = (out["terminate"] == 1) & ~fallen_only
+    combos = {(int(a), int(b)) for a, b in zip(out["reset"], out["terminate"])}
+    assert combos == {(0, 0), (1, 0), (1, 1)} and fallen_only.sum() > 20 and lost_only.sum() > 5 and ((out['reset'] == 1) & (out['terminate'] == 0)).sum() > 5, (combos, fallen_only.sum(), lost_only.sum())
+    assert ((st["progress"] <= 1) & (out["terminate"] == 0)).sum() > 10
+    out["amp_obs"] = out["amp_obs"][:, :AMP_STEP_DIM].copy()
+    np.savez_compressed(os.path.join(OUT, "post_step_branches.npz"), seed=7, N=256, **{f"out_{k}": v for k, v in out.items()})
+    print("post_step_branches", sorted(combos), int(fallen_only.sum()), int(lost_only.sum()))
+    np.savez_compressed(os.path.join(OUT, "nets.npz"), **reference_nets())
+    np.savez_compressed(os.path.join(OUT, "play_block.npz"), **reference_play_block())
+    np.savez_compressed(os.path.join(OUT, "plausibl.npz"), **reference_plausibl())
+    np.savez_compressed(os.path.join(OUT, "rms_update.npz"), **reference_rms_update())
     traj, pose, vel = synth_locoval(64, 2)
     W, out = reference_locoval(traj, pose, vel)
     np.savez_compressed(os.path.join(OUT, "locoval.npz"), traj=traj, pose=pose, vel=vel,

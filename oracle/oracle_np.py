@@ -559,6 +559,45 @@ def disc_reward(amp_obs, D, scale=2.0):
 
 
 # ----------------------------------------------------------------------------------------
+# a12-a14: per-step reward / value plumbing and the LocoVal-target bookkeeping
+# ----------------------------------------------------------------------------------------
+def value_unnormalize(v, mean, var, eps=1e-5):
+    """RunningMeanStd.forward(unnorm=True), utils/running_mean_std.py:78-80: sqrt(var + eps) * clamp(v, +-5) + mean."""
+    return (np.sqrt(F(var) + F(eps)) * np.clip(v, F(-5), F(5)) + F(mean)).astype(F)
+
+
+def rollout_record(st, rew, reset, terminate, next_value_raw, logit, inverted=None, value_mean=0.0, value_var=1.0,
+                   inv_penalty=0.3, disc_scale=2.0, gamma=0.99, step_to_pred=144):
+    """The body of the horizon loop of AMPValueAgent.play_steps after env_step (learning/amp_continuous_value.py:61-118).
+    st: dict of float32 [N] arrays current_rewards, current_lengths, current_combined, discount, game_combined,
+    terminated_flags (updated in place).  rew [N] task reward of the env step, reset / terminate int64 [N], next_value_raw [N]
+    critic(next obs) before un-normalisation, logit [N] discriminator logit, inverted bool [N] or None.
+    Returns the rows written to the experience buffer: rewards, dones, next_values, amp_rewards (all [N])."""
+    r = rew.astype(F).copy()
+    if inverted is not None:
+        r[inverted.astype(bool)] *= F(-inv_penalty)                                            # :62-64
+    shaped = r * F(1.0)                                                                        # rewards_shaper, scale_value 1
+    term = terminate.astype(F)
+    st["terminated_flags"] += term                                                             # :76-77
+    next_values = value_unnormalize(next_value_raw, value_mean, value_var) * (F(1) - term)     # :87-89
+    prob = F(1) / (F(1) + np.exp(-logit.astype(F)))
+    amp_r = (-np.log(np.maximum(F(1) - prob, F(0.0001))) * F(disc_scale)).astype(F)            # amp_continuous.py:675-692
+    done = (reset != 0).astype(F)
+    nd = F(1) - done
+    st["current_rewards"] = st["current_rewards"] + r                                          # :94
+    st["current_lengths"] = st["current_lengths"] + F(1)
+    st["current_combined"] = st["current_combined"] + (shaped + amp_r) * st["discount"]        # :96-97
+    ln = st["current_lengths"]
+    sel = ((ln <= step_to_pred) & (done != 0)) | ((ln == step_to_pred) & (nd != 0))            # :106-107
+    st["game_combined"] = st["game_combined"] + st["current_combined"] * sel.astype(F)         # :109
+    st["current_combined"] = st["current_combined"] * nd                                       # :113
+    st["discount"] = np.where(done != 0, F(1), st["discount"] * F(gamma)).astype(F)            # :114-116
+    st["current_rewards"] = st["current_rewards"] * nd                                         # :117-118
+    st["current_lengths"] = st["current_lengths"] * nd
+    return dict(rewards=shaped, dones=done, next_values=next_values, amp_rewards=amp_r)
+
+
+# ----------------------------------------------------------------------------------------
 # a15: GAE
 # ----------------------------------------------------------------------------------------
 def discount_values(fdones, values, rewards, next_values, gamma=0.99, tau=0.95):

@@ -133,3 +133,143 @@ def load():
     )
     _cache["ns"] = ns
     return ns
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The reference's own network classes (learning/network_builder.py -> amp_network_builder.py -> amp_network_sept_builder.py
+# -> amp_network_sept_value_builder.py).  They import rl_games (rl-games==1.1.4, pinned in pacer/requirements.txt, NOT vendored
+# and not installed): the five names they touch at import / build time are stubbed below - an object factory (a dict of
+# builders) and four symbols that are only referenced by branches the default cfg never takes (noisy dense, D2RL, SAC, conv).
+# The network arithmetic that runs is the reference's.
+# ------------------------------------------------------------------------------------------------------------------
+def _stub_rl_games():
+    if "rl_games" in sys.modules and getattr(sys.modules["rl_games"], "_emloco_stub", False):
+        return
+    import torch
+
+    def pkg(name):
+        m = types.ModuleType(name)
+        m.__path__ = []
+        sys.modules[name] = m
+        return m
+
+    rl = pkg("rl_games"); rl._emloco_stub = True
+    common = pkg("rl_games.common"); algos = pkg("rl_games.algos_torch")
+    rl.common, rl.algos_torch = common, algos
+
+    of = types.ModuleType("rl_games.common.object_factory")
+
+    class ObjectFactory:                       # rl_games/common/object_factory.py (1.1.4): name -> builder(**kwargs)
+        def __init__(self):
+            self._builders = {}
+
+        def register_builder(self, name, builder):
+            self._builders[name] = builder
+
+        def set_builders(self, builders):
+            self._builders = builders
+
+        def create(self, name, **kwargs):
+            builder = self._builders.get(name)
+            if not builder:
+                raise ValueError(name)
+            return builder(**kwargs)
+
+    of.ObjectFactory = ObjectFactory
+    sys.modules["rl_games.common.object_factory"] = of
+    common.object_factory = of
+    for sub, names in (("torch_ext", ()), ("layers", ()), ("d2rl", ("D2RLNet",)), ("sac_helper", ("SquashedNormal",))):
+        m = types.ModuleType(f"rl_games.algos_torch.{sub}")
+        for n in names:
+            setattr(m, n, type(n, (), {}))
+        sys.modules[f"rl_games.algos_torch.{sub}"] = m
+        setattr(algos, sub, m)
+
+
+def network_params():
+    """The `params.network` tree of data/cfg/train/rlg/amp_humanoid_smpl_sept_task.yaml (read from the reference at run time)."""
+    import yaml
+    with open(os.path.join(PACER, "data/cfg/train/rlg/amp_humanoid_smpl_sept_task.yaml")) as f:
+        return yaml.safe_load(f)["params"]["network"]
+
+
+def load_network(seed=0, randomize_bias=True):
+    """AMPSeptValueBuilder.Network built exactly as `AMPAgent._build_net_config` + `ModelAMPContinuous.build` do for the default
+    task (amp_continuous.py:500-510, common_agent.py:56-63,611-619): obs 1422 = 368 + 1054 (traj 30 + heightmap 1024), AMP obs 3090,
+    69 actions.  randomize_bias: the reference zeroes every bias at construction; the fixtures use non-zero ones so that the
+    tests are not blind to them."""
+    if ("net", seed, randomize_bias) in _cache:
+        return _cache[("net", seed, randomize_bias)]
+    R = load()
+    torch = R.torch
+    _stub_rl_games()
+    learning = types.ModuleType("learning")
+    learning.__path__ = [os.path.join(PACER, "learning")]
+    sys.modules["learning"] = learning
+    import importlib
+    importlib.import_module("learning.network_builder")
+    mod = importlib.import_module("learning.amp_network_sept_value_builder")
+    import contextlib, io
+    torch.manual_seed(seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        mean_std = R.RunningMeanStd((1422,))
+        builder = mod.AMPSeptValueBuilder()
+        builder.load(network_params())
+        net = builder.build("amp", actions_num=69, input_shape=(1422,), num_seqs=1, value_size=1, amp_input_shape=(3090,),
+                            self_obs_size=368, task_obs_size=1054, task_obs_size_detail={"traj": 30, "heightmap": 1024},
+                            mean_std=mean_std)
+    if randomize_bias:
+        with torch.no_grad():
+            for m in net.modules():
+                if isinstance(m, torch.nn.Linear):
+                    m.bias.uniform_(-0.1, 0.1)
+    net.eval()
+    _cache[("net", seed, randomize_bias)] = net
+    return net
+
+
+def load_agent_blocks():
+    """Pieces of the agent classes re-hosted on a holder (the enclosing modules import rl_games / isaacgym / tensorboardX):
+      * AMPAgent._preproc_obs (learning/amp_continuous.py:322-333),
+      * AMPAgent._preproc_amp_obs / _combine_rewards / _eval_disc / _calc_amp_rewards / _calc_disc_rewards
+        (learning/amp_continuous.py:651-693),
+      * CommonAgent._eval_critic, _actor_loss, _critic_loss, _calc_advs, bound_loss (learning/common_agent.py:594-602,647-696),
+      * AMPAgent._disc_loss .. _compute_disc_acc (learning/amp_continuous.py:536-616), _sym_loss (:517-534),
+      * AMPValueAgent._task_value_loss (learning/amp_continuous_value.py:430-444),
+      * the per-step body of AMPValueAgent.play_steps from env_step to the end of the no_grad block
+        (learning/amp_continuous_value.py:61-121) as `Holder.play_block(self)`."""
+    if "agent" in _cache:
+        return _cache["agent"]
+    load()
+    ac = os.path.join(PACER, "learning/amp_continuous.py")
+    ca = os.path.join(PACER, "learning/common_agent.py")
+    av = os.path.join(PACER, "learning/amp_continuous_value.py")
+    src = "import torch\nimport numpy as np\nfrom torch import nn\n\nclass Holder:\n"
+    src += _lines(ac, 322, 333) + "\n" + _lines(ac, 517, 616) + "\n" + _lines(ac, 651, 693) + "\n"
+    src += _lines(ca, 594, 602) + "\n" + _lines(ca, 647, 696) + "\n"
+    src += _lines(av, 430, 444) + "\n"
+    # locals of play_steps that the block reads (n, res_dict, terminated_flags, reward_raw) become arguments; its locals are returned
+    src += ("    def play_block(self, n, res_dict, terminated_flags, reward_raw):\n"
+            + textwrap.indent(textwrap.dedent(_lines(av, 61, 121)), " " * 8) + "\n        return locals()\n")
+    tmp = tempfile.mkdtemp(prefix="emloco_ref_")
+    p = os.path.join(tmp, "emloco_ref_agent.py")
+    with open(p, "w") as f:
+        f.write(src)
+    mod = _import_path("emloco_ref_agent", p)
+    _cache["agent"] = mod.Holder
+    return mod.Holder
+
+
+def load_plausibl_mlp():
+    """plausibl/test_value_mlp.py:24-113 `class MLP` (the script's imports point at a developer's home directory)."""
+    if "plausibl" in _cache:
+        return _cache["plausibl"]
+    load()
+    src = "import torch\nimport torch.nn as nn\n\n" + _lines(os.path.join(REF, "plausibl/test_value_mlp.py"), 24, 113)
+    tmp = tempfile.mkdtemp(prefix="emloco_ref_")
+    p = os.path.join(tmp, "emloco_ref_plausibl.py")
+    with open(p, "w") as f:
+        f.write(src)
+    mod = _import_path("emloco_ref_plausibl", p)
+    _cache["plausibl"] = mod.MLP
+    return mod.MLP

@@ -120,3 +120,38 @@ def test_reference_yaml_maps_onto_our_defaults():
     assert k["traj"] == dict(speed_min=0.0005, speed_max=3.0, accel_max=2.0, sharp_turn_prob=0.02, hybrid_init_prob=0.5)
     with __import__("pytest").raises(ValueError):
         kwargs_from_reference_cfg(env_cfg, train_cfg, dict(pred_path=True))
+
+
+def test_running_mean_std_fp32_copies_follow_every_kind_of_update():
+    """the fp32 copies the kernels read must follow in-place updates AND attribute re-assignment (fresh
+    tensors whose _version is 0 again, the reference's way: utils/running_mean_std.py:93-96), at a fixed address."""
+    import torch
+    from emloco_b200.policy import RunningMeanStd
+    m = RunningMeanStd(5)
+    mean, var = m.f32()
+    ptrs = (mean.data_ptr(), var.data_ptr(), m.inv_std().data_ptr())
+    m.running_mean.add_(1.0)
+    assert torch.equal(m.f32()[0], torch.ones(5))
+    for k in (2.0, 3.0):
+        m.running_mean = torch.full((5,), k, dtype=torch.float64)
+        m.running_var = torch.full((5,), k * k, dtype=torch.float64)
+        mean, var = m.f32()
+        assert torch.equal(mean, torch.full((5,), k)) and torch.equal(var, torch.full((5,), k * k))
+        torch.testing.assert_close(m.inv_std(), torch.full((5,), 1.0 / (k * k + 1e-5) ** 0.5))
+    assert ptrs == (mean.data_ptr(), var.data_ptr(), m.inv_std().data_ptr())
+
+
+def test_running_mean_std_update_matches_reference_golden():
+    """RunningMeanStd.update against the reference's training-mode forward (utils/running_mean_std.py:86-96), three batches."""
+    import os
+    import numpy as np
+    import torch
+    from conftest import GOLDEN
+    from emloco_b200.policy import RunningMeanStd
+    g = np.load(os.path.join(GOLDEN, "rms_update.npz"))
+    m = RunningMeanStd(g["x0"].shape[1])
+    for i in range(3):
+        m.update(torch.from_numpy(g[f"x{i}"]))
+        np.testing.assert_allclose(m.running_mean.numpy(), g[f"mean{i}"], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(m.running_var.numpy(), g[f"var{i}"], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(m.count.numpy(), g[f"count{i}"])

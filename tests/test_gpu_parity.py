@@ -545,3 +545,126 @@ def test_linear_bf16x3_split_k_and_sample_actions_parts(tile):
     assert torch.equal(a1, a2) and torch.allclose(n1, n2, rtol=1e-5, atol=1e-4)
     with pytest.raises(Exception):
         linear_bf16x3(sx, sw, T(b), True, y32=parts[0], tile=tile, splits=S)           # ReLU cannot be split
+
+
+# ---- round 2: fixtures generated from the reference's own network / agent / plausibl classes ---------------------------
+def _golden_net(seed):
+    """AMPSeptValueNetwork carrying the synthetic parameters the reference network was run with (oracle/netweights.py)."""
+    from emloco_b200.policy import AMPSeptValueNetwork
+    from oracle import netweights
+    sd = netweights.synth_state_dict(seed)
+    net = AMPSeptValueNetwork()
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    return net.cuda(), sd
+
+
+@pytest.mark.parametrize("tc", [False, True])
+def test_networks_match_reference_network_golden(tc):
+    """a11-a13 against AMPSeptValueBuilder.Network + the agent's _eval_critic / _calc_disc_rewards / _combine_rewards run
+    from the reference tree (tests/golden/nets.npz), FMA and tcgen05 back ends."""
+    from emloco_b200.policy import RolloutNets, RunningMeanStd, disc_reward
+    from oracle import netweights
+    g = np.load(os.path.join(GOLDEN, "nets.npz"))
+    net, sd = _golden_net(int(g["seed"]))
+    np.testing.assert_array_equal(netweights.checksum(sd), g["weights_checksum"])
+    M = g["obs"].shape[0]
+    on, an = RunningMeanStd(1422), RunningMeanStd(3090)
+    on.running_mean.copy_(torch.from_numpy(g["obs_mean"])); on.running_var.copy_(torch.from_numpy(g["obs_var"]))
+    an.running_mean.copy_(torch.from_numpy(g["amp_mean"])); an.running_var.copy_(torch.from_numpy(g["amp_var"]))
+    nets = RolloutNets(net, on.cuda(), an.cuda(), M, tensor_cores=tc)
+    obs, amp = torch.from_numpy(g["obs"]).cuda(), torch.from_numpy(g["amp_obs"]).cuda()
+    noise = torch.zeros(M, 69, device="cuda")
+    r = nets.action_values(obs, noise)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(r["mus"].cpu().numpy(), g["out_mu"], rtol=RTOL, atol=5e-5)
+    np.testing.assert_allclose(r["actions"].cpu().numpy(), g["out_mu"], rtol=RTOL, atol=5e-5)          # zero noise
+    np.testing.assert_allclose(r["values"].cpu().numpy(), g["out_value"], rtol=RTOL, atol=5e-5)
+    np.testing.assert_allclose(r["task_values"].cpu().numpy(), g["out_task_value"], rtol=RTOL, atol=5e-5)
+    np.testing.assert_array_equal(r["sigmas"].cpu().numpy(), g["out_sigma"][0])                        # network-level sigma = log std
+    nv = nets.critic(obs).cpu().numpy()
+    std = np.sqrt(np.float32(g["value_var"][0]) + np.float32(1e-5))
+    np.testing.assert_allclose(std * np.clip(nv, -5, 5) + np.float32(g["value_mean"][0]), g["out_next_value_unnorm"], rtol=RTOL, atol=5e-5)
+    logit = nets.disc_logits(amp).clone()
+    np.testing.assert_allclose(logit.cpu().numpy(), g["out_disc_logit"], rtol=RTOL, atol=1e-4)
+    dr, comb = disc_reward(logit, torch.from_numpy(g["task_rewards"]).cuda(), 2.0, 0.5, 0.5)
+    np.testing.assert_allclose(dr.cpu().numpy(), g["out_disc_reward"], rtol=RTOL, atol=1e-4)
+    np.testing.assert_allclose(comb.cpu().numpy(), g["out_combined"], rtol=RTOL, atol=1e-4)
+
+
+def test_rollout_record_matches_reference_loop_body_golden():
+    """a14: emloco_rollout_record against amp_continuous_value.py:61-121 executed from the reference (play_block.npz): the
+    inversion penalty, next_vals *= 1 - terminated, AMP reward with its 1e-4 floor, both snapshot conditions."""
+    import ctypes as C
+    from emloco_b200 import _lib
+    from emloco_b200.sim import _ptr, _stream
+    g = np.load(os.path.join(GOLDEN, "play_block.npz"))
+    N = int(g["N"])
+    T = lambda a, dt=torch.float32: torch.from_numpy(np.ascontiguousarray(a)).to(dt).cuda()
+    state = torch.zeros(6, N, device="cuda")
+    state[0] = T(g["state0_current_rewards"][:, 0]); state[1] = T(g["state0_current_lengths"]); state[2] = T(g["state0_current_combined"])
+    state[3] = T(g["state0_discount"])
+    inv = T(g["inverted"], torch.uint8)
+    rcfg = _lib.RolloutCfg(0.3, 1.0, float(g["value_mean"]), float(np.sqrt(np.float32(g["value_var"]) + np.float32(1e-5))), 2.0, 0.99, 144, 1)
+    f = lambda *s: torch.zeros(*s, device="cuda")
+    for n in range(int(g["steps"])):
+        rew, reset, term = T(g["in_rew"][n][:, 0]), T(g["in_reset"][n], torch.int64), T(g["in_terminate"][n], torch.int64)
+        nv, logit, pv = T(g["in_critic_raw"][n]), T(g["in_logit"][n]), f(N, 1)
+        o_val, o_rew, o_done, o_nv, o_amp = f(N, 1), f(N, 1), f(N), f(N, 1), f(N, 1)
+        _lib.check(_lib.load().emloco_rollout_record(C.byref(rcfg), _ptr(rew), _ptr(reset), _ptr(term), _ptr(pv), _ptr(nv), _ptr(logit),
+                                                     _ptr(inv), _ptr(o_val), _ptr(o_rew), _ptr(o_done), _ptr(o_nv), _ptr(o_amp),
+                                                     _ptr(state), N, _stream()), "emloco_rollout_record")
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(o_rew.cpu().numpy(), g["row_rewards"][n], rtol=1e-6, atol=1e-7)
+        np.testing.assert_array_equal(o_done.cpu().numpy(), g["row_dones"][n].astype(np.float32))
+        np.testing.assert_allclose(o_nv.cpu().numpy(), g["row_next_values"][n], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(o_amp.cpu().numpy()[:, 0], g["row_amp_rewards"][n], rtol=1e-4, atol=1e-6)
+        st = state.cpu().numpy()
+        for row, ref in ((1, "out_current_lengths"), (2, "out_current_combined"), (3, "out_discount"), (4, "out_game_combined"),
+                         (5, "out_terminated_flags")):
+            np.testing.assert_allclose(st[row], g[ref][n], rtol=1e-5, atol=1e-5, err_msg=f"step {n} {ref}")
+        np.testing.assert_allclose(st[0], g["out_current_rewards"][n][:, 0], rtol=1e-5, atol=1e-5)
+        if n == int(g["zero_game_after_step"]):
+            state[4].zero_()
+
+
+def test_post_step_reset_branches_match_reference_golden():
+    """a8: every branch of compute_humanoid_reset at 256 envs (post_step_branches.npz), masks bit-exact."""
+    from oracle.make_golden import synth_state_branches
+    g = np.load(os.path.join(GOLDEN, "post_step_branches.npz"))
+    st = synth_state_branches(int(g["N"]), int(g["seed"]))
+    out = _run_post(st)
+    assert {(int(a), int(b)) for a, b in zip(g["out_reset"], g["out_terminate"])} == {(0, 0), (1, 0), (1, 1)}
+    for k in ("reset", "terminate"):
+        assert out[k].dtype == np.int64
+        np.testing.assert_array_equal(out[k], g["out_" + k])
+    for k in ("rew", "reward_raw"):
+        np.testing.assert_allclose(out[k], g["out_" + k], rtol=RTOL, atol=ATOL, err_msg=k)
+    for k in ("obs", "flip_obs"):
+        np.testing.assert_allclose(out[k][:, :398], g["out_" + k][:, :398], rtol=RTOL, atol=ATOL, err_msg=k)
+        assert _height_mismatch_ok(out[k][:, 398:], g["out_" + k][:, 398:]), k + " heights"
+    np.testing.assert_allclose(out["amp_obs"][:, :206], g["out_amp_obs"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_array_equal(out["amp_obs"][:, 206:], st["amp_buf"][:, :14].reshape(int(g["N"]), -1))
+
+
+@pytest.mark.parametrize("B", [0, 1, 40, 100000])
+def test_plausibl_mlp_matches_reference_class_golden(B):
+    """a17: emloco_b200.plausibl.test_value_mlp.MLP against the reference class (plausibl.npz); larger batches against the
+    oracle with the same weights; the empty batch returns an empty result."""
+    from emloco_b200.plausibl.test_value_mlp import MLP
+    from oracle import oracle_np as O
+    g = np.load(os.path.join(GOLDEN, "plausibl.npz"))
+    m = MLP()
+    sd = {k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("w_")}
+    m._value_mlp.load_state_dict({k[len("_value_mlp."):]: v for k, v in sd.items() if k.startswith("_value_mlp.")})
+    m._value_logits.load_state_dict({k[len("_value_logits."):]: v for k, v in sd.items() if k.startswith("_value_logits.")})
+    m.cuda()
+    if B == 40:
+        y = m.forward(torch.from_numpy(g["x"]).cuda())
+        np.testing.assert_allclose(y.cpu().numpy(), g["y"], rtol=1e-5, atol=1e-6)
+        return
+    x = np.random.default_rng(B).normal(0, 2, (B, 24)).astype(np.float32)
+    y = m(torch.from_numpy(x).cuda())
+    assert y.shape == (B, 1)
+    W = dict(fc1=(g["w__value_mlp.0.weight"], g["w__value_mlp.0.bias"]), fc2=(g["w__value_mlp.2.weight"], g["w__value_mlp.2.bias"]),
+             fc3=(g["w__value_logits.weight"], g["w__value_logits.bias"]))
+    np.testing.assert_allclose(y.cpu().numpy(), O.plausibl_mlp(x, W), rtol=1e-4, atol=1e-5)

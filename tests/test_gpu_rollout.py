@@ -593,3 +593,107 @@ def test_rollout_from_reference_configuration():
     assert out["dones"].sum() >= 48 and (R.sim.traj_verts != v0).any()               # resets regenerated trajectories
     assert R.valuenet.finetune_stats()[3] >= 48                                     # done_early episodes fed LocoVal
     R.close()
+
+
+def test_graphed_rollout_follows_weight_and_normaliser_updates():
+    """Captured graphs must not keep rolling out with the weights / statistics of capture time: after an
+    optimiser-style in-place parameter update, a load_state_dict, a running-statistics update by in-place copy AND by attribute
+    re-assignment (the reference's way, running_mean_std.py:93-96: fresh tensors with _version 0) and a value_mean_std update,
+    graphed horizons equal eager horizons bit for bit; in-place updates do not re-capture."""
+    from emloco_b200.policy import AMPSeptValueNetwork, RunningMeanStd
+    from emloco_b200.rollout import Rollout
+    n, T = 96, 3
+    mk = lambda: (torch.manual_seed(4), AMPSeptValueNetwork())[1]
+    A = Rollout(n, seed=9, net=mk(), tensor_cores=True, horizon=T, traj_flags=0)
+    B = Rollout(n, seed=9, net=mk(), tensor_cores=True, horizon=T, traj_flags=0)
+    keys = ("obses", "actions", "values", "next_values", "rewards", "dones", "amp_rewards", "returns", "advantages")
+
+    def both(fn):
+        for R in (A, B):
+            fn(R)
+
+    def horizon(tag):
+        oa = A.play_steps(graphed=False); ob = B.play_steps(graphed=True)
+        torch.cuda.synchronize()
+        for k in keys:
+            np.testing.assert_array_equal(oa[k].cpu().numpy(), ob[k].cpu().numpy(), err_msg=f"{k} after {tag}")
+        return oa
+
+    horizon("warm-up"); horizon("capture")
+    base = horizon("replay")
+    captured = dict(B._graphs)
+    g = torch.Generator().manual_seed(1)
+
+    def perturb(R):
+        with torch.no_grad():
+            for p in R.net.parameters():
+                if p.requires_grad:
+                    p.add_(0.02 * torch.randn(p.shape, generator=torch.Generator().manual_seed(p.numel())).to(p.device))
+    both(perturb)
+    o1 = horizon("in-place parameter update")
+    assert not np.array_equal(o1["actions"].cpu().numpy(), base["actions"].cpu().numpy())
+    assert all(B._graphs.get(k) is captured[k] for k in captured), "an in-place update must not force a re-capture"
+
+    def stats_inplace(R):
+        R.obs_norm.running_mean.add_(0.05); R.obs_norm.running_var.mul_(1.3)
+        R.amp_norm.running_mean.sub_(0.02); R.amp_norm.running_var.mul_(0.8)
+        R.value_norm.running_mean.fill_(0.7); R.value_norm.running_var.fill_(2.5)
+    both(stats_inplace)
+    o2 = horizon("in-place statistics update")
+    assert not np.array_equal(o2["values"].cpu().numpy(), o1["values"].cpu().numpy())
+    assert all(B._graphs.get(k) is captured[k] for k in captured)
+
+    def stats_reassign(R):      # twice: the second fresh tensor has the same _version (0) as the first
+        for scale in (1.5, 0.6):
+            R.obs_norm.running_mean = R.obs_norm.running_mean * scale + 0.01
+            R.obs_norm.running_var = R.obs_norm.running_var * scale
+            R.value_norm.running_mean = R.value_norm.running_mean + 0.25
+            R.value_norm.running_var = R.value_norm.running_var * scale
+    both(stats_reassign)
+    o3 = horizon("statistics re-assigned")
+    assert not np.array_equal(o3["values"].cpu().numpy(), o2["values"].cpu().numpy())
+
+    sd = {k: v + 0.01 for k, v in A.net.state_dict().items()}
+    both(lambda R: R.net.load_state_dict(sd))
+    horizon("load_state_dict")
+
+    def realloc(R):             # parameter storage replaced: pointers baked into the graphs are stale -> must re-capture
+        R.net.mu.bias.data = R.net.mu.bias.data.clone() + 0.05
+    both(realloc)
+    horizon("parameter re-allocated")
+    assert any(B._graphs.get(k) is not captured[k] for k in captured)
+    A.close(); B.close()
+
+
+def test_batched_filter_reference_compat_reproduces_the_sequential_in_place_loop():
+    """evaluate_jta.py:298-302 scores prediction and ground truth of every mode on ONE init_pose view that
+    ValuePoseNet rotates / zeroes in place, cumulatively.  score_and_filter(reference_compat=True) must give the values of
+    that sequential loop (run here through the in-place drop-in, batch of 1, exactly like the reference) in a single launch."""
+    from emloco_b200.formats import score_and_filter
+    from emloco_b200.value_pose_net import ValuePoseNet
+    torch.manual_seed(1)
+    S, M = 40, 5
+    net = ValuePoseNet(True, True).cuda().eval()
+    with torch.no_grad():
+        for m in net._network:
+            if hasattr(m, "bias"):
+                m.bias.uniform_(-0.2, 0.2)
+    trajs = (torch.randn(S, M, 13, 2, device="cuda") * 0.4).cumsum(2); trajs[:, :, 0] = 0
+    gts = (torch.randn(S, 13, 2, device="cuda") * 0.4).cumsum(1); gts[:, 0] = 0
+    pose = torch.randn(S, 24, 3, device="cuda") * 0.3
+    vel = torch.randn(S, 2, device="cuda")
+    values, keep = score_and_filter(net, trajs, pose.clone(), vel, threshold=0.5, reference_compat=True, gt_trajs=gts)
+    plain, _ = score_and_filter(net, trajs, pose.clone(), vel, threshold=0.5)
+    seq = torch.zeros(S, M)
+    with torch.no_grad():
+        for s in range(S):
+            p = pose[s].clone()                                        # the scene's init_pose tensor, mutated by every call
+            for m in range(M):
+                v, _ = net.calc_embodied_motion_loss(trajs[s, m][None].contiguous(), p.unsqueeze(0), vel[s][None])
+                net.calc_embodied_motion_loss(gts[s][None].contiguous(), p.unsqueeze(0), vel[s][None])
+                seq[s, m] = v.item()
+    np.testing.assert_allclose(values.cpu().numpy(), seq.numpy(), rtol=1e-3, atol=2e-4)
+    np.testing.assert_allclose(plain[:, 0].cpu().numpy(), seq[:, 0].numpy(), rtol=1e-3, atol=2e-4)     # mode 0 sees the original pose
+    assert (plain[:, 1:].cpu() - seq[:, 1:]).abs().max() > 1e-2                                        # ... later modes do not
+    with pytest.raises(ValueError):
+        score_and_filter(net, trajs, pose, vel, reference_compat=True)
