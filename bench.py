@@ -160,18 +160,30 @@ def cpu_rollout_rate(envs, steps, warmup, seed=0, budget_s=None):
     return envs * done / dt, done, dt
 
 
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def run_reference(args):
+    """The CPU arm: the whole workload (all `--envs` envs, same step definition as the GPU arm) on the host cores of rank 0.
+    main() has already lifted torchrun's OMP_NUM_THREADS=1 (set before numpy / torch / the OpenMP physics oracle load)."""
     rank, _, world = dist_env()
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    envs = min(args.envs, 256)          # bounded sample of the 4096-env workload: ~0.3-1 s of host work per step
-    rate, done, dt = cpu_rollout_rate(envs, args.steps, min(args.warmup, 2), budget_s=150.0)
-    sample = f"{envs} of {args.envs} envs per step, {done} steps in {dt:.1f} s (oracle port: fp64 C physics + numpy nets / post-step / LocoVal scoring / post-horizon pass)"
+    cores = host_cores()
+    from oracle import oracle_np as O
+    O.set_linear_backend("torch", cores)            # dense layers through torch's CPU sgemm, as the reference's nn.Linear would
+    envs = args.envs
+    warm = min(args.warmup, 3)
+    rate, done, dt = cpu_rollout_rate(envs, args.steps, warm, budget_s=240.0)
+    sample = (f"all {envs} envs per step, {done} steps in {dt:.1f} s on {cores} threads (oracle port: fp64 C physics with OpenMP, torch CPU "
+              f"sgemm nets, numpy post-step / LocoVal scoring / post-horizon pass)")
     print(json.dumps({
         "impl": "reference", "metric": "env_steps_per_sec", "value": rate, "unit": "env-steps/s", "n_gpus": args.gpus,
-        "steps": done, "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * dt / max(done, 1), "higher_is_better": True,
+        "steps": done, "warmup": warm, "ms_per_step": 1e3 * dt / max(done, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.envs} SMPL-humanoid envs per GPU, PACER AMP rollout step + LocoVal scoring (configs[1])",
                    "horizon": HORIZON},
@@ -189,6 +201,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     from emloco_b200 import dist as D
+    numa = D.bind_to_gpu_numa_node(local_rank)          # before any pinned allocation: host buffers on the GPU's NUMA node
     D.init("nccl")
     from emloco_b200 import _lib
     from emloco_b200.rollout import Rollout
@@ -273,51 +286,26 @@ def run_ours(args):
 
     # ---- end to end: the vec-env / agent boundary with HOST buffers (rl_device = cpu): every step copies the step's
     # inputs (obs for the nets, policy noise) from pinned host memory and reads the results back (next obs, rewards,
-    # dones, actions, neglogp, values) ----
-    pin = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt).pin_memory()
-    h_obs, h_noise = pin(N, 1422), pin(N, 69).normal_()
-    h_out = dict(obs=pin(N, 1422), rew=pin(N), reset=pin(N, dt=torch.int64), actions=pin(N, 69), neglogp=pin(N), values=pin(N, 1))
-    h_obs.copy_(R.sim.obs)
+    # dones, actions, neglogp, values).  emloco_b200.host_pipeline.HostRolloutPipeline: the N envs run as `--e2e-groups`
+    # independent groups whose copies and compute overlap; per group a step is issued only when the host holds the previous
+    # step's results of that group (what came back is what the next step is fed) ----
+    from emloco_b200.host_pipeline import HostRolloutPipeline
+    pipe = HostRolloutPipeline(N, groups=args.e2e_groups, device=local_rank, seed=D.rank_seed(args.seed, rank) + 101, graphs=graphs,
+                               tensor_cores=args.tensor_cores, recompute_disc=not args.dedup_disc, concurrent=not args.serial,
+                               traj_flags=TRAJ_FLAGS, traj_pool=pool)
+    pipe.warm()
     Ke = max(HORIZON, min(K, 2 * HORIZON))
-    copy_stream, env_done = torch.cuda.Stream(), torch.cuda.Event()
-    host = {"obs": h_obs}                               # the two pinned observation buffers swap roles every step
-
-    def read_back_env():
-        # the env step is done: next obs / reward / dones travel back on a copy stream while critic, discriminator and the
-        # bookkeeping of the same step still run (VecTaskPython.step returns them to the rl_device, vec_task.py:125-134)
-        env_done.record()
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(env_done)
-            h_out["obs"].copy_(R.sim.obs, non_blocking=True); h_out["rew"].copy_(R.sim.rew, non_blocking=True)
-            h_out["reset"].copy_(R.sim.reset, non_blocking=True)
-
-    def e2e_step(i):
-        n = i % HORIZON
-        R.sim.obs.copy_(host["obs"], non_blocking=True)  # the policy reads the obs the host handed over
-        R.noise.copy_(h_noise, non_blocking=True)
-        if graphs:
-            R.step_graphed_host_noise(n, after_env_step=read_back_env)
-        else:
-            R.step(n, noise=R.noise, host_obs=True)
-            read_back_env()
-        if n == HORIZON - 1:
-            (R.finish_graphed if graphs else R.finish)()
-        h_out["actions"].copy_(R.mb["actions"][n], non_blocking=True)
-        h_out["neglogp"].copy_(R.mb["neglogpacs"][n], non_blocking=True); h_out["values"].copy_(R.mb["values"][n], non_blocking=True)
-        copy_stream.synchronize()
-        torch.cuda.current_stream().synchronize()       # the host consumes the results before issuing the next step
-        host["obs"], h_out["obs"] = h_out["obs"], host["obs"]      # what came back is what the next step is fed (no host memcpy)
-    for i in range(HORIZON if graphs else 3):
-        e2e_step(i)
     barrier()
     e0.record()
-    for i in range(Ke):
-        e2e_step(i)
+    pipe.run(Ke)
+    for st_ in pipe.stream:
+        torch.cuda.current_stream().wait_stream(st_)
     e1.record()
     barrier()
     e2e_value = world * N * Ke / (D.max_over_ranks(e0.elapsed_time(e1), device="cuda") * 1e-3)
-    h2d = h_obs.numel() * 4 + h_noise.numel() * 4
-    d2h = sum(v.numel() * v.element_size() for v in h_out.values())
+    h2d, d2h = pipe.h2d_bytes_per_step, pipe.d2h_bytes_per_step
+    pipe.close(); del pipe
+    torch.cuda.empty_cache()
 
     # ---- variant (reported beside the headline, never as it): value reuse.  The headline evaluates the critic twice per
     # observation like the reference does; with reuse the second evaluation is taken from the next step's policy pass
@@ -424,7 +412,9 @@ def run_ours(args):
                                     "--adjust_root_vel, --init_heading) for the envs that finish, every step" % TRAJ_POOL,
                        "tensor_cores": bool(args.tensor_cores), "cuda_graphs": graphs, "parallel_branches": not args.serial},
             "clocks": clocks, "gpu_launches": launches,
-            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
+                    "groups": args.e2e_groups, "numa_node": numa,
+                    "note": "HostRolloutPipeline: envs split into independent groups so host<->device copies of one group overlap the other's step; per group, step k+1 is issued after the host holds step k's results"},
             "roofline": roof, "kernels": kern, "segments_ms": seg,
             "post_horizon_ms": finish_ms,
             "post_horizon_share": {"passes_in_window": fin_in_window, "expected": K / HORIZON, "charged_ms": fin_share * finish_ms},
@@ -454,10 +444,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the value-reuse variant measurement")
     ap.add_argument("--serial", action="store_true", help="no parallel graph branches (critic / discriminator / LocoVal / heads)")
+    ap.add_argument("--e2e-groups", type=int, default=2, help="env groups of the end-to-end (host buffer) pipeline")
     ap.add_argument("--eager", action="store_true", help="launch every kernel from the host instead of replaying CUDA graphs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
+        # all host threads for the CPU arm: torchrun exports OMP_NUM_THREADS=1 to its workers, which would leave the OpenMP
+        # physics oracle, OpenBLAS and torch's intra-op pool single-threaded (numpy / torch are not imported yet at this point)
+        for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+            os.environ[k] = str(host_cores())
         run_reference(args)
     else:
         run_ours(args)

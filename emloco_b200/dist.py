@@ -30,6 +30,35 @@ def init(backend=None):
     return rank, local_rank, world
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pins this process to the CPUs of the NUMA node its GPU hangs off (read from sysfs through the GPU's PCI address), so
+    that pinned host buffers allocated afterwards are first-touched on that node and host<->device copies do not cross the
+    socket interconnect.  With every rank left on the launcher's default affinity (all ranks on node 0) the end-to-end path of
+    8 ranks ran at 0.46 efficiency (SCALE_r01).  Best effort: returns the node (or None when it cannot be determined)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[local_rank])
+                                              if os.environ.get("CUDA_VISIBLE_DEVICES", "").replace(",", "").isdigit() else local_rank)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bdf = bus.lower()[-12:]                                       # 00000000:1B:00.0 -> 0000:1b:00.0
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0)) or cpus
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def rank_seed(seed, rank):
     """run.py:65: every rank simulates its own envs with its own random stream."""
     return int(seed) + int(rank)

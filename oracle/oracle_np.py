@@ -507,7 +507,35 @@ def rms_normalize(x, mean, var, eps=1e-5):
     return np.clip(y, F(-5.0), F(5.0)).astype(F)
 
 
+_LINEAR = {"backend": "numpy", "cache": {}}
+
+
+def set_linear_backend(name, threads=None):
+    """'numpy' (default, the checker) or 'torch': the dense layers through torch's CPU `F.linear` (MKL / oneDNN sgemm on all
+    host threads) - what the reference's own `nn.Linear` modules run when the agent sits on the CPU.
+    Used by bench.py's CPU arm only; same arithmetic (fp32 GEMM + bias + ReLU), different BLAS."""
+    assert name in ("numpy", "torch")
+    _LINEAR["backend"] = name
+    if name == "torch":
+        import torch
+        if threads:
+            torch.set_num_threads(int(threads))
+
+
 def _mlp(x, layers, relu_last=True):
+    if _LINEAR["backend"] == "torch":
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(x, dtype=F))
+        with torch.no_grad():
+            for i, (W, b) in enumerate(layers):
+                key = (id(W), id(b))
+                wb = _LINEAR["cache"].get(key)
+                if wb is None or wb[2] is not W:
+                    wb = _LINEAR["cache"][key] = (torch.from_numpy(np.ascontiguousarray(W, dtype=F)), torch.from_numpy(np.ascontiguousarray(b, dtype=F)), W)
+                t = torch.nn.functional.linear(t, wb[0], wb[1])
+                if relu_last or i < len(layers) - 1:
+                    t = torch.relu_(t)
+        return t.numpy()
     for i, (W, b) in enumerate(layers):
         x = x @ W.T.astype(F) + b.astype(F)
         if relu_last or i < len(layers) - 1:

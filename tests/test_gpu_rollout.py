@@ -617,7 +617,7 @@ def test_graphed_rollout_follows_weight_and_normaliser_updates():
         torch.cuda.synchronize()
         for k in keys:
             np.testing.assert_array_equal(oa[k].cpu().numpy(), ob[k].cpu().numpy(), err_msg=f"{k} after {tag}")
-        return oa
+        return {k: oa[k].clone() for k in keys}          # the experience rows are reused by the next horizon
 
     horizon("warm-up"); horizon("capture")
     base = horizon("replay")
@@ -697,3 +697,182 @@ def test_batched_filter_reference_compat_reproduces_the_sequential_in_place_loop
     assert (plain[:, 1:].cpu() - seq[:, 1:]).abs().max() > 1e-2                                        # ... later modes do not
     with pytest.raises(ValueError):
         score_and_filter(net, trajs, pose, vel, reference_compat=True)
+
+
+def test_benched_configuration_4096_envs_graphed_tensor_core_horizon_in_lockstep_with_cpu_oracle():
+    """Parity ON THE CONFIGURATION bench.py TIMES: Rollout(4096, tensor_cores=True, rows_only=True,
+    traj_flags=1|2|4, traj_pool=2048 polylines), CUDA-graph replay of every step (`step_graphed`) and of the post-horizon pass
+    (`finish_graphed`), parallel branches, deferred trajectory reset.  A full 32-step horizon is replayed; at every step the
+    first 256 envs are checked against the CPU oracle started from the GPU's own pre-step state of those envs (re-synchronised
+    each step so fp32-vs-fp64 round-off cannot accumulate through the contact dynamics), using the policy noise the graph drew.
+    After the horizon: AMP rewards of the post-horizon discriminator pass, combined rewards, GAE advantages and returns."""
+    import bench
+    from emloco_b200.model import build_model_arrays, rest_root_height
+    from emloco_b200.policy import AMPSeptValueNetwork
+    from emloco_b200.rollout import Rollout
+    from emloco_b200.synthetic import synthetic_env_state, synthetic_traj_pool
+    from oracle import oracle_np as O
+    from oracle.cpu_rollout import CpuRollout, weights_from_state_dict
+    N, n, T = 4096, 256, 32
+    torch.manual_seed(0)
+    net = AMPSeptValueNetwork()
+    gpu = Rollout(N, seed=0, net=net, tensor_cores=True, traj_flags=bench.TRAJ_FLAGS, traj_pool=synthetic_traj_pool(bench.TRAJ_POOL, 0))
+    assert gpu.rows_only and gpu.concurrent and gpu._traj_deferred and not gpu.reuse_values      # the bench defaults
+    A = build_model_arrays()
+    P, D = weights_from_state_dict(net.state_dict())
+    st = synthetic_env_state(N, 0, rest_root_height(A))
+    cpu = CpuRollout(A, {k: v[:n * 69] if k == "dof" else v[:n] for k, v in st.items()}, P, D)
+    sim = gpu.sim
+    # as bench.py: three eager steps, then every slot captured during one horizon, then replays
+    for k in range(3):
+        gpu.step(k)
+    gpu.finish()
+    for k in range(3, 3 + T):
+        gpu.step_graphed(k % T)
+        if k % T == T - 1:
+            gpu.finish_graphed()
+    for k in range(3):                      # slots 0..2 of the next horizon: the checked horizon starts at slot 0 below
+        gpu.step_graphed(k)
+    for k in range(3, T):
+        gpu.step_graphed(k)
+    gpu.finish_graphed()
+    graphs_before = dict(gpu._graphs)
+    assert all(k in graphs_before for k in range(T)) and "finish" in graphs_before
+
+    worst, mask_mismatch, n_resets, n_inv = {}, 0, 0, 0
+
+    def upd(key, a, b, atol):
+        err = np.abs(a - b) / (atol + RTOL * np.abs(b))
+        worst[key] = max(worst.get(key, 0.0), float(err.max()))
+
+    f64 = lambda t: t.detach().cpu().numpy().astype(np.float64)
+    for k in range(T):
+        torch.cuda.synchronize()
+        cpu.root = f64(sim.root_state).reshape(N, 13)[:n].copy()
+        cpu.jq = f64(sim.joint_quat).reshape(N, 23, 4)[:n].copy()
+        cpu.jw = f64(sim.dof_state).reshape(N, 69, 2)[:n, :, 1].copy()
+        cpu.progress = sim.progress[:n].cpu().numpy().copy(); cpu.reset = sim.reset[:n].cpu().numpy().copy()
+        cpu.terminate = sim.terminate[:n].cpu().numpy().copy()
+        ring = gpu.mb["amp_obs"][(k - 1) % T]                       # rows_only: the ring lives in the previous step's experience row
+        cpu.amp_buf = ring[:n].cpu().numpy().reshape(n, 15, 206).copy()
+        cpu.contact = f64(sim.contact).reshape(N, 24, 3)[:n].copy(); cpu.dof_force = f64(sim.dof_force).reshape(N, 69)[:n].copy()
+        cpu.obs = (gpu.mb["obses"][T] if k == 0 else gpu.mb["obses"][k])[:n].cpu().numpy().copy()
+        cpu.state = gpu.state[:, :n].cpu().numpy().copy()
+        cpu.verts = sim.traj_verts[:n].cpu().numpy().copy()          # reset envs still see their OLD polyline in the reset observation
+        n_resets += int(cpu.reset.sum())
+        gpu.step_graphed(k)                                          # replay
+        torch.cuda.synchronize()
+        noise = gpu.noise[:n].cpu().numpy().copy()
+        cpu.reset_done()                                             # env_reset(done_indices) with the old polylines ...
+        cpu.verts = sim.traj_verts[:n].cpu().numpy().copy()          # ... then _reset_task: the device's regenerated polylines (Philox
+        cpu.inverted = gpu.inverted[:n].cpu().numpy().astype(bool)   #     draws; the generator itself is pinned by traj_reset_*.npz)
+        n_inv += int(cpu.inverted.sum())
+        o = cpu.step(noise)
+        mb = {key: v[k][:n].cpu().numpy() for key, v in gpu.mb.items() if v is not None}
+        upd("obs_in", mb["obses"][:, :398], o["obs"][:, :398], 5e-3)
+        upd("mus", mb["mus"], o["mu"], 5e-5); upd("actions", mb["actions"], o["actions"], 5e-5)
+        upd("neglogp", mb["neglogpacs"], o["neglogp"], 1e-3)
+        upd("values", mb["values"][:, 0], o["values"], 5e-5); upd("task_values", mb["task_values"], o["task_values"], 5e-5)
+        rb = sim.rb_state.view(N, 24, 13)[:n].cpu().numpy()
+        upd("rb_pos", rb[..., 0:3], o["rb"][..., 0:3], 1e-3); upd("rb_rot", rb[..., 3:7], o["rb"][..., 3:7], 1e-3)
+        upd("rb_vel", rb[..., 7:13], o["rb"][..., 7:13], 1e-2)
+        same = mb["dones"] == o["dones"]
+        mask_mismatch += int((~same).sum())
+        upd("rewards", mb["rewards"][same, 0], o["rewards"][same], 5e-3)
+        upd("next_values", mb["next_values"][same, 0], o["next_values"][same], 1e-4)
+        upd("amp_rewards", mb["amp_rewards"][:, 0], o["amp_rewards"], 1e-3)
+        upd("self_obs", gpu.mb["obses"][k + 1][:n, :368].cpu().numpy(), o["next_obs"][:, :368], 5e-3)
+        upd("amp_row", mb["amp_obs"][:, :206], o["amp_obs"][:, :206], 5e-3)
+        upd("state", gpu.state[:, :n].cpu().numpy()[:, same], cpu.state[:, same], 3e-2)
+    out = gpu.finish_graphed()                                        # replay of the post-horizon pass
+    torch.cuda.synchronize()
+    assert all(gpu._graphs[k] is graphs_before[k] for k in graphs_before), "the checked horizon must be pure replay"
+    g = {k: out[k][:, :n].cpu().numpy() for k in ("amp_obs", "task_rewards", "amp_rewards", "rewards", "dones", "values", "next_values",
+                                                   "returns", "advantages")}
+    amp_r = np.stack([O.disc_reward(g["amp_obs"][t], cpu.D, 2.0)[0] for t in range(T)])
+    upd("post_amp_rewards", g["amp_rewards"], amp_r, 1e-3)
+    comb = (np.float32(0.5) * g["task_rewards"] + np.float32(0.5) * amp_r).astype(np.float32)
+    upd("combined", g["rewards"], comb, 1e-3)
+    adv = O.discount_values(g["dones"], g["values"], g["rewards"], g["next_values"])
+    upd("advantages", g["advantages"], adv, 1e-4); upd("returns", g["returns"], adv + g["values"], 1e-4)
+    print("benched-config lockstep worst error / tolerance:", {k_: round(v, 3) for k_, v in worst.items()}, "mask mismatches",
+          mask_mismatch, "resets", n_resets)
+    assert n_resets > 20                      # episodes ended and restarted inside the checked horizon
+    assert mask_mismatch <= 3
+    for key, v in worst.items():
+        assert v <= 1.0, (key, v)
+    gpu.close()
+
+
+def test_step_host_c_abi_entry_equals_the_device_step():
+    """emloco_step_host (include/emloco.h: the vec-env call of a host-side user, run.py:148-160): host buffers in and out,
+    same results as emloco_step on device tensors - obs, rewards, int64 reset mask and AMP observations bit for bit."""
+    import ctypes as C
+    from emloco_b200 import _lib
+    from emloco_b200.model import rest_root_height
+    from emloco_b200.sim import EmlocoSim
+    from emloco_b200.synthetic import synthetic_env_state
+    n = 80
+    sims = [EmlocoSim(n) for _ in range(2)]
+    st = synthetic_env_state(n, 3, rest_root_height(sims[0].model_arrays))
+    root, dof = torch.from_numpy(st["root"]).cuda(), torch.from_numpy(st["dof"]).cuda()
+    for s in sims:
+        s.traj_verts.copy_(torch.from_numpy(st["verts"]).cuda())
+        s.reset.fill_(1)
+        s.reset_done(root, dof)
+    rng = np.random.default_rng(0)
+    h_obs, h_rew = np.zeros((n, 1422), np.float32), np.zeros(n, np.float32)
+    h_reset, h_amp = np.zeros(n, np.int64), np.zeros((n, 3090), np.float32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    for k in range(6):
+        act = rng.uniform(-0.5, 0.5, (n, 69)).astype(np.float32)
+        sims[0].step(torch.from_numpy(act).cuda())
+        torch.cuda.synchronize()
+        _lib.check(_lib.load().emloco_step_host(sims[1]._h, vp(act), vp(h_obs), vp(h_rew), vp(h_reset), vp(h_amp)), "emloco_step_host")
+        np.testing.assert_array_equal(h_obs, sims[0].obs.cpu().numpy(), err_msg=f"obs step {k}")
+        np.testing.assert_array_equal(h_rew, sims[0].rew.cpu().numpy())
+        np.testing.assert_array_equal(h_reset, sims[0].reset.cpu().numpy())
+        np.testing.assert_array_equal(h_amp, sims[0].amp_obs.reshape(n, 3090).cpu().numpy())
+    # optional outputs may be NULL; a NULL action pointer is an error, reported through emloco_last_error
+    assert _lib.load().emloco_step_host(sims[1]._h, vp(act), None, None, None, None) == 0
+    assert _lib.load().emloco_step_host(sims[1]._h, None, vp(h_obs), None, None, None) != 0
+    assert b"emloco_step_host" in _lib.load().emloco_last_error()
+    for s in sims:
+        s.close()
+
+
+def test_host_pipeline_groups_equal_plain_host_steps():
+    """HostRolloutPipeline (the end-to-end path bench.py times): two env groups in flight, host buffers in and out.  Every
+    group's results must equal, bit for bit, those of a plain Rollout with the group's seed stepped serially on the same
+    host-provided observations and noise."""
+    from emloco_b200.host_pipeline import HostRolloutPipeline
+    from emloco_b200.policy import AMPSeptValueNetwork
+    from emloco_b200.rollout import Rollout
+    N, G, T = 192, 2, 4
+    mk = lambda: (torch.manual_seed(2), AMPSeptValueNetwork())[1]
+    pipe = HostRolloutPipeline(N, groups=G, seed=5, horizon=T, tensor_cores=True, net=mk(), traj_flags=0)
+    refs = [Rollout(N // G, seed=5 + 7919 * g, horizon=T, tensor_cores=True, net=mk(), traj_flags=0) for g in range(G)]
+    assert pipe.h2d_bytes_per_step == N * (1422 + 69) * 4 and pipe.d2h_bytes_per_step == N * (1422 + 1 + 2 + 69 + 1 + 1) * 4
+    for g in range(G):
+        pipe.host[g]["noise"].copy_(torch.randn(N // G, 69, generator=torch.Generator().manual_seed(g)))
+    feed = [pipe.host[g]["obs_in"].clone() for g in range(G)]
+    for k in range(2 * T + 1):                 # eager first steps, graph capture, replay - all compared
+        for g in range(G):
+            pipe.submit(g)
+        for g in range(G):
+            h = pipe.wait(g)
+            R = refs[g]
+            R.sim.obs.copy_(feed[g].cuda()); R.noise.copy_(h["noise"].cuda())
+            R.step(k % T, noise=R.noise, host_obs=True)
+            if k % T == T - 1:
+                R.finish()
+            torch.cuda.synchronize()
+            np.testing.assert_array_equal(h["obs_in"].numpy(), R.sim.obs.cpu().numpy(), err_msg=f"obs step {k} group {g}")   # swapped: results are the next input
+            np.testing.assert_array_equal(h["rew"].numpy(), R.sim.rew.cpu().numpy())
+            np.testing.assert_array_equal(h["reset"].numpy(), R.sim.reset.cpu().numpy())
+            np.testing.assert_array_equal(h["actions"].numpy(), R.mb["actions"][k % T].cpu().numpy())
+            np.testing.assert_array_equal(h["values"].numpy(), R.mb["values"][k % T].cpu().numpy())
+            feed[g] = h["obs_in"].clone()
+    pipe.close()
+    for R in refs:
+        R.close()
