@@ -83,7 +83,7 @@ class HostRolloutPipeline:
         with torch.cuda.stream(st):
             R.sim.obs.copy_(h["obs_in"], non_blocking=True)        # the policy reads the observations the host handed over
             R.noise.copy_(h["noise"], non_blocking=True)
-            if self.graphs:
+            if self.graphs and R._warmed:      # a Rollout's very first step runs eagerly (one-time initialisations)
                 R.step_graphed_host_noise(n, after_env_step=read_back_env)
             else:
                 R.step(n, noise=R.noise, host_obs=True)
