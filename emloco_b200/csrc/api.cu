@@ -20,6 +20,24 @@ cudaError_t eml_linear_fma(const float*, long long, const float*, const float*, 
 cudaError_t eml_linear_tc(const float*, long long, const float*, const float*, float*, long long, long long, int, int,
                           const float*, const float*, float, int, cudaStream_t);
 
+cudaError_t eml_xform(const float* x, long long ldx, const float* rowvec, const float* rowscale, long long lds, const float* mean,
+                      const float* var, float eps, const float* gate, long long ldg, float scale, float* y32, long long ldy,
+                      float* yT32, long long ldyT, void* hi, void* lo, long long ld16, void* hiT, void* loT, long long ldT,
+                      float* colsum, float* sumsq, long long M, int K, cudaStream_t st);
+cudaError_t eml_ppo_heads(const float* mu, long long ldmu, const float* logstd, const float* actions, const float* old_neglogp,
+                          const float* adv, const float* value, const float* task_value, const float* returns, const float* old_mu,
+                          const float* old_sigma, float* dmu, long long lddmu, float* dvalue, float* dtask, float* stats, long long B,
+                          int A, float e_clip, float actor_coef, float critic_coef, float tv_coef, float bounds_coef, cudaStream_t st);
+cudaError_t eml_disc_heads(const float* logit, float* dlogit, float* stats, long long n_agent, long long n_demo, float coef, cudaStream_t st);
+cudaError_t eml_amp_dropout_mask(const float* u, float* mask, long long rows, float rate, cudaStream_t st);
+cudaError_t eml_rms_update(const float* x, long long ldx, long long M, int K, double* scratch, double* rmean, double* rvar, double* count,
+                           float* mean32, float* var32, float* inv32, float eps, cudaStream_t st);
+cudaError_t eml_grad_sumsq(const float* g, long long n, float* state, cudaStream_t st);
+cudaError_t eml_adam_clip(float* p, const float* g, float* m, float* v, long long n, float* state, float lr, float beta1, float beta2,
+                          float eps, float max_norm, float grad_scale, cudaStream_t st);
+cudaError_t eml_adam_begin(float* state, cudaStream_t st);
+cudaError_t eml_axpy(float* y, const float* x, float a, long long n, cudaStream_t st);
+
 static thread_local std::string g_err;
 static int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
     char buf[512];
@@ -568,6 +586,83 @@ int emloco_normalize(const float* d_x, int64_t ldx, float* d_y, int64_t ldy, int
                      const float* d_var, float eps, void* stream) {
     if (!d_x || !d_y || !d_mean || !d_var || M < 0 || K <= 0 || ldx < K || ldy < K) return fail(EMLOCO_EINVAL, "emloco_normalize: bad argument");
     CK(eml_normalize(d_x, ldx, d_y, ldy, M, K, d_mean, d_var, eps, (cudaStream_t)stream), "normalize");
+    return EMLOCO_OK;
+}
+
+// ---- PPO / AMP update step (csrc/update.cu) ----
+int emloco_xform(const float* d_x, int64_t ldx, const float* d_rowvec, const float* d_rowscale, int64_t lds, const float* d_mean,
+                 const float* d_var, float eps, const float* d_gate, int64_t ldg, float scale, float* d_y32, int64_t ldy,
+                 float* d_yT32, int64_t ldyT, uint16_t* d_hi, uint16_t* d_lo, int64_t ld16, uint16_t* d_hiT, uint16_t* d_loT,
+                 int64_t ldT, float* d_colsum, float* d_sumsq, int64_t M, int32_t K, void* stream) {
+    if ((!d_x && !d_rowvec) || M < 0 || K < 0 || ((d_mean == nullptr) != (d_var == nullptr)) || (d_mean && !d_x) ||
+        ((d_hi == nullptr) != (d_lo == nullptr)) || ((d_hiT == nullptr) != (d_loT == nullptr)))
+        return fail(EMLOCO_EINVAL, "emloco_xform: bad argument");
+    if ((d_hi && (ld16 < K)) || (d_hiT && (ldT < M)) || (d_y32 && ldy < K) || (d_yT32 && ldyT < M))
+        return fail(EMLOCO_EINVAL, "emloco_xform: output pitch smaller than the row length");
+    CK(eml_xform(d_x, ldx, d_rowvec, d_rowscale, lds, d_mean, d_var, eps, d_gate, ldg, scale, d_y32, ldy, d_yT32, ldyT, d_hi, d_lo, ld16,
+                 d_hiT, d_loT, ldT, d_colsum, d_sumsq, M, K, (cudaStream_t)stream), "xform");
+    return EMLOCO_OK;
+}
+
+int emloco_ppo_heads(const float* d_mu, int64_t ldmu, const float* d_logstd, const float* d_actions, const float* d_old_neglogp,
+                     const float* d_adv, const float* d_value, const float* d_task_value, const float* d_returns,
+                     const float* d_old_mu, const float* d_old_sigma, float* d_dmu, int64_t lddmu, float* d_dvalue, float* d_dtask,
+                     float* d_stats, int64_t B, int32_t A, float e_clip, float actor_coef, float critic_coef, float tv_coef,
+                     float bounds_coef, void* stream) {
+    if (!d_mu || !d_logstd || !d_actions || !d_old_neglogp || !d_adv || !d_value || !d_task_value || !d_returns || !d_dmu || !d_dvalue ||
+        !d_dtask || !d_stats || B < 0 || A <= 0 || ((d_old_mu == nullptr) != (d_old_sigma == nullptr)))
+        return fail(EMLOCO_EINVAL, "emloco_ppo_heads: bad argument");
+    CK(eml_ppo_heads(d_mu, ldmu, d_logstd, d_actions, d_old_neglogp, d_adv, d_value, d_task_value, d_returns, d_old_mu, d_old_sigma, d_dmu,
+                     lddmu, d_dvalue, d_dtask, d_stats, B, A, e_clip, actor_coef, critic_coef, tv_coef, bounds_coef, (cudaStream_t)stream),
+       "ppo heads");
+    return EMLOCO_OK;
+}
+
+int emloco_disc_heads(const float* d_logit, float* d_dlogit, float* d_stats, int64_t n_agent, int64_t n_demo, float coef, void* stream) {
+    if (!d_logit || !d_dlogit || !d_stats || n_agent < 0 || n_demo < 0) return fail(EMLOCO_EINVAL, "emloco_disc_heads: bad argument");
+    CK(eml_disc_heads(d_logit, d_dlogit, d_stats, n_agent, n_demo, coef, (cudaStream_t)stream), "disc heads");
+    return EMLOCO_OK;
+}
+
+int emloco_amp_dropout_mask(const float* d_u, float* d_mask, int64_t rows, float rate, void* stream) {
+    if (!d_u || !d_mask || rows < 0) return fail(EMLOCO_EINVAL, "emloco_amp_dropout_mask: bad argument");
+    CK(eml_amp_dropout_mask(d_u, d_mask, rows, rate, (cudaStream_t)stream), "amp dropout mask");
+    return EMLOCO_OK;
+}
+
+int emloco_rms_update(const float* d_x, int64_t ldx, int64_t M, int32_t K, double* d_scratch, double* d_running_mean,
+                      double* d_running_var, double* d_count, float* d_mean32, float* d_var32, float* d_inv_std32, float eps,
+                      void* stream) {
+    if (!d_x || !d_scratch || !d_running_mean || !d_running_var || !d_count || M < 0 || K < 0 ||
+        (d_mean32 && (!d_var32 || !d_inv_std32)))
+        return fail(EMLOCO_EINVAL, "emloco_rms_update: bad argument");
+    CK(eml_rms_update(d_x, ldx, M, K, d_scratch, d_running_mean, d_running_var, d_count, d_mean32, d_var32, d_inv_std32, eps,
+                      (cudaStream_t)stream), "rms update");
+    return EMLOCO_OK;
+}
+
+int emloco_adam_begin(float* d_state, void* stream) {
+    if (!d_state) return fail(EMLOCO_EINVAL, "emloco_adam_begin: null argument");
+    CK(eml_adam_begin(d_state, (cudaStream_t)stream), "adam begin");
+    return EMLOCO_OK;
+}
+
+int emloco_grad_sumsq(const float* d_grad, int64_t n, float* d_state, void* stream) {
+    if (!d_grad || !d_state || n < 0) return fail(EMLOCO_EINVAL, "emloco_grad_sumsq: bad argument");
+    CK(eml_grad_sumsq(d_grad, n, d_state, (cudaStream_t)stream), "grad sumsq");
+    return EMLOCO_OK;
+}
+
+int emloco_adam_clip(float* d_param, const float* d_grad, float* d_m, float* d_v, int64_t n, float* d_state, float lr, float beta1,
+                     float beta2, float eps, float max_norm, float grad_scale, void* stream) {
+    if (!d_param || !d_grad || !d_m || !d_v || !d_state || n < 0) return fail(EMLOCO_EINVAL, "emloco_adam_clip: bad argument");
+    CK(eml_adam_clip(d_param, d_grad, d_m, d_v, n, d_state, lr, beta1, beta2, eps, max_norm, grad_scale, (cudaStream_t)stream), "adam");
+    return EMLOCO_OK;
+}
+
+int emloco_axpy(float* d_y, const float* d_x, float a, int64_t n, void* stream) {
+    if (!d_y || !d_x || n < 0) return fail(EMLOCO_EINVAL, "emloco_axpy: bad argument");
+    CK(eml_axpy(d_y, d_x, a, n, (cudaStream_t)stream), "axpy");
     return EMLOCO_OK;
 }
 

@@ -386,6 +386,49 @@ int emloco_fill_next_values(const emloco_rollout_cfg* cfg, const float* d_value_
 int emloco_normalize(const float* d_x, int64_t ldx, float* d_y, int64_t ldy, int64_t M, int32_t K, const float* d_mean,
                      const float* d_var, float eps, void* stream);
 
+/* ---- PPO / AMP update step: `AMPValueAgent.calc_gradients`, pacer/pacer/learning/amp_continuous_value.py:276-428
+ * (losses: learning/common_agent.py:594-602,657-683, amp_continuous_value.py:430-444, amp_continuous.py:536-616; optimiser:
+ * common_agent.py:84-87 torch.optim.Adam + nn.utils.clip_grad_norm_(grad_norm 50); multi-GPU: Horovod `optimizer.synchronize()`
+ * :386-394, replaced by one NCCL all-reduce over a flat gradient buffer).  The dense layers of forward, dgrad, wgrad and of the
+ * gradient-penalty double backward run on emloco_linear_bf16x3; the entries below are everything else (csrc/update.cu).
+ *
+ * emloco_xform: y[m,k] = scale * rowscale[m] * src[m,k] * (gate[m,k] > 0), src = clamp((x-mean)/sqrt(var+eps),+-5) | x | rowvec[k]
+ * (x == NULL).  Any subset of outputs: fp32 y [M,K] and y^T [K,M]; bf16 hi/lo split of y and of y^T (the A / W operands of
+ * the GEMMs: activations and weight transposes for dgrad, transposed activations and output gradients for wgrad); colsum[k] +=
+ * sum_m y (bias gradients); *sumsq += sum y^2 (the gradient penalty).  Pointers NULL when unused. */
+int emloco_xform(const float* d_x, int64_t ldx, const float* d_rowvec, const float* d_rowscale, int64_t lds, const float* d_mean,
+                 const float* d_var, float eps, const float* d_gate, int64_t ldg, float scale, float* d_y32, int64_t ldy,
+                 float* d_yT32, int64_t ldyT, uint16_t* d_hi, uint16_t* d_lo, int64_t ld16, uint16_t* d_hiT, uint16_t* d_loT,
+                 int64_t ldT, float* d_colsum, float* d_sumsq, int64_t M, int32_t K, void* stream);
+/* actor (PPO clip), critic, task-value and bound losses -> gradients of the weighted, batch-averaged total loss w.r.t. mu [B,A],
+ * value [B], task value [B]; d_stats[7] += sums of {actor loss, critic loss, task-value loss, bound loss, clipped, kl, entropy}. */
+int emloco_ppo_heads(const float* d_mu, int64_t ldmu, const float* d_logstd, const float* d_actions, const float* d_old_neglogp,
+                     const float* d_adv, const float* d_value, const float* d_task_value, const float* d_returns,
+                     const float* d_old_mu, const float* d_old_sigma, float* d_dmu, int64_t lddmu, float* d_dvalue, float* d_dtask,
+                     float* d_stats, int64_t B, int32_t A, float e_clip, float actor_coef, float critic_coef, float tv_coef,
+                     float bounds_coef, void* stream);
+/* discriminator prediction loss 0.5 * (BCE(fake, 0) + BCE(real, 1)) * coef -> d loss / d logit; rows [0, n_agent) are the agent
+ * + replay logits, [n_agent, n_agent + n_demo) the demo logits; d_stats[4] += {sum softplus(fake), sum softplus(-real), #fake < 0,
+ * #real > 0}. */
+int emloco_disc_heads(const float* d_logit, float* d_dlogit, float* d_stats, int64_t n_agent, int64_t n_demo, float coef, void* stream);
+/* whole-joint dropout masks of the AMP observations (learning/amp_models.py:49-90): u [rows,19] uniform draws -> mask [rows,3090]. */
+int emloco_amp_dropout_mask(const float* d_u, float* d_mask, int64_t rows, float rate, void* stream);
+/* RunningMeanStd training-mode update (utils/running_mean_std.py:33-43,86-96) of float64 running_mean / running_var / count from
+ * the batch x [M,K]; also refreshes the fp32 copies mean / var / 1/sqrt(var+eps) (may be NULL).  d_scratch: 2*K doubles, zero on
+ * entry, left zero. */
+int emloco_rms_update(const float* d_x, int64_t ldx, int64_t M, int32_t K, double* d_scratch, double* d_running_mean,
+                      double* d_running_var, double* d_count, float* d_mean32, float* d_var32, float* d_inv_std32, float eps,
+                      void* stream);
+/* clip_grad_norm_ + Adam over flat buffers.  d_state[2] = {step count, sum of squares of the gradient}: emloco_adam_begin
+ * increments the step and clears the sum, emloco_grad_sumsq accumulates it (after the all-reduce, on the SUMMED gradient),
+ * emloco_adam_clip scales the gradient by grad_scale (1 / world size) and min(1, max_norm / (norm + 1e-6)) and steps. */
+int emloco_adam_begin(float* d_state, void* stream);
+int emloco_grad_sumsq(const float* d_grad, int64_t n, float* d_state, void* stream);
+int emloco_adam_clip(float* d_param, const float* d_grad, float* d_m, float* d_v, int64_t n, float* d_state, float lr, float beta1,
+                     float beta2, float eps, float max_norm, float grad_scale, void* stream);
+/* y += a * x (weight-decay / logit-regularisation terms of the discriminator loss, amp_continuous.py:548-550,585-589). */
+int emloco_axpy(float* d_y, const float* d_x, float a, int64_t n, void* stream);
+
 int emloco_sync(emloco_sim* sim);
 const char* emloco_last_error(void);
 const char* emloco_version(void);

@@ -503,6 +503,186 @@ def reference_play_block(N=96, steps=8, seed=31):
         out[f"row_{k}"] = np.stack(rec[k])
     return out
 
+UPDATE_MU_GAIN = 3.0
+UPDATE_CFG = dict(e_clip=0.2, actor_coef=1.0, critic_coef=5.0, tv_coef=5.0, bounds_loss_coef=10.0, entropy_coef=0.0, disc_coef=5.0,
+                  disc_logit_reg=0.01, disc_grad_penalty=5.0, disc_weight_decay=0.0001, dropout_rate=0.3, lr=2e-5, grad_norm=50.0)
+# the values of data/cfg/train/rlg/amp_humanoid_smpl_sept_task.yaml:84-122 (checked against the file by reference_update_step)
+
+
+def synth_update_batch(B, Ba, seed):
+    """Seeded minibatch of the PPO / AMP update (the `input_dict` of calc_gradients): also used, same code, by the GPU tests."""
+    rng = np.random.default_rng(seed)
+    f = np.float32
+    obs = rng.normal(0, 2.0, (B, 1422)).astype(f); obs[:, ::7] *= 4
+    # `actions` / `old_logp_actions` here are placeholders: reference_update_step replaces them by samples around the
+    # network's own mu (so that PPO ratios straddle the clip range) and stores those in the fixture
+    d = dict(obs=obs, actions=rng.normal(0, 0.4, (B, 69)).astype(f), old_logp_actions=rng.normal(-140, 3, B).astype(f),
+             advantages=rng.normal(0, 1, B).astype(f), returns=rng.normal(0, 1, (B, 1)).astype(f), old_values=rng.normal(0, 1, (B, 1)).astype(f),
+             mu=rng.normal(0, 0.3, (B, 69)).astype(f), sigma=np.full((B, 69), np.exp(-2.9), f))
+    for k in ("amp_obs", "amp_obs_replay", "amp_obs_demo"):
+        a = rng.normal(0, 2.0, (Ba, 3090)).astype(f); a[:, ::11] *= 4
+        d[k] = a
+    d["dropout_u"] = rng.random((19, Ba, 3)).astype(f)               # get_dropout_mask: one torch.rand(B, 3) per joint
+    stats = dict(obs_mean=rng.normal(0, 1, 1422), obs_var=rng.uniform(0.05, 4, 1422), obs_count=np.float64(1000.0),
+                 amp_mean=rng.normal(0, 1, 3090), amp_var=rng.uniform(0.05, 4, 3090), amp_count=np.float64(500.0))
+    return d, stats
+
+
+def reference_update_step(B=48, Ba=40, seed=61, wseed=21):
+    """f1: one `calc_gradients` call (amp_continuous_value.py:276-428) on the reference's own network and loss code - body of
+    the method from set_train() to the assembled loss executed by line range (ref_extract `Holder.calc_loss`), dropout masks from
+    the reference's get_dropout_mask with recorded draws, `loss.backward()`, nn.utils.clip_grad_norm_(50) and one
+    torch.optim.Adam(lr 2e-5, eps 1e-8) step (common_agent.py:84-87).  rl_games' model wrapper (ModelA2CContinuousLogStd, 1.1.4,
+    not in the tree) is restated inline: mu / logstd / value from the network, neglogp and entropy of Normal(mu, exp(logstd)).
+    The 11.2 M-element gradient does not fit a fixture: per parameter tensor the fixture keeps the L2 norm, the sum and 48 sampled
+    entries of the gradient and of the Adam update; the tests recompute all of them."""
+    import types
+    import yaml
+    from . import netweights
+    R = ref_extract.load()
+    torch = R.torch
+    cfgy = yaml.safe_load(open(os.path.join(ref_extract.PACER, "data/cfg/train/rlg/amp_humanoid_smpl_sept_task.yaml")))["params"]["config"]
+    U = UPDATE_CFG
+    for a, b in (("e_clip", "e_clip"), ("actor_coef", "actor_coef"), ("critic_coef", "critic_coef"), ("tv_coef", "tv_coef"),
+                 ("bounds_loss_coef", "bounds_loss_coef"), ("entropy_coef", "entropy_coef"), ("disc_coef", "disc_coef"),
+                 ("disc_logit_reg", "disc_logit_reg"), ("disc_grad_penalty", "disc_grad_penalty"), ("disc_weight_decay", "disc_weight_decay"),
+                 ("lr", "learning_rate"), ("grad_norm", "grad_norm")):
+        assert float(cfgy[b]) == float(U[a]), (a, cfgy[b])
+    net = ref_extract.load_network(seed=1)
+    sd = netweights.synth_state_dict(wseed, mu_gain=UPDATE_MU_GAIN)
+    net.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in sd.items()}, strict=True)
+    net.train()
+    batch, stats = synth_update_batch(B, Ba, seed)
+    # the rollout that "collected" this minibatch: actions sampled around the current policy's mean, old neglogp a little off
+    rng = np.random.default_rng(seed + 1)
+    with torch.no_grad():
+        import contextlib as _c, io as _io
+        with _c.redirect_stdout(_io.StringIO()):
+            tmp = R.RunningMeanStd((1422,))
+        tmp.running_mean[:] = torch.from_numpy(stats["obs_mean"]); tmp.running_var[:] = torch.from_numpy(stats["obs_var"]); tmp.eval()
+        mu0, ls0 = net.eval_actor(tmp(torch.from_numpy(batch["obs"])))
+        mu0, sg0 = mu0.numpy(), np.exp(ls0.numpy())
+    batch["actions"] = (mu0 + sg0 * rng.normal(0, 1, mu0.shape)).astype(np.float32)
+    nl0 = 0.5 * (((batch["actions"] - mu0) / sg0) ** 2).sum(-1) + 0.5 * np.log(2 * np.pi) * 69 + np.log(sg0).sum(-1)
+    batch["old_logp_actions"] = (nl0 + rng.normal(0, 0.15, B)).astype(np.float32)
+    batch["mu"] = (mu0 + rng.normal(0, 0.02, mu0.shape)).astype(np.float32)
+    H = ref_extract.load_agent_blocks()
+    h = H()
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        h.running_mean_std, h._amp_input_mean_std = R.RunningMeanStd((1422,)), R.RunningMeanStd((3090,))
+    for m, pre in ((h.running_mean_std, "obs"), (h._amp_input_mean_std, "amp")):
+        m.running_mean[:] = torch.from_numpy(stats[pre + "_mean"]); m.running_var[:] = torch.from_numpy(stats[pre + "_var"])
+        m.count.fill_(float(stats[pre + "_count"]))
+    h.set_train = lambda: (h.running_mean_std.train(), h._amp_input_mean_std.train())
+    h.normalize_input = h._normalize_amp_input = True
+    h._amp_minibatch_size = Ba
+    h.last_lr, h.e_clip = U["lr"], U["e_clip"]
+    h.config = {"amp_dropout": True}
+    h.vec_env = types.SimpleNamespace(env=types.SimpleNamespace(task=types.SimpleNamespace(_num_amp_obs_steps=15, cfg={"env": {}})))
+    h.motion_sym_loss = h.is_rnn = h.mixed_precision = h.clip_value = False
+    h.critic_coef, h._actor_coef, h.entropy_coef, h.bounds_loss_coef = U["critic_coef"], U["actor_coef"], U["entropy_coef"], U["bounds_loss_coef"]
+    h._disc_coef, h._tv_coef = U["disc_coef"], U["tv_coef"]
+    h._disc_logit_reg, h._disc_grad_penalty, h._disc_weight_decay = U["disc_logit_reg"], U["disc_grad_penalty"], U["disc_weight_decay"]
+    # dropout draws replayed: the hosted module's `torch.rand` returns the recorded uniforms, one [Ba, 3] per joint
+    mod = sys_modules_get("emloco_ref_agent")
+    draws = iter(torch.from_numpy(batch["dropout_u"][j]) for j in range(19))
+
+    class TorchProxy:
+        def __getattr__(self, k):
+            return getattr(torch, k)
+
+        def rand(self, *a, **kw):
+            t = next(draws)
+            assert tuple(a) == tuple(t.shape), (a, t.shape)
+            return t
+    captured = {}
+
+    def model(bd):
+        # rl_games 1.1.4 ModelA2CContinuousLogStd.Network.forward (is_train branch), then learning/amp_models.py:20-44 and
+        # learning/amp_sept_value_models.py:22-30
+        mu, logstd, value, states = net(bd)                                   # AMPBuilder.Network.forward (amp_network_builder.py:39-48)
+        sigma = torch.exp(logstd)
+        distr = torch.distributions.Normal(mu, sigma)
+        entropy = distr.entropy().sum(dim=-1)
+        x = bd["prev_actions"]
+        neglogp = 0.5 * (((x - mu) / sigma) ** 2).sum(dim=-1) + 0.5 * np.log(2.0 * np.pi) * x.size()[-1] + logstd.sum(dim=-1)
+        res = {"prev_neglogp": torch.squeeze(neglogp), "values": value, "entropy": entropy, "rnn_states": states, "mus": mu, "sigmas": sigma}
+        amp_obs, amp_replay, amp_demo = bd["amp_obs"], bd["amp_obs_replay"], bd["amp_obs_demo"]
+        if bd.get("amp_dropout", False):
+            mod.torch = TorchProxy()
+            try:
+                dm = h.get_dropout_mask(bd["amp_obs"], bd["amp_steps"], bd["env_cfg"])
+            finally:
+                mod.torch = torch
+            captured["mask"] = dm.numpy().copy()
+            amp_obs, amp_replay, amp_demo = (h.dropout_amp_obs(amp_obs, dm[..., 0]), h.dropout_amp_obs(amp_replay, dm[..., 1]),
+                                             h.dropout_amp_obs(amp_demo, dm[..., 2]))
+        res["disc_agent_logit"] = net.eval_disc(amp_obs)
+        res["disc_agent_replay_logit"] = net.eval_disc(amp_replay)
+        res["disc_demo_logit"] = net.eval_disc(amp_demo)
+        res["task_values"] = net.eval_task_value(bd["obs"])
+        return res
+    model.a2c_network = net
+    model.parameters = net.parameters
+    h.model = model
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    inp = {k: T(batch[k]) for k in ("old_values", "old_logp_actions", "advantages", "mu", "sigma", "returns", "actions", "obs", "amp_obs",
+                                    "amp_obs_replay", "amp_obs_demo")}
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        loc = h.calc_loss(inp)
+    loss = loc["loss"]
+    params = dict(net.named_parameters())
+    opt = torch.optim.Adam(net.parameters(), float(U["lr"]), eps=1e-08, weight_decay=0)        # common_agent.py:84-87
+    for p in net.parameters():
+        p.grad = None
+    loss.backward()
+    grads = {k: (p.grad.detach().numpy().copy() if p.grad is not None else None) for k, p in params.items()}
+    total_norm = float(torch.nn.utils.clip_grad_norm_(net.parameters(), U["grad_norm"]))
+    before = {k: p.detach().numpy().copy() for k, p in params.items()}
+    opt.step()
+    with torch.no_grad():                                                               # torch_ext.policy_kl (rl_games 1.1.4), reduce=True
+        p0m, p0s, p1m, p1s = loc["mu"].detach(), loc["sigma"].detach(), inp["mu"], inp["sigma"]
+        c1 = torch.log(p1s / p0s + 1e-5); c2 = (p0s ** 2 + (p1m - p0m) ** 2) / (2.0 * (p1s ** 2 + 1e-5))
+        kl = (c1 + c2 - 0.5).sum(dim=-1).mean().item()
+    out = dict(B=B, Ba=Ba, seed=seed, wseed=wseed, in_actions=batch["actions"], in_old_logp_actions=batch["old_logp_actions"], in_mu=batch["mu"],
+               kl=np.float32(kl), weights_checksum=netweights.checksum(sd), loss=np.float32(loss.item()),
+               a_loss=np.float32(loc["a_loss"].item()), c_loss=np.float32(loc["c_loss"].item()), b_loss=np.float32(loc["b_loss"].item()),
+               tv_loss=np.float32(loc["tv_loss"].item()), entropy=np.float32(loc["entropy"].item()),
+               disc_loss=np.float32(loc["disc_loss"].item()), disc_grad_penalty=np.float32(loc["disc_info"]["disc_grad_penalty"].item()),
+               disc_logit_loss=np.float32(loc["disc_info"]["disc_logit_loss"].item()),
+               disc_agent_acc=np.float32(loc["disc_info"]["disc_agent_acc"].item()), disc_demo_acc=np.float32(loc["disc_info"]["disc_demo_acc"].item()),
+               a_clip_frac=np.float32(loc["a_info"]["actor_clipped"].float().mean().item()), total_norm=np.float32(total_norm),
+               mus=loc["mu"].detach().numpy(), values=loc["values"].detach().numpy(), task_values=loc["task_values"].detach().numpy(),
+               neglogp=loc["action_log_probs"].detach().numpy(), disc_agent_logit=loc["disc_agent_cat_logit"].detach().numpy(),
+               disc_demo_logit=loc["disc_demo_logit"].detach().numpy(), dropout_mask=captured["mask"][:, :206, :].astype(np.uint8),
+               obs_mean_after=h.running_mean_std.running_mean.numpy().copy(), obs_var_after=h.running_mean_std.running_var.numpy().copy(),
+               obs_count_after=np.float64(h.running_mean_std.count.item()),
+               amp_mean_after=h._amp_input_mean_std.running_mean.numpy().copy(), amp_var_after=h._amp_input_mean_std.running_var.numpy().copy(),
+               amp_count_after=np.float64(h._amp_input_mean_std.count.item()))
+    assert (captured["mask"].reshape(Ba, 15, 206, 3) == captured["mask"][:, None, :206, :]).all()      # the 15 steps share one mask
+    srng = np.random.default_rng(seed + 5)
+    for k, p in params.items():
+        g = grads[k]
+        if g is None:
+            assert k == "sigma"
+            continue
+        idx = srng.integers(0, g.size, 48)
+        out[f"gidx_{k}"] = idx
+        out[f"gnorm_{k}"] = np.float64(np.linalg.norm(g.astype(np.float64)))
+        out[f"gsum_{k}"] = np.float64(g.astype(np.float64).sum())
+        out[f"gval_{k}"] = g.reshape(-1)[idx].copy()
+        out[f"step_{k}"] = (p.detach().numpy().reshape(-1)[idx] - before[k].reshape(-1)[idx]).astype(np.float32)
+    return out
+
+
+def sys_modules_get(name):
+    import sys
+    return sys.modules[name]
+
+
 
 def reference_rms_update(seed=51):
     """RunningMeanStd in training mode (utils/running_mean_std.py:86-96): statistics after each of three batches."""
@@ -569,6 +749,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "play_block.npz"), **reference_play_block())
     np.savez_compressed(os.path.join(OUT, "plausibl.npz"), **reference_plausibl())
     np.savez_compressed(os.path.join(OUT, "rms_update.npz"), **reference_rms_update())
+    np.savez_compressed(os.path.join(OUT, "update_step.npz"), **reference_update_step())
     traj, pose, vel = synth_locoval(64, 2)
     W, out = reference_locoval(traj, pose, vel)
     np.savez_compressed(os.path.join(OUT, "locoval.npz"), traj=traj, pose=pose, vel=vel,

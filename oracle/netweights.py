@@ -14,7 +14,7 @@ SHAPES = (("actor_mlp.0", 2048, 624), ("actor_mlp.2", 1024, 2048), ("critic_mlp.
           ("_value_logits", 1, 6))
 
 
-def synth_state_dict(seed=0, sigma=-2.9):
+def synth_state_dict(seed=0, sigma=-2.9, mu_gain=1.0):
     rng = np.random.default_rng(seed)
     sd = {}
     for name, n_out, n_in in SHAPES:
@@ -23,6 +23,7 @@ def synth_state_dict(seed=0, sigma=-2.9):
             b = 1.0                                                  # uniform(-1, 1) heads (DISC_LOGIT_INIT_SCALE)
         sd[f"{name}.weight"] = rng.uniform(-b, b, (n_out, n_in)).astype(np.float32)
         sd[f"{name}.bias"] = rng.uniform(-0.1, 0.1, n_out).astype(np.float32)
+    sd["mu.weight"] *= np.float32(mu_gain)            # > 1: pushes some action means beyond the +-1 soft bound (bound_loss)
     sd["sigma"] = np.full(69, sigma, np.float32)
     return sd
 

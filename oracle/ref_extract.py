@@ -236,6 +236,10 @@ def load_agent_blocks():
       * CommonAgent._eval_critic, _actor_loss, _critic_loss, _calc_advs, bound_loss (learning/common_agent.py:594-602,647-696),
       * AMPAgent._disc_loss .. _compute_disc_acc (learning/amp_continuous.py:536-616), _sym_loss (:517-534),
       * AMPValueAgent._task_value_loss (learning/amp_continuous_value.py:430-444),
+      * AMPValueAgent.calc_gradients up to the total loss (learning/amp_continuous_value.py:277-362) as `Holder.calc_loss`,
+      * ModelAMPContinuous.Network.dropout_amp_obs / get_dropout_mask (learning/amp_models.py:46-90),
+      * AMPValueAgent.calc_gradients up to the total loss (learning/amp_continuous_value.py:277-362) as `Holder.calc_loss`,
+      * ModelAMPContinuous.Network.dropout_amp_obs / get_dropout_mask (learning/amp_models.py:46-90),
       * the per-step body of AMPValueAgent.play_steps from env_step to the end of the no_grad block
         (learning/amp_continuous_value.py:61-121) as `Holder.play_block(self)`."""
     if "agent" in _cache:
@@ -249,6 +253,12 @@ def load_agent_blocks():
     src += _lines(ca, 594, 602) + "\n" + _lines(ca, 647, 696) + "\n"
     src += _lines(av, 430, 444) + "\n"
     # locals of play_steps that the block reads (n, res_dict, terminated_flags, reward_raw) become arguments; its locals are returned
+    # calc_gradients from set_train() to the assembled total loss (learning/amp_continuous_value.py:277-362): locals returned
+    src += ("    def calc_loss(self, input_dict):\n" + textwrap.indent(textwrap.dedent(_lines(av, 277, 362)), " " * 8)
+            + "\n        return locals()\n")
+    # ModelAMPContinuous.Network.dropout_amp_obs / get_dropout_mask (learning/amp_models.py:46-90)
+    am = os.path.join(PACER, "learning/amp_models.py")
+    src += textwrap.indent(textwrap.dedent(_lines(am, 46, 90)), " " * 4) + "\n"
     src += ("    def play_block(self, n, res_dict, terminated_flags, reward_raw):\n"
             + textwrap.indent(textwrap.dedent(_lines(av, 61, 121)), " " * 8) + "\n        return locals()\n")
     tmp = tempfile.mkdtemp(prefix="emloco_ref_")
