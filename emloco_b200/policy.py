@@ -181,6 +181,8 @@ class RolloutNets:
         ps = (n.actor_mlp[0].weight, n.actor_mlp[0].bias, n.critic_mlp[0].weight, n.critic_mlp[0].bias)
         key = tuple((p.data_ptr(), p._version) for p in ps)
         c = self._stacked
+        if c is not None and c[0] == "adopted":       # views of a flat parameter buffer (update.PPOUpdate.adopt_into): always current
+            return c[1], c[2]
         if c is None or c[1].device != ps[0].device:
             c = self._stacked = [key, torch.cat([ps[0].detach(), ps[2].detach()]).contiguous(),
                                  torch.cat([ps[1].detach(), ps[3].detach()]).contiguous()]
@@ -470,9 +472,18 @@ class _TcWeights:
         self._c = {}
         self.generation = 0
 
+    def adopt(self, name, split):
+        """Use a split owned (and kept current) by someone else - the update step refreshes its operand splits after every
+        optimiser step (update.PPOUpdate.adopt_into); no version checks, no copies."""
+        if name not in self._c or self._c[name][1] is not split:
+            self.generation += 1
+        self._c[name] = ["adopted", split]
+
     def get(self, name, weight):
-        key = (weight.data_ptr(), weight._version)
         ent = self._c.get(name)
+        if ent is not None and ent[0] == "adopted":
+            return ent[1]
+        key = (weight.data_ptr(), weight._version)
         if ent is not None and ent[0] == key:
             return ent[1]
         w = weight.detach()
