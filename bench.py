@@ -192,6 +192,87 @@ def run_reference(args):
 
 
 # =====================================================================================================
+# PPO / AMP update step (BASELINE configs[2]: training step with the NCCL gradient all-reduce)
+# =====================================================================================================
+def train_step_bench(args, R, D, rank, world, pk):
+    """One "train step" = one minibatch of `AMPValueAgent.calc_gradients` (amp_continuous_value.py:276-428): forward in training
+    mode, losses, backward, gradient all-reduce over the ranks (inside the timed window), clip-norm, Adam, operand refresh -
+    emloco_b200.update.PPOUpdate.  Minibatches are contiguous slices of the experience the rollout just produced (zero copy);
+    the demo buffer is synthetic (the AMASS clips are not redistributable).  Device-timed, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from emloco_b200 import _lib
+    from emloco_b200.update import PPOUpdate
+    T, N = R.T, R.N
+    B = Ba = args.minibatch
+    up = PPOUpdate(R.net, R.obs_norm, R.amp_norm, B, Ba)
+    up.adopt_into(R.nets)
+    out = R.finish()
+    fl = lambda t: t.reshape(T * N, *t.shape[2:])
+    adv = fl(out["advantages"])[:, 0]
+    adv = ((adv - adv.mean()) / (adv.std() + 1e-8)).contiguous()                       # _calc_advs (common_agent.py:685-696)
+    ret = fl(out["returns"]); ret = ((ret - ret.mean()) / (ret.std() + 1e-5)).contiguous()
+    obs, act, nlp, mus = fl(R.mb["obses"][:T]), fl(R.mb["actions"]), fl(R.mb["neglogpacs"].unsqueeze(-1))[:, 0], fl(R.mb["mus"])
+    amp = fl(R.mb["amp_obs"])
+    sig = torch.full_like(mus, float(torch.exp(R.net.sigma[0])))
+    g = torch.Generator(device=obs.device).manual_seed(1234 + rank)
+    demo = torch.randn(B, 3090, device=obs.device, generator=g)
+    nmb = (T * N) // B
+    batches = []
+    for i in range(nmb):
+        sl = slice(i * B, (i + 1) * B)
+        rp = slice(((i + 1) % nmb) * B, ((i + 1) % nmb + 1) * B)                     # "replay" rows: another minibatch of the horizon
+        batches.append(dict(obs=obs[sl], actions=act[sl], old_logp_actions=nlp[sl].contiguous(), advantages=adv[sl], returns=ret[sl],
+                            mu=mus[sl], sigma=sig[sl], amp_obs=amp[sl][:Ba], amp_obs_replay=amp[rp][:Ba], amp_obs_demo=demo))
+    K = args.train_steps
+
+    def barrier():
+        D.barrier(); torch.cuda.synchronize()
+    for i in range(3):
+        up.step(batches[i % nmb])
+    barrier()
+    m0, l0 = _lib.mac_count, _lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        up.step(batches[i % nmb])
+    e1.record()
+    barrier()
+    ms = D.max_over_ranks(e0.elapsed_time(e1), device="cuda") / K
+    macs, launches = (_lib.mac_count - m0) / K, (_lib.launch_count - l0) / K
+    # the same step without the optimiser half / without the collective, and the collective alone (bus bandwidth)
+    e0.record()
+    for i in range(K):
+        up.forward_backward(batches[i % nmb])
+    e1.record()
+    barrier()
+    fb_ms = D.max_over_ranks(e0.elapsed_time(e1), device="cuda") / K
+    ar = None
+    if world > 1:
+        flat = up.flat.g
+        for _ in range(3):
+            dist.all_reduce(flat)
+        barrier()
+        e0.record()
+        for _ in range(20):
+            dist.all_reduce(flat)
+        e1.record()
+        barrier()
+        ar_ms = D.max_over_ranks(e0.elapsed_time(e1), device="cuda") / 20
+        nbytes = flat.numel() * 4
+        ar = {"bytes": nbytes, "ms": ar_ms, "algbw_gbs": nbytes / (ar_ms * 1e-3) / 1e9, "busbw_gbs": nbytes / (ar_ms * 1e-3) / 1e9 * 2 * (world - 1) / world,
+              "exposed_ms": max(ms - fb_ms, 0.0), "note": "exposed = (step - forward/backward-only step), i.e. collective + clip-norm + Adam + operand refresh not hidden"}
+    info = up.info()
+    tf = 2 * macs / (ms * 1e-3) / 1e12
+    return {"metric": "train_samples_per_sec", "value": world * B / (ms * 1e-3), "unit": "samples/s", "ms_per_minibatch": ms,
+            "forward_backward_ms": fb_ms, "minibatch": B, "amp_minibatch": Ba, "minibatches_per_epoch": nmb, "steps": K,
+            "gemm_macs_per_minibatch": macs, "launches_per_minibatch": launches,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": tf / pk["tf_sustained"],
+                         "note": "algorithmic FLOPs of the GEMMs (forward + dgrad + wgrad + gradient-penalty double backward) counted once; bf16x3 issues 3 MMAs per product"},
+            "allreduce": ar, "parameters": up.flat.n, "losses": {k: info[k] for k in ("a_loss", "c_loss", "tv_loss", "b_loss", "disc_grad_penalty", "total_norm")}}
+
+
+# =====================================================================================================
 # GPU arm
 # =====================================================================================================
 def run_ours(args):
@@ -342,6 +423,10 @@ def run_ours(args):
                                    "note": "critic(next obs) reused from the next step's policy pass; compact critic pass for timed-out envs"}}
         R = R2
 
+    train = None
+    if not args.no_train:
+        train = train_step_bench(args, R, D, rank, world, pk)
+
     out = None
     if rank == 0:
         # ---- LocoVal scores/s: 1M synthetic 12-step futures (configs[3]), device-resident ----
@@ -419,7 +504,7 @@ def run_ours(args):
             "post_horizon_ms": finish_ms,
             "post_horizon_share": {"passes_in_window": fin_in_window, "expected": K / HORIZON, "charged_ms": fin_share * finish_ms},
             "locoval": {"metric": "locoval_scores_per_sec", "value": lv_rate, "unit": "scores/s", "batch": B, "ms": lv_ms},
-            "cpu_baseline": cpu, "variants": variant,
+            "cpu_baseline": cpu, "variants": variant, "train_step": train,
         }
         print(json.dumps(out), flush=True)
     R.close()
@@ -444,6 +529,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the value-reuse variant measurement")
     ap.add_argument("--serial", action="store_true", help="no parallel graph branches (critic / discriminator / LocoVal / heads)")
+    ap.add_argument("--minibatch", type=int, default=16384, help="PPO / AMP minibatch (rows) of the train-step measurement")
+    ap.add_argument("--train-steps", type=int, default=16)
+    ap.add_argument("--no-train", action="store_true", help="skip the train-step (update) measurement")
     ap.add_argument("--e2e-groups", type=int, default=2, help="env groups of the end-to-end (host buffer) pipeline")
     ap.add_argument("--eager", action="store_true", help="launch every kernel from the host instead of replaying CUDA graphs")
     args = ap.parse_args()

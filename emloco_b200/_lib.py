@@ -156,6 +156,7 @@ LAUNCHES = {"emloco_step": 2, "emloco_physics_step": 1, "emloco_post_step": 1, "
             "emloco_xform": 1, "emloco_ppo_heads": 1, "emloco_disc_heads": 1, "emloco_amp_dropout_mask": 1, "emloco_rms_update": 2,
             "emloco_adam_begin": 1, "emloco_grad_sumsq": 1, "emloco_adam_clip": 1, "emloco_axpy": 1}
 launch_count = 0
+mac_count = 0          # multiply-accumulates of the dense-layer launches (M * N * K each), for the benches' FLOP figures
 
 
 def check(rc, what=""):

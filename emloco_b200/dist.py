@@ -130,6 +130,32 @@ class FlatGrads:
         return self.flat.numel() * 4
 
 
+class BucketedAllReduce:
+    """The gradient all-reduce of the update step in two buckets over ONE flat buffer: `start_first()` launches the reduction
+    of [0, split) as soon as that part of the backward pass has been queued (asynchronously: the kernels issued afterwards
+    overlap it), `finish()` reduces [split, n) and waits for both.  Sums, does not average - the 1 / world factor is folded
+    into the optimiser kernel.  World size 1 or an uninitialised process group: no-ops."""
+
+    def __init__(self, flat, split, overlap=True):
+        self.flat, self.split, self.overlap = flat, int(split), bool(overlap)
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self._pending = None
+
+    def start_first(self):
+        if self.world > 1 and self.overlap and 0 < self.split < self.flat.numel():
+            self._pending = dist.all_reduce(self.flat[:self.split], op=dist.ReduceOp.SUM, async_op=True)
+
+    def finish(self):
+        if self.world <= 1:
+            return
+        if self._pending is not None:
+            dist.all_reduce(self.flat[self.split:], op=dist.ReduceOp.SUM)
+            self._pending.wait()
+            self._pending = None
+        else:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+
+
 def finalize():
     if dist.is_initialized():
         dist.barrier()

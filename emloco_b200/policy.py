@@ -443,6 +443,7 @@ def linear_bf16x3(a: _Split, w: _Split, bias, relu, y32=None, y16: _Split = None
           into the epilogue (emloco_linear_bf16x3_head); y32 / y16 may then be omitted."""
     M, K, N = a.rows, a.K, w.rows
     assert w.K == K
+    _lib.mac_count += M * N * K
     if y32 is not None:
         assert y32.shape == (M, N) and y32.stride(1) == 1
     args = (_ptr(a.hi), _ptr(a.lo), a.ld, _ptr(w.hi), _ptr(w.lo), w.ld, _ptr(bias), M, N, K, int(bool(relu)) | (int(tile) << 8) | (int(splits) << 20),

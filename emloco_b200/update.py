@@ -66,8 +66,9 @@ class FlatParams:
     the same layout.  Order: the big GEMM-written weights first (actor / critic first layers adjacent = one stacked [4096,624]
     matrix), then every tensor whose gradient is accumulated by atomics (biases, single-row heads) in one tail block that is
     cleared with one memset per step."""
-    GEMM = ("actor_mlp.0.weight", "critic_mlp.0.weight", "actor_mlp.2.weight", "critic_mlp.2.weight", "mu.weight", "_task_mlp.0.weight",
-            "_task_mlp.2.weight", "_disc_mlp.0.weight", "_disc_mlp.2.weight", "_task_value_mlp.0.weight", "_task_value_mlp.2.weight")
+    GEMM = ("_disc_mlp.0.weight", "_disc_mlp.2.weight",                       # bucket 0: complete when the discriminator's backward is
+            "actor_mlp.0.weight", "critic_mlp.0.weight", "actor_mlp.2.weight", "critic_mlp.2.weight", "mu.weight", "_task_mlp.0.weight",
+            "_task_mlp.2.weight", "_task_value_mlp.0.weight", "_task_value_mlp.2.weight")
     TAIL = ("actor_mlp.0.bias", "critic_mlp.0.bias", "actor_mlp.2.bias", "critic_mlp.2.bias", "mu.bias", "value.weight", "value.bias",
             "_task_mlp.0.bias", "_task_mlp.2.bias", "_disc_mlp.0.bias", "_disc_mlp.2.bias", "_disc_logits.weight", "_disc_logits.bias",
             "_task_value_mlp.0.bias", "_task_value_mlp.2.bias", "_value_logits.weight", "_value_logits.bias")
@@ -85,6 +86,7 @@ class FlatParams:
             self.off[k] = n
             n += (named[k].numel() + 3) // 4 * 4                       # 16-byte aligned starts
         self.n = n
+        self.bucket0 = self.off["actor_mlp.0.weight"]                      # [0, bucket0): discriminator weights
         z = lambda: torch.zeros(n, device=dev, dtype=torch.float32)
         self.p, self.g, self.m, self.v = z(), z(), z(), z()
         self.state = torch.zeros(2, device=dev, dtype=torch.float32)      # Adam step count, sum of squares of the gradient
@@ -188,7 +190,10 @@ class PPOUpdate:
         self.du2_32 = f(Ba, d2)
         self.stats = torch.zeros(16, device=dev)            # [0:7] PPO sums, [8:12] disc sums, [12] sum g^2 of the penalty
         self.rms_scratch = torch.zeros(2 * AMP_OBS, device=dev, dtype=torch.float64)
-        self._comm = torch.cuda.Stream(device=dev) if self.world > 1 else None
+        from .dist import BucketedAllReduce
+        self.reducer = BucketedAllReduce(self.flat.g, self.flat.bucket0, overlap=self.overlap)
+        if world is None:
+            self.world = self.reducer.world
         self.refresh_weights()
 
     # ---- parameters -------------------------------------------------------------------------------------------------------
@@ -324,6 +329,9 @@ class PPOUpdate:
         self._axpy(G("_disc_logits.weight"), n._disc_logits.weight, 2.0 * dc * (cfg["disc_logit_reg"] + cfg["disc_weight_decay"]))
         self._axpy(G("_disc_mlp.0.weight"), n._disc_mlp[0].weight, 2.0 * dc * cfg["disc_weight_decay"])
         self._axpy(G("_disc_mlp.2.weight"), n._disc_mlp[2].weight, 2.0 * dc * cfg["disc_weight_decay"])
+        # the discriminator's weight gradients (33 % of all parameters) are final: their all-reduce runs under the actor /
+        # critic backward that follows
+        self.reducer.start_first()
 
         # ---- backward, actor / critic / task trunk ----
         xform(x=self.dmu32, split=self.s_dmu, splitT=self.dmuT, colsum=G("mu.bias"))
@@ -359,8 +367,7 @@ class PPOUpdate:
     def reduce_and_apply(self):
         """Gradient average over ranks (one all-reduce of the flat buffer), clip-norm, Adam, fresh operand splits."""
         FP, cfg, lib = self.flat, self.cfg, _lib.load()
-        if self.world > 1:
-            dist.all_reduce(FP.g, op=dist.ReduceOp.SUM)                # summed; the 1 / world factor is folded into the Adam kernel
+        self.reducer.finish()                                          # summed; the 1 / world factor is folded into the Adam kernel
         _lib.check(lib.emloco_grad_sumsq(_ptr(FP.g), FP.n, _ptr(FP.state), _stream()), "emloco_grad_sumsq")
         _lib.check(lib.emloco_adam_clip(_ptr(FP.p), _ptr(FP.g), _ptr(FP.m), _ptr(FP.v), FP.n, _ptr(FP.state), cfg["lr"], 0.9, 0.999, 1e-8,
                                         cfg["grad_norm"], 1.0 / self.world, _stream()), "emloco_adam_clip")

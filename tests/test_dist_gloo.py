@@ -35,6 +35,18 @@ def _worker(rank, world, port, q):
                sigma_grad=float(net.mu.bias.grad.mean()), nbytes=fg.nbytes())
     fg.zero()
     assert float(net.mu.weight.grad.abs().sum()) == 0.0       # the views survive zeroing
+    # the update step's bucketed reduction (emloco_b200.update.PPOUpdate -> dist.BucketedAllReduce): first bucket asynchronous
+    flat = torch.arange(1000, dtype=torch.float32) * (r + 1)
+    red = D.BucketedAllReduce(flat, 333)
+    red.start_first()
+    flat[333:] += 1.0                                          # "backward kernels" of the second bucket issued meanwhile
+    red.finish()
+    want = torch.arange(1000, dtype=torch.float32) * 3
+    want[333:] += 2.0
+    out["bucketed_ok"] = bool(torch.equal(flat, want))
+    flat2 = torch.ones(10) * (r + 1)
+    D.BucketedAllReduce(flat2, 4, overlap=False).finish()
+    out["single_ok"] = bool(torch.equal(flat2, torch.full((10,), 3.0)))
     D.finalize()
     q.put(out)
 
@@ -59,6 +71,7 @@ def test_two_rank_gloo_plumbing():
     mean = 0.5 * (res[0]["local_sum"] + res[1]["local_sum"])
     assert all(abs(d["avg_sum"] - mean) <= 1e-6 * max(1.0, abs(mean)) for d in res)
     assert all(abs(d["sigma_grad"] - 5.5) < 1e-5 for d in res)                   # 4 rows + (1 + 2) / 2
+    assert all(d["bucketed_ok"] and d["single_ok"] for d in res)
 
 
 def test_bench_reference_arm_under_two_ranks():
