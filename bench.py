@@ -240,6 +240,7 @@ def train_step_bench(args, R, D, rank, world, pk):
     barrier()
     ms = D.max_over_ranks(e0.elapsed_time(e1), device="cuda") / K
     macs, launches = (_lib.mac_count - m0) / K, (_lib.launch_count - l0) / K
+    info = up.info()
     # the same step without the optimiser half / without the collective, and the collective alone (bus bandwidth)
     e0.record()
     for i in range(K):
@@ -262,7 +263,6 @@ def train_step_bench(args, R, D, rank, world, pk):
         nbytes = flat.numel() * 4
         ar = {"bytes": nbytes, "ms": ar_ms, "algbw_gbs": nbytes / (ar_ms * 1e-3) / 1e9, "busbw_gbs": nbytes / (ar_ms * 1e-3) / 1e9 * 2 * (world - 1) / world,
               "exposed_ms": max(ms - fb_ms, 0.0), "note": "exposed = (step - forward/backward-only step), i.e. collective + clip-norm + Adam + operand refresh not hidden"}
-    info = up.info()
     tf = 2 * macs / (ms * 1e-3) / 1e12
     return {"metric": "train_samples_per_sec", "value": world * B / (ms * 1e-3), "unit": "samples/s", "ms_per_minibatch": ms,
             "forward_backward_ms": fb_ms, "minibatch": B, "amp_minibatch": Ba, "minibatches_per_epoch": nmb, "steps": K,

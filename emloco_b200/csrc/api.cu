@@ -21,9 +21,9 @@ cudaError_t eml_linear_tc(const float*, long long, const float*, const float*, f
                           const float*, const float*, float, int, cudaStream_t);
 
 cudaError_t eml_xform(const float* x, long long ldx, const float* rowvec, const float* rowscale, long long lds, const float* mean,
-                      const float* var, float eps, const float* gate, long long ldg, float scale, float* y32, long long ldy,
-                      float* yT32, long long ldyT, void* hi, void* lo, long long ld16, void* hiT, void* loT, long long ldT,
-                      float* colsum, float* sumsq, long long M, int K, cudaStream_t st);
+                      const float* var, float eps, const float* gate, long long ldg, const float* drop_u, float drop_rate, float scale,
+                      float* y32, long long ldy, float* yT32, long long ldyT, void* hi, void* lo, long long ld16, void* hiT, void* loT,
+                      long long ldT, float* colsum, float* sumsq, long long M, int K, cudaStream_t st);
 cudaError_t eml_ppo_heads(const float* mu, long long ldmu, const float* logstd, const float* actions, const float* old_neglogp,
                           const float* adv, const float* value, const float* task_value, const float* returns, const float* old_mu,
                           const float* old_sigma, float* dmu, long long lddmu, float* dvalue, float* dtask, float* stats, long long B,
@@ -37,6 +37,7 @@ cudaError_t eml_adam_clip(float* p, const float* g, float* m, float* v, long lon
                           float eps, float max_norm, float grad_scale, cudaStream_t st);
 cudaError_t eml_adam_begin(float* state, cudaStream_t st);
 cudaError_t eml_axpy(float* y, const float* x, float a, long long n, cudaStream_t st);
+cudaError_t eml_sum_parts(const float* parts, int S, long long stride, float* out, long long n, int accumulate, cudaStream_t st);
 
 static thread_local std::string g_err;
 static int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
@@ -591,15 +592,16 @@ int emloco_normalize(const float* d_x, int64_t ldx, float* d_y, int64_t ldy, int
 
 // ---- PPO / AMP update step (csrc/update.cu) ----
 int emloco_xform(const float* d_x, int64_t ldx, const float* d_rowvec, const float* d_rowscale, int64_t lds, const float* d_mean,
-                 const float* d_var, float eps, const float* d_gate, int64_t ldg, float scale, float* d_y32, int64_t ldy,
-                 float* d_yT32, int64_t ldyT, uint16_t* d_hi, uint16_t* d_lo, int64_t ld16, uint16_t* d_hiT, uint16_t* d_loT,
-                 int64_t ldT, float* d_colsum, float* d_sumsq, int64_t M, int32_t K, void* stream) {
+                 const float* d_var, float eps, const float* d_gate, int64_t ldg, const float* d_drop_u, float drop_rate, float scale,
+                 float* d_y32, int64_t ldy, float* d_yT32, int64_t ldyT, uint16_t* d_hi, uint16_t* d_lo, int64_t ld16, uint16_t* d_hiT,
+                 uint16_t* d_loT, int64_t ldT, float* d_colsum, float* d_sumsq, int64_t M, int32_t K, void* stream) {
     if ((!d_x && !d_rowvec) || M < 0 || K < 0 || ((d_mean == nullptr) != (d_var == nullptr)) || (d_mean && !d_x) ||
         ((d_hi == nullptr) != (d_lo == nullptr)) || ((d_hiT == nullptr) != (d_loT == nullptr)))
         return fail(EMLOCO_EINVAL, "emloco_xform: bad argument");
     if ((d_hi && (ld16 < K)) || (d_hiT && (ldT < M)) || (d_y32 && ldy < K) || (d_yT32 && ldyT < M))
         return fail(EMLOCO_EINVAL, "emloco_xform: output pitch smaller than the row length");
-    CK(eml_xform(d_x, ldx, d_rowvec, d_rowscale, lds, d_mean, d_var, eps, d_gate, ldg, scale, d_y32, ldy, d_yT32, ldyT, d_hi, d_lo, ld16,
+    if (d_drop_u && K % EML_AMP_STEP) return fail(EMLOCO_EINVAL, "emloco_xform: the joint-dropout gate applies to AMP observation rows (K a multiple of 206)");
+    CK(eml_xform(d_x, ldx, d_rowvec, d_rowscale, lds, d_mean, d_var, eps, d_gate, ldg, d_drop_u, drop_rate, scale, d_y32, ldy, d_yT32, ldyT, d_hi, d_lo, ld16,
                  d_hiT, d_loT, ldT, d_colsum, d_sumsq, M, K, (cudaStream_t)stream), "xform");
     return EMLOCO_OK;
 }
@@ -657,6 +659,12 @@ int emloco_adam_clip(float* d_param, const float* d_grad, float* d_m, float* d_v
                      float beta2, float eps, float max_norm, float grad_scale, void* stream) {
     if (!d_param || !d_grad || !d_m || !d_v || !d_state || n < 0) return fail(EMLOCO_EINVAL, "emloco_adam_clip: bad argument");
     CK(eml_adam_clip(d_param, d_grad, d_m, d_v, n, d_state, lr, beta1, beta2, eps, max_norm, grad_scale, (cudaStream_t)stream), "adam");
+    return EMLOCO_OK;
+}
+
+int emloco_sum_parts(const float* d_parts, int32_t num_parts, int64_t part_stride, float* d_out, int64_t n, int32_t accumulate, void* stream) {
+    if (!d_parts || !d_out || num_parts <= 0 || n < 0 || part_stride < n) return fail(EMLOCO_EINVAL, "emloco_sum_parts: bad argument");
+    CK(eml_sum_parts(d_parts, num_parts, part_stride, d_out, n, accumulate, (cudaStream_t)stream), "sum parts");
     return EMLOCO_OK;
 }
 

@@ -24,6 +24,8 @@ struct XformParams {
     const float* rowscale; long long lds;   // [M] (stride lds) or NULL
     const float* mean; const float* var; float eps;   // optional normalisation of x: clamp((x-mean)/sqrt(var+eps), +-5)
     const float* gate; long long ldg;       // [M,K] or NULL: pass where gate > 0
+    const float* drop_u; float drop_rate;   // [M,19] or NULL: whole-joint dropout of AMP observation columns (amp_models.py:49-90):
+                                            // column k of joint j passes where drop_u[m,j] > drop_rate (computed inline, no mask tensor)
     float scale;
     float* y32; long long ldy;              // [M,K]
     float* yT32; long long ldyT;            // [K,M]
@@ -46,9 +48,15 @@ __global__ void __launch_bounds__(256) xform_kernel(XformParams P) {
     const int k = k0 + c;
     float mu = 0.f, is = 1.f, rv = 0.f;
     const bool kin = k < P.K;
+    int jd = -1;
     if (kin) {
         if (P.mean) { mu = P.mean[k]; is = 1.0f / sqrtf(P.var[k] + P.eps); }
         if (!P.x) rv = P.rowvec[k];
+        if (P.drop_u) {
+            const int f = k % EML_AMP_STEP;
+            if (f >= 12 && f < 12 + 19 * 6) jd = (f - 12) / 6;
+            else if (f >= 126 && f < 126 + 19 * 3) jd = (f - 126) / 3;
+        }
     }
     float ss = 0.f;
 #pragma unroll 4
@@ -64,6 +72,7 @@ __global__ void __launch_bounds__(256) xform_kernel(XformParams P) {
             if (P.rowscale) v *= P.rowscale[m * P.lds];
             v *= P.scale;
             if (P.gate && !(P.gate[m * P.ldg + k] > 0.f)) v = 0.f;
+            if (jd >= 0 && !(P.drop_u[m * 19 + jd] > P.drop_rate)) v = 0.f;
             if (P.y32) P.y32[m * P.ldy + k] = v;
             if (P.hi) {
                 const __nv_bfloat16 h = __float2bfloat16_rn(v);
@@ -89,6 +98,108 @@ __global__ void __launch_bounds__(256) xform_kernel(XformParams P) {
                     const __nv_bfloat16 h = __float2bfloat16_rn(v);
                     P.hiT[(long long)(k0 + kk) * P.ldT + m] = h;
                     P.loT[(long long)(k0 + kk) * P.ldT + m] = __float2bfloat16_rn(v - __bfloat162float(h));
+                }
+            }
+        }
+    }
+    if (P.colsum && tid < XT && k0 + tid < P.K) {
+        float a = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < XT; ++r) a += tile[r][tid];
+        atomicAdd(P.colsum + k0 + tid, a);
+    }
+    if (P.sumsq) {
+        ss = warp_sum(ss);
+        if ((tid & 31) == 0) red[tid >> 5] = ss;
+        __syncthreads();
+        if (tid == 0) { float a = 0.f; for (int w = 0; w < 8; ++w) a += red[w]; atomicAdd(P.sumsq, a); }
+    }
+}
+
+// joint of AMP-observation column k (206 features per history step: 12 root features, 19 x 6 joint rotations, 19 x 3 joint
+// velocities, 12 key-body + 11 shape features), or -1 when the column is never dropped
+__device__ __forceinline__ int amp_joint_of(int k) {
+    const int f = k % EML_AMP_STEP;
+    if (f >= 12 && f < 12 + 19 * 6) return (f - 12) / 6;
+    if (f >= 126 && f < 126 + 19 * 3) return (f - 126) / 3;
+    return -1;
+}
+
+// Same operation, two adjacent columns per thread: 8-byte loads, packed bf16x2 stores in both orientations.  Launched when
+// K, the pitches and the base pointers allow it (eml_xform checks); the scalar kernel above is the general path.
+__global__ void __launch_bounds__(256) xform2_kernel(XformParams P) {
+    __shared__ float tile[XT][XT + 1];
+    __shared__ float red[8];
+    const int tid = threadIdx.x;
+    const long long m0 = (long long)blockIdx.y * XT;
+    const int k0 = blockIdx.x * XT;
+    const int c = tid & 31, r0 = tid >> 5;               // column pair within the tile, first row; rows r0, r0+8, ...
+    const int k = k0 + 2 * c;
+    const bool kin = k < P.K;                            // K is even: the pair is in or out together
+    float2 mu = make_float2(0.f, 0.f), is = make_float2(1.f, 1.f), rv = make_float2(0.f, 0.f);
+    int j0 = -1, j1 = -1;
+    if (kin) {
+        if (P.mean) {
+            mu = *reinterpret_cast<const float2*>(P.mean + k);
+            const float2 vr = *reinterpret_cast<const float2*>(P.var + k);
+            is = make_float2(1.0f / sqrtf(vr.x + P.eps), 1.0f / sqrtf(vr.y + P.eps));
+        }
+        if (!P.x) rv = *reinterpret_cast<const float2*>(P.rowvec + k);
+        if (P.drop_u) { j0 = amp_joint_of(k); j1 = amp_joint_of(k + 1); }
+    }
+    float ss = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < XT / 8; ++i) {
+        const int r = r0 + 8 * i;
+        const long long m = m0 + r;
+        float2 v = make_float2(0.f, 0.f);
+        if (kin && m < P.M) {
+            if (P.x) {
+                v = *reinterpret_cast<const float2*>(P.x + m * P.ldx + k);
+                if (P.mean) {
+                    v.x = fminf(fmaxf((v.x - mu.x) * is.x, -5.0f), 5.0f);
+                    v.y = fminf(fmaxf((v.y - mu.y) * is.y, -5.0f), 5.0f);
+                }
+            } else v = rv;
+            float sc = P.scale;
+            if (P.rowscale) sc *= P.rowscale[m * P.lds];
+            v.x *= sc; v.y *= sc;
+            if (P.gate) {
+                const float2 g = *reinterpret_cast<const float2*>(P.gate + m * P.ldg + k);
+                if (!(g.x > 0.f)) v.x = 0.f;
+                if (!(g.y > 0.f)) v.y = 0.f;
+            }
+            if (P.drop_u) {
+                if (j0 >= 0 && !(P.drop_u[m * 19 + j0] > P.drop_rate)) v.x = 0.f;
+                if (j1 >= 0 && !(P.drop_u[m * 19 + j1] > P.drop_rate)) v.y = 0.f;
+            }
+            if (P.y32) *reinterpret_cast<float2*>(P.y32 + m * P.ldy + k) = v;
+            if (P.hi) {
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y);
+                const __nv_bfloat16 l0 = __float2bfloat16_rn(v.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v.y - __bfloat162float(h1));
+                *reinterpret_cast<uint32_t*>(P.hi + m * P.ld16 + k) = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                *reinterpret_cast<uint32_t*>(P.lo + m * P.ld16 + k) = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            }
+            ss += v.x * v.x + v.y * v.y;
+        }
+        tile[r][2 * c] = v.x; tile[r][2 * c + 1] = v.y;
+    }
+    __syncthreads();
+    if (P.yT32 || P.hiT) {
+        // transposed write: thread (c, r0) owns rows 2c, 2c+1 of the tile (two adjacent m) and columns r0, r0+8, ... (k's)
+        const long long m = m0 + 2 * c;
+        if (m < P.M) {                                  // M is even: the pair is in or out together
+#pragma unroll 4
+            for (int i = 0; i < XT / 8; ++i) {
+                const int kk = r0 + 8 * i;
+                if (k0 + kk >= P.K) break;
+                const float a = tile[2 * c][kk], b = tile[2 * c + 1][kk];
+                if (P.yT32) *reinterpret_cast<float2*>(P.yT32 + (long long)(k0 + kk) * P.ldyT + m) = make_float2(a, b);
+                if (P.hiT) {
+                    const __nv_bfloat16 h0 = __float2bfloat16_rn(a), h1 = __float2bfloat16_rn(b);
+                    const __nv_bfloat16 l0 = __float2bfloat16_rn(a - __bfloat162float(h0)), l1 = __float2bfloat16_rn(b - __bfloat162float(h1));
+                    *reinterpret_cast<uint32_t*>(P.hiT + (long long)(k0 + kk) * P.ldT + m) = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                    *reinterpret_cast<uint32_t*>(P.loT + (long long)(k0 + kk) * P.ldT + m) = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
                 }
             }
         }
@@ -296,6 +407,15 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(float* __restrict__ p, c
 
 __global__ void bump_step_kernel(float* state) { state[0] += 1.0f; state[1] = 0.f; }
 
+// out[i] = sum_s parts[s * stride + i] (+ out[i] when accumulate): the partial matrices of a split-K GEMM, added in split order
+__global__ void sum_parts_kernel(const float* __restrict__ parts, int S, long long stride, float* __restrict__ out, long long n, int accumulate) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float a = accumulate ? out[i] : 0.f;
+        for (int s = 0; s < S; ++s) a += parts[(long long)s * stride + i];
+        out[i] = a;
+    }
+}
+
 __global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, float a, long long n) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] += a * x[i];
 }
@@ -303,17 +423,23 @@ __global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, 
 }  // namespace
 
 cudaError_t eml_xform(const float* x, long long ldx, const float* rowvec, const float* rowscale, long long lds, const float* mean,
-                      const float* var, float eps, const float* gate, long long ldg, float scale, float* y32, long long ldy,
-                      float* yT32, long long ldyT, void* hi, void* lo, long long ld16, void* hiT, void* loT, long long ldT,
-                      float* colsum, float* sumsq, long long M, int K, cudaStream_t st) {
+                      const float* var, float eps, const float* gate, long long ldg, const float* drop_u, float drop_rate, float scale,
+                      float* y32, long long ldy, float* yT32, long long ldyT, void* hi, void* lo, long long ld16, void* hiT, void* loT,
+                      long long ldT, float* colsum, float* sumsq, long long M, int K, cudaStream_t st) {
     if (M <= 0 || K <= 0) return cudaSuccess;
     XformParams P;
     P.x = x; P.ldx = ldx; P.rowvec = rowvec; P.rowscale = rowscale; P.lds = lds; P.mean = mean; P.var = var; P.eps = eps;
-    P.gate = gate; P.ldg = ldg; P.scale = scale; P.y32 = y32; P.ldy = ldy; P.yT32 = yT32; P.ldyT = ldyT;
+    P.gate = gate; P.ldg = ldg; P.drop_u = drop_u; P.drop_rate = drop_rate; P.scale = scale; P.y32 = y32; P.ldy = ldy; P.yT32 = yT32; P.ldyT = ldyT;
     P.hi = (__nv_bfloat16*)hi; P.lo = (__nv_bfloat16*)lo; P.ld16 = ld16; P.hiT = (__nv_bfloat16*)hiT; P.loT = (__nv_bfloat16*)loT; P.ldT = ldT;
     P.colsum = colsum; P.sumsq = sumsq; P.M = M; P.K = K;
     dim3 grid((K + XT - 1) / XT, (unsigned)((M + XT - 1) / XT));
-    xform_kernel<<<grid, 256, 0, st>>>(P);
+    // two-column kernel: needs even K (and even M for the transposed outputs), even pitches, 8-byte (fp32) / 4-byte (bf16) aligned bases
+    auto al = [](const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; };
+    bool v2 = (K % 2 == 0) && (!x || (al(x, 8) && ldx % 2 == 0)) && (!rowvec || al(rowvec, 8)) && (!mean || (al(mean, 8) && al(var, 8))) &&
+              (!gate || (al(gate, 8) && ldg % 2 == 0)) && (!y32 || (al(y32, 8) && ldy % 2 == 0)) && (!hi || (al(hi, 4) && al(lo, 4) && ld16 % 2 == 0));
+    if (yT32 || hiT) v2 = v2 && (M % 2 == 0) && (!yT32 || (al(yT32, 8) && ldyT % 2 == 0)) && (!hiT || (al(hiT, 4) && al(loT, 4) && ldT % 2 == 0));
+    if (v2) xform2_kernel<<<grid, 256, 0, st>>>(P);
+    else xform_kernel<<<grid, 256, 0, st>>>(P);
     return cudaGetLastError();
 }
 
@@ -372,6 +498,13 @@ cudaError_t eml_adam_clip(float* p, const float* g, float* m, float* v, long lon
 
 cudaError_t eml_adam_begin(float* state, cudaStream_t st) {
     bump_step_kernel<<<1, 1, 0, st>>>(state);
+    return cudaGetLastError();
+}
+
+cudaError_t eml_sum_parts(const float* parts, int S, long long stride, float* out, long long n, int accumulate, cudaStream_t st) {
+    if (n <= 0 || S <= 0) return cudaSuccess;
+    long long blocks = (n + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
+    sum_parts_kernel<<<(unsigned)blocks, 256, 0, st>>>(parts, S, stride, out, n, accumulate);
     return cudaGetLastError();
 }
 

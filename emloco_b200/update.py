@@ -34,7 +34,7 @@ DEFAULT_CFG = dict(e_clip=0.2, actor_coef=1.0, critic_coef=5.0, tv_coef=5.0, bou
 
 
 def xform(x=None, rowvec=None, rowscale=None, mean=None, var=None, eps=1e-5, gate=None, scale=1.0, y32=None, yT32=None, split=None,
-          splitT=None, colsum=None, sumsq=None, M=None, K=None):
+          splitT=None, colsum=None, sumsq=None, M=None, K=None, drop_u=None, drop_rate=0.3):
     """emloco_xform: y = scale * rowscale[m] * src * (gate > 0); see include/emloco.h.  split / splitT: `_Split` (row-major [M,K] /
     transposed [K,M])."""
     if x is not None:
@@ -45,6 +45,8 @@ def xform(x=None, rowvec=None, rowscale=None, mean=None, var=None, eps=1e-5, gat
         assert gate.shape == (M, K) and gate.stride(1) == 1
     if rowscale is not None:
         assert rowscale.numel() == M and rowscale.is_contiguous()
+    if drop_u is not None:
+        assert drop_u.shape == (M, 19) and drop_u.is_contiguous()
     if split is not None:
         assert split.rows == M and split.K == K
     if splitT is not None:
@@ -55,7 +57,7 @@ def xform(x=None, rowvec=None, rowscale=None, mean=None, var=None, eps=1e-5, gat
         assert yT32.shape == (K, M) and yT32.stride(1) == 1
     _lib.check(_lib.load().emloco_xform(
         _ptr(x), 0 if x is None else x.stride(0), _ptr(rowvec), _ptr(rowscale), 1, _ptr(mean), _ptr(var), eps, _ptr(gate),
-        0 if gate is None else gate.stride(0), float(scale), _ptr(y32), 0 if y32 is None else y32.stride(0), _ptr(yT32),
+        0 if gate is None else gate.stride(0), _ptr(drop_u), float(drop_rate), float(scale), _ptr(y32), 0 if y32 is None else y32.stride(0), _ptr(yT32),
         0 if yT32 is None else yT32.stride(0), None if split is None else _ptr(split.hi), None if split is None else _ptr(split.lo),
         0 if split is None else split.ld, None if splitT is None else _ptr(splitT.hi), None if splitT is None else _ptr(splitT.lo),
         0 if splitT is None else splitT.ld, _ptr(colsum), _ptr(sumsq), M, K, _stream()), "emloco_xform")
@@ -173,8 +175,7 @@ class PPOUpdate:
         # ---- discriminator side: rows = [agent | replay | demo] (3 Ba); the wgrad operands carry Ba extra columns so that the
         # gradient-penalty term is accumulated by the same GEMM (contraction over 3 Ba + Ba columns) ----
         R3, R4 = 3 * Ba, 4 * Ba
-        self.mask = f(R3, AMP_OBS)
-        self.u = f(R3, 19)
+        self.u = f(R3, 19)                                    # per-joint uniform draws of the dropout gate (no mask tensor)
         self.s_xa, self.xaT = S(R3, AMP_OBS), S(AMP_OBS, R4)
         self.h1_32, self.s_h1, self.h1T = f(R3, d1), S(R3, d1), S(d1, R4)
         self.h2_32 = f(R3, d2)
@@ -190,6 +191,8 @@ class PPOUpdate:
         self.du2_32 = f(Ba, d2)
         self.stats = torch.zeros(16, device=dev)            # [0:7] PPO sums, [8:12] disc sums, [12] sum g^2 of the penalty
         self.rms_scratch = torch.zeros(2 * AMP_OBS, device=dev, dtype=torch.float64)
+        self._ws, self._e0_scale = None, 1.0
+        self.split_k = True                 # weight gradients with few output tiles: split the contraction (the minibatch) over CTAs
         from .dist import BucketedAllReduce
         self.reducer = BucketedAllReduce(self.flat.g, self.flat.bucket0, overlap=self.overlap)
         if world is None:
@@ -257,12 +260,11 @@ class PPOUpdate:
                 self.u.uniform_()
             else:                                   # reference layout [19, Ba, 3] -> rows (source, sample), columns joints
                 self.u.copy_(dropout_u.permute(2, 1, 0).reshape(R3, 19))
-            _lib.check(lib_.emloco_amp_dropout_mask(_ptr(self.u), _ptr(self.mask), R3, cfg["dropout_rate"], _stream()), "emloco_amp_dropout_mask")
         for i, k in enumerate(("amp_obs", "amp_obs_replay", "amp_obs_demo")):     # three calls, each sees the previous update
             a = batch[k]
             assert a.shape == (Ba, AMP_OBS) and a.is_contiguous()
             rows = slice(i * Ba, (i + 1) * Ba)
-            xform(x=a, mean=am, var=av, gate=self.mask[rows] if cfg["amp_dropout"] else None,
+            xform(x=a, mean=am, var=av, drop_u=self.u[rows] if cfg["amp_dropout"] else None, drop_rate=cfg["dropout_rate"],
                   split=self.s_xa.rows_view(Ba, i * Ba), splitT=self.xaT.cols(i * Ba, (i + 1) * Ba))
             self._rms_update(self.amp_norm, a)
 
@@ -314,16 +316,17 @@ class PPOUpdate:
         lin(self.s_u2, WT["_disc_mlp.2"], None, False, y32=self.v1g_32)                                               # u2 W2
         xform(x=self.v1g_32, gate=h1d, split=self.s_u1, splitT=self.dh1T.cols(R3, R3 + Ba))                           # u1 (and u1^T: wgrad of W1)
         lin(self.s_u1, WT["_disc_mlp.0"], None, False, y32=self.gx_32)                                                # u1 W1
-        dmask = self.mask[demo] if cfg["amp_dropout"] else None
-        xform(x=self.gx_32, gate=dmask, sumsq=self.stats[12:13])                                                       # sum g^2
-        xform(x=self.gx_32, gate=dmask, scale=2.0 * cgp / Ba, split=self.s_e0, splitT=self.xaT.cols(R3, R3 + Ba))     # e0 = d / d gx
+        # e0 = d penalty / d gx = (2 cgp / Ba) * mask * gx; its sum of squares gives the penalty itself (info() undoes the scale)
+        self._e0_scale = 2.0 * cgp / Ba
+        xform(x=self.gx_32, drop_u=self.u[demo] if cfg["amp_dropout"] else None, drop_rate=cfg["dropout_rate"], scale=self._e0_scale,
+              split=self.s_e0, splitT=self.xaT.cols(R3, R3 + Ba), sumsq=self.stats[12:13])
         lin(self.s_e0, W["_disc_mlp.0"], None, False, y32=self.du1_32)                                                # e0 W1^T
         xform(x=self.du1_32, gate=h1d, split=self.s_dv1g, splitT=self.h1T.cols(R3, R3 + Ba))                          # d / d (u2 W2)
         lin(self.s_dv1g, W["_disc_mlp.2"], None, False, y32=self.du2_32)                                              # dv1g W2^T
         xform(x=self.du2_32, gate=h2d, colsum=G("_disc_logits.weight").reshape(-1))
         # weight gradients: prediction-loss and penalty terms in ONE product each (contraction over 3 Ba + Ba columns)
         lin(self.dh1T, self.xaT, None, False, y32=G("_disc_mlp.0.weight"))
-        lin(self.dh2T, self.h1T, None, False, y32=G("_disc_mlp.2.weight"))
+        self._wgrad(self.dh2T, self.h1T, G("_disc_mlp.2.weight"))
         # regularisers: logit_reg * |w3|^2 + weight_decay * (|W1|^2 + |W2|^2 + |w3|^2), times disc_coef
         dc = cfg["disc_coef"]
         self._axpy(G("_disc_logits.weight"), n._disc_logits.weight, 2.0 * dc * (cfg["disc_logit_reg"] + cfg["disc_weight_decay"]))
@@ -336,7 +339,7 @@ class PPOUpdate:
         # ---- backward, actor / critic / task trunk ----
         xform(x=self.dmu32, split=self.s_dmu, splitT=self.dmuT, colsum=G("mu.bias"))
         lin(self.s_dmu, WT["mu"], None, False, y32=self.da2_32)
-        lin(self.dmuT, self.a2T, None, False, y32=G("mu.weight"))
+        self._wgrad(self.dmuT, self.a2T, G("mu.weight"))
         xform(x=self.da2_32, gate=self.a2_32, split=self.s_da2, splitT=self.da2T, colsum=G("actor_mlp.2.bias"))
         lin(self.s_da2, WT["actor_mlp.2"], None, False, y32=self.dac1_32[:, :h])
         lin(self.da2T, self.ac1T.rows_view(h, 0), None, False, y32=G("actor_mlp.2.weight"))
@@ -351,18 +354,18 @@ class PPOUpdate:
         lin(self.dac1T, self.ainT, None, False, y32=FP.stacked("actor_mlp.0.weight", "critic_mlp.0.weight", "g"))
         xform(x=self.dain_32[:, SELF_OBS:], gate=self.t2_32, split=self.s_dt2, splitT=self.dt2T, colsum=G("_task_mlp.2.bias"))
         lin(self.s_dt2, WT["_task_mlp.2"], None, False, y32=self.dt1_32)
-        lin(self.dt2T, self.t1T, None, False, y32=G("_task_mlp.2.weight"))
+        self._wgrad(self.dt2T, self.t1T, G("_task_mlp.2.weight"))
         xform(x=self.dt1_32, gate=self.t1_32, splitT=self.dt1T, colsum=G("_task_mlp.0.bias"))
-        lin(self.dt1T, self.tinT, None, False, y32=G("_task_mlp.0.weight"))
+        self._wgrad(self.dt1T, self.tinT, G("_task_mlp.0.weight"))
         # task-value MLP
         wl = n._value_logits.weight.detach().reshape(-1)
         xform(x=self.v2_32, rowscale=self.dtv, colsum=G("_value_logits.weight").reshape(-1))
         xform(x=self.dtv.view(B, 1), colsum=G("_value_logits.bias"))
         xform(rowvec=wl, rowscale=self.dtv, gate=self.v2_32, M=B, K=D["v2"], split=self.s_dv2, splitT=self.dv2T, colsum=G("_task_value_mlp.2.bias"))
         lin(self.s_dv2, WT["_task_value_mlp.2"], None, False, y32=self.dv1_32)
-        lin(self.dv2T, self.v1T, None, False, y32=G("_task_value_mlp.2.weight"))
+        self._wgrad(self.dv2T, self.v1T, G("_task_value_mlp.2.weight"))
         xform(x=self.dv1_32, gate=self.v1_32, splitT=self.dv1T, colsum=G("_task_value_mlp.0.bias"))
-        lin(self.dv1T, self.tinT.rows_view(TRAJ_OBS, 0), None, False, y32=G("_task_value_mlp.0.weight"))
+        self._wgrad(self.dv1T, self.tinT.rows_view(TRAJ_OBS, 0), G("_task_value_mlp.0.weight"))
 
     def reduce_and_apply(self):
         """Gradient average over ranks (one all-reduce of the flat buffer), clip-norm, Adam, fresh operand splits."""
@@ -372,6 +375,33 @@ class PPOUpdate:
         _lib.check(lib.emloco_adam_clip(_ptr(FP.p), _ptr(FP.g), _ptr(FP.m), _ptr(FP.v), FP.n, _ptr(FP.state), cfg["lr"], 0.9, 0.999, 1e-8,
                                         cfg["grad_norm"], 1.0 / self.world, _stream()), "emloco_adam_clip")
         self.refresh_weights()
+
+    def _wgrad(self, aT, xT, out):
+        """out[N_out, K_in] = aT [N_out, rows] . xT [K_in, rows]^T.  When the output has too few 128 x 128 tiles to fill the 148
+        SMs the contraction (the minibatch rows) is split over up to 15 CTAs per tile and the partial matrices are added in
+        split order (deterministic)."""
+        M, N = out.shape
+        tiles = ((M + 127) // 128) * ((N + 127) // 128)
+        splits = min(15, 128 // tiles) if (self.split_k and tiles <= 48) else 1
+        while splits > 1:                   # every split must own at least one k-block, for both k-block sizes of the kernel
+            if all((splits - 1) * (-(-(-(-aT.K // bk)) // splits)) < -(-aT.K // bk) for bk in (64, 32)):
+                break
+            splits -= 1
+        if splits <= 1:
+            linear_bf16x3(aT, xT, None, False, y32=out)
+            return
+        need = splits * M * N
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, device=self.dev, dtype=torch.float32)
+        parts = self._ws[:need].view(splits, M, N)
+        linear_bf16x3(aT, xT, None, False, y32=parts[0], splits=splits)
+        _lib.check(_lib.load().emloco_sum_parts(_ptr(parts), splits, M * N, _ptr(out), M * N, 0, _stream()), "emloco_sum_parts")
+
+    def dropout_mask(self):
+        """The dropout gates of the last step as a [3 Ba, 3090] 0/1 tensor (tests; the step itself never materialises it)."""
+        m = torch.empty(3 * self.Ba, AMP_OBS, device=self.dev, dtype=torch.float32)
+        _lib.check(_lib.load().emloco_amp_dropout_mask(_ptr(self.u), _ptr(m), 3 * self.Ba, self.cfg["dropout_rate"], _stream()), "emloco_amp_dropout_mask")
+        return m
 
     def _axpy(self, y, x, a):
         _lib.check(_lib.load().emloco_axpy(_ptr(y), _ptr(x.detach()), float(a), y.numel(), _stream()), "emloco_axpy")
@@ -393,7 +423,7 @@ class PPOUpdate:
         logit_reg = float((w3 ** 2).sum().item())
         a_loss, c_loss, tv_loss, b_loss = s[0] / B, s[1] / B, s[2] / B, s[3] / B
         pred = 0.5 * (s[8] / (2 * Ba) + s[9] / Ba)
-        gp = s[12] / Ba
+        gp = s[12] / (self._e0_scale ** 2) / Ba
         return dict(a_loss=a_loss, c_loss=c_loss, tv_loss=tv_loss, b_loss=b_loss, a_clip_frac=s[4] / B, kl=s[5] / B, entropy=s[6] / B,
                     disc_pred_loss=pred, disc_grad_penalty=gp, disc_logit_loss=logit_reg, disc_agent_acc=s[10] / (2 * Ba), disc_demo_acc=s[11] / Ba,
                     total_norm=(total_sq ** 0.5) / self.world)

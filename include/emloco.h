@@ -395,11 +395,14 @@ int emloco_normalize(const float* d_x, int64_t ldx, float* d_y, int64_t ldy, int
  * emloco_xform: y[m,k] = scale * rowscale[m] * src[m,k] * (gate[m,k] > 0), src = clamp((x-mean)/sqrt(var+eps),+-5) | x | rowvec[k]
  * (x == NULL).  Any subset of outputs: fp32 y [M,K] and y^T [K,M]; bf16 hi/lo split of y and of y^T (the A / W operands of
  * the GEMMs: activations and weight transposes for dgrad, transposed activations and output gradients for wgrad); colsum[k] +=
- * sum_m y (bias gradients); *sumsq += sum y^2 (the gradient penalty).  Pointers NULL when unused. */
+ * sum_m y (bias gradients); *sumsq += sum y^2 (the gradient penalty).  d_drop_u [M,19] (or NULL): a second gate, the whole-joint
+ * dropout of AMP-observation columns (learning/amp_models.py:49-90) evaluated inline from the per-joint uniform draws - column k
+ * of joint j passes where d_drop_u[m,j] > drop_rate (K must be a multiple of 206); no mask tensor is materialised.
+ * Pointers NULL when unused. */
 int emloco_xform(const float* d_x, int64_t ldx, const float* d_rowvec, const float* d_rowscale, int64_t lds, const float* d_mean,
-                 const float* d_var, float eps, const float* d_gate, int64_t ldg, float scale, float* d_y32, int64_t ldy,
-                 float* d_yT32, int64_t ldyT, uint16_t* d_hi, uint16_t* d_lo, int64_t ld16, uint16_t* d_hiT, uint16_t* d_loT,
-                 int64_t ldT, float* d_colsum, float* d_sumsq, int64_t M, int32_t K, void* stream);
+                 const float* d_var, float eps, const float* d_gate, int64_t ldg, const float* d_drop_u, float drop_rate, float scale,
+                 float* d_y32, int64_t ldy, float* d_yT32, int64_t ldyT, uint16_t* d_hi, uint16_t* d_lo, int64_t ld16, uint16_t* d_hiT,
+                 uint16_t* d_loT, int64_t ldT, float* d_colsum, float* d_sumsq, int64_t M, int32_t K, void* stream);
 /* actor (PPO clip), critic, task-value and bound losses -> gradients of the weighted, batch-averaged total loss w.r.t. mu [B,A],
  * value [B], task value [B]; d_stats[7] += sums of {actor loss, critic loss, task-value loss, bound loss, clipped, kl, entropy}. */
 int emloco_ppo_heads(const float* d_mu, int64_t ldmu, const float* d_logstd, const float* d_actions, const float* d_old_neglogp,
@@ -428,6 +431,10 @@ int emloco_adam_clip(float* d_param, const float* d_grad, float* d_m, float* d_v
                      float beta2, float eps, float max_norm, float grad_scale, void* stream);
 /* y += a * x (weight-decay / logit-regularisation terms of the discriminator loss, amp_continuous.py:548-550,585-589). */
 int emloco_axpy(float* d_y, const float* d_x, float a, int64_t n, void* stream);
+/* out[i] = sum_s parts[s * part_stride + i] (+ out[i] when accumulate != 0), in split order: the consumer of a split-K
+ * emloco_linear_bf16x3 launch (weight gradients whose output has too few tiles to fill the SMs; the contraction runs over the
+ * whole minibatch, so it is split instead). */
+int emloco_sum_parts(const float* d_parts, int32_t num_parts, int64_t part_stride, float* d_out, int64_t n, int32_t accumulate, void* stream);
 
 int emloco_sync(emloco_sim* sim);
 const char* emloco_last_error(void);

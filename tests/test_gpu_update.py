@@ -62,7 +62,7 @@ def test_update_step_matches_reference_calc_gradients_golden():
     up.step(d, dropout_u=d["dropout_u"])
     torch.cuda.synchronize()
     info = up.info()
-    np.testing.assert_array_equal(up.mask[:, :206].cpu().numpy().reshape(3, Ba, 206).transpose(1, 2, 0), g["dropout_mask"])
+    np.testing.assert_array_equal(up.dropout_mask()[:, :206].cpu().numpy().reshape(3, Ba, 206).transpose(1, 2, 0), g["dropout_mask"])
     for k in ("a_loss", "c_loss", "b_loss", "tv_loss", "entropy", "disc_grad_penalty", "disc_logit_loss", "disc_agent_acc", "disc_demo_acc",
               "a_clip_frac", "total_norm", "kl"):
         # a_loss / kl amplify the fp32 round-off of mu by 1 / sigma^2 = e^5.8 (neglogp = 0.5 sum ((a - mu) / sigma)^2)
