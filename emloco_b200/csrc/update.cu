@@ -15,6 +15,7 @@
 //   sumsq / adam_clip     nn.utils.clip_grad_norm_(50) + torch.optim.Adam step over flat parameter / gradient buffers
 #include "sim.h"
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -34,16 +35,31 @@ struct XformParams {
     float* colsum;                          // [K] += sum over rows
     float* sumsq;                           // [1] += sum of squares
     long long M; int K;
+    int xg;                                 // m-tiles per block group (see xform_tile)
 };
 
 constexpr int XT = 64;     // tile edge
+
+// Block -> tile.  Blocks that run at the same time should touch neighbouring memory in BOTH orientations: xg consecutive blocks
+// take xg consecutive m-tiles of one k-tile (their transposed stores fill xg x 128 contiguous bytes of every k-row), the next
+// xg blocks take the next k-tile of the same rows (their row-major accesses continue where the previous group stopped).
+__device__ __forceinline__ bool xform_tile(const XformParams& P, int& kt, int& mt) {
+    const int gx = (P.K + XT - 1) / XT;
+    const long long gy = (P.M + XT - 1) / XT;
+    const long long g = blockIdx.x / P.xg;
+    kt = (int)(g % gx);
+    mt = (int)((g / gx) * P.xg + blockIdx.x % P.xg);
+    return mt < gy;
+}
 
 __global__ void __launch_bounds__(256) xform_kernel(XformParams P) {
     __shared__ float tile[XT][XT + 1];
     __shared__ float red[8];
     const int tid = threadIdx.x;
-    const long long m0 = (long long)blockIdx.y * XT;
-    const int k0 = blockIdx.x * XT;
+    int kt, mt;
+    if (!xform_tile(P, kt, mt)) return;
+    const long long m0 = (long long)mt * XT;
+    const int k0 = kt * XT;
     const int c = tid & 63, r0 = tid >> 6;              // column within the tile, first row; rows r0, r0+4, ...
     const int k = k0 + c;
     float mu = 0.f, is = 1.f, rv = 0.f;
@@ -131,8 +147,10 @@ __global__ void __launch_bounds__(256) xform2_kernel(XformParams P) {
     __shared__ float tile[XT][XT + 1];
     __shared__ float red[8];
     const int tid = threadIdx.x;
-    const long long m0 = (long long)blockIdx.y * XT;
-    const int k0 = blockIdx.x * XT;
+    int kt, mt;
+    if (!xform_tile(P, kt, mt)) return;
+    const long long m0 = (long long)mt * XT;
+    const int k0 = kt * XT;
     const int c = tid & 31, r0 = tid >> 5;               // column pair within the tile, first row; rows r0, r0+8, ...
     const int k = k0 + 2 * c;
     const bool kin = k < P.K;                            // K is even: the pair is in or out together
@@ -432,7 +450,10 @@ cudaError_t eml_xform(const float* x, long long ldx, const float* rowvec, const 
     P.gate = gate; P.ldg = ldg; P.drop_u = drop_u; P.drop_rate = drop_rate; P.scale = scale; P.y32 = y32; P.ldy = ldy; P.yT32 = yT32; P.ldyT = ldyT;
     P.hi = (__nv_bfloat16*)hi; P.lo = (__nv_bfloat16*)lo; P.ld16 = ld16; P.hiT = (__nv_bfloat16*)hiT; P.loT = (__nv_bfloat16*)loT; P.ldT = ldT;
     P.colsum = colsum; P.sumsq = sumsq; P.M = M; P.K = K;
-    dim3 grid((K + XT - 1) / XT, (unsigned)((M + XT - 1) / XT));
+    const long long gx = (K + XT - 1) / XT, gy = (M + XT - 1) / XT;
+    static const int xg_env = [] { const char* e = getenv("EMLOCO_XG"); int v = e ? atoi(e) : 0; return v > 0 ? v : 8; }();
+    P.xg = xg_env;
+    const unsigned grid = (unsigned)(gx * ((gy + P.xg - 1) / P.xg) * P.xg);
     // two-column kernel: needs even K (and even M for the transposed outputs), even pitches, 8-byte (fp32) / 4-byte (bf16) aligned bases
     auto al = [](const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; };
     bool v2 = (K % 2 == 0) && (!x || (al(x, 8) && ldx % 2 == 0)) && (!rowvec || al(rowvec, 8)) && (!mean || (al(mean, 8) && al(var, 8))) &&
