@@ -41,6 +41,28 @@ HORIZON = 32
 NCU_TRAFFIC = {"physics": 5.36e6, "post_step": 200.5e6, "nets": 363.7e6, "locoval": 427.1e6}
 
 
+_OUT_FD = None
+
+
+def capture_stdout():
+    """stdout carries exactly ONE JSON line: everything else any library prints there (NCCL's version banner, torch notices)
+    is sent to stderr by pointing fd 1 at fd 2 for the duration of the run; emit() writes the line to the real stdout."""
+    global _OUT_FD
+    if _OUT_FD is None:
+        sys.stdout.flush()
+        _OUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _OUT_FD is None:
+        os.write(1, line)
+    else:
+        os.write(_OUT_FD, line)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -181,14 +203,14 @@ def run_reference(args):
     rate, done, dt = cpu_rollout_rate(envs, args.steps, warm, budget_s=240.0)
     sample = (f"all {envs} envs per step, {done} steps in {dt:.1f} s on {cores} threads (oracle port: fp64 C physics with OpenMP, torch CPU "
               f"sgemm nets, numpy post-step / LocoVal scoring / post-horizon pass)")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "env_steps_per_sec", "value": rate, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": done, "warmup": warm, "ms_per_step": 1e3 * dt / max(done, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.envs} SMPL-humanoid envs per GPU, PACER AMP rollout step + LocoVal scoring (configs[1])",
                    "horizon": HORIZON},
         "cpu_baseline": {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": rate, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        "e2e": {"value": rate, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
 
 # =====================================================================================================
@@ -506,14 +528,14 @@ def run_ours(args):
             "locoval": {"metric": "locoval_scores_per_sec", "value": lv_rate, "unit": "scores/s", "batch": B, "ms": lv_ms},
             "cpu_baseline": cpu, "variants": variant, "train_step": train,
         }
-        print(json.dumps(out), flush=True)
+        emit(out)
     R.close()
     D.finalize()
 
 
 def main():
     # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
         os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -535,6 +557,7 @@ def main():
     ap.add_argument("--e2e-groups", type=int, default=2, help="env groups of the end-to-end (host buffer) pipeline")
     ap.add_argument("--eager", action="store_true", help="launch every kernel from the host instead of replaying CUDA graphs")
     args = ap.parse_args()
+    capture_stdout()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         # all host threads for the CPU arm: torchrun exports OMP_NUM_THREADS=1 to its workers, which would leave the OpenMP

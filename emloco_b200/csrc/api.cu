@@ -39,6 +39,11 @@ cudaError_t eml_adam_begin(float* state, cudaStream_t st);
 cudaError_t eml_axpy(float* y, const float* x, float a, long long n, cudaStream_t st);
 cudaError_t eml_sum_parts(const float* parts, int S, long long stride, float* out, long long n, int accumulate, cudaStream_t st);
 
+cudaError_t eml_player_record(const float* rew, const float* rew_raw, const int64_t* reset, const float* logit, const float* scores,
+                              const uint8_t* inverted, float* st, long long N, float* results, int* count, int capacity,
+                              int plot_val_reward, float inv_penalty, float disc_scale, float gamma, int step_to_pred, float min_reward,
+                              float max_reward, cudaStream_t stream);
+
 static thread_local std::string g_err;
 static int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
     char buf[512];
@@ -587,6 +592,19 @@ int emloco_normalize(const float* d_x, int64_t ldx, float* d_y, int64_t ldy, int
                      const float* d_var, float eps, void* stream) {
     if (!d_x || !d_y || !d_mean || !d_var || M < 0 || K <= 0 || ldx < K || ldy < K) return fail(EMLOCO_EINVAL, "emloco_normalize: bad argument");
     CK(eml_normalize(d_x, ldx, d_y, ldy, M, K, d_mean, d_var, eps, (cudaStream_t)stream), "normalize");
+    return EMLOCO_OK;
+}
+
+int emloco_player_record(const float* d_rew, const float* d_rew_raw, const int64_t* d_reset, const float* d_disc_logit,
+                         const float* d_locoval_scores, const uint8_t* d_inverted, float* d_state, int64_t N, float* d_results,
+                         int32_t* d_count, int32_t capacity, int32_t plot_val_reward, float inversion_penalty_scale,
+                         float disc_reward_scale, float gamma, int32_t step_to_pred, float min_reward, float max_reward, void* stream) {
+    if (!d_rew || !d_rew_raw || !d_reset || !d_disc_logit || !d_locoval_scores || !d_state || !d_results || !d_count || N < 0 || capacity < 0 ||
+        max_reward == min_reward)
+        return fail(EMLOCO_EINVAL, "emloco_player_record: bad argument");
+    CK(eml_player_record(d_rew, d_rew_raw, d_reset, d_disc_logit, d_locoval_scores, d_inverted, d_state, N, d_results, d_count, capacity,
+                         plot_val_reward, inversion_penalty_scale, disc_reward_scale, gamma, step_to_pred, min_reward, max_reward,
+                         (cudaStream_t)stream), "player record");
     return EMLOCO_OK;
 }
 

@@ -224,3 +224,61 @@ cudaError_t eml_head_reduce(const float* part, int groups, const float* bias, fl
     head_reduce_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(part, groups, bias, out, M);
     return cudaGetLastError();
 }
+
+
+// ---- inference loop bookkeeping: AMPPlayerContinuousValue.run (pacer/pacer/learning/amp_value_players.py:123-198), all envs at once.
+// Per env: LocoVal score kept from the episode's first step, discounted return ((r_loc + r_pow) * 0.5 + r_disc * 0.25) * gamma^(n+1)
+// (or the penalised task reward when plot_val_reward is off), snapshot at n == step_to_pred or at an earlier end; a finished
+// episode appends {env, pred, cr_to_pred, normalised return, c_loc, c_pow, c_disc, steps} to the result list.
+// state [11,N]: n, cr, coef, pred, cr_to_pred, c_loc, c_pow, c_disc, loc_to_pred, pow_to_pred, disc_to_pred
+__global__ void player_record_kernel(const float* __restrict__ rew, const float* __restrict__ rew_raw, const int64_t* __restrict__ reset,
+                                     const float* __restrict__ logit, const float* __restrict__ scores, const uint8_t* __restrict__ inverted,
+                                     float* __restrict__ st, long long N, float* __restrict__ results, int* __restrict__ count, int capacity,
+                                     int plot_val_reward, float inv_penalty, float disc_scale, float gamma, float step_to_pred,
+                                     float min_reward, float max_reward) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float* S[11];
+#pragma unroll
+    for (int q = 0; q < 11; ++q) S[q] = st + (long long)q * N + i;
+    const float n = *S[0];
+    float pred = *S[3];
+    if (n == 0.f) pred = scores[i];                                       // :128-137
+    const float disc = disc_r(logit[i], disc_scale);
+    const float coef = *S[2] * gamma;                                     // :144, before use
+    float cr = *S[1], c_loc = *S[5], c_pow = *S[6], c_disc = *S[7];
+    if (plot_val_reward) {                                                // :145-160
+        const float r_loc = rew_raw[2 * i], r_pow = rew_raw[2 * i + 1];
+        c_disc += disc * 0.25f * coef; c_loc += r_loc * 0.5f * coef; c_pow += r_pow * 0.5f * coef;
+        cr += ((r_loc + r_pow) * 0.5f + disc * 0.25f) * coef;
+    } else {                                                              // :161-163 with the penalty of :127
+        float r = rew[i];
+        if (inverted && inverted[i]) r *= -inv_penalty;
+        cr += r * coef;
+    }
+    const bool done = reset[i] != 0;
+    float ctp = *S[4], ltp = *S[8], ptp = *S[9], dtp = *S[10];
+    if (n == step_to_pred || (done && n < step_to_pred)) { ctp = cr; ltp = c_loc; ptp = c_pow; dtp = c_disc; }   // :177-193
+    if (done) {
+        const int slot = atomicAdd(count, 1);
+        if (slot < capacity) {
+            float* o = results + (long long)slot * 8;
+            o[0] = (float)i; o[1] = pred; o[2] = ctp; o[3] = (ctp - min_reward) / (max_reward - min_reward);    // :195
+            o[4] = ltp; o[5] = ptp; o[6] = dtp; o[7] = n + 1.0f;
+        }
+        cr = 0.f; c_loc = 0.f; c_pow = 0.f; c_disc = 0.f;                  // the next game starts from scratch (:76-100)
+    }
+    *S[0] = done ? 0.f : n + 1.0f; *S[1] = cr; *S[2] = done ? 1.0f : coef; *S[3] = pred; *S[4] = ctp;
+    *S[5] = c_loc; *S[6] = c_pow; *S[7] = c_disc; *S[8] = ltp; *S[9] = ptp; *S[10] = dtp;
+}
+
+cudaError_t eml_player_record(const float* rew, const float* rew_raw, const int64_t* reset, const float* logit, const float* scores,
+                              const uint8_t* inverted, float* st, long long N, float* results, int* count, int capacity,
+                              int plot_val_reward, float inv_penalty, float disc_scale, float gamma, int step_to_pred, float min_reward,
+                              float max_reward, cudaStream_t stream) {
+    if (N <= 0) return cudaSuccess;
+    player_record_kernel<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(rew, rew_raw, reset, logit, scores, inverted, st, N, results, count,
+                                                                         capacity, plot_val_reward, inv_penalty, disc_scale, gamma,
+                                                                         (float)step_to_pred, min_reward, max_reward);
+    return cudaGetLastError();
+}

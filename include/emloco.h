@@ -386,6 +386,19 @@ int emloco_fill_next_values(const emloco_rollout_cfg* cfg, const float* d_value_
 int emloco_normalize(const float* d_x, int64_t ldx, float* d_y, int64_t ldy, int64_t M, int32_t K, const float* d_mean,
                      const float* d_var, float eps, void* stream);
 
+/* ---- inference loop: `AMPPlayerContinuousValue.run` (pacer/pacer/learning/amp_value_players.py:123-198), all envs at once ----
+ * Per env and control step: the LocoVal score of the episode is taken at its first step (:128-137); the discounted return
+ * cr += ((r_loc + r_pow) * 0.5 + r_disc * 0.25) * gamma^(n+1) (plot_val_reward, :144-160) or cr += r * gamma^(n+1) with the
+ * inversion penalty (:127,:161-163) is accumulated; cr is snapshotted at n == step_to_pred or when the episode ends earlier
+ * (:177-193).  Every episode that ends appends 8 floats {env, pred, cr_to_pred, (cr_to_pred - min) / (max - min), c_loc, c_pow,
+ * c_disc, steps} to d_results (slot = atomic increment of *d_count; entries beyond `capacity` are dropped but counted) - the
+ * pairs of the value / return correlation (:263-279).  d_state [11,N] f32 (zero-initialised, row 2 = discount coefficients = 1):
+ * n, cr, coef, pred, cr_to_pred, c_loc, c_pow, c_disc and the three component snapshots.  d_rew_raw [N,2] = task.reward_raw. */
+int emloco_player_record(const float* d_rew, const float* d_rew_raw, const int64_t* d_reset, const float* d_disc_logit,
+                         const float* d_locoval_scores, const uint8_t* d_inverted, float* d_state, int64_t N, float* d_results,
+                         int32_t* d_count, int32_t capacity, int32_t plot_val_reward, float inversion_penalty_scale,
+                         float disc_reward_scale, float gamma, int32_t step_to_pred, float min_reward, float max_reward, void* stream);
+
 /* ---- PPO / AMP update step: `AMPValueAgent.calc_gradients`, pacer/pacer/learning/amp_continuous_value.py:276-428
  * (losses: learning/common_agent.py:594-602,657-683, amp_continuous_value.py:430-444, amp_continuous.py:536-616; optimiser:
  * common_agent.py:84-87 torch.optim.Adam + nn.utils.clip_grad_norm_(grad_norm 50); multi-GPU: Horovod `optimizer.synchronize()`

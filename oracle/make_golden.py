@@ -702,6 +702,61 @@ def reference_rms_update(seed=51):
     return out
 
 
+def reference_player(seed=71, step_to_pred=6):
+    """SURVEY component 14: the step loop of AMPPlayerContinuousValue.run (amp_value_players.py:123-198) executed from the
+    reference on a holder whose env / value net return recorded tensors - three games of one env: one that runs past
+    step_to_pred, one that ends early, one that ends exactly at step_to_pred.  The per-game locals are re-initialised as
+    :76-100 does."""
+    import types
+    R = ref_extract.load()
+    torch = R.torch
+    H = ref_extract.load_player_block()
+    h = H()
+    rng = np.random.default_rng(seed)
+    f = np.float32
+    cur = {}
+    h.env = types.SimpleNamespace(task=types.SimpleNamespace(_humanoid_root_states=torch.zeros(1, 13)), get_waypoint_traj=lambda: torch.zeros(1, 13, 3),
+                                  get_init_pose=lambda: torch.zeros(1, 24, 3), get_init_vel=lambda: torch.zeros(1, 2),
+                                  raw_reward=lambda: cur["raw"])
+    h.env_step = lambda env, a: ({"obs": None}, cur["r"].clone(), cur["done"], {})
+    h.inversion_penalty_scale = 0.3
+    h.device = "cpu"
+    h.valuenet = lambda w, p, v: cur["score"]
+    h.visualized_pose = True
+    h._post_step = lambda info: (0.0, 0.0, float(cur["disc"]))
+    h.gamma, h.step_to_pred, h.num_agents, h.plot_val_reward, h.is_rnn = 0.99, step_to_pred, 1, True, False
+    h.criterion = torch.nn.MSELoss()
+    bar = types.SimpleNamespace(set_description=lambda s: None, update=lambda k: None)
+    games, steps_in = [], []
+    rl, rp, rd = [], [], []
+    for length, inverted in ((10, False), (4, True), (step_to_pred + 1, False)):
+        L = dict(real_traj=[], inverted_envs=inverted, cr=torch.zeros(1), steps=torch.zeros(1), c_task_value=0, c_critic_value=0,
+                 c_disc_reward=0, c_loc_reward=0, c_pow_reward=0, rew_disc_coef=1.0, max_frame_rew=-100, min_frame_rew=100,
+                 rew_lists={'total': [], 'loc': [], 'disc': [], 'pow': []}, bar=bar, t=len(games), games_played=0, rewards_loc=rl, rewards_pow=rp,
+                 rewards_disc=rd, min_reward=-10, max_reward=100, total_value_loss=0)
+        score = f(rng.uniform(0.2, 0.9))
+        ins = []
+        import contextlib, io
+        for n in range(length):
+            raw = rng.uniform([0.0, -0.3], [1.0, 0.0]).astype(f)
+            logit = f(rng.normal(0, 3))
+            prob = 1 / (1 + np.exp(-logit)); disc = f(-np.log(max(1 - prob, 0.0001)) * 2)
+            cur.update(raw=torch.from_numpy(raw[None]), r=torch.tensor([raw.sum()]), done=torch.tensor([int(n == length - 1)]), disc=disc,
+                       score=torch.tensor([[score]]))
+            with contextlib.redirect_stdout(io.StringIO()), torch.no_grad():
+                L = h.player_block(n, L)
+            ins.append(dict(raw=raw, logit=logit, disc=disc, done=int(n == length - 1)))
+        games.append(dict(score=score, inverted=inverted, cr_to_pred=f(L["cr_to_pred"].item()), norm_reward=f(L["norm_rewards"].item()),
+                          value_loss=f(L["value_loss"].item()), steps=length))
+        steps_in.append(ins)
+    out = dict(step_to_pred=step_to_pred, n_games=len(games), rewards_loc=np.array(rl, f), rewards_pow=np.array(rp, f), rewards_disc=np.array(rd, f))
+    for i, (gm, ins) in enumerate(zip(games, steps_in)):
+        out.update({f"g{i}_{k}": v for k, v in gm.items()})
+        out[f"g{i}_raw"] = np.stack([x["raw"] for x in ins]); out[f"g{i}_logit"] = np.array([x["logit"] for x in ins], f)
+        out[f"g{i}_disc"] = np.array([x["disc"] for x in ins], f)
+    return out
+
+
 def reference_plausibl(B=40, seed=41):
     """a17: plausibl/test_value_mlp.py:24-113 `MLP` (24 -> 12 -> 6 -> 1, no sigmoid), biases randomised."""
     R = ref_extract.load()
@@ -750,6 +805,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "plausibl.npz"), **reference_plausibl())
     np.savez_compressed(os.path.join(OUT, "rms_update.npz"), **reference_rms_update())
     np.savez_compressed(os.path.join(OUT, "update_step.npz"), **reference_update_step())
+    np.savez_compressed(os.path.join(OUT, "player.npz"), **reference_player())
     traj, pose, vel = synth_locoval(64, 2)
     W, out = reference_locoval(traj, pose, vel)
     np.savez_compressed(os.path.join(OUT, "locoval.npz"), traj=traj, pose=pose, vel=vel,

@@ -625,6 +625,50 @@ def rollout_record(st, rew, reset, terminate, next_value_raw, logit, inverted=No
     return dict(rewards=shaped, dones=done, next_values=next_values, amp_rewards=amp_r)
 
 
+def player_record(st, rew, rew_raw, reset, logit, locoval_scores, inverted=None, plot_val_reward=True, inv_penalty=0.3, disc_scale=2.0,
+                  gamma=0.99, step_to_pred=144, min_reward=-10.0, max_reward=100.0):
+    """One iteration of the step loop of AMPPlayerContinuousValue.run (learning/amp_value_players.py:123-198), vectorised over
+    envs (the reference plays one env).  st: dict of float32 [N] arrays n (steps played in the running episode), cr, coef, pred,
+    cr_to_pred, c_loc, c_pow, c_disc and their snapshots loc_to_pred, pow_to_pred, disc_to_pred (updated in place).  rew [N] task reward, rew_raw [N,2] (location, power), reset int64 [N],
+    logit [N] discriminator logit, locoval_scores [N].  -> finished episodes as dict(env, pred, cr_to_pred, norm_reward, sq_err,
+    c_loc, c_pow, c_disc, steps)."""
+    n = st["n"]
+    first = n == 0
+    st["pred"] = np.where(first, locoval_scores.astype(F), st["pred"])                             # :128-137 score at the episode's first step
+    prob = F(1) / (F(1) + np.exp(-logit.astype(F)))
+    disc = (-np.log(np.maximum(F(1) - prob, F(0.0001))) * F(disc_scale)).astype(F)
+    st["coef"] = (st["coef"] * F(gamma)).astype(F)                                                 # :144, before use
+    c = st["coef"]
+    if plot_val_reward:                                                                            # :145-160
+        r_loc, r_pow = rew_raw[:, 0].astype(F), rew_raw[:, 1].astype(F)
+        st["c_disc"] = st["c_disc"] + disc * F(0.25) * c
+        st["c_loc"] = st["c_loc"] + r_loc * F(0.5) * c
+        st["c_pow"] = st["c_pow"] + r_pow * F(0.5) * c
+        st["cr"] = st["cr"] + ((r_loc + r_pow) * F(0.5) + disc * F(0.25)) * c
+    else:                                                                                          # :161-163, with the penalty of :127
+        r = rew.astype(F).copy()
+        if inverted is not None:
+            r[inverted.astype(bool)] *= F(-inv_penalty)
+        st["cr"] = st["cr"] + r * c
+    at_pred = n == step_to_pred                                                                    # :177-179
+    done = reset != 0
+    early = done & (n < step_to_pred)                                                              # :186-188
+    snap = at_pred | early
+    st["cr_to_pred"] = np.where(snap, st["cr"], st["cr_to_pred"]).astype(F)
+    for a, b in (("loc_to_pred", "c_loc"), ("pow_to_pred", "c_pow"), ("disc_to_pred", "c_disc")):  # rewards_loc / _pow / _disc (:180-193)
+        st[a] = np.where(snap, st[b], st[a]).astype(F)
+    ids = np.nonzero(done)[0]
+    norm = ((st["cr_to_pred"][ids] - F(min_reward)) / F(max_reward - min_reward)).astype(F)        # :195
+    out = dict(env=ids, pred=st["pred"][ids].copy(), cr_to_pred=st["cr_to_pred"][ids].copy(), norm_reward=norm,
+               sq_err=((st["pred"][ids] - norm) ** 2).astype(F), c_loc=st["loc_to_pred"][ids].copy(), c_pow=st["pow_to_pred"][ids].copy(),
+               c_disc=st["disc_to_pred"][ids].copy(), steps=(n[ids] + 1).copy())
+    for k in ("cr", "c_loc", "c_pow", "c_disc"):                                                   # :214-217 (new game: counters restart)
+        st[k] = np.where(done, F(0), st[k]).astype(F)
+    st["coef"] = np.where(done, F(1), st["coef"]).astype(F)
+    st["n"] = np.where(done, F(0), n + 1).astype(F)
+    return out
+
+
 # ----------------------------------------------------------------------------------------
 # a15: GAE
 # ----------------------------------------------------------------------------------------

@@ -270,6 +270,35 @@ def load_agent_blocks():
     return mod.Holder
 
 
+PLAYER_LOCALS = ("action", "real_traj", "inverted_envs", "cr", "steps", "c_task_value", "c_critic_value", "c_disc_reward", "c_loc_reward",
+                 "c_pow_reward", "rew_disc_coef", "max_frame_rew", "min_frame_rew", "rew_lists", "bar", "t", "games_played", "cr_to_pred",
+                 "rewards_loc", "rewards_pow", "rewards_disc", "min_reward", "max_reward", "total_value_loss", "valuenet_pred", "waypoint_traj",
+                 "init_pose", "init_vel")
+
+
+def load_player_block():
+    """One iteration of the step loop of AMPPlayerContinuousValue.run (learning/amp_value_players.py:123-198: env_step, inversion
+    penalty, LocoVal score at n == 0, discounted reward accumulation, snapshot at step_to_pred / early done, MSE against the
+    normalised return) as `Holder.player_block(self, n, L)`; L carries the loop's local variables (PLAYER_LOCALS)."""
+    if "player" in _cache:
+        return _cache["player"]
+    load()
+    pl = os.path.join(PACER, "learning/amp_value_players.py")
+    src = "import copy\nimport torch\nimport numpy as np\n\nclass Holder:\n    def player_block(self, n, L):\n"
+    src += "".join(f"        {v} = L.get('{v}')\n" for v in PLAYER_LOCALS)
+    src += "        done_count = 0\n"
+    src += textwrap.indent(textwrap.dedent(_lines(pl, 123, 198)), " " * 8) + "\n"
+    src += "        L.update({" + ", ".join(f"'{v}': {v}" for v in PLAYER_LOCALS) + ", 'done': done, 'done_count': done_count})\n"
+    src += "        if done_count > 0:\n            L.update(norm_rewards=norm_rewards, value_loss=value_loss)\n        return L\n"
+    tmp = tempfile.mkdtemp(prefix="emloco_ref_")
+    p = os.path.join(tmp, "emloco_ref_player.py")
+    with open(p, "w") as f:
+        f.write(src)
+    mod = _import_path("emloco_ref_player", p)
+    _cache["player"] = mod.Holder
+    return mod.Holder
+
+
 def load_plausibl_mlp():
     """plausibl/test_value_mlp.py:24-113 `class MLP` (the script's imports point at a developer's home directory)."""
     if "plausibl" in _cache:

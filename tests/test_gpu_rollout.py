@@ -876,3 +876,86 @@ def test_host_pipeline_groups_equal_plain_host_steps():
     pipe.close()
     for R in refs:
         R.close()
+
+
+def test_player_record_kernel_matches_reference_loop_golden_and_oracle():
+    """SURVEY component 14: emloco_player_record against the step loop of AMPPlayerContinuousValue.run executed from the
+    reference (player.npz, three games played as three parallel envs) and against the oracle on 500 envs x 40 random steps
+    with both reward modes."""
+    import os
+    from conftest import GOLDEN
+    from emloco_b200 import _lib
+    from emloco_b200.sim import _ptr, _stream
+    from oracle import oracle_np as O
+    g = np.load(os.path.join(GOLDEN, "player.npz"))
+    T = lambda a, dt=torch.float32: torch.from_numpy(np.ascontiguousarray(a)).to(dt).cuda()
+
+    def run(N, steps, gen, plot, stp):
+        st = torch.zeros(11, N, device="cuda"); st[2] = 1
+        names = ("n", "cr", "coef", "pred", "cr_to_pred", "c_loc", "c_pow", "c_disc", "loc_to_pred", "pow_to_pred", "disc_to_pred")
+        ost = {k: np.zeros(N, np.float32) for k in names}; ost["coef"][:] = 1
+        res, cnt = torch.zeros(4096, 8, device="cuda"), torch.zeros(1, dtype=torch.int32, device="cuda")
+        ref = []
+        for n in range(steps):
+            rew, raw, reset, logit, scores, inv = gen(n)
+            _lib.check(_lib.load().emloco_player_record(_ptr(T(rew)), _ptr(T(raw)), _ptr(T(reset, torch.int64)), _ptr(T(logit)), _ptr(T(scores)),
+                                                        _ptr(T(inv, torch.uint8)), _ptr(st), N, _ptr(res), _ptr(cnt), 4096, int(plot), 0.3, 2.0, 0.99,
+                                                        stp, -10.0, 100.0, _stream()), "emloco_player_record")
+            o = O.player_record(ost, rew, raw, reset, logit, scores, inv, plot_val_reward=plot, step_to_pred=stp)
+            ref += [(e, o["pred"][j], o["cr_to_pred"][j], o["norm_reward"][j], o["c_loc"][j], o["c_pow"][j], o["c_disc"][j], o["steps"][j], n)
+                    for j, e in enumerate(o["env"])]
+        torch.cuda.synchronize()
+        k = int(cnt.item())
+        assert k == len(ref)
+        got = res[:k].cpu().numpy()
+        np.testing.assert_allclose(st.cpu().numpy(), np.stack([ost[q] for q in names]), rtol=1e-5, atol=1e-6)
+        return got, np.array([r[:8] for r in ref], np.float32)
+
+    # the reference's three games as three envs (frozen once over: compare each env's first finished episode)
+    G = int(g["n_games"]); lens = [int(g[f"g{i}_steps"]) for i in range(G)]
+
+    def gen_ref(n):
+        raw = np.stack([g[f"g{i}_raw"][min(n, lens[i] - 1)] for i in range(G)]).astype(np.float32)
+        logit = np.array([g[f"g{i}_logit"][min(n, lens[i] - 1)] for i in range(G)], np.float32)
+        reset = np.array([int(n == L - 1) for L in lens], np.int64)
+        return raw.sum(1), raw, reset, logit, np.array([g[f"g{i}_score"] for i in range(G)], np.float32), np.zeros(G, np.uint8)
+    got, _ = run(G, max(lens), gen_ref, True, int(g["step_to_pred"]))
+    first = {}
+    for row in got:
+        first.setdefault(int(row[0]), row)
+    for i in range(G):
+        np.testing.assert_allclose(first[i][2], g[f"g{i}_cr_to_pred"], rtol=1e-5)
+        np.testing.assert_allclose(first[i][3], g[f"g{i}_norm_reward"], rtol=1e-5)
+        np.testing.assert_allclose((first[i][1] - first[i][3]) ** 2, g[f"g{i}_value_loss"], rtol=1e-4)
+        np.testing.assert_allclose(first[i][4:7], [g["rewards_loc"][i], g["rewards_pow"][i], g["rewards_disc"][i]], rtol=1e-4)
+        assert first[i][7] == lens[i]
+    # random play against the oracle, both reward modes
+    for plot in (True, False):
+        rng = np.random.default_rng(3)
+        N = 500
+
+        def gen(n):
+            raw = rng.uniform([0, -0.3], [1, 0], (N, 2)).astype(np.float32)
+            return (raw.sum(1), raw, (rng.random(N) < 0.07).astype(np.int64), rng.normal(0, 3, N).astype(np.float32),
+                    rng.uniform(0, 1, N).astype(np.float32), (rng.random(N) < 0.3).astype(np.uint8))
+        got, ref = run(N, 40, gen, plot, 12)
+        assert len(got) > 500
+        key = lambda a: a[np.lexsort((a[:, 7], a[:, 2], a[:, 0]))]
+        np.testing.assert_allclose(key(got), key(ref), rtol=1e-4, atol=1e-5)
+
+
+def test_player_runs_games_and_reports_the_value_return_correlation():
+    """emloco_b200.player.AMPPlayerContinuousValue over a tensor-core Rollout: deterministic actions, finished episodes
+    collected on the device, MSE / correlation report as the reference prints it (amp_value_players.py:263-279)."""
+    from emloco_b200.player import AMPPlayerContinuousValue
+    from emloco_b200.rollout import Rollout
+    R = Rollout(256, seed=2, tensor_cores=True, traj_flags=1 | 2 | 4, traj_pool=None)
+    P = AMPPlayerContinuousValue(R)
+    out = P.run(300)
+    assert out["games"] >= 300 and np.isfinite(out["value_loss"])
+    assert ((out["vals"] > 0) & (out["vals"] < 1)).all()                       # sigmoid outputs of LocoVal
+    assert (out["steps"] >= 1).all() and (out["steps"] <= 168).all()
+    assert set(np.unique(out["env"])) <= set(range(256))
+    # deterministic actions: the sampled action equals the policy mean
+    np.testing.assert_array_equal(R.mb["actions"][0].cpu().numpy(), R.mb["mus"][0].cpu().numpy())
+    R.close()

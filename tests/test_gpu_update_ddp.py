@@ -32,7 +32,7 @@ rank, local_rank, world = D.init("nccl")
 from test_gpu_update import _setup, _dev
 from oracle.make_golden import synth_update_batch
 B, Ba = 512, 256
-up, net, sd, _, stats = _setup(B, Ba, 5, 7)                       # same weights on every rank (hvd broadcast)
+up, net, sd, _, stats = _setup(B, Ba, 5, 7, world=None)           # same weights on every rank (hvd broadcast); world from the process group
 assert up.world == world == 2 and up.reducer.world == 2
 batches = [_dev(synth_update_batch(B, Ba, 100 + r)[0]) for r in range(world)]
 up.step(batches[rank], dropout_u=batches[rank]["dropout_u"])
