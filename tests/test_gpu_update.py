@@ -248,3 +248,42 @@ def test_rollout_after_an_update_uses_the_new_weights_through_adopted_splits():
     np.testing.assert_array_equal(r["mus"].cpu().numpy(), r1["mus"].cpu().numpy())
     np.testing.assert_array_equal(r["values"].cpu().numpy(), r1["values"].cpu().numpy())
     R.close(); R2.close()
+
+
+def test_train_epoch_rollout_then_updates_then_rollout():
+    """emloco_b200.agent.AMPValueAgent.train_epoch (amp_continuous_value.py:180-274): graphed rollout -> buffers -> dataset ->
+    mini_epochs x minibatches of update steps -> replay store, twice.  Checks the bookkeeping the reference implies: optimiser
+    step count, sample counts absorbed by the three normalisers, buffer fill, and that the second rollout runs on the updated
+    weights through the adopted operand splits (no re-capture of the step graphs)."""
+    from emloco_b200.agent import AMPValueAgent
+    N, T, mb = 64, 4, 128
+    ag = AMPValueAgent(N, horizon=T, minibatch_size=mb, mini_epochs=2, amp_batch_size=32, amp_obs_demo_buffer_size=512, amp_replay_buffer_size=300,
+                       seed=1, traj_flags=0)
+    p0 = ag.up.flat.p.clone()
+    i1 = ag.train_epoch()
+    graphs = dict(ag.R._graphs)
+    p1 = ag.up.flat.p.clone()
+    i2 = ag.train_epoch()
+    torch.cuda.synchronize()
+    steps_per_epoch = 2 * (N * T // mb)
+    assert float(ag.up.flat.state[0].item()) == 2 * steps_per_epoch
+    assert float((p1 - p0).abs().max()) > 0 and float((ag.up.flat.p - p1).abs().max()) > 0
+    for i in (i1, i2):
+        assert all(np.isfinite(v) for k, v in i.items()), i
+    assert ag.R.obs_norm.count.item() == 1 + 2 * steps_per_epoch * mb
+    assert ag.R.amp_norm.count.item() == 1 + 2 * steps_per_epoch * 3 * mb
+    assert ag.R.value_norm.count.item() == 1 + 2 * 2 * N * T                       # values and returns, every epoch
+    assert ag._replay.get_total_count() == 2 * N * T and ag._demo.get_total_count() >= 512
+    assert all(ag.R._graphs.get(k) is g for k, g in graphs.items() if isinstance(k, int)), "step graphs must survive the updates"
+    # the rollout reads the updated weights: its policy head equals a fresh evaluation of the current parameters
+    obs = ag.R.mb["obses"][0]
+    from emloco_b200.policy import AMPSeptValueNetwork, RolloutNets, RunningMeanStd
+    net2 = AMPSeptValueNetwork(); net2.load_state_dict({k: v.detach().cpu().clone() for k, v in ag.R.net.state_dict().items()})
+    on = RunningMeanStd(1422); on.load_state_dict({k: v.cpu() for k, v in ag.R.obs_norm.state_dict().items()})
+    an = RunningMeanStd(3090)
+    fresh = RolloutNets(net2.cuda(), on.cuda(), an.cuda(), N, tensor_cores=True)
+    z = torch.zeros(N, 69, device="cuda")
+    a, b = ag.R.nets.action_values(obs, z), fresh.action_values(obs, z)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(a["mus"].cpu().numpy(), b["mus"].cpu().numpy())
+    ag.close()
