@@ -898,9 +898,10 @@ def test_player_record_kernel_matches_reference_loop_golden_and_oracle():
         ref = []
         for n in range(steps):
             rew, raw, reset, logit, scores, inv = gen(n)
-            _lib.check(_lib.load().emloco_player_record(_ptr(T(rew)), _ptr(T(raw)), _ptr(T(reset, torch.int64)), _ptr(T(logit)), _ptr(T(scores)),
-                                                        _ptr(T(inv, torch.uint8)), _ptr(st), N, _ptr(res), _ptr(cnt), 4096, int(plot), 0.3, 2.0, 0.99,
+            d = [T(rew), T(raw), T(reset, torch.int64), T(logit), T(scores), T(inv, torch.uint8)]      # kept alive across the launch
+            _lib.check(_lib.load().emloco_player_record(*[_ptr(t) for t in d], _ptr(st), N, _ptr(res), _ptr(cnt), 4096, int(plot), 0.3, 2.0, 0.99,
                                                         stp, -10.0, 100.0, _stream()), "emloco_player_record")
+            torch.cuda.synchronize()
             o = O.player_record(ost, rew, raw, reset, logit, scores, inv, plot_val_reward=plot, step_to_pred=stp)
             ref += [(e, o["pred"][j], o["cr_to_pred"][j], o["norm_reward"][j], o["c_loc"][j], o["c_pow"][j], o["c_disc"][j], o["steps"][j], n)
                     for j, e in enumerate(o["env"])]
@@ -949,7 +950,7 @@ def test_player_runs_games_and_reports_the_value_return_correlation():
     collected on the device, MSE / correlation report as the reference prints it (amp_value_players.py:263-279)."""
     from emloco_b200.player import AMPPlayerContinuousValue
     from emloco_b200.rollout import Rollout
-    R = Rollout(256, seed=2, tensor_cores=True, traj_flags=1 | 2 | 4, traj_pool=None)
+    R = Rollout(256, seed=2, tensor_cores=True, traj_flags=2 | 4)                # --adjust_root_vel --init_heading, random-walk paths
     P = AMPPlayerContinuousValue(R)
     out = P.run(300)
     assert out["games"] >= 300 and np.isfinite(out["value_loss"])
