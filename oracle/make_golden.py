@@ -70,17 +70,31 @@ def synth_state(N, seed, map_shape=(1080, 1080), rough=True):
                 betas=betas, verts=verts, height_samples=hs, amp_buf=amp_buf)
 
 
-def reference_post_step(st):
-    """Drives the reference functions exactly as the task code does (call sites cited inline)."""
+def post_step_inputs(st, device="cpu"):
+    """Tensors of one env state on `device` (the sim tensors and constants the task code holds)."""
     R = ref_extract.load()
     torch = R.torch
-    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
     N = st["rb"].shape[0]
-    rb = T(st["rb"])
+    I = dict(N=N, rb=T(st["rb"]), ds=T(st["dof_state"]), betas=T(st["betas"]), limb=torch.zeros(N, 10, device=device), progress=T(st["progress"]),
+             verts=T(st["verts"]), heightsamples=T(st["height_samples"]), grid=T(square_height_points())[None].repeat(N, 1, 1),
+             grid9=T(center_height_points())[None].repeat(N, 1, 1), dof_force=T(st["dof_force"]), contact=T(st["contact"]),
+             amp_buf=T(st["amp_buf"]), env_ids=torch.arange(N, dtype=torch.long, device=device),
+             ts=torch.arange(NUM_TRAJ_SAMPLES, dtype=torch.float, device=device) * TRAJ_SAMPLE_DT,
+             contact_bodies=torch.tensor(CONTACT_BODIES, device=device), dof_subset=torch.from_numpy(DOF_SUBSET).to(device),
+             term_heights=torch.zeros(NB, device=device), reset0=torch.zeros(N, dtype=torch.long, device=device))
+    return I
+
+
+def post_step_run(I):
+    """Drives the reference functions exactly as the task code does (call sites cited inline); torch tensors in and out."""
+    R = ref_extract.load()
+    torch = R.torch
+    N = I["N"]
+    rb = I["rb"]
     bp, br, bv, bw = rb[..., 0:3], rb[..., 3:7], rb[..., 7:10], rb[..., 10:13]
-    ds = T(st["dof_state"]); dpos, dvel = ds[..., 0].contiguous(), ds[..., 1].contiguous()
-    betas = T(st["betas"]); limb = torch.zeros(N, 10)
-    progress = T(st["progress"])
+    ds = I["ds"]; dpos, dvel = ds[..., 0].contiguous(), ds[..., 1].contiguous()
+    betas, limb, progress = I["betas"], I["limb"], I["progress"]
     # --- self obs: humanoid_pedestrain_terrain.py:240-268 (root_height_obs False)
     so = R.jit.compute_humanoid_observations_smpl_max(bp.clone(), br, bv, bw, betas, limb, True, False, True, True, False)
     # --- flip self obs: humanoid.py:1066-1108
@@ -93,25 +107,23 @@ def reference_post_step(st):
     fso = R.jit.compute_humanoid_observations_smpl_max(fp, fr, fv, fw, betas, limb, True, False, True, True, False)
     # --- traj generator holder (traj_generator.py:24-36, 256-272)
     tg = R.meth.TrajHolder()
-    tg._verts = T(st["verts"]); tg._verts_flat = tg._verts.view(-1, 3)
+    tg._verts = I["verts"]; tg._verts_flat = tg._verts.view(-1, 3)
     tg._dt = (EPISODE_LEN * CONTROL_DT) / (NUM_VERTS - 1)
     tg.get_num_verts = lambda: tg._verts.shape[1]
     tg.get_num_segs = lambda: tg._verts.shape[1] - 1
     tg.get_traj_duration = lambda: tg.get_num_verts() * tg._dt
-    env_ids = torch.arange(N, dtype=torch.long)
+    env_ids = I["env_ids"]
     # --- _fetch_traj_samples: humanoid_traj.py:208-224
     t0 = progress * CONTROL_DT
-    ts = torch.arange(NUM_TRAJ_SAMPLES, dtype=torch.float) * TRAJ_SAMPLE_DT
-    tt = t0.unsqueeze(-1) + ts
+    tt = t0.unsqueeze(-1) + I["ts"]
     ids = torch.broadcast_to(env_ids.unsqueeze(-1), tt.shape)
     samples = tg.calc_pos(ids.flatten(), tt.flatten()).reshape(N, NUM_TRAJ_SAMPLES, 3)
     root_states = torch.cat([bp[:, 0], br[:, 0], bv[:, 0], bw[:, 0]], -1)
     loc = R.jit.compute_location_observations(root_states, samples, True)
     # --- heights: humanoid_pedestrain_terrain.py:761-815, 732-759, 1212-1288
     ter = R.meth.TerrainHolder()
-    ter.heightsamples = T(st["height_samples"]); ter.horizontal_scale = 0.1; ter.vertical_scale = 0.005
-    grid = T(square_height_points())[None].repeat(N, 1, 1)
-    grid9 = T(center_height_points())[None].repeat(N, 1, 1)
+    ter.heightsamples = I["heightsamples"]; ter.horizontal_scale = 0.1; ter.vertical_scale = 0.005
+    grid, grid9 = I["grid"], I["grid9"]
     head = torch.cat([bp[:, HEAD], br[:, HEAD]], 1)
     hq = R.ptu.calc_heading_quat(head[:, 3:7])
     pts = R.itu.quat_apply(hq.repeat(1, grid.shape[1]).reshape(-1, 4), grid) + head[:, :3].unsqueeze(1)
@@ -129,24 +141,27 @@ def reference_post_step(st):
     # --- reward: humanoid_pedestrain_terrain.py:907-930
     tar = tg.calc_pos(env_ids, progress * CONTROL_DT)
     loc_r = 1 * R.jit.compute_location_reward(bp[:, 0], tar)
-    power = torch.abs(torch.multiply(T(st["dof_force"]), dvel)).sum(dim=-1)
+    power = torch.abs(torch.multiply(I["dof_force"], dvel)).sum(dim=-1)
     pow_r = -0.0005 * power
     rew = loc_r + pow_r
     rew_raw = torch.cat([loc_r[:, None], pow_r[:, None]], dim=-1)
     # --- reset: humanoid_pedestrain_terrain.py:883-905
     reset, term = R.jit.compute_humanoid_reset(
-        torch.zeros(N, dtype=torch.long), progress, T(st["contact"]), torch.tensor(CONTACT_BODIES),
-        ch, bp, tar, float(EPISODE_LEN), 4.0, True, torch.zeros(NB), False)
+        I["reset0"], progress, I["contact"], I["contact_bodies"],
+        ch, bp, tar, float(EPISODE_LEN), 4.0, True, I["term_heights"], False)
     # --- AMP obs: humanoid_amp.py:585-657
     key = bp[:, KEY_BODIES, :]
     cur = R.jit.build_amp_observations_smpl(bp[:, 0], br[:, 0], bv[:, 0], bw[:, 0], dpos, dvel, key, betas, limb,
-                                            torch.from_numpy(DOF_SUBSET), True, False, True, True, False, True)
-    amp = T(st["amp_buf"]).clone()
+                                            I["dof_subset"], True, False, True, True, False, True)
+    amp = I["amp_buf"].clone()
     amp[:, 1:] = amp[:, 0:AMP_STEPS - 1].clone()
     amp[:, 0] = cur
-    out = dict(obs=torch.cat([so, tobs], -1), flip_obs=torch.cat([fso, ftobs], -1), rew=rew, reward_raw=rew_raw,
-               reset=reset, terminate=term, amp_obs=amp.view(N, -1), tar_pos=tar, traj_samples=samples)
-    return {k: v.numpy() for k, v in out.items()}
+    return dict(obs=torch.cat([so, tobs], -1), flip_obs=torch.cat([fso, ftobs], -1), rew=rew, reward_raw=rew_raw,
+                reset=reset, terminate=term, amp_obs=amp.view(N, -1), tar_pos=tar, traj_samples=samples)
+
+
+def reference_post_step(st):
+    return {k: v.cpu().numpy() for k, v in post_step_run(post_step_inputs(st)).items()}
 
 
 def synth_locoval(B, seed):
