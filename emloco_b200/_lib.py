@@ -19,7 +19,7 @@ SYMBOLS = [
     "emloco_disc_reward", "emloco_rollout_record", "emloco_normalize", "emloco_physics_step", "emloco_split_bf16",
     "emloco_linear_bf16x3", "emloco_set_post_sinks", "emloco_linear_bf16x3_rows", "emloco_timeout_gather",
     "emloco_rollout_record_deferred", "emloco_fill_next_values", "emloco_traj_reset", "emloco_set_traj_reset", "emloco_locoval_backward_pose", "emloco_locoval_train_step", "emloco_locoval_train_workspace_bytes", "emloco_linear_bf16x3_head", "emloco_sample_actions_parts", "emloco_linear", "emloco_xform", "emloco_ppo_heads", "emloco_disc_heads", "emloco_amp_dropout_mask",
-    "emloco_rms_update", "emloco_adam_begin", "emloco_grad_sumsq", "emloco_adam_clip", "emloco_axpy", "emloco_sum_parts", "emloco_player_record", "emloco_sync", "emloco_last_error", "emloco_version",
+    "emloco_rms_update", "emloco_adam_begin", "emloco_grad_sumsq", "emloco_adam_clip", "emloco_axpy", "emloco_sum_parts", "emloco_player_record", "emloco_motion_state", "emloco_amp_obs_demo", "emloco_sync", "emloco_last_error", "emloco_version",
 ]
 
 
@@ -41,6 +41,11 @@ class RolloutCfg(C.Structure):
     _fields_ = [("inversion_penalty_scale", C.c_float), ("reward_scale", C.c_float), ("value_mean", C.c_float),
                 ("value_std", C.c_float), ("disc_reward_scale", C.c_float), ("gamma", C.c_float),
                 ("step_to_pred", C.c_int32), ("unnorm_value", C.c_int32), ("d_value_stats", C.c_void_p)]
+
+
+class MotionLib(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("d_gts", "d_grs", "d_lrs", "d_gvs", "d_gavs", "d_dvs", "d_length", "d_dt", "d_bodies", "d_num_frames",
+                                          "d_start")] + [("num_motions", C.c_int32), ("reserved", C.c_int32)]
 
 
 class PostSinks(C.Structure):
@@ -139,6 +144,8 @@ def load():
     lib.emloco_axpy.argtypes = [vp, vp, f32, i64, vp]
     lib.emloco_sum_parts.argtypes = [vp, i32, i64, vp, i64, i32, vp]
     lib.emloco_player_record.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, i32, i32, f32, f32, f32, i32, f32, f32, vp]
+    lib.emloco_motion_state.argtypes = [C.POINTER(MotionLib), vp, vp, i64, vp, vp, vp, vp, vp]
+    lib.emloco_amp_obs_demo.argtypes = [C.POINTER(MotionLib), vp, vp, i64, i32, f32, vp, vp]
     lib.emloco_sync.argtypes = [vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
@@ -156,7 +163,7 @@ LAUNCHES = {"emloco_step": 2, "emloco_physics_step": 1, "emloco_post_step": 1, "
             "emloco_locoval_forward_host": 1, "emloco_split_bf16": 1, "emloco_linear_bf16x3": 1, "emloco_linear_bf16x3_rows": 1, "emloco_linear_bf16x3_head": 2,
             "emloco_timeout_gather": 1, "emloco_rollout_record_deferred": 1, "emloco_fill_next_values": 1,
             "emloco_xform": 1, "emloco_ppo_heads": 1, "emloco_disc_heads": 1, "emloco_amp_dropout_mask": 1, "emloco_rms_update": 2,
-            "emloco_adam_begin": 1, "emloco_grad_sumsq": 1, "emloco_adam_clip": 1, "emloco_axpy": 1, "emloco_sum_parts": 1, "emloco_player_record": 1}
+            "emloco_adam_begin": 1, "emloco_grad_sumsq": 1, "emloco_adam_clip": 1, "emloco_axpy": 1, "emloco_sum_parts": 1, "emloco_player_record": 1, "emloco_motion_state": 1, "emloco_amp_obs_demo": 1}
 launch_count = 0
 mac_count = 0          # multiply-accumulates of the dense-layer launches (M * N * K each), for the benches' FLOP figures
 

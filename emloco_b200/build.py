@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libemloco_b200.so")
-SOURCES = ["api.cu", "physics.cu", "physics_soa.cu", "poststep.cu", "locoval.cu", "locoval_tc.cu", "locoval_train.cu", "gae.cu", "rollout.cu", "trajreset.cu", "linear.cu", "linear_tc.cu", "update.cu"]
+SOURCES = ["api.cu", "physics.cu", "physics_soa.cu", "poststep.cu", "locoval.cu", "locoval_tc.cu", "locoval_train.cu", "gae.cu", "rollout.cu", "trajreset.cu", "linear.cu", "linear_tc.cu", "update.cu", "motion.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

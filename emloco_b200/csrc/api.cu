@@ -44,6 +44,17 @@ cudaError_t eml_player_record(const float* rew, const float* rew_raw, const int6
                               int plot_val_reward, float inv_penalty, float disc_scale, float gamma, int step_to_pred, float min_reward,
                               float max_reward, cudaStream_t stream);
 
+struct EmlMotionLibDev {
+    const float *gts, *grs, *lrs, *gvs, *gavs, *dvs;
+    const float *length, *dt, *bodies;
+    const int *num_frames, *start;
+    int num_motions;
+};
+cudaError_t eml_motion_state(const EmlMotionLibDev& L, const int* ids, const float* times, long long n, float* root, float* dof,
+                             float* key_pos, float* rb, cudaStream_t st);
+cudaError_t eml_amp_obs_demo(const EmlMotionLibDev& L, const int* ids, const float* times0, long long n, int steps, float dt, float* out,
+                             cudaStream_t st);
+
 static thread_local std::string g_err;
 static int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
     char buf[512];
@@ -605,6 +616,33 @@ int emloco_player_record(const float* d_rew, const float* d_rew_raw, const int64
     CK(eml_player_record(d_rew, d_rew_raw, d_reset, d_disc_logit, d_locoval_scores, d_inverted, d_state, N, d_results, d_count, capacity,
                          plot_val_reward, inversion_penalty_scale, disc_reward_scale, gamma, step_to_pred, min_reward, max_reward,
                          (cudaStream_t)stream), "player record");
+    return EMLOCO_OK;
+}
+
+// ---- mocap reset state / AMP demo observations (csrc/motion.cu) ----
+static bool motion_lib_ok(const emloco_motion_lib* L) {
+    return L && L->d_gts && L->d_grs && L->d_lrs && L->d_gvs && L->d_gavs && L->d_dvs && L->d_length && L->d_dt && L->d_bodies &&
+           L->d_num_frames && L->d_start && L->num_motions > 0;
+}
+static EmlMotionLibDev motion_lib_dev(const emloco_motion_lib* L) {
+    EmlMotionLibDev D;
+    D.gts = L->d_gts; D.grs = L->d_grs; D.lrs = L->d_lrs; D.gvs = L->d_gvs; D.gavs = L->d_gavs; D.dvs = L->d_dvs;
+    D.length = L->d_length; D.dt = L->d_dt; D.bodies = L->d_bodies; D.num_frames = L->d_num_frames; D.start = L->d_start;
+    D.num_motions = L->num_motions;
+    return D;
+}
+int emloco_motion_state(const emloco_motion_lib* lib, const int32_t* d_motion_ids, const float* d_motion_times, int64_t n,
+                        float* d_root_state, float* d_dof_state, float* d_key_pos, float* d_rb_state, void* stream) {
+    if (!motion_lib_ok(lib) || !d_motion_ids || !d_motion_times || n < 0) return fail(EMLOCO_EINVAL, "emloco_motion_state: bad argument");
+    CK(eml_motion_state(motion_lib_dev(lib), d_motion_ids, d_motion_times, n, d_root_state, d_dof_state, d_key_pos, d_rb_state,
+                        (cudaStream_t)stream), "motion state");
+    return EMLOCO_OK;
+}
+int emloco_amp_obs_demo(const emloco_motion_lib* lib, const int32_t* d_motion_ids, const float* d_motion_times0, int64_t n,
+                        int32_t num_steps, float dt, float* d_amp_obs, void* stream) {
+    if (!motion_lib_ok(lib) || !d_motion_ids || !d_motion_times0 || !d_amp_obs || n < 0 || num_steps <= 0 || !(dt > 0))
+        return fail(EMLOCO_EINVAL, "emloco_amp_obs_demo: bad argument");
+    CK(eml_amp_obs_demo(motion_lib_dev(lib), d_motion_ids, d_motion_times0, n, num_steps, dt, d_amp_obs, (cudaStream_t)stream), "amp obs demo");
     return EMLOCO_OK;
 }
 

@@ -90,3 +90,81 @@ def synthetic_locoval_batch(b, seed=0, rest_joint_pos=None):
     pose -= pose[:, :1].copy()
     vel = ((traj[:, 1] - traj[:, 0]) * 2.5).astype(np.float32)
     return traj, pose, vel
+
+
+# ---- synthetic motion library (the AMASS clips of utils/motion_lib_smpl.py are not redistributable) ----------
+def _q_mul(a, b):
+    ax, ay, az, aw = a[..., 0], a[..., 1], a[..., 2], a[..., 3]
+    bx, by, bz, bw = b[..., 0], b[..., 1], b[..., 2], b[..., 3]
+    return np.stack([aw * bx + ax * bw + ay * bz - az * by, aw * by - ax * bz + ay * bw + az * bx,
+                     aw * bz + ax * by - ay * bx + az * bw, aw * bw - ax * bx - ay * by - az * bz], -1)
+
+
+def _q_rot(q, v):
+    qv = q[..., :3]
+    t = 2.0 * np.cross(qv, v)
+    return v + q[..., 3:4] * t + np.cross(qv, t)
+
+
+def _q_exp(e):
+    ang = np.linalg.norm(e, axis=-1, keepdims=True)
+    ax = np.where(ang > 1e-8, e / np.maximum(ang, 1e-8), np.array([0.0, 0.0, 1.0]))
+    return np.concatenate([ax * np.sin(ang / 2), np.cos(ang / 2)], -1)
+
+
+def synthetic_motion_lib(num_motions=16, seed=0, parent=None, offset=None, fps=30.0):
+    """Walking-like clips in the layout MotionLibSMPL keeps on the device (utils/motion_lib_smpl.py:248-330): per-frame global
+    translations gts [F,24,3], global / local rotations grs / lrs [F,24,4] (xyzw), global linear / angular velocities gvs / gavs
+    [F,24,3], joint velocities dvs [F,23,3]; per motion: length (s), frame count, dt, first-frame index, shape parameters [17].
+    Joint angles are sums of sinusoids, the root walks along its heading; velocities are finite differences, like poselib's."""
+    from .model import build_model_arrays
+    if parent is None:
+        A = build_model_arrays()
+        parent, offset = A["parent"], A["offset"]
+    rng = np.random.default_rng(seed)
+    out = {k: [] for k in ("gts", "grs", "lrs", "gvs", "gavs", "dvs")}
+    lens, nfr, starts = [], [], []
+    dt = 1.0 / fps
+    start = 0
+    for m in range(num_motions):
+        Fm = int(rng.integers(45, 150))
+        t = np.arange(Fm)[:, None, None] * dt
+        amp = rng.uniform(0.05, 0.6, (1, 23, 3)); freq = rng.uniform(0.5, 2.0, (1, 23, 3)); ph = rng.uniform(0, 2 * np.pi, (1, 23, 3))
+        e = amp * np.sin(2 * np.pi * freq * t + ph)                                  # joint exp-maps [F,23,3]
+        yaw0, yawr = rng.uniform(-np.pi, np.pi), rng.uniform(-0.5, 0.5)
+        yaw = yaw0 + yawr * t[:, 0, 0]
+        tilt = 0.08 * np.sin(2 * np.pi * 1.1 * t[:, 0, :] + rng.uniform(0, 6, (1, 1)))  # [F,1]
+        rq = _q_mul(np.stack([0 * yaw, 0 * yaw, np.sin(yaw / 2), np.cos(yaw / 2)], -1), _q_exp(np.concatenate([tilt, tilt * 0.5, 0 * tilt], -1)))
+        lrs = np.concatenate([rq[:, None], _q_exp(e)], 1)                            # [F,24,4]
+        speed = rng.uniform(0.6, 1.6)
+        vel = speed * np.stack([np.cos(yaw), np.sin(yaw), 0 * yaw], -1)
+        rp = np.cumsum(vel * dt, 0) + np.array([rng.uniform(-2, 2), rng.uniform(-2, 2), 0.0])
+        rp[:, 2] = 0.9 + 0.02 * np.sin(2 * np.pi * 2.0 * t[:, 0, 0])
+        grs, gts = np.zeros((Fm, 24, 4)), np.zeros((Fm, 24, 3))
+        grs[:, 0], gts[:, 0] = lrs[:, 0], rp
+        for b in range(1, 24):
+            p = int(parent[b])
+            grs[:, b] = _q_mul(grs[:, p], lrs[:, b])
+            gts[:, b] = gts[:, p] + _q_rot(grs[:, p], np.broadcast_to(offset[b], (Fm, 3)))
+        grs /= np.linalg.norm(grs, axis=-1, keepdims=True)
+        gvs = np.gradient(gts, dt, axis=0)
+
+        def ang_vel(q):                                                              # from consecutive orientations
+            dq = _q_mul(q[1:], q[:-1] * np.array([-1, -1, -1, 1.0]))
+            dq *= np.sign(dq[..., 3:4] + 1e-12)
+            ang = 2 * np.arctan2(np.linalg.norm(dq[..., :3], axis=-1, keepdims=True), dq[..., 3:4])
+            ax = dq[..., :3] / np.maximum(np.linalg.norm(dq[..., :3], axis=-1, keepdims=True), 1e-9)
+            w = ax * ang / dt
+            return np.concatenate([w, w[-1:]], 0)
+        gavs = ang_vel(grs)
+        dvs = ang_vel(lrs[:, 1:])
+        for k, v in (("gts", gts), ("grs", grs), ("lrs", lrs), ("gvs", gvs), ("gavs", gavs), ("dvs", dvs)):
+            out[k].append(v.astype(np.float32))
+        lens.append(dt * (Fm - 1)); nfr.append(Fm); starts.append(start)
+        start += Fm
+    lib = {k: np.concatenate(v, 0) for k, v in out.items()}
+    lib.update(motion_lengths=np.array(lens, np.float32), motion_num_frames=np.array(nfr, np.int32), motion_dt=np.full(num_motions, dt, np.float32),
+               length_starts=np.array(starts, np.int32),
+               motion_bodies=np.concatenate([rng.integers(0, 2, (num_motions, 1)), rng.normal(0, 1, (num_motions, 16))], 1).astype(np.float32),
+               weights=np.full(num_motions, 1.0 / num_motions, np.float32))
+    return lib

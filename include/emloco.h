@@ -399,6 +399,29 @@ int emloco_player_record(const float* d_rew, const float* d_rew_raw, const int64
                          int32_t* d_count, int32_t capacity, int32_t plot_val_reward, float inversion_penalty_scale,
                          float disc_reward_scale, float gamma, int32_t step_to_pred, float min_reward, float max_reward, void* stream);
 
+/* ---- mocap reset state and AMP demo observations (reference pacer/pacer/utils/motion_lib_smpl.py:485-563,596-614
+ * `MotionLibSMPL.get_motion_state_smpl`, env/tasks/humanoid_amp.py:168-220 `fetch_amp_obs_demo` / `build_amp_obs_demo`) ----
+ * The motion library as MotionLibSMPL keeps it on the device (:248-330): per FRAME (all clips concatenated) global translations
+ * gts [F,24,3], global / local rotations grs / lrs [F,24,4] (xyzw), global linear / angular velocities gvs / gavs [F,24,3], joint
+ * velocities dvs [F,23,3]; per MOTION its length (s), frame period, frame count, index of its first frame and shape parameters
+ * [17] (gender + betas).  All device pointers, fp32 / int32. */
+typedef struct emloco_motion_lib {
+    const float *d_gts, *d_grs, *d_lrs, *d_gvs, *d_gavs, *d_dvs;
+    const float *d_length, *d_dt, *d_bodies;
+    const int32_t *d_num_frames, *d_start;
+    int32_t num_motions, reserved;
+} emloco_motion_lib;
+/* get_motion_state_smpl for n (motion id, time) pairs: frame pair + blend (:596-606), lerp / slerp, local rotations -> exp-map
+ * DOFs.  Outputs (any may be NULL) in the layouts the sim consumes: d_root_state [n,13] (pos, rot xyzw, lin vel, ang vel - the
+ * rows of emloco_reset_done's d_init_root), d_dof_state [n,69,2] (pos, vel - d_init_dof), d_key_pos [n,4,3] (R/L ankle, R/L
+ * wrist), d_rb_state [n,24,13] (rg_pos, rb_rot, body_vel, body_ang_vel). */
+int emloco_motion_state(const emloco_motion_lib* lib, const int32_t* d_motion_ids, const float* d_motion_times, int64_t n,
+                        float* d_root_state, float* d_dof_state, float* d_key_pos, float* d_rb_state, void* stream);
+/* build_amp_obs_demo: for each of n samples `num_steps` AMP observations (206 floats: build_amp_observations_smpl,
+ * humanoid_amp.py:917-971) at times t0 - k * dt, newest first -> d_amp_obs [n, num_steps * 206]. */
+int emloco_amp_obs_demo(const emloco_motion_lib* lib, const int32_t* d_motion_ids, const float* d_motion_times0, int64_t n,
+                        int32_t num_steps, float dt, float* d_amp_obs, void* stream);
+
 /* ---- PPO / AMP update step: `AMPValueAgent.calc_gradients`, pacer/pacer/learning/amp_continuous_value.py:276-428
  * (losses: learning/common_agent.py:594-602,657-683, amp_continuous_value.py:430-444, amp_continuous.py:536-616; optimiser:
  * common_agent.py:84-87 torch.optim.Adam + nn.utils.clip_grad_norm_(grad_norm 50); multi-GPU: Horovod `optimizer.synchronize()`

@@ -772,6 +772,42 @@ def reference_player(seed=71, step_to_pred=6):
     return out
 
 
+def reference_motion_lib(n=40, seed=81):
+    """f2: MotionLibSMPL.get_motion_state_smpl (utils/motion_lib_smpl.py:485-563) and HumanoidAMP.build_amp_obs_demo
+    (env/tasks/humanoid_amp.py:186-211, smpl branch -> build_amp_observations_smpl) executed from the reference on the synthetic
+    clips of emloco_b200.synthetic.synthetic_motion_lib(6, seed) - the fixture stores sampled ids / times and the outputs."""
+    from emloco_b200.synthetic import synthetic_motion_lib
+    R = ref_extract.load()
+    torch = R.torch
+    lib = synthetic_motion_lib(6, seed)
+    H = ref_extract.load_motion_lib_block()
+    h = H()
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    h.num_bodies = 24
+    h._key_body_ids = torch.tensor(KEY_BODIES)
+    h._motion_lengths, h._motion_num_frames, h._motion_dt = T(lib["motion_lengths"]), T(lib["motion_num_frames"].astype(np.int64)), T(lib["motion_dt"])
+    h.length_starts = T(lib["length_starts"].astype(np.int64))
+    h.lrs, h.gvs, h.gavs, h.gts, h.dvs, h.grs = (T(lib[k]) for k in ("lrs", "gvs", "gavs", "gts", "dvs", "grs"))
+    h._motion_aa = torch.zeros(lib["gts"].shape[0], 72)
+    h._motion_bodies, h._motion_limb_weights = T(lib["motion_bodies"]), torch.zeros(len(lib["motion_lengths"]), 10)
+    rng = np.random.default_rng(seed)
+    ids = rng.integers(0, 6, n).astype(np.int64)
+    times = (rng.random(n) * lib["motion_lengths"][ids]).astype(np.float32)
+    times[:4] = [0.0, -0.2, lib["motion_lengths"][ids[2]], lib["motion_lengths"][ids[3]] + 0.3]        # both ends and beyond
+    ms = h.get_motion_state_smpl(T(ids), T(times))
+    # build_amp_obs_demo (humanoid_amp.py:186-211): 15 steps back in time, newest first
+    dt = CONTROL_DT
+    mi = torch.tile(T(ids).unsqueeze(-1), [1, AMP_STEPS]).view(-1)
+    mt = (T(times).unsqueeze(-1) + (-dt * torch.arange(0, AMP_STEPS))).view(-1).float()
+    r = h.get_motion_state_smpl(mi, mt)
+    demo = R.jit.build_amp_observations_smpl(r["root_pos"], r["root_rot"], r["root_vel"], r["root_ang_vel"], r["dof_pos"], r["dof_vel"], r["key_pos"],
+                                             r["motion_bodies"], r["motion_limb_weights"], torch.from_numpy(DOF_SUBSET), True, False, True, True, False, True)
+    out = dict(lib_seed=seed, lib_motions=6, ids=ids, times=times, demo=demo.view(n, -1).numpy())
+    for k in ("root_pos", "root_rot", "dof_pos", "root_vel", "root_ang_vel", "dof_vel", "key_pos", "rg_pos", "rb_rot", "body_vel", "body_ang_vel"):
+        out["ms_" + k] = ms[k].numpy()
+    return out
+
+
 def reference_plausibl(B=40, seed=41):
     """a17: plausibl/test_value_mlp.py:24-113 `MLP` (24 -> 12 -> 6 -> 1, no sigmoid), biases randomised."""
     R = ref_extract.load()
@@ -821,6 +857,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "rms_update.npz"), **reference_rms_update())
     np.savez_compressed(os.path.join(OUT, "update_step.npz"), **reference_update_step())
     np.savez_compressed(os.path.join(OUT, "player.npz"), **reference_player())
+    np.savez_compressed(os.path.join(OUT, "motion_lib.npz"), **reference_motion_lib())
     traj, pose, vel = synth_locoval(64, 2)
     W, out = reference_locoval(traj, pose, vel)
     np.savez_compressed(os.path.join(OUT, "locoval.npz"), traj=traj, pose=pose, vel=vel,

@@ -670,6 +670,85 @@ def player_record(st, rew, rew_raw, reset, logit, locoval_scores, inverted=None,
 
 
 # ----------------------------------------------------------------------------------------
+# f2: mocap reset state and AMP demo observations (utils/motion_lib_smpl.py, env/tasks/humanoid_amp.py:168-220)
+# ----------------------------------------------------------------------------------------
+def slerp(q0, q1, t):
+    """utils/torch_utils.py:114-136 (t broadcastable to [..., 1])."""
+    q0, q1 = q0.astype(F), q1.astype(F).copy()
+    c = np.sum(q0 * q1, axis=-1, dtype=F)
+    neg = c < 0
+    q1[neg] = -q1[neg]
+    c = np.abs(c)[..., None]
+    half = np.arccos(np.minimum(c, F(1))).astype(F)
+    s = np.sqrt(np.maximum(F(1) - c * c, F(0))).astype(F)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ra = np.sin((F(1) - t) * half) / s
+        rb = np.sin(t * half) / s
+        q = ra * q0 + rb * q1
+    q = np.where(np.abs(s) < F(0.001), F(0.5) * q0 + F(0.5) * q1, q)
+    q = np.where(np.abs(c) >= 1, q0, q)
+    return q.astype(F)
+
+
+def quat_to_exp_map(q):
+    """utils/torch_utils.py:27-65: angle-axis with angle wrapped to (-pi, pi], default axis z below 1e-5."""
+    q = q.astype(F)
+    sin_t = np.sqrt(np.maximum(F(1) - q[..., 3] * q[..., 3], F(0))).astype(F)
+    ang = normalize_angle((F(2) * np.arccos(np.clip(q[..., 3], F(-1), F(1)))).astype(F))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        axis = q[..., :3] / sin_t[..., None]
+    mask = np.abs(sin_t) > F(1e-5)
+    default = np.zeros_like(axis); default[..., 2] = 1
+    ang = np.where(mask, ang, F(0))
+    axis = np.where(mask[..., None], axis, default)
+    return (ang[..., None] * axis).astype(F)
+
+
+def calc_frame_blend(time, length, num_frames, dt):
+    """utils/motion_lib_smpl.py:596-606."""
+    time = time.astype(F).copy()
+    phase = np.clip(time / length, F(0), F(1))
+    time[time < 0] = 0
+    f0 = (phase * (num_frames - 1).astype(F)).astype(np.int64)
+    f1 = np.minimum(f0 + 1, num_frames - 1)
+    blend = (time - f0.astype(F) * dt) / dt
+    return f0, f1, blend.astype(F)
+
+
+def motion_state(lib, motion_ids, motion_times):
+    """MotionLibSMPL.get_motion_state_smpl (utils/motion_lib_smpl.py:485-563) on the flat arrays of `lib`
+    (emloco_b200.synthetic.synthetic_motion_lib layout)."""
+    f0, f1, blend = calc_frame_blend(motion_times, lib["motion_lengths"][motion_ids], lib["motion_num_frames"][motion_ids], lib["motion_dt"][motion_ids])
+    f0l, f1l = f0 + lib["length_starts"][motion_ids], f1 + lib["length_starts"][motion_ids]
+    b = blend[:, None, None]
+    lerp = lambda k: ((F(1) - b) * lib[k][f0l] + b * lib[k][f1l]).astype(F)
+    rg_pos, body_vel, body_ang_vel, dof_vel = lerp("gts"), lerp("gvs"), lerp("gavs"), lerp("dvs")
+    local_rot = slerp(lib["lrs"][f0l], lib["lrs"][f1l], b)
+    rb_rot = slerp(lib["grs"][f0l], lib["grs"][f1l], b)
+    dof_pos = quat_to_exp_map(local_rot[:, 1:]).reshape(len(motion_ids), -1)
+    return dict(root_pos=rg_pos[:, 0], root_rot=rb_rot[:, 0], dof_pos=dof_pos, root_vel=body_vel[:, 0], root_ang_vel=body_ang_vel[:, 0],
+                dof_vel=dof_vel.reshape(len(motion_ids), -1), key_pos=rg_pos[:, KEY_BODIES], rg_pos=rg_pos, rb_rot=rb_rot, body_vel=body_vel,
+                body_ang_vel=body_ang_vel, motion_bodies=lib["motion_bodies"][motion_ids])
+
+
+def amp_obs_demo(lib, motion_ids, motion_times0, dt=CONTROL_DT, steps=AMP_STEPS):
+    """HumanoidAMP.build_amp_obs_demo (env/tasks/humanoid_amp.py:186-211): `steps` observations per sample at times
+    t0 - k dt, newest first -> [n, steps * 206]."""
+    n = len(motion_ids)
+    ids = np.repeat(motion_ids, steps)
+    times = (motion_times0[:, None].astype(F) + (-F(dt) * np.arange(steps, dtype=F))[None]).reshape(-1)
+    m = motion_state(lib, ids, times)
+    hinv = calc_heading_quat_inv(m["root_rot"])
+    root_rot_obs = quat_to_tan_norm(quat_mul(hinv, m["root_rot"]))
+    lv, la = my_quat_rotate(hinv, m["root_vel"]), my_quat_rotate(hinv, m["root_ang_vel"])
+    key = m["key_pos"] - m["root_pos"][:, None]
+    key = my_quat_rotate(np.repeat(hinv[:, None], 4, 1).reshape(-1, 4), key.reshape(-1, 3)).reshape(len(ids), 12)
+    dof_obs = quat_to_tan_norm(exp_map_to_quat(m["dof_pos"][:, DOF_SUBSET].reshape(-1, 3))).reshape(len(ids), -1)
+    obs = np.concatenate([root_rot_obs, lv, la, dof_obs, m["dof_vel"][:, DOF_SUBSET], key, m["motion_bodies"][:, :-6]], -1).astype(F)
+    return obs.reshape(n, steps * AMP_STEP_DIM)
+
+
+# ----------------------------------------------------------------------------------------
 # a15: GAE
 # ----------------------------------------------------------------------------------------
 def discount_values(fdones, values, rewards, next_values, gamma=0.99, tau=0.95):

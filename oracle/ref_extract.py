@@ -299,6 +299,23 @@ def load_player_block():
     return mod.Holder
 
 
+def load_motion_lib_block():
+    """MotionLibSMPL.get_motion_state_smpl / _calc_frame_blend / _get_num_bodies / _local_rotation_to_dof_smpl
+    (utils/motion_lib_smpl.py:485-563,596-614) on a holder (the module imports poselib, joblib pickles and the SMPL parser)."""
+    if "motionlib" in _cache:
+        return _cache["motionlib"]
+    load()
+    ml = os.path.join(PACER, "utils/motion_lib_smpl.py")
+    src = "import torch\nimport numpy as np\nfrom utils import torch_utils\n\nclass Holder:\n" + _lines(ml, 485, 563) + "\n" + _lines(ml, 596, 614) + "\n"
+    tmp = tempfile.mkdtemp(prefix="emloco_ref_")
+    p = os.path.join(tmp, "emloco_ref_motionlib.py")
+    with open(p, "w") as f:
+        f.write(src)
+    mod = _import_path("emloco_ref_motionlib", p)
+    _cache["motionlib"] = mod.Holder
+    return mod.Holder
+
+
 def load_plausibl_mlp():
     """plausibl/test_value_mlp.py:24-113 `class MLP` (the script's imports point at a developer's home directory)."""
     if "plausibl" in _cache:

@@ -90,6 +90,9 @@ int main(void) {
     printf("emloco_rollout_cfg %zu\\n", sizeof(emloco_rollout_cfg));
     printf("emloco_post_sinks %zu\\n", sizeof(emloco_post_sinks));
     printf("emloco_traj_cfg %zu\\n", sizeof(emloco_traj_cfg));
+    printf("emloco_motion_lib %zu\\n", sizeof(emloco_motion_lib));
+    printf("rollout.d_value_stats %zu\\n", offsetof(emloco_rollout_cfg, d_value_stats));
+    printf("motion.num_motions %zu\\n", offsetof(emloco_motion_lib, num_motions));
     printf("cfg.max_effort %zu\\n", offsetof(emloco_cfg, max_effort));
     printf("cfg.physics_impl %zu\\n", offsetof(emloco_cfg, physics_impl));
     printf("sinks.rows_only %zu\\n", offsetof(emloco_post_sinks, rows_only));
@@ -109,6 +112,9 @@ int main(void) {
     assert out["emloco_rollout_cfg"] == C.sizeof(_lib.RolloutCfg)
     assert out["emloco_post_sinks"] == C.sizeof(_lib.PostSinks)
     assert out["emloco_traj_cfg"] == C.sizeof(_lib.TrajCfg)
+    assert out["emloco_motion_lib"] == C.sizeof(_lib.MotionLib)
+    assert out["rollout.d_value_stats"] == _lib.RolloutCfg.d_value_stats.offset
+    assert out["motion.num_motions"] == _lib.MotionLib.num_motions.offset
     assert out["cfg.max_effort"] == _lib.Cfg.max_effort.offset and out["cfg.physics_impl"] == _lib.Cfg.physics_impl.offset
     assert out["sinks.rows_only"] == _lib.PostSinks.rows_only.offset and out["sinks.ld_amp"] == _lib.PostSinks.ld_amp.offset
     assert out["traj.seed"] == _lib.TrajCfg.seed.offset and out["traj.num_waypoints"] == _lib.TrajCfg.num_waypoints.offset

@@ -668,3 +668,48 @@ def test_plausibl_mlp_matches_reference_class_golden(B):
     W = dict(fc1=(g["w__value_mlp.0.weight"], g["w__value_mlp.0.bias"]), fc2=(g["w__value_mlp.2.weight"], g["w__value_mlp.2.bias"]),
              fc3=(g["w__value_logits.weight"], g["w__value_logits.bias"]))
     np.testing.assert_allclose(y.cpu().numpy(), O.plausibl_mlp(x, W), rtol=1e-4, atol=1e-5)
+
+
+def test_motion_lib_state_and_amp_demo_match_reference_golden():
+    """f2: emloco_motion_state / emloco_amp_obs_demo against the reference's motion-library code (motion_lib.npz) and the oracle
+    on 5000 fresh samples; reset-state sampling writes valid rows into a Rollout's init buffers."""
+    from emloco_b200.motion_lib import MotionLibSMPL
+    from emloco_b200.synthetic import synthetic_motion_lib
+    from oracle import oracle_np as O
+    g = np.load(os.path.join(GOLDEN, "motion_lib.npz"))
+    arrays = synthetic_motion_lib(int(g["lib_motions"]), int(g["lib_seed"]))
+    lib = MotionLibSMPL(arrays)
+    ids, times = torch.from_numpy(g["ids"]).cuda(), torch.from_numpy(g["times"]).cuda()
+    ms = lib.get_motion_state_smpl(ids, times, full=True)
+    root, dof, rb = ms["root_state"].cpu().numpy(), ms["dof_state"].cpu().numpy(), ms["rb_state"].cpu().numpy()
+    tol = dict(rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(root[:, 0:3], g["ms_root_pos"], **tol); np.testing.assert_allclose(root[:, 3:7], g["ms_root_rot"], **tol)
+    np.testing.assert_allclose(root[:, 7:10], g["ms_root_vel"], **tol); np.testing.assert_allclose(root[:, 10:13], g["ms_root_ang_vel"], **tol)
+    np.testing.assert_allclose(dof[..., 0], g["ms_dof_pos"], rtol=1e-4, atol=5e-5); np.testing.assert_allclose(dof[..., 1], g["ms_dof_vel"], **tol)
+    np.testing.assert_allclose(ms["key_pos"].cpu().numpy(), g["ms_key_pos"], **tol)
+    np.testing.assert_allclose(rb[..., 0:3], g["ms_rg_pos"], **tol); np.testing.assert_allclose(rb[..., 3:7], g["ms_rb_rot"], **tol)
+    np.testing.assert_allclose(rb[..., 7:10], g["ms_body_vel"], **tol); np.testing.assert_allclose(rb[..., 10:13], g["ms_body_ang_vel"], **tol)
+    demo = lib.fetch_amp_obs_demo(len(g["ids"]), motion_ids=ids, motion_times0=times)
+    np.testing.assert_allclose(demo.cpu().numpy(), g["demo"], rtol=1e-3, atol=5e-5)
+    # larger, fresh draws against the oracle
+    big = MotionLibSMPL(synthetic_motion_lib(32, 5), seed=3)
+    i2 = big.sample_motions(5000); t2 = big.sample_time(i2)
+    assert i2.min() >= 0 and i2.max() < 32 and (t2 >= 0).all() and (t2 <= big.motion_lengths[i2.long()]).all()
+    d2 = big.fetch_amp_obs_demo(5000, motion_ids=i2, motion_times0=t2).cpu().numpy()
+    ref = O.amp_obs_demo(synthetic_motion_lib(32, 5), i2.cpu().numpy().astype(np.int64), t2.cpu().numpy())
+    np.testing.assert_allclose(d2, ref, rtol=1e-3, atol=1e-4)
+    assert big.fetch_amp_obs_demo(0).shape == (0, 3090)
+    # reset from mocap states: rows written in place, xy kept, unit root quaternions
+    from emloco_b200.rollout import Rollout
+    R = Rollout(64, seed=1, tensor_cores=False)
+    xy = R.init_root[:, :2].clone()
+    big.sample_reset_state(R.init_root, R.init_dof)
+    torch.cuda.synchronize()
+    assert torch.equal(R.init_root[:, :2], xy)
+    np.testing.assert_allclose(R.init_root[:, 3:7].norm(dim=1).cpu().numpy(), 1.0, atol=1e-5)
+    assert float(R.init_dof.abs().max()) > 0.01
+    R.sim.reset.fill_(1)
+    R.step(0)                                        # envs restart from the sampled mocap states and step without NaNs
+    torch.cuda.synchronize()
+    assert torch.isfinite(R.sim.obs).all() and torch.isfinite(R.sim.rb_state).all()
+    R.close()
