@@ -62,7 +62,7 @@ class ReplayBuffer:
 class AMPValueAgent:
     def __init__(self, num_envs, horizon=32, minibatch_size=16384, amp_minibatch_size=None, mini_epochs=6, amp_batch_size=None,
                  amp_obs_demo_buffer_size=200000, amp_replay_buffer_size=200000, amp_replay_keep_prob=0.01, fetch_amp_obs_demo=None,
-                 normalize_advantage=True, seed=0, device=0, update_cfg=None, graphed=True, **rollout_kw):
+                 normalize_advantage=True, seed=0, device=0, update_cfg=None, graphed=True, motion_lib=None, **rollout_kw):
         self.R = Rollout(num_envs, device=device, horizon=horizon, seed=seed, tensor_cores=True, **rollout_kw)
         R = self.R
         self.T, self.N = R.T, R.N
@@ -80,9 +80,15 @@ class AMPValueAgent:
         self._demo = ReplayBuffer(amp_obs_demo_buffer_size, dev, self.gen)
         self._replay = ReplayBuffer(amp_replay_buffer_size, dev, self.gen)
         self._keep_prob = float(amp_replay_keep_prob)
-        # demos: `task.fetch_amp_obs_demo(n)` (humanoid_amp.py:168-220) needs the motion library; a callable can be passed, the
-        # default draws synthetic rows (no AMASS data in the tree)
-        self.fetch_amp_obs_demo = fetch_amp_obs_demo or (lambda n: torch.randn(n, AMP_OBS, device=dev, generator=self.gen))
+        # demos and reset states come from the motion library (motion_lib.MotionLibSMPL: `task.fetch_amp_obs_demo(n)`,
+        # humanoid_amp.py:168-220, and `_sample_ref_state`, :295-317).  Default: synthetic walking clips (the AMASS data the
+        # reference loads are not redistributable); pass `motion_lib=` built from real clips, or a `fetch_amp_obs_demo` callable.
+        if motion_lib is None and fetch_amp_obs_demo is None:
+            from .motion_lib import MotionLibSMPL
+            from .synthetic import synthetic_motion_lib
+            motion_lib = MotionLibSMPL(synthetic_motion_lib(64, seed), device=device, seed=seed + 5)
+        self.motion_lib = motion_lib
+        self.fetch_amp_obs_demo = fetch_amp_obs_demo or (lambda n: motion_lib.fetch_amp_obs_demo(n, dt=2.0 / 60.0))
         for _ in range(-(-self._demo.get_buffer_size() // self.amp_batch_size)):        # _init_amp_demo_buf (:636-644)
             self._demo.store({"amp_obs": self.fetch_amp_obs_demo(self.amp_batch_size)})
         self.epoch = 0
@@ -98,6 +104,10 @@ class AMPValueAgent:
 
     def train_epoch(self):
         R, up, T, N = self.R, self.up, self.T, self.N
+        if self.motion_lib is not None:
+            # fresh mocap start states for the envs that reset during this horizon (one draw per env and horizon; the reference
+            # draws at every reset, humanoid_amp.py:295-317 - same distribution, consumed by the device-side reset)
+            self.motion_lib.sample_reset_state(R.init_root, R.init_dof)
         b = R.play_steps(graphed=self.graphed)                                          # :183-186
         fl = lambda t: t.reshape(T * N, *t.shape[2:])
         self._demo.store({"amp_obs": self.fetch_amp_obs_demo(self.amp_batch_size)})     # _update_amp_demos (:646-649)
