@@ -139,7 +139,7 @@ def load():
     lib.emloco_amp_dropout_mask.argtypes = [vp, vp, i64, f32, vp]
     lib.emloco_rms_update.argtypes = [vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, f32, vp]
     lib.emloco_adam_begin.argtypes = [vp, vp]
-    lib.emloco_grad_sumsq.argtypes = [vp, i64, vp, vp]
+    lib.emloco_grad_sumsq.argtypes = [vp, i64, vp, vp, vp]
     lib.emloco_adam_clip.argtypes = [vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, f32, f32, vp]
     lib.emloco_axpy.argtypes = [vp, vp, f32, i64, vp]
     lib.emloco_sum_parts.argtypes = [vp, i32, i64, vp, i64, i32, vp]
@@ -163,7 +163,7 @@ LAUNCHES = {"emloco_step": 2, "emloco_physics_step": 1, "emloco_post_step": 1, "
             "emloco_locoval_forward_host": 1, "emloco_split_bf16": 1, "emloco_linear_bf16x3": 1, "emloco_linear_bf16x3_rows": 1, "emloco_linear_bf16x3_head": 2,
             "emloco_timeout_gather": 1, "emloco_rollout_record_deferred": 1, "emloco_fill_next_values": 1,
             "emloco_xform": 1, "emloco_ppo_heads": 1, "emloco_disc_heads": 1, "emloco_amp_dropout_mask": 1, "emloco_rms_update": 2,
-            "emloco_adam_begin": 1, "emloco_grad_sumsq": 1, "emloco_adam_clip": 1, "emloco_axpy": 1, "emloco_sum_parts": 1, "emloco_player_record": 1, "emloco_motion_state": 1, "emloco_amp_obs_demo": 1}
+            "emloco_adam_begin": 1, "emloco_grad_sumsq": 2, "emloco_adam_clip": 1, "emloco_axpy": 1, "emloco_sum_parts": 1, "emloco_player_record": 1, "emloco_motion_state": 1, "emloco_amp_obs_demo": 1}
 launch_count = 0
 mac_count = 0          # multiply-accumulates of the dense-layer launches (M * N * K each), for the benches' FLOP figures
 

@@ -32,7 +32,7 @@ cudaError_t eml_disc_heads(const float* logit, float* dlogit, float* stats, long
 cudaError_t eml_amp_dropout_mask(const float* u, float* mask, long long rows, float rate, cudaStream_t st);
 cudaError_t eml_rms_update(const float* x, long long ldx, long long M, int K, double* scratch, double* rmean, double* rvar, double* count,
                            float* mean32, float* var32, float* inv32, float eps, cudaStream_t st);
-cudaError_t eml_grad_sumsq(const float* g, long long n, float* state, cudaStream_t st);
+cudaError_t eml_grad_sumsq(const float* g, long long n, float* state, float* partials, cudaStream_t st);
 cudaError_t eml_adam_clip(float* p, const float* g, float* m, float* v, long long n, float* state, float lr, float beta1, float beta2,
                           float eps, float max_norm, float grad_scale, cudaStream_t st);
 cudaError_t eml_adam_begin(float* state, cudaStream_t st);
@@ -705,9 +705,9 @@ int emloco_adam_begin(float* d_state, void* stream) {
     return EMLOCO_OK;
 }
 
-int emloco_grad_sumsq(const float* d_grad, int64_t n, float* d_state, void* stream) {
-    if (!d_grad || !d_state || n < 0) return fail(EMLOCO_EINVAL, "emloco_grad_sumsq: bad argument");
-    CK(eml_grad_sumsq(d_grad, n, d_state, (cudaStream_t)stream), "grad sumsq");
+int emloco_grad_sumsq(const float* d_grad, int64_t n, float* d_state, float* d_partials, void* stream) {
+    if (!d_grad || !d_state || !d_partials || n < 0) return fail(EMLOCO_EINVAL, "emloco_grad_sumsq: bad argument");
+    CK(eml_grad_sumsq(d_grad, n, d_state, d_partials, (cudaStream_t)stream), "grad sumsq");
     return EMLOCO_OK;
 }
 

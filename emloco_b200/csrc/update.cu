@@ -394,14 +394,25 @@ __global__ void rms_update_kernel(double* __restrict__ sum, double* __restrict__
 }
 
 // ---- clip_grad_norm_ + Adam ----
-__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+// Deterministic (fixed grid, fixed summation order): every rank of a data-parallel run computes bit-identical norms from the
+// bit-identical all-reduced gradient, so the parameters never drift apart (float atomics would differ in the last bit).
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ partials) {
     __shared__ float red[8];
     float a = 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) { const float v = g[i]; a += v * v; }
     a = warp_sum(a);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
     __syncthreads();
-    if (threadIdx.x == 0) { float s = 0.f; for (int w = 0; w < 8; ++w) s += red[w]; atomicAdd(out, s); }
+    if (threadIdx.x == 0) { float s = 0.f; for (int w = 0; w < 8; ++w) s += red[w]; partials[blockIdx.x] = s; }
+}
+__global__ void __launch_bounds__(256) sumsq_final_kernel(const float* __restrict__ partials, int count, float* __restrict__ out) {
+    __shared__ float red[256];
+    float a = 0.f;
+    for (int i = threadIdx.x; i < count; i += 256) a += partials[i];
+    red[threadIdx.x] = a;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) *out += red[0];
 }
 
 // state: [0] step count (float), [1] sum of squares of the gradient (input, cleared by the last block... no: cleared by the caller)
@@ -502,10 +513,11 @@ cudaError_t eml_rms_update(const float* x, long long ldx, long long M, int K, do
     return cudaGetLastError();
 }
 
-cudaError_t eml_grad_sumsq(const float* g, long long n, float* state, cudaStream_t st) {
+cudaError_t eml_grad_sumsq(const float* g, long long n, float* state, float* partials, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     long long blocks = (n + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
-    sumsq_kernel<<<(unsigned)blocks, 256, 0, st>>>(g, n, state + 1);
+    sumsq_kernel<<<(unsigned)blocks, 256, 0, st>>>(g, n, partials);
+    sumsq_final_kernel<<<1, 256, 0, st>>>(partials, (int)blocks, state + 1);
     return cudaGetLastError();
 }
 

@@ -92,6 +92,7 @@ class FlatParams:
         z = lambda: torch.zeros(n, device=dev, dtype=torch.float32)
         self.p, self.g, self.m, self.v = z(), z(), z(), z()
         self.state = torch.zeros(2, device=dev, dtype=torch.float32)      # Adam step count, sum of squares of the gradient
+        self.partials = torch.zeros(148 * 8, device=dev, dtype=torch.float32)
         for k in self.GEMM + self.TAIL:
             q = named[k]
             view = self.p[self.off[k]:self.off[k] + q.numel()].view_as(q)
@@ -371,7 +372,7 @@ class PPOUpdate:
         """Gradient average over ranks (one all-reduce of the flat buffer), clip-norm, Adam, fresh operand splits."""
         FP, cfg, lib = self.flat, self.cfg, _lib.load()
         self.reducer.finish()                                          # summed; the 1 / world factor is folded into the Adam kernel
-        _lib.check(lib.emloco_grad_sumsq(_ptr(FP.g), FP.n, _ptr(FP.state), _stream()), "emloco_grad_sumsq")
+        _lib.check(lib.emloco_grad_sumsq(_ptr(FP.g), FP.n, _ptr(FP.state), _ptr(FP.partials), _stream()), "emloco_grad_sumsq")
         _lib.check(lib.emloco_adam_clip(_ptr(FP.p), _ptr(FP.g), _ptr(FP.m), _ptr(FP.v), FP.n, _ptr(FP.state), cfg["lr"], 0.9, 0.999, 1e-8,
                                         cfg["grad_norm"], 1.0 / self.world, _stream()), "emloco_adam_clip")
         self.refresh_weights()

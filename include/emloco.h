@@ -459,10 +459,11 @@ int emloco_rms_update(const float* d_x, int64_t ldx, int64_t M, int32_t K, doubl
                       double* d_running_var, double* d_count, float* d_mean32, float* d_var32, float* d_inv_std32, float eps,
                       void* stream);
 /* clip_grad_norm_ + Adam over flat buffers.  d_state[2] = {step count, sum of squares of the gradient}: emloco_adam_begin
- * increments the step and clears the sum, emloco_grad_sumsq accumulates it (after the all-reduce, on the SUMMED gradient),
+ * increments the step and clears the sum, emloco_grad_sumsq accumulates it (after the all-reduce, on the SUMMED gradient;
+ * deterministic two-stage reduction through d_partials [>= 1184] so that every rank computes the same norm to the last bit),
  * emloco_adam_clip scales the gradient by grad_scale (1 / world size) and min(1, max_norm / (norm + 1e-6)) and steps. */
 int emloco_adam_begin(float* d_state, void* stream);
-int emloco_grad_sumsq(const float* d_grad, int64_t n, float* d_state, void* stream);
+int emloco_grad_sumsq(const float* d_grad, int64_t n, float* d_state, float* d_partials, void* stream);
 int emloco_adam_clip(float* d_param, const float* d_grad, float* d_m, float* d_v, int64_t n, float* d_state, float lr, float beta1,
                      float beta2, float eps, float max_norm, float grad_scale, void* stream);
 /* y += a * x (weight-decay / logit-regularisation terms of the discriminator loss, amp_continuous.py:548-550,585-589). */
