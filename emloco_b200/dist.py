@@ -136,9 +136,10 @@ class BucketedAllReduce:
     overlap it), `finish()` reduces [split, n) and waits for both.  Sums, does not average - the 1 / world factor is folded
     into the optimiser kernel.  World size 1 or an uninitialised process group: no-ops."""
 
-    def __init__(self, flat, split, overlap=True):
+    def __init__(self, flat, split, overlap=True, world=None):
         self.flat, self.split, self.overlap = flat, int(split), bool(overlap)
-        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        # world = 1 forces a purely local step even inside an initialised process group (single-process reference runs)
+        self.world = (dist.get_world_size() if dist.is_initialized() else 1) if world is None else int(world)
         self._pending = None
 
     def start_first(self):

@@ -195,9 +195,7 @@ class PPOUpdate:
         self._ws, self._e0_scale = None, 1.0
         self.split_k = True                 # weight gradients with few output tiles: split the contraction (the minibatch) over CTAs
         from .dist import BucketedAllReduce
-        self.reducer = BucketedAllReduce(self.flat.g, self.flat.bucket0, overlap=self.overlap)
-        if world is None:
-            self.world = self.reducer.world
+        self.reducer = BucketedAllReduce(self.flat.g, self.flat.bucket0, overlap=self.overlap, world=self.world)
         self.refresh_weights()
 
     # ---- parameters -------------------------------------------------------------------------------------------------------

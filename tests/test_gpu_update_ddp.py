@@ -18,7 +18,7 @@ def test_two_rank_update_equals_single_process_step_on_averaged_gradients(tmp_pa
     script.write_text(WORKER_ONE_STEP)
     env = dict(os.environ, EMLOCO_ROOT=ROOT)
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                          "--master-port", str(29700 + os.getpid() % 200), str(script)], env=env, capture_output=True, text=True, timeout=900)
+                          "--master-port", str(29700 + os.getpid() % 200), str(script)], env=env, capture_output=True, text=True, timeout=150)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "DDP_OK" in out.stdout, out.stdout[-2000:]
 
