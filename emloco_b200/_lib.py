@@ -19,7 +19,7 @@ SYMBOLS = [
     "emloco_disc_reward", "emloco_rollout_record", "emloco_normalize", "emloco_physics_step", "emloco_split_bf16",
     "emloco_linear_bf16x3", "emloco_set_post_sinks", "emloco_linear_bf16x3_rows", "emloco_timeout_gather",
     "emloco_rollout_record_deferred", "emloco_fill_next_values", "emloco_traj_reset", "emloco_set_traj_reset", "emloco_locoval_backward_pose", "emloco_locoval_train_step", "emloco_locoval_train_workspace_bytes", "emloco_linear_bf16x3_head", "emloco_sample_actions_parts", "emloco_linear", "emloco_xform", "emloco_ppo_heads", "emloco_disc_heads", "emloco_amp_dropout_mask",
-    "emloco_rms_update", "emloco_adam_begin", "emloco_grad_sumsq", "emloco_adam_clip", "emloco_axpy", "emloco_sum_parts", "emloco_player_record", "emloco_motion_state", "emloco_amp_obs_demo", "emloco_sync", "emloco_last_error", "emloco_version",
+    "emloco_rms_update", "emloco_adam_begin", "emloco_grad_sumsq", "emloco_adam_clip", "emloco_axpy", "emloco_sum_parts", "emloco_player_record", "emloco_motion_state", "emloco_amp_obs_demo", "emloco_set_env_models", "emloco_sync", "emloco_last_error", "emloco_version",
 ]
 
 
@@ -146,6 +146,7 @@ def load():
     lib.emloco_player_record.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, i32, i32, f32, f32, f32, i32, f32, f32, vp]
     lib.emloco_motion_state.argtypes = [C.POINTER(MotionLib), vp, vp, i64, vp, vp, vp, vp, vp]
     lib.emloco_amp_obs_demo.argtypes = [C.POINTER(MotionLib), vp, vp, i64, i32, f32, vp, vp]
+    lib.emloco_set_env_models.argtypes = [vp, vp]
     lib.emloco_sync.argtypes = [vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)

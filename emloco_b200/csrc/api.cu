@@ -187,10 +187,32 @@ int emloco_destroy(emloco_sim* s) {
     cudaSetDevice(s->device);
     void* ptrs[] = {s->root_state, s->dof_state, s->rb_state, s->contact, s->dof_force, s->pd_target, s->joint_quat, s->actions,
                     s->obs, s->flip_obs, s->rew, s->rew_raw, s->reset, s->terminate, s->progress, s->amp_obs, s->verts, s->betas,
-                    s->height, s->traj_epoch, (void*)s->ring_ptr};
+                    s->height, s->traj_epoch, (void*)s->ring_ptr, s->env_model};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (s->h_pin) cudaFreeHost(s->h_pin);
     free(s);
+    return EMLOCO_OK;
+}
+
+int emloco_set_env_models(emloco_sim* s, const float* h_env_models) {
+    if (!s) return fail(EMLOCO_EINVAL, "emloco_set_env_models: null sim");
+    CK(cudaSetDevice(s->device), "cudaSetDevice");
+    CK(cudaDeviceSynchronize(), "sync before replacing the body models");
+    if (!h_env_models) {                                      // back to the shared model
+        if (s->env_model) cudaFree(s->env_model);
+        s->env_model = nullptr;
+        return EMLOCO_OK;
+    }
+    const size_t N = (size_t)s->N;
+    std::vector<float> t((size_t)EM_FLOATS * N);              // env-major [N][576] -> field-major [576][N]
+    for (size_t e = 0; e < N; ++e) {
+        const float* m = h_env_models + e * EM_FLOATS;
+        for (int b = 0; b < EML_NB; ++b)
+            if (!(m[EM_MASS + b] > 0.f)) return fail(EMLOCO_EINVAL, "emloco_set_env_models: body mass must be positive");
+        for (int f = 0; f < EM_FLOATS; ++f) t[(size_t)f * N + e] = m[f];
+    }
+    if (!s->env_model) CK(cudaMalloc(&s->env_model, t.size() * sizeof(float)), "cudaMalloc env models");
+    CK(cudaMemcpy(s->env_model, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice), "upload env models");
     return EMLOCO_OK;
 }
 

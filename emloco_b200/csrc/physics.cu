@@ -23,6 +23,7 @@
 #define PH_WARPS 4
 
 
+template <bool ENVM>
 __global__ void __launch_bounds__(PH_WARPS * 32) physics_kernel(PhysParams P) {
     __shared__ __align__(16) float s_rb[PH_WARPS][EML_NB * 13];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -33,16 +34,17 @@ __global__ void __launch_bounds__(PH_WARPS * 32) physics_kernel(PhysParams P) {
     const bool body = lane < EML_NB;
     const int b = body ? lane : 0;
     const EmlModelDev& Mo = *P.model;
+    const ModelView<ENVM> MV{Mo, P.env_model, (size_t)P.N, (size_t)env};
 
     // ---- per-lane model constants ----
     const int parent = body ? Mo.parent[b] : 0;
     const int level = body ? Mo.level[b] : 99;
     const int par = parent < 0 ? 0 : parent;
     int ch0 = body ? Mo.child[b][0] : -1, ch1 = body ? Mo.child[b][1] : -1, ch2 = body ? Mo.child[b][2] : -1;
-    const f3 offset = mk3(Mo.offset[b][0], Mo.offset[b][1], Mo.offset[b][2]);
-    const float mass = Mo.mass[b];
-    const f3 com = mk3(Mo.com[b][0], Mo.com[b][1], Mo.com[b][2]);
-    const float kp = Mo.kp[b], kd = Mo.kd[b], arm = Mo.arm[b];
+    const f3 offset = MV.offset(b);
+    const float mass = MV.mass(b);
+    const f3 com = MV.com(b);
+    const float kp = MV.kp(b), kd = MV.kd(b), arm = MV.arm(b);
     const int max_level = Mo.max_level;
     const bool joint = body && b > 0;
 
@@ -126,8 +128,7 @@ __global__ void __launch_bounds__(PH_WARPS * 32) physics_kernel(PhysParams P) {
         // ================= rigid-body inertia about O, bias force, gravity =================
         S3 A, Mm; M3 Bm; f3 pn, pf;
         {
-            const float* I6 = Mo.inertia[b];
-            S3 Ib; Ib.xx = I6[0]; Ib.xy = I6[1]; Ib.xz = I6[2]; Ib.yy = I6[3]; Ib.yz = I6[4]; Ib.zz = I6[5];
+            S3 Ib; Ib.xx = MV.inertia(b, 0); Ib.xy = MV.inertia(b, 1); Ib.xz = MV.inertia(b, 2); Ib.yy = MV.inertia(b, 3); Ib.yz = MV.inertia(b, 4); Ib.zz = MV.inertia(b, 5);
             M3 T;                                                    // T = R * Ib
 #pragma unroll
             for (int r = 0; r < 3; ++r) setrow(T, r, sv(Ib, row(R, r)));
@@ -155,9 +156,9 @@ __global__ void __launch_bounds__(PH_WARPS * 32) physics_kernel(PhysParams P) {
         float F0z = 0, Sbt = 0, Sbn = 0, Stz = 0, Sty = 0, Stx = 0, Sny = 0, Snx = 0;
         if (body) {
             const int gt = Mo.geom_type[b];
-            const f3 ga = mk3(Mo.geom_a[b][0], Mo.geom_a[b][1], Mo.geom_a[b][2]);
-            const f3 gb = mk3(Mo.geom_b[b][0], Mo.geom_b[b][1], Mo.geom_b[b][2]);
-            const float drop = gt == 2 ? 0.f : Mo.geom_r[b];
+            const f3 ga = MV.geom_a(b);
+            const f3 gb = MV.geom_b(b);
+            const float drop = gt == 2 ? 0.f : MV.geom_r(b);
             const int np = gt == 0 ? 1 : (gt == 1 ? 2 : 8);
             const float bn = P.kn * dt + P.cn;
 #pragma unroll 1
@@ -373,7 +374,7 @@ cudaError_t eml_upload_model(const EmlModelDev* m) {
 void eml_fill_phys_params(emloco_sim* s, PhysParams& P);
 static void fill_params(emloco_sim* s, PhysParams& P) { eml_fill_phys_params(s, P); }
 void eml_fill_phys_params(emloco_sim* s, PhysParams& P) {
-    P.model = g_model_dev;
+    P.model = g_model_dev; P.env_model = s->env_model;
     P.actions = nullptr; P.pd_target = s->pd_target; P.actions_copy = nullptr;
     P.root = s->root_state; P.dof = s->dof_state; P.jq = s->joint_quat; P.rb = s->rb_state;
     P.contact = s->contact; P.dof_force = s->dof_force;
@@ -392,7 +393,8 @@ cudaError_t eml_launch_physics(emloco_sim* s, const float* d_actions, int n_subs
     PhysParams P; fill_params(s, P);
     P.actions = d_actions; P.actions_copy = d_actions ? s->actions : nullptr; P.n_sub = n_substeps;
     int blocks = (s->N + PH_WARPS - 1) / PH_WARPS;
-    physics_kernel<<<blocks, PH_WARPS * 32, 0, st>>>(P);
+    if (P.env_model) physics_kernel<true><<<blocks, PH_WARPS * 32, 0, st>>>(P);
+    else physics_kernel<false><<<blocks, PH_WARPS * 32, 0, st>>>(P);
     return cudaGetLastError();
 }
 
@@ -401,7 +403,8 @@ cudaError_t eml_launch_fk(emloco_sim* s, const int32_t* d_env_ids, int n, cudaSt
     P.fk_only = 1; P.env_ids = d_env_ids; P.N = d_env_ids ? n : s->N;
     if (P.N <= 0) return cudaSuccess;
     int blocks = (P.N + PH_WARPS - 1) / PH_WARPS;
-    physics_kernel<<<blocks, PH_WARPS * 32, 0, st>>>(P);
+    if (P.env_model) physics_kernel<true><<<blocks, PH_WARPS * 32, 0, st>>>(P);
+    else physics_kernel<false><<<blocks, PH_WARPS * 32, 0, st>>>(P);
     return cudaGetLastError();
 }
 
@@ -411,7 +414,8 @@ cudaError_t eml_reset_done(emloco_sim* s, const float* d_init_root, const float*
     PhysParams P; fill_params(s, P);
     P.fk_only = 1; P.reset_mask = s->reset; P.init_root = d_init_root; P.init_dof = d_init_dof;
     int blocks = (P.N + PH_WARPS - 1) / PH_WARPS;
-    physics_kernel<<<blocks, PH_WARPS * 32, 0, st>>>(P);
+    if (P.env_model) physics_kernel<true><<<blocks, PH_WARPS * 32, 0, st>>>(P);
+    else physics_kernel<false><<<blocks, PH_WARPS * 32, 0, st>>>(P);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     e = eml_launch_post_reset(s, s->traj_on, st);

@@ -69,6 +69,7 @@ __device__ __forceinline__ f4 qnormalize(f4 q) {
 
 struct PhysParams {
     const EmlModelDev* model;           // device copy of the model
+    const float* env_model;             // [EM_FLOATS][N] per-env body models or NULL
     const float* actions;               // [N,69] or NULL (then pd_target is used as is)
     float* pd_target;                   // [N,69]
     float* actions_copy;                // [N,69] or NULL
@@ -82,6 +83,24 @@ struct PhysParams {
     float gz, kn, cn, ct, mu, max_w, max_effort, max_turn;
     int fk_only;
     int epb;                            // lane-per-env kernel: envs per CTA (<= 32)
+};
+
+// Body-model access: the shared EmlModelDev, or (ENVM) the env's own arrays.  Compile-time switch: the shared-model kernels are
+// unchanged instruction for instruction.
+template <bool ENVM> struct ModelView {
+    const EmlModelDev& Mo; const float* em; size_t N; size_t env;
+    __device__ __forceinline__ float g(int off, int i) const { return __ldg(em + (size_t)(off + i) * N + env); }
+    __device__ __forceinline__ f3 offset(int b) const { return ENVM ? mk3(g(EM_OFFSET, 3 * b), g(EM_OFFSET, 3 * b + 1), g(EM_OFFSET, 3 * b + 2)) : mk3(Mo.offset[b][0], Mo.offset[b][1], Mo.offset[b][2]); }
+    __device__ __forceinline__ f3 com(int b) const { return ENVM ? mk3(g(EM_COM, 3 * b), g(EM_COM, 3 * b + 1), g(EM_COM, 3 * b + 2)) : mk3(Mo.com[b][0], Mo.com[b][1], Mo.com[b][2]); }
+    __device__ __forceinline__ f3 geom_a(int b) const { return ENVM ? mk3(g(EM_GA, 3 * b), g(EM_GA, 3 * b + 1), g(EM_GA, 3 * b + 2)) : mk3(Mo.geom_a[b][0], Mo.geom_a[b][1], Mo.geom_a[b][2]); }
+    __device__ __forceinline__ f3 geom_b(int b) const { return ENVM ? mk3(g(EM_GB, 3 * b), g(EM_GB, 3 * b + 1), g(EM_GB, 3 * b + 2)) : mk3(Mo.geom_b[b][0], Mo.geom_b[b][1], Mo.geom_b[b][2]); }
+    __device__ __forceinline__ float mass(int b) const { return ENVM ? g(EM_MASS, b) : Mo.mass[b]; }
+    __device__ __forceinline__ float inertia(int b, int k) const { return ENVM ? g(EM_INERTIA, 6 * b + k) : Mo.inertia[b][k]; }
+    __device__ __forceinline__ float kp(int b) const { return ENVM ? g(EM_KP, b) : Mo.kp[b]; }
+    __device__ __forceinline__ float kd(int b) const { return ENVM ? g(EM_KD, b) : Mo.kd[b]; }
+    __device__ __forceinline__ float arm(int b) const { return ENVM ? g(EM_ARM, b) : Mo.arm[b]; }
+    __device__ __forceinline__ float geom_r(int b) const { return ENVM ? g(EM_GR, b) : Mo.geom_r[b]; }
+    __device__ __forceinline__ float geom_bound(int b) const { return ENVM ? g(EM_BOUND, b) : Mo.geom_bound[b]; }
 };
 
 __device__ __forceinline__ float ground_height(const PhysParams& P, float x, float y) {

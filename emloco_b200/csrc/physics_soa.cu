@@ -229,6 +229,7 @@ __device__ __noinline__ void finish_body(float* smem, int lane, int b, f3& aw, f
     }
 }
 
+template <bool ENVM>
 __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams P) {
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -238,6 +239,7 @@ __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams 
     const bool env_ok = env_raw < P.N && lane < P.epb;
     const int env = env_ok ? env_raw : P.N - 1;                    // clamped: tail lanes recompute the last env, stores masked
     const EmlModelDev& Mo = *P.model;
+    const ModelView<ENVM> MV{Mo, P.env_model, (size_t)P.N, (size_t)env};
 
     // ---------------- load: root -> smem (warp 0), joints (bodies warp, warp+8, warp+16) -> smem, drive targets -> registers
     if (warp == 0) {
@@ -300,7 +302,7 @@ __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams 
             for (int i = -pre; i < clen; ++i) {
                 const int b = i < 0 ? 12 + i : c_chain_body[chain][i];
                 f3 cw, cl;
-                k = kin_step(k, mk3(Mo.offset[b][0], Mo.offset[b][1], Mo.offset[b][2]), ld4(smem, lane, b, F_JQ), ld3(smem, lane, b, F_JW), cw, cl);
+                k = kin_step(k, MV.offset(b), ld4(smem, lane, b, F_JQ), ld3(smem, lane, b, F_JW), cw, cl);
                 if (i >= 0) {
                     st3(smem, lane, b, F_X, k.x); st4(smem, lane, b, F_QW, k.q); st3(smem, lane, b, F_VW, k.w); st3(smem, lane, b, F_VL, k.l);
                     st3(smem, lane, b, F_C, cw); st3(smem, lane, b, F_C + 3, cl);
@@ -349,15 +351,14 @@ __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams 
             const int b = warp + SOA_WARPS * s;
             const f3 x = ld3(smem, lane, b, F_X), vw = ld3(smem, lane, b, F_VW), vl = ld3(smem, lane, b, F_VL);
             const M3 R = quat_to_mat(ld4(smem, lane, b, F_QW));
-            const float mass = Mo.mass[b];
+            const float mass = MV.mass(b);
             Sp sp;
             {
-                const float* I6 = Mo.inertia[b];
-                S3 Ib; Ib.xx = I6[0]; Ib.xy = I6[1]; Ib.xz = I6[2]; Ib.yy = I6[3]; Ib.yz = I6[4]; Ib.zz = I6[5];
+                S3 Ib; Ib.xx = MV.inertia(b, 0); Ib.xy = MV.inertia(b, 1); Ib.xz = MV.inertia(b, 2); Ib.yy = MV.inertia(b, 3); Ib.yz = MV.inertia(b, 4); Ib.zz = MV.inertia(b, 5);
                 M3 T;                                                    // T = R * Ib
 #pragma unroll
                 for (int r = 0; r < 3; ++r) setrow(T, r, sv(Ib, row(R, r)));
-                f3 c = x + mv(R, mk3(Mo.com[b][0], Mo.com[b][1], Mo.com[b][2]));
+                f3 c = x + mv(R, MV.com(b));
                 float c2 = dot3(c, c);
                 sp.A.xx = dot3(row(T, 0), row(R, 0)) + mass * (c2 - c.x * c.x);
                 sp.A.xy = dot3(row(T, 0), row(R, 1)) - mass * c.x * c.y;
@@ -380,14 +381,14 @@ __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams 
             float F0z = 0, Sbt = 0, Sbn = 0, Stz = 0, Sty = 0, Stx = 0, Sny = 0, Snx = 0;
             {
                 const int gt = Mo.geom_type[b];
-                const f3 ga = mk3(Mo.geom_a[b][0], Mo.geom_a[b][1], Mo.geom_a[b][2]);
-                const f3 gb = mk3(Mo.geom_b[b][0], Mo.geom_b[b][1], Mo.geom_b[b][2]);
-                const float drop = gt == 2 ? 0.f : Mo.geom_r[b];
+                const f3 ga = MV.geom_a(b);
+                const f3 gb = MV.geom_b(b);
+                const float drop = gt == 2 ? 0.f : MV.geom_r(b);
                 const int np = gt == 0 ? 1 : (gt == 1 ? 2 : 8);
                 const float bn = P.kn * dt + P.cn;
                 // no contact point of this body can be below the highest terrain sample: skip the loop when that holds for
                 // every env of the warp (same result: each point would find gap >= 0)
-                const bool reach = p0.z + x.z - Mo.geom_bound[b] < P.hf_max;
+                const bool reach = p0.z + x.z - MV.geom_bound(b) < P.hf_max;
                 const int npw = __any_sync(FULL, reach) ? np : 0;          // evaluated once, while the warp is converged
 #pragma unroll 1
                 for (int k = 0; k < npw; ++k) {
@@ -422,7 +423,7 @@ __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams 
             SM(b, F_CS + 5) = Stx; SM(b, F_CS + 6) = Sny; SM(b, F_CS + 7) = Snx;
             // ---- implicit PD drive ----
             if (b > 0) {
-                const float kp = Mo.kp[b], kd = Mo.kd[b];
+                const float kp = MV.kp(b), kd = MV.kd(b);
                 const f4 jq = ld4(smem, lane, b, F_JQ); const f3 jw = ld3(smem, lane, b, F_JW);
                 f3 e = log_quat(qmul(qconj(jq), qtgt[s]));              // position error on SO(3), child frame
                 float tm = fmaxf(fmaxf(fabsf(kp * e.x - kd * jw.x), fabsf(kp * e.y - kd * jw.y)), fabsf(kp * e.z - kd * jw.z));
@@ -445,7 +446,7 @@ __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams 
                 const int b = c_chain_body[chain][i];
                 Sp sp; ld_sp(smem, lane, b, sp);
                 if (i < clen - 1) add_sp(sp, carry);
-                aba_body(smem, lane, b, sp, Mo.arm[b]);
+                aba_body(smem, lane, b, sp, MV.arm(b));
                 carry = sp;
             }
             if (chain != 2) st_xchg(smem, lane, chain < 2 ? chain : chain - 1, carry);   // slots: 0,1 legs; 2,3 arms
@@ -459,7 +460,7 @@ __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams 
                 Sp sp; ld_sp(smem, lane, b, sp);
                 add_sp(sp, carry);
                 if (b == 11) { add_xchg(smem, lane, 2, sp); add_xchg(smem, lane, 3, sp); }
-                aba_body(smem, lane, b, sp, Mo.arm[b]);
+                aba_body(smem, lane, b, sp, MV.arm(b));
                 carry = sp;
             }
             Sp sp; ld_sp(smem, lane, 0, sp);
@@ -508,7 +509,7 @@ __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams 
             for (int b = 9; b <= 11; ++b) {
                 finish_body(smem, lane, b, aw, al, v0, st, df_row);
                 f3 cw, cl;
-                k = kin_step(k, mk3(Mo.offset[b][0], Mo.offset[b][1], Mo.offset[b][2]), ld4(smem, lane, b, F_JQ), ld3(smem, lane, b, F_JW), cw, cl);
+                k = kin_step(k, MV.offset(b), ld4(smem, lane, b, F_JQ), ld3(smem, lane, b, F_JW), cw, cl);
                 store_kin(smem, lane, b, k, cw, cl);
                 wm = fmaxf(wm, dot3(k.w, k.w));
             }
@@ -537,7 +538,7 @@ __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams 
                 const int b = c_chain_body[chain][i];
                 finish_body(smem, lane, b, aw, al, v0, st, df_row);
                 f3 cw, cl;                                                 // kinematics of the coming part
-                k = kin_step(k, mk3(Mo.offset[b][0], Mo.offset[b][1], Mo.offset[b][2]), ld4(smem, lane, b, F_JQ), ld3(smem, lane, b, F_JW), cw, cl);
+                k = kin_step(k, MV.offset(b), ld4(smem, lane, b, F_JQ), ld3(smem, lane, b, F_JW), cw, cl);
                 store_kin(smem, lane, b, k, cw, cl);
                 wm = fmaxf(wm, dot3(k.w, k.w));
             }
@@ -579,7 +580,7 @@ __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams 
         for (int i = -pre; i < clen; ++i) {
             const int b = i < 0 ? 12 + i : c_chain_body[chain][i];
             const f4 jq = ld4(smem, lane, b, F_JQ); const f3 jw = ld3(smem, lane, b, F_JW);
-            const f3 t = qrot(qw, mk3(Mo.offset[b][0], Mo.offset[b][1], Mo.offset[b][2]));
+            const f3 t = qrot(qw, MV.offset(b));
             lv = lv + cross3(wv, t);
             x = x + t;
             qw = qmul(qw, jq);
@@ -603,7 +604,8 @@ void eml_fill_phys_params(emloco_sim* s, PhysParams& P);
 cudaError_t eml_launch_physics_soa(emloco_sim* s, const float* d_actions, int n_substeps, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(physics_soa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SOA_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(physics_soa_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SOA_SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(physics_soa_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SOA_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr = true;
     }
@@ -617,6 +619,7 @@ cudaError_t eml_launch_physics_soa(emloco_sim* s, const float* d_actions, int n_
     if ((s->N + epb - 1) / epb > sms && epb < 32) epb = 32;      // more than one wave anyway: use full warps
     P.epb = epb;
     const int blocks = (s->N + epb - 1) / epb;
-    physics_soa_kernel<<<blocks, SOA_THREADS, SOA_SMEM_BYTES, st>>>(P);
+    if (P.env_model) physics_soa_kernel<true><<<blocks, SOA_THREADS, SOA_SMEM_BYTES, st>>>(P);        // per-env body models (row f3)
+    else physics_soa_kernel<false><<<blocks, SOA_THREADS, SOA_SMEM_BYTES, st>>>(P);
     return cudaGetLastError();
 }

@@ -28,11 +28,19 @@ struct EmlModelDev {
     int   max_level;
 };
 
+// Per-env body models (has_shape_variation - every env simulates the body generated from its own SMPL shape
+// parameters, humanoid.py:597-739; PD gains scaled by the body's mass, :905-910).  Optional device array [EM_FLOATS][N]
+// (field-major, env-minor: the lane-per-env physics kernel reads it coalesced); when absent all envs share EmlModelDev.
+// Topology, geometry TYPES and the action -> PD-target map are shape independent and stay in EmlModelDev.
+enum { EM_OFFSET = 0, EM_MASS = 72, EM_COM = 96, EM_INERTIA = 168, EM_KP = 312, EM_KD = 336, EM_ARM = 360, EM_GA = 384, EM_GB = 456,
+       EM_GR = 528, EM_BOUND = 552, EM_FLOATS = 576 };
+
 struct emloco_sim {
     emloco_cfg cfg;
     int N;
     int device;
     int physics_impl;       // 0: lane-per-env kernel (physics_soa.cu), 1: warp-per-env kernel (physics.cu)
+    float* env_model;       // [EM_FLOATS][N] per-env body models, or NULL (shared model)
     // --- state owned by the sim; addresses are stable for its lifetime (gymtorch.wrap_tensor aliases) ---
     float*   root_state;    // [N,13]   pos3 quat4 lin3 ang3
     float*   dof_state;     // [N*69,2] (exp-map pos, vel) interleaved

@@ -79,3 +79,49 @@ def rest_joint_positions(arrs):
     for i in range(1, NBn):
         x[i] = x[arrs["parent"][i]] + arrs["offset"][i]
     return x
+
+
+EM_FLOATS = 576
+
+
+def geom_bound(arrs):
+    """Largest distance from each body origin to one of its contact points, + the primitive's radius (the bound the physics
+    kernel uses to skip the contact loop of bodies that cannot reach the ground; same formula as emloco_create)."""
+    out = np.zeros(NB, np.float32)
+    for i in range(NB):
+        a, b, r, t = np.asarray(arrs["geom_a"][i], np.float64), np.asarray(arrs["geom_b"][i], np.float64), float(arrs["geom_r"][i]), int(arrs["geom_type"][i])
+        if t == 0:
+            ext = np.linalg.norm(a) + r
+        elif t == 1:
+            ext = max(np.linalg.norm(a), np.linalg.norm(b)) + r
+        else:
+            ext = np.linalg.norm(np.abs(a) + np.abs(b))
+        out[i] = ext * 1.0001 + 1e-5
+    return out
+
+
+def pack_env_model(arrs):
+    """One env's body model as the 576 floats of emloco_set_env_models (include/emloco.h)."""
+    f = lambda a: np.asarray(a, np.float32).reshape(-1)
+    v = np.concatenate([f(arrs["offset"]), f(arrs["mass"]), f(arrs["com"]), f(arrs["inertia6"]), f(arrs["kp_joint"]), f(arrs["kd_joint"]),
+                        f(arrs["arm_joint"]), f(arrs["geom_a"]), f(arrs["geom_b"]), f(arrs["geom_r"]), geom_bound(arrs)])
+    assert v.size == EM_FLOATS
+    return v
+
+
+def scaled_model_arrays(arrs, scale, default_mass=77.0):
+    """A body of the same proportions `scale` times as tall: lengths x s, masses x s^3, inertias x s^5, and the PD gains of the
+    reference's mass rule `stiffness *= humanoid_mass / 77 * kp_scale` (humanoid.py:905-910) re-applied to the new mass.
+    Stand-in for the per-beta bodies `Robot.load_from_skeleton` generates (uhc/smpllib/smpl_local_robot.py:1235 - needs the
+    licensed SMPL model files): exercises per-env models with physically consistent numbers."""
+    s = float(scale)
+    out = dict(arrs)
+    for k in ("offset", "com", "geom_a", "geom_b", "geom_r"):
+        out[k] = np.asarray(arrs[k], np.float64) * s
+    out["mass"] = np.asarray(arrs["mass"], np.float64) * s ** 3
+    out["inertia6"] = np.asarray(arrs["inertia6"], np.float64) * s ** 5
+    out["total_mass"] = float(arrs["total_mass"]) * s ** 3
+    gain = s ** 3                                               # (new mass / 77) / (old mass / 77)
+    for k in ("kp", "kd", "kp_joint", "kd_joint"):
+        out[k] = np.asarray(arrs[k], np.float64) * gain
+    return out

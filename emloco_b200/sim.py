@@ -85,6 +85,25 @@ class EmlocoSim:
             return t[name]
         raise AttributeError(name)
 
+    # -- per-env body models (has_shape_variation, humanoid.py:597-739,905-910) --------------
+    def set_env_models(self, models, shape_of_env=None, betas=None):
+        """models: list of model-array dicts (model.build_model_arrays / scaled_model_arrays ...), one per distinct shape;
+        shape_of_env: int array [N] (default env i -> shape i % len(models), the reference's assignment, humanoid.py:606).
+        betas: optional [num_shapes, 17] shape parameters copied into the `betas` observation tensor.  None restores the
+        shared model."""
+        if models is None:
+            _lib.check(self.lib.emloco_set_env_models(self._h, None), "emloco_set_env_models")
+            self._env_models = None
+            return
+        from .model import pack_env_model
+        packed = np.stack([pack_env_model(m) for m in models])
+        idx = np.arange(self.num_envs) % len(models) if shape_of_env is None else np.asarray(shape_of_env, np.int64)
+        per_env = np.ascontiguousarray(packed[idx], dtype=np.float32)
+        _lib.check(self.lib.emloco_set_env_models(self._h, per_env.ctypes.data_as(C.c_void_p)), "emloco_set_env_models")
+        self._env_models = (models, idx)
+        if betas is not None:
+            self.betas.copy_(torch.as_tensor(np.asarray(betas, np.float32)[idx]).to(self.betas.device))
+
     # -- terrain -----------------------------------------------------------------------------
     def set_height_field(self, samples):
         a = np.ascontiguousarray(samples, dtype=np.int16)

@@ -103,6 +103,17 @@ enum { EMLOCO_DTYPE_F32 = 0, EMLOCO_DTYPE_I64 = 1, EMLOCO_DTYPE_I16 = 2 };
  * (base_task.py:238, humanoid.py:643-946, base_task.py:128). */
 int emloco_create(const emloco_cfg* cfg, const emloco_model* model, emloco_sim** out);
 int emloco_destroy(emloco_sim* sim);
+
+/* Per-env body models (reference `has_shape_variation`, pacer/pacer/env/tasks/humanoid.py:597-739: every env
+ * simulates the body generated from its own SMPL shape parameters, with PD gains scaled by that body's mass, :905-910).
+ * h_env_models: HOST array [num_envs][576] fp32, per env the floats
+ *   offset[24][3] | mass[24] | com[24][3] | inertia[24][6] (xx xy xz yy yz zz about the COM) | kp[24] | kd[24] | armature[24]
+ *   (per joint, index = body, entry 0 unused) | geom_a[24][3] | geom_b[24][3] | geom_r[24] | geom_bound[24]
+ * (same meaning as the fields of emloco_model; geom_bound = largest distance from the body origin to a contact point).
+ * Topology, primitive types and the action -> PD-target map stay those of the emloco_model given to emloco_create.
+ * NULL restores the shared model.  Synchronises the device.  The shape parameters the observations carry (`betas` tensor) are
+ * set by the caller, like `humanoid_betas` in the reference. */
+int emloco_set_env_models(emloco_sim* sim, const float* h_env_models);
 void emloco_default_cfg(emloco_cfg* cfg);
 
 /* gym.acquire_*_tensor -> gymapi.Tensor{data_address, shape, dtype} (isaacgym/python/isaacgym/gymtorch.py:61-106).

@@ -158,3 +158,52 @@ def test_reset_indexed_only_touches_listed_envs():
     assert changed.tolist() == [i in (2, 5) for i in range(N)]
     assert abs(after[2, 0, 0].item() - 3.0) < 1e-6
     sim.close()
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+def test_per_env_body_models_match_fp64_oracle_per_shape(impl):
+    """SURVEY 8 row f3 (has_shape_variation): three body models (0.88x, 1x, 1.15x: lengths, masses, inertias, mass-scaled PD
+    gains) assigned env i -> shape i % 3 as the reference does (humanoid.py:606); every env must step like the fp64 oracle
+    run with ITS shape's model - in the air and in contact - and differently from the shared-model step.  Switching the per-env
+    models off restores the shared-model result bit for bit."""
+    from emloco_b200.model import rest_root_height, scaled_model_arrays
+    from emloco_b200.sim import EmlocoSim
+    A, M0, PO, h0 = _setup()
+    shapes = [scaled_model_arrays(A, s) for s in (0.88, 1.0, 1.15)]
+    oracles = [PO.make_model(S["parent"], S["offset"], S["mass"], S["com"], S["inertia6"], S["kp_joint"], S["kd_joint"], S["arm_joint"],
+                             S["geom_type"], S["geom_a"], S["geom_b"], S["geom_r"]) for S in shapes]
+    N = 250
+    for case, z_lo, z_hi in (("airborne", 2.0, 3.0), ("contact", 0.72, 1.02)):
+        root, dof_pos, dof_vel, actions = _random_state(N, 21 if case == "airborne" else 22, z_lo, z_hi)
+        sim = EmlocoSim(N, physics_impl=impl)
+        betas = np.concatenate([np.zeros((3, 1)), np.linspace(-1, 1, 3)[:, None] * np.ones((3, 16))], 1)
+        sim.set_env_models(shapes, betas=betas)
+        idx = np.arange(N) % 3
+
+        def run():
+            sim.root_state.copy_(torch.from_numpy(root).float().cuda())
+            sim.dof_state.copy_(torch.from_numpy(np.stack([dof_pos, dof_vel], -1).reshape(N * 69, 2)).float().cuda())
+            sim.reset_indexed(None)
+            sim.step(torch.from_numpy(actions).float().cuda().contiguous())
+            torch.cuda.synchronize()
+            return {k: v.cpu().numpy().astype(np.float64) for k, v in dict(root=sim.root_state, rb=sim.rb_state.reshape(N, 24, 13),
+                    dof=sim.dof_state.reshape(N, 69, 2), contact=sim.contact.reshape(N, 24, 3), obs=sim.obs).items()}
+        g = run()
+        for k in range(3):
+            sel = idx == k
+            o = _oracle_step(shapes[k], oracles[k], PO, root[sel], dof_pos[sel], dof_vel[sel], actions[sel])
+            np.testing.assert_allclose(g["root"][sel], o["root"], rtol=1e-3, atol=2e-3, err_msg=f"{case} shape {k}")
+            np.testing.assert_allclose(g["rb"][sel], o["rb"], rtol=1e-3, atol=5e-3, err_msg=f"{case} shape {k}")
+            np.testing.assert_allclose(g["dof"][sel], o["dof"], rtol=1e-3, atol=5e-3, err_msg=f"{case} shape {k}")
+            np.testing.assert_allclose(g["contact"][sel], o["contact"], rtol=5e-3, atol=2.0, err_msg=f"{case} shape {k}")
+            np.testing.assert_allclose(g["obs"][sel, 357:368], np.broadcast_to(betas[k, :11], (sel.sum(), 11)), atol=1e-6)   # shape obs
+        # the shapes matter: envs of shape 0 / 2 deviate from what the shared model gives, shape 1 does not
+        sim.set_env_models(None)
+        shared = run()
+        assert np.abs(shared["rb"][idx == 0] - g["rb"][idx == 0]).max() > 1e-2
+        np.testing.assert_array_equal(shared["rb"][idx == 1], g["rb"][idx == 1])
+        ref = _gpu_step(N, root, dof_pos, dof_vel, actions, impl=impl)
+        np.testing.assert_array_equal(shared["rb"], ref["rb"])
+        if case == "contact":
+            assert (np.abs(g["contact"]).sum(axis=(1, 2)) > 0).mean() > 0.3
+        sim.close()
