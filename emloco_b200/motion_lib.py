@@ -59,6 +59,8 @@ class MotionLibSMPL:
 
     # ---- sampling (motion_lib_smpl.py:390-407) ----
     def sample_motions(self, n):
+        if int(n) <= 0:
+            return torch.zeros(0, dtype=torch.int32, device=self.device)
         return torch.multinomial(self._prob, num_samples=int(n), replacement=True, generator=self.gen).to(torch.int32)
 
     def sample_time(self, motion_ids, truncate_time=None):
