@@ -83,8 +83,9 @@ class MotionLibSMPL:
         dof = f(n, 69, 2) if dof_out is None else dof_out
         assert root.is_contiguous() and dof.is_contiguous() and root.numel() == n * 13 and dof.numel() == n * 138
         key, rb = f(n, 4, 3), (f(n, 24, 13) if full else None)
-        _lib.check(_lib.load().emloco_motion_state(C.byref(self._L), _ptr(ids), _ptr(times), n, _ptr(root), _ptr(dof), _ptr(key), _ptr(rb),
-                                                   _stream()), "emloco_motion_state")
+        if n:
+            _lib.check(_lib.load().emloco_motion_state(C.byref(self._L), _ptr(ids), _ptr(times), n, _ptr(root), _ptr(dof), _ptr(key), _ptr(rb),
+                                                       _stream()), "emloco_motion_state")
         out = dict(root_state=root, dof_state=dof, key_pos=key)
         if full:
             out["rb_state"] = rb
@@ -95,6 +96,8 @@ class MotionLibSMPL:
         ids = self.sample_motions(num_samples) if motion_ids is None else motion_ids.to(self.device, torch.int32).contiguous()
         t0 = self.sample_time(ids) if motion_times0 is None else motion_times0.to(self.device, torch.float32).contiguous()
         out = torch.empty(ids.numel(), num_steps * AMP_STEP_DIM, device=self.device, dtype=torch.float32)
+        if ids.numel() == 0:
+            return out
         _lib.check(_lib.load().emloco_amp_obs_demo(C.byref(self._L), _ptr(ids), _ptr(t0), ids.numel(), num_steps, float(dt), _ptr(out), _stream()),
                    "emloco_amp_obs_demo")
         return out
