@@ -700,12 +700,7 @@ cudaError_t eml_linear_bf16x3(const void* a_hi, const void* a_lo, long long lda,
         return tc::launch_2cta<128>((const __nv_bfloat16*)a_hi, (const __nv_bfloat16*)a_lo, lda, (const __nv_bfloat16*)w_hi,
                                     (const __nv_bfloat16*)w_lo, ldw, g, st);
     }
-    // Tile choice by waves: measured on the rollout's layers, a 128 x 256 tile costs ~1.9x a 128 x 128 tile (both are bound by
-    // the MMA rate), so what decides is how the tile count quantises onto the SMs - e.g. the stacked actor / critic first layer
-    // (4096 x 4096 x 624): 1024 narrow tiles = 7 waves (61 us) against 512 wide tiles = 4 waves of double cost (69 us)
-    const long long tiles128 = ((M + tc::BM - 1) / tc::BM) * ((N + 127) / 128);
-    const long long waves128 = (tiles128 + sms - 1) / sms, waves256 = (tiles256 + sms - 1) / sms;
-    const bool wide = tile_n == 256 || (tile_n == 0 && N >= 256 && waves256 * 19 < waves128 * 10);
+    const bool wide = tile_n == 256 || (tile_n == 0 && N >= 256 && tiles256 * 8 >= (long long)sms * 7);
     if (wide)
         return tc::launch<256>((const __nv_bfloat16*)a_hi, (const __nv_bfloat16*)a_lo, lda, (const __nv_bfloat16*)w_hi,
                                (const __nv_bfloat16*)w_lo, ldw, g, st);
