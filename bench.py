@@ -513,12 +513,14 @@ def run_ours(args):
                             "frac counts algorithmic FLOPs once, so its ceiling is 1/3; MMA-issue rate = 3 x achieved")
 
         # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ----
-        cores = os.cpu_count() or 1
+        cores = host_cores()
         cpu = None
         if not args.no_cpu_baseline and world == 1:     # reported at N = 1 only
-            rate, done, dt = cpu_rollout_rate(256, 1000, 2, seed=args.seed, budget_s=15.0)
+            from oracle import oracle_np as O
+            O.set_linear_backend("torch", cores)        # dense layers through torch's CPU sgemm, like the --impl reference arm
+            rate, done, dt = cpu_rollout_rate(1024, 1000, 2, seed=args.seed, budget_s=15.0)
             cpu = {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                   "sample": f"256 of {N} envs per step, {done} steps in {dt:.1f} s (fp64 C physics oracle with OpenMP + numpy nets / post-step / LocoVal scoring / post-horizon pass)"}
+                   "sample": f"1024 of {N} envs per step, {done} steps in {dt:.1f} s (fp64 C physics oracle with OpenMP, torch CPU sgemm nets, numpy post-step / LocoVal scoring / post-horizon pass); the --impl reference arm runs all {N} envs"}
 
         out = {
             "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K_req, "steps_timed": K, "warmup": W,

@@ -53,12 +53,14 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 
 def full(tag, rep):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """rep: a .ncu-rep file, or the CSV that `ncu -i rep --page raw --csv` wrote on the GPU box."""
+    raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     idx = {w: hdr.index(w) for w in WANT if w in hdr}
     kn = hdr.index("Kernel Name")
     best = {}
+    gs = hdr.index("Grid Size") if "Grid Size" in hdr else None
     for r in rows[2:]:
         name = r[kn].split("(")[0][:60]
         d = float(r[idx["gpu__time_duration.sum"]].replace(",", ""))
