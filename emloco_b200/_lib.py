@@ -19,7 +19,7 @@ SYMBOLS = [
     "emloco_disc_reward", "emloco_rollout_record", "emloco_normalize", "emloco_physics_step", "emloco_split_bf16",
     "emloco_linear_bf16x3", "emloco_set_post_sinks", "emloco_linear_bf16x3_rows", "emloco_timeout_gather",
     "emloco_rollout_record_deferred", "emloco_fill_next_values", "emloco_traj_reset", "emloco_set_traj_reset", "emloco_locoval_backward_pose", "emloco_locoval_train_step", "emloco_locoval_train_workspace_bytes", "emloco_linear_bf16x3_head", "emloco_sample_actions_parts", "emloco_linear", "emloco_xform", "emloco_ppo_heads", "emloco_disc_heads", "emloco_amp_dropout_mask",
-    "emloco_rms_update", "emloco_adam_begin", "emloco_grad_sumsq", "emloco_adam_clip", "emloco_axpy", "emloco_sum_parts", "emloco_player_record", "emloco_motion_state", "emloco_amp_obs_demo", "emloco_set_env_models", "emloco_sync", "emloco_last_error", "emloco_version",
+    "emloco_rms_update", "emloco_adam_begin", "emloco_grad_sumsq", "emloco_adam_clip", "emloco_axpy", "emloco_sum_parts", "emloco_player_record", "emloco_dp_reduce_shard", "emloco_dp_adam_shard", "emloco_motion_state", "emloco_amp_obs_demo", "emloco_set_env_models", "emloco_sync", "emloco_last_error", "emloco_version",
 ]
 
 
@@ -143,6 +143,8 @@ def load():
     lib.emloco_adam_clip.argtypes = [vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, f32, f32, vp]
     lib.emloco_axpy.argtypes = [vp, vp, f32, i64, vp]
     lib.emloco_sum_parts.argtypes = [vp, i32, i64, vp, i64, i32, vp]
+    lib.emloco_dp_reduce_shard.argtypes = [vp, vp, i64, i64, vp, vp, i32, vp]
+    lib.emloco_dp_adam_shard.argtypes = [vp, vp, vp, vp, vp, i64, i64, vp, i32, vp, f32, f32, f32, f32, f32, f32, vp]
     lib.emloco_player_record.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, i32, i32, f32, f32, f32, i32, f32, f32, vp]
     lib.emloco_motion_state.argtypes = [C.POINTER(MotionLib), vp, vp, i64, vp, vp, vp, vp, vp]
     lib.emloco_amp_obs_demo.argtypes = [C.POINTER(MotionLib), vp, vp, i64, i32, f32, vp, vp]
@@ -164,7 +166,7 @@ LAUNCHES = {"emloco_step": 2, "emloco_physics_step": 1, "emloco_post_step": 1, "
             "emloco_locoval_forward_host": 1, "emloco_split_bf16": 1, "emloco_linear_bf16x3": 1, "emloco_linear_bf16x3_rows": 1, "emloco_linear_bf16x3_head": 2,
             "emloco_timeout_gather": 1, "emloco_rollout_record_deferred": 1, "emloco_fill_next_values": 1,
             "emloco_xform": 1, "emloco_ppo_heads": 1, "emloco_disc_heads": 1, "emloco_amp_dropout_mask": 1, "emloco_rms_update": 2,
-            "emloco_adam_begin": 1, "emloco_grad_sumsq": 2, "emloco_adam_clip": 1, "emloco_axpy": 1, "emloco_sum_parts": 1, "emloco_player_record": 1, "emloco_motion_state": 1, "emloco_amp_obs_demo": 1}
+            "emloco_adam_begin": 1, "emloco_grad_sumsq": 2, "emloco_adam_clip": 1, "emloco_axpy": 1, "emloco_sum_parts": 1, "emloco_player_record": 1, "emloco_dp_reduce_shard": 2, "emloco_dp_adam_shard": 1, "emloco_motion_state": 1, "emloco_amp_obs_demo": 1}
 launch_count = 0
 mac_count = 0          # multiply-accumulates of the dense-layer launches (M * N * K each), for the benches' FLOP figures
 

@@ -36,6 +36,11 @@ cudaError_t eml_grad_sumsq(const float* g, long long n, float* state, float* par
 cudaError_t eml_adam_clip(float* p, const float* g, float* m, float* v, long long n, float* state, float lr, float beta1, float beta2,
                           float eps, float max_norm, float grad_scale, cudaStream_t st);
 cudaError_t eml_adam_begin(float* state, cudaStream_t st);
+cudaError_t eml_dp_reduce_shard(const float* mc_grad, float* shard, long long lo, long long count, float* partials, float* mc_exchange,
+                                int rank, cudaStream_t st);
+cudaError_t eml_dp_adam_shard(float* mc_param, const float* p_local, const float* shard, float* m, float* v, long long lo, long long count,
+                              const float* exchange, int world, float* state, float lr, float beta1, float beta2, float eps, float max_norm,
+                              float grad_scale, cudaStream_t st);
 cudaError_t eml_axpy(float* y, const float* x, float a, long long n, cudaStream_t st);
 cudaError_t eml_sum_parts(const float* parts, int S, long long stride, float* out, long long n, int accumulate, cudaStream_t st);
 
@@ -737,6 +742,24 @@ int emloco_adam_clip(float* d_param, const float* d_grad, float* d_m, float* d_v
                      float beta2, float eps, float max_norm, float grad_scale, void* stream) {
     if (!d_param || !d_grad || !d_m || !d_v || !d_state || n < 0) return fail(EMLOCO_EINVAL, "emloco_adam_clip: bad argument");
     CK(eml_adam_clip(d_param, d_grad, d_m, d_v, n, d_state, lr, beta1, beta2, eps, max_norm, grad_scale, (cudaStream_t)stream), "adam");
+    return EMLOCO_OK;
+}
+
+int emloco_dp_reduce_shard(const float* mc_grad, float* d_shard_grad, int64_t lo, int64_t count, float* d_partials, float* mc_exchange,
+                           int32_t rank, void* stream) {
+    if (!mc_grad || !d_shard_grad || !d_partials || !mc_exchange || lo < 0 || count < 0 || (lo & 3) || (count & 3) || rank < 0)
+        return fail(EMLOCO_EINVAL, "emloco_dp_reduce_shard: bad argument (slices are multiples of 4 floats)");
+    CK(eml_dp_reduce_shard(mc_grad, d_shard_grad, lo, count, d_partials, mc_exchange, rank, (cudaStream_t)stream), "dp reduce shard");
+    return EMLOCO_OK;
+}
+int emloco_dp_adam_shard(float* mc_param, const float* d_param_local, const float* d_shard_grad, float* d_m, float* d_v, int64_t lo, int64_t count,
+                         const float* d_exchange_local, int32_t world, float* d_state, float lr, float beta1, float beta2, float eps,
+                         float max_norm, float grad_scale, void* stream) {
+    if (!mc_param || !d_param_local || !d_shard_grad || !d_m || !d_v || !d_exchange_local || !d_state || lo < 0 || count < 0 || (lo & 3) ||
+        (count & 3) || world < 1)
+        return fail(EMLOCO_EINVAL, "emloco_dp_adam_shard: bad argument");
+    CK(eml_dp_adam_shard(mc_param, d_param_local, d_shard_grad, d_m, d_v, lo, count, d_exchange_local, world, d_state, lr, beta1, beta2, eps,
+                         max_norm, grad_scale, (cudaStream_t)stream), "dp adam shard");
     return EMLOCO_OK;
 }
 

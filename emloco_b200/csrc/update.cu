@@ -436,6 +436,81 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(float* __restrict__ p, c
 
 __global__ void bump_step_kernel(float* state) { state[0] += 1.0f; state[1] = 0.f; }
 
+// ---- data-parallel optimiser step fused with its collective over NVLink / NVSwitch multicast memory (NVLS) --------------------
+// The flat gradient and parameter buffers of all ranks are mapped behind ONE multicast address each (torch symmetric memory).
+// Rank r owns the slice [lo, lo + count) of the flat vector:
+//   dp_reduce_shard   multimem.ld_reduce: the switch adds the W ranks' gradients of the slice (one load per 16 bytes, no
+//                     reduce-scatter round trips); the slice's sum of squares goes, by multimem.st, into slot r of every
+//                     rank's exchange buffer
+//   dp_adam_shard     every rank adds the W slots in rank order (same bits everywhere), clips, runs Adam on ITS slice only
+//                     (moments are sharded: 1/W of the optimiser state per rank) and broadcasts the new parameters with
+//                     multimem.st - the all-gather happens inside the store
+// Replaces: NCCL all-reduce (44.8 MB) + norm + Adam over the whole vector on every rank.  Cross-rank ordering: symmetric-memory
+// barriers issued on the stream around the two kernels (update.py).
+__device__ __forceinline__ float4 mm_ld_reduce_f4(const float* mc) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mm_st_f4(float* mc, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__global__ void __launch_bounds__(256) dp_reduce_shard_kernel(const float* __restrict__ mc_grad, float* __restrict__ shard, long long lo,
+                                                              long long count4, float* __restrict__ partials) {
+    __shared__ float red[8];
+    float a = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = mm_ld_reduce_f4(mc_grad + lo + 4 * i);
+        reinterpret_cast<float4*>(shard)[i] = v;
+        a += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    a = warp_sum(a);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) { float s = 0.f; for (int w = 0; w < 8; ++w) s += red[w]; partials[blockIdx.x] = s; }
+}
+__global__ void __launch_bounds__(256) dp_publish_sumsq_kernel(const float* __restrict__ partials, int count, float* __restrict__ mc_exchange, int rank) {
+    __shared__ float red[256];
+    float a = 0.f;
+    for (int i = threadIdx.x; i < count; i += 256) a += partials[i];
+    red[threadIdx.x] = a;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) { mm_st_f4(mc_exchange + 4 * rank, make_float4(red[0], 0.f, 0.f, 0.f)); __threadfence_system(); }
+}
+__global__ void __launch_bounds__(256) dp_adam_shard_kernel(float* __restrict__ mc_param, const float* __restrict__ p_local,
+                                                            const float* __restrict__ shard, float* __restrict__ m, float* __restrict__ v,
+                                                            long long lo, long long count4, const float* __restrict__ exchange, int world,
+                                                            float* __restrict__ state, float lr, float beta1, float beta2, float eps,
+                                                            float max_norm, float grad_scale) {
+    float total = 0.f;
+    for (int r = 0; r < world; ++r) total += exchange[4 * r];                    // rank order: identical bits on every rank
+    const float t = state[0];
+    float coef = grad_scale;
+    if (max_norm > 0.f) coef *= fminf(max_norm / (sqrtf(total) * grad_scale + 1e-6f), 1.0f);
+    const float bc1 = 1.0f - powf(beta1, t), bc2 = 1.0f - powf(beta2, t);
+    const float step_size = lr / bc1, rs_bc2 = rsqrtf(bc2);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 g4 = reinterpret_cast<const float4*>(shard)[i];
+        float4 m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
+        float4 p4 = *reinterpret_cast<const float4*>(p_local + lo + 4 * i);
+        const float g[4] = {g4.x * coef, g4.y * coef, g4.z * coef, g4.w * coef};
+        float* mm = &m4.x; float* vv = &v4.x; float* pp = &p4.x;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            mm[q] = beta1 * mm[q] + (1.0f - beta1) * g[q];
+            vv[q] = beta2 * vv[q] + (1.0f - beta2) * g[q] * g[q];
+            pp[q] -= step_size * mm[q] / (sqrtf(vv[q]) * rs_bc2 + eps);
+        }
+        reinterpret_cast<float4*>(m)[i] = m4; reinterpret_cast<float4*>(v)[i] = v4;
+        mm_st_f4(mc_param + lo + 4 * i, p4);                                      // lands in every rank's parameter buffer
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) state[1] = total;
+    __threadfence_system();
+}
+
 // out[i] = sum_s parts[s * stride + i] (+ out[i] when accumulate): the partial matrices of a split-K GEMM, added in split order
 __global__ void sum_parts_kernel(const float* __restrict__ parts, int S, long long stride, float* __restrict__ out, long long n, int accumulate) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -526,6 +601,26 @@ cudaError_t eml_adam_clip(float* p, const float* g, float* m, float* v, long lon
     if (n <= 0) return cudaSuccess;
     long long blocks = (n + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
     adam_clip_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, n, state, lr, beta1, beta2, eps, max_norm, grad_scale);
+    return cudaGetLastError();
+}
+
+cudaError_t eml_dp_reduce_shard(const float* mc_grad, float* shard, long long lo, long long count, float* partials, float* mc_exchange,
+                                int rank, cudaStream_t st) {
+    if (count <= 0) return cudaSuccess;
+    const long long c4 = count / 4;
+    long long blocks = (c4 + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8; if (blocks < 1) blocks = 1;
+    dp_reduce_shard_kernel<<<(unsigned)blocks, 256, 0, st>>>(mc_grad, shard, lo, c4, partials);
+    dp_publish_sumsq_kernel<<<1, 256, 0, st>>>(partials, (int)blocks, mc_exchange, rank);
+    return cudaGetLastError();
+}
+cudaError_t eml_dp_adam_shard(float* mc_param, const float* p_local, const float* shard, float* m, float* v, long long lo, long long count,
+                              const float* exchange, int world, float* state, float lr, float beta1, float beta2, float eps, float max_norm,
+                              float grad_scale, cudaStream_t st) {
+    if (count <= 0) return cudaSuccess;
+    const long long c4 = count / 4;
+    long long blocks = (c4 + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8; if (blocks < 1) blocks = 1;
+    dp_adam_shard_kernel<<<(unsigned)blocks, 256, 0, st>>>(mc_param, p_local, shard, m, v, lo, c4, exchange, world, state, lr, beta1, beta2, eps,
+                                                          max_norm, grad_scale);
     return cudaGetLastError();
 }
 

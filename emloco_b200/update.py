@@ -75,7 +75,7 @@ class FlatParams:
             "_task_mlp.0.bias", "_task_mlp.2.bias", "_disc_mlp.0.bias", "_disc_mlp.2.bias", "_disc_logits.weight", "_disc_logits.bias",
             "_task_value_mlp.0.bias", "_task_value_mlp.2.bias", "_value_logits.weight", "_value_logits.bias")
 
-    def __init__(self, net: AMPSeptValueNetwork):
+    def __init__(self, net: AMPSeptValueNetwork, symmetric=False):
         named = dict(net.named_parameters())
         assert set(self.GEMM) | set(self.TAIL) | {"sigma"} == set(named), sorted(set(named) ^ (set(self.GEMM) | set(self.TAIL) | {"sigma"}))
         dev = named["mu.weight"].device
@@ -90,7 +90,14 @@ class FlatParams:
         self.n = n
         self.bucket0 = self.off["actor_mlp.0.weight"]                      # [0, bucket0): discriminator weights
         z = lambda: torch.zeros(n, device=dev, dtype=torch.float32)
-        self.p, self.g, self.m, self.v = z(), z(), z(), z()
+        if symmetric:
+            # parameters and gradients in symmetric memory: every rank maps every rank's buffers (and one multicast address for
+            # all of them) - the fused optimiser step of `NvlsShardedAdam` reads / writes them through the NVSwitch
+            import torch.distributed._symmetric_memory as symm
+            self.p, self.g = (symm.empty(n, dtype=torch.float32, device=dev).zero_() for _ in range(2))
+            self.m = self.v = None                                         # moments are sharded (NvlsShardedAdam)
+        else:
+            self.p, self.g, self.m, self.v = z(), z(), z(), z()
         self.state = torch.zeros(2, device=dev, dtype=torch.float32)      # Adam step count, sum of squares of the gradient
         self.partials = torch.zeros(148 * 8, device=dev, dtype=torch.float32)
         for k in self.GEMM + self.TAIL:
@@ -120,17 +127,70 @@ class FlatParams:
         self.g[self.tail_start:].zero_()
 
 
+class NvlsShardedAdam:
+    """The data-parallel optimiser step fused with its collective over NVLink / NVSwitch multicast memory
+    (`emloco_dp_reduce_shard` + `emloco_dp_adam_shard`, csrc/update.cu): rank r reduces ITS 1/W slice of the flat gradient inside
+    the switch (`multimem.ld_reduce`), the slices' sums of squares are exchanged through a W-slot multicast buffer, the rank
+    clips and runs Adam on its slice with its shard of the moments, and broadcasts the new parameters to every rank
+    (`multimem.st`).  Three stream-ordered symmetric-memory barriers order the ranks; no NCCL call, no host synchronisation.
+    Every rank ends up with bit-identical parameters (each element is reduced and updated exactly once, by its owner)."""
+
+    def __init__(self, flat: "FlatParams", group=None):
+        import torch.distributed._symmetric_memory as symm
+        group = dist.group.WORLD if group is None else group
+        self.flat, self.world, self.rank = flat, dist.get_world_size(group), dist.get_rank(group)
+        dev = flat.p.device
+        self.hg, self.hp = symm.rendezvous(flat.g, group), symm.rendezvous(flat.p, group)
+        self.x = symm.empty(4 * self.world, dtype=torch.float32, device=dev).zero_()
+        self.hx = symm.rendezvous(self.x, group)
+        if not (self.hg.multicast_ptr and self.hp.multicast_ptr and self.hx.multicast_ptr):
+            raise _lib.EmlocoError("NvlsShardedAdam needs NVSwitch multicast (NVLS) support; use reducer='nccl'")
+        per = -(-flat.n // (4 * self.world)) * 4
+        self.lo = min(self.rank * per, flat.n)
+        self.count = max(0, min(flat.n, self.lo + per) - self.lo)
+        z = lambda: torch.zeros(max(self.count, 4), device=dev, dtype=torch.float32)
+        self.shard, self.m, self.v = z(), z(), z()
+        self.hg.barrier(channel=0)
+
+    def step(self, lr, beta1, beta2, eps, max_norm):
+        FP, lib = self.flat, _lib.load()
+        p = lambda a: C.c_void_p(int(a))
+        self.hg.barrier(channel=0)                                        # every rank's backward pass has been issued and finished
+        _lib.check(lib.emloco_dp_reduce_shard(p(self.hg.multicast_ptr), _ptr(self.shard), self.lo, self.count, _ptr(FP.partials),
+                                              p(self.hx.multicast_ptr), self.rank, _stream()), "emloco_dp_reduce_shard")
+        self.hg.barrier(channel=1)                                        # all slices reduced (gradients may be overwritten), all slots published
+        _lib.check(lib.emloco_dp_adam_shard(p(self.hp.multicast_ptr), _ptr(FP.p), _ptr(self.shard), _ptr(self.m), _ptr(self.v), self.lo, self.count,
+                                            _ptr(self.x), self.world, _ptr(FP.state), lr, beta1, beta2, eps, max_norm, 1.0 / self.world, _stream()),
+                   "emloco_dp_adam_shard")
+        self.hg.barrier(channel=2)                                        # every rank's parameter buffer holds all slices
+
+
 class PPOUpdate:
-    """One optimiser step per `step(batch)` for fixed minibatch sizes B (policy rows) and Ba (AMP rows per source)."""
+    """One optimiser step per `step(batch)` for fixed minibatch sizes B (policy rows) and Ba (AMP rows per source).
+    reducer: how the ranks' gradients meet - "nccl" (bucketed all-reduce, then norm + Adam on every rank), "nvls" (the fused
+    NVSwitch-multicast step of `NvlsShardedAdam`) or "auto" (nvls on more than one rank when multicast is available)."""
 
     def __init__(self, net: AMPSeptValueNetwork, obs_norm: RunningMeanStd, amp_norm: RunningMeanStd, B, Ba, cfg=None, world=None,
-                 overlap_allreduce=True):
+                 overlap_allreduce=True, reducer="auto"):
         self.cfg = dict(DEFAULT_CFG, **(cfg or {}))
         self.net, self.obs_norm, self.amp_norm, self.B, self.Ba = net, obs_norm, amp_norm, int(B), int(Ba)
-        self.flat = FlatParams(net)
+        self.world = (dist.get_world_size() if dist.is_initialized() else 1) if world is None else int(world)
+        assert reducer in ("auto", "nccl", "nvls")
+        use_nvls = self.world > 1 and reducer in ("auto", "nvls") and dist.is_initialized() and dist.get_backend() == "nccl"
+        self.nvls = None
+        if use_nvls:
+            try:
+                self.flat = FlatParams(net, symmetric=True)
+                self.nvls = NvlsShardedAdam(self.flat)
+            except Exception:
+                if reducer == "nvls":
+                    raise
+                self.flat, self.nvls = None, None
+        if self.nvls is None:
+            self.flat = FlatParams(net)
+        self.reducer_name = "nvls" if self.nvls is not None else ("nccl" if self.world > 1 else "none")
         dev = self.flat.p.device
         self.dev = dev
-        self.world = (dist.get_world_size() if dist.is_initialized() else 1) if world is None else int(world)
         self.overlap = bool(overlap_allreduce)
         f = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
         S = lambda rows, k: _Split(rows, k, dev)
@@ -333,7 +393,8 @@ class PPOUpdate:
         self._axpy(G("_disc_mlp.2.weight"), n._disc_mlp[2].weight, 2.0 * dc * cfg["disc_weight_decay"])
         # the discriminator's weight gradients (33 % of all parameters) are final: their all-reduce runs under the actor /
         # critic backward that follows
-        self.reducer.start_first()
+        if self.nvls is None:
+            self.reducer.start_first()
 
         # ---- backward, actor / critic / task trunk ----
         xform(x=self.dmu32, split=self.s_dmu, splitT=self.dmuT, colsum=G("mu.bias"))
@@ -369,6 +430,10 @@ class PPOUpdate:
     def reduce_and_apply(self):
         """Gradient average over ranks (one all-reduce of the flat buffer), clip-norm, Adam, fresh operand splits."""
         FP, cfg, lib = self.flat, self.cfg, _lib.load()
+        if self.nvls is not None:                                      # collective and optimiser in one pass over NVLink multicast memory
+            self.nvls.step(cfg["lr"], 0.9, 0.999, 1e-8, cfg["grad_norm"])
+            self.refresh_weights()
+            return
         self.reducer.finish()                                          # summed; the 1 / world factor is folded into the Adam kernel
         _lib.check(lib.emloco_grad_sumsq(_ptr(FP.g), FP.n, _ptr(FP.state), _ptr(FP.partials), _stream()), "emloco_grad_sumsq")
         _lib.check(lib.emloco_adam_clip(_ptr(FP.p), _ptr(FP.g), _ptr(FP.m), _ptr(FP.v), FP.n, _ptr(FP.state), cfg["lr"], 0.9, 0.999, 1e-8,

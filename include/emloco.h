@@ -477,6 +477,21 @@ int emloco_adam_begin(float* d_state, void* stream);
 int emloco_grad_sumsq(const float* d_grad, int64_t n, float* d_state, float* d_partials, void* stream);
 int emloco_adam_clip(float* d_param, const float* d_grad, float* d_m, float* d_v, int64_t n, float* d_state, float lr, float beta1,
                      float beta2, float eps, float max_norm, float grad_scale, void* stream);
+/* The optimiser step FUSED WITH ITS COLLECTIVE over NVLink / NVSwitch multicast memory (replaces all-reduce + norm + Adam on every
+ * rank; reference: Horovod `optimizer.synchronize()` + clip_grad_norm_ + Adam, amp_continuous_value.py:381-398).  mc_* are
+ * MULTICAST addresses of buffers every rank allocated symmetrically (flat gradient, flat parameters, exchange [world x 4] floats);
+ * rank r owns the slice [lo, lo + count) of the flat vector (multiples of 4 floats).
+ * emloco_dp_reduce_shard: `multimem.ld_reduce` adds the ranks' gradients of the slice inside the switch -> d_shard_grad [count];
+ *   the slice's sum of squares is broadcast (`multimem.st`) into slot `rank` of every rank's exchange buffer.
+ * emloco_dp_adam_shard: sums the `world` exchange slots in rank order, clips (max_norm on the gradient scaled by grad_scale =
+ *   1 / world), runs Adam on the slice with THIS rank's moments d_m / d_v [count] (optimiser state sharded over ranks) and
+ *   broadcasts the new parameters into every rank's parameter buffer (`multimem.st`).  d_state = {step, total sum of squares}.
+ * The caller orders the ranks with symmetric-memory barriers before, between and after the two calls. */
+int emloco_dp_reduce_shard(const float* mc_grad, float* d_shard_grad, int64_t lo, int64_t count, float* d_partials, float* mc_exchange,
+                           int32_t rank, void* stream);
+int emloco_dp_adam_shard(float* mc_param, const float* d_param_local, const float* d_shard_grad, float* d_m, float* d_v, int64_t lo, int64_t count,
+                         const float* d_exchange_local, int32_t world, float* d_state, float lr, float beta1, float beta2, float eps,
+                         float max_norm, float grad_scale, void* stream);
 /* y += a * x (weight-decay / logit-regularisation terms of the discriminator loss, amp_continuous.py:548-550,585-589). */
 int emloco_axpy(float* d_y, const float* d_x, float a, int64_t n, void* stream);
 /* out[i] = sum_s parts[s * part_stride + i] (+ out[i] when accumulate != 0), in split order: the consumer of a split-K

@@ -28,7 +28,7 @@ def _grad_err(G, ref):
     return float((np.abs(G - ref) / (1e-3 * np.abs(ref) + 3e-4 * (np.abs(ref).max() + 1e-12))).max())
 
 
-def _setup(B, Ba, seed, wseed, world=1, sigma=-2.9):
+def _setup(B, Ba, seed, wseed, world=1, sigma=-2.9, reducer="auto"):
     from emloco_b200.policy import AMPSeptValueNetwork, RunningMeanStd
     from emloco_b200.update import PPOUpdate
     from oracle import netweights
@@ -42,7 +42,7 @@ def _setup(B, Ba, seed, wseed, world=1, sigma=-2.9):
     for m, pre in ((on, "obs"), (an, "amp")):
         m.running_mean.copy_(torch.from_numpy(stats[pre + "_mean"])); m.running_var.copy_(torch.from_numpy(stats[pre + "_var"]))
         m.count.fill_(float(stats[pre + "_count"]))
-    up = PPOUpdate(net, on.cuda(), an.cuda(), B, Ba, cfg=dict(UPDATE_CFG, amp_dropout=True), world=world)
+    up = PPOUpdate(net, on.cuda(), an.cuda(), B, Ba, cfg=dict(UPDATE_CFG, amp_dropout=True), world=world, reducer=reducer)
     return up, net, sd, batch, stats
 
 
