@@ -268,6 +268,7 @@ def train_step_bench(args, R, D, rank, world, pk):
     ms = D.max_over_ranks(e0.elapsed_time(e1), device="cuda") / K
     macs, launches = (_lib.mac_count - m0) / K, (_lib.launch_count - l0) / K
     info = up.info()
+    reducer = up.reducer_name
     # the same step without the optimiser half / without the collective, and the collective alone (bus bandwidth)
     e0.record()
     for i in range(K):
@@ -288,11 +289,22 @@ def train_step_bench(args, R, D, rank, world, pk):
         barrier()
         ar_ms = D.max_over_ranks(e0.elapsed_time(e1), device="cuda") / 20
         nbytes = flat.numel() * 4
-        ar = {"bytes": nbytes, "ms": ar_ms, "algbw_gbs": nbytes / (ar_ms * 1e-3) / 1e9, "busbw_gbs": nbytes / (ar_ms * 1e-3) / 1e9 * 2 * (world - 1) / world,
-              "exposed_ms": max(ms - fb_ms, 0.0), "note": "exposed = (step - forward/backward-only step), i.e. collective + clip-norm + Adam + operand refresh not hidden"}
+        ar = {"bytes": nbytes, "nccl_allreduce_ms": ar_ms, "algbw_gbs": nbytes / (ar_ms * 1e-3) / 1e9, "busbw_gbs": nbytes / (ar_ms * 1e-3) / 1e9 * 2 * (world - 1) / world,
+              "exposed_ms": max(ms - fb_ms, 0.0), "note": "nccl_allreduce_ms / bus bandwidth: a stand-alone NCCL all-reduce of the flat gradient, for reference; exposed_ms = (step - forward/backward-only step) = collective + clip-norm + Adam + operand refresh with the reducer in use"}
+        if reducer == "nvls":                             # the same step with the NCCL reducer (bucketed all-reduce, norm + Adam on every rank)
+            up2 = PPOUpdate(R.net, R.obs_norm, R.amp_norm, B, Ba, reducer="nccl")
+            for i in range(3):
+                up2.step(batches[i % nmb])
+            barrier()
+            e0.record()
+            for i in range(K):
+                up2.step(batches[i % nmb])
+            e1.record()
+            barrier()
+            ar["ms_per_minibatch_with_nccl_reducer"] = D.max_over_ranks(e0.elapsed_time(e1), device="cuda") / K
     tf = 2 * macs / (ms * 1e-3) / 1e12
     return {"metric": "train_samples_per_sec", "value": world * B / (ms * 1e-3), "unit": "samples/s", "ms_per_minibatch": ms,
-            "forward_backward_ms": fb_ms, "minibatch": B, "amp_minibatch": Ba, "minibatches_per_epoch": nmb, "steps": K,
+            "forward_backward_ms": fb_ms, "reducer": reducer, "minibatch": B, "amp_minibatch": Ba, "minibatches_per_epoch": nmb, "steps": K,
             "gemm_macs_per_minibatch": macs, "launches_per_minibatch": launches,
             "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": tf / pk["tf_sustained"],
                          "note": "algorithmic FLOPs of the GEMMs (forward + dgrad + wgrad + gradient-penalty double backward) counted once; bf16x3 issues 3 MMAs per product"},
