@@ -332,7 +332,8 @@ def run_ours(args):
     from emloco_b200.synthetic import synthetic_traj_pool
     pool = synthetic_traj_pool(TRAJ_POOL, args.seed)
     R = Rollout(N, device=local_rank, seed=D.rank_seed(args.seed, rank), tensor_cores=args.tensor_cores, recompute_disc=not args.dedup_disc,
-                concurrent=not args.serial, traj_flags=TRAJ_FLAGS, traj_pool=pool)
+                concurrent=not args.serial, traj_flags=TRAJ_FLAGS, traj_pool=pool, chain=False if args.no_chain else None)
+    chain_on = bool(R.chain)
     pk = peaks()
 
     def barrier():
@@ -516,7 +517,8 @@ def run_ours(args):
             k["frac"] = k["achieved"] / k["peak"]
             k["traffic"] = NCU_TRAFFIC[name] if (name != "locoval" or B == 1 << 20) else None
         dom = max(("physics", "post_step", "nets"), key=lambda k: kern[k]["ms"])
-        names = {"nets": "tc::linear_bf16x3_kernel (the 12 tcgen05 dense-layer launches of a step)", "physics": "physics_soa_kernel",
+        names = {"nets": "tc::linear_chain_kernel (the 2 persistent tcgen05 launches of a step: policy pass, critic + discriminator pass)" if chain_on
+                 else "tc::linear_bf16x3_kernel (the 12 tcgen05 dense-layer launches of a step)", "physics": "physics_soa_kernel",
                  "post_step": "post_step_kernel"}
         roof = dict(kern[dom]); roof.update(kernel=names[dom], traffic=NCU_TRAFFIC[dom], peak_source=pk["src"],
                                             traffic_source="profiles/r01g_full.md + gpurun r01g_prof.ncu-rep (ncu --set full; per step for nets, per launch otherwise)")
@@ -543,7 +545,8 @@ def run_ours(args):
                        "post_horizon_disc_pass": "recomputed" if not args.dedup_disc else "reused per-step logits",
                        "env_reset": "on device: state reset + TrajGenerator.reset (--real_path pool of %d synthetic polylines, "
                                     "--adjust_root_vel, --init_heading) for the envs that finish, every step" % TRAJ_POOL,
-                       "tensor_cores": bool(args.tensor_cores), "cuda_graphs": graphs, "parallel_branches": not args.serial},
+                       "tensor_cores": bool(args.tensor_cores), "cuda_graphs": graphs, "parallel_branches": not args.serial,
+                       "layer_chain": chain_on},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                     "groups": args.e2e_groups, "numa_node": numa,
@@ -582,6 +585,7 @@ def main():
     ap.add_argument("--train-steps", type=int, default=16)
     ap.add_argument("--no-train", action="store_true", help="skip the train-step (update) measurement")
     ap.add_argument("--e2e-groups", type=int, default=2, help="env groups of the end-to-end (host buffer) pipeline")
+    ap.add_argument("--no-chain", action="store_true", help="one launch per dense layer instead of one persistent launch per network pass")
     ap.add_argument("--eager", action="store_true", help="launch every kernel from the host instead of replaying CUDA graphs")
     args = ap.parse_args()
     capture_stdout()

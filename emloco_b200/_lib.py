@@ -18,7 +18,7 @@ SYMBOLS = [
     "emloco_plausibl_mlp_forward", "emloco_gae", "emloco_reset_done", "emloco_sample_actions",
     "emloco_disc_reward", "emloco_rollout_record", "emloco_normalize", "emloco_physics_step", "emloco_split_bf16",
     "emloco_linear_bf16x3", "emloco_set_post_sinks", "emloco_linear_bf16x3_rows", "emloco_timeout_gather",
-    "emloco_rollout_record_deferred", "emloco_fill_next_values", "emloco_traj_reset", "emloco_set_traj_reset", "emloco_locoval_backward_pose", "emloco_locoval_train_step", "emloco_locoval_train_workspace_bytes", "emloco_linear_bf16x3_head", "emloco_sample_actions_parts", "emloco_linear", "emloco_xform", "emloco_ppo_heads", "emloco_disc_heads", "emloco_amp_dropout_mask",
+    "emloco_rollout_record_deferred", "emloco_fill_next_values", "emloco_traj_reset", "emloco_set_traj_reset", "emloco_locoval_backward_pose", "emloco_locoval_train_step", "emloco_locoval_train_workspace_bytes", "emloco_linear_bf16x3_head", "emloco_linear_chain", "emloco_linear_chain_workspace_ints", "emloco_linear_chain_trace", "emloco_sample_actions_parts", "emloco_linear", "emloco_xform", "emloco_ppo_heads", "emloco_disc_heads", "emloco_amp_dropout_mask",
     "emloco_rms_update", "emloco_adam_begin", "emloco_grad_sumsq", "emloco_adam_clip", "emloco_axpy", "emloco_sum_parts", "emloco_player_record", "emloco_dp_reduce_shard", "emloco_dp_adam_shard", "emloco_motion_state", "emloco_amp_obs_demo", "emloco_set_env_models", "emloco_sync", "emloco_last_error", "emloco_version",
 ]
 
@@ -55,6 +55,14 @@ class PostSinks(C.Structure):
                 ("amp_mean", C.c_void_p), ("amp_inv_std", C.c_void_p),
                 ("amp_hi", C.c_void_p), ("amp_lo", C.c_void_p), ("ld_amp", C.c_int64),
                 ("rows_only", C.c_int32), ("reserved", C.c_int32)]
+
+
+class ChainLayer(C.Structure):
+    """emloco_chain_layer (include/emloco.h): one dense layer of an emloco_linear_chain launch."""
+    _fields_ = [("a_hi", C.c_void_p), ("a_lo", C.c_void_p), ("lda", C.c_int64), ("w_hi", C.c_void_p), ("w_lo", C.c_void_p), ("ldw", C.c_int64),
+                ("d_bias", C.c_void_p), ("M", C.c_int64), ("N", C.c_int32), ("K", C.c_int32), ("relu", C.c_int32), ("dep", C.c_int32),
+                ("d_y32", C.c_void_p), ("ldy", C.c_int64), ("y_hi", C.c_void_p), ("y_lo", C.c_void_p), ("ldy16", C.c_int64),
+                ("d_head_w", C.c_void_p), ("d_head_bias", C.c_void_p), ("d_head_part", C.c_void_p), ("d_head_out", C.c_void_p)]
 
 
 class TrajCfg(C.Structure):
@@ -129,6 +137,10 @@ def load():
     lib.emloco_linear_bf16x3.argtypes = [vp, vp, i64, vp, vp, i64, vp, i64, i32, i32, i32, vp, i64, vp, vp, i64, vp]
     lib.emloco_linear_bf16x3_rows.argtypes = [vp, vp, vp, i64, vp, vp, i64, vp, i64, i32, i32, i32, vp, i64, vp, vp, i64, vp]
     lib.emloco_linear_bf16x3_head.argtypes = [vp, vp, vp, i64, vp, vp, i64, vp, i64, i32, i32, i32, vp, i64, vp, vp, i64, vp, vp, vp, vp, vp]
+    lib.emloco_linear_chain.argtypes = [C.POINTER(ChainLayer), i32, C.POINTER(i32), i32, vp, i64, vp]
+    lib.emloco_linear_chain_workspace_ints.argtypes = [C.POINTER(ChainLayer), i32]
+    lib.emloco_linear_chain_workspace_ints.restype = i64
+    lib.emloco_linear_chain_trace.argtypes = [vp]
     lib.emloco_timeout_gather.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp, i64, vp, vp, i64, vp, vp, i64, vp, vp, vp]
     lib.emloco_rollout_record_deferred.argtypes = [C.POINTER(RolloutCfg)] + [vp] * 12 + [i64] + [vp] * 6
     lib.emloco_fill_next_values.argtypes = [C.POINTER(RolloutCfg), vp, vp, vp, i64, vp]
@@ -152,7 +164,7 @@ def load():
     lib.emloco_sync.argtypes = [vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
-        if name not in ("emloco_last_error", "emloco_version", "emloco_default_cfg", "emloco_locoval_train_workspace_bytes"):
+        if name not in ("emloco_last_error", "emloco_version", "emloco_default_cfg", "emloco_locoval_train_workspace_bytes", "emloco_linear_chain_workspace_ints"):
             fn.restype = C.c_int
     _lib = lib
     return lib
@@ -163,7 +175,7 @@ LAUNCHES = {"emloco_step": 2, "emloco_physics_step": 1, "emloco_post_step": 1, "
             "emloco_reset_indexed": 1, "emloco_traj_reset": 1, "emloco_linear": 1, "emloco_normalize": 1, "emloco_sample_actions": 1, "emloco_sample_actions_parts": 1,
             "emloco_disc_reward": 1, "emloco_rollout_record": 1, "emloco_gae": 1, "emloco_locoval_forward": 1,
             "emloco_locoval_backward": 1, "emloco_locoval_backward_pose": 1, "emloco_locoval_train_step": 2, "emloco_plausibl_mlp_forward": 1, "emloco_step_host": 2,
-            "emloco_locoval_forward_host": 1, "emloco_split_bf16": 1, "emloco_linear_bf16x3": 1, "emloco_linear_bf16x3_rows": 1, "emloco_linear_bf16x3_head": 2,
+            "emloco_locoval_forward_host": 1, "emloco_split_bf16": 1, "emloco_linear_bf16x3": 1, "emloco_linear_bf16x3_rows": 1, "emloco_linear_bf16x3_head": 2, "emloco_linear_chain": 1,
             "emloco_timeout_gather": 1, "emloco_rollout_record_deferred": 1, "emloco_fill_next_values": 1,
             "emloco_xform": 1, "emloco_ppo_heads": 1, "emloco_disc_heads": 1, "emloco_amp_dropout_mask": 1, "emloco_rms_update": 2,
             "emloco_adam_begin": 1, "emloco_grad_sumsq": 2, "emloco_adam_clip": 1, "emloco_axpy": 1, "emloco_sum_parts": 1, "emloco_player_record": 1, "emloco_dp_reduce_shard": 2, "emloco_dp_adam_shard": 1, "emloco_motion_state": 1, "emloco_amp_obs_demo": 1}

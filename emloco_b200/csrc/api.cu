@@ -613,6 +613,25 @@ int emloco_linear_bf16x3_head(const int32_t* d_rows, const uint16_t* a_hi, const
     return EMLOCO_OK;
 }
 
+int64_t emloco_linear_chain_workspace_ints(const emloco_chain_layer* layers, int32_t n_layers) {
+    if (!layers || n_layers <= 0) return 0;
+    return eml_linear_chain_workspace_ints(layers, n_layers);
+}
+
+int emloco_linear_chain_trace(int64_t* d_trace) {
+    eml_linear_chain_trace((long long*)d_trace);
+    return EMLOCO_OK;
+}
+
+int emloco_linear_chain(const emloco_chain_layer* layers, int32_t n_layers, const int32_t* order, int32_t n_segments,
+                        int32_t* d_workspace, int64_t workspace_ints, void* stream) {
+    const char* why = nullptr;
+    cudaError_t e = eml_linear_chain(layers, n_layers, order, n_segments, d_workspace, workspace_ints, (cudaStream_t)stream, &why);
+    if (e == cudaErrorInvalidValue && why) return fail(EMLOCO_EINVAL, why);
+    CK(e, "linear chain (tcgen05)");
+    return EMLOCO_OK;
+}
+
 int emloco_linear_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, const uint16_t* w_hi, const uint16_t* w_lo,
                          int64_t ldw, const float* d_bias, int64_t M, int32_t N, int32_t K, int32_t relu, float* d_y32, int64_t ldy,
                          uint16_t* y_hi, uint16_t* y_lo, int64_t ldy16, void* stream) {

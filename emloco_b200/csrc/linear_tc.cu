@@ -21,6 +21,7 @@
 #include <cuda_bf16.h>
 #include <mutex>
 #include <unordered_map>
+#include <vector>
 #include "sim.h"
 
 namespace tc {
@@ -540,6 +541,364 @@ linear_bf16x3_2cta_kernel(const __grid_constant__ CUtensorMap map_ah, const __gr
     }
 }
 
+// =====================================================================================================================
+// LAYER CHAIN: every dense layer of one network pass (task MLP -> actor / critic -> heads, discriminator) in ONE persistent
+// kernel (amp_network_sept_builder.py:69-111 evaluated top to bottom without leaving the SMs).
+//   * work unit = one 128 x 128 output tile of one layer; the host lists the tiles of all layers in a dependency-respecting
+//     order (segments); CTAs claim tickets from a global counter, so the 148 SMs stay busy across layer boundaries and
+//     across layers of different depth - the wave quantisation of one launch per layer (4096 rows = 128 / 256 / 512 tiles on
+//     148 SMs) and the launch gaps between them disappear
+//   * a layer's A operand is the bf16 hi/lo output the previous layer's epilogues wrote to global memory (L2 resident);
+//     the producer waits on a per-(layer, 128-row block) counter that the epilogues bump after their stores
+//     (st.global -> fence -> atomic;  ld.acquire -> fence.proxy.async -> TMA load)
+//   * single-output heads (value / logit): the CTA that completes a row block adds the per-64-column partial sums in
+//     column order (same arithmetic as head_reduce_kernel)
+//   * deadlock freedom: tickets are claimed in order and every tile only waits on tiles with lower tickets, which are held by
+//     CTAs that are resident and never wait on higher tickets
+// Tile shape / pipeline = linear_bf16x3_kernel<128>; results are bit-identical to the per-layer launches.
+// =====================================================================================================================
+constexpr int CHAIN_MAX_LAYERS = 8, CHAIN_MAX_SEGS = 24, CHAIN_RING = 4;
+
+struct ChainLayer {
+    GemmArgs g;
+    const float* head_bias; float* head_out;
+    int dep;          // layer whose output rows are this layer's A operand (-1: operands complete at launch)
+    int need;         // tiles that complete one 128-row block of `dep`
+    int tiles_n, num_kb;
+    int cnt_off;      // this layer's row-block counters in the workspace
+};
+struct alignas(64) ChainParams {
+    CUtensorMap maps[CHAIN_MAX_LAYERS][6];     // A hi, A lo, W hi, W lo (loads); y hi, y lo (stores, 32 x 32 boxes)
+    ChainLayer L[CHAIN_MAX_LAYERS];
+    int seg_layer[CHAIN_MAX_SEGS], seg_first[CHAIN_MAX_SEGS], seg_end[CHAIN_MAX_SEGS];   // tickets [seg_end[i-1], seg_end[i])
+    int n_segs, total, ws_ints;
+    int* ws;          // [0] next ticket, [1] CTAs that have left, [2..) row-block counters; all zero between launches
+    long long* trace; // optional (profiling): per ticket {cta, layer << 24 | tile, t claimed, t rows ready, t accumulator ready, t stored, t MMA thread free, t first k-block landed} (globaltimer ns)
+};
+
+__device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+
+constexpr int CHAIN_STAGE_OUT = 4096;          // per epilogue warp: 32 rows x 64 B of hi, then of lo (64B-swizzled TMA boxes)
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+
+// epilogue_chunk of the chain kernel: same arithmetic; the split output leaves through shared memory and two TMA stores per
+// 32 x 32 block (full 64-byte row segments) instead of 16-byte pieces in 32 different rows per store instruction - the
+// per-thread stores made the epilogue of a 128 x 128 tile take 6.4 us, as long as a 10-k-block main loop (chain trace).
+__device__ __forceinline__ float chain_epilogue_chunk(const uint32_t* r, const float* __restrict__ s_bias, const float* __restrict__ s_head,
+                                                      int nb, int row, int row0, bool row_ok, const GemmArgs& g, uint8_t* stage,
+                                                      uint32_t stage_u32, const CUtensorMap* map_yh, const CUtensorMap* map_yl,
+                                                      int lane, bool& stores_in_flight) {
+    if (nb >= g.N) return 0.f;                                              // warp-uniform
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(s_bias + j);
+        float x0 = __uint_as_float(r[j]) + b4.x, x1 = __uint_as_float(r[j + 1]) + b4.y;
+        float x2 = __uint_as_float(r[j + 2]) + b4.z, x3 = __uint_as_float(r[j + 3]) + b4.w;
+        v[j] = g.relu ? fmaxf(x0, 0.f) : x0; v[j + 1] = g.relu ? fmaxf(x1, 0.f) : x1;
+        v[j + 2] = g.relu ? fmaxf(x2, 0.f) : x2; v[j + 3] = g.relu ? fmaxf(x3, 0.f) : x3;
+    }
+    float hd = 0.f;
+    if (g.head_w) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) hd += v[j] * s_head[j];
+    }
+    if (g.y32 && row_ok) {
+        float* o = g.y32 + (long long)row * g.ldy + nb;
+        if (nb + 32 <= g.N && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (nb + j < g.N) o[j] = v[j];
+        }
+    }
+    if (g.y_hi) {                                                           // warp-uniform
+        uint32_t ph[16], pl[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+            __nv_bfloat16 h0 = __float2bfloat16_rn(v[j]), h1 = __float2bfloat16_rn(v[j + 1]);
+            __nv_bfloat16 l0 = __float2bfloat16_rn(v[j] - __bfloat162float(h0));
+            __nv_bfloat16 l1 = __float2bfloat16_rn(v[j + 1] - __bfloat162float(h1));
+            ph[j / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            pl[j / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        }
+        if (stores_in_flight) {                                             // the previous block's stores still read the buffer
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+        }
+        const int sw = (lane >> 1) & 3;                                     // 64-byte swizzle: 16-byte unit ^= (row / 2) % 4
+        uint4* sh_hi = reinterpret_cast<uint4*>(stage + lane * 64);
+        uint4* sh_lo = reinterpret_cast<uint4*>(stage + 2048 + lane * 64);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            sh_hi[j ^ sw] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
+            sh_lo[j ^ sw] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic smem writes -> async-proxy (TMA) reads
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_2d(map_yh, stage_u32, nb, row0);                      // rows / columns outside [M, N] are clipped by the unit
+            tma_store_2d(map_yl, stage_u32 + 2048, nb, row0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        stores_in_flight = true;
+    }
+    return hd;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) linear_chain_kernel(const __grid_constant__ ChainParams P) {
+    using T = Tile<128>;
+    constexpr int BN = 128, BK = T::BK, SW = T::SWIZZLE_BYTES;
+    // layout: 3 stages (192 KB) | barriers + ticket ring (256 B) | bias / head slices (2 KB) | pad to 3 KB | output staging (8 x 4 KB): 227 KB,
+    // which leaves no room for alignment slack - the dynamic window of a kernel without static shared memory starts 1 KB-aligned
+    extern __shared__ __align__(1024) uint8_t chain_smem[];
+    uint8_t* const smem_raw = chain_smem;
+    const uint32_t base = smem_u32(smem_raw);
+    if (base & 1023u) __trap();
+    const uint32_t bars = base + T::STAGES * T::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (T::STAGES + s); };
+    auto tfull_bar = [&](int a) { return bars + 8u * (2 * T::STAGES + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (2 * T::STAGES + 2 + a); };
+    auto sfull_bar = [&](int r) { return bars + 8u * (2 * T::STAGES + 4 + r); };                       // ring entry written
+    auto sempty_bar = [&](int r) { return bars + 8u * (2 * T::STAGES + 4 + CHAIN_RING + r); };          // ring entry consumed
+    constexpr uint32_t MISC = 8u * (2 * T::STAGES + 4 + 2 * CHAIN_RING);     // tmem slot, ticket ring, flag
+    static_assert(MISC + 12 + 8 * CHAIN_RING <= T::BAR_BYTES, "barrier block");
+    const uint32_t tmem_slot = bars + MISC;
+    uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
+    uint8_t* misc = smem_gen + T::STAGES * T::STAGE_BYTES + MISC;
+    volatile int* s_sched = reinterpret_cast<volatile int*>(misc + 8);                               // [CHAIN_RING]
+    volatile int* s_last = reinterpret_cast<volatile int*>(misc + 8 + 4 * CHAIN_RING);
+    volatile int* s_ticket = reinterpret_cast<volatile int*>(misc + 12 + 4 * CHAIN_RING);              // [CHAIN_RING] (trace only)
+    float* s_bias = reinterpret_cast<float*>(smem_gen + T::STAGES * T::STAGE_BYTES + T::BAR_BYTES);   // [2][BN]
+    float* s_head = s_bias + 2 * BN;                                                                 // [2][BN]
+    constexpr uint32_t OUT_OFF = T::STAGES * T::STAGE_BYTES + 3072;                                   // 1 KB-aligned (the swizzle works on address bits)
+    static_assert(T::BAR_BYTES + 2 * T::BIAS_BYTES <= 3072, "staging offset");
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < T::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 32 * NUM_EPI_WARPS); }
+        for (int r = 0; r < CHAIN_RING; ++r) { mbar_init(sfull_bar(r), 1); mbar_init(sempty_bar(r), 2); }   // MMA thread + one epilogue thread
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    } else if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(T::TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(misc);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== scheduler + TMA producer =====================
+            // (A separate scheduler warp that claims and dependency-checks tickets ahead of the loads was tried: the CTAs then
+            // hoard up to a ring of tiles, the pass ends ragged - 159 instead of 149 us - and the tile period did not improve.)
+            int stage = 0; uint32_t phase = 0;
+            int slot = 0; uint32_t sphase = 0;
+            int t = atomicAdd(P.ws, 1);
+            for (;;) {
+                int info = -1, layer = 0, tile = 0;
+                if (t < P.total) {
+                    int s = 0;
+                    while (t >= P.seg_end[s]) ++s;
+                    layer = P.seg_layer[s];
+                    tile = P.seg_first[s] + t - (s ? P.seg_end[s - 1] : 0);
+                    info = (layer << 24) | tile;
+                }
+                mbar_wait(sempty_bar(slot), sphase ^ 1);
+                s_sched[slot] = info;
+                s_ticket[slot] = t;
+                mbar_arrive(sfull_bar(slot));                               // release: the ring entry is visible to the waiters
+                long long* tr = (P.trace && info >= 0) ? P.trace + 8ll * t : nullptr;
+                if (tr) { tr[0] = blockIdx.x; tr[1] = info; tr[2] = gtimer(); }
+                if (++slot == CHAIN_RING) { slot = 0; sphase ^= 1; }
+                if (info < 0) break;
+                const ChainLayer& Ly = P.L[layer];
+                const int m_blk = tile / Ly.tiles_n;
+                const int m0 = m_blk * BM, n0 = (tile - m_blk * Ly.tiles_n) * BN;
+                if (Ly.dep >= 0) {                                          // rows written by the previous layer's epilogues
+                    const int* c = P.ws + P.L[Ly.dep].cnt_off + m_blk;
+                    while (ld_acquire_gpu(c) < Ly.need) __nanosleep(32);
+                    // (no proxy fence: the rows were written by TMA stores and are read by TMA loads - the same, async, proxy)
+                }
+                if (tr) tr[3] = gtimer();
+                const CUtensorMap* mp = P.maps[layer];
+                const int num_kb = Ly.num_kb;
+                int t_next = 0;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    const uint32_t sa = base + stage * T::STAGE_BYTES;
+                    mbar_expect_tx(full_bar(stage), T::STAGE_BYTES);
+                    tma_load_2d(sa, mp + 0, full_bar(stage), kb * BK, m0);
+                    tma_load_2d(sa + T::A_BYTES, mp + 1, full_bar(stage), kb * BK, m0);
+                    tma_load_2d(sa + 2 * T::A_BYTES, mp + 2, full_bar(stage), kb * BK, n0);
+                    tma_load_2d(sa + 2 * T::A_BYTES + T::B_BYTES, mp + 3, full_bar(stage), kb * BK, n0);
+                    if (++stage == T::STAGES) { stage = 0; phase ^= 1; }
+                    // the next ticket is requested three k-blocks before the end: the atomic's round trip (0.7 us) overlaps the last
+                    // loads (not earlier: a ticket held for a whole tile is a tile another CTA could have started)
+                    if (kb == (num_kb > 3 ? num_kb - 3 : 0)) t_next = atomicAdd(P.ws, 1);
+                }
+                t = t_next;
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===================== MMA issuer =====================
+            constexpr uint32_t idesc = make_idesc<BN>();
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            int slot = 0; uint32_t sphase = 0;
+            for (;;) {
+                mbar_wait(sfull_bar(slot), sphase);
+                const int info = s_sched[slot];
+                long long* tr = (P.trace && info >= 0) ? P.trace + 8ll * s_ticket[slot] : nullptr;
+                mbar_arrive(sempty_bar(slot));
+                if (++slot == CHAIN_RING) { slot = 0; sphase ^= 1; }
+                if (info < 0) break;
+                const int num_kb = P.L[info >> 24].num_kb;
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                tc_fence_after();
+                if (tr) tr[6] = gtimer();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    if (tr && kb == 0) tr[7] = gtimer();
+                    const uint32_t sa = base + stage * T::STAGE_BYTES;
+                    const uint64_t d_ah = make_smem_desc<SW>(sa), d_al = make_smem_desc<SW>(sa + T::A_BYTES);
+                    const uint64_t d_wh = make_smem_desc<SW>(sa + 2 * T::A_BYTES);
+                    const uint64_t d_wl = make_smem_desc<SW>(sa + 2 * T::A_BYTES + T::B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t ko = (uint64_t)((k * UMMA_K * 2) >> 4);
+                        umma_bf16(d_tmem, d_al + ko, d_wh + ko, idesc, (kb | k) != 0);      // same order as the per-layer kernel
+                        umma_bf16(d_tmem, d_ah + ko, d_wl + ko, idesc, 1);
+                        umma_bf16(d_tmem, d_ah + ko, d_wh + ko, idesc, 1);
+                    }
+                    umma_commit(empty_bar(stage));
+                    if (++stage == T::STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tfull_bar(acc));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue: warps 2..9 =====================
+        const int quad = warp & 3, half = (warp - 2) >> 2;
+        const int et = threadIdx.x - 64;
+        constexpr int NC = BN / 64;
+        int acc = 0; uint32_t acc_phase = 0;
+        int slot = 0; uint32_t sphase = 0;
+        // A finished tile is PUBLISHED (stores complete -> fences -> row-block counter) at the top of the next iteration, after the
+        // next ring entry and its bias slice have been requested: the completion latency of the TMA stores overlaps those waits.
+        // (Not later: the next blocking wait - the accumulator - may depend on this very publication.)
+        int pub = -1, pub_stores = 0;                                       // ring word of the tile to publish
+        for (;;) {
+            mbar_wait(sfull_bar(slot), sphase);
+            const int info = s_sched[slot];
+            const ChainLayer& Ly = P.L[info < 0 ? 0 : info >> 24];
+            const GemmArgs g = Ly.g;
+            const int tile = info & 0xffffff;
+            long long* tr = (P.trace && et == 0 && info >= 0) ? P.trace + 8ll * s_ticket[slot] : nullptr;
+            const int m_blk = tile / Ly.tiles_n;
+            const int m0 = m_blk * BM, n0 = (tile - m_blk * Ly.tiles_n) * BN;
+            float bias_v = 0.f, head_v = 0.f;
+            if (info >= 0 && et < BN && n0 + et < g.N) {
+                if (g.bias) bias_v = __ldg(g.bias + n0 + et);
+                if (g.head_w) head_v = __ldg(g.head_w + n0 + et);
+            }
+            if (pub >= 0) {
+                const ChainLayer& Lp = P.L[pub >> 24];
+                const int pm = (pub & 0xffffff) / Lp.tiles_n;
+                if (pub_stores && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the tile's rows are written
+                asm volatile("fence.proxy.async;" ::: "memory");
+                __threadfence();
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");
+                if (et == 0) {
+                    const int old = atomicAdd(P.ws + Lp.cnt_off + pm, 1);
+                    *s_last = old == Lp.tiles_n - 1;
+                    __threadfence();
+                }
+                if (Lp.head_out) {                                          // uniform per tile
+                    asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");
+                    if (*s_last && et < BM && pm * BM + et < Lp.g.M) {      // this CTA completed the row block: add the partials
+                        const float* hp = Lp.g.head_part + (long long)(pm * BM + et) * Lp.g.head_ld;
+                        float a = 0.f;
+                        for (int q = 0; q < Lp.g.head_ld; ++q) a += __ldcg(hp + q);
+                        Lp.head_out[pm * BM + et] = a + (Lp.head_bias ? __ldg(Lp.head_bias) : 0.f);
+                    }
+                }
+            }
+            if (info < 0) break;                                            // (the ring is not reused after the end marker)
+            if (et < BN) {
+                s_bias[acc * BN + et] = bias_v;
+                if (g.head_w) s_head[acc * BN + et] = head_v;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");       // everyone has read the ring entry
+            if (et == 0) mbar_arrive(sempty_bar(slot));
+            if (++slot == CHAIN_RING) { slot = 0; sphase ^= 1; }
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            if (tr) tr[4] = gtimer();
+            const int row = m0 + quad * 32 + lane;
+            const bool row_ok = row < g.M;
+            const int c0 = half * (BN / 2);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c0;
+            const float* sb = s_bias + acc * BN + c0;
+            const float* sh = s_head + acc * BN + c0;
+            uint32_t ra[32], rb[32];
+            uint8_t* const stage = smem_gen + OUT_OFF + (warp - 2) * CHAIN_STAGE_OUT;
+            const uint32_t stage_u32 = base + OUT_OFF + (warp - 2) * CHAIN_STAGE_OUT;
+            const CUtensorMap* const map_yh = &P.maps[info >> 24][4];
+            const int row0 = m0 + quad * 32;
+            bool in_flight = false;
+            tmem_ld32(taddr, ra);
+            tmem_ld_wait(ra);
+#pragma unroll
+            for (int c = 0; c < NC; c += 2) {
+                tmem_ld32(taddr + (c + 1) * 32, rb);
+                float hd = chain_epilogue_chunk(ra, sb + c * 32, sh + c * 32, n0 + c0 + c * 32, row, row0, row_ok, g, stage, stage_u32,
+                                                map_yh, map_yh + 1, lane, in_flight);
+                tmem_ld_wait(rb);
+                if (c + 2 < NC) tmem_ld32(taddr + (c + 2) * 32, ra);
+                hd += chain_epilogue_chunk(rb, sb + (c + 1) * 32, sh + (c + 1) * 32, n0 + c0 + (c + 1) * 32, row, row0, row_ok, g, stage,
+                                           stage_u32, map_yh, map_yh + 1, lane, in_flight);
+                if (c + 2 < NC) tmem_ld_wait(ra);
+                const int grp = (n0 + c0 + c * 32) >> 6;
+                if (g.head_part && row_ok && grp < g.head_ld) g.head_part[(long long)row * g.head_ld + grp] = hd;
+            }
+            tc_fence_before();
+            mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (tr) tr[5] = gtimer();
+            pub = info; pub_stores = in_flight;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(T::TMEM_COLS));
+    } else if (warp == 0) {
+        // the last CTA to leave zeroes the workspace for the next launch (nobody reads it any more)
+        int left = 0;
+        if (lane == 0) { __threadfence(); left = atomicAdd(P.ws + 1, 1); }
+        left = __shfl_sync(0xffffffffu, left, 0);
+        if (left == (int)gridDim.x - 1)
+            for (int i = lane; i < P.ws_ints; i += 32) P.ws[i] = 0;
+    }
+}
+
 // ---- fp32 -> (optional running-mean-std normalisation, utils/running_mean_std.py:82-84) -> bf16 hi/lo split ----
 // Only columns [0,K) are written: the TMA tensor maps carry the exact K, so pad columns of the pitch are never read.
 __global__ void split_bf16_kernel(const float* __restrict__ x, long long ldx, long long M, int K, const float* __restrict__ mean,
@@ -661,6 +1020,107 @@ static cudaError_t launch_2cta(const __nv_bfloat16* a_hi, const __nv_bfloat16* a
     return cudaGetLastError();
 }
 
+
+long long* g_chain_trace = nullptr;      // emloco_linear_chain_trace: profiling aid, NULL in production
+
+static cudaError_t launch_chain(const emloco_chain_layer* layers, int n_layers, const int* order, int n_segments, int* ws,
+                                long long ws_ints, cudaStream_t st, const char** why) {
+    using T = Tile<128>;
+    auto bad = [&](const char* m) { if (why) *why = m; return cudaErrorInvalidValue; };
+    if (!layers || n_layers <= 0 || n_layers > CHAIN_MAX_LAYERS) return bad("emloco_linear_chain: 1..8 layers");
+    if (!ws) return bad("emloco_linear_chain: null workspace");
+    static ChainParams P;                                   // (host calls are serialised by the Python GIL / one thread per sim)
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    int tiles_m[CHAIN_MAX_LAYERS], tiles[CHAIN_MAX_LAYERS];
+    int off = 2;
+    for (int l = 0; l < n_layers; ++l) {
+        const emloco_chain_layer& a = layers[l];
+        if (!a.a_hi || !a.a_lo || !a.w_hi || !a.w_lo || a.M <= 0 || a.N <= 0 || a.K <= 0 || a.lda < a.K || a.ldw < a.K || (a.lda & 7) || (a.ldw & 7))
+            return bad("emloco_linear_chain: bad operand");
+        if (((uintptr_t)a.a_hi | (uintptr_t)a.a_lo | (uintptr_t)a.w_hi | (uintptr_t)a.w_lo) & 15) return bad("emloco_linear_chain: operand pointers must be 16-byte aligned");
+        if (!a.d_y32 && !a.y_hi && !a.d_head_w) return bad("emloco_linear_chain: layer without output");
+        if (a.d_y32 && a.ldy < a.N) return bad("emloco_linear_chain: ldy < N");
+        if ((a.y_hi == nullptr) != (a.y_lo == nullptr)) return bad("emloco_linear_chain: y_hi and y_lo must come together");
+        if (a.y_hi && ((a.N & 31) || a.ldy16 < a.N || (a.ldy16 & 7) || (((uintptr_t)a.y_hi | (uintptr_t)a.y_lo) & 15)))
+            return bad("emloco_linear_chain: split output needs N % 32 == 0, pitch % 8 == 0, 16-byte aligned pointers");
+        if (a.d_head_w && (!a.d_head_part || !a.d_head_out)) return bad("emloco_linear_chain: null head argument");
+        if (a.dep >= l || a.dep < -1) return bad("emloco_linear_chain: dep must name an earlier layer");
+        if (a.dep >= 0 && (layers[a.dep].M != a.M || !layers[a.dep].y_hi)) return bad("emloco_linear_chain: dep needs the same M and a split output");
+        tiles_m[l] = (int)((a.M + BM - 1) / BM);
+        ChainLayer& L = P.L[l];
+        L.tiles_n = (a.N + 127) / 128; L.num_kb = (a.K + T::BK - 1) / T::BK;
+        tiles[l] = tiles_m[l] * L.tiles_n;
+        if (tiles[l] >= (1 << 24)) return bad("emloco_linear_chain: too many tiles");
+        L.dep = a.dep; L.need = a.dep >= 0 ? P.L[a.dep].tiles_n : 0;
+        L.cnt_off = off; off += tiles_m[l];
+        L.head_bias = a.d_head_bias; L.head_out = a.d_head_w ? a.d_head_out : nullptr;
+        GemmArgs& g = L.g;
+        g.bias = a.d_bias; g.y32 = a.d_y32; g.ldy = a.ldy; g.y_hi = (__nv_bfloat16*)a.y_hi; g.y_lo = (__nv_bfloat16*)a.y_lo; g.ldy16 = a.ldy16;
+        g.M = (int)a.M; g.N = a.N; g.K = a.K; g.relu = a.relu & 1; g.m_dev = nullptr;
+        g.head_w = a.d_head_w; g.head_part = a.d_head_w ? a.d_head_part : nullptr; g.head_ld = (a.N + 63) / 64;
+        g.k_splits = 0; g.split_stride = 0; g.n_fast = 1;
+        if (!make_map(&P.maps[l][0], a.a_hi, a.M, a.K, a.lda, BM, T::BK) || !make_map(&P.maps[l][1], a.a_lo, a.M, a.K, a.lda, BM, T::BK) ||
+            !make_map(&P.maps[l][2], a.w_hi, a.N, a.K, a.ldw, 128, T::BK) || !make_map(&P.maps[l][3], a.w_lo, a.N, a.K, a.ldw, 128, T::BK))
+            return bad("emloco_linear_chain: cuTensorMapEncodeTiled failed");
+        if (a.y_hi && (!make_map(&P.maps[l][4], a.y_hi, a.M, a.N, a.ldy16, 32, 32) || !make_map(&P.maps[l][5], a.y_lo, a.M, a.N, a.ldy16, 32, 32)))
+            return bad("emloco_linear_chain: cuTensorMapEncodeTiled failed (output)");
+    }
+    if (ws_ints < off) return bad("emloco_linear_chain: workspace too small");
+    P.ws = ws; P.ws_ints = off; P.trace = g_chain_trace;
+    // the ticket order: given segments, or the layers one after the other
+    int seg[CHAIN_MAX_SEGS][3];
+    if (order) {
+        if (n_segments <= 0 || n_segments > CHAIN_MAX_SEGS) return bad("emloco_linear_chain: 1..24 segments");
+        for (int i = 0; i < n_segments; ++i) for (int j = 0; j < 3; ++j) seg[i][j] = order[3 * i + j];
+    } else {
+        n_segments = n_layers;
+        for (int l = 0; l < n_layers; ++l) { seg[l][0] = l; seg[l][1] = 0; seg[l][2] = tiles[l]; }
+    }
+    // every tile exactly once, and after the tiles of its dep that cover its row block (=> no ticket waits on a later one)
+    {
+        std::vector<int> claimed[CHAIN_MAX_LAYERS];            // per row block: tiles handed out so far
+        std::vector<char> seen[CHAIN_MAX_LAYERS];
+        for (int l = 0; l < n_layers; ++l) { claimed[l].assign(tiles_m[l], 0); seen[l].assign(tiles[l], 0); }
+        int total = 0;
+        for (int i = 0; i < n_segments; ++i) {
+            const int l = seg[i][0];
+            if (l < 0 || l >= n_layers || seg[i][1] < 0 || seg[i][2] <= 0 || seg[i][1] + seg[i][2] > tiles[l]) return bad("emloco_linear_chain: bad segment");
+            for (int t = seg[i][1]; t < seg[i][1] + seg[i][2]; ++t) {
+                if (seen[l][t]) return bad("emloco_linear_chain: tile listed twice");
+                seen[l][t] = 1;
+                const int mb = t / P.L[l].tiles_n;
+                if (P.L[l].dep >= 0 && claimed[P.L[l].dep][mb] != P.L[P.L[l].dep].tiles_n)
+                    return bad("emloco_linear_chain: a tile is ordered before the tiles it depends on");
+                ++claimed[l][mb];
+            }
+            total += seg[i][2];
+            P.seg_layer[i] = l; P.seg_first[i] = seg[i][1]; P.seg_end[i] = total;
+        }
+        int want = 0;
+        for (int l = 0; l < n_layers; ++l) want += tiles[l];
+        if (total != want) return bad("emloco_linear_chain: the order does not cover every tile");
+        P.n_segs = n_segments; P.total = total;
+        for (int i = n_segments; i < CHAIN_MAX_SEGS; ++i) { P.seg_layer[i] = 0; P.seg_first[i] = 0; P.seg_end[i] = 0x7fffffff; }
+    }
+    auto kern = linear_chain_kernel;
+    constexpr int CHAIN_SMEM = T::STAGES * T::STAGE_BYTES + 3072 + NUM_EPI_WARPS * CHAIN_STAGE_OUT;      // = 227 KB
+    static_assert(CHAIN_SMEM <= 227 * 1024, "shared memory");
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    if (!g_num_sms) {
+        int dev = 0; cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int grid = P.total < g_num_sms ? P.total : g_num_sms;
+    kern<<<grid, NUM_THREADS, CHAIN_SMEM, st>>>(P);
+    return cudaGetLastError();
+}
+
 }  // namespace tc
 
 cudaError_t eml_split_bf16(const float* x, long long ldx, long long M, int K, const float* mean, const float* var, float eps,
@@ -723,4 +1183,17 @@ cudaError_t eml_linear_tc(const float* x, long long ldx, const float* w, const f
         e = eml_linear_bf16x3(ah, al, kp, wh, wl, kp, b, M, N, K, relu, y, ldy, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr, 0, st);
     cudaError_t e2 = cudaFreeAsync(scratch, st);
     return e != cudaSuccess ? e : e2;
+}
+
+void eml_linear_chain_trace(long long* buf) { tc::g_chain_trace = buf; }
+
+long long eml_linear_chain_workspace_ints(const emloco_chain_layer* layers, int n_layers) {
+    long long n = 2;
+    for (int l = 0; l < n_layers; ++l) n += (layers[l].M + tc::BM - 1) / tc::BM;
+    return n;
+}
+
+cudaError_t eml_linear_chain(const emloco_chain_layer* layers, int n_layers, const int* order, int n_segments, int* ws, long long ws_ints,
+                             cudaStream_t st, const char** why) {
+    return tc::launch_chain(layers, n_layers, order, n_segments, ws, ws_ints, st, why);
 }

@@ -123,6 +123,10 @@ cudaError_t eml_linear_bf16x3(const void* a_hi, const void* a_lo, long long lda,
                               const float* bias, long long M, int N, int K, int relu, float* y32, long long ldy, void* y_hi,
                               void* y_lo, long long ldy16, int tile_n, const int* m_dev, const float* head_w, float* head_part,
                               int head_ld, cudaStream_t st);
+cudaError_t eml_linear_chain(const emloco_chain_layer* layers, int n_layers, const int* order, int n_segments, int* ws, long long ws_ints,
+                             cudaStream_t st, const char** why);
+void eml_linear_chain_trace(long long* buf);
+long long eml_linear_chain_workspace_ints(const emloco_chain_layer* layers, int n_layers);
 cudaError_t eml_head_reduce(const float* part, int groups, const float* bias, float* out, long long M, cudaStream_t st);
 cudaError_t eml_timeout_gather(const int64_t* reset, const int64_t* terminate, long long N, const uint16_t* self_hi,
                                const uint16_t* self_lo, long long ld_self, const uint16_t* task_hi, const uint16_t* task_lo,

@@ -136,8 +136,11 @@ class RolloutNets:
     """Evaluates the networks for a fixed row count with preallocated workspaces (CUDA-graph friendly)."""
 
     def __init__(self, net: AMPSeptValueNetwork, obs_norm: RunningMeanStd, amp_norm: RunningMeanStd, rows: int,
-                 tensor_cores: bool = False, concurrent: bool = False, amp_slots: int = 1):
+                 tensor_cores: bool = False, concurrent: bool = False, amp_slots: int = 1, chain: bool = False):
         self.net, self.obs_norm, self.amp_norm, self.M, self.tc = net, obs_norm, amp_norm, int(rows), bool(tensor_cores)
+        # chain: the dense layers of a network pass run as ONE persistent launch (emloco_linear_chain) instead of one per layer
+        self.chain = bool(chain) and self.tc
+        self._chain_ws = {}
         dev = net.mu.weight.device
         if dev.type != "cuda":
             raise _lib.EmlocoError("RolloutNets needs its parameters on a CUDA device; there is no CPU fallback")
@@ -316,7 +319,30 @@ class RolloutNets:
             self._lin(self.v1, n._task_value_mlp[2], True, self.v2)
             self._lin(self.v2, n._value_logits, False, task_value_out)
 
-        if self.fork is not None:
+        def chain_main():
+            # task MLP -> stacked actor / critic first layer -> actor / critic second layers -> mu, value: one launch
+            if not operands_ready:
+                eps = self.obs_norm.epsilon
+                split_bf16(obs[:, :SELF_OBS], self.s_ain.cols(0, SELF_OBS), mean[:SELF_OBS], var[:SELF_OBS], eps)
+                split_bf16(obs[:, SELF_OBS:], self.s_tin, mean[SELF_OBS:], var[SELF_OBS:], eps)
+            tm = (self.M + 127) // 128
+            L = [chain_layer(self.s_tin, W("t0", n._task_mlp[0].weight), n._task_mlp[0].bias.detach(), True, y16=self.s_t1),
+                 chain_layer(self.s_t1, W("t2", n._task_mlp[2].weight), n._task_mlp[2].bias.detach(), True, dep=0,
+                             y16=self.s_ain.cols(SELF_OBS, self.s_ain.K)),
+                 chain_layer(self.s_ain, W("ac1", w), b, True, dep=1, y16=self.s_ac1),
+                 chain_layer(self.s_ac1.cols(0, h), W("a2", n.actor_mlp[2].weight), n.actor_mlp[2].bias.detach(), True, dep=2, y16=self.s_a2),
+                 chain_layer(self.s_ac1.cols(h, 2 * h), W("c2", n.critic_mlp[2].weight), n.critic_mlp[2].bias.detach(), True, dep=2,
+                             head=(n.value, self.value, self.hp_c)),
+                 chain_layer(self.s_a2, W("mu", n.mu.weight), n.mu.bias.detach(), False, dep=3, y32=mu_out)]
+            linear_chain(L, self.policy_order(tm, L), self._ws("policy", L))
+            sample_actions(mu_out, n.sigma, noise, actions_out, neglogp_out)
+
+        if self.chain:
+            if self.fork is not None:
+                self.fork.run(chain_main, task_value)
+            else:
+                chain_main(); task_value()
+        elif self.fork is not None:
             trunk_ac1()
             # the actor branch (a2 -> mu -> sample) is the longer one and the physics step waits for it: it runs on a
             # high-priority side stream so that a2's tiles are dispatched before c2's and mu / sample overlap c2's second wave
@@ -341,6 +367,66 @@ class RolloutNets:
         self._lin(self.ac1[:, h:], n.critic_mlp[2], True, self.c2)
         self._lin(self.c2, n.value, False, self.next_value)
         return self.next_value
+
+    def _ws(self, name, layers):
+        """Zero-initialised counter workspace of a chain (the kernel leaves it zeroed); one per pass."""
+        ws = self._chain_ws.get(name)
+        need = chain_workspace_ints(layers)
+        if ws is None or ws.numel() < need:
+            ws = self._chain_ws[name] = torch.zeros(need, device=self.mu.device, dtype=torch.int32)
+        return ws
+
+    @staticmethod
+    def policy_order(tm, L):
+        """Ticket order of the policy pass: task MLP, stacked first layer, actor second layer, most of the critic's second
+        layer, the mu tiles (their rows are complete by then), the rest of the critic."""
+        t = [tiles_of(l) for l in L]
+        c_first = min(t[4], 5 * tm)
+        return [(0, 0, t[0]), (1, 0, t[1]), (2, 0, t[2]), (3, 0, t[3]), (4, 0, c_first), (5, 0, t[5])] + \
+               ([(4, c_first, t[4] - c_first)] if t[4] > c_first else [])
+
+    @staticmethod
+    def post_order(tm, L, sms=148):
+        """Ticket order of the critic(next obs) + discriminator pass: the discriminator's first layer (independent of
+        everything, the longest tiles) fills the SMs while the dependent critic chain works through its short layers; the
+        pass ends on the short tiles of the discriminator's second layer."""
+        t = [tiles_of(l) for l in L]
+        a = max(0, min(t[4], sms - t[0]))
+        b = min(t[4] - a, 84 * tm // 32)
+        c = t[4] - a - b
+        o = [(0, 0, t[0])]
+        if a: o.append((4, 0, a))
+        o.append((1, 0, t[1]))
+        if b: o.append((4, a, b))
+        o.append((2, 0, t[2]))
+        if c: o.append((4, a + b, c))
+        o += [(3, 0, t[3]), (5, 0, t[5])]
+        return o
+
+    def critic_disc(self, obs, amp_obs, slot=0, operands_ready=False, logit_out=None):
+        """`_eval_critic(next obs)` (common_agent.py:647-655, before un-normalisation) and `_eval_disc`
+        (amp_continuous.py:666-668) as ONE launch: -> (next_value [M,1], disc logit [M,1])."""
+        n, W, M = self.net, self.w16.get, self.M
+        assert self.chain and amp_obs.shape[0] == M
+        out = self.logit if logit_out is None else logit_out
+        s_amp = self.s_amp.rows_view(M, slot * M)
+        if not operands_ready:
+            mean, var = self.obs_norm.f32(); am, av = self.amp_norm.f32()
+            split_bf16(obs[:, :SELF_OBS], self.s_ain.cols(0, SELF_OBS), mean[:SELF_OBS], var[:SELF_OBS], self.obs_norm.epsilon)
+            split_bf16(obs[:, SELF_OBS:], self.s_tin, mean[SELF_OBS:], var[SELF_OBS:], self.obs_norm.epsilon)
+            split_bf16(amp_obs, s_amp, am, av, self.amp_norm.epsilon)
+        h = n.critic_mlp[0].out_features
+        L = [chain_layer(self.s_tin, W("t0", n._task_mlp[0].weight), n._task_mlp[0].bias.detach(), True, y16=self.s_t1),
+             chain_layer(self.s_t1, W("t2", n._task_mlp[2].weight), n._task_mlp[2].bias.detach(), True, dep=0,
+                         y16=self.s_ain.cols(SELF_OBS, self.s_ain.K)),
+             chain_layer(self.s_ain, W("c0", n.critic_mlp[0].weight), n.critic_mlp[0].bias.detach(), True, dep=1, y16=self.s_ac1.cols(h, 2 * h)),
+             chain_layer(self.s_ac1.cols(h, 2 * h), W("c2", n.critic_mlp[2].weight), n.critic_mlp[2].bias.detach(), True, dep=2,
+                         head=(n.value, self.next_value, self.hp_c)),
+             chain_layer(s_amp, W("d0", n._disc_mlp[0].weight), n._disc_mlp[0].bias.detach(), True, y16=self.s_d1),
+             chain_layer(self.s_d1, W("d2", n._disc_mlp[2].weight), n._disc_mlp[2].bias.detach(), True, dep=4,
+                         head=(n._disc_logits, out, self.hp_d))]
+        linear_chain(L, self.post_order((M + 127) // 128, L), self._ws("post", L))
+        return self.next_value, out
 
     def critic_timeouts(self, reset, terminate):
         """The critic on the terminal observation of the envs that were reset WITHOUT terminating (episode time-out) - the
@@ -462,6 +548,52 @@ def linear_bf16x3(a: _Split, w: _Split, bias, relu, y32=None, y16: _Split = None
         _lib.check(_lib.load().emloco_linear_bf16x3(*args), "emloco_linear_bf16x3")
     else:
         _lib.check(_lib.load().emloco_linear_bf16x3_rows(_ptr(rows), *args), "emloco_linear_bf16x3_rows")
+
+
+def chain_layer(a: _Split, w: _Split, bias, relu, dep=-1, y32=None, y16: _Split = None, head=None):
+    """One layer of an emloco_linear_chain launch (arguments as linear_bf16x3; dep = index of the layer that writes `a`)."""
+    M, K, N = a.rows, a.K, w.rows
+    assert w.K == K
+    L = _lib.ChainLayer()
+    L.a_hi, L.a_lo, L.lda, L.w_hi, L.w_lo, L.ldw = _ptr(a.hi), _ptr(a.lo), a.ld, _ptr(w.hi), _ptr(w.lo), w.ld
+    L.d_bias, L.M, L.N, L.K, L.relu, L.dep = _ptr(bias), M, N, K, int(bool(relu)), dep
+    if y32 is not None:
+        assert y32.shape == (M, N) and y32.stride(1) == 1
+        L.d_y32, L.ldy = _ptr(y32), y32.stride(0)
+    if y16 is not None:
+        assert y16.rows == M and y16.K == N
+        L.y_hi, L.y_lo, L.ldy16 = _ptr(y16.hi), _ptr(y16.lo), y16.ld
+    if head is not None:
+        layer, out, part = head
+        hw = layer.weight.detach()
+        assert hw.shape == (1, N) and hw.is_contiguous() and out.shape == (M, 1) and out.is_contiguous()
+        assert part.is_contiguous() and part.shape[0] >= M and part.shape[1] == (N + 63) // 64
+        L.d_head_w, L.d_head_bias, L.d_head_part, L.d_head_out = _ptr(hw), _ptr(layer.bias.detach()), _ptr(part), _ptr(out)
+    return L
+
+
+def tiles_of(layer):
+    return ((layer.M + 127) // 128) * ((layer.N + 127) // 128)
+
+
+def chain_workspace_ints(layers):
+    arr = (_lib.ChainLayer * len(layers))(*layers)
+    return int(_lib.load().emloco_linear_chain_workspace_ints(arr, len(layers)))
+
+
+def linear_chain(layers, order=None, ws=None):
+    """All `layers` (chain_layer) in one persistent tcgen05 launch.  order: [(layer, first tile, tile count)] or None (layer by
+    layer); ws: int32 workspace, zero before its first use (torch.zeros), at least chain_workspace_ints(layers) long."""
+    arr = (_lib.ChainLayer * len(layers))(*layers)
+    if ws is None:
+        ws = torch.zeros(chain_workspace_ints(layers), device=torch.device("cuda", torch.cuda.current_device()), dtype=torch.int32)
+    o, ns = None, 0
+    if order is not None:
+        flat = [int(v) for seg in order for v in seg]
+        o, ns = (C.c_int32 * len(flat))(*flat), len(order)
+    for L in layers:
+        _lib.mac_count += L.M * L.N * L.K
+    _lib.check(_lib.load().emloco_linear_chain(arr, len(layers), o, ns, _ptr(ws), ws.numel(), _stream()), "emloco_linear_chain")
 
 
 class _TcWeights:

@@ -34,7 +34,7 @@ class Rollout:
                  step_to_pred=144, normalize_value=True, net=None, obs_norm=None, amp_norm=None, value_norm=None,
                  recompute_disc=True, valuenet=None, fuse_sinks=True, concurrent=True, reuse_values=False, traj_flags=None,
                  traj_pool=None, traj_deferred=None, finetune=False, value_lr=1e-3,
-                 min_cum_rewards=-10.0, max_cum_rewards=100.0, sim_cfg=None, traj_cfg=None, rows_only=True):
+                 min_cum_rewards=-10.0, max_cum_rewards=100.0, sim_cfg=None, traj_cfg=None, rows_only=True, chain=None):
         self.N, self.T, self.device = int(num_envs), int(horizon), int(device)
         self.gamma, self.tau = gamma, tau
         self.task_reward_w, self.disc_reward_w, self.disc_reward_scale = task_reward_w, disc_reward_w, disc_reward_scale
@@ -49,9 +49,15 @@ class Rollout:
         self.obs_norm = (obs_norm or RunningMeanStd(OBS)).to(dev)
         self.amp_norm = (amp_norm or RunningMeanStd(AMP_OBS)).to(dev)
         self.value_norm = (value_norm or RunningMeanStd(1)).to(dev)
+        # chain (default with tensor cores + parallel branches): each of the two network passes of a step is ONE persistent
+        # launch over all its dense layers (emloco_linear_chain); the value-reuse variant keeps the per-layer launches
+        self.chain = (bool(tensor_cores) and bool(concurrent) and not reuse_values) if chain is None else (bool(chain) and bool(tensor_cores))
         self.nets = RolloutNets(self.net, self.obs_norm, self.amp_norm, self.N, tensor_cores=tensor_cores, concurrent=concurrent,
-                                amp_slots=self.T if (tensor_cores and recompute_disc) else 1)
+                                amp_slots=self.T if (tensor_cores and recompute_disc) else 1, chain=self.chain)
         self.concurrent = bool(concurrent)
+        # with the chain every SM holds one of its CTAs (197 KB of shared memory), so the LocoVal kernel (107 KB) cannot run beside
+        # it: it becomes a branch of the post-step launch instead (its inputs are fixed at reset, nothing in the step feeds it)
+        self.locoval_with_post = self.chain and self.concurrent
         self._side = Fork(dev, 1) if concurrent else None      # outer branches (noise draw, trajectory reset) around the nets' own fork
         # value reuse needs the operand sinks (the compact critic reads the rows the post-step kernel wrote)
         self.reuse_values = bool(reuse_values) and bool(tensor_cores) and bool(fuse_sinks)
@@ -208,6 +214,12 @@ class Rollout:
             sim.physics_step(cur["res"]["actions"])
 
         def seg_post():                                                                #           post_physics_step
+            if self.locoval_with_post:
+                self._side.run(post_main, seg_locoval)
+            else:
+                post_main()
+
+        def post_main():
             if fuse:
                 # rows_only: the mirrored observation and the AMP ring are written once, into the experience rows (the ring of
                 # the next step is shifted out of row n); sim.flip_obs / sim.amp_obs stay stale while the rollout runs fused
@@ -265,9 +277,19 @@ class Rollout:
         def seg_locoval():
             self.locoval_scores = self.valuenet(self.waypoint_traj, self.init_pose, self.init_vel)
 
+        def seg_chain2():  # critic(next obs) and the discriminator: one launch over the six layers
+            cur["nv"], cur["logit"] = nets.critic_disc(sim.obs, mb["amp_obs"][n] if fuse else sim.amp_obs.view(self.N, AMP_OBS), slot=slot,
+                                                       operands_ready=fuse)
+
         def seg_nets2():   # critic(next obs), discriminator and LocoVal scoring are independent: three graph branches
             # the critic chain (5 dependent layers) is the longer branch: it goes on a high-priority side stream and the
             # discriminator's big GEMM fills the SMs its small layers leave idle (183 -> 172 us for the segment)
+            if self.chain and not reuse:
+                if self.locoval_with_post:
+                    seg_chain2()
+                else:
+                    nets.fork.run(seg_chain2, seg_locoval)
+                return
             nets.fork.run(seg_disc, seg_critic, seg_locoval)
 
         def seg_record_ft():

@@ -368,6 +368,40 @@ int emloco_linear_bf16x3_head(const int32_t* d_rows, const uint16_t* a_hi, const
                               float* d_y32, int64_t ldy, uint16_t* y_hi, uint16_t* y_lo, int64_t ldy16, const float* d_head_w,
                               const float* d_head_bias, float* d_head_part, float* d_head_out, void* stream);
 
+/* ---- layer chain: all dense layers of ONE network pass in a single persistent launch --------------------------------------
+ * Replaces the sequence of nn.Linear / ReLU modules that `AMPSeptValueBuilder.Network.eval_actor / eval_critic / eval_disc`
+ * walk per call (amp_network_sept_builder.py:69-111, amp_network_builder.py:81-84; called from get_action_values,
+ * _eval_critic and _calc_amp_rewards, amp_continuous_value.py:53,85,93).  Every layer is an emloco_linear_bf16x3 problem
+ * (same operand format, same arithmetic, bit-identical outputs); `dep` names the layer whose split output (y_hi / y_lo) is this
+ * layer's A operand, -1 when the operand is complete before the launch.  The layers' 128 x 128 output tiles are handed out to the
+ * SMs from one queue, so that 4096-row layers of different widths fill the 148 SMs without the wave quantisation and launch gaps
+ * of one launch per layer; a tile starts as soon as the 128 rows it reads are complete (per-row-block counters in d_workspace).
+ *   order: n_segments triples {layer, first tile, tile count}; tiles of a layer are numbered row block major (tile =
+ *          row_block * ceil(N/128) + column block).  Every tile must appear exactly once and after all tiles of `dep` that cover
+ *          its row block (checked on the host: EMLOCO_EINVAL otherwise).  NULL = the layers one after the other.
+ *   head_w / head_bias / head_part / head_out: the single-output layer that follows (emloco_linear_bf16x3_head semantics);
+ *          the CTA that completes a row block adds the partial sums in column order.
+ *   d_workspace: emloco_linear_chain_workspace_ints(...) int32 words, zero before the FIRST launch (the kernel leaves it zeroed);
+ *          one workspace per chain that may be in flight.
+ * At most 8 layers and 24 segments; all layers that are linked by `dep` have the same M. */
+typedef struct {
+    const uint16_t* a_hi; const uint16_t* a_lo; int64_t lda;
+    const uint16_t* w_hi; const uint16_t* w_lo; int64_t ldw;
+    const float* d_bias;
+    int64_t M; int32_t N, K;
+    int32_t relu, dep;
+    float* d_y32; int64_t ldy;
+    uint16_t* y_hi; uint16_t* y_lo; int64_t ldy16;
+    const float* d_head_w; const float* d_head_bias; float* d_head_part; float* d_head_out;
+} emloco_chain_layer;
+int64_t emloco_linear_chain_workspace_ints(const emloco_chain_layer* layers, int32_t n_layers);
+/* Profiling aid (NULL = off, the default): later emloco_linear_chain launches record, per ticket (= position in `order`), eight
+ * int64 words {CTA, layer << 24 | tile, ns claimed, ns rows ready, ns accumulator complete, ns stored, ns the MMA thread reached the
+ * tile, ns its first k-block landed} (%globaltimer) into d_trace[8 * tiles]; scripts/chain_trace.py turns them into per-layer occupancy figures. */
+int emloco_linear_chain_trace(int64_t* d_trace);
+int emloco_linear_chain(const emloco_chain_layer* layers, int32_t n_layers, const int32_t* order, int32_t n_segments,
+                        int32_t* d_workspace, int64_t workspace_ints, void* stream);
+
 /* ---- value reuse (optional): `_eval_critic(next obs)` of play_steps (amp_continuous_value.py:85-90) without a second full
  * critic pass.  For an env that is not reset, the next observation IS the observation of the following step, whose policy
  * pass evaluates the critic on it anyway; terminated envs get next_value = 0; only envs reset by the episode time-out

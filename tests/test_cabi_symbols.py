@@ -91,6 +91,9 @@ int main(void) {
     printf("emloco_post_sinks %zu\\n", sizeof(emloco_post_sinks));
     printf("emloco_traj_cfg %zu\\n", sizeof(emloco_traj_cfg));
     printf("emloco_motion_lib %zu\\n", sizeof(emloco_motion_lib));
+    printf("emloco_chain_layer %zu\\n", sizeof(emloco_chain_layer));
+    printf("chain.dep %zu\\n", offsetof(emloco_chain_layer, dep));
+    printf("chain.d_head_out %zu\\n", offsetof(emloco_chain_layer, d_head_out));
     printf("rollout.d_value_stats %zu\\n", offsetof(emloco_rollout_cfg, d_value_stats));
     printf("motion.num_motions %zu\\n", offsetof(emloco_motion_lib, num_motions));
     printf("cfg.max_effort %zu\\n", offsetof(emloco_cfg, max_effort));
@@ -113,6 +116,8 @@ int main(void) {
     assert out["emloco_post_sinks"] == C.sizeof(_lib.PostSinks)
     assert out["emloco_traj_cfg"] == C.sizeof(_lib.TrajCfg)
     assert out["emloco_motion_lib"] == C.sizeof(_lib.MotionLib)
+    assert out["emloco_chain_layer"] == C.sizeof(_lib.ChainLayer)
+    assert out["chain.dep"] == _lib.ChainLayer.dep.offset and out["chain.d_head_out"] == _lib.ChainLayer.d_head_out.offset
     assert out["rollout.d_value_stats"] == _lib.RolloutCfg.d_value_stats.offset
     assert out["motion.num_motions"] == _lib.MotionLib.num_motions.offset
     assert out["cfg.max_effort"] == _lib.Cfg.max_effort.offset and out["cfg.physics_impl"] == _lib.Cfg.physics_impl.offset
