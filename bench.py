@@ -44,6 +44,9 @@ HORIZON = 32
 # the rows_only sinks: 63 MB read + 137 MB written back by the end of the launch); nets: the same capture, summed over the
 # 12 tcgen05 launches of one step; locoval: profiles/r01f_locoval.md, the 1 M-score launch
 NCU_TRAFFIC = {"physics": 5.36e6, "post_step": 200.5e6, "nets": 363.7e6, "locoval": 427.1e6}
+# with the layer chain: the two persistent launches of a step (profiles/r02r_full.md: policy pass 98.7 MB read + 82.6 MB written,
+# critic + discriminator pass 154.4 + 57.4 MB)
+NCU_TRAFFIC_NETS_CHAIN = 393.1e6
 
 
 _OUT_FD = None
@@ -516,12 +519,15 @@ def run_ours(args):
         for name, k in kern.items():
             k["frac"] = k["achieved"] / k["peak"]
             k["traffic"] = NCU_TRAFFIC[name] if (name != "locoval" or B == 1 << 20) else None
+        if chain_on:
+            kern["nets"]["traffic"] = NCU_TRAFFIC_NETS_CHAIN
         dom = max(("physics", "post_step", "nets"), key=lambda k: kern[k]["ms"])
         names = {"nets": "tc::linear_chain_kernel (the 2 persistent tcgen05 launches of a step: policy pass, critic + discriminator pass)" if chain_on
                  else "tc::linear_bf16x3_kernel (the 12 tcgen05 dense-layer launches of a step)", "physics": "physics_soa_kernel",
                  "post_step": "post_step_kernel"}
-        roof = dict(kern[dom]); roof.update(kernel=names[dom], traffic=NCU_TRAFFIC[dom], peak_source=pk["src"],
-                                            traffic_source="profiles/r01g_full.md + gpurun r01g_prof.ncu-rep (ncu --set full; per step for nets, per launch otherwise)")
+        roof = dict(kern[dom]); roof.update(kernel=names[dom], traffic=kern[dom]["traffic"], peak_source=pk["src"],
+                                            traffic_source="profiles/r02r_full.md (ncu --set full; per step for nets: both chain launches; per launch otherwise)" if chain_on
+                                            else "profiles/r01g_full.md + gpurun r01g_prof.ncu-rep (ncu --set full; per step for nets, per launch otherwise)")
         if dom == "nets":
             roof["note"] = ("fp32 operands are carried as bf16 hi+lo and every k-step issues 3 MMAs (bf16x3, fp32-grade products): "
                             "frac counts algorithmic FLOPs once, so its ceiling is 1/3; MMA-issue rate = 3 x achieved")
