@@ -335,7 +335,7 @@ def run_ours(args):
     from emloco_b200.synthetic import synthetic_traj_pool
     pool = synthetic_traj_pool(TRAJ_POOL, args.seed)
     R = Rollout(N, device=local_rank, seed=D.rank_seed(args.seed, rank), tensor_cores=args.tensor_cores, recompute_disc=not args.dedup_disc,
-                concurrent=not args.serial, traj_flags=TRAJ_FLAGS, traj_pool=pool, chain=False if args.no_chain else None)
+                concurrent=not args.serial, traj_flags=TRAJ_FLAGS, traj_pool=pool, chain=False if args.no_chain else None, merged=False if args.no_merge else None)
     chain_on = bool(R.chain)
     pk = peaks()
 
@@ -361,7 +361,8 @@ def run_ours(args):
         R.step(n)
     R.finish()
     step_i[0] = 3
-    for _ in range(max(W, HORIZON if graphs else 0)):   # with graphs: every slot's graph is captured during warm-up
+    for _ in range(max(W, HORIZON + 8 if graphs else 0)):   # with graphs: every slot's graph is captured during warm-up (merged
+        # schedule: the slot the graphed steps start on is captured twice, without and with an outstanding previous step)
         one_step()
     barrier()
     sampler = ClockSampler(local_rank)
@@ -397,16 +398,35 @@ def run_ours(args):
     finish_ms = ef0.elapsed_time(ef1)
     clocks = sampler.stop() if rank == 0 else None
     # per-segment device times: the same step replayed as seven per-segment graphs (8 slots) with an event between them
-    seg_step = (lambda i: R.step_segments_graphed(i % 8)) if graphs else (lambda i: R.step(i % HORIZON))
-    for i in range(8):
-        seg_step(i)
-    torch.cuda.synchronize()
-    R.enable_segment_timing(True)
-    for i in range(24):
-        seg_step(i)
-    torch.cuda.synchronize()
-    seg, _ = R.segment_ms()
-    R.enable_segment_timing(False)
+    merged_on = bool(graphs and R.merged)
+    if merged_on:
+        # merged schedule: slots 1..8 of a horizon, each holding its policy pass AND the critic / discriminator / bookkeeping of the
+        # slot before it (slot 0, untimed, only leaves its own outstanding)
+        def seg_cycle():
+            R.flush()
+            R.step_graphed(0)
+            for n in range(1, 9):
+                R.step_segments_graphed(n)
+        seg_cycle()
+        torch.cuda.synchronize()
+        R.enable_segment_timing(True)
+        for _ in range(3):
+            seg_cycle()
+        torch.cuda.synchronize()
+        seg, _ = R.segment_ms()
+        R.enable_segment_timing(False)
+        R.flush()
+    else:
+        seg_step = (lambda i: R.step_segments_graphed(i % 8)) if graphs else (lambda i: R.step(i % HORIZON))
+        for i in range(8):
+            seg_step(i)
+        torch.cuda.synchronize()
+        R.enable_segment_timing(True)
+        for i in range(24):
+            seg_step(i)
+        torch.cuda.synchronize()
+        seg, _ = R.segment_ms()
+        R.enable_segment_timing(False)
     ms = D.max_over_ranks(ms, device="cuda")           # slowest rank
     value = world * N * K / (ms * 1e-3)
 
@@ -501,7 +521,11 @@ def run_ours(args):
         lv_rate = B / (lv_ms * 1e-3)
 
         # ---- rooflines from the live segment timings ----
-        nets_ms = seg["policy"] + (seg["critic+disc+locoval"] if "critic+disc+locoval" in seg else seg["critic"] + seg["disc"])
+        if merged_on:
+            nets_ms = seg["nets"]
+            seg["physics"] = seg["physics+record"]
+        else:
+            nets_ms = seg["policy"] + (seg["critic+disc+locoval"] if "critic+disc+locoval" in seg else seg["critic"] + seg["disc"])
         kern = {
             "physics": {"bound": "hbm", "ms": seg["physics"], "achieved": N * BYTES_PHYSICS / (seg["physics"] * 1e-3) / 1e9,
                         "peak": pk["hbm"], "unit": "GB/s",
@@ -522,7 +546,8 @@ def run_ours(args):
         if chain_on:
             kern["nets"]["traffic"] = NCU_TRAFFIC_NETS_CHAIN
         dom = max(("physics", "post_step", "nets"), key=lambda k: kern[k]["ms"])
-        names = {"nets": "tc::linear_chain_kernel (the 2 persistent tcgen05 launches of a step: policy pass, critic + discriminator pass)" if chain_on
+        names = {"nets": "tc::linear_chain_kernel (ONE persistent tcgen05 launch per step: policy pass of the step + critic / discriminator pass of the step before, 12 layers)" if merged_on
+                 else "tc::linear_chain_kernel (the 2 persistent tcgen05 launches of a step: policy pass, critic + discriminator pass)" if chain_on
                  else "tc::linear_bf16x3_kernel (the 12 tcgen05 dense-layer launches of a step)", "physics": "physics_soa_kernel",
                  "post_step": "post_step_kernel"}
         roof = dict(kern[dom]); roof.update(kernel=names[dom], traffic=kern[dom]["traffic"], peak_source=pk["src"],
@@ -552,7 +577,7 @@ def run_ours(args):
                        "env_reset": "on device: state reset + TrajGenerator.reset (--real_path pool of %d synthetic polylines, "
                                     "--adjust_root_vel, --init_heading) for the envs that finish, every step" % TRAJ_POOL,
                        "tensor_cores": bool(args.tensor_cores), "cuda_graphs": graphs, "parallel_branches": not args.serial,
-                       "layer_chain": chain_on},
+                       "layer_chain": chain_on, "merged_passes": merged_on},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                     "groups": args.e2e_groups, "numa_node": numa,
@@ -591,6 +616,7 @@ def main():
     ap.add_argument("--train-steps", type=int, default=16)
     ap.add_argument("--no-train", action="store_true", help="skip the train-step (update) measurement")
     ap.add_argument("--e2e-groups", type=int, default=2, help="env groups of the end-to-end (host buffer) pipeline")
+    ap.add_argument("--no-merge", action="store_true", help="two chain launches per step (policy pass; critic + discriminator pass) instead of one merged launch")
     ap.add_argument("--no-chain", action="store_true", help="one launch per dense layer instead of one persistent launch per network pass")
     ap.add_argument("--eager", action="store_true", help="launch every kernel from the host instead of replaying CUDA graphs")
     args = ap.parse_args()

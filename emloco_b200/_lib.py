@@ -54,7 +54,8 @@ class PostSinks(C.Structure):
                 ("task_hi", C.c_void_p), ("task_lo", C.c_void_p), ("ld_task", C.c_int64),
                 ("amp_mean", C.c_void_p), ("amp_inv_std", C.c_void_p),
                 ("amp_hi", C.c_void_p), ("amp_lo", C.c_void_p), ("ld_amp", C.c_int64),
-                ("rows_only", C.c_int32), ("reserved", C.c_int32)]
+                ("rows_only", C.c_int32), ("reserved", C.c_int32),
+                ("self_hi2", C.c_void_p), ("self_lo2", C.c_void_p), ("task_hi2", C.c_void_p), ("task_lo2", C.c_void_p)]
 
 
 class ChainLayer(C.Structure):

@@ -298,6 +298,8 @@ int emloco_set_post_sinks(emloco_sim* s, const emloco_post_sinks* k) {
         return fail(EMLOCO_EINVAL, "emloco_set_post_sinks: incomplete obs operand sink");
     if (k->amp_hi && (!k->amp_lo || !k->amp_mean || !k->amp_inv_std || (k->ld_amp & 7) || k->ld_amp < EML_AMP_OBS))
         return fail(EMLOCO_EINVAL, "emloco_set_post_sinks: incomplete AMP operand sink");
+    if (k->self_hi2 && (!k->self_hi || !k->self_lo2 || !k->task_hi2 || !k->task_lo2))
+        return fail(EMLOCO_EINVAL, "emloco_set_post_sinks: the second operand set needs the first and all four of its pointers");
     s->sinks = *k;
     return EMLOCO_OK;
 }

@@ -557,7 +557,7 @@ linear_bf16x3_2cta_kernel(const __grid_constant__ CUtensorMap map_ah, const __gr
 //     CTAs that are resident and never wait on higher tickets
 // Tile shape / pipeline = linear_bf16x3_kernel<128>; results are bit-identical to the per-layer launches.
 // =====================================================================================================================
-constexpr int CHAIN_MAX_LAYERS = 8, CHAIN_MAX_SEGS = 24, CHAIN_RING = 4;
+constexpr int CHAIN_MAX_LAYERS = 12, CHAIN_MAX_SEGS = 32, CHAIN_RING = 4;
 
 struct ChainLayer {
     GemmArgs g;
@@ -573,6 +573,7 @@ struct alignas(64) ChainParams {
     int seg_layer[CHAIN_MAX_SEGS], seg_first[CHAIN_MAX_SEGS], seg_end[CHAIN_MAX_SEGS];   // tickets [seg_end[i-1], seg_end[i])
     int n_segs, total, ws_ints;
     int* ws;          // [0] next ticket, [1] CTAs that have left, [2..) row-block counters; all zero between launches
+    int dbg;          // profiling experiments (EMLOCO_CHAIN_DBG): 1 = do not issue the output TMA stores, 2 = no staging either
     long long* trace; // optional (profiling): per ticket {cta, layer << 24 | tile, t claimed, t rows ready, t accumulator ready, t stored, t MMA thread free, t first k-block landed} (globaltimer ns)
 };
 
@@ -594,7 +595,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
 __device__ __forceinline__ float chain_epilogue_chunk(const uint32_t* r, const float* __restrict__ s_bias, const float* __restrict__ s_head,
                                                       int nb, int row, int row0, bool row_ok, const GemmArgs& g, uint8_t* stage,
                                                       uint32_t stage_u32, const CUtensorMap* map_yh, const CUtensorMap* map_yl,
-                                                      int lane, bool& stores_in_flight) {
+                                                      int lane, bool& stores_in_flight, int dbg = 0) {
     if (nb >= g.N) return 0.f;                                              // warp-uniform
     float v[32];
 #pragma unroll
@@ -620,7 +621,7 @@ __device__ __forceinline__ float chain_epilogue_chunk(const uint32_t* r, const f
             for (int j = 0; j < 32; ++j) if (nb + j < g.N) o[j] = v[j];
         }
     }
-    if (g.y_hi) {                                                           // warp-uniform
+    if (g.y_hi && dbg < 2) {                                                // warp-uniform
         uint32_t ph[16], pl[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
@@ -644,7 +645,7 @@ __device__ __forceinline__ float chain_epilogue_chunk(const uint32_t* r, const f
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic smem writes -> async-proxy (TMA) reads
         __syncwarp();
-        if (lane == 0) {
+        if (lane == 0 && dbg == 0) {
             tma_store_2d(map_yh, stage_u32, nb, row0);                      // rows / columns outside [M, N] are clipped by the unit
             tma_store_2d(map_yl, stage_u32 + 2048, nb, row0);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -868,11 +869,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) linear_chain_kernel(const __gr
             for (int c = 0; c < NC; c += 2) {
                 tmem_ld32(taddr + (c + 1) * 32, rb);
                 float hd = chain_epilogue_chunk(ra, sb + c * 32, sh + c * 32, n0 + c0 + c * 32, row, row0, row_ok, g, stage, stage_u32,
-                                                map_yh, map_yh + 1, lane, in_flight);
+                                                map_yh, map_yh + 1, lane, in_flight, P.dbg);
                 tmem_ld_wait(rb);
                 if (c + 2 < NC) tmem_ld32(taddr + (c + 2) * 32, ra);
                 hd += chain_epilogue_chunk(rb, sb + (c + 1) * 32, sh + (c + 1) * 32, n0 + c0 + (c + 1) * 32, row, row0, row_ok, g, stage,
-                                           stage_u32, map_yh, map_yh + 1, lane, in_flight);
+                                           stage_u32, map_yh, map_yh + 1, lane, in_flight, P.dbg);
                 if (c + 2 < NC) tmem_ld_wait(ra);
                 const int grp = (n0 + c0 + c * 32) >> 6;
                 if (g.head_part && row_ok && grp < g.head_ld) g.head_part[(long long)row * g.head_ld + grp] = hd;
@@ -1027,7 +1028,7 @@ static cudaError_t launch_chain(const emloco_chain_layer* layers, int n_layers, 
                                 long long ws_ints, cudaStream_t st, const char** why) {
     using T = Tile<128>;
     auto bad = [&](const char* m) { if (why) *why = m; return cudaErrorInvalidValue; };
-    if (!layers || n_layers <= 0 || n_layers > CHAIN_MAX_LAYERS) return bad("emloco_linear_chain: 1..8 layers");
+    if (!layers || n_layers <= 0 || n_layers > CHAIN_MAX_LAYERS) return bad("emloco_linear_chain: 1..12 layers");
     if (!ws) return bad("emloco_linear_chain: null workspace");
     static ChainParams P;                                   // (host calls are serialised by the Python GIL / one thread per sim)
     static std::mutex mu;
@@ -1068,10 +1069,11 @@ static cudaError_t launch_chain(const emloco_chain_layer* layers, int n_layers, 
     }
     if (ws_ints < off) return bad("emloco_linear_chain: workspace too small");
     P.ws = ws; P.ws_ints = off; P.trace = g_chain_trace;
+    { const char* e = getenv("EMLOCO_CHAIN_DBG"); P.dbg = e ? atoi(e) : 0; }
     // the ticket order: given segments, or the layers one after the other
     int seg[CHAIN_MAX_SEGS][3];
     if (order) {
-        if (n_segments <= 0 || n_segments > CHAIN_MAX_SEGS) return bad("emloco_linear_chain: 1..24 segments");
+        if (n_segments <= 0 || n_segments > CHAIN_MAX_SEGS) return bad("emloco_linear_chain: 1..32 segments");
         for (int i = 0; i < n_segments; ++i) for (int j = 0; j < 3; ++j) seg[i][j] = order[3 * i + j];
     } else {
         n_segments = n_layers;

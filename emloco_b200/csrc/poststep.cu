@@ -298,12 +298,21 @@ __global__ void __launch_bounds__(PS_THREADS) post_step_kernel(PostParams P) {
                 if (i2 < EML_OBS / 2) {
                     uint32_t hi, lo;
                     norm_split2(s_obs[i], s_obs[i + 1], m[k], is[k], hi, lo);
+                    const bool second = P.k.self_hi2 && !rmode;           // the next-observation copy is not touched by resets
                     if (i < EML_SELF_OBS) {
                         *reinterpret_cast<uint32_t*>(P.k.self_hi + (size_t)env * P.k.ld_self + i) = hi;
                         *reinterpret_cast<uint32_t*>(P.k.self_lo + (size_t)env * P.k.ld_self + i) = lo;
+                        if (second) {
+                            *reinterpret_cast<uint32_t*>(P.k.self_hi2 + (size_t)env * P.k.ld_self + i) = hi;
+                            *reinterpret_cast<uint32_t*>(P.k.self_lo2 + (size_t)env * P.k.ld_self + i) = lo;
+                        }
                     } else {
                         *reinterpret_cast<uint32_t*>(P.k.task_hi + (size_t)env * P.k.ld_task + (i - EML_SELF_OBS)) = hi;
                         *reinterpret_cast<uint32_t*>(P.k.task_lo + (size_t)env * P.k.ld_task + (i - EML_SELF_OBS)) = lo;
+                        if (second) {
+                            *reinterpret_cast<uint32_t*>(P.k.task_hi2 + (size_t)env * P.k.ld_task + (i - EML_SELF_OBS)) = hi;
+                            *reinterpret_cast<uint32_t*>(P.k.task_lo2 + (size_t)env * P.k.ld_task + (i - EML_SELF_OBS)) = lo;
+                        }
                     }
                 }
             }

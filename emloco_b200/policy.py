@@ -177,6 +177,8 @@ class RolloutNets:
             self._all = None
             self._cc = None
             self.w16 = _TcWeights()
+            self._q = None          # second operand / activation set of the critic(next obs) pass (merged launches), made on demand
+            self.value2 = f(M, 1)   # policy-pass value of odd steps (merged launches: step n-1's value is still needed during step n)
 
     def _w_ac1(self):
         """Actor and critic first layers stacked into one [2*h, 624] weight (buffers of fixed address, refreshed in place)."""
@@ -229,7 +231,18 @@ class RolloutNets:
             fp.append(self.w16.generation)
         return tuple(fp)
 
-    def post_sinks(self, obs_copy=None, amp_copy=None, slot=0, flip_copy=None, rows_only=False):
+    def next_obs_set(self):
+        """Second operand / activation set: emloco_post_step writes the normalised next observation into BOTH sets; resets patch only
+        the first, so `critic(next obs)` of step n can run after the reset of step n+1 - in the same launch as its policy pass."""
+        if self._q is None:
+            n, M, dev = self.net, self.M, self.mu.device
+            S = lambda k: _Split(M, k, dev)
+            t1, t2 = n._task_mlp[0].out_features, n._task_mlp[2].out_features
+            self._q = dict(tin=S(TASK_OBS), t1=S(t1), ain=S(SELF_OBS + t2), c1=S(n.critic_mlp[0].out_features),
+                           hp=torch.empty(M, (n.critic_mlp[2].out_features + 63) // 64, device=dev))
+        return self._q
+
+    def post_sinks(self, obs_copy=None, amp_copy=None, slot=0, flip_copy=None, rows_only=False, second=False):
         """emloco_post_sinks pointing at this object's operand buffers (tensor-core path) plus the given experience rows.
         rows_only: sim.flip_obs / sim.amp_obs are not refreshed, the experience rows are the only copies."""
         k = _lib.PostSinks()
@@ -245,6 +258,11 @@ class RolloutNets:
             k.amp_mean, k.amp_inv_std = am.data_ptr(), self.amp_norm.inv_std().data_ptr()
             sa = self.s_amp.rows_view(self.M, slot * self.M)
             k.amp_hi, k.amp_lo, k.ld_amp = sa.hi.data_ptr(), sa.lo.data_ptr(), sa.ld
+            if second:
+                q = self.next_obs_set()
+                assert q["ain"].ld == self.s_ain.ld and q["tin"].ld == self.s_tin.ld
+                k.self_hi2, k.self_lo2, k.task_hi2, k.task_lo2 = (q["ain"].hi.data_ptr(), q["ain"].lo.data_ptr(), q["tin"].hi.data_ptr(),
+                                                                  q["tin"].lo.data_ptr())
         return k
 
     def _lin(self, x, layer, relu, out, mean=None, var=None):
@@ -271,7 +289,7 @@ class RolloutNets:
         return mean, var
 
     def action_values(self, obs, noise, mu_out=None, task_value_out=None, actions_out=None, neglogp_out=None,
-                      operands_ready=False):
+                      operands_ready=False, value_out=None):
         """get_action_values (rl_games A2CBase; called at amp_continuous_value.py:53): mu, sigma(logstd), value (still in
         normalised units), task value, sampled action, neglogp.  obs [M,1422], noise [M,69] (standard normal).
         The *_out tensors let the heads write directly into the caller's experience rows."""
@@ -280,6 +298,8 @@ class RolloutNets:
         task_value_out = self.task_value if task_value_out is None else task_value_out
         actions_out = self.actions if actions_out is None else actions_out
         neglogp_out = self.neglogp if neglogp_out is None else neglogp_out
+        value_out = self.value if value_out is None else value_out
+        assert value_out is self.value or self.chain
         mean, var = self.obs_norm.f32()
         w, b = self._w_ac1()
         h = n.actor_mlp[0].out_features
@@ -326,14 +346,7 @@ class RolloutNets:
                 split_bf16(obs[:, :SELF_OBS], self.s_ain.cols(0, SELF_OBS), mean[:SELF_OBS], var[:SELF_OBS], eps)
                 split_bf16(obs[:, SELF_OBS:], self.s_tin, mean[SELF_OBS:], var[SELF_OBS:], eps)
             tm = (self.M + 127) // 128
-            L = [chain_layer(self.s_tin, W("t0", n._task_mlp[0].weight), n._task_mlp[0].bias.detach(), True, y16=self.s_t1),
-                 chain_layer(self.s_t1, W("t2", n._task_mlp[2].weight), n._task_mlp[2].bias.detach(), True, dep=0,
-                             y16=self.s_ain.cols(SELF_OBS, self.s_ain.K)),
-                 chain_layer(self.s_ain, W("ac1", w), b, True, dep=1, y16=self.s_ac1),
-                 chain_layer(self.s_ac1.cols(0, h), W("a2", n.actor_mlp[2].weight), n.actor_mlp[2].bias.detach(), True, dep=2, y16=self.s_a2),
-                 chain_layer(self.s_ac1.cols(h, 2 * h), W("c2", n.critic_mlp[2].weight), n.critic_mlp[2].bias.detach(), True, dep=2,
-                             head=(n.value, self.value, self.hp_c)),
-                 chain_layer(self.s_a2, W("mu", n.mu.weight), n.mu.bias.detach(), False, dep=3, y32=mu_out)]
+            L = self._policy_layers(mu_out, value_out)
             linear_chain(L, self.policy_order(tm, L), self._ws("policy", L))
             sample_actions(mu_out, n.sigma, noise, actions_out, neglogp_out)
 
@@ -349,7 +362,7 @@ class RolloutNets:
             self.fork.run(critic, actor, task_value)
         else:
             trunk_ac1(); actor(); critic(); task_value()
-        return dict(mus=mu_out, sigmas=n.sigma, values=self.value, task_values=task_value_out, actions=actions_out,
+        return dict(mus=mu_out, sigmas=n.sigma, values=value_out, task_values=task_value_out, actions=actions_out,
                     neglogpacs=neglogp_out)
 
     def critic(self, obs, operands_ready=False):
@@ -403,28 +416,89 @@ class RolloutNets:
         o += [(3, 0, t[3]), (5, 0, t[5])]
         return o
 
-    def critic_disc(self, obs, amp_obs, slot=0, operands_ready=False, logit_out=None):
+    def _policy_layers(self, mu_out, value_out, base=0):
+        n, W = self.net, self.w16.get
+        w, b = self._w_ac1()
+        h = n.actor_mlp[0].out_features
+        return [chain_layer(self.s_tin, W("t0", n._task_mlp[0].weight), n._task_mlp[0].bias.detach(), True, y16=self.s_t1),
+                chain_layer(self.s_t1, W("t2", n._task_mlp[2].weight), n._task_mlp[2].bias.detach(), True, dep=base,
+                            y16=self.s_ain.cols(SELF_OBS, self.s_ain.K)),
+                chain_layer(self.s_ain, W("ac1", w), b, True, dep=base + 1, y16=self.s_ac1),
+                chain_layer(self.s_ac1.cols(0, h), W("a2", n.actor_mlp[2].weight), n.actor_mlp[2].bias.detach(), True, dep=base + 2, y16=self.s_a2),
+                chain_layer(self.s_ac1.cols(h, 2 * h), W("c2", n.critic_mlp[2].weight), n.critic_mlp[2].bias.detach(), True, dep=base + 2,
+                            head=(n.value, value_out, self.hp_c)),
+                chain_layer(self.s_a2, W("mu", n.mu.weight), n.mu.bias.detach(), False, dep=base + 3, y32=mu_out)]
+
+    def _next_obs_layers(self, slot, logit_out, base=0, second=False):
+        """critic(next obs) + discriminator; second: operands / activations of the second set (next_obs_set)."""
+        n, W, M = self.net, self.w16.get, self.M
+        h = n.critic_mlp[0].out_features
+        if second:
+            q = self.next_obs_set()
+            tin, t1, ain, c1, hp = q["tin"], q["t1"], q["ain"], q["c1"], q["hp"]
+        else:
+            tin, t1, ain, c1, hp = self.s_tin, self.s_t1, self.s_ain, self.s_ac1.cols(h, 2 * h), self.hp_c
+        s_amp = self.s_amp.rows_view(M, slot * M)
+        return [chain_layer(tin, W("t0", n._task_mlp[0].weight), n._task_mlp[0].bias.detach(), True, y16=t1),
+                chain_layer(t1, W("t2", n._task_mlp[2].weight), n._task_mlp[2].bias.detach(), True, dep=base, y16=ain.cols(SELF_OBS, ain.K)),
+                chain_layer(ain, W("c0", n.critic_mlp[0].weight), n.critic_mlp[0].bias.detach(), True, dep=base + 1, y16=c1),
+                chain_layer(c1, W("c2", n.critic_mlp[2].weight), n.critic_mlp[2].bias.detach(), True, dep=base + 2,
+                            head=(n.value, self.next_value, hp)),
+                chain_layer(s_amp, W("d0", n._disc_mlp[0].weight), n._disc_mlp[0].bias.detach(), True, y16=self.s_d1),
+                chain_layer(self.s_d1, W("d2", n._disc_mlp[2].weight), n._disc_mlp[2].bias.detach(), True, dep=base + 4,
+                            head=(n._disc_logits, logit_out, self.hp_d))]
+
+    @staticmethod
+    def merged_order(tm, L):
+        """Ticket order of the merged launch, layers 0-5 = policy pass (t0 t2 ac1 a2 c2 mu), 6-11 = next-observation pass (t0 t2 c0 c2
+        d0 d2).  Long dependent chains first, the discriminator's long independent tiles as filler under the layer boundaries, the
+        short tiles (discriminator second layer, mu) last so that the launch ends evenly."""
+        t = [tiles_of(l) for l in L]
+        d_a = min(t[10], 2 * tm)
+        return [(0, 0, t[0]), (6, 0, t[6]), (1, 0, t[1]), (10, 0, d_a), (7, 0, t[7]), (2, 0, t[2]), (8, 0, t[8])] + \
+               ([(10, d_a, t[10] - d_a)] if t[10] > d_a else []) + [(3, 0, t[3]), (4, 0, t[4]), (9, 0, t[9]), (11, 0, t[11]), (5, 0, t[5])]
+
+    def merged_pass(self, noise, prev_slot, mu_out, value_out, actions_out, neglogp_out, task_value_out, obs, logit_out=None):
+        """get_action_values of step n AND `_eval_critic(next obs)` + `_eval_disc` of step n-1 in ONE launch (12 layers): the two
+        passes are independent given the two operand sets (next_obs_set), so the dependency bubbles of one are filled by the
+        other's tiles and there is one tail instead of two.  Outputs as action_values / critic_disc."""
+        n = self.net
+        assert self.chain
+        out = self.logit if logit_out is None else logit_out
+        mean, var = self.obs_norm.f32()
+
+        def chain_main():
+            L = self._policy_layers(mu_out, value_out) + self._next_obs_layers(prev_slot, out, base=6, second=True)
+            linear_chain(L, self.merged_order((self.M + 127) // 128, L), self._ws("merged", L))
+            sample_actions(mu_out, n.sigma, noise, actions_out, neglogp_out)
+
+        def task_value():
+            self._lin(obs[:, SELF_OBS:SELF_OBS + TRAJ_OBS], n._task_value_mlp[0], True, self.v1,
+                      mean[SELF_OBS:SELF_OBS + TRAJ_OBS], var[SELF_OBS:SELF_OBS + TRAJ_OBS])
+            self._lin(self.v1, n._task_value_mlp[2], True, self.v2)
+            self._lin(self.v2, n._value_logits, False, task_value_out)
+
+        if self.fork is not None:
+            self.fork.run(chain_main, task_value)
+        else:
+            chain_main(); task_value()
+        return dict(mus=mu_out, sigmas=n.sigma, values=value_out, task_values=task_value_out, actions=actions_out,
+                    neglogpacs=neglogp_out), self.next_value, out
+
+    def critic_disc(self, obs, amp_obs, slot=0, operands_ready=False, logit_out=None, second=False):
         """`_eval_critic(next obs)` (common_agent.py:647-655, before un-normalisation) and `_eval_disc`
         (amp_continuous.py:666-668) as ONE launch: -> (next_value [M,1], disc logit [M,1])."""
-        n, W, M = self.net, self.w16.get, self.M
+        n, M = self.net, self.M
         assert self.chain and amp_obs.shape[0] == M
         out = self.logit if logit_out is None else logit_out
-        s_amp = self.s_amp.rows_view(M, slot * M)
         if not operands_ready:
+            assert not second
+            s_amp = self.s_amp.rows_view(M, slot * M)
             mean, var = self.obs_norm.f32(); am, av = self.amp_norm.f32()
             split_bf16(obs[:, :SELF_OBS], self.s_ain.cols(0, SELF_OBS), mean[:SELF_OBS], var[:SELF_OBS], self.obs_norm.epsilon)
             split_bf16(obs[:, SELF_OBS:], self.s_tin, mean[SELF_OBS:], var[SELF_OBS:], self.obs_norm.epsilon)
             split_bf16(amp_obs, s_amp, am, av, self.amp_norm.epsilon)
-        h = n.critic_mlp[0].out_features
-        L = [chain_layer(self.s_tin, W("t0", n._task_mlp[0].weight), n._task_mlp[0].bias.detach(), True, y16=self.s_t1),
-             chain_layer(self.s_t1, W("t2", n._task_mlp[2].weight), n._task_mlp[2].bias.detach(), True, dep=0,
-                         y16=self.s_ain.cols(SELF_OBS, self.s_ain.K)),
-             chain_layer(self.s_ain, W("c0", n.critic_mlp[0].weight), n.critic_mlp[0].bias.detach(), True, dep=1, y16=self.s_ac1.cols(h, 2 * h)),
-             chain_layer(self.s_ac1.cols(h, 2 * h), W("c2", n.critic_mlp[2].weight), n.critic_mlp[2].bias.detach(), True, dep=2,
-                         head=(n.value, self.next_value, self.hp_c)),
-             chain_layer(s_amp, W("d0", n._disc_mlp[0].weight), n._disc_mlp[0].bias.detach(), True, y16=self.s_d1),
-             chain_layer(self.s_d1, W("d2", n._disc_mlp[2].weight), n._disc_mlp[2].bias.detach(), True, dep=4,
-                         head=(n._disc_logits, out, self.hp_d))]
+        L = self._next_obs_layers(slot, out, second=second)
         linear_chain(L, self.post_order((M + 127) // 128, L), self._ws("post", L))
         return self.next_value, out
 

@@ -34,7 +34,7 @@ class Rollout:
                  step_to_pred=144, normalize_value=True, net=None, obs_norm=None, amp_norm=None, value_norm=None,
                  recompute_disc=True, valuenet=None, fuse_sinks=True, concurrent=True, reuse_values=False, traj_flags=None,
                  traj_pool=None, traj_deferred=None, finetune=False, value_lr=1e-3,
-                 min_cum_rewards=-10.0, max_cum_rewards=100.0, sim_cfg=None, traj_cfg=None, rows_only=True, chain=None):
+                 min_cum_rewards=-10.0, max_cum_rewards=100.0, sim_cfg=None, traj_cfg=None, rows_only=True, chain=None, merged=None):
         self.N, self.T, self.device = int(num_envs), int(horizon), int(device)
         self.gamma, self.tau = gamma, tau
         self.task_reward_w, self.disc_reward_w, self.disc_reward_scale = task_reward_w, disc_reward_w, disc_reward_scale
@@ -111,6 +111,18 @@ class Rollout:
         self.cum_reward_range = (float(min_cum_rewards), float(max_cum_rewards))          # common_agent.py:154-155
         if self.finetune:
             self.valuenet.enable_finetune()
+        # merged (CUDA-graph steps only): `_eval_critic(next obs)` + `_calc_amp_rewards` + the bookkeeping of step n-1 run INSIDE
+        # step n - the two network passes become ONE 12-layer emloco_linear_chain launch after the reset (RolloutNets.merged_pass),
+        # the bookkeeping kernel runs beside the physics step; `finish` completes the last step.  Same numbers, bit for bit.
+        # Needs what the bench configuration has: the chain, operand sinks, the deferred trajectory reset (it is what clears the
+        # reset flags, after the snapshot the late bookkeeping reads) and no LocoVal fine-tuning inside the step.
+        can_merge = bool(self.chain and self.concurrent and self.fuse and self._traj_deferred and not self.finetune and not self.reuse_values)
+        self.merged = can_merge if merged is None else (bool(merged) and can_merge)
+        self._pending = None                  # step whose critic / discriminator / bookkeeping is still outstanding
+        if self.merged:
+            self._snap = torch.zeros(2, N, device=dev, dtype=torch.int64)          # reset / terminate flags of the outstanding step
+            self._snap_inv = torch.zeros(N, device=dev, dtype=torch.uint8)
+            self._side3 = Fork(dev, 2)
         self._marks = None
         self._graphs = {}
         self._cur = {}
@@ -143,8 +155,12 @@ class Rollout:
             self._graphs.clear()
             self._fingerprint = fp
 
+    MERGED_SEGMENTS = ("reset", "nets", "physics+record", "post_step")
+
     @property
     def SEGMENTS(self):
+        if getattr(self, "_seg_merged", False):
+            return self.MERGED_SEGMENTS
         if self.concurrent:
             return ("reset", "policy", "physics", "post_step", "critic+disc+locoval", "record")
         return ("reset", "policy", "physics", "post_step", "critic", "disc", "record")
@@ -171,7 +187,9 @@ class Rollout:
         return {s: v / max(steps, 1) for s, v in out.items()}, steps
 
     # ---- one control step: everything inside the `for n in range(horizon_length)` body, as seven segments ----
-    def _segment_fns(self, n, noise=None, host_obs=False):
+    def _segment_fns(self, n, noise=None, host_obs=False, merged=False):
+        if merged and self.merged and not host_obs:
+            return self._segment_fns_merged(n, noise)
         sim, nets, mb, cur = self.sim, self.nets, self.mb, self._cur
 
         fuse = self.fuse                                # post-step side: experience rows + operands of critic(next obs) / disc
@@ -224,7 +242,7 @@ class Rollout:
                 # rows_only: the mirrored observation and the AMP ring are written once, into the experience rows (the ring of
                 # the next step is shifted out of row n); sim.flip_obs / sim.amp_obs stay stale while the rollout runs fused
                 sim.set_post_sinks(nets.post_sinks(obs_copy=mb["obses"][nxt], amp_copy=mb["amp_obs"][n], slot=slot,
-                                                   flip_copy=mb["flip_obs"][n], rows_only=self.rows_only))
+                                                   flip_copy=mb["flip_obs"][n], rows_only=self.rows_only, second=self.merged))
                 sim.post_step(True)
             else:
                 sim.post_step(True)
@@ -302,19 +320,111 @@ class Rollout:
             return [seg_reset, seg_policy, seg_physics, seg_post, seg_nets2, seg_record_ft]
         return [seg_reset, seg_policy, seg_physics, seg_post, seg_critic, seg_disc, lambda: (seg_record_ft(), seg_locoval())]
 
-    def step(self, n, noise=None, host_obs=False):
-        """host_obs: the caller overwrote sim.obs (host-provided observations): operands are re-derived from it."""
+    def _record_args(self, k, value_raw, nv, logit, reset, terminate, inverted):
+        mb = self.mb
+        return (C.byref(self.rcfg), _ptr(self.sim.rew), _ptr(reset), _ptr(terminate), _ptr(value_raw), _ptr(nv), _ptr(logit),
+                None if inverted is None else _ptr(inverted), _ptr(mb["values"][k]), _ptr(mb["rewards"][k]), _ptr(mb["dones"][k]),
+                _ptr(mb["next_values"][k]), _ptr(mb["amp_rewards"][k]), _ptr(self.state), self.N, _stream())
+
+    def _value_buf(self, k):
+        return self.nets.value if k % 2 == 0 else self.nets.value2
+
+    def _segment_fns_merged(self, n, noise=None):
+        """Step n of the merged schedule (see __init__): reset -> ONE launch for get_action_values(n) and, when step n-1 is still
+        outstanding, its critic(next obs) + discriminator -> physics(n) beside the bookkeeping of n-1 -> post-step(n)."""
+        sim, nets, mb, cur, T = self.sim, self.nets, self.mb, self._cur, self.T
+        pend = self._pending
+        assert pend is None or pend == n - 1, "merged steps must be consecutive (flush() in between otherwise)"
+
+        def draw_noise():
+            cur["noise"] = self.noise.normal_(generator=self.gen) if noise is None else noise
+
+        def snapshot():          # the flags / inversion marks of step n-1, before the trajectory reset of step n clears / redraws them
+            torch.stack((sim.reset, sim.terminate), out=self._snap)
+            if self.inverted is not None:
+                self._snap_inv.copy_(self.inverted)
+
+        def reset_main():
+            if n == 0:
+                mb["obses"][0].copy_(mb["obses"][T])
+            sim.set_post_sinks(nets.post_sinks(obs_copy=mb["obses"][n]))           # patches the first operand set only
+            sim.reset_done(self.init_root, self.init_dof)
+
+        def seg_reset():
+            if pend is None:
+                self._side3.run(reset_main, draw_noise)
+            else:
+                self._side3.run(reset_main, draw_noise, snapshot)
+
+        def nets_main():
+            kw = dict(mu_out=mb["mus"][n], task_value_out=mb["task_values"][n], actions_out=mb["actions"][n], neglogp_out=mb["neglogpacs"][n],
+                      value_out=self._value_buf(n))
+            if pend is None:
+                cur["res"] = nets.action_values(sim.obs, cur["noise"], operands_ready=True, **kw)
+            else:
+                cur["res"], cur["nv"], cur["logit"] = nets.merged_pass(cur["noise"], pend, obs=sim.obs, **kw)
+
+        def seg_nets():
+            self._side.run(nets_main, sim.traj_reset)
+
+        def record_prev():
+            _lib.check(_lib.load().emloco_rollout_record(*self._record_args(
+                pend, self._value_buf(pend), cur["nv"], cur["logit"], self._snap[0], self._snap[1],
+                None if self.inverted is None else self._snap_inv)), "emloco_rollout_record")
+
+        def seg_physics():
+            if pend is None:
+                sim.physics_step(cur["res"]["actions"])
+            else:
+                self._side.run(lambda: sim.physics_step(cur["res"]["actions"]), record_prev)
+
+        def locoval():
+            self.locoval_scores = self.valuenet(self.waypoint_traj, self.init_pose, self.init_vel)
+
+        def post_main():
+            sim.set_post_sinks(nets.post_sinks(obs_copy=mb["obses"][n + 1], amp_copy=mb["amp_obs"][n], slot=n, flip_copy=mb["flip_obs"][n],
+                                               rows_only=self.rows_only, second=True))
+            sim.post_step(True)
+
+        def seg_post():
+            self._side.run(post_main, locoval)
+
+        return [seg_reset, seg_nets, seg_physics, seg_post]
+
+    def _flush_kernels(self):
+        """critic(next obs) + discriminator + bookkeeping of the outstanding step (nothing has been reset since its post-step, so
+        the flags are read in place)."""
+        k = self._pending
+        if k is None:
+            return
+        nv, logit = self.nets.critic_disc(None, self.mb["amp_obs"][k], slot=k, operands_ready=True, second=True)
+        _lib.check(_lib.load().emloco_rollout_record(*self._record_args(k, self._value_buf(k), nv, logit, self.sim.reset, self.sim.terminate,
+                                                                        self.inverted)), "emloco_rollout_record")
+
+    def flush(self):
+        """Completes the step the merged schedule left outstanding (its next values, AMP rewards, dones, bookkeeping rows)."""
+        self._flush_kernels()
+        self._pending = None
+
+    def step(self, n, noise=None, host_obs=False, merged=False):
+        """host_obs: the caller overwrote sim.obs (host-provided observations): operands are re-derived from it.
+        merged: use the merged schedule (the step's critic / discriminator / bookkeeping are left to the next step or to flush())."""
         if n == 0 and not torch.cuda.is_current_stream_capturing():
             self.sync_weights()
         self._warmed = True
-        for f in self._segment_fns(n, noise, host_obs):
+        merged = bool(merged) and self.merged and not host_obs
+        if not merged and self._pending is not None:
+            self.flush()
+        for f in self._segment_fns(n, noise, host_obs, merged):
             self._mark()
             f()
         self._mark()
+        self._pending = n if merged else None
 
     # ---- after the horizon: disc over the stored AMP obs, combine, GAE (:150-163) ----
     def finish(self):
         self._finish_warm = True
+        self.flush()
         mb, T, N = self.mb, self.T, self.N
         if self.recompute_disc:
             if getattr(self.nets, "amp_slots", 1) == T:
@@ -377,7 +487,15 @@ class Rollout:
         if not self._warmed:          # the very first step runs eagerly: one-time initialisations must not land in a capture
             self.step(n)
             return
-        self._replay(n, lambda: self.step(n))
+        if not self.merged:
+            self._replay(n, lambda: self.step(n))
+            return
+        # merged schedule: the graph of slot n also holds the outstanding part of step n-1 (none at the start of a horizon)
+        if self._pending is not None and self._pending != n - 1:
+            self.flush()
+        key = n if self._pending is not None or n == 0 else (n, "first")
+        self._replay(key, lambda: self.step(n, merged=True))
+        self._pending = n
 
     def step_graphed_host_noise(self, n, after_env_step=None):
         """step(n) on observations and policy noise the caller put into sim.obs / self.noise (no generator call in the graph).
@@ -400,17 +518,23 @@ class Rollout:
         fns = None
         if n == 0:
             self.sync_weights()
+        self._seg_merged = self.merged
+        if self._pending is not None and self._pending != n - 1:
+            self.flush()
+        pend = self._pending is not None
         for i, name in enumerate(self.SEGMENTS):
             self._mark()
-            if ("seg", n, i) not in self._graphs and fns is None:
-                fns = self._segment_fns(n)
-            self._replay(("seg", n, i), fns[i] if fns else None)
+            if ("seg", n, i, pend) not in self._graphs and fns is None:
+                fns = self._segment_fns(n, merged=self.merged)
+            self._replay(("seg", n, i, pend), fns[i] if fns else None)
         self._mark()
+        self._pending = n if self.merged else None
 
     def finish_graphed(self):
         if not getattr(self, "_finish_warm", False):      # first call eager: workspaces are allocated outside a capture
             return self.finish()
-        self._replay("finish", self.finish)
+        self._replay("finish" if (self._pending is not None or not self.merged) else ("finish", "flushed"), self.finish)
+        self._pending = None
         return self._finish_out
 
     def play_steps(self, graphed=False):

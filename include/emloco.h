@@ -160,6 +160,10 @@ typedef struct emloco_post_sinks {
      * its EMLOCO_T_AMP_OBS row after a reset) and shifts from there: that row must stay intact until the env's next
      * emloco_post_step. */
     int32_t   rows_only; int32_t reserved;
+    /* second destination of the self / task operands (same pitches), written by emloco_post_step ONLY - not by the post-step part
+     * of emloco_reset_done: the rows keep the observation that FOLLOWED the step (what `_eval_critic(next obs)` reads) while the
+     * reset patches the first set for the next policy pass.  Lets both passes run in one emloco_linear_chain launch.  May be NULL. */
+    uint16_t* self_hi2; uint16_t* self_lo2; uint16_t* task_hi2; uint16_t* task_lo2;
 } emloco_post_sinks;
 int emloco_set_post_sinks(emloco_sim* sim, const emloco_post_sinks* sinks /* NULL clears */);
 
@@ -383,7 +387,7 @@ int emloco_linear_bf16x3_head(const int32_t* d_rows, const uint16_t* a_hi, const
  *          the CTA that completes a row block adds the partial sums in column order.
  *   d_workspace: emloco_linear_chain_workspace_ints(...) int32 words, zero before the FIRST launch (the kernel leaves it zeroed);
  *          one workspace per chain that may be in flight.
- * At most 8 layers and 24 segments; all layers that are linked by `dep` have the same M. */
+ * At most 12 layers and 32 segments; all layers that are linked by `dep` have the same M. */
 typedef struct {
     const uint16_t* a_hi; const uint16_t* a_lo; int64_t lda;
     const uint16_t* w_hi; const uint16_t* w_lo; int64_t ldw;

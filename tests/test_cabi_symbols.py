@@ -100,6 +100,7 @@ int main(void) {
     printf("cfg.physics_impl %zu\\n", offsetof(emloco_cfg, physics_impl));
     printf("sinks.rows_only %zu\\n", offsetof(emloco_post_sinks, rows_only));
     printf("sinks.ld_amp %zu\\n", offsetof(emloco_post_sinks, ld_amp));
+    printf("sinks.task_lo2 %zu\\n", offsetof(emloco_post_sinks, task_lo2));
     printf("traj.seed %zu\\n", offsetof(emloco_traj_cfg, seed));
     printf("traj.num_waypoints %zu\\n", offsetof(emloco_traj_cfg, num_waypoints));
     return 0;
@@ -122,4 +123,5 @@ int main(void) {
     assert out["motion.num_motions"] == _lib.MotionLib.num_motions.offset
     assert out["cfg.max_effort"] == _lib.Cfg.max_effort.offset and out["cfg.physics_impl"] == _lib.Cfg.physics_impl.offset
     assert out["sinks.rows_only"] == _lib.PostSinks.rows_only.offset and out["sinks.ld_amp"] == _lib.PostSinks.ld_amp.offset
+    assert out["sinks.task_lo2"] == _lib.PostSinks.task_lo2.offset
     assert out["traj.seed"] == _lib.TrajCfg.seed.offset and out["traj.num_waypoints"] == _lib.TrajCfg.num_waypoints.offset

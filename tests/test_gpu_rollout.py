@@ -141,6 +141,51 @@ def test_play_steps_horizon_and_gae_consistency():
     R.close()
 
 
+def test_merged_schedule_is_bit_identical_to_the_step_by_step_schedule():
+    """The merged schedule of the graphed steps (ONE 12-layer launch for the policy pass of step n and the critic / discriminator
+    pass of step n-1, bookkeeping beside the physics step, `finish` completing the last step) against the eager step-by-step
+    schedule: every experience row, the post-horizon outputs and the simulator state are identical, bit for bit, over several
+    horizons with resets and trajectory regeneration."""
+    import bench
+    from emloco_b200.policy import AMPSeptValueNetwork
+    from emloco_b200.rollout import Rollout
+    from emloco_b200.synthetic import synthetic_traj_pool
+    n, T = 200, 6
+    torch.manual_seed(4)
+    net = AMPSeptValueNetwork()
+    pool = synthetic_traj_pool(64, 0)
+    kw = dict(seed=9, net=net, tensor_cores=True, horizon=T, traj_flags=bench.TRAJ_FLAGS, traj_pool=pool, sim_cfg=dict(episode_length=9))
+    A = Rollout(n, merged=False, **kw)
+    B = Rollout(n, **kw)
+    assert B.merged and not A.merged
+    for k in range(T):
+        A.step(k); B.step(k)            # eager warm-up on both (identical generators -> identical noise)
+    A.finish(); B.finish()
+    resets = 0
+    for rep in range(3):
+        for k in range(T):
+            A.step(k)
+            B.step_graphed(k)
+            resets += int(A.sim.reset.sum())
+        oa, ob = A.finish(), B.finish_graphed()
+        torch.cuda.synchronize()
+        for key in ("obses", "actions", "neglogpacs", "mus", "values", "task_values", "rewards", "task_rewards", "dones", "next_values",
+                    "amp_rewards", "amp_obs", "flip_obs", "returns", "advantages"):
+            np.testing.assert_array_equal(oa[key].cpu().numpy(), ob[key].cpu().numpy(), err_msg=f"{key} rep {rep}")
+        np.testing.assert_array_equal(A.state.cpu().numpy(), B.state.cpu().numpy())
+    assert resets > 0
+    np.testing.assert_array_equal(A.sim.rb_state.cpu().numpy(), B.sim.rb_state.cpu().numpy())
+    assert any(isinstance(k, int) for k in B._graphs) and B._pending is None
+    # flush() completes an outstanding step on demand
+    B.step_graphed(0); A.step(0)
+    assert B._pending == 0
+    B.flush()
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(A.mb["next_values"][0].cpu().numpy(), B.mb["next_values"][0].cpu().numpy())
+    np.testing.assert_array_equal(A.mb["amp_rewards"][0].cpu().numpy(), B.mb["amp_rewards"][0].cpu().numpy())
+    A.close(); B.close()
+
+
 def test_graphed_steps_equal_eager_steps():
     """CUDA-graph replay of a step must produce exactly what the eager launches produce (same kernels, same order)."""
     from emloco_b200.policy import AMPSeptValueNetwork
@@ -746,6 +791,21 @@ def test_benched_configuration_4096_envs_graphed_tensor_core_horizon_in_lockstep
         worst[key] = max(worst.get(key, 0.0), float(err.max()))
 
     f64 = lambda t: t.detach().cpu().numpy().astype(np.float64)
+    assert gpu.merged, "the bench configuration runs the merged schedule"
+
+    def check_bookkeeping(k, o, cpu_state):
+        """Rows the bookkeeping kernel of step k writes - with the merged schedule they are complete one step later (or after finish)."""
+        nonlocal mask_mismatch
+        mb = {key: gpu.mb[key][k][:n].cpu().numpy() for key in ("dones", "rewards", "next_values", "amp_rewards", "values")}
+        upd("values", mb["values"][:, 0], o["values"], 5e-5)
+        same = mb["dones"] == o["dones"]
+        mask_mismatch += int((~same).sum())
+        upd("rewards", mb["rewards"][same, 0], o["rewards"][same], 5e-3)
+        upd("next_values", mb["next_values"][same, 0], o["next_values"][same], 1e-4)
+        upd("amp_rewards", mb["amp_rewards"][:, 0], o["amp_rewards"], 1e-3)
+        upd("state", gpu.state[:, :n].cpu().numpy()[:, same], cpu_state[:, same], 3e-2)
+
+    prev = None
     for k in range(T):
         torch.cuda.synchronize()
         cpu.root = f64(sim.root_state).reshape(N, 13)[:n].copy()
@@ -757,35 +817,33 @@ def test_benched_configuration_4096_envs_graphed_tensor_core_horizon_in_lockstep
         cpu.amp_buf = ring[:n].cpu().numpy().reshape(n, 15, 206).copy()
         cpu.contact = f64(sim.contact).reshape(N, 24, 3)[:n].copy(); cpu.dof_force = f64(sim.dof_force).reshape(N, 69)[:n].copy()
         cpu.obs = (gpu.mb["obses"][T] if k == 0 else gpu.mb["obses"][k])[:n].cpu().numpy().copy()
-        cpu.state = gpu.state[:, :n].cpu().numpy().copy()
         cpu.verts = sim.traj_verts[:n].cpu().numpy().copy()          # reset envs still see their OLD polyline in the reset observation
         n_resets += int(cpu.reset.sum())
-        gpu.step_graphed(k)                                          # replay
+        gpu.step_graphed(k)                                          # replay: step k + the outstanding part of step k-1
         torch.cuda.synchronize()
+        if prev is not None:
+            check_bookkeeping(k - 1, *prev)
+        cpu.state = gpu.state[:, :n].cpu().numpy().copy()            # bookkeeping state after step k-1 = before step k
         noise = gpu.noise[:n].cpu().numpy().copy()
         cpu.reset_done()                                             # env_reset(done_indices) with the old polylines ...
         cpu.verts = sim.traj_verts[:n].cpu().numpy().copy()          # ... then _reset_task: the device's regenerated polylines (Philox
         cpu.inverted = gpu.inverted[:n].cpu().numpy().astype(bool)   #     draws; the generator itself is pinned by traj_reset_*.npz)
         n_inv += int(cpu.inverted.sum())
         o = cpu.step(noise)
-        mb = {key: v[k][:n].cpu().numpy() for key, v in gpu.mb.items() if v is not None}
+        prev = (o, cpu.state.copy())
+        mb = {key: gpu.mb[key][k][:n].cpu().numpy() for key in ("obses", "mus", "actions", "neglogpacs", "values", "task_values", "amp_obs")}
         upd("obs_in", mb["obses"][:, :398], o["obs"][:, :398], 5e-3)
         upd("mus", mb["mus"], o["mu"], 5e-5); upd("actions", mb["actions"], o["actions"], 5e-5)
         upd("neglogp", mb["neglogpacs"], o["neglogp"], 1e-3)
-        upd("values", mb["values"][:, 0], o["values"], 5e-5); upd("task_values", mb["task_values"], o["task_values"], 5e-5)
+        upd("task_values", mb["task_values"], o["task_values"], 5e-5)
         rb = sim.rb_state.view(N, 24, 13)[:n].cpu().numpy()
         upd("rb_pos", rb[..., 0:3], o["rb"][..., 0:3], 1e-3); upd("rb_rot", rb[..., 3:7], o["rb"][..., 3:7], 1e-3)
         upd("rb_vel", rb[..., 7:13], o["rb"][..., 7:13], 1e-2)
-        same = mb["dones"] == o["dones"]
-        mask_mismatch += int((~same).sum())
-        upd("rewards", mb["rewards"][same, 0], o["rewards"][same], 5e-3)
-        upd("next_values", mb["next_values"][same, 0], o["next_values"][same], 1e-4)
-        upd("amp_rewards", mb["amp_rewards"][:, 0], o["amp_rewards"], 1e-3)
         upd("self_obs", gpu.mb["obses"][k + 1][:n, :368].cpu().numpy(), o["next_obs"][:, :368], 5e-3)
         upd("amp_row", mb["amp_obs"][:, :206], o["amp_obs"][:, :206], 5e-3)
-        upd("state", gpu.state[:, :n].cpu().numpy()[:, same], cpu.state[:, same], 3e-2)
-    out = gpu.finish_graphed()                                        # replay of the post-horizon pass
+    out = gpu.finish_graphed()                                        # replay: the outstanding part of the last step + the post-horizon pass
     torch.cuda.synchronize()
+    check_bookkeeping(T - 1, *prev)
     assert all(gpu._graphs[k] is graphs_before[k] for k in graphs_before), "the checked horizon must be pure replay"
     g = {k: out[k][:, :n].cpu().numpy() for k in ("amp_obs", "task_rewards", "amp_rewards", "rewards", "dones", "values", "next_values",
                                                    "returns", "advantages")}
