@@ -22,6 +22,14 @@
 #define SOA_WARPS 12        // 12 x 166 registers x 32 lanes just fit the register file; the per-body phases run 2 bodies per warp
 #define SOA_BPW (EML_NB / SOA_WARPS)
 #define SOA_THREADS (SOA_WARPS * 32)
+// tree-pass loops (B1, B2, C): NOT unrolled - unrolling by two (168 registers) made the kernel 15 % slower (116 vs 100 us): the
+// compiler does not interleave consecutive bodies and the loop body outgrows the instruction cache
+#ifndef SOA_TREE_UNROLL_N
+#define SOA_TREE_UNROLL_N 1
+#endif
+#define SOA_PRAGMA_(x) _Pragma(#x)
+#define SOA_PRAGMA(x) SOA_PRAGMA_(x)
+#define SOA_TREE_UNROLL SOA_PRAGMA(unroll SOA_TREE_UNROLL_N)
 
 // floats per body in shared memory
 enum {
@@ -209,7 +217,7 @@ __device__ __forceinline__ void contact_force(float* smem, int lane, int b, f3 a
 
 // joint acceleration from the parent's, contact force, drive torque, joint integration (physics.cu pass 3 + integrate).
 // aw/al: in = parent's spatial acceleration, out = this body's.  The drive torque of the env's last live part goes to dof_force.
-__device__ __noinline__ void finish_body(float* smem, int lane, int b, f3& aw, f3& al, f3 v0, const SoaStep& st, float* dof_force_row) {
+__device__ __forceinline__ void finish_body(float* smem, int lane, int b, f3& aw, f3& al, f3 v0, const SoaStep& st, float* dof_force_row) {
     const f3 wdot = acc_body(smem, lane, b, aw, al);
     contact_force(smem, lane, b, aw, al, v0, st);
     const M3 R = quat_to_mat(ld4(smem, lane, b, F_QW));
@@ -441,7 +449,7 @@ __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams 
         Sp carry;
         if (chain < 5) {
             const int stop = chain == 2 ? 3 : 0;                       // spine warp: head, neck now; chest.. after the arms
-#pragma unroll 1
+SOA_TREE_UNROLL
             for (int i = clen - 1; i >= stop; --i) {
                 const int b = c_chain_body[chain][i];
                 Sp sp; ld_sp(smem, lane, b, sp);
@@ -455,7 +463,7 @@ __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams 
 
         // ================= B2 (spine warp): chest, spine, torso; pelvis and the 6x6 root solve; accelerations of torso..chest ==========
         if (chain == 2) {
-#pragma unroll 1
+SOA_TREE_UNROLL
             for (int b = 11; b >= 9; --b) {
                 Sp sp; ld_sp(smem, lane, b, sp);
                 add_sp(sp, carry);
@@ -505,7 +513,7 @@ __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams 
             }
             float wm = dot3(k.w, k.w);
             st3(smem, lane, 0, F_X, k.x); st4(smem, lane, 0, F_QW, k.q); st3(smem, lane, 0, F_VW, k.w); st3(smem, lane, 0, F_VL, k.l);
-#pragma unroll 1
+SOA_TREE_UNROLL
             for (int b = 9; b <= 11; ++b) {
                 finish_body(smem, lane, b, aw, al, v0, st, df_row);
                 f3 cw, cl;
@@ -533,7 +541,7 @@ __global__ void __launch_bounds__(SOA_THREADS, 1) physics_soa_kernel(PhysParams 
                 k.q = mk4(nr[96], nr[128], nr[160], nr[192]); k.x = mk3(0, 0, 0);
                 k.w = mk3(nr[320], nr[352], nr[384]); k.l = mk3(0, 0, 0);
             }
-#pragma unroll 1
+SOA_TREE_UNROLL
             for (int i = chain == 2 ? 3 : 0; i < clen; ++i) {
                 const int b = c_chain_body[chain][i];
                 finish_body(smem, lane, b, aw, al, v0, st, df_row);
