@@ -523,7 +523,7 @@ def run_ours(args):
         # ---- rooflines from the live segment timings ----
         if merged_on:
             nets_ms = seg["nets"]
-            seg["physics"] = seg["physics+record"]
+            seg["post_step"] = seg["post_step+record"]
         else:
             nets_ms = seg["policy"] + (seg["critic+disc+locoval"] if "critic+disc+locoval" in seg else seg["critic"] + seg["disc"])
         kern = {

@@ -113,7 +113,7 @@ class Rollout:
             self.valuenet.enable_finetune()
         # merged (CUDA-graph steps only): `_eval_critic(next obs)` + `_calc_amp_rewards` + the bookkeeping of step n-1 run INSIDE
         # step n - the two network passes become ONE 12-layer emloco_linear_chain launch after the reset (RolloutNets.merged_pass),
-        # the bookkeeping kernel runs beside the physics step; `finish` completes the last step.  Same numbers, bit for bit.
+        # the bookkeeping kernel (reading snapshots of flags / rewards) runs beside the next post-step; `finish` completes the last step.  Same numbers, bit for bit.
         # Needs what the bench configuration has: the chain, operand sinks, the deferred trajectory reset (it is what clears the
         # reset flags, after the snapshot the late bookkeeping reads) and no LocoVal fine-tuning inside the step.
         can_merge = bool(self.chain and self.concurrent and self.fuse and self._traj_deferred and not self.finetune and not self.reuse_values)
@@ -122,6 +122,7 @@ class Rollout:
         if self.merged:
             self._snap = torch.zeros(2, N, device=dev, dtype=torch.int64)          # reset / terminate flags of the outstanding step
             self._snap_inv = torch.zeros(N, device=dev, dtype=torch.uint8)
+            self._snap_rew = torch.zeros(N, device=dev, dtype=torch.float32)
             self._side3 = Fork(dev, 2)
         self._marks = None
         self._graphs = {}
@@ -155,7 +156,7 @@ class Rollout:
             self._graphs.clear()
             self._fingerprint = fp
 
-    MERGED_SEGMENTS = ("reset", "nets", "physics+record", "post_step")
+    MERGED_SEGMENTS = ("reset", "nets", "physics", "post_step+record")
 
     @property
     def SEGMENTS(self):
@@ -320,9 +321,9 @@ class Rollout:
             return [seg_reset, seg_policy, seg_physics, seg_post, seg_nets2, seg_record_ft]
         return [seg_reset, seg_policy, seg_physics, seg_post, seg_critic, seg_disc, lambda: (seg_record_ft(), seg_locoval())]
 
-    def _record_args(self, k, value_raw, nv, logit, reset, terminate, inverted):
+    def _record_args(self, k, value_raw, nv, logit, reset, terminate, inverted, rew=None):
         mb = self.mb
-        return (C.byref(self.rcfg), _ptr(self.sim.rew), _ptr(reset), _ptr(terminate), _ptr(value_raw), _ptr(nv), _ptr(logit),
+        return (C.byref(self.rcfg), _ptr(self.sim.rew if rew is None else rew), _ptr(reset), _ptr(terminate), _ptr(value_raw), _ptr(nv), _ptr(logit),
                 None if inverted is None else _ptr(inverted), _ptr(mb["values"][k]), _ptr(mb["rewards"][k]), _ptr(mb["dones"][k]),
                 _ptr(mb["next_values"][k]), _ptr(mb["amp_rewards"][k]), _ptr(self.state), self.N, _stream())
 
@@ -331,7 +332,7 @@ class Rollout:
 
     def _segment_fns_merged(self, n, noise=None):
         """Step n of the merged schedule (see __init__): reset -> ONE launch for get_action_values(n) and, when step n-1 is still
-        outstanding, its critic(next obs) + discriminator -> physics(n) beside the bookkeeping of n-1 -> post-step(n)."""
+        outstanding, its critic(next obs) + discriminator -> physics(n) -> post-step(n) beside the bookkeeping of n-1."""
         sim, nets, mb, cur, T = self.sim, self.nets, self.mb, self._cur, self.T
         pend = self._pending
         assert pend is None or pend == n - 1, "merged steps must be consecutive (flush() in between otherwise)"
@@ -341,6 +342,7 @@ class Rollout:
 
         def snapshot():          # the flags / inversion marks of step n-1, before the trajectory reset of step n clears / redraws them
             torch.stack((sim.reset, sim.terminate), out=self._snap)
+            self._snap_rew.copy_(sim.rew)
             if self.inverted is not None:
                 self._snap_inv.copy_(self.inverted)
 
@@ -370,13 +372,10 @@ class Rollout:
         def record_prev():
             _lib.check(_lib.load().emloco_rollout_record(*self._record_args(
                 pend, self._value_buf(pend), cur["nv"], cur["logit"], self._snap[0], self._snap[1],
-                None if self.inverted is None else self._snap_inv)), "emloco_rollout_record")
+                None if self.inverted is None else self._snap_inv, rew=self._snap_rew)), "emloco_rollout_record")
 
         def seg_physics():
-            if pend is None:
-                sim.physics_step(cur["res"]["actions"])
-            else:
-                self._side.run(lambda: sim.physics_step(cur["res"]["actions"]), record_prev)
+            sim.physics_step(cur["res"]["actions"])
 
         def locoval():
             self.locoval_scores = self.valuenet(self.waypoint_traj, self.init_pose, self.init_vel)
@@ -386,8 +385,11 @@ class Rollout:
                                                rows_only=self.rows_only, second=True))
             sim.post_step(True)
 
-        def seg_post():
-            self._side.run(post_main, locoval)
+        def seg_post():      # the bookkeeping of step n-1 (it reads snapshots) hides under the memory-bound post-step launch
+            if pend is None:
+                self._side3.run(post_main, locoval)
+            else:
+                self._side3.run(post_main, locoval, record_prev)
 
         return [seg_reset, seg_nets, seg_physics, seg_post]
 
