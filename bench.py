@@ -47,6 +47,10 @@ NCU_TRAFFIC = {"physics": 5.36e6, "post_step": 200.5e6, "nets": 363.7e6, "locova
 # with the layer chain: the two persistent launches of a step (profiles/r02r_full.md: policy pass 98.7 MB read + 82.6 MB written,
 # critic + discriminator pass 154.4 + 57.4 MB)
 NCU_TRAFFIC_NETS_CHAIN = 393.1e6
+# merged schedule (profiles/r02s_full.md): the ONE 12-layer launch of a step moves 306.0 MB + 164.4 MB; the post-step launch also
+# writes the second operand set (next-observation copy for the critic pass): 63.7 MB read + 160.4 MB written
+NCU_TRAFFIC_NETS_MERGED, NCU_TRAFFIC_POST_MERGED = 470.4e6, 224.1e6
+BYTES_POST_SECOND_SET = 1422 * 4      # bf16 hi + lo of the observation, second copy
 
 
 _OUT_FD = None
@@ -544,14 +548,21 @@ def run_ours(args):
             k["frac"] = k["achieved"] / k["peak"]
             k["traffic"] = NCU_TRAFFIC[name] if (name != "locoval" or B == 1 << 20) else None
         if chain_on:
-            kern["nets"]["traffic"] = NCU_TRAFFIC_NETS_CHAIN
+            kern["nets"]["traffic"] = NCU_TRAFFIC_NETS_MERGED if merged_on else NCU_TRAFFIC_NETS_CHAIN
+        if merged_on:
+            ps = kern["post_step"]
+            ps["traffic"] = NCU_TRAFFIC_POST_MERGED
+            ps["bytes_incl_sinks"] = BYTES_POST_WITH_SINKS + BYTES_POST_SECOND_SET
+            ps["achieved_incl_sinks"] = N * ps["bytes_incl_sinks"] / (seg["post_step"] * 1e-3) / 1e9
+            ps["frac_incl_sinks"] = ps["achieved_incl_sinks"] / pk["hbm"]
+            ps["note"] += "; merged schedule: the segment also holds the LocoVal scoring launch and the bookkeeping kernel of the previous step on side branches"
         dom = max(("physics", "post_step", "nets"), key=lambda k: kern[k]["ms"])
         names = {"nets": "tc::linear_chain_kernel (ONE persistent tcgen05 launch per step: policy pass of the step + critic / discriminator pass of the step before, 12 layers)" if merged_on
                  else "tc::linear_chain_kernel (the 2 persistent tcgen05 launches of a step: policy pass, critic + discriminator pass)" if chain_on
                  else "tc::linear_bf16x3_kernel (the 12 tcgen05 dense-layer launches of a step)", "physics": "physics_soa_kernel",
                  "post_step": "post_step_kernel"}
         roof = dict(kern[dom]); roof.update(kernel=names[dom], traffic=kern[dom]["traffic"], peak_source=pk["src"],
-                                            traffic_source="profiles/r02r_full.md (ncu --set full; per step for nets: both chain launches; per launch otherwise)" if chain_on
+                                            traffic_source=("profiles/r02s_full.md (ncu --set full; per launch)" if merged_on else "profiles/r02r_full.md (ncu --set full; per step for nets: both chain launches; per launch otherwise)") if chain_on
                                             else "profiles/r01g_full.md + gpurun r01g_prof.ncu-rep (ncu --set full; per step for nets, per launch otherwise)")
         if dom == "nets":
             roof["note"] = ("fp32 operands are carried as bf16 hi+lo and every k-step issues 3 MMAs (bf16x3, fp32-grade products): "
