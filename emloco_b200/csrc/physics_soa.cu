@@ -558,6 +558,15 @@ SOA_TREE_UNROLL
     }
 
     // ================= refresh: forward kinematics -> rigid-body state, DOF state, contact forces =================
+    // Lane = env means that a direct store of a body's 13 state floats is 32 scattered 4-byte writes per instruction (env rows are
+    // 1248 B apart): the refresh took ~20 % of the kernel.  The walk therefore leaves its results in shared memory - body b's 26
+    // output floats in the dead fields of b's own block, pitch 33 so that the transposed reads below are conflict free - and all
+    // 12 warps then copy each env's contiguous global rows (rb 312, contact 72, dof 138, joint quaternions 92, root 13 floats)
+    // with coalesced stores.  Same values, same arithmetic.
+    constexpr int ST_OFF = 7 * 32, ST_PITCH = 33;         // after F_JQ / F_JW (still read by the walk); k-th staged float of a body
+    constexpr int BLK = F_PER_BODY * 32;
+    static_assert(ST_OFF + 29 * ST_PITCH + 32 <= BLK, "staging fits the body block");
+#define STG(b, k) smem[(b) * BLK + ST_OFF + (k) * ST_PITCH + lane]
     if (chain < 5) {
         const float* root = smem + SOA_ROOT + rb * 13 * 32;
         const f3 p0 = mk3(root[lane], root[32 + lane], root[64 + lane]);
@@ -566,22 +575,16 @@ SOA_TREE_UNROLL
         const f3 w0 = mk3(root[10 * 32 + lane], root[11 * 32 + lane], root[12 * 32 + lane]);
         const float inv = P.n_sub > 0 ? 1.0f / (float)P.n_sub : 0.f;   // mean force over the sub-steps
         f4 qw = q0; f3 x = p0, wv = w0, lv = v0;
-        auto put_body = [&](int b) {
-            if (!env_ok) return;
-            float* o = P.rb + ((size_t)env * EML_NB + b) * 13;
-            o[0] = x.x; o[1] = x.y; o[2] = x.z; o[3] = qw.x; o[4] = qw.y; o[5] = qw.z; o[6] = qw.w;
-            o[7] = lv.x; o[8] = lv.y; o[9] = lv.z; o[10] = wv.x; o[11] = wv.y; o[12] = wv.z;
+        auto put_body = [&](int b) {                                   // k 0..12 rigid-body state, 13..15 contact force
+            STG(b, 0) = x.x; STG(b, 1) = x.y; STG(b, 2) = x.z; STG(b, 3) = qw.x; STG(b, 4) = qw.y; STG(b, 5) = qw.z; STG(b, 6) = qw.w;
+            STG(b, 7) = lv.x; STG(b, 8) = lv.y; STG(b, 9) = lv.z; STG(b, 10) = wv.x; STG(b, 11) = wv.y; STG(b, 12) = wv.z;
             const float* fs = smem + SOA_FSUM + b * 3 * 32 + lane;
-            float* c = P.contact + ((size_t)env * EML_NB + b) * 3;
-            c[0] = fs[0] * inv; c[1] = fs[32] * inv; c[2] = fs[64] * inv;
+            STG(b, 13) = fs[0] * inv; STG(b, 14) = fs[32] * inv; STG(b, 15) = fs[64] * inv;
         };
         if (chain == 2) {
-            put_body(0);
-            if (env_ok) {
-                float* r = P.root + (size_t)env * 13;
-                r[0] = p0.x; r[1] = p0.y; r[2] = p0.z; r[3] = q0.x; r[4] = q0.y; r[5] = q0.z; r[6] = q0.w;
-                r[7] = v0.x; r[8] = v0.y; r[9] = v0.z; r[10] = w0.x; r[11] = w0.y; r[12] = w0.z;
-            }
+            put_body(0);                                               // k 16..28 of body 0: the root state row
+            STG(0, 16) = p0.x; STG(0, 17) = p0.y; STG(0, 18) = p0.z; STG(0, 19) = q0.x; STG(0, 20) = q0.y; STG(0, 21) = q0.z; STG(0, 22) = q0.w;
+            STG(0, 23) = v0.x; STG(0, 24) = v0.y; STG(0, 25) = v0.z; STG(0, 26) = w0.x; STG(0, 27) = w0.y; STG(0, 28) = w0.z;
         }
         const int pre = chain >= 3 ? 3 : 0;
 #pragma unroll 1
@@ -595,15 +598,32 @@ SOA_TREE_UNROLL
             wv = wv + qrot(qw, jw);
             if (i < 0) continue;
             put_body(b);
-            if (env_ok) {
-                const int d = 3 * (b - 1);
-                const f3 e = log_quat(jq);
-                float2* ds = reinterpret_cast<float2*>(P.dof + ((size_t)env * EML_ND + d) * 2);
-                ds[0] = make_float2(e.x, jw.x); ds[1] = make_float2(e.y, jw.y); ds[2] = make_float2(e.z, jw.z);
-                *reinterpret_cast<float4*>(P.jq + ((size_t)env * EML_NJ + (b - 1)) * 4) = make_float4(jq.x, jq.y, jq.z, jq.w);
-            }
+            const f3 e = log_quat(jq);                                 // k 16..18 exp-map position, 19..21 rate, 22..25 joint quaternion
+            STG(b, 16) = e.x; STG(b, 17) = e.y; STG(b, 18) = e.z; STG(b, 19) = jw.x; STG(b, 20) = jw.y; STG(b, 21) = jw.z;
+            STG(b, 22) = jq.x; STG(b, 23) = jq.y; STG(b, 24) = jq.z; STG(b, 25) = jq.w;
         }
     }
+    __syncthreads();
+    {
+        const int env0 = blockIdx.x * P.epb;
+        for (int e = warp; e < P.epb && env0 + e < P.N; e += SOA_WARPS) {
+            const size_t g = (size_t)(env0 + e);
+            const float* st = smem + ST_OFF + e;                       // + body * BLK + k * ST_PITCH
+            float* o = P.rb + g * (EML_NB * 13);
+            for (int r = lane; r < EML_NB * 13; r += 32) { const int b = r / 13, k = r - b * 13; o[r] = st[b * BLK + k * ST_PITCH]; }
+            o = P.contact + g * (EML_NB * 3);
+            for (int r = lane; r < EML_NB * 3; r += 32) { const int b = r / 3, k = r - b * 3; o[r] = st[b * BLK + (13 + k) * ST_PITCH]; }
+            o = P.dof + g * (EML_ND * 2);
+            for (int r = lane; r < EML_ND * 2; r += 32) {              // (position, velocity) pairs of the 69 DOFs
+                const int d = r >> 1, b = d / 3 + 1, k = 16 + 3 * (r & 1) + (d - (b - 1) * 3);
+                o[r] = st[b * BLK + k * ST_PITCH];
+            }
+            o = P.jq + g * (EML_NJ * 4);
+            for (int r = lane; r < EML_NJ * 4; r += 32) { const int b = (r >> 2) + 1; o[r] = st[b * BLK + (22 + (r & 3)) * ST_PITCH]; }
+            if (lane < 13) P.root[g * 13 + lane] = st[(16 + lane) * ST_PITCH];
+        }
+    }
+#undef STG
 }
 
 const EmlModelDev* eml_model_dev();
