@@ -103,11 +103,17 @@ template <bool ENVM> struct ModelView {
     __device__ __forceinline__ float geom_bound(int b) const { return ENVM ? g(EM_BOUND, b) : Mo.geom_bound[b]; }
 };
 
+// trunc(x / 0.1f) without the IEEE division subroutine: same integer part as the fp32 quotient for every float in [0, 2^24)
+// (see div_by_tenth in poststep.cu and scripts/cu/div_by_tenth_check.cu); evaluated for every contact point of every sub-step
+__device__ __forceinline__ int cell_index(float x, int n) {
+    const float q0 = __fmul_rn(x, 10.0f);
+    const float q = __fmaf_rn(__fmaf_rn(-q0, 0.1f, x), 10.0f, q0);
+    const int i = __float2int_rz(fminf(fmaxf(q, -1.0f), (float)n));
+    return i < 0 ? 0 : (i > n - 1 ? n - 1 : i);
+}
 __device__ __forceinline__ float ground_height(const PhysParams& P, float x, float y) {
     if (!P.height) return 0.f;
-    long long px = (long long)(x / 0.1f), py = (long long)(y / 0.1f);
-    px = px < 0 ? 0 : (px > P.hf_rows - 1 ? P.hf_rows - 1 : px);
-    py = py < 0 ? 0 : (py > P.hf_cols - 1 ? P.hf_cols - 1 : py);
+    const int px = cell_index(x, P.hf_rows), py = cell_index(y, P.hf_cols);
     return (float)__ldg(P.height + px * P.hf_cols + py) * 0.005f;
 }
 
