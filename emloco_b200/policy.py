@@ -451,12 +451,12 @@ class RolloutNets:
     @staticmethod
     def merged_order(tm, L):
         """Ticket order of the merged launch, layers 0-5 = policy pass (t0 t2 ac1 a2 c2 mu), 6-11 = next-observation pass (t0 t2 c0 c2
-        d0 d2).  Long dependent chains first, the discriminator's long independent tiles as filler under the layer boundaries, the
-        short tiles (discriminator second layer, mu) last so that the launch ends evenly."""
+        d0 d2).  Both task MLPs, then the discriminator's long independent tiles (they fill the SMs while the dependent chains work through
+        their first layers), the wide first layers, the second layers, and the short tiles (discriminator second layer, mu) last so that
+        the launch ends evenly.  Measured on one box: 289 us against 292 (discriminator tiles split around the task MLPs), 291
+        (discriminator first) and 306 (policy pass, then next-observation pass)."""
         t = [tiles_of(l) for l in L]
-        d_a = min(t[10], 2 * tm)
-        return [(0, 0, t[0]), (6, 0, t[6]), (1, 0, t[1]), (10, 0, d_a), (7, 0, t[7]), (2, 0, t[2]), (8, 0, t[8])] + \
-               ([(10, d_a, t[10] - d_a)] if t[10] > d_a else []) + [(3, 0, t[3]), (4, 0, t[4]), (9, 0, t[9]), (11, 0, t[11]), (5, 0, t[5])]
+        return [(i, 0, t[i]) for i in (0, 6, 1, 7, 10, 2, 3, 8, 4, 9, 11, 5)]
 
     def merged_pass(self, noise, prev_slot, mu_out, value_out, actions_out, neglogp_out, task_value_out, obs, logit_out=None):
         """get_action_values of step n AND `_eval_critic(next obs)` + `_eval_disc` of step n-1 in ONE launch (12 layers): the two
