@@ -13,9 +13,11 @@ from .mjcf import HumanoidModel, default_model
 NB, ND = 24, 69
 
 
-def pd_action_offset_scale(limit_lo, limit_hi, names):
-    """_build_pd_action_offset_scale (humanoid.py:950-1025), bias_offset False, 3-dof joints."""
-    lo, hi = np.array(limit_lo, np.float64), np.array(limit_hi, np.float64)
+def pd_action_offset_scale(limit_lo, limit_hi, names, smpl_pd_offset=False):
+    """_build_pd_action_offset_scale (humanoid.py:950-1025), bias_offset False, 3-dof joints; float32 like the reference (Isaac Gym
+    reports the DOF limits as float32).  smpl_pd_offset: cfg env.has_smpl_pd_offset with has_upright_start (shoulder x offsets
+    -+pi/2, :1015-1018; default cfg: False).  Pinned to the reference function by tests/golden/pd_table.npz."""
+    lo, hi = np.array(limit_lo, np.float32), np.array(limit_hi, np.float32)
     for j in range(len(lo) // 3):
         s = slice(3 * j, 3 * j + 3)
         sc = max(np.max(np.abs(lo[s])), np.max(np.abs(hi[s])))
@@ -23,9 +25,12 @@ def pd_action_offset_scale(limit_lo, limit_hi, names):
         lo[s], hi[s] = -sc, sc
     offset = (0.5 * (hi + lo)).astype(np.float32)
     scale = (0.5 * (hi - lo)).astype(np.float32)
-    dof_names = names[1:]
+    dof_names = list(names[1:])
     scale[dof_names.index("L_Knee") * 3 + 1] = 5     # humanoid.py:1009-1013
     scale[dof_names.index("R_Knee") * 3 + 1] = 5
+    if smpl_pd_offset:
+        offset[dof_names.index("L_Shoulder") * 3] = -np.pi / 2
+        offset[dof_names.index("R_Shoulder") * 3] = np.pi / 2
     return offset, scale
 
 

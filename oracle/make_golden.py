@@ -826,8 +826,32 @@ def reference_plausibl(B=40, seed=41):
     return dict(x=x, y=y, **{f"w_{k}": v for k, v in sd.items()})
 
 
+def reference_pd_table():
+    """a2: the PD target offset / scale table.  The reference's own `Humanoid._build_pd_action_offset_scale` (humanoid.py:949-1025,
+    hosted by line range) on the joint ranges of the reference MJCF (what Isaac Gym reports as DOF limits), with the flags of
+    data/cfg/pacer.yaml (bias_offset False, has_upright_start True, has_smpl_pd_offset False) and with has_smpl_pd_offset True."""
+    import types
+    R = ref_extract.load()
+    torch = R.torch
+    from emloco_b200.mjcf import load_mjcf
+    mdl = load_mjcf(os.path.join(ref_extract.PACER, "data/assets/mjcf/smpl_humanoid.xml"))
+    out = dict(limit_lo=np.asarray(mdl.limit_lo, np.float64), limit_hi=np.asarray(mdl.limit_hi, np.float64), names=np.array(mdl.names))
+    for tag, smpl_off in (("", False), ("_smpl_offset", True)):
+        h = ref_extract.load_pd_block()()
+        h._dof_offsets = list(range(0, ND + 1, 3))
+        h.dof_limits_lower = torch.tensor(out["limit_lo"], dtype=torch.float32)
+        h.dof_limits_upper = torch.tensor(out["limit_hi"], dtype=torch.float32)
+        h._bias_offset, h.smpl_humanoid, h._has_smpl_pd_offset, h._has_upright_start, h.device = False, True, smpl_off, True, "cpu"
+        h._dof_names = list(mdl.names[1:])
+        h._build_pd_action_offset_scale()
+        out["offset" + tag] = h._pd_action_offset.numpy().copy()
+        out["scale" + tag] = h._pd_action_scale.numpy().copy()
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, "pd_table.npz"), **reference_pd_table())
     for name, fl in (("traj_reset_plain", 0), ("traj_reset_train", O.TRAJ_F_REAL | O.TRAJ_F_ADJUST_VEL | O.TRAJ_F_INIT_HEADING),
                      ("traj_reset_inv", O.TRAJ_F_REAL | O.TRAJ_F_INIT_HEADING | O.TRAJ_F_INVERSION | O.TRAJ_F_SLOW)):
         g = reference_traj_reset(24, 10, 11 + fl, fl)

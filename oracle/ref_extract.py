@@ -316,6 +316,25 @@ def load_motion_lib_block():
     return mod.Holder
 
 
+def load_pd_block():
+    """Humanoid._build_pd_action_offset_scale (env/tasks/humanoid.py:949-1025) as a method of a holder: the PD target offset / scale
+    table the actions are mapped with (a2).  The holder carries what the method reads: _dof_offsets, dof_limits_lower / _upper
+    (Isaac Gym's DOF properties = the MJCF joint ranges), _bias_offset, smpl_humanoid, _dof_names, _has_smpl_pd_offset,
+    _has_upright_start, device."""
+    if "pd" in _cache:
+        return _cache["pd"]
+    R = load()
+    hp = os.path.join(PACER, "env/tasks/humanoid.py")
+    src = "import numpy as np\nimport torch\nfrom isaacgym.torch_utils import to_torch\n\nclass Holder:\n" + _lines(hp, 949, 1025) + "\n"
+    tmp = tempfile.mkdtemp(prefix="emloco_ref_")
+    p = os.path.join(tmp, "emloco_ref_pd.py")
+    with open(p, "w") as f:
+        f.write(src)
+    mod = _import_path("emloco_ref_pd", p)
+    _cache["pd"] = mod.Holder
+    return mod.Holder
+
+
 def load_plausibl_mlp():
     """plausibl/test_value_mlp.py:24-113 `class MLP` (the script's imports point at a developer's home directory)."""
     if "plausibl" in _cache:
