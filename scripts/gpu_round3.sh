@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 (second half) GPU visit: all GPU tests + smoke, bench (both arms), ncu launch list and full captures exported to CSV on the
 # box (the .ncu-rep files are too large to travel back).  Usage: scripts/gpu_round3.sh [tag]
-TAG=${1:-r02t}
+TAG=${1:-r02u}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_gpu.txt 2>&1
 nproc >> gpurun_out/${TAG}_gpu.txt
