@@ -415,6 +415,7 @@ class Rollout:
             self.sync_weights()
         self._warmed = True
         merged = bool(merged) and self.merged and not host_obs
+        self._seg_merged = merged                 # SEGMENTS / segment_ms() name the schedule that ran last
         if not merged and self._pending is not None:
             self.flush()
         for f in self._segment_fns(n, noise, host_obs, merged):
