@@ -767,6 +767,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) linear_chain_kernel(const __gr
                 if (++slot == CHAIN_RING) { slot = 0; sphase ^= 1; }
                 if (info < 0) break;
                 const int num_kb = P.L[info >> 24].num_kb;
+                // k-steps of the last k-block that hold columns below K: the rest of the box is zero fill and adds nothing
+                const int last_steps = (P.L[info >> 24].g.K - (num_kb - 1) * BK + UMMA_K - 1) / UMMA_K;
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1);
                 tc_fence_after();
                 if (tr) tr[6] = gtimer();
@@ -779,8 +781,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) linear_chain_kernel(const __gr
                     const uint64_t d_ah = make_smem_desc<SW>(sa), d_al = make_smem_desc<SW>(sa + T::A_BYTES);
                     const uint64_t d_wh = make_smem_desc<SW>(sa + 2 * T::A_BYTES);
                     const uint64_t d_wl = make_smem_desc<SW>(sa + 2 * T::A_BYTES + T::B_BYTES);
+                    const int steps = kb == num_kb - 1 ? last_steps : BK / UMMA_K;
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
+                        if (k >= steps) break;
                         const uint64_t ko = (uint64_t)((k * UMMA_K * 2) >> 4);
                         umma_bf16(d_tmem, d_al + ko, d_wh + ko, idesc, (kb | k) != 0);      // same order as the per-layer kernel
                         umma_bf16(d_tmem, d_ah + ko, d_wl + ko, idesc, 1);
